@@ -1,0 +1,251 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (sg-slam_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'), ('response', '<f4'),
+                     ('octave', '<i4'), ('class_id', '<i4')])
+assert KP_DTYPE.itemsize == 28
+
+
+class OrbParams(C.Structure):
+    _fields_ = [('nfeatures', C.c_int32), ('scaleFactor', C.c_float), ('nlevels', C.c_int32),
+                ('iniThFAST', C.c_int32), ('minThFAST', C.c_int32)]
+
+
+class SgoFrame(C.Structure):
+    _fields_ = [('N', C.c_int32), ('keysUn', C.c_void_p), ('uRight', C.c_void_p), ('desc', C.c_void_p),
+                ('minX', C.c_float), ('minY', C.c_float), ('maxX', C.c_float), ('maxY', C.c_float),
+                ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float), ('bf', C.c_float),
+                ('nlevels', C.c_int32), ('scaleFactors', C.c_void_p), ('logScaleFactor', C.c_float)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, 'liboracle.so')
+    src = os.path.join(_HERE, 'sgs_oracle.cpp')
+    if force or not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+        subprocess.check_call(['make', '-C', _HERE, '-s', 'liboracle.so'])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.sgo_fast_atan2.restype = C.c_float
+        _LIB.sgo_fast_atan2.argtypes = [C.c_float, C.c_float]
+        _LIB.sgo_ic_angle.restype = C.c_float
+        _LIB.sgo_extract_dump.restype = C.c_void_p
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def params(nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7):
+    return OrbParams(nfeatures, scale, nlevels, ini, mn)
+
+
+def orb_tables(p):
+    n = p.nlevels
+    sc, isc, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+    npl = np.zeros(n, np.int32)
+    umax = np.zeros(16, np.int32)
+    lib().sgo_orb_tables(C.byref(p), _p(sc), _p(isc), _p(s2), _p(is2), _p(npl), _p(umax))
+    return dict(scale=sc, invScale=isc, sigma2=s2, invSigma2=is2, nPerLevel=npl, umax=umax)
+
+
+def level_size(p, w, h, level):
+    lw, lh = C.c_int32(), C.c_int32()
+    lib().sgo_level_size(C.byref(p), w, h, level, C.byref(lw), C.byref(lh))
+    return lw.value, lh.value
+
+
+def resize(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().sgo_resize(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def fast_view(view, threshold, nms=True):
+    """cv::FAST on a (possibly non-contiguous) 2-D uint8 view; returns int32 [n,3] (x, y, score)."""
+    assert view.dtype == np.uint8 and view.strides[1] == 1
+    h, w = view.shape
+    out = np.zeros((max(1, w * h), 3), np.int32)
+    n = lib().sgo_fast_view(C.c_void_p(view.ctypes.data), view.strides[0], w, h, threshold, int(nms), _p(out), out.shape[0])
+    assert n >= 0
+    return out[:n].copy()
+
+
+def fast_level(img, ini=20, mn=7):
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size // 4 + 16
+    out = np.zeros((cap, 3), np.float32)
+    nf = C.c_int32()
+    n = lib().sgo_fast_level(_p(img), img.shape[1], img.shape[0], img.strides[0], ini, mn, _p(out), cap, C.byref(nf))
+    assert n >= 0
+    return out[:n].copy(), nf.value
+
+
+def octree(cands, minX, maxX, minY, maxY, N):
+    cands = np.ascontiguousarray(cands, np.float32)
+    sel = np.zeros(N + 64 + len(cands), np.int32)
+    n = lib().sgo_octree(_p(cands), len(cands), minX, maxX, minY, maxY, N, _p(sel), len(sel))
+    assert n >= 0
+    return sel[:n].copy()
+
+
+def fast_atan2(y, x):
+    return lib().sgo_fast_atan2(float(y), float(x))
+
+
+def ic_angle(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    m01, m10 = C.c_int32(), C.c_int32()
+    a = lib().sgo_ic_angle(_p(img), img.shape[1], img.shape[0], img.strides[0], C.c_float(x), C.c_float(y), C.byref(m01), C.byref(m10))
+    return a, m01.value, m10.value
+
+
+def blur(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    lib().sgo_blur(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), out.strides[0])
+    return out
+
+
+def brief(blurred, x, y, angle):
+    blurred = np.ascontiguousarray(blurred, np.uint8)
+    d = np.zeros(32, np.uint8)
+    lib().sgo_brief(_p(blurred), blurred.shape[1], blurred.shape[0], blurred.strides[0], C.c_float(x), C.c_float(y), C.c_float(angle), _p(d))
+    return d
+
+
+def pattern_extent(angle):
+    return lib().sgo_pattern_extent(C.c_float(angle))
+
+
+def extract(img, p=None):
+    p = p or params()
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = p.nfeatures + 8 * p.nlevels + 64
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = lib().sgo_extract(C.byref(p), _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
+    assert n >= 0, n
+    return kps[:n].copy(), desc[:n].copy()
+
+
+class ExtractDump:
+    """Per-stage outputs of one oracle extraction (pyramid, candidates, blurred levels, final)."""
+
+    def __init__(self, img, p=None):
+        self.p = p or params()
+        img = np.ascontiguousarray(img, np.uint8)
+        L = lib()
+        h = C.c_void_p(L.sgo_extract_dump(C.byref(self.p), _p(img), img.shape[1], img.shape[0], img.strides[0]))
+        try:
+            n = L.sgo_dump_nkps(h)
+            self.kps = np.zeros(n, KP_DTYPE)
+            self.desc = np.zeros((n, 32), np.uint8)
+            if n:
+                L.sgo_dump_kps(h, _p(self.kps), _p(self.desc))
+            self.nfallback = L.sgo_dump_nfallback(h)
+            self.pyramid, self.blurred, self.cands = [], [], []
+            for lvl in range(self.p.nlevels):
+                for which, dst in ((0, self.pyramid), (1, self.blurred)):
+                    w, hh = C.c_int32(), C.c_int32()
+                    sz = L.sgo_dump_level(h, lvl, which, C.byref(w), C.byref(hh), None)
+                    if sz > 0:
+                        a = np.zeros((hh.value, w.value), np.uint8)
+                        L.sgo_dump_level(h, lvl, which, C.byref(w), C.byref(hh), _p(a))
+                        dst.append(a)
+                    else:
+                        dst.append(None)
+                nc = L.sgo_dump_cands(h, lvl, None, 0)
+                c = np.zeros((max(nc, 1), 3), np.float32)
+                L.sgo_dump_cands(h, lvl, _p(c), nc)
+                self.cands.append(c[:nc].copy())
+        finally:
+            L.sgo_dump_free(h)
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().sgo_hamming(_p(a), _p(b))
+
+
+def bf_match(q, t):
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    bi = np.zeros(len(q), np.int32); bd = np.zeros(len(q), np.int32); sd = np.zeros(len(q), np.int32)
+    lib().sgo_bf_match(_p(q), len(q), _p(t), len(t), _p(bi), _p(bd), _p(sd))
+    return bi, bd, sd
+
+
+class FrameArrays:
+    """Keeps the numpy arrays behind an SgoFrame alive."""
+
+    def __init__(self, keysUn, uRight, desc, w, h, fx, fy, cx, cy, bf, scaleFactors):
+        self.keysUn = np.ascontiguousarray(keysUn, KP_DTYPE)
+        self.uRight = np.ascontiguousarray(uRight, np.float32)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.scaleFactors = np.ascontiguousarray(scaleFactors, np.float32)
+        self.c = SgoFrame(len(self.keysUn), self.keysUn.ctypes.data, self.uRight.ctypes.data, self.desc.ctypes.data,
+                          0.0, 0.0, float(w), float(h), fx, fy, cx, cy, bf, len(self.scaleFactors),
+                          self.scaleFactors.ctypes.data, float(np.log(np.float32(self.scaleFactors[1]))) if len(self.scaleFactors) > 1 else 0.0)
+
+
+def features_in_area(fr, x, y, r, minLevel=-1, maxLevel=-1):
+    out = np.zeros(fr.c.N + 1, np.int32)
+    n = lib().sgo_features_in_area(C.byref(fr.c), C.c_float(x), C.c_float(y), C.c_float(r), minLevel, maxLevel, _p(out), len(out))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def search_by_projection_last(cur, Tcw_cur, Tcw_last, last_has_mp, last_xyz, last_desc, last_obs, last_octave,
+                              last_angle, th, mono=False, check_ori=True, cur_mp=None, cur_mp_obs=None):
+    n = len(last_has_mp)
+    Tc = np.ascontiguousarray(Tcw_cur, np.float32); Tl = np.ascontiguousarray(Tcw_last, np.float32)
+    has = np.ascontiguousarray(last_has_mp, np.uint8); xyz = np.ascontiguousarray(last_xyz, np.float32)
+    ld = np.ascontiguousarray(last_desc, np.uint8); lo = np.ascontiguousarray(last_obs, np.uint8)
+    loct = np.ascontiguousarray(last_octave, np.int32); la = np.ascontiguousarray(last_angle, np.float32)
+    mp = np.full(cur.c.N, -1, np.int32) if cur_mp is None else np.ascontiguousarray(cur_mp, np.int32).copy()
+    mpo = None if cur_mp_obs is None else np.ascontiguousarray(cur_mp_obs, np.uint8)
+    ncand = C.c_int64()
+    nm = lib().sgo_search_by_projection_last(C.byref(cur.c), _p(Tc), _p(Tl), n, _p(has), _p(xyz), _p(ld), _p(lo), _p(loct),
+                                             _p(la), C.c_float(th), int(mono), int(check_ori), _p(mp),
+                                             _p(mpo) if mpo is not None else None, C.byref(ncand))
+    return nm, mp, ncand.value
+
+
+def search_by_projection_local(fr, inview, projx, projy, projxr, level, viewcos, mp_desc, mp_obs, th, nnratio,
+                               f_mp, f_mp_obs, id_base=0):
+    n = len(inview)
+    a = [np.ascontiguousarray(inview, np.uint8), np.ascontiguousarray(projx, np.float32), np.ascontiguousarray(projy, np.float32),
+         np.ascontiguousarray(projxr, np.float32), np.ascontiguousarray(level, np.int32), np.ascontiguousarray(viewcos, np.float32),
+         np.ascontiguousarray(mp_desc, np.uint8), np.ascontiguousarray(mp_obs, np.uint8)]
+    mp = np.ascontiguousarray(f_mp, np.int32).copy(); mpo = np.ascontiguousarray(f_mp_obs, np.uint8).copy()
+    ncand = C.c_int64()
+    nm = lib().sgo_search_by_projection_local(C.byref(fr.c), n, *[_p(x) for x in a], C.c_float(th), C.c_float(nnratio), id_base,
+                                              _p(mp), _p(mpo), C.byref(ncand))
+    return nm, mp, mpo, ncand.value
+
+
+def dynreject(cur_xy, prev_xy, F, boxes, have_dyn, nfeatures):
+    cur = np.ascontiguousarray(cur_xy, np.float32); prev = np.ascontiguousarray(prev_xy, np.float32)
+    n = len(cur)
+    Fm = None if F is None else np.ascontiguousarray(F, np.float64).reshape(9)
+    bx = np.ascontiguousarray(boxes, np.float32).reshape(-1, 4) if boxes is not None and len(boxes) else np.zeros((0, 4), np.float32)
+    keep = np.zeros(n, np.uint8); dist = np.zeros(n, np.float64); rest = C.c_int32()
+    s = lib().sgo_dynreject(_p(cur), _p(prev), n, _p(Fm) if Fm is not None else None, _p(bx), len(bx), int(have_dyn), nfeatures,
+                            _p(keep), _p(dist), C.byref(rest))
+    return s, keep, dist, bool(rest.value)
