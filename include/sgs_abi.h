@@ -1,0 +1,250 @@
+/* =====================================================================================
+ * sgs_abi.h -- C ABI of libsgs_cuda.so: the B200-native (sm_100a) replacement for the
+ * SG-SLAM / ORB-SLAM2 per-frame tracking hot path.
+ *
+ * The reference has no FFI layer: the boundary is three C++ classes inside libsg-slam.so
+ * (ORB_SLAM2::ORBextractor, ORB_SLAM2::ORBmatcher, ORB_SLAM2::Frame).  Each entry point
+ * below names the reference interface it replaces (paths relative to
+ * /root/reference/src/sg-slam/).  the headers under include/sgslam/ hold the header-compatible C++
+ * mirror of those classes implemented on top of this ABI; INTEGRATION.md shows the
+ * reference-side binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / OpenCV / STL types
+ *   - every function returns an sgs_status (0 == SGS_OK); sgs_last_error() gives the
+ *     message of the calling thread's last failure
+ *   - "_device" variants take/return CUDA device pointers and enqueue on the given
+ *     cudaStream_t (passed as void*, NULL == the handle's own stream) without
+ *     synchronising; all other variants take HOST pointers and synchronise before return
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     SGS_ERR_CUDA
+ * ===================================================================================== */
+#ifndef SGS_ABI_H_
+#define SGS_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SGS_API __attribute__((visibility("default")))
+#else
+#define SGS_API
+#endif
+
+#define SGS_ABI_VERSION 1
+
+typedef enum sgs_status {
+    SGS_OK = 0,
+    SGS_ERR_INVALID = 1,     /* bad argument (NULL, size mismatch, unsupported geometry) */
+    SGS_ERR_CUDA = 2,        /* CUDA runtime failure or no device */
+    SGS_ERR_CAPACITY = 3,    /* caller-provided capacity too small; nothing was truncated silently */
+    SGS_ERR_UNSUPPORTED = 4  /* configuration outside what the reference itself supports */
+} sgs_status;
+
+/* ORBextractor constructor arguments, src/ORBextractor.cc:411-413 (TUM3.yaml:41-54). */
+typedef struct sgs_orb_params {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+} sgs_orb_params;
+
+/* Binary layout of cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct sgs_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} sgs_keypoint;
+
+typedef struct sgs_rect { float x, y, w, h; } sgs_rect; /* cv::Rect_<float> */
+
+SGS_API int sgs_abi_version(void);
+SGS_API const char* sgs_last_error(void);
+SGS_API int sgs_device_count(int* n);
+
+/* ------------------------------------------------------------------------------------
+ * ORBextractor  (include/ORBextractor.h:45-105, src/ORBextractor.cc)
+ * One handle = one extractor bound to an image geometry and a maximum batch size; device
+ * buffers (pyramids, candidate lists, results) are owned by the handle.
+ * ------------------------------------------------------------------------------------ */
+typedef struct sgs_extractor sgs_extractor;
+
+/* ORBextractor::ORBextractor (src/ORBextractor.cc:411-471) + buffer allocation for frames of width x height,
+ * up to max_batch frames per call, on CUDA device `device`. */
+SGS_API int sgs_extractor_create(const sgs_orb_params* params, int width, int height, int max_batch, int device,
+                                 sgs_extractor** out);
+SGS_API void sgs_extractor_destroy(sgs_extractor* ex);
+
+/* Getters: GetLevels/GetScaleFactors/GetInverseScaleFactors/GetScaleSigmaSquares/GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:62-85); any output pointer may be NULL.  Arrays have nlevels entries. */
+SGS_API int sgs_extractor_tables(const sgs_extractor* ex, float* scale, float* inv_scale, float* sigma2,
+                                 float* inv_sigma2, int32_t* features_per_level);
+/* Upper bound on keypoints per frame (nfeatures + 3 per level): size output buffers with it. */
+SGS_API int sgs_extractor_max_keypoints(const sgs_extractor* ex, int* cap);
+/* Level geometry of mvImagePyramid[level] (include/ORBextractor.h:87): width, height and device pitch. */
+SGS_API int sgs_extractor_level_info(const sgs_extractor* ex, int level, int* width, int* height, int* pitch);
+
+/* ORBextractor::operator() (src/ORBextractor.cc:1045-1106) on ONE host image (8-bit gray, `pitch` bytes/row).
+ * kps/desc are caller-allocated with room for `cap` keypoints (desc: cap x 32 bytes, row i belongs to kps[i]).
+ * An empty image (gray == NULL or w*h == 0) yields *n = 0 like the reference's early return (:1048). */
+SGS_API int sgs_extract(sgs_extractor* ex, const uint8_t* gray, int width, int height, int pitch, sgs_keypoint* kps,
+                        uint8_t* desc, int cap, int* n);
+
+/* Same, for `nframes` independent host images laid out `frame_stride` bytes apart.  kps: [nframes][cap],
+ * desc: [nframes][cap][32], n: [nframes].  Host<->device copies happen inside. */
+SGS_API int sgs_extract_batch(sgs_extractor* ex, const uint8_t* gray, int nframes, size_t frame_stride, int pitch,
+                              sgs_keypoint* kps, uint8_t* desc, int cap, int* n);
+
+/* Device-resident batch: d_gray is a DEVICE pointer ([nframes] images, frame_stride/pitch bytes); results stay on the
+ * device inside the handle (see sgs_extractor_results_device).  Asynchronous on `stream`. */
+SGS_API int sgs_extract_batch_device(sgs_extractor* ex, const uint8_t* d_gray, int nframes, size_t frame_stride,
+                                     int pitch, void* stream);
+/* Device pointers to the results of the last *_device call: kps [max_batch][cap], desc [max_batch][cap][32],
+ * counts [max_batch] (int32).  Valid until the next call on the handle. */
+SGS_API int sgs_extractor_results_device(const sgs_extractor* ex, const sgs_keypoint** d_kps, const uint8_t** d_desc,
+                                         const int32_t** d_counts, int* cap);
+
+/* Copies the results of the last call on the handle (device-resident or not) for frames [0,nframes) to host buffers
+ * kps [nframes][cap], desc [nframes][cap][32], n [nframes]; synchronises `stream` (NULL == the handle's stream). */
+SGS_API int sgs_extractor_fetch(sgs_extractor* ex, int nframes, sgs_keypoint* kps, uint8_t* desc, int cap, int* n, void* stream);
+
+/* Parity / debugging accessors (host copies of device intermediates of the LAST call, frame index `frame`). */
+SGS_API int sgs_extractor_read_level(sgs_extractor* ex, int frame, int level, int blurred, uint8_t* out, int out_pitch);
+/* FAST candidates of one level before the quadtree: packed as int32 triples (x, y, score) relative to (16,16),
+ * in unspecified order.  Returns SGS_ERR_CAPACITY (with *n = required) when cap is too small. */
+SGS_API int sgs_extractor_read_candidates(sgs_extractor* ex, int frame, int level, int32_t* xyscore, int cap, int* n);
+
+/* ------------------------------------------------------------------------------------
+ * ORBmatcher  (include/ORBmatcher.h:41-89, src/ORBmatcher.cc)
+ * ------------------------------------------------------------------------------------ */
+
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1649-1665) for n pairs of 32-byte descriptors (host). */
+SGS_API int sgs_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int32_t* dist, int device);
+
+/* Brute-force nearest / second-nearest train descriptor for every query descriptor (the inner loop shared by every
+ * ORBmatcher search, src/ORBmatcher.cc:93-113, over an unrestricted candidate set; first index wins ties).
+ * best_idx/best_dist/second_dist: [nq].  Host pointers. */
+SGS_API int sgs_hamming_bf(const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* best_idx,
+                           int32_t* best_dist, int32_t* second_dist, int device);
+/* Device-resident variant (all pointers are device pointers), asynchronous on `stream`.  d_scratch (int32 elements,
+ * size from sgs_hamming_bf_scratch_elems; may be NULL) lets small query sets split the train set over all SMs. */
+SGS_API int sgs_hamming_bf_scratch_elems(int nq, int nt, int64_t* elems);
+SGS_API int sgs_hamming_bf_device(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, int32_t* d_best_idx,
+                                  int32_t* d_best_dist, int32_t* d_second_dist, int32_t* d_scratch, void* stream);
+
+/* Flattened read-only view of a Frame as the matchers need it (src/Frame.cc:129-198): undistorted keypoints,
+ * mvuRight, descriptors, image bounds (mnMinX..), intrinsics and the extractor's scale factors. */
+typedef struct sgs_frame_view {
+    int32_t n;                  /* Frame::N */
+    const sgs_keypoint* keys_un;/* mvKeysUn */
+    const float* u_right;       /* mvuRight */
+    const uint8_t* desc;        /* mDescriptors, n x 32 */
+    float min_x, min_y, max_x, max_y; /* mnMinX.. (src/Frame.cc:686-714) */
+    float fx, fy, cx, cy, bf;   /* Frame::fx.., mbf */
+    int32_t nlevels;
+    const float* scale_factors; /* mvScaleFactors */
+} sgs_frame_view;
+
+/* ORBmatcher::SearchByProjection(Frame& Current, const Frame& Last, th, bMono) (src/ORBmatcher.cc:1332-1472).
+ * The LastFrame object graph is flattened by the caller:
+ *   last_has_mp[i]  LastFrame.mvpMapPoints[i] != NULL && !LastFrame.mvbOutlier[i]
+ *   last_xyz        pMP->GetWorldPos() (3 floats)      last_desc    pMP->GetDescriptor() (32 bytes)
+ *   last_obs[i]     pMP->Observations() > 0            last_octave  LastFrame.mvKeys[i].octave
+ *   last_angle      LastFrame.mvKeysUn[i].angle
+ * tcw_cur / tcw_last: 4x4 row-major float poses (Frame::mTcw).
+ * cur_mp_inout[j]: index i of the last-frame point assigned to CurrentFrame.mvpMapPoints[j], -1 for NULL; on entry it
+ * holds the caller's state (Tracking.cc:916 clears it), cur_mp_obs_in[j] (may be NULL == all 1) tells whether a
+ * pre-existing entry has Observations()>0.  *nmatches is the reference's return value.  Host pointers. */
+SGS_API int sgs_match_project_lastframe(const sgs_frame_view* cur, const float* tcw_cur, const float* tcw_last, int nlast,
+                                        const uint8_t* last_has_mp, const float* last_xyz, const uint8_t* last_desc,
+                                        const uint8_t* last_obs, const int32_t* last_octave, const float* last_angle,
+                                        float th, int mono, int check_orientation, int32_t* cur_mp_inout,
+                                        const uint8_t* cur_mp_obs_in, int* nmatches, int device);
+
+/* ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129) with the fields
+ * Frame::isInFrustum (src/Frame.cc:296-352) stores in each MapPoint passed as flat arrays:
+ *   mp_inview[i] (mbTrackInView && !isBad()), proj_x/proj_y/proj_xr (mTrackProjX/Y/XR), level (mnTrackScaleLevel),
+ *   view_cos (mTrackViewCos), mp_desc (GetDescriptor), mp_obs (Observations()>0).
+ * f_mp_inout[j] >= 0 means F.mvpMapPoints[j] is set (opaque id), f_mp_obs_inout[j] its Observations()>0 flag.  New
+ * matches store id_base + i.  nnratio is ORBmatcher::mfNNratio. */
+SGS_API int sgs_match_project_localmap(const sgs_frame_view* f, int nmp, const uint8_t* mp_inview, const float* proj_x,
+                                       const float* proj_y, const float* proj_xr, const int32_t* level,
+                                       const float* view_cos, const uint8_t* mp_desc, const uint8_t* mp_obs, float th,
+                                       float nnratio, int32_t id_base, int32_t* f_mp_inout, uint8_t* f_mp_obs_inout,
+                                       int* nmatches, int device);
+
+/* ---- batched, device-resident matchers (one CUDA block per independent frame / stream) --------------------------
+ * Per-frame arrays are laid out [nframes][cap]; every pointer is a DEVICE pointer.  The camera block carries the Frame
+ * statics (src/Frame.cc:176-196) and the extractor's scale factors. */
+typedef struct sgs_camera {
+    float min_x, min_y, max_x, max_y;
+    float fx, fy, cx, cy, bf;
+    int32_t nlevels;
+    float scale_factors[16];
+} sgs_camera;
+
+typedef struct sgs_matcher sgs_matcher;   /* owns the per-point scratch of the batched kernels */
+SGS_API int sgs_matcher_create(int device, int max_frames, int cur_cap, int point_cap, sgs_matcher** out);
+SGS_API void sgs_matcher_destroy(sgs_matcher* m);
+
+typedef struct sgs_lastframe_batch {      /* SearchByProjection(Frame&, const Frame&, th, bMono), src/ORBmatcher.cc:1332 */
+    sgs_camera cam;
+    const sgs_keypoint* cur_kps; const uint8_t* cur_desc; const float* cur_uright; const int32_t* cur_n; /* [F][cur_cap] / [F] */
+    const float* last_xyz;        /* [F][point_cap][3] */
+    const uint8_t* last_desc;     /* [F][point_cap][32] */
+    const uint8_t* last_flags;    /* bit0: map point present && !outlier, bit1: Observations()>0 */
+    const int32_t* last_octave; const float* last_angle; const int32_t* last_n;
+    const float* tcw_cur; const float* tcw_last;   /* [F][16] row-major */
+    float th; int32_t mono, check_orientation;
+    int32_t* cur_mp;              /* in/out [F][cur_cap]: index of the matched last-frame point or -1 */
+    const uint8_t* cur_mp_obs_in; /* may be NULL */
+    int32_t* nmatches;            /* out [F] */
+    uint64_t* ncand;              /* out [F] (accumulated): candidates examined, for the roofline byte count */
+} sgs_lastframe_batch;
+SGS_API int sgs_match_project_lastframe_batch_device(sgs_matcher* m, const sgs_lastframe_batch* args, int nframes, void* stream);
+
+typedef struct sgs_localmap_batch {       /* SearchByProjection(Frame&, vector<MapPoint*>&, th), src/ORBmatcher.cc:45 */
+    sgs_camera cam;
+    const sgs_keypoint* cur_kps; const uint8_t* cur_desc; const float* cur_uright; const int32_t* cur_n;
+    const uint8_t* mp_inview; const float* proj_x; const float* proj_y; const float* proj_xr; const int32_t* level;
+    const float* view_cos; const uint8_t* mp_desc; const uint8_t* mp_obs; const int32_t* mp_n;
+    float th, nnratio; int32_t id_base;
+    int32_t* f_mp; uint8_t* f_mp_obs; int32_t* nmatches; uint64_t* ncand;
+} sgs_localmap_batch;
+SGS_API int sgs_match_project_localmap_batch_device(sgs_matcher* m, const sgs_localmap_batch* args, int nframes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Frame: dynamic-feature rejection, geometry half
+ * Frame::RmDynamicPointWithSemanticAndGeometry "version3" loop (src/Frame.cc:560-604) +
+ * CheckEpiLineDistToRmDynamicPoint (:613-627) + isInDynamicRegion (:629-652).
+ *   cur_xy / prev_xy : mvKeys[i].pt and the LK-tracked previous point (2 floats each)
+ *   F                : 3x3 row-major double from findFundamentalMat (NULL == empty matrix: keep all, quirk Q11)
+ *   boxes            : mvPotentialDynamicBorderForRmDynamicFeature; have_dyn = mbHaveDynamicObjectForRmDynamicFeature
+ *   keep[i]          : 1 iff keypoint i passes its epipolar test; dist (may be NULL): the distances (double)
+ *   *nkeep           : Cur_keypoint_sum (the reference's return value)
+ *   *restored        : 1 when the restore-all branch fired (:599-602): the caller keeps every keypoint
+ * ------------------------------------------------------------------------------------ */
+SGS_API int sgs_dynreject(const float* cur_xy, const float* prev_xy, int n, const double* F, const sgs_rect* boxes,
+                          int nboxes, int have_dyn, int nfeatures, uint8_t* keep, double* dist, int* nkeep,
+                          int* restored, int device);
+
+/* Fused device-side variant used by the batched pipeline: computes the verdicts and applies them as an ORDERED compaction
+ * of keypoints and descriptor rows (the erase loop :563-597) for `nframes` frames resident on the device.
+ *   in : d_kps [F][cap], d_desc [F][cap][32], d_counts [F], d_prev_xy [F][cap][2], d_F [F][9] (double; a NaN in F[0] marks
+ *        an empty matrix), d_boxes [F][max_boxes], d_nboxes [F], d_have_dyn [F] (uint8)
+ *   out: d_kps_out / d_desc_out / d_counts_out (same shapes; when the restore-all branch fires the frame is copied
+ *        unchanged), d_keep [F][cap] (per-point verdicts, may be NULL) */
+SGS_API int sgs_dynreject_batch_device(const sgs_keypoint* d_kps, const uint8_t* d_desc, const int32_t* d_counts, int cap,
+                                       int nframes, const float* d_prev_xy, const double* d_F, const sgs_rect* d_boxes,
+                                       const int32_t* d_nboxes, int max_boxes, const uint8_t* d_have_dyn, int nfeatures,
+                                       sgs_keypoint* d_kps_out, uint8_t* d_desc_out, int32_t* d_counts_out, uint8_t* d_keep,
+                                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGS_ABI_H_ */

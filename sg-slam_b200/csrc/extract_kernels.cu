@@ -1,0 +1,464 @@
+// extract_kernels.cu -- hand-written sm_100a kernels of the batched ORB extractor.
+//
+// Stage            reference (src/ORBextractor.cc)                kernel
+//   pyramid        ComputePyramid :1108-1133 (cv::resize)          resize_level_kernel   (1 launch per level >= 1, all frames)
+//   FAST + NMS     ComputeKeyPointsOctTree :766-830 (cv::FAST)     fast_cells_kernel     (1 launch: all levels, all frames)
+//   distribution   DistributeOctTree :540-764                      quadtree_kernel       (1 launch: block per (level, frame))
+//   blur           GaussianBlur :1086-1087                         blur_level_kernel     (1 launch per level)
+//   orient + BRIEF IC_Angle :78-105, computeOrbDescriptor :109-148 describe_kernel       (1 launch: warp per keypoint)
+//
+// All integer stages are bit-exact by construction; float work uses explicitly rounded intrinsics (no FMA).
+#include <cuda_runtime.h>
+
+#include "extract_dev.cuh"
+#include "extract_kernels.h"
+
+namespace sgs {
+
+// 256 BRIEF point pairs (x0,y0,x1,y1) as int8; lane i of a warp reads its 32 bytes with two 128-bit loads
+__device__ __align__(16) const int8_t g_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+// --------------------------------------------------------------------------------------------------------------------
+// Pyramid: cv::resize(INTER_LINEAR) for CV_8UC1 in its 11-bit fixed-point form.  Each thread produces 4 consecutive
+// pixels of one output row (one 32-bit store); tables hold (src index, w0, w1) per output column / row.
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_level_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, int64_t sfstride,
+                                                           uint8_t* __restrict__ dst, int dw, int dh, int dpitch, int64_t dfstride,
+                                                           const short4* __restrict__ xtab, const short4* __restrict__ ytab) {
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x4 >= dw || y >= dh) return;
+    const uint8_t* S = src + (int64_t)blockIdx.z * sfstride;
+    uint8_t* D = dst + (int64_t)blockIdx.z * dfstride;
+    const short4 ty = __ldg(&ytab[y]);
+    const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1);
+    const int b0 = ty.y, b1 = ty.z;
+    const uint8_t* r0 = S + (int64_t)sy0 * spitch;
+    const uint8_t* r1 = S + (int64_t)sy1 * spitch;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x4 + i;
+        int v = 0;
+        if (x < dw) {
+            const short4 tx = __ldg(&xtab[x]);
+            const int sx0 = tx.x, sx1 = min(sx0 + 1, sw - 1);
+            const int a0 = tx.y, a1 = tx.z;
+            const int h0 = (int)__ldg(r0 + sx0) * a0 + (int)__ldg(r0 + sx1) * a1;
+            const int h1 = (int)__ldg(r1 + sx0) * a0 + (int)__ldg(r1 + sx1) * a1;
+            v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+        }
+        packed |= (uint32_t)v << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(D + (int64_t)y * dpitch + x4) = packed;  // dpitch is a multiple of 16: in-bounds
+}
+
+void launch_resize(const DevPlan& P, int level, cudaStream_t st) {
+    const DevLevel& s = P.lv[level - 1];
+    const DevLevel& d = P.lv[level];
+    dim3 block(32, 8), grid((d.w + 127) / 128, (d.h + 7) / 8, P.nframes);
+    resize_level_kernel<<<grid, block, 0, st>>>(s.img, s.w, s.h, s.pitch, s.fstride, d.img_w, d.w, d.h, d.pitch, d.fstride, d.xtab, d.ytab);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// FAST-9-16 + cell-local 3x3 NMS + per-cell threshold fallback.  One block per (cell, frame); a cell is one cv::FAST call
+// of the reference.  Facts used (proved against cv2 in tests/test_oracle_golden.py):
+//   * score(p) = max over the 16 contiguous 9-arcs of max(min d, -max d) - 1 with d_k = I(p) - I(ring_k);  p is a corner
+//     at threshold t  <=>  score(p) >= t; the reported response is that score whatever t was;
+//   * NMS keeps p iff score(p) > score(q) for its 8 neighbours q, pixels outside the cell interior counting as 0 -- the
+//     predicate is the same for both thresholds because neighbours below the threshold are below score(p) anyway;
+//   * the cell uses iniTh when that leaves at least one keypoint, otherwise minTh (:813-817).
+// Phases: (A) 4-point compass reject -> survivor list, (B) full 16-bit segment test -> corner list, (C) exact score,
+// (D) NMS + threshold choice + emission of packed candidates through one global atomic per cell.
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int kFastThreads = 256;
+constexpr int kTileMax = 66;     // w_cell <= 60 (n_cols = floor(width/30)) plus the 6-px overlap
+constexpr int kTilePitch = 72;
+
+__device__ __forceinline__ int fast_score_from_ring(int v, const int (&r)[16]) {
+    int d[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d[k] = v - r[k];
+    int mn2[16], mx2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
+    int mn4[16], mx4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
+    int best = -256;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+        best = max(best, max(mn9, -mx9));
+    }
+    return best - 1;
+}
+
+__device__ __forceinline__ bool has_arc9(uint32_t m) {
+    m |= m << 16;
+    uint32_t r = m & (m >> 1);
+    r &= r >> 2;   // runs of 4
+    r &= r >> 4;   // runs of 8
+    r &= m >> 8;   // runs of 9
+    return (r & 0xFFFFu) != 0;
+}
+
+__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ DevPlan P, const FastCell* __restrict__ cells) {
+    __shared__ __align__(16) uint8_t tile[kTileMax * kTilePitch];
+    __shared__ __align__(16) uint8_t score[(kTileMax + 2) * kTilePitch];  // +1 row above/below; columns x-1/x+1 stay inside the pitch
+    __shared__ uint16_t list_a[kTileMax * kTileMax];
+    __shared__ uint16_t list_b[kTileMax * kTileMax];
+    __shared__ int s_na, s_nb, s_nk, s_any_ini, s_base;
+
+    const FastCell c = cells[blockIdx.x];
+    const DevLevel& L = P.lv[c.level];
+    const int f = blockIdx.y;
+    const int w = c.x1 - c.x0, h = c.y1 - c.y0;
+    const uint8_t* img = L.img + (int64_t)f * L.fstride + (int64_t)c.y0 * L.pitch + c.x0;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_na = 0; s_nb = 0; s_nk = 0; s_any_ini = 0; }
+    for (int i = tid; i < (kTileMax + 2) * kTilePitch / 4; i += kFastThreads) reinterpret_cast<uint32_t*>(score)[i] = 0u;
+    for (int i = tid; i < w * h; i += kFastThreads) {
+        const int y = i / w, x = i - y * w;
+        tile[y * kTilePitch + x] = __ldg(img + (int64_t)y * L.pitch + x);
+    }
+    __syncthreads();
+    const int t_lo = min(P.ini_th, P.min_th);
+    const int iw = w - 6, ih = h - 6;
+    // (A) compass test: any 9-arc contains at least 2 of the ring pixels 0,4,8,12
+    for (int i0 = 0; i0 < iw * ih; i0 += kFastThreads) {
+        const int i = i0 + tid;
+        bool surv = false;
+        int pos = 0;
+        if (i < iw * ih) {
+            const int y = i / iw + 3, x = i - (i / iw) * iw + 3;
+            pos = y * kTilePitch + x;
+            const int v = tile[pos];
+            const int p0 = tile[pos + 3 * kTilePitch], p4 = tile[pos + 3], p8 = tile[pos - 3 * kTilePitch], p12 = tile[pos - 3];
+            const int hi = v + t_lo, lo = v - t_lo;
+            const int nb = (p0 > hi) + (p4 > hi) + (p8 > hi) + (p12 > hi);
+            const int nd = (p0 < lo) + (p4 < lo) + (p8 < lo) + (p12 < lo);
+            surv = (nb >= 2) | (nd >= 2);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, surv);
+        if (m) {
+            const int lane = tid & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_na, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (surv) list_a[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;
+        }
+    }
+    __syncthreads();
+    // (B) full segment test at the lower threshold
+    const int na = s_na;
+    for (int i0 = 0; i0 < na; i0 += kFastThreads) {
+        const int i = i0 + tid;
+        bool corner = false;
+        int pos = 0;
+        if (i < na) {
+            pos = list_a[i];
+            const uint8_t* p = tile + pos;
+            const int v = p[0];
+            const int hi = v + t_lo, lo = v - t_lo;
+            uint32_t mb = 0, md = 0;
+#define SGS_RING(k, dx, dy) { const int r = p[(dy) * kTilePitch + (dx)]; mb |= (uint32_t)(r > hi) << (k); md |= (uint32_t)(r < lo) << (k); }
+            SGS_RING(0, 0, 3) SGS_RING(1, 1, 3) SGS_RING(2, 2, 2) SGS_RING(3, 3, 1) SGS_RING(4, 3, 0) SGS_RING(5, 3, -1) SGS_RING(6, 2, -2) SGS_RING(7, 1, -3)
+            SGS_RING(8, 0, -3) SGS_RING(9, -1, -3) SGS_RING(10, -2, -2) SGS_RING(11, -3, -1) SGS_RING(12, -3, 0) SGS_RING(13, -3, 1) SGS_RING(14, -2, 2) SGS_RING(15, -1, 3)
+#undef SGS_RING
+            corner = has_arc9(mb) || has_arc9(md);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, corner);
+        if (m) {
+            const int lane = tid & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nb, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (corner) list_b[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;
+        }
+    }
+    __syncthreads();
+    // (C) exact score of every corner
+    const int nb = s_nb;
+    for (int i = tid; i < nb; i += kFastThreads) {
+        const int pos = list_b[i];
+        const uint8_t* p = tile + pos;
+        int r[16];
+        r[0] = p[3 * kTilePitch]; r[1] = p[3 * kTilePitch + 1]; r[2] = p[2 * kTilePitch + 2]; r[3] = p[kTilePitch + 3];
+        r[4] = p[3]; r[5] = p[-kTilePitch + 3]; r[6] = p[-2 * kTilePitch + 2]; r[7] = p[-3 * kTilePitch + 1];
+        r[8] = p[-3 * kTilePitch]; r[9] = p[-3 * kTilePitch - 1]; r[10] = p[-2 * kTilePitch - 2]; r[11] = p[-kTilePitch - 3];
+        r[12] = p[-3]; r[13] = p[kTilePitch - 3]; r[14] = p[2 * kTilePitch - 2]; r[15] = p[3 * kTilePitch - 1];
+        score[pos + kTilePitch] = (uint8_t)fast_score_from_ring(p[0], r);  // score map is shifted one row down
+    }
+    __syncthreads();
+    // (D) NMS (cell-local: the score map is zero outside the interior) and threshold choice
+    bool keep = false;  // valid for at most ceil(nb / threads) == handled in a loop below
+    for (int i0 = 0; i0 < nb; i0 += kFastThreads) {
+        const int i = i0 + tid;
+        keep = false;
+        int pos = 0, s = 0;
+        if (i < nb) {
+            pos = list_b[i];
+            const uint8_t* q = score + pos + kTilePitch;
+            s = q[0];
+            keep = s > q[-1] && s > q[1] && s > q[-kTilePitch - 1] && s > q[-kTilePitch] && s > q[-kTilePitch + 1] &&
+                   s > q[kTilePitch - 1] && s > q[kTilePitch] && s > q[kTilePitch + 1];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            const int lane = tid & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nk, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) {
+                list_a[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;  // list_a is free again: reuse for kept
+                if (s >= P.ini_th) s_any_ini = 1;
+            }
+        }
+    }
+    __syncthreads();
+    const int nk = s_nk;
+    const int thr = s_any_ini ? P.ini_th : P.min_th;
+    // count the emitted ones, reserve, write
+    int cnt = 0;
+    for (int i = tid; i < nk; i += kFastThreads) cnt += (score[list_a[i] + kTilePitch] >= thr) ? 1 : 0;
+    // block-wide sum via shared atomics (tiny)
+    if (tid == 0) s_na = 0;
+    __syncthreads();
+    if (cnt) atomicAdd(&s_na, cnt);
+    __syncthreads();
+    const int total = s_na;
+    if (total == 0) return;
+    if (tid == 0) {
+        s_base = atomicAdd(&P.cand_count[f * P.nlevels + c.level], total);
+        s_nb = 0;
+    }
+    __syncthreads();
+    const int base = s_base;
+    if (base + total > L.cand_cap) { if (tid == 0) atomicExch(P.error_flag, 1); return; }
+    uint32_t* out = L.cand + (int64_t)f * P.cand_fstride;
+    for (int i = tid; i < nk; i += kFastThreads) {
+        const int pos = list_a[i];
+        const int s = score[pos + kTilePitch];
+        if (s >= thr) {
+            const int y = pos / kTilePitch, x = pos - y * kTilePitch;
+            const int slot = atomicAdd(&s_nb, 1);
+            out[base + slot] = qt_pack(c.x0 + x - kMinBorder, c.y0 + y - kMinBorder, s);
+        }
+    }
+}
+
+void launch_fast(const DevPlan& P, const FastCell* d_cells, int ncells, cudaStream_t st) {
+    dim3 grid(ncells, P.nframes);
+    fast_cells_kernel<<<grid, kFastThreads, 0, st>>>(P, d_cells);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Quadtree distribution: one block per (level, frame) running qt_distribute (quadtree_core.h).
+// Shared memory: node-side arrays (sized for the largest level) + sort keys when they fit; otherwise the keys live in a
+// global scratch area (pathological candidate counts, e.g. pure-noise images).
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int kQtThreads = 256;
+
+struct CudaCtx {
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int nthreads() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
+__host__ __device__ inline size_t qt_node_bytes(int cap) {
+    // lo, hi, seq, free, list_a, list_b, exp_a, exp_b : 8 x int32 ; exp_key : u64 ; bnd : 3 x int32 ; child : 4 x int32 ; depth, flag : 2 x u8
+    return (size_t)cap * (8 * 4 + 8 + 3 * 4 + 4 * 4 + 2) + 64 + 16 * 4;
+}
+
+__global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const __grid_constant__ DevPlan P, int smem_key_cap, int node_cap, uint64_t* __restrict__ key_scratch,
+                                                              int64_t key_scratch_fstride, const int64_t* __restrict__ key_scratch_off) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int level = blockIdx.x, f = blockIdx.y;
+    const DevLevel& L = P.lv[level];
+    const int n = min(P.cand_count[f * P.nlevels + level], L.cand_cap);
+    int n_sort = 1;
+    while (n_sort < n) n_sort <<= 1;
+    QtWork w;
+    uint8_t* p = smem;
+    w.exp_key = reinterpret_cast<uint64_t*>(p); p += (size_t)node_cap * 8;
+    w.lo = reinterpret_cast<int32_t*>(p); p += (size_t)node_cap * 4;
+    w.hi = reinterpret_cast<int32_t*>(p); p += (size_t)node_cap * 4;
+    w.seq = reinterpret_cast<int32_t*>(p); p += (size_t)node_cap * 4;
+    w.free_list = reinterpret_cast<int32_t*>(p); p += (size_t)node_cap * 4;
+    w.list_a = reinterpret_cast<int32_t*>(p); p += (size_t)node_cap * 4;
+    w.list_b = reinterpret_cast<int32_t*>(p); p += (size_t)node_cap * 4;
+    w.exp_a = reinterpret_cast<int32_t*>(p); p += (size_t)node_cap * 4;
+    w.exp_b = reinterpret_cast<int32_t*>(p); p += (size_t)node_cap * 4;
+    w.bnd = reinterpret_cast<int32_t*>(p); p += (size_t)node_cap * 12;
+    w.child = reinterpret_cast<int32_t*>(p); p += (size_t)node_cap * 16;
+    w.sc = reinterpret_cast<int32_t*>(p); p += 16 * 4;
+    w.depth = p; p += node_cap;
+    w.flag = p; p += node_cap;
+    p = smem + ((p - smem + 15) & ~(size_t)15);
+    w.pool_cap = qt_pool_cap(L.qt.n_target, L.qt.n_ini);
+    w.n = n; w.n_sort = n_sort;
+    if (n_sort <= smem_key_cap) w.keys = reinterpret_cast<uint64_t*>(p);
+    else w.keys = key_scratch + (int64_t)f * key_scratch_fstride + key_scratch_off[level];
+    CudaCtx ctx;
+    uint32_t* out = P.kp_stage + (int64_t)f * P.kp_stage_per_frame + L.kp_off;
+    qt_distribute(ctx, L.cand + (int64_t)f * P.cand_fstride, L.qt, w, out, L.kp_cap, &P.kp_stage_n[f * P.nlevels + level]);
+}
+
+void launch_quadtree(const DevPlan& P, int smem_key_cap, int node_cap, size_t smem_bytes, uint64_t* key_scratch, int64_t key_scratch_fstride,
+                     const int64_t* d_key_scratch_off, cudaStream_t st) {
+    dim3 grid(P.nlevels, P.nframes);
+    quadtree_kernel<<<grid, kQtThreads, smem_bytes, st>>>(P, smem_key_cap, node_cap, key_scratch, key_scratch_fstride, d_key_scratch_off);
+}
+
+cudaError_t configure_quadtree_smem(size_t smem_bytes) {
+    return cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+
+size_t quadtree_node_bytes(int cap) { return qt_node_bytes(cap); }
+
+// --------------------------------------------------------------------------------------------------------------------
+// GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) in OpenCV's bit-exact 8.8 fixed point: taps {18,34,48,56,48,34,18}/256,
+// horizontal sums are exact 16-bit values, the vertical pass accumulates in 32 bits and rounds once: (v + 2^15) >> 16.
+// Block = 64 x 32 output tile; the (64+6) x (32+6) input tile is staged in shared memory with the reflected border.
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int kBlurTW = 64, kBlurTH = 32;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) blur_level_kernel(const uint8_t* __restrict__ src, int w, int h, int spitch, int64_t sfstride,
+                                                         uint8_t* __restrict__ dst, int dpitch, int64_t dfstride) {
+    __shared__ uint8_t in[(kBlurTH + 6) * (kBlurTW + 8)];
+    __shared__ uint16_t hs[(kBlurTH + 6) * kBlurTW];
+    const uint8_t* S = src + (int64_t)blockIdx.z * sfstride;
+    uint8_t* D = dst + (int64_t)blockIdx.z * dfstride;
+    const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
+        const int ty = i / (kBlurTW + 6), tx = i - ty * (kBlurTW + 6);
+        const int gx = reflect101(min(x0 + tx - 3, w + 2), w);   // columns past the image are never used for real outputs
+        const int gy = reflect101(min(y0 + ty - 3, h + 2), h);
+        in[ty * (kBlurTW + 8) + tx] = __ldg(S + (int64_t)gy * spitch + gx);
+    }
+    __syncthreads();
+    for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
+        const int ty = i / kBlurTW, tx = i - ty * kBlurTW;
+        const uint8_t* r = in + ty * (kBlurTW + 8) + tx;
+        const int v = 18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3];
+        hs[i] = (uint16_t)v;
+    }
+    __syncthreads();
+    for (int i = tid; i < kBlurTH * kBlurTW / 4; i += 256) {
+        const int ty = i / (kBlurTW / 4), tx4 = (i - ty * (kBlurTW / 4)) * 4;
+        const int gy = y0 + ty;
+        if (gy >= h || x0 + tx4 >= w) continue;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint16_t* c = hs + ty * kBlurTW + tx4 + k;
+            const uint32_t v = 18u * (c[0] + c[6 * kBlurTW]) + 34u * (c[kBlurTW] + c[5 * kBlurTW]) + 48u * (c[2 * kBlurTW] + c[4 * kBlurTW]) + 56u * c[3 * kBlurTW];
+            packed |= ((v + 32768u) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(D + (int64_t)gy * dpitch + x0 + tx4) = packed;  // pitch multiple of 16: in-bounds
+    }
+}
+
+void launch_blur(const DevPlan& P, int level, cudaStream_t st) {
+    const DevLevel& L = P.lv[level];
+    dim3 grid((L.w + kBlurTW - 1) / kBlurTW, (L.h + kBlurTH - 1) / kBlurTH, P.nframes);
+    blur_level_kernel<<<grid, 256, 0, st>>>(L.img, L.w, L.h, L.pitch, L.fstride, L.blur, L.bpitch, L.bfstride);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Orientation (intensity centroid over the 749-pixel disc) + rotated BRIEF, one warp per keypoint.
+//   lanes 0..30 own the patch rows dy = lane-15 for the moments; lane i owns descriptor byte i.
+//   cos/sin follow the contract of SURVEY Appendix A9: (float)cos((double)angle_rad).
+// Also writes the final cv::KeyPoint records (coordinates scaled to level 0, :1096-1102) and the per-frame count.
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ DevPlan P) {
+    const int f = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * 8 + warp;
+    // locate keypoint k of this frame: levels are concatenated 0..L-1 (:1076-1105)
+    int total = 0, level = -1, idx = 0;
+    for (int l = 0; l < P.nlevels; ++l) {
+        const int nl = min(P.kp_stage_n[f * P.nlevels + l], P.lv[l].kp_cap);
+        if (level < 0 && k < total + nl) { level = l; idx = k - total; }
+        total += nl;
+    }
+    if (k == 0 && lane == 0) {
+        P.out_count[f] = min(total, P.out_cap);
+        if (total > P.out_cap) atomicExch(P.error_flag, 2);
+    }
+    if (level < 0 || k >= P.out_cap) return;
+    const DevLevel& L = P.lv[level];
+    const uint32_t c = P.kp_stage[(int64_t)f * P.kp_stage_per_frame + L.kp_off + idx];
+    const int kx = qt_x(c) + kMinBorder, ky = qt_y(c) + kMinBorder;
+    // --- IC_Angle ---
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int dy = lane - 15;
+        const int d = P.umax[dy < 0 ? -dy : dy];
+        const uint8_t* row = L.img + (int64_t)f * L.fstride + (int64_t)(ky + dy) * L.pitch + kx;
+        int s = 0;
+        for (int u = -d; u <= d; ++u) {
+            const int v = __ldg(row + u);
+            m10 += u * v;
+            s += v;
+        }
+        m01 = dy * s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = dev_fast_atan2((float)m01, (float)m10);
+    // --- rotated BRIEF ---
+    const float factor_pi = (float)(3.14159265358979323846 / (double)180.f);
+    const float ang = __fmul_rn(angle, factor_pi);
+    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    const uint8_t* center = L.blur + (int64_t)f * L.bfstride + (int64_t)ky * L.bpitch + kx;
+    __align__(16) int8_t pat[32];
+    *reinterpret_cast<int4*>(pat) = __ldg(reinterpret_cast<const int4*>(g_pattern + lane * 32));
+    *reinterpret_cast<int4*>(pat + 16) = __ldg(reinterpret_cast<const int4*>(g_pattern + lane * 32 + 16));
+    int byte = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float x0 = (float)pat[4 * j], y0 = (float)pat[4 * j + 1], x1 = (float)pat[4 * j + 2], y1 = (float)pat[4 * j + 3];
+        const int r0 = dev_cv_round(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = dev_cv_round(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = dev_cv_round(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = dev_cv_round(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = __ldg(center + (int64_t)r0 * L.bpitch + c0);
+        const int t1 = __ldg(center + (int64_t)r1 * L.bpitch + c1);
+        byte |= (t0 < t1) << j;
+    }
+    P.out_desc[((int64_t)f * P.out_cap + k) * 32 + lane] = (uint8_t)byte;
+    if (lane == 0) {
+        sgs_keypoint kp;
+        kp.x = (level == 0) ? (float)kx : __fmul_rn((float)kx, L.scale);
+        kp.y = (level == 0) ? (float)ky : __fmul_rn((float)ky, L.scale);
+        kp.size = L.patch_size;
+        kp.angle = angle;
+        kp.response = (float)qt_score(c);
+        kp.octave = level;
+        kp.class_id = -1;
+        P.out_kps[(int64_t)f * P.out_cap + k] = kp;
+    }
+}
+
+void launch_describe(const DevPlan& P, cudaStream_t st) {
+    dim3 grid((P.out_cap + 7) / 8, P.nframes);
+    describe_kernel<<<grid, 256, 0, st>>>(P);
+}
+
+}  // namespace sgs

@@ -1,0 +1,200 @@
+// match_api.cu -- C-ABI entry points of the projection matchers: the batched device API (sgs_matcher handle) and the
+// single-frame host-pointer wrappers that flatten one Frame pair, run the same kernels with nframes = 1 and copy back.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <vector>
+
+#include "match_dev.cuh"
+
+using namespace sgs;
+
+struct sgs_matcher {
+    int device = 0, max_frames = 0, cur_cap = 0, point_cap = 0;
+    PointPre* d_pre = nullptr;
+    LocalPre* d_lpre = nullptr;
+    int32_t* d_events = nullptr;
+};
+
+namespace {
+
+int pow2_at_least(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+MatchCam to_cam(const sgs_camera& c) {
+    MatchCam m;
+    m.min_x = c.min_x; m.min_y = c.min_y; m.max_x = c.max_x; m.max_y = c.max_y;
+    m.fx = c.fx; m.fy = c.fy; m.cx = c.cx; m.cy = c.cy; m.bf = c.bf; m.nlevels = c.nlevels;
+    for (int i = 0; i < kMaxLevels; ++i) m.scale[i] = c.scale_factors[i];
+    return m;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    cudaError_t upload(const void* h, size_t bytes) {
+        cudaError_t e = alloc(bytes);
+        if (e != cudaSuccess || !bytes) return e;
+        return cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice);
+    }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+sgs_camera view_cam(const sgs_frame_view* v) {
+    sgs_camera c;
+    std::memset(&c, 0, sizeof c);
+    c.min_x = v->min_x; c.min_y = v->min_y; c.max_x = v->max_x; c.max_y = v->max_y;
+    c.fx = v->fx; c.fy = v->fy; c.cx = v->cx; c.cy = v->cy; c.bf = v->bf; c.nlevels = v->nlevels;
+    for (int i = 0; i < v->nlevels && i < kMaxLevels; ++i) c.scale_factors[i] = v->scale_factors[i];
+    return c;
+}
+
+}  // namespace
+
+extern "C" {
+
+SGS_API int sgs_matcher_create(int device, int max_frames, int cur_cap, int point_cap, sgs_matcher** out) {
+    if (!out || max_frames < 1 || cur_cap < 1 || point_cap < 1) { set_error("sgs_matcher_create: bad argument"); return SGS_ERR_INVALID; }
+    if (cur_cap > 8192) { set_error("sgs_matcher_create: cur_cap %d exceeds the 8192 keypoints per frame the shared-memory grid supports", cur_cap); return SGS_ERR_UNSUPPORTED; }
+    *out = nullptr;
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    sgs_matcher* m = new sgs_matcher();
+    m->device = device; m->max_frames = max_frames; m->cur_cap = cur_cap; m->point_cap = point_cap;
+    const size_t np = (size_t)max_frames * point_cap;
+    if (cudaMalloc(&m->d_pre, np * sizeof(PointPre)) != cudaSuccess || cudaMalloc(&m->d_lpre, np * sizeof(LocalPre)) != cudaSuccess ||
+        cudaMalloc(&m->d_events, np * sizeof(int32_t)) != cudaSuccess) {
+        set_error("sgs_matcher_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(m->d_pre); cudaFree(m->d_lpre); cudaFree(m->d_events); delete m;
+        return SGS_ERR_CUDA;
+    }
+    *out = m;
+    return SGS_OK;
+}
+
+SGS_API void sgs_matcher_destroy(sgs_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->d_pre); cudaFree(m->d_lpre); cudaFree(m->d_events);
+    delete m;
+}
+
+SGS_API int sgs_match_project_lastframe_batch_device(sgs_matcher* m, const sgs_lastframe_batch* a, int nframes, void* stream) {
+    if (!m || !a) { set_error("sgs_match_project_lastframe_batch_device: NULL"); return SGS_ERR_INVALID; }
+    if (nframes < 1 || nframes > m->max_frames) { set_error("nframes outside [1,max_frames]"); return SGS_ERR_INVALID; }
+    LastFrameArgs A;
+    A.cam = to_cam(a->cam);
+    A.cur_kps = a->cur_kps; A.cur_desc = a->cur_desc; A.cur_uright = a->cur_uright; A.cur_n = a->cur_n;
+    A.cur_cap = m->cur_cap; A.cur_cap_pow2 = pow2_at_least(m->cur_cap);
+    A.last_xyz = a->last_xyz; A.last_desc = a->last_desc; A.last_flags = a->last_flags; A.last_octave = a->last_octave;
+    A.last_angle = a->last_angle; A.last_n = a->last_n; A.last_cap = m->point_cap;
+    A.tcw_cur = a->tcw_cur; A.tcw_last = a->tcw_last; A.th = a->th; A.mono = a->mono; A.check_ori = a->check_orientation;
+    A.cur_mp = a->cur_mp; A.cur_mp_obs_in = a->cur_mp_obs_in; A.nmatches = a->nmatches; A.ncand = (unsigned long long*)a->ncand;
+    A.pre = m->d_pre; A.events = m->d_events;
+    return launch_match_lastframe(A, nframes, (cudaStream_t)stream);
+}
+
+SGS_API int sgs_match_project_localmap_batch_device(sgs_matcher* m, const sgs_localmap_batch* a, int nframes, void* stream) {
+    if (!m || !a) { set_error("sgs_match_project_localmap_batch_device: NULL"); return SGS_ERR_INVALID; }
+    if (nframes < 1 || nframes > m->max_frames) { set_error("nframes outside [1,max_frames]"); return SGS_ERR_INVALID; }
+    LocalMapArgs A;
+    A.cam = to_cam(a->cam);
+    A.cur_kps = a->cur_kps; A.cur_desc = a->cur_desc; A.cur_uright = a->cur_uright; A.cur_n = a->cur_n;
+    A.cur_cap = m->cur_cap; A.cur_cap_pow2 = pow2_at_least(m->cur_cap);
+    A.mp_inview = a->mp_inview; A.proj_x = a->proj_x; A.proj_y = a->proj_y; A.proj_xr = a->proj_xr; A.level = a->level;
+    A.view_cos = a->view_cos; A.mp_desc = a->mp_desc; A.mp_obs = a->mp_obs; A.mp_n = a->mp_n; A.mp_cap = m->point_cap;
+    A.th = a->th; A.nnratio = a->nnratio; A.id_base = a->id_base;
+    A.f_mp = a->f_mp; A.f_mp_obs = a->f_mp_obs; A.nmatches = a->nmatches; A.ncand = (unsigned long long*)a->ncand;
+    A.pre = m->d_lpre;
+    return launch_match_localmap(A, nframes, (cudaStream_t)stream);
+}
+
+SGS_API int sgs_match_project_lastframe(const sgs_frame_view* cur, const float* tcw_cur, const float* tcw_last, int nlast,
+                                        const uint8_t* last_has_mp, const float* last_xyz, const uint8_t* last_desc, const uint8_t* last_obs,
+                                        const int32_t* last_octave, const float* last_angle, float th, int mono, int check_orientation,
+                                        int32_t* cur_mp_inout, const uint8_t* cur_mp_obs_in, int* nmatches, int device) {
+    if (!cur || !tcw_cur || !tcw_last || !nmatches || nlast < 0 || cur->n < 0) { set_error("sgs_match_project_lastframe: bad argument"); return SGS_ERR_INVALID; }
+    *nmatches = 0;
+    if (nlast == 0 || cur->n == 0) return SGS_OK;
+    if (!last_has_mp || !last_xyz || !last_desc || !last_obs || !last_octave || !last_angle || !cur_mp_inout || !cur->keys_un || !cur->u_right || !cur->desc) {
+        set_error("sgs_match_project_lastframe: NULL array"); return SGS_ERR_INVALID;
+    }
+    sgs_matcher* m = nullptr;
+    int rc = sgs_matcher_create(device, 1, cur->n, nlast, &m);
+    if (rc != SGS_OK) return rc;
+    struct Guard { sgs_matcher* m; ~Guard() { sgs_matcher_destroy(m); } } guard{m};
+    const int n = cur->n;
+    std::vector<uint8_t> flags(nlast);
+    for (int i = 0; i < nlast; ++i) flags[i] = (uint8_t)((last_has_mp[i] ? 1 : 0) | (last_obs[i] ? 2 : 0));
+    DevBuf kps, desc, ur, cn, xyz, ld, lf, lo, la, ln, tc, tl, mp, mpo, nm, nc;
+    const int32_t n32 = n, nl32 = nlast;
+    SGS_CUDA_TRY(kps.upload(cur->keys_un, sizeof(sgs_keypoint) * n)); SGS_CUDA_TRY(desc.upload(cur->desc, (size_t)32 * n));
+    SGS_CUDA_TRY(ur.upload(cur->u_right, 4 * (size_t)n)); SGS_CUDA_TRY(cn.upload(&n32, 4));
+    SGS_CUDA_TRY(xyz.upload(last_xyz, 12 * (size_t)nlast)); SGS_CUDA_TRY(ld.upload(last_desc, 32 * (size_t)nlast));
+    SGS_CUDA_TRY(lf.upload(flags.data(), nlast)); SGS_CUDA_TRY(lo.upload(last_octave, 4 * (size_t)nlast));
+    SGS_CUDA_TRY(la.upload(last_angle, 4 * (size_t)nlast)); SGS_CUDA_TRY(ln.upload(&nl32, 4));
+    SGS_CUDA_TRY(tc.upload(tcw_cur, 64)); SGS_CUDA_TRY(tl.upload(tcw_last, 64));
+    SGS_CUDA_TRY(mp.upload(cur_mp_inout, 4 * (size_t)n));
+    if (cur_mp_obs_in) SGS_CUDA_TRY(mpo.upload(cur_mp_obs_in, n));
+    SGS_CUDA_TRY(nm.alloc(4)); SGS_CUDA_TRY(nc.alloc(8)); SGS_CUDA_TRY(cudaMemset(nc.p, 0, 8));
+    sgs_lastframe_batch b;
+    std::memset(&b, 0, sizeof b);
+    b.cam = view_cam(cur);
+    b.cur_kps = kps.as<sgs_keypoint>(); b.cur_desc = desc.as<uint8_t>(); b.cur_uright = ur.as<float>(); b.cur_n = cn.as<int32_t>();
+    b.last_xyz = xyz.as<float>(); b.last_desc = ld.as<uint8_t>(); b.last_flags = lf.as<uint8_t>(); b.last_octave = lo.as<int32_t>();
+    b.last_angle = la.as<float>(); b.last_n = ln.as<int32_t>(); b.tcw_cur = tc.as<float>(); b.tcw_last = tl.as<float>();
+    b.th = th; b.mono = mono; b.check_orientation = check_orientation;
+    b.cur_mp = mp.as<int32_t>(); b.cur_mp_obs_in = cur_mp_obs_in ? mpo.as<uint8_t>() : nullptr; b.nmatches = nm.as<int32_t>(); b.ncand = nc.as<uint64_t>();
+    rc = sgs_match_project_lastframe_batch_device(m, &b, 1, nullptr);
+    if (rc != SGS_OK) return rc;
+    SGS_CUDA_TRY(cudaDeviceSynchronize());
+    int32_t nm_h = 0;
+    SGS_CUDA_TRY(cudaMemcpy(&nm_h, nm.p, 4, cudaMemcpyDeviceToHost));
+    SGS_CUDA_TRY(cudaMemcpy(cur_mp_inout, mp.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    *nmatches = nm_h;
+    return SGS_OK;
+}
+
+SGS_API int sgs_match_project_localmap(const sgs_frame_view* f, int nmp, const uint8_t* mp_inview, const float* proj_x, const float* proj_y,
+                                       const float* proj_xr, const int32_t* level, const float* view_cos, const uint8_t* mp_desc,
+                                       const uint8_t* mp_obs, float th, float nnratio, int32_t id_base, int32_t* f_mp_inout,
+                                       uint8_t* f_mp_obs_inout, int* nmatches, int device) {
+    if (!f || !nmatches || nmp < 0 || f->n < 0) { set_error("sgs_match_project_localmap: bad argument"); return SGS_ERR_INVALID; }
+    *nmatches = 0;
+    if (nmp == 0 || f->n == 0) return SGS_OK;
+    if (!mp_inview || !proj_x || !proj_y || !proj_xr || !level || !view_cos || !mp_desc || !mp_obs || !f_mp_inout || !f_mp_obs_inout) {
+        set_error("sgs_match_project_localmap: NULL array"); return SGS_ERR_INVALID;
+    }
+    sgs_matcher* m = nullptr;
+    int rc = sgs_matcher_create(device, 1, f->n, nmp, &m);
+    if (rc != SGS_OK) return rc;
+    struct Guard { sgs_matcher* m; ~Guard() { sgs_matcher_destroy(m); } } guard{m};
+    const int n = f->n;
+    const int32_t n32 = n, nmp32 = nmp;
+    DevBuf kps, desc, ur, cn, iv, px, py, pxr, lv, vc, md, mo, mn, mp, mpo, nm, nc;
+    SGS_CUDA_TRY(kps.upload(f->keys_un, sizeof(sgs_keypoint) * n)); SGS_CUDA_TRY(desc.upload(f->desc, (size_t)32 * n));
+    SGS_CUDA_TRY(ur.upload(f->u_right, 4 * (size_t)n)); SGS_CUDA_TRY(cn.upload(&n32, 4));
+    SGS_CUDA_TRY(iv.upload(mp_inview, nmp)); SGS_CUDA_TRY(px.upload(proj_x, 4 * (size_t)nmp)); SGS_CUDA_TRY(py.upload(proj_y, 4 * (size_t)nmp));
+    SGS_CUDA_TRY(pxr.upload(proj_xr, 4 * (size_t)nmp)); SGS_CUDA_TRY(lv.upload(level, 4 * (size_t)nmp)); SGS_CUDA_TRY(vc.upload(view_cos, 4 * (size_t)nmp));
+    SGS_CUDA_TRY(md.upload(mp_desc, 32 * (size_t)nmp)); SGS_CUDA_TRY(mo.upload(mp_obs, nmp)); SGS_CUDA_TRY(mn.upload(&nmp32, 4));
+    SGS_CUDA_TRY(mp.upload(f_mp_inout, 4 * (size_t)n)); SGS_CUDA_TRY(mpo.upload(f_mp_obs_inout, n));
+    SGS_CUDA_TRY(nm.alloc(4)); SGS_CUDA_TRY(nc.alloc(8)); SGS_CUDA_TRY(cudaMemset(nc.p, 0, 8));
+    sgs_localmap_batch b;
+    std::memset(&b, 0, sizeof b);
+    b.cam = view_cam(f);
+    b.cur_kps = kps.as<sgs_keypoint>(); b.cur_desc = desc.as<uint8_t>(); b.cur_uright = ur.as<float>(); b.cur_n = cn.as<int32_t>();
+    b.mp_inview = iv.as<uint8_t>(); b.proj_x = px.as<float>(); b.proj_y = py.as<float>(); b.proj_xr = pxr.as<float>(); b.level = lv.as<int32_t>();
+    b.view_cos = vc.as<float>(); b.mp_desc = md.as<uint8_t>(); b.mp_obs = mo.as<uint8_t>(); b.mp_n = mn.as<int32_t>();
+    b.th = th; b.nnratio = nnratio; b.id_base = id_base;
+    b.f_mp = mp.as<int32_t>(); b.f_mp_obs = mpo.as<uint8_t>(); b.nmatches = nm.as<int32_t>(); b.ncand = nc.as<uint64_t>();
+    rc = sgs_match_project_localmap_batch_device(m, &b, 1, nullptr);
+    if (rc != SGS_OK) return rc;
+    SGS_CUDA_TRY(cudaDeviceSynchronize());
+    int32_t nm_h = 0;
+    SGS_CUDA_TRY(cudaMemcpy(&nm_h, nm.p, 4, cudaMemcpyDeviceToHost));
+    SGS_CUDA_TRY(cudaMemcpy(f_mp_inout, mp.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    SGS_CUDA_TRY(cudaMemcpy(f_mp_obs_inout, mpo.p, n, cudaMemcpyDeviceToHost));
+    *nmatches = nm_h;
+    return SGS_OK;
+}
+
+}  // extern "C"

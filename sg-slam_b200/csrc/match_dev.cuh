@@ -1,0 +1,56 @@
+// match_dev.cuh -- argument blocks of the batched projection matchers (match.cu).  All pointers are DEVICE pointers;
+// per-frame arrays are laid out [nframes][cap] with the given capacities.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "sgs_common.h"
+
+namespace sgs {
+
+struct MatchCam {                 // Frame statics (src/Frame.cc:176-196) + the extractor's scale factors
+    float min_x, min_y, max_x, max_y;
+    float fx, fy, cx, cy, bf;
+    int32_t nlevels;
+    float scale[kMaxLevels];
+};
+
+struct PointPre {                 // phase-2 result of one last-frame point
+    uint32_t best_key;            // dist << 16 | position in the sorted grid array; 0xFFFFFFFF = none
+    float u, v, invz, radius;
+    int16_t min_level, max_level;
+    int32_t valid;
+};
+
+struct LocalPre { uint32_t k1, k2; };
+
+struct LastFrameArgs {
+    MatchCam cam;
+    // current frames
+    const sgs_keypoint* cur_kps; const uint8_t* cur_desc; const float* cur_uright; const int32_t* cur_n;
+    int32_t cur_cap, cur_cap_pow2;
+    // last-frame map points
+    const float* last_xyz; const uint8_t* last_desc; const uint8_t* last_flags;  // bit0: has map point & !outlier, bit1: Observations()>0
+    const int32_t* last_octave; const float* last_angle; const int32_t* last_n; int32_t last_cap;
+    const float* tcw_cur; const float* tcw_last;   // [nframes][16]
+    float th; int32_t mono, check_ori;
+    // in/out
+    int32_t* cur_mp; const uint8_t* cur_mp_obs_in; int32_t* nmatches; unsigned long long* ncand;
+    // scratch [nframes][last_cap]
+    PointPre* pre; int32_t* events;
+};
+
+struct LocalMapArgs {
+    MatchCam cam;
+    const sgs_keypoint* cur_kps; const uint8_t* cur_desc; const float* cur_uright; const int32_t* cur_n;
+    int32_t cur_cap, cur_cap_pow2;
+    const uint8_t* mp_inview; const float* proj_x; const float* proj_y; const float* proj_xr; const int32_t* level;
+    const float* view_cos; const uint8_t* mp_desc; const uint8_t* mp_obs; const int32_t* mp_n; int32_t mp_cap;
+    float th, nnratio; int32_t id_base;
+    int32_t* f_mp; uint8_t* f_mp_obs; int32_t* nmatches; unsigned long long* ncand;
+    LocalPre* pre;
+};
+
+int launch_match_lastframe(const LastFrameArgs& A, int nframes, cudaStream_t st);
+int launch_match_localmap(const LocalMapArgs& A, int nframes, cudaStream_t st);
+
+}  // namespace sgs

@@ -1,0 +1,295 @@
+"""ctypes binding of libsgs_cuda.so (include/sgs_abi.h) for the Python-side harness (tests, bench).
+
+There is NO CPU fallback: loading fails loudly when the library has not been built, and every call fails with
+SGS_ERR_CUDA on a machine without a CUDA device."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_PKG, 'lib', 'libsgs_cuda.so')
+_LIB = None
+
+KP_DTYPE = np.dtype([('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'), ('response', '<f4'),
+                     ('octave', '<i4'), ('class_id', '<i4')])
+
+SGS_OK, SGS_ERR_INVALID, SGS_ERR_CUDA, SGS_ERR_CAPACITY, SGS_ERR_UNSUPPORTED = range(5)
+
+
+class SgsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('sgs status %d: %s' % (code, msg))
+        self.code = code
+
+
+class OrbParams(C.Structure):
+    _fields_ = [('nfeatures', C.c_int32), ('scale_factor', C.c_float), ('nlevels', C.c_int32),
+                ('ini_th_fast', C.c_int32), ('min_th_fast', C.c_int32)]
+
+
+class FrameView(C.Structure):
+    _fields_ = [('n', C.c_int32), ('keys_un', C.c_void_p), ('u_right', C.c_void_p), ('desc', C.c_void_p),
+                ('min_x', C.c_float), ('min_y', C.c_float), ('max_x', C.c_float), ('max_y', C.c_float),
+                ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float), ('bf', C.c_float),
+                ('nlevels', C.c_int32), ('scale_factors', C.c_void_p)]
+
+
+class Camera(C.Structure):
+    _fields_ = [('min_x', C.c_float), ('min_y', C.c_float), ('max_x', C.c_float), ('max_y', C.c_float),
+                ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float), ('bf', C.c_float),
+                ('nlevels', C.c_int32), ('scale_factors', C.c_float * 16)]
+
+
+class LastFrameBatch(C.Structure):
+    _fields_ = [('cam', Camera),
+                ('cur_kps', C.c_void_p), ('cur_desc', C.c_void_p), ('cur_uright', C.c_void_p), ('cur_n', C.c_void_p),
+                ('last_xyz', C.c_void_p), ('last_desc', C.c_void_p), ('last_flags', C.c_void_p), ('last_octave', C.c_void_p),
+                ('last_angle', C.c_void_p), ('last_n', C.c_void_p), ('tcw_cur', C.c_void_p), ('tcw_last', C.c_void_p),
+                ('th', C.c_float), ('mono', C.c_int32), ('check_orientation', C.c_int32),
+                ('cur_mp', C.c_void_p), ('cur_mp_obs_in', C.c_void_p), ('nmatches', C.c_void_p), ('ncand', C.c_void_p)]
+
+
+class LocalMapBatch(C.Structure):
+    _fields_ = [('cam', Camera),
+                ('cur_kps', C.c_void_p), ('cur_desc', C.c_void_p), ('cur_uright', C.c_void_p), ('cur_n', C.c_void_p),
+                ('mp_inview', C.c_void_p), ('proj_x', C.c_void_p), ('proj_y', C.c_void_p), ('proj_xr', C.c_void_p), ('level', C.c_void_p),
+                ('view_cos', C.c_void_p), ('mp_desc', C.c_void_p), ('mp_obs', C.c_void_p), ('mp_n', C.c_void_p),
+                ('th', C.c_float), ('nnratio', C.c_float), ('id_base', C.c_int32),
+                ('f_mp', C.c_void_p), ('f_mp_obs', C.c_void_p), ('nmatches', C.c_void_p), ('ncand', C.c_void_p)]
+
+
+ABI_SYMBOLS = [
+    'sgs_abi_version', 'sgs_last_error', 'sgs_device_count',
+    'sgs_extractor_create', 'sgs_extractor_destroy', 'sgs_extractor_tables', 'sgs_extractor_max_keypoints', 'sgs_extractor_level_info',
+    'sgs_extract', 'sgs_extract_batch', 'sgs_extract_batch_device', 'sgs_extractor_results_device', 'sgs_extractor_fetch', 'sgs_extractor_read_level',
+    'sgs_extractor_read_candidates',
+    'sgs_hamming_pairs', 'sgs_hamming_bf', 'sgs_hamming_bf_scratch_elems', 'sgs_hamming_bf_device',
+    'sgs_match_project_lastframe', 'sgs_match_project_localmap', 'sgs_matcher_create', 'sgs_matcher_destroy',
+    'sgs_match_project_lastframe_batch_device', 'sgs_match_project_localmap_batch_device',
+    'sgs_dynreject', 'sgs_dynreject_batch_device',
+]
+
+
+def build(force=False):
+    csrc = os.path.join(_PKG, 'csrc')
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(['make', '-C', csrc, '-s', os.path.join('..', 'lib', 'libsgs_cuda.so')])
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('libsgs_cuda.so is not built (run __graft_entry__.build() or make -C sg-slam_b200/csrc); there is no CPU fallback')
+        _LIB = C.CDLL(LIB_PATH)
+        _LIB.sgs_last_error.restype = C.c_char_p
+    return _LIB
+
+
+def check(code):
+    if code != SGS_OK:
+        raise SgsError(code, lib().sgs_last_error().decode('utf-8', 'replace'))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_count():
+    n = C.c_int()
+    check(lib().sgs_device_count(C.byref(n)))
+    return n.value
+
+
+class Extractor:
+    """ORB_SLAM2::ORBextractor on the GPU (sgs_extractor_* of include/sgs_abi.h)."""
+
+    def __init__(self, width, height, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, max_batch=1, device=0):
+        self.params = OrbParams(nfeatures, scale, nlevels, ini, mn)
+        self.width, self.height, self.max_batch, self.device = width, height, max_batch, device
+        self.h = C.c_void_p()
+        check(lib().sgs_extractor_create(C.byref(self.params), width, height, max_batch, device, C.byref(self.h)))
+        cap = C.c_int()
+        check(lib().sgs_extractor_max_keypoints(self.h, C.byref(cap)))
+        self.cap = cap.value
+
+    def close(self):
+        if self.h:
+            lib().sgs_extractor_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tables(self):
+        n = self.params.nlevels
+        sc, isc, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        fpl = np.zeros(n, np.int32)
+        check(lib().sgs_extractor_tables(self.h, _p(sc), _p(isc), _p(s2), _p(is2), _p(fpl)))
+        return dict(scale=sc, invScale=isc, sigma2=s2, invSigma2=is2, nPerLevel=fpl)
+
+    def level_info(self, level):
+        w, h, p = C.c_int(), C.c_int(), C.c_int()
+        check(lib().sgs_extractor_level_info(self.h, level, C.byref(w), C.byref(h), C.byref(p)))
+        return w.value, h.value, p.value
+
+    def extract(self, img):
+        """One host image -> (keypoints [n] KP_DTYPE, descriptors [n,32] u8)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n = C.c_int()
+        check(lib().sgs_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), self.cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, imgs, out_kps=None, out_desc=None, out_n=None):
+        """Host batch [F,h,w] -> (kps [F,cap], desc [F,cap,32], n [F])."""
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        F = imgs.shape[0]
+        kps = out_kps if out_kps is not None else np.zeros((F, self.cap), KP_DTYPE)
+        desc = out_desc if out_desc is not None else np.zeros((F, self.cap, 32), np.uint8)
+        n = out_n if out_n is not None else np.zeros(F, np.int32)
+        check(lib().sgs_extract_batch(self.h, _p(imgs), F, C.c_size_t(imgs.strides[0]), imgs.strides[1], _p(kps), _p(desc), self.cap, _p(n)))
+        return kps, desc, n
+
+    def extract_batch_device(self, d_ptr, nframes, frame_stride, pitch, stream=0):
+        check(lib().sgs_extract_batch_device(self.h, C.c_void_p(d_ptr), nframes, C.c_size_t(frame_stride), pitch, C.c_void_p(stream)))
+
+    def fetch(self, nframes, stream=0):
+        kps = np.zeros((nframes, self.cap), KP_DTYPE); desc = np.zeros((nframes, self.cap, 32), np.uint8); n = np.zeros(nframes, np.int32)
+        check(lib().sgs_extractor_fetch(self.h, nframes, _p(kps), _p(desc), self.cap, _p(n), C.c_void_p(stream)))
+        return kps, desc, n
+
+    def results_device(self):
+        k, d, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        cap = C.c_int()
+        check(lib().sgs_extractor_results_device(self.h, C.byref(k), C.byref(d), C.byref(c), C.byref(cap)))
+        return k.value, d.value, c.value, cap.value
+
+    def read_level(self, frame, level, blurred=False):
+        w, h, _ = self.level_info(level)
+        out = np.zeros((h, w), np.uint8)
+        check(lib().sgs_extractor_read_level(self.h, frame, level, int(blurred), _p(out), w))
+        return out
+
+    def read_candidates(self, frame, level):
+        n = C.c_int()
+        code = lib().sgs_extractor_read_candidates(self.h, frame, level, None, 0, C.byref(n))
+        if code not in (SGS_OK, SGS_ERR_CAPACITY):
+            check(code)
+        out = np.zeros((max(n.value, 1), 3), np.int32)
+        if n.value:
+            check(lib().sgs_extractor_read_candidates(self.h, frame, level, _p(out), n.value, C.byref(n)))
+        return out[:n.value]
+
+
+def hamming_pairs(a, b, device=0):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    out = np.zeros(len(a), np.int32)
+    check(lib().sgs_hamming_pairs(_p(a), _p(b), len(a), _p(out), device))
+    return out
+
+
+def hamming_bf(q, t, device=0):
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    bi = np.zeros(len(q), np.int32); bd = np.zeros(len(q), np.int32); sd = np.zeros(len(q), np.int32)
+    check(lib().sgs_hamming_bf(_p(q), len(q), _p(t) if len(t) else None, len(t), _p(bi), _p(bd), _p(sd), device))
+    return bi, bd, sd
+
+
+def hamming_bf_scratch_elems(nq, nt):
+    e = C.c_int64()
+    check(lib().sgs_hamming_bf_scratch_elems(nq, nt, C.byref(e)))
+    return e.value
+
+
+def hamming_bf_device(dq, nq, dt, nt, d_idx, d_best, d_second, d_scratch=0, stream=0):
+    check(lib().sgs_hamming_bf_device(C.c_void_p(dq), nq, C.c_void_p(dt), nt, C.c_void_p(d_idx), C.c_void_p(d_best), C.c_void_p(d_second),
+                                      C.c_void_p(d_scratch), C.c_void_p(stream)))
+
+
+class HostFrame:
+    """numpy arrays behind an sgs_frame_view."""
+
+    def __init__(self, keysUn, uRight, desc, w, h, fx, fy, cx, cy, bf, scaleFactors):
+        self.keysUn = np.ascontiguousarray(keysUn, KP_DTYPE)
+        self.uRight = np.ascontiguousarray(uRight, np.float32)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.scaleFactors = np.ascontiguousarray(scaleFactors, np.float32)
+        self.c = FrameView(len(self.keysUn), self.keysUn.ctypes.data, self.uRight.ctypes.data, self.desc.ctypes.data,
+                           0.0, 0.0, float(w), float(h), fx, fy, cx, cy, bf, len(self.scaleFactors), self.scaleFactors.ctypes.data)
+
+
+def match_project_lastframe(cur, Tcw_cur, Tcw_last, last_has_mp, last_xyz, last_desc, last_obs, last_octave, last_angle, th,
+                            mono=False, check_ori=True, cur_mp=None, cur_mp_obs=None, device=0):
+    n = len(last_has_mp)
+    Tc = np.ascontiguousarray(Tcw_cur, np.float32); Tl = np.ascontiguousarray(Tcw_last, np.float32)
+    has = np.ascontiguousarray(last_has_mp, np.uint8); xyz = np.ascontiguousarray(last_xyz, np.float32)
+    ld = np.ascontiguousarray(last_desc, np.uint8); lo = np.ascontiguousarray(last_obs, np.uint8)
+    loct = np.ascontiguousarray(last_octave, np.int32); la = np.ascontiguousarray(last_angle, np.float32)
+    mp = np.full(cur.c.n, -1, np.int32) if cur_mp is None else np.ascontiguousarray(cur_mp, np.int32).copy()
+    mpo = None if cur_mp_obs is None else np.ascontiguousarray(cur_mp_obs, np.uint8)
+    nm = C.c_int()
+    check(lib().sgs_match_project_lastframe(C.byref(cur.c), _p(Tc), _p(Tl), n, _p(has), _p(xyz), _p(ld), _p(lo), _p(loct), _p(la),
+                                            C.c_float(th), int(mono), int(check_ori), _p(mp), _p(mpo), C.byref(nm), device))
+    return nm.value, mp
+
+
+def match_project_localmap(fr, inview, projx, projy, projxr, level, viewcos, mp_desc, mp_obs, th, nnratio, f_mp, f_mp_obs, id_base=0, device=0):
+    n = len(inview)
+    a = [np.ascontiguousarray(inview, np.uint8), np.ascontiguousarray(projx, np.float32), np.ascontiguousarray(projy, np.float32),
+         np.ascontiguousarray(projxr, np.float32), np.ascontiguousarray(level, np.int32), np.ascontiguousarray(viewcos, np.float32),
+         np.ascontiguousarray(mp_desc, np.uint8), np.ascontiguousarray(mp_obs, np.uint8)]
+    mp = np.ascontiguousarray(f_mp, np.int32).copy(); mpo = np.ascontiguousarray(f_mp_obs, np.uint8).copy()
+    nm = C.c_int()
+    check(lib().sgs_match_project_localmap(C.byref(fr.c), n, *[_p(x) for x in a], C.c_float(th), C.c_float(nnratio), id_base, _p(mp), _p(mpo),
+                                           C.byref(nm), device))
+    return nm.value, mp, mpo
+
+
+def dynreject(cur_xy, prev_xy, F, boxes, have_dyn, nfeatures, device=0):
+    cur = np.ascontiguousarray(cur_xy, np.float32); prev = np.ascontiguousarray(prev_xy, np.float32)
+    n = len(cur)
+    Fm = None if F is None else np.ascontiguousarray(F, np.float64).reshape(9)
+    bx = np.ascontiguousarray(boxes, np.float32).reshape(-1, 4) if boxes is not None and len(boxes) else np.zeros((0, 4), np.float32)
+    keep = np.zeros(n, np.uint8); dist = np.zeros(n, np.float64); nk = C.c_int(); rest = C.c_int()
+    check(lib().sgs_dynreject(_p(cur), _p(prev), n, _p(Fm), _p(bx) if len(bx) else None, len(bx), int(have_dyn), nfeatures, _p(keep), _p(dist),
+                              C.byref(nk), C.byref(rest), device))
+    return nk.value, keep, dist, bool(rest.value)
+
+
+class Matcher:
+    def __init__(self, max_frames, cur_cap, point_cap, device=0):
+        self.h = C.c_void_p()
+        check(lib().sgs_matcher_create(device, max_frames, cur_cap, point_cap, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().sgs_matcher_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def lastframe_batch(self, args, nframes, stream=0):
+        check(lib().sgs_match_project_lastframe_batch_device(self.h, C.byref(args), nframes, C.c_void_p(stream)))
+
+    def localmap_batch(self, args, nframes, stream=0):
+        check(lib().sgs_match_project_localmap_batch_device(self.h, C.byref(args), nframes, C.c_void_p(stream)))
+
+
+def dynreject_batch_device(d_kps, d_desc, d_counts, cap, nframes, d_prev, d_F, d_boxes, d_nboxes, max_boxes, d_have, nfeatures,
+                           d_kps_out, d_desc_out, d_counts_out, d_keep=0, stream=0):
+    v = C.c_void_p
+    check(lib().sgs_dynreject_batch_device(v(d_kps), v(d_desc), v(d_counts), cap, nframes, v(d_prev), v(d_F), v(d_boxes), v(d_nboxes), max_boxes,
+                                           v(d_have), nfeatures, v(d_kps_out), v(d_desc_out), v(d_counts_out), v(d_keep), v(stream)))

@@ -1,0 +1,180 @@
+"""GPU parity: Hamming / projection matchers / dyn-reject (through the C ABI) against the CPU oracle.
+Integer results bit-exact; epipolar distances within 1e-5 (they are in fact identical FP64 values)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle as O  # noqa: E402
+import scenarios as S  # noqa: E402
+from pysgs import binding as B  # noqa: E402
+from pysgs import synth  # noqa: E402
+
+
+def test_hamming_pairs_and_known_answers():
+    a = synth.descriptors_s5(5000, 1); b = synth.descriptors_s5(5000, 2)
+    got = B.hamming_pairs(a, b)
+    ref = np.unpackbits(a ^ b, axis=1).sum(1)
+    assert np.array_equal(got, ref)
+    z = np.zeros((3, 32), np.uint8); f = np.full((3, 32), 255, np.uint8)
+    assert B.hamming_pairs(z, f).tolist() == [256, 256, 256] and B.hamming_pairs(z, z).tolist() == [0, 0, 0]
+    assert all(O.hamming(a[i], b[i]) == got[i] for i in range(50))
+
+
+@pytest.mark.parametrize('nq,nt', [(1, 1), (7, 300), (1000, 1000), (1000, 257), (130, 5000), (4096, 4096), (3, 0)])
+def test_bf_matches_oracle(nq, nt):
+    t = synth.descriptors_s5(max(nt, 1), 5)[:nt]
+    q = synth.descriptors_near(synth.descriptors_s5(max(nq, 1), 5)[:nq] if nt == 0 else t[np.random.RandomState(nq).randint(0, nt, nq)], 6)
+    gi, gd, gs = B.hamming_bf(q, t)
+    if nt == 0:
+        assert (gi == -1).all() and (gd == 256).all() and (gs == 256).all()
+        return
+    oi, od, os_ = O.bf_match(q, t)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od) and np.array_equal(gs, os_)
+
+
+def test_bf_tie_break_first_index_wins():
+    t = np.zeros((600, 32), np.uint8)         # all identical: every distance ties
+    q = np.zeros((40, 32), np.uint8); q[:, 0] = 1
+    gi, gd, gs = B.hamming_bf(q, t)
+    assert (gi == 0).all() and (gd == 1).all() and (gs == 1).all()
+
+
+def test_bf_large_property():
+    """BASELINE config 5 sizes: not oracle-checked pair by pair (too slow); size-independent properties instead."""
+    n = 16384
+    t = synth.descriptors_s5(n, 5)
+    q = synth.descriptors_near(t, 6, maxflips=20)
+    gi, gd, gs = B.hamming_bf(q, t)
+    # the planted neighbour (<= 20 flips) must be found: random 256-bit strings are ~128 apart
+    assert np.array_equal(gi, np.arange(n))
+    assert np.array_equal(gd, np.unpackbits(q ^ t, axis=1).sum(1))
+    assert (gs >= gd).all() and (gs > 60).all()
+    # idempotence / self-match
+    si, sd, _ = B.hamming_bf(t[:2048], t)
+    assert np.array_equal(si, np.arange(2048)) and (sd == 0).all()
+
+
+def _frames(s):
+    fo = O.FrameArrays(s['kps'], s['uright'], s['desc'], s['w'], s['h'], s['cam']['fx'], s['cam']['fy'], s['cam']['cx'], s['cam']['cy'], s['cam']['bf'], s['sf'])
+    fg = B.HostFrame(s['kps'], s['uright'], s['desc'], s['w'], s['h'], s['cam']['fx'], s['cam']['fy'], s['cam']['cx'], s['cam']['cy'], s['cam']['bf'], s['sf'])
+    return fo, fg
+
+
+@pytest.mark.parametrize('seed', range(6))
+@pytest.mark.parametrize('th', [15.0, 30.0])
+def test_search_by_projection_lastframe(seed, th):
+    s = S.random_lastframe_scenario(seed, n_cur=1000 + 37 * seed, n_last=900 + 53 * seed, conflict=[0.0, 0.3, 0.6][seed % 3], mono=(seed == 5))
+    fo, fg = _frames(s)
+    args = (s['Tcw_cur'], s['Tcw_last'], s['last_has'], s['last_xyz'], s['last_desc'], s['last_obs'], s['last_oct'], s['last_angle'], th)
+    for check_ori in (True, False):
+        nm_o, mp_o, _ = O.search_by_projection_last(fo, *args, mono=s['mono'], check_ori=check_ori)
+        nm_g, mp_g = B.match_project_lastframe(fg, *args, mono=s['mono'], check_ori=check_ori)
+        assert nm_g == nm_o, (seed, th, check_ori)
+        assert np.array_equal(mp_g, mp_o)
+        assert nm_o > 50   # the scenario really matches something
+
+
+def test_search_by_projection_lastframe_preexisting_matches():
+    s = S.random_lastframe_scenario(7)
+    fo, fg = _frames(s)
+    rng = np.random.RandomState(1)
+    pre = np.full(len(s['kps']), -1, np.int32); m = rng.rand(len(pre)) < 0.3; pre[m] = 5
+    pre_obs = (rng.rand(len(pre)) < 0.5).astype(np.uint8)
+    args = (s['Tcw_cur'], s['Tcw_last'], s['last_has'], s['last_xyz'], s['last_desc'], s['last_obs'], s['last_oct'], s['last_angle'], 15.0)
+    nm_o, mp_o, _ = O.search_by_projection_last(fo, *args, cur_mp=pre, cur_mp_obs=pre_obs)
+    nm_g, mp_g = B.match_project_lastframe(fg, *args, cur_mp=pre, cur_mp_obs=pre_obs)
+    assert nm_g == nm_o and np.array_equal(mp_g, mp_o)
+
+
+@pytest.mark.parametrize('seed', range(5))
+def test_search_by_projection_localmap(seed):
+    s = S.random_localmap_scenario(seed, n_cur=1000, n_mp=2500 + 100 * seed, conflict=[0.2, 0.5][seed % 2])
+    fo, fg = _frames(s)
+    for th, ratio in ((3.0, 0.8), (1.0, 0.8), (5.0, 0.6)):
+        a = (s['inview'], s['projx'], s['projy'], s['projxr'], s['level'], s['viewcos'], s['mp_desc'], s['mp_obs'], th, ratio, s['f_mp'], s['f_obs'])
+        nm_o, mp_o, ob_o, _ = O.search_by_projection_local(fo, *a)
+        nm_g, mp_g, ob_g = B.match_project_localmap(fg, *a)
+        assert nm_g == nm_o, (seed, th)
+        assert np.array_equal(mp_g, mp_o) and np.array_equal(ob_g, ob_o)
+        assert nm_o > 100
+
+
+def test_matchers_on_extracted_frames():
+    """End-to-end shaped case: frame k-1 keypoints with depth become map points, matched into frame k."""
+    frames, _ = synth.stream_s2(2, 640, 480, seed=4, person=False)
+    k0, d0 = O.extract(frames[0]); k1, d1 = O.extract(frames[1])
+    depth = synth.depth_s1()
+    cam = synth.TUM3; sf = S.scale_factors()
+    z = depth[k0['y'].astype(np.int64), k0['x'].astype(np.int64)]
+    Xw = np.stack([(k0['x'] - cam['cx']) * z / cam['fx'], (k0['y'] - cam['cy']) * z / cam['fy'], z], 1).astype(np.float32)
+    z1 = depth[k1['y'].astype(np.int64), k1['x'].astype(np.int64)]
+    ur = (k1['x'] - np.float32(cam['bf']) / z1).astype(np.float32)
+    fo = O.FrameArrays(k1, ur, d1, 640, 480, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], sf)
+    fg = B.HostFrame(k1, ur, d1, 640, 480, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], sf)
+    T = np.eye(4, dtype=np.float32)
+    ones = np.ones(len(k0), np.uint8)
+    args = (T, T, ones, Xw, d0, ones, k0['octave'], k0['angle'], 15.0)
+    nm_o, mp_o, _ = O.search_by_projection_last(fo, *args)
+    nm_g, mp_g = B.match_project_lastframe(fg, *args)
+    assert nm_g == nm_o and np.array_equal(mp_g, mp_o)
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_dynreject(seed):
+    s = S.dynreject_scenario(seed, n=1000 + 13 * seed)
+    for have_dyn in (True, False):
+        so, ko, do, ro = O.dynreject(s['cur'], s['prev'], s['F'], s['boxes'], have_dyn, 1000)
+        sg, kg, dg, rg = B.dynreject(s['cur'], s['prev'], s['F'], s['boxes'], have_dyn, 1000)
+        assert sg == so and rg == ro and np.array_equal(kg, ko)
+        assert np.all(np.abs(dg - do) <= 1e-5 * np.maximum(1.0, np.abs(do)))      # tolerance from BASELINE.json north_star
+        assert np.array_equal(dg.view(np.uint64), do.view(np.uint64))              # and in fact bit-identical
+        assert 0 < so < len(ko)
+    # restore-all branch: almost everything rejected while a person box is present
+    prev_bad = s['prev'] + 50
+    so, ko, _, ro = O.dynreject(s['cur'], prev_bad, s['F'], s['boxes'], True, 1000)
+    sg, kg, _, rg = B.dynreject(s['cur'], prev_bad, s['F'], s['boxes'], True, 1000)
+    assert ro and rg and sg == so and np.array_equal(kg, ko)
+    # empty F (quirk Q11): keep everything
+    sg, kg, _, rg = B.dynreject(s['cur'], s['prev'], None, s['boxes'], True, 1000)
+    assert sg == len(kg) and kg.all() and not rg
+    # degenerate F (all zeros): distance is NaN -> everything removed, as in the reference
+    so, ko, _, _ = O.dynreject(s['cur'], s['prev'], np.zeros(9), None, False, 1000)
+    sg, kg, _, _ = B.dynreject(s['cur'], s['prev'], np.zeros(9), None, False, 1000)
+    assert sg == so == 0 and not kg.any()
+
+
+def test_dynreject_batch_device_compaction():
+    import torch
+    F_, cap = 5, 1100
+    rng = np.random.RandomState(0)
+    kps = np.zeros((F_, cap), B.KP_DTYPE); desc = rng.randint(0, 256, (F_, cap, 32)).astype(np.uint8)
+    counts = np.array([1000, 1013, 0, 37, 1100], np.int32)
+    prev = np.zeros((F_, cap, 2), np.float32); Fm = np.zeros((F_, 9)); boxes = np.zeros((F_, 4, 4), np.float32)
+    nb = np.array([2, 0, 1, 2, 2], np.int32); have = np.array([1, 0, 1, 1, 1], np.uint8)
+    refs = []
+    for f in range(F_):
+        s = S.dynreject_scenario(20 + f, n=cap)
+        kps[f]['x'] = s['cur'][:, 0]; kps[f]['y'] = s['cur'][:, 1]; kps[f]['octave'] = rng.randint(0, 8, cap); kps[f]['angle'] = rng.rand(cap)
+        prev[f] = s['prev'] if f != 3 else s['prev'] + 40     # frame 3: restore-all branch
+        Fm[f] = s['F'].reshape(9); boxes[f, :2] = s['boxes']
+        if f == 4:
+            Fm[f, 0] = np.nan                                  # empty F
+        n = counts[f]
+        so, ko, _, ro = O.dynreject(s['cur'][:n], prev[f, :n], None if f == 4 else Fm[f], boxes[f, :nb[f]], bool(have[f]), 1000)
+        refs.append((so, ko, ro))
+    t = {k: torch.from_numpy(v).cuda() for k, v in dict(kps=kps.view(np.uint8).reshape(F_, cap, 28), desc=desc, counts=counts, prev=prev, Fm=Fm, boxes=boxes, nb=nb, have=have).items()}
+    ko_t = torch.zeros_like(t['kps']); do_t = torch.zeros_like(t['desc']); co_t = torch.zeros_like(t['counts']); keep_t = torch.zeros(F_, cap, dtype=torch.uint8, device='cuda')
+    torch.cuda.synchronize()
+    B.dynreject_batch_device(t['kps'].data_ptr(), t['desc'].data_ptr(), t['counts'].data_ptr(), cap, F_, t['prev'].data_ptr(), t['Fm'].data_ptr(),
+                             t['boxes'].data_ptr(), t['nb'].data_ptr(), 4, t['have'].data_ptr(), 1000, ko_t.data_ptr(), do_t.data_ptr(), co_t.data_ptr(), keep_t.data_ptr(), 0)
+    torch.cuda.synchronize()
+    co = co_t.cpu().numpy(); ko = ko_t.cpu().numpy().reshape(F_, cap * 28).view(B.KP_DTYPE).reshape(F_, cap); do_ = do_t.cpu().numpy(); keep = keep_t.cpu().numpy()
+    for f in range(F_):
+        so, kref, ro = refs[f]
+        n = counts[f]
+        assert np.array_equal(keep[f, :n], kref)
+        sel = np.arange(n) if ro else np.nonzero(kref)[0]
+        assert co[f] == len(sel)
+        assert ko[f, :len(sel)].tobytes() == kps[f][sel].tobytes()
+        assert np.array_equal(do_[f, :len(sel)], desc[f][sel])
