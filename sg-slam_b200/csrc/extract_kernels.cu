@@ -78,24 +78,29 @@ constexpr int kFastThreads = 256;
 constexpr int kTileMax = 66;     // w_cell <= 60 (n_cols = floor(width/30)) plus the 6-px overlap
 constexpr int kTilePitch = 72;
 
+// Exact FAST score from the 16 ring values: max over the 16 contiguous 9-arcs of max(min d, -max d) - 1, d_k = v - r_k.
+// Both halves are evaluated at once as packed signed 16-bit lanes (lo = d, hi = -d; |d| <= 255) with a sliding
+// min: windows of 2, 4, 8 then 9 ring positions (VIMNMX.S16x2).
+// NOTE (toolchain finding): with CUDA 12.9 ptxas -O3 for sm_100a the straightforward 32-bit formulation
+// `max(best, max(mn9, -mx9))` is MISCOMPILED (the negation is folded into a 3-input VIMNMX3 incorrectly; -Xptxas -O0
+// gives the right answer).  tools/ptxas_minmax_repro.cu reproduces it.  This formulation never negates a max result.
 __device__ __forceinline__ int fast_score_from_ring(int v, const int (&r)[16]) {
-    int d[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = v - r[k];
-    int mn2[16], mx2[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
-    int mn4[16], mx4[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
-    int best = -256;
+    unsigned p[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, max(mn9, -mx9));
+        const int d = v - r[k];
+        p[k] = ((unsigned)d & 0xFFFFu) | ((unsigned)(-d) << 16);
     }
-    return best - 1;
+    unsigned w2[16], w4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w2[k] = __vmins2(p[k], p[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w4[k] = __vmins2(w2[k], w2[(k + 2) & 15]);
+    unsigned best = 0x80008000u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) best = __vmaxs2(best, __vmins2(__vmins2(w4[k], w4[(k + 4) & 15]), p[(k + 8) & 15]));
+    const int lo = (int)(short)(best & 0xFFFFu), hi = (int)(short)(best >> 16);
+    return (lo > hi ? lo : hi) - 1;
 }
 
 __device__ __forceinline__ bool has_arc9(uint32_t m) {
