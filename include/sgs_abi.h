@@ -244,6 +244,54 @@ SGS_API int sgs_dynreject_batch_device(const sgs_keypoint* d_kps, const uint8_t*
                                        sgs_keypoint* d_kps_out, uint8_t* d_desc_out, int32_t* d_counts_out, uint8_t* d_keep,
                                        void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Batched front end with HOST buffers: the part of Frame::Frame (RGB-D ctor, src/Frame.cc:129-198) and
+ * Tracking::TrackWithMotionModel (src/Tracking.cc:906-931) that runs on the GPU, for `nframes` independent frames.
+ *   sgs_tracker_extract : ExtractORB (src/Frame.cc:146).  Keypoints/descriptors return to the host, which runs
+ *                         calcOpticalFlowPyrLK + findFundamentalMat (src/Frame.cc:445-472) -- not on the GPU in this round.
+ *   sgs_tracker_track   : dyn-reject verdicts + ordered compaction of keypoints, descriptors and u_right
+ *                         (src/Frame.cc:560-604) on the device-resident extraction results, then
+ *                         SearchByProjection(cur, last, th, mono) (src/ORBmatcher.cc:1332-1472).
+ * Array shapes: prev_xy [F][cap][2], u_right [F][cap] (mvuRight of the UNfiltered keypoints), F [F][9] (NaN in F[0] ==
+ * empty matrix), boxes [F][max_boxes], last_* [F][point_cap](..), tcw_* [F][16]; outputs kps_out [F][cap],
+ * desc_out [F][cap][32], u_right_out [F][cap] (may be NULL), counts_out [F], cur_mp_out [F][cap], nmatches_out [F].
+ * Pinned host memory is copied without staging.
+ * ------------------------------------------------------------------------------------ */
+typedef struct sgs_tracker sgs_tracker;
+SGS_API int sgs_tracker_create(const sgs_orb_params* params, int width, int height, int max_batch, int point_cap,
+                               int max_boxes, const sgs_camera* cam, int device, sgs_tracker** out);
+SGS_API void sgs_tracker_destroy(sgs_tracker* t);
+SGS_API int sgs_tracker_max_keypoints(const sgs_tracker* t, int* cap);
+SGS_API int sgs_tracker_extract(sgs_tracker* t, const uint8_t* gray, int nframes, size_t frame_stride, int pitch,
+                                sgs_keypoint* kps, uint8_t* desc, int cap, int* n);
+SGS_API int sgs_tracker_track(sgs_tracker* t, int nframes, const float* prev_xy, const float* u_right, const double* F,
+                              const sgs_rect* boxes, const int32_t* nboxes, const uint8_t* have_dyn, const float* last_xyz,
+                              const uint8_t* last_desc, const uint8_t* last_flags, const int32_t* last_octave,
+                              const float* last_angle, const int32_t* last_n, const float* tcw_cur, const float* tcw_last,
+                              float th, int mono, int check_orientation, sgs_keypoint* kps_out, uint8_t* desc_out,
+                              float* u_right_out, int32_t* counts_out, int32_t* cur_mp_out, int32_t* nmatches_out);
+
+/* Device-resident variants: every pointer is a DEVICE pointer, work is enqueued on `stream` without synchronising and
+ * the results stay in the handle (sgs_tracker_results_device: kps [F][cap], desc, u_right, counts [F], cur_mp [F][cap],
+ * nmatches [F], ncand [F] = candidates examined by the matcher, for the roofline byte count). */
+SGS_API int sgs_tracker_extract_device(sgs_tracker* t, const uint8_t* d_gray, int nframes, size_t frame_stride, int pitch,
+                                       void* stream);
+SGS_API int sgs_tracker_track_device(sgs_tracker* t, int nframes, const float* prev_xy, const float* u_right, const double* F,
+                                     const sgs_rect* boxes, const int32_t* nboxes, const uint8_t* have_dyn,
+                                     const float* last_xyz, const uint8_t* last_desc, const uint8_t* last_flags,
+                                     const int32_t* last_octave, const float* last_angle, const int32_t* last_n,
+                                     const float* tcw_cur, const float* tcw_last, float th, int mono, int check_orientation,
+                                     void* stream);
+SGS_API int sgs_tracker_results_device(const sgs_tracker* t, const sgs_keypoint** kps, const uint8_t** desc,
+                                       const float** u_right, const int32_t** counts, const int32_t** cur_mp,
+                                       const int32_t** nmatches, const uint64_t** ncand);
+SGS_API sgs_extractor* sgs_tracker_extractor(sgs_tracker* t);  /* the extractor owned by the tracker (tables, profiling) */
+
+/* ---- measurement hooks (bench.py): per-stage device time of the extractor from CUDA events recorded on the launching
+ * stream.  Stages: 0 pyramid, 1 FAST, 2 quadtree, 3 blur, 4 orientation+BRIEF.  ms_total5 accumulates over `ncalls`. */
+SGS_API int sgs_extractor_set_profiling(sgs_extractor* ex, int enable);
+SGS_API int sgs_extractor_stage_times(sgs_extractor* ex, double* ms_total5, int* ncalls);
+
 #ifdef __cplusplus
 }
 #endif

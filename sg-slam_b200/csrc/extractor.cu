@@ -40,6 +40,13 @@ struct sgs_extractor {
     sgs_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_count = nullptr; int32_t* h_error = nullptr;
     int last_nframes = 0;
     bool last_level0_external = false;
+    // optional per-stage timing (CUDA events on the launching stream): pyramid, FAST, quadtree, blur, describe
+    bool profiling = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double stage_ms_acc[5] = {0, 0, 0, 0, 0};
+    int stage_calls = 0;
+    bool stage_pending = false;
+    cudaStream_t last_stream = nullptr;
 };
 
 namespace {
@@ -57,6 +64,7 @@ void free_all(sgs_extractor* ex) {
     if (ex->h_desc) cudaFreeHost(ex->h_desc);
     if (ex->h_count) cudaFreeHost(ex->h_count);
     if (ex->h_error) cudaFreeHost(ex->h_error);
+    for (auto& e : ex->ev) if (e) cudaEventDestroy(e);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
 }
@@ -67,14 +75,29 @@ int enqueue(sgs_extractor* ex, const uint8_t* d_l0, int pitch, int64_t fstride, 
     P.nframes = nframes;
     P.lv[0].img = d_l0; P.lv[0].pitch = pitch; P.lv[0].fstride = fstride;
     const int L = P.nlevels;
+    const bool prof = ex->profiling;
+    if (prof && ex->stage_pending) {  // fold the previous call's events before reusing them
+        if (cudaEventSynchronize(ex->ev[5]) == cudaSuccess) {
+            for (int i = 0; i < 5; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ex->ev[i], ex->ev[i + 1]); ex->stage_ms_acc[i] += ms; }
+            ex->stage_calls++;
+        }
+        ex->stage_pending = false;
+    }
     SGS_CUDA_TRY(cudaMemsetAsync(ex->d_cand_count, 0, sizeof(int32_t) * (size_t)nframes * L, st));
+    if (prof) cudaEventRecord(ex->ev[0], st);
     for (int l = 1; l < L; ++l) launch_resize(P, l, st);
+    if (prof) cudaEventRecord(ex->ev[1], st);
     launch_fast(P, ex->d_cells, (int)ex->plan.cells.size(), st);
+    if (prof) cudaEventRecord(ex->ev[2], st);
     launch_quadtree(P, ex->smem_key_cap, ex->node_cap, ex->qt_smem, ex->d_key_scratch, ex->key_scratch_fstride, ex->d_key_scratch_off, st);
+    if (prof) cudaEventRecord(ex->ev[3], st);
     for (int l = 0; l < L; ++l) launch_blur(P, l, st);
+    if (prof) cudaEventRecord(ex->ev[4], st);
     launch_describe(P, st);
+    if (prof) { cudaEventRecord(ex->ev[5], st); ex->stage_pending = true; }
     SGS_CUDA_TRY(cudaGetLastError());
     ex->last_nframes = nframes;
+    ex->last_stream = st;
     return SGS_OK;
 }
 
@@ -209,6 +232,29 @@ SGS_API int sgs_extractor_create(const sgs_orb_params* params, int width, int he
 
 SGS_API void sgs_extractor_destroy(sgs_extractor* ex) { free_all(ex); }
 
+SGS_API int sgs_extractor_set_profiling(sgs_extractor* ex, int enable) {
+    if (!ex) return fail_invalid("sgs_extractor_set_profiling: NULL handle");
+    SGS_CUDA_TRY(cudaSetDevice(ex->device));
+    if (enable && !ex->ev[0]) for (auto& e : ex->ev) SGS_CUDA_TRY(cudaEventCreate(&e));
+    ex->profiling = enable != 0;
+    ex->stage_pending = false; ex->stage_calls = 0;
+    for (double& v : ex->stage_ms_acc) v = 0;
+    return SGS_OK;
+}
+
+SGS_API int sgs_extractor_stage_times(sgs_extractor* ex, double* ms_total5, int* ncalls) {
+    if (!ex || !ms_total5 || !ncalls) return fail_invalid("sgs_extractor_stage_times: NULL");
+    if (ex->stage_pending) {
+        SGS_CUDA_TRY(cudaEventSynchronize(ex->ev[5]));
+        for (int i = 0; i < 5; ++i) { float ms = 0; SGS_CUDA_TRY(cudaEventElapsedTime(&ms, ex->ev[i], ex->ev[i + 1])); ex->stage_ms_acc[i] += ms; }
+        ex->stage_calls++;
+        ex->stage_pending = false;
+    }
+    for (int i = 0; i < 5; ++i) ms_total5[i] = ex->stage_ms_acc[i];
+    *ncalls = ex->stage_calls;
+    return SGS_OK;
+}
+
 SGS_API int sgs_extractor_tables(const sgs_extractor* ex, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* fpl) {
     if (!ex) return fail_invalid("sgs_extractor_tables: NULL handle");
     for (int l = 0; l < ex->plan.nlevels; ++l) {
@@ -287,11 +333,23 @@ SGS_API int sgs_extract_batch(sgs_extractor* ex, const uint8_t* gray, int nframe
     SGS_CUDA_TRY(cudaSetDevice(ex->device));
     cudaStream_t st = ex->stream;
     const LevelGeom& g0 = PL.lv[0];
-    // host -> pinned staging (dense rows) -> device level 0 (own pitch)
-    for (int f = 0; f < nframes; ++f)
-        for (int y = 0; y < PL.height; ++y)
-            std::memcpy(ex->h_in + (size_t)f * g0.frame_stride + (size_t)y * g0.pitch, gray + (size_t)f * frame_stride + (size_t)y * pitch, PL.width);
-    SGS_CUDA_TRY(cudaMemcpyAsync(ex->d_pyr, ex->h_in, (size_t)nframes * g0.frame_stride, cudaMemcpyHostToDevice, st));
+    // pinned caller memory is copied straight to the device; pageable memory goes through the pinned staging buffer
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, gray) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        if (frame_stride == (size_t)pitch * PL.height) {
+            SGS_CUDA_TRY(cudaMemcpy2DAsync(ex->d_pyr, g0.pitch, gray, pitch, PL.width, (size_t)PL.height * nframes, cudaMemcpyHostToDevice, st));
+        } else {
+            for (int f = 0; f < nframes; ++f)
+                SGS_CUDA_TRY(cudaMemcpy2DAsync(ex->d_pyr + (size_t)f * g0.frame_stride, g0.pitch, gray + (size_t)f * frame_stride, pitch, PL.width, PL.height, cudaMemcpyHostToDevice, st));
+        }
+    } else {
+        for (int f = 0; f < nframes; ++f)
+            for (int y = 0; y < PL.height; ++y)
+                std::memcpy(ex->h_in + (size_t)f * g0.frame_stride + (size_t)y * g0.pitch, gray + (size_t)f * frame_stride + (size_t)y * pitch, PL.width);
+        SGS_CUDA_TRY(cudaMemcpyAsync(ex->d_pyr, ex->h_in, (size_t)nframes * g0.frame_stride, cudaMemcpyHostToDevice, st));
+    }
     ex->last_level0_external = false;
     int rc = enqueue(ex, ex->d_pyr, g0.pitch, g0.frame_stride, nframes, st);
     if (rc != SGS_OK) return rc;

@@ -1,0 +1,205 @@
+// tracker.cu -- batched front end of the tracking thread's per-frame hot path with HOST buffers at the boundary:
+//   sgs_tracker_extract : Frame::ExtractORB (src/Frame.cc:274-280) for a batch of frames; keypoints go back to the host
+//                         (the host runs LK + findFundamentalMat on them, src/Frame.cc:445-472 -- not on the GPU yet);
+//   sgs_tracker_track   : dyn-reject verdicts + ordered compaction (src/Frame.cc:560-604) followed by
+//                         ORBmatcher::SearchByProjection(cur, last, th, mono) (src/ORBmatcher.cc:1332-1472, called from
+//                         Tracking::TrackWithMotionModel, src/Tracking.cc:924), on the device-resident extraction results.
+// One H2D of the frames, one H2D of the per-frame track inputs, one D2H of the compacted results + matches.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <vector>
+
+#include "sgs_common.h"
+
+struct sgs_tracker {
+    int device = 0, max_batch = 0, cap = 0, point_cap = 0, max_boxes = 0, nfeatures = 0;
+    sgs_camera cam{};
+    sgs_extractor* ex = nullptr;
+    sgs_matcher* mt = nullptr;
+    cudaStream_t st = nullptr;
+    // device inputs of track()
+    float* d_prev = nullptr; float* d_uright_in = nullptr; double* d_F = nullptr; sgs_rect* d_boxes = nullptr; int32_t* d_nboxes = nullptr;
+    uint8_t* d_have = nullptr;
+    float* d_lxyz = nullptr; uint8_t* d_ldesc = nullptr; uint8_t* d_lflags = nullptr; int32_t* d_loct = nullptr; float* d_lang = nullptr;
+    int32_t* d_ln = nullptr; float* d_tc = nullptr; float* d_tl = nullptr;
+    // device outputs
+    sgs_keypoint* d_kps2 = nullptr; uint8_t* d_desc2 = nullptr; int32_t* d_cnt2 = nullptr; uint8_t* d_keep = nullptr; float* d_uright2 = nullptr;
+    int32_t* d_mp = nullptr; int32_t* d_nm = nullptr; unsigned long long* d_ncand = nullptr;
+    int last_nframes = 0;
+};
+
+namespace sgs {
+// ordered compaction of the per-keypoint u_right side array with the verdicts of the dyn-reject kernel
+__global__ void compact_uright_kernel(const float* __restrict__ ur_in, const uint8_t* __restrict__ keep, const int32_t* __restrict__ n_in,
+                                      const int32_t* __restrict__ n_out, int cap, float* __restrict__ ur_out, int32_t* __restrict__ mp) {
+    __shared__ int s_warp[8];
+    __shared__ int s_carry;
+    const int f = blockIdx.x;
+    const int n = min(n_in[f], cap);
+    const bool restored = n_out[f] == n;   // restore-all (or nothing rejected): identity
+    const int64_t base = (int64_t)f * cap;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        const bool ok = i < n && (restored || keep[base + i]);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int off = s_carry;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (ok) ur_out[base + off + __popc(m & ((1u << lane) - 1))] = ur_in[base + i];
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_carry += t; }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < cap; i += 256) mp[base + i] = -1;   // Tracking.cc:916 clears mvpMapPoints before the search
+}
+}  // namespace sgs
+
+using namespace sgs;
+
+namespace {
+int bad(const char* m) { set_error("%s", m); return SGS_ERR_INVALID; }
+template <class T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T) + 16); }
+}  // namespace
+
+extern "C" {
+
+SGS_API void sgs_tracker_destroy(sgs_tracker* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    if (t->ex) sgs_extractor_destroy(t->ex);
+    if (t->mt) sgs_matcher_destroy(t->mt);
+    void* ptrs[] = {t->d_prev, t->d_uright_in, t->d_F, t->d_boxes, t->d_nboxes, t->d_have, t->d_lxyz, t->d_ldesc, t->d_lflags, t->d_loct, t->d_lang,
+                    t->d_ln, t->d_tc, t->d_tl, t->d_kps2, t->d_desc2, t->d_cnt2, t->d_keep, t->d_uright2, t->d_mp, t->d_nm, t->d_ncand};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (t->st) cudaStreamDestroy(t->st);
+    delete t;
+}
+
+SGS_API int sgs_tracker_create(const sgs_orb_params* params, int width, int height, int max_batch, int point_cap, int max_boxes,
+                               const sgs_camera* cam, int device, sgs_tracker** out) {
+    if (!params || !cam || !out || point_cap < 1 || max_boxes < 0) return bad("sgs_tracker_create: bad argument");
+    *out = nullptr;
+    sgs_tracker* t = new sgs_tracker();
+    t->device = device; t->max_batch = max_batch; t->point_cap = point_cap; t->max_boxes = max_boxes > 0 ? max_boxes : 1; t->cam = *cam;
+    t->nfeatures = params->nfeatures;
+    int rc = sgs_extractor_create(params, width, height, max_batch, device, &t->ex);
+    if (rc != SGS_OK) { delete t; return rc; }
+    sgs_extractor_max_keypoints(t->ex, &t->cap);
+    rc = sgs_matcher_create(device, max_batch, t->cap, point_cap, &t->mt);
+    if (rc != SGS_OK) { sgs_tracker_destroy(t); return rc; }
+    const size_t B = max_batch, K = t->cap, M = point_cap;
+    cudaError_t e = cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking);
+#define A(call) if (e == cudaSuccess) e = (call)
+    A(dalloc(&t->d_prev, B * K * 2)); A(dalloc(&t->d_uright_in, B * K)); A(dalloc(&t->d_F, B * 9)); A(dalloc(&t->d_boxes, B * t->max_boxes));
+    A(dalloc(&t->d_nboxes, B)); A(dalloc(&t->d_have, B)); A(dalloc(&t->d_lxyz, B * M * 3)); A(dalloc(&t->d_ldesc, B * M * 32));
+    A(dalloc(&t->d_lflags, B * M)); A(dalloc(&t->d_loct, B * M)); A(dalloc(&t->d_lang, B * M)); A(dalloc(&t->d_ln, B));
+    A(dalloc(&t->d_tc, B * 16)); A(dalloc(&t->d_tl, B * 16)); A(dalloc(&t->d_kps2, B * K)); A(dalloc(&t->d_desc2, B * K * 32));
+    A(dalloc(&t->d_cnt2, B)); A(dalloc(&t->d_keep, B * K)); A(dalloc(&t->d_uright2, B * K)); A(dalloc(&t->d_mp, B * K)); A(dalloc(&t->d_nm, B));
+    A(dalloc(&t->d_ncand, B));
+#undef A
+    if (e != cudaSuccess) { set_error("sgs_tracker_create: %s", cudaGetErrorString(e)); sgs_tracker_destroy(t); return SGS_ERR_CUDA; }
+    *out = t;
+    return SGS_OK;
+}
+
+SGS_API int sgs_tracker_max_keypoints(const sgs_tracker* t, int* cap) {
+    if (!t || !cap) return bad("sgs_tracker_max_keypoints: NULL");
+    *cap = t->cap;
+    return SGS_OK;
+}
+
+SGS_API int sgs_tracker_extract(sgs_tracker* t, const uint8_t* gray, int nframes, size_t frame_stride, int pitch, sgs_keypoint* kps, uint8_t* desc,
+                                int cap, int* n) {
+    if (!t) return bad("sgs_tracker_extract: NULL handle");
+    int rc = sgs_extract_batch(t->ex, gray, nframes, frame_stride, pitch, kps, desc, cap, n);
+    if (rc == SGS_OK) t->last_nframes = nframes;
+    return rc;
+}
+
+SGS_API int sgs_tracker_extract_device(sgs_tracker* t, const uint8_t* d_gray, int nframes, size_t frame_stride, int pitch, void* stream) {
+    if (!t) return bad("sgs_tracker_extract_device: NULL handle");
+    int rc = sgs_extract_batch_device(t->ex, d_gray, nframes, frame_stride, pitch, stream ? stream : (void*)t->st);
+    if (rc == SGS_OK) t->last_nframes = nframes;
+    return rc;
+}
+
+// all pointers are DEVICE pointers; enqueues dyn-reject + u_right compaction + projection matching on `stream`
+SGS_API int sgs_tracker_track_device(sgs_tracker* t, int nframes, const float* prev_xy, const float* u_right, const double* F, const sgs_rect* boxes,
+                                     const int32_t* nboxes, const uint8_t* have_dyn, const float* last_xyz, const uint8_t* last_desc,
+                                     const uint8_t* last_flags, const int32_t* last_octave, const float* last_angle, const int32_t* last_n,
+                                     const float* tcw_cur, const float* tcw_last, float th, int mono, int check_orientation, void* stream) {
+    if (!t || !prev_xy || !u_right || !F || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle ||
+        !last_n || !tcw_cur || !tcw_last) return bad("sgs_tracker_track_device: NULL argument");
+    if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_track_device: nframes exceeds the last extract call");
+    cudaStream_t st = stream ? (cudaStream_t)stream : t->st;
+    const sgs_keypoint* d_kps; const uint8_t* d_desc; const int32_t* d_cnt; int cap = 0;
+    sgs_extractor_results_device(t->ex, &d_kps, &d_desc, &d_cnt, &cap);
+    int rc = sgs_dynreject_batch_device(d_kps, d_desc, d_cnt, cap, nframes, prev_xy, F, boxes ? boxes : t->d_boxes, nboxes, t->max_boxes, have_dyn,
+                                        t->nfeatures, t->d_kps2, t->d_desc2, t->d_cnt2, t->d_keep, st);
+    if (rc != SGS_OK) return rc;
+    compact_uright_kernel<<<nframes, 256, 0, st>>>(u_right, t->d_keep, d_cnt, t->d_cnt2, cap, t->d_uright2, t->d_mp);
+    SGS_CUDA_TRY(cudaMemsetAsync(t->d_ncand, 0, (size_t)nframes * 8, st));
+    sgs_lastframe_batch a;
+    std::memset(&a, 0, sizeof a);
+    a.cam = t->cam;
+    a.cur_kps = t->d_kps2; a.cur_desc = t->d_desc2; a.cur_uright = t->d_uright2; a.cur_n = t->d_cnt2;
+    a.last_xyz = last_xyz; a.last_desc = last_desc; a.last_flags = last_flags; a.last_octave = last_octave; a.last_angle = last_angle; a.last_n = last_n;
+    a.tcw_cur = tcw_cur; a.tcw_last = tcw_last; a.th = th; a.mono = mono; a.check_orientation = check_orientation;
+    a.cur_mp = t->d_mp; a.cur_mp_obs_in = nullptr; a.nmatches = t->d_nm; a.ncand = (uint64_t*)t->d_ncand;
+    return sgs_match_project_lastframe_batch_device(t->mt, &a, nframes, st);
+}
+
+// device pointers to the results of the last track call: kps [B][cap], desc, u_right, counts [B], cur_mp [B][cap], nmatches [B], ncand [B]
+SGS_API int sgs_tracker_results_device(const sgs_tracker* t, const sgs_keypoint** kps, const uint8_t** desc, const float** u_right,
+                                       const int32_t** counts, const int32_t** cur_mp, const int32_t** nmatches, const uint64_t** ncand) {
+    if (!t) return bad("sgs_tracker_results_device: NULL handle");
+    if (kps) *kps = t->d_kps2;
+    if (desc) *desc = t->d_desc2;
+    if (u_right) *u_right = t->d_uright2;
+    if (counts) *counts = t->d_cnt2;
+    if (cur_mp) *cur_mp = t->d_mp;
+    if (nmatches) *nmatches = t->d_nm;
+    if (ncand) *ncand = (const uint64_t*)t->d_ncand;
+    return SGS_OK;
+}
+
+SGS_API int sgs_tracker_track(sgs_tracker* t, int nframes, const float* prev_xy, const float* u_right, const double* F, const sgs_rect* boxes,
+                              const int32_t* nboxes, const uint8_t* have_dyn, const float* last_xyz, const uint8_t* last_desc,
+                              const uint8_t* last_flags, const int32_t* last_octave, const float* last_angle, const int32_t* last_n,
+                              const float* tcw_cur, const float* tcw_last, float th, int mono, int check_orientation, sgs_keypoint* kps_out,
+                              uint8_t* desc_out, float* u_right_out, int32_t* counts_out, int32_t* cur_mp_out, int32_t* nmatches_out) {
+    if (!t || !prev_xy || !u_right || !F || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle ||
+        !last_n || !tcw_cur || !tcw_last || !kps_out || !desc_out || !counts_out || !cur_mp_out || !nmatches_out)
+        return bad("sgs_tracker_track: NULL argument");
+    if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_track: nframes exceeds the last sgs_tracker_extract call");
+    SGS_CUDA_TRY(cudaSetDevice(t->device));
+    const size_t B = nframes, K = t->cap, M = t->point_cap;
+    cudaStream_t st = t->st;
+#define H2D(dst, src, bytes) SGS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st))
+    H2D(t->d_prev, prev_xy, B * K * 8); H2D(t->d_uright_in, u_right, B * K * 4); H2D(t->d_F, F, B * 72);
+    if (boxes) H2D(t->d_boxes, boxes, B * t->max_boxes * sizeof(sgs_rect));
+    H2D(t->d_nboxes, nboxes, B * 4); H2D(t->d_have, have_dyn, B);
+    H2D(t->d_lxyz, last_xyz, B * M * 12); H2D(t->d_ldesc, last_desc, B * M * 32); H2D(t->d_lflags, last_flags, B * M);
+    H2D(t->d_loct, last_octave, B * M * 4); H2D(t->d_lang, last_angle, B * M * 4); H2D(t->d_ln, last_n, B * 4);
+    H2D(t->d_tc, tcw_cur, B * 64); H2D(t->d_tl, tcw_last, B * 64);
+#undef H2D
+    int rc = sgs_tracker_track_device(t, nframes, t->d_prev, t->d_uright_in, t->d_F, t->d_boxes, t->d_nboxes, t->d_have, t->d_lxyz, t->d_ldesc,
+                                      t->d_lflags, t->d_loct, t->d_lang, t->d_ln, t->d_tc, t->d_tl, th, mono, check_orientation, st);
+    if (rc != SGS_OK) return rc;
+#define D2H(dst, src, bytes) SGS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st))
+    D2H(kps_out, t->d_kps2, B * K * sizeof(sgs_keypoint)); D2H(desc_out, t->d_desc2, B * K * 32); D2H(counts_out, t->d_cnt2, B * 4);
+    if (u_right_out) D2H(u_right_out, t->d_uright2, B * K * 4);
+    D2H(cur_mp_out, t->d_mp, B * K * 4); D2H(nmatches_out, t->d_nm, B * 4);
+#undef D2H
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    return SGS_OK;
+}
+
+SGS_API sgs_extractor* sgs_tracker_extractor(sgs_tracker* t) { return t ? t->ex : nullptr; }
+
+}  // extern "C"

@@ -70,6 +70,8 @@ ABI_SYMBOLS = [
     'sgs_match_project_lastframe', 'sgs_match_project_localmap', 'sgs_matcher_create', 'sgs_matcher_destroy',
     'sgs_match_project_lastframe_batch_device', 'sgs_match_project_localmap_batch_device',
     'sgs_dynreject', 'sgs_dynreject_batch_device',
+    'sgs_tracker_create', 'sgs_tracker_destroy', 'sgs_tracker_max_keypoints', 'sgs_tracker_extract', 'sgs_tracker_track',
+    'sgs_extractor_set_profiling', 'sgs_extractor_stage_times',
 ]
 
 
@@ -166,6 +168,14 @@ class Extractor:
         kps = np.zeros((nframes, self.cap), KP_DTYPE); desc = np.zeros((nframes, self.cap, 32), np.uint8); n = np.zeros(nframes, np.int32)
         check(lib().sgs_extractor_fetch(self.h, nframes, _p(kps), _p(desc), self.cap, _p(n), C.c_void_p(stream)))
         return kps, desc, n
+
+    def set_profiling(self, on=True):
+        check(lib().sgs_extractor_set_profiling(self.h, int(on)))
+
+    def stage_times(self):
+        ms = (C.c_double * 5)(); n = C.c_int()
+        check(lib().sgs_extractor_stage_times(self.h, ms, C.byref(n)))
+        return [ms[i] for i in range(5)], n.value
 
     def results_device(self):
         k, d, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -293,3 +303,47 @@ def dynreject_batch_device(d_kps, d_desc, d_counts, cap, nframes, d_prev, d_F, d
     v = C.c_void_p
     check(lib().sgs_dynreject_batch_device(v(d_kps), v(d_desc), v(d_counts), cap, nframes, v(d_prev), v(d_F), v(d_boxes), v(d_nboxes), max_boxes,
                                            v(d_have), nfeatures, v(d_kps_out), v(d_desc_out), v(d_counts_out), v(d_keep), v(stream)))
+
+
+def make_camera(w, h, cam, scale_factors):
+    c = Camera()
+    c.min_x, c.min_y, c.max_x, c.max_y = 0.0, 0.0, float(w), float(h)
+    c.fx, c.fy, c.cx, c.cy, c.bf = cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf']
+    c.nlevels = len(scale_factors)
+    for i, v in enumerate(scale_factors):
+        c.scale_factors[i] = float(v)
+    return c
+
+
+class Tracker:
+    """Batched front end with host buffers (sgs_tracker_* of include/sgs_abi.h)."""
+
+    def __init__(self, width, height, camera, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, max_batch=1, point_cap=1100, max_boxes=4, device=0):
+        self.params = OrbParams(nfeatures, scale, nlevels, ini, mn)
+        self.h = C.c_void_p()
+        self.cam = camera
+        check(lib().sgs_tracker_create(C.byref(self.params), width, height, max_batch, point_cap, max_boxes, C.byref(camera), device, C.byref(self.h)))
+        cap = C.c_int()
+        check(lib().sgs_tracker_max_keypoints(self.h, C.byref(cap)))
+        self.cap, self.point_cap, self.max_boxes, self.max_batch = cap.value, point_cap, max_boxes, max_batch
+
+    def close(self):
+        if self.h:
+            lib().sgs_tracker_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def extract(self, gray_ptr, nframes, frame_stride, pitch, kps_ptr, desc_ptr, n_ptr):
+        v = C.c_void_p
+        check(lib().sgs_tracker_extract(self.h, v(gray_ptr), nframes, C.c_size_t(frame_stride), pitch, v(kps_ptr), v(desc_ptr), self.cap, v(n_ptr)))
+
+    def track(self, nframes, ptrs, th, mono, check_ori, out_ptrs):
+        """ptrs: prev_xy, u_right, F, boxes, nboxes, have_dyn, last_xyz, last_desc, last_flags, last_octave, last_angle, last_n, tcw_cur, tcw_last
+        out_ptrs: kps, desc, u_right (or 0), counts, cur_mp, nmatches   (all raw host addresses)"""
+        v = C.c_void_p
+        check(lib().sgs_tracker_track(self.h, nframes, *[v(p) for p in ptrs], C.c_float(th), int(mono), int(check_ori), *[v(p) for p in out_ptrs]))
