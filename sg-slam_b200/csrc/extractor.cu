@@ -3,6 +3,7 @@
 // extract_kernels.cu on one stream.  Replaces ORB_SLAM2::ORBextractor (include/ORBextractor.h:45-105).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -35,6 +36,11 @@ struct sgs_extractor {
     std::vector<int64_t> lvl_off;  // byte offset of level l (frame 0) inside d_pyr / d_blur
     int smem_key_cap = 0, node_cap = 0;
     size_t qt_smem = 0;
+    FastLaunchPlan fast_plan;
+    FastTmaMaps fast_maps{};
+    bool maps_ok = false;            // levels >= 1 (own buffers) encoded
+    const void* map0_ptr = nullptr; int map0_pitch = 0; int64_t map0_fstride = 0; int map0_frames = 0; bool map0_ok = false;
+    int fast_variant = 2;            // 2: warp-per-cell + TMA, 1: warp-per-cell plain loads, 0: block-per-cell reference kernel
     // pinned staging for the host API
     uint8_t* h_in = nullptr; size_t h_in_bytes = 0;
     sgs_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_count = nullptr; int32_t* h_error = nullptr;
@@ -87,7 +93,16 @@ int enqueue(sgs_extractor* ex, const uint8_t* d_l0, int pitch, int64_t fstride, 
     if (prof) cudaEventRecord(ex->ev[0], st);
     for (int l = 1; l < L; ++l) launch_resize(P, l, st);
     if (prof) cudaEventRecord(ex->ev[1], st);
-    launch_fast(P, ex->d_cells, (int)ex->plan.cells.size(), st);
+    if (ex->fast_variant == 0) {
+        launch_fast(P, ex->d_cells, (int)ex->plan.cells.size(), st);
+    } else {
+        bool tma = ex->fast_variant == 2 && ex->maps_ok;
+        if (tma && !(ex->map0_ok && ex->map0_ptr == d_l0 && ex->map0_pitch == pitch && ex->map0_fstride == fstride && ex->map0_frames >= nframes)) {
+            ex->map0_ok = encode_level_map(&ex->fast_maps.m[0], d_l0, P.lv[0].w, P.lv[0].h, pitch, fstride, nframes, ex->fast_plan.tp, ex->fast_plan.th);
+            ex->map0_ptr = d_l0; ex->map0_pitch = pitch; ex->map0_fstride = fstride; ex->map0_frames = nframes;
+        }
+        launch_fast_v2(P, ex->fast_maps, tma && ex->map0_ok, ex->fast_plan, ex->d_cells, (int)ex->plan.cells.size(), st);
+    }
     if (prof) cudaEventRecord(ex->ev[2], st);
     launch_quadtree(P, ex->smem_key_cap, ex->node_cap, ex->qt_smem, ex->d_key_scratch, ex->key_scratch_fstride, ex->d_key_scratch_off, st);
     if (prof) cudaEventRecord(ex->ev[3], st);
@@ -218,6 +233,14 @@ SGS_API int sgs_extractor_create(const sgs_orb_params* params, int width, int he
         d.qt.h_cell = g.h_cell; d.qt.n_target = g.n_target;
         d.scale = g.scale; d.patch_size = g.patch_size;
     }
+    // warp-per-cell FAST: tile geometry, shared-memory opt-in, TMA tensor maps of the own pyramid levels
+    ex->fast_plan = make_fast_launch_plan(PL);
+    if (ex->fast_plan.smem_bytes > 200 * 1024) ex->fast_variant = 0;
+    else TRY_OR_FREE(configure_fast_smem(ex->fast_plan.smem_bytes));
+    if (const char* v = getenv("SGS_FAST_VARIANT")) ex->fast_variant = atoi(v);
+    ex->maps_ok = true;
+    for (int l = 1; l < L && ex->maps_ok; ++l)
+        ex->maps_ok = encode_level_map(&ex->fast_maps.m[l], D.lv[l].img, D.lv[l].w, D.lv[l].h, D.lv[l].pitch, D.lv[l].fstride, max_batch, ex->fast_plan.tp, ex->fast_plan.th);
     // pinned result staging
     TRY_OR_FREE(cudaMallocHost(&ex->h_kps, sizeof(sgs_keypoint) * (size_t)(B * PL.max_kp_per_frame)));
     TRY_OR_FREE(cudaMallocHost(&ex->h_desc, (size_t)(B * PL.max_kp_per_frame) * 32));
