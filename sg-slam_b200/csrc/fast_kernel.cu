@@ -33,33 +33,29 @@ struct FastTileGeom {
     int32_t use_tma;
 };
 
-// ---- exact FAST score (see extract_kernels.cu history / DESIGN.md for the ptxas VIMNMX3 note) ----------------------------
+// ---- exact FAST score -------------------------------------------------------------------------------------------------------
+// max over the 16 contiguous 9-arcs of max(min d, -max d) - 1 with d_k = v - r_k, evaluated for d and -d at once in packed 16-bit
+// lanes biased by +256 (lo = v - r_k + 256, hi = r_k - v + 256, both in [1,511]): one IMAD builds a lane pair
+// (r_k * 0xFFFF + C), then a sliding minimum over windows of 2, 4, 8, 9 ring positions with VIMNMX.U16x2.
+// (A plain 32-bit `max(best, max(mn9, -mx9))` formulation is MISCOMPILED by CUDA 12.9 ptxas -O3 for sm_100a -- the negation is
+//  folded into a 3-input VIMNMX3 incorrectly; tools/ptxas_minmax_repro.cu reproduces it.  This form never negates a max result.)
 __device__ __forceinline__ int fast_score16(int v, const int (&r)[16]) {
+    const unsigned C = (unsigned)(v + 256) + ((unsigned)(256 - v) << 16);
     unsigned p[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int d = v - r[k];
-        p[k] = ((unsigned)d & 0xFFFFu) | ((unsigned)(-d) << 16);
-    }
-    unsigned w2[16], w4[16];
+    for (int k = 0; k < 16; ++k) p[k] = (unsigned)r[k] * 0xFFFFu + C;
+    unsigned w2[16], w4[16], w8[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) w2[k] = __vmins2(p[k], p[(k + 1) & 15]);
+    for (int k = 0; k < 16; ++k) w2[k] = __vminu2(p[k], p[(k + 1) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) w4[k] = __vmins2(w2[k], w2[(k + 2) & 15]);
-    unsigned best = 0x80008000u;
+    for (int k = 0; k < 16; ++k) w4[k] = __vminu2(w2[k], w2[(k + 2) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) best = __vmaxs2(best, __vmins2(__vmins2(w4[k], w4[(k + 4) & 15]), p[(k + 8) & 15]));
-    const int lo = (int)(short)(best & 0xFFFFu), hi = (int)(short)(best >> 16);
-    return (lo > hi ? lo : hi) - 1;
-}
-
-__device__ __forceinline__ bool arc9(uint32_t m) {
-    m |= m << 16;
-    uint32_t r = m & (m >> 1);
-    r &= r >> 2;
-    r &= r >> 4;
-    r &= m >> 8;
-    return (r & 0xFFFFu) != 0;
+    for (int k = 0; k < 16; ++k) w8[k] = __vminu2(w4[k], w4[(k + 4) & 15]);
+    unsigned best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) best = __vmaxu2(best, __vminu2(w8[k], p[(k + 8) & 15]));
+    const int lo = (int)(best & 0xFFFFu), hi = (int)(best >> 16);
+    return (lo > hi ? lo : hi) - 257;
 }
 
 // bytes of `ad` strictly greater than t (0 <= t <= 126) -> 0x80 in that byte, carry-free
@@ -121,115 +117,124 @@ __global__ void __launch_bounds__(kFastWarps * 32) fast_warp_cells_kernel(const 
     }
     __syncwarp();
 
-    const int t_lo = min(P.ini_th, P.min_th);
-    // ---- A. packed compass pre-test ----------------------------------------------------------------------------------------
+    // ---- detection at one threshold: returns the number of NMS survivors, their tile positions are list[0..n) ----------------
+    // The reference runs cv::FAST at iniTh and, only when that leaves the cell empty, again at minTh (:810-817).  Scores do not
+    // depend on the threshold, and a neighbour that is not a corner at the current threshold counts as 0 in the NMS, so each pass
+    // only needs the corners of ITS threshold: the (rare) second pass simply redoes the cell at the lower threshold.
     const int ix0 = off + 3, ix1 = off + 3 + iw;       // interior tile columns [ix0, ix1)
     const int a0 = ix0 & ~3;                            // first smem-aligned word touching the interior
     const int nw = (ix1 - a0 + 3) >> 2;                 // aligned 4-pixel words per interior row (<= 16)
     const uint32_t inv_nw = (65536u + nw - 1) / nw;     // row = item / nw by multiply-shift (exact for item < 4096)
-    const uint32_t kk = (uint32_t)(127 - (t_lo < 126 ? t_lo : 126)) * 0x01010101u;
-    int nlist = 0;                                      // warp-uniform
-    for (int i0 = 0; i0 < ih * nw; i0 += 32) {
-        const int it = i0 + lane;
-        const int row = (int)(((uint32_t)it * inv_nw) >> 16), col = it - row * nw;
-        uint32_t flags = 0;
-        int pos = 0;
-        if (it < ih * nw) {
-            pos = (row + 3) * TP + a0 + 4 * col;
-            const uint32_t* rp = reinterpret_cast<const uint32_t*>(tile + pos);
-            const uint32_t cc = rp[0], ll = rp[-1], rr = rp[1];
-            const uint32_t up = *reinterpret_cast<const uint32_t*>(tile + pos - 3 * TP);
-            const uint32_t dn = *reinterpret_cast<const uint32_t*>(tile + pos + 3 * TP);
-            const uint32_t p4 = __byte_perm(cc, rr, 0x6543), p12 = __byte_perm(ll, cc, 0x4321);
-            const uint32_t f0 = gt_flags(__vabsdiffu4(dn, cc), kk), f8 = gt_flags(__vabsdiffu4(up, cc), kk);
-            const uint32_t f4 = gt_flags(__vabsdiffu4(p4, cc), kk), f12 = gt_flags(__vabsdiffu4(p12, cc), kk);
-            flags = (f0 & f4) | (f8 & f12) | ((f0 | f4) & (f8 | f12));
-            const int x = a0 + 4 * col;
-            const int lead = ix0 - x;                   // bytes of this word left of the interior
-            const int over = x + 4 - ix1;               // bytes right of the interior
-            if (lead > 0) flags &= 0x80808080u << (8 * lead);
-            if (over > 0) flags &= 0x80808080u >> (8 * over);
-        }
-        const unsigned any = __ballot_sync(0xffffffffu, flags != 0);
-        if (any) {
-            const int cnt = __popc(flags);
-            int incl = cnt;                             // inclusive warp scan of the per-lane survivor counts
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            int dst = nlist + incl - cnt;
-            uint32_t fl = flags;
-            while (fl) {
-                const int b = (__ffs(fl) - 1) >> 3;     // byte index 0..3
-                fl &= fl - 1;
-                list[dst++] = (uint16_t)(pos + b);
+    auto detect = [&](const int t) -> int {
+        // A. packed compass pre-test (sign-agnostic superset)
+        const uint32_t kk = (uint32_t)(127 - (t < 126 ? t : 126)) * 0x01010101u;
+        int nlist = 0;                                  // warp-uniform
+        for (int i0 = 0; i0 < ih * nw; i0 += 32) {
+            const int it = i0 + lane;
+            const int row = (int)(((uint32_t)it * inv_nw) >> 16), col = it - row * nw;
+            uint32_t flags = 0;
+            int pos = 0;
+            if (it < ih * nw) {
+                pos = (row + 3) * TP + a0 + 4 * col;
+                const uint32_t* rp = reinterpret_cast<const uint32_t*>(tile + pos);
+                const uint32_t cc = rp[0], ll = rp[-1], rr = rp[1];
+                const uint32_t up = *reinterpret_cast<const uint32_t*>(tile + pos - 3 * TP);
+                const uint32_t dn = *reinterpret_cast<const uint32_t*>(tile + pos + 3 * TP);
+                const uint32_t p4 = __byte_perm(cc, rr, 0x6543), p12 = __byte_perm(ll, cc, 0x4321);
+                const uint32_t f0 = gt_flags(__vabsdiffu4(dn, cc), kk), f8 = gt_flags(__vabsdiffu4(up, cc), kk);
+                const uint32_t f4 = gt_flags(__vabsdiffu4(p4, cc), kk), f12 = gt_flags(__vabsdiffu4(p12, cc), kk);
+                flags = (f0 & f4) | (f8 & f12) | ((f0 | f4) & (f8 | f12));
+                const int x = a0 + 4 * col;
+                const int lead = ix0 - x;               // bytes of this word left of the interior
+                const int over = x + 4 - ix1;           // bytes right of the interior
+                if (lead > 0) flags &= 0x80808080u << (8 * lead);
+                if (over > 0) flags &= 0x80808080u >> (8 * over);
             }
-            nlist += __shfl_sync(0xffffffffu, incl, 31);
-        }
-    }
-    __syncwarp();
-
-    // ---- B. segment test + exact score; corners are compacted in place ------------------------------------------------------
-    int ncorner = 0;
-    for (int i0 = 0; i0 < nlist; i0 += 32) {
-        const int i = i0 + lane;
-        bool corner = false;
-        int pos = 0;
-        if (i < nlist) {
-            pos = list[i];
-            const uint8_t* p = tile + pos;
-            const int v = p[0];
-            const int hi = v + t_lo, lo = v - t_lo;
-            const int r0 = p[3 * TP], r4 = p[3], r8 = p[-3 * TP], r12 = p[-3];
-            const int nb = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi);
-            const int nd = (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo);
-            if (nb >= 2 || nd >= 2) {
-                int r[16];
-                r[0] = r0; r[4] = r4; r[8] = r8; r[12] = r12;
-                r[1] = p[3 * TP + 1]; r[2] = p[2 * TP + 2]; r[3] = p[TP + 3]; r[5] = p[-TP + 3]; r[6] = p[-2 * TP + 2]; r[7] = p[-3 * TP + 1];
-                r[9] = p[-3 * TP - 1]; r[10] = p[-2 * TP - 2]; r[11] = p[-TP - 3]; r[13] = p[TP - 3]; r[14] = p[2 * TP - 2]; r[15] = p[3 * TP - 1];
-                uint32_t mb = 0, md = 0;
+            const unsigned any = __ballot_sync(0xffffffffu, flags != 0);
+            if (any) {
+                const int cnt = __popc(flags);
+                int incl = cnt;                         // inclusive warp scan of the per-lane survivor counts
 #pragma unroll
-                for (int k = 0; k < 16; ++k) { mb |= (uint32_t)(r[k] > hi) << k; md |= (uint32_t)(r[k] < lo) << k; }
-                if (arc9(mb) || arc9(md)) {
-                    corner = true;
-                    score[pos + TP] = (uint8_t)fast_score16(v, r);
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                int dst = nlist + incl - cnt;
+                uint32_t fl = flags;
+                while (fl) {
+                    const int b = (__ffs(fl) - 1) >> 3; // byte index 0..3
+                    fl &= fl - 1;
+                    list[dst++] = (uint16_t)(pos + b);
                 }
+                nlist += __shfl_sync(0xffffffffu, incl, 31);
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, corner);
-        __syncwarp();                                    // all reads of list[i0..i0+31] done before the in-place writes
-        if (corner) list[ncorner + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;
-        ncorner += __popc(m);
-    }
-    __syncwarp();
-
-    // ---- C. NMS, threshold choice, emission ---------------------------------------------------------------------------------
-    int nkept = 0;
-    bool any_ini = false;
-    for (int i0 = 0; i0 < ncorner; i0 += 32) {
-        const int i = i0 + lane;
-        bool keep = false;
-        int pos = 0, s = 0;
-        if (i < ncorner) {
-            pos = list[i];
-            const uint8_t* q = score + pos + TP;
-            s = q[0];
-            keep = s > q[-1] && s > q[1] && s > q[-TP - 1] && s > q[-TP] && s > q[-TP + 1] && s > q[TP - 1] && s > q[TP] && s > q[TP + 1];
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        any_ini |= __any_sync(0xffffffffu, keep && s >= P.ini_th);
         __syncwarp();
-        if (keep) list[nkept + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;
-        nkept += __popc(m);
-    }
-    __syncwarp();
-    const int thr = any_ini ? P.ini_th : P.min_th;
-    int total = 0;
-    for (int i0 = 0; i0 < nkept; i0 += 32) {
-        const int i = i0 + lane;
-        const bool emit = i < nkept && score[list[i] + TP] >= thr;
-        total += __popc(__ballot_sync(0xffffffffu, emit));
-    }
+        // B1. scalar sign-aware compass re-check, survivors compacted in place
+        int nb1 = 0;
+        for (int i0 = 0; i0 < nlist; i0 += 32) {
+            const int i = i0 + lane;
+            bool pass = false;
+            int pos = 0;
+            if (i < nlist) {
+                pos = list[i];
+                const uint8_t* p = tile + pos;
+                const int v = p[0];
+                const int hi = v + t, lo = v - t;
+                const int r0 = p[3 * TP], r4 = p[3], r8 = p[-3 * TP], r12 = p[-3];
+                const int nb = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi);
+                const int nd = (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo);
+                pass = (nb >= 2) | (nd >= 2);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            __syncwarp();                               // reads of list[i0..i0+31] precede the in-place writes
+            if (pass) list[nb1 + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;
+            nb1 += __popc(m);
+        }
+        __syncwarp();
+        // B2. exact score; p is a corner at t  <=>  score >= t; corners compacted in place
+        int ncorner = 0;
+        for (int i0 = 0; i0 < nb1; i0 += 32) {
+            const int i = i0 + lane;
+            bool corner = false;
+            int pos = 0;
+            if (i < nb1) {
+                pos = list[i];
+                const uint8_t* p = tile + pos;
+                int r[16];
+                r[0] = p[3 * TP]; r[1] = p[3 * TP + 1]; r[2] = p[2 * TP + 2]; r[3] = p[TP + 3]; r[4] = p[3]; r[5] = p[-TP + 3];
+                r[6] = p[-2 * TP + 2]; r[7] = p[-3 * TP + 1]; r[8] = p[-3 * TP]; r[9] = p[-3 * TP - 1]; r[10] = p[-2 * TP - 2];
+                r[11] = p[-TP - 3]; r[12] = p[-3]; r[13] = p[TP - 3]; r[14] = p[2 * TP - 2]; r[15] = p[3 * TP - 1];
+                const int sc = fast_score16(p[0], r);
+                corner = sc >= t;
+                if (corner) score[pos + TP] = (uint8_t)sc;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, corner);
+            __syncwarp();
+            if (corner) list[ncorner + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;
+            ncorner += __popc(m);
+        }
+        __syncwarp();
+        // C. NMS against the 8 neighbours (cell-local: the score map is zero outside the interior)
+        int nkept = 0;
+        for (int i0 = 0; i0 < ncorner; i0 += 32) {
+            const int i = i0 + lane;
+            bool keep = false;
+            int pos = 0;
+            if (i < ncorner) {
+                pos = list[i];
+                const uint8_t* q = score + pos + TP;
+                const int sc = q[0];
+                keep = sc > q[-1] && sc > q[1] && sc > q[-TP - 1] && sc > q[-TP] && sc > q[-TP + 1] && sc > q[TP - 1] && sc > q[TP] && sc > q[TP + 1];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) list[nkept + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;
+            nkept += __popc(m);
+        }
+        __syncwarp();
+        return nkept;
+    };
+    int nkept = detect(P.ini_th);
+    if (nkept == 0) nkept = detect(P.min_th);
+    const int total = nkept;
     if (total == 0) return;
     int base = 0;
     if (lane == 0) base = atomicAdd(&P.cand_count[f * P.nlevels + c.level], total);
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) fast_warp_cells_kernel(const 
         const int i = i0 + lane;
         int pos = 0, s = 0;
         bool emit = false;
-        if (i < nkept) { pos = list[i]; s = score[pos + TP]; emit = s >= thr; }
+        if (i < nkept) { pos = list[i]; s = score[pos + TP]; emit = true; }
         const unsigned m = __ballot_sync(0xffffffffu, emit);
         if (emit) {
             const int y = pos / TP, x = pos - y * TP - off;         // tile column `off` == view column 0
