@@ -4,7 +4,7 @@
 //   pyramid        ComputePyramid :1108-1133 (cv::resize)          resize_level_kernel   (1 launch per level >= 1, all frames)
 //   FAST + NMS     ComputeKeyPointsOctTree :766-830 (cv::FAST)     fast_cells_kernel     (1 launch: all levels, all frames)
 //   distribution   DistributeOctTree :540-764                      quadtree_kernel       (1 launch: block per (level, frame))
-//   blur           GaussianBlur :1086-1087                         blur_level_kernel     (1 launch per level)
+//   blur           GaussianBlur :1086-1087                         blur_tile_kernel      (blur_kernel.cu, 1 launch per level)
 //   orient + BRIEF IC_Angle :78-105, computeOrbDescriptor :109-148 describe_kernel       (1 launch: warp per keypoint)
 //
 // All integer stages are bit-exact by construction; float work uses explicitly rounded intrinsics (no FMA).
@@ -325,62 +325,6 @@ cudaError_t configure_quadtree_smem(size_t smem_bytes) {
 }
 
 size_t quadtree_node_bytes(int cap) { return qt_node_bytes(cap); }
-
-// --------------------------------------------------------------------------------------------------------------------
-// GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) in OpenCV's bit-exact 8.8 fixed point: taps {18,34,48,56,48,34,18}/256,
-// horizontal sums are exact 16-bit values, the vertical pass accumulates in 32 bits and rounds once: (v + 2^15) >> 16.
-// Block = 64 x 32 output tile; the (64+6) x (32+6) input tile is staged in shared memory with the reflected border.
-// --------------------------------------------------------------------------------------------------------------------
-constexpr int kBlurTW = 64, kBlurTH = 32;
-
-__device__ __forceinline__ int reflect101(int i, int n) {
-    if (i < 0) i = -i;
-    if (i >= n) i = 2 * (n - 1) - i;
-    return i;
-}
-
-__global__ void __launch_bounds__(256) blur_level_kernel(const uint8_t* __restrict__ src, int w, int h, int spitch, int64_t sfstride,
-                                                         uint8_t* __restrict__ dst, int dpitch, int64_t dfstride) {
-    __shared__ uint8_t in[(kBlurTH + 6) * (kBlurTW + 8)];
-    __shared__ uint16_t hs[(kBlurTH + 6) * kBlurTW];
-    const uint8_t* S = src + (int64_t)blockIdx.z * sfstride;
-    uint8_t* D = dst + (int64_t)blockIdx.z * dfstride;
-    const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
-        const int ty = i / (kBlurTW + 6), tx = i - ty * (kBlurTW + 6);
-        const int gx = reflect101(min(x0 + tx - 3, w + 2), w);   // columns past the image are never used for real outputs
-        const int gy = reflect101(min(y0 + ty - 3, h + 2), h);
-        in[ty * (kBlurTW + 8) + tx] = __ldg(S + (int64_t)gy * spitch + gx);
-    }
-    __syncthreads();
-    for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
-        const int ty = i / kBlurTW, tx = i - ty * kBlurTW;
-        const uint8_t* r = in + ty * (kBlurTW + 8) + tx;
-        const int v = 18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3];
-        hs[i] = (uint16_t)v;
-    }
-    __syncthreads();
-    for (int i = tid; i < kBlurTH * kBlurTW / 4; i += 256) {
-        const int ty = i / (kBlurTW / 4), tx4 = (i - ty * (kBlurTW / 4)) * 4;
-        const int gy = y0 + ty;
-        if (gy >= h || x0 + tx4 >= w) continue;
-        uint32_t packed = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint16_t* c = hs + ty * kBlurTW + tx4 + k;
-            const uint32_t v = 18u * (c[0] + c[6 * kBlurTW]) + 34u * (c[kBlurTW] + c[5 * kBlurTW]) + 48u * (c[2 * kBlurTW] + c[4 * kBlurTW]) + 56u * c[3 * kBlurTW];
-            packed |= ((v + 32768u) >> 16) << (8 * k);
-        }
-        *reinterpret_cast<uint32_t*>(D + (int64_t)gy * dpitch + x0 + tx4) = packed;  // pitch multiple of 16: in-bounds
-    }
-}
-
-void launch_blur(const DevPlan& P, int level, cudaStream_t st) {
-    const DevLevel& L = P.lv[level];
-    dim3 grid((L.w + kBlurTW - 1) / kBlurTW, (L.h + kBlurTH - 1) / kBlurTH, P.nframes);
-    blur_level_kernel<<<grid, 256, 0, st>>>(L.img, L.w, L.h, L.pitch, L.fstride, L.blur, L.bpitch, L.bfstride);
-}
 
 // --------------------------------------------------------------------------------------------------------------------
 // Orientation (intensity centroid over the 749-pixel disc) + rotated BRIEF, one warp per keypoint.
