@@ -5,13 +5,16 @@
 //
 // Both reference loops are order dependent (a keypoint already holding a map point with Observations()>0 is skipped,
 // last writer wins).  Exact restatement in three phases per frame:
-//   1. the Frame grid (Frame::AssignFeaturesToGrid, src/Frame.cc:257-272) as a sorted key array (cell << 16 | index):
-//      ascending position in that array == the iteration order of Frame::GetFeaturesInArea (src/Frame.cc:354-407);
-//   2. every map point scores its window in parallel (one warp per point) IGNORING claims -> optimistic best;
-//   3. one warp walks the points in index order, accepts the optimistic result when its keypoint is not claimed,
-//      otherwise rescans the window with the current claims (rare), reproducing the sequential semantics exactly.
+//   1. the Frame grid (Frame::AssignFeaturesToGrid, src/Frame.cc:257-272) as a counting sort of the keypoints by cell
+//      (cell = ix*48+iy, ascending keypoint index inside a cell): ascending position in that array == the iteration order of
+//      Frame::GetFeaturesInArea (src/Frame.cc:354-407);
+//   2. every map point scores its window in parallel (one THREAD per point: windows hold a handful of candidates) IGNORING
+//      claims -> optimistic best (and second best);
+//   3. one warp resolves the points in index order, 32 at a time: a point whose optimistic keypoints are neither claimed nor
+//      tentatively claimed by an earlier point of the chunk is final; the first blocked point of a chunk is rescanned with
+//      the claims in force (rare), then the rest of the chunk is re-evaluated.  This reproduces the sequential semantics.
 // The sequential "dist < best" / "dist < second" updates keep the two smallest candidates under the order
-// (distance, iteration position); that is what the warp reductions compute.
+// (distance, iteration position): a thread walking its window in iteration order gets them with the same comparisons.
 #include <cuda_runtime.h>
 
 #include <vector>
@@ -28,81 +31,109 @@ constexpr int kThHigh = 100, kHistoLen = 30;          // src/ORBmatcher.cc:37-39
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 
 struct FrameSmem {
-    uint32_t* keys;      // [n_sort]  cell << 16 | keypoint index, sorted; kNoKey padding
+    uint16_t* order;     // [cap]  keypoint indices sorted by (cell, index)
     float* kx; float* ky; float* ur;
     uint8_t* oct;
     uint8_t* claimed;    // 1 = holds a map point with Observations() > 0
+    uint8_t* tent;       // tentative claims of the chunk being resolved (lane + 1, 0 = none)
     int32_t* cell_start; // [kGridCells + 1]
-    int n, n_sort;
+    int32_t* cursor;     // [kGridCells] scatter cursors
+    int n;
 };
 
-__device__ __forceinline__ size_t frame_smem_bytes(int cap_pow2) {
-    return (size_t)cap_pow2 * (4 + 4 + 4 + 4 + 1 + 1) + (kGridCells + 1) * 4 + 64;
+__host__ __device__ inline size_t frame_smem_bytes(int cap) {
+    const size_t c = (size_t)((cap + 15) & ~15);
+    return c * (2 + 4 + 4 + 4 + 1 + 1 + 1) + (size_t)(kGridCells + 1) * 4 + (size_t)kGridCells * 4 + 256;
 }
 
-__device__ __forceinline__ void carve(uint8_t* base, int cap_pow2, FrameSmem& s) {
-    s.keys = reinterpret_cast<uint32_t*>(base); base += (size_t)cap_pow2 * 4;
-    s.kx = reinterpret_cast<float*>(base); base += (size_t)cap_pow2 * 4;
-    s.ky = reinterpret_cast<float*>(base); base += (size_t)cap_pow2 * 4;
-    s.ur = reinterpret_cast<float*>(base); base += (size_t)cap_pow2 * 4;
+__device__ __forceinline__ void carve(uint8_t* base, int cap, FrameSmem& s) {
+    const size_t c = (size_t)((cap + 15) & ~15);
+    s.kx = reinterpret_cast<float*>(base); base += c * 4;
+    s.ky = reinterpret_cast<float*>(base); base += c * 4;
+    s.ur = reinterpret_cast<float*>(base); base += c * 4;
     s.cell_start = reinterpret_cast<int32_t*>(base); base += (size_t)(kGridCells + 1) * 4;
-    s.oct = base; base += cap_pow2;
-    s.claimed = base;
+    s.cursor = reinterpret_cast<int32_t*>(base); base += (size_t)kGridCells * 4;
+    s.order = reinterpret_cast<uint16_t*>(base); base += c * 2;
+    s.oct = base; base += c;
+    s.claimed = base; base += c;
+    s.tent = base;
 }
 
 // Frame::PosInGrid (src/Frame.cc:409-419): round() is half away from zero
 __device__ __forceinline__ int grid_round(float v) { return (int)roundf(v); }
 
+// counting sort by cell; entries of a cell end up in ascending keypoint index (== push_back order of AssignFeaturesToGrid)
 __device__ void build_frame_grid(const MatchCam& cam, const sgs_keypoint* __restrict__ kps, const float* __restrict__ uright, int n, FrameSmem& s) {
+    __shared__ int s_scan[kMatchThreads];
     const float w_inv = __fdiv_rn((float)kGridCols, __fsub_rn(cam.max_x, cam.min_x));   // Frame.cc:183-184
     const float h_inv = __fdiv_rn((float)kGridRows, __fsub_rn(cam.max_y, cam.min_y));
-    for (int i = threadIdx.x; i < s.n_sort; i += blockDim.x) {
-        uint32_t key = kNoKey;
-        if (i < n) {
-            const sgs_keypoint kp = kps[i];
-            s.kx[i] = kp.x; s.ky[i] = kp.y; s.oct[i] = (uint8_t)kp.octave; s.ur[i] = uright[i];
-            const int px = grid_round(__fmul_rn(__fsub_rn(kp.x, cam.min_x), w_inv));
-            const int py = grid_round(__fmul_rn(__fsub_rn(kp.y, cam.min_y), h_inv));
-            if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) key = ((uint32_t)(px * kGridRows + py) << 16) | (uint32_t)i;
-        }
-        s.keys[i] = key;
+    const int tid = threadIdx.x;
+    for (int c = tid; c <= kGridCells; c += kMatchThreads) s.cell_start[c] = 0;
+    __syncthreads();
+    // histogram (cell id kept in `order` temporarily is not needed: recomputed in the scatter pass)
+    for (int i = tid; i < n; i += kMatchThreads) {
+        const sgs_keypoint kp = kps[i];
+        s.kx[i] = kp.x; s.ky[i] = kp.y; s.oct[i] = (uint8_t)kp.octave; s.ur[i] = uright[i];
+        const int px = grid_round(__fmul_rn(__fsub_rn(kp.x, cam.min_x), w_inv));
+        const int py = grid_round(__fmul_rn(__fsub_rn(kp.y, cam.min_y), h_inv));
+        if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) atomicAdd(&s.cell_start[px * kGridRows + py + 1], 1);
     }
     __syncthreads();
-    for (int k = 2; k <= s.n_sort; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (s.n_sort >> 1); t += blockDim.x) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int p = i | j;
-                const bool up = ((i & k) == 0);
-                const uint32_t x = s.keys[i], y = s.keys[p];
-                if ((x > y) == up) { s.keys[i] = y; s.keys[p] = x; }
-            }
-            __syncthreads();
+    // inclusive scan of cell_start[1..kGridCells] (12 cells per thread + block scan of the partial sums)
+    constexpr int kPer = kGridCells / kMatchThreads;   // 3072 / 256 = 12
+    int local = 0;
+    for (int k = 0; k < kPer; ++k) local += s.cell_start[1 + tid * kPer + k];
+    s_scan[tid] = local;
+    __syncthreads();
+    for (int o = 1; o < kMatchThreads; o <<= 1) {
+        const int v = tid >= o ? s_scan[tid - o] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    int run = s_scan[tid] - local;
+    for (int k = 0; k < kPer; ++k) {
+        const int c = tid * kPer + k;
+        const int cnt = s.cell_start[1 + c];
+        s.cursor[c] = run;
+        run += cnt;
+        s.cell_start[1 + c] = run;
+    }
+    __syncthreads();
+    // scatter (unordered inside a cell), then order each cell's few entries by keypoint index
+    for (int i = tid; i < n; i += kMatchThreads) {
+        const int px = grid_round(__fmul_rn(__fsub_rn(s.kx[i], cam.min_x), w_inv));
+        const int py = grid_round(__fmul_rn(__fsub_rn(s.ky[i], cam.min_y), h_inv));
+        if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) s.order[atomicAdd(&s.cursor[px * kGridRows + py], 1)] = (uint16_t)i;
+    }
+    __syncthreads();
+    for (int c = tid; c < kGridCells; c += kMatchThreads) {
+        const int b = s.cell_start[c], e = s.cell_start[c + 1];
+        for (int i = b + 1; i < e; ++i) {               // insertion sort: cells hold ~0.3 keypoints on average
+            const uint16_t v = s.order[i];
+            int j = i - 1;
+            while (j >= b && s.order[j] > v) { s.order[j + 1] = s.order[j]; --j; }
+            s.order[j + 1] = v;
         }
-    for (int c = threadIdx.x; c <= kGridCells; c += blockDim.x) {
-        const uint32_t target = (uint32_t)c << 16;
-        int lo = 0, hi = s.n_sort;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.keys[mid] < target) lo = mid + 1; else hi = mid; }
-        s.cell_start[c] = lo;
     }
     __syncthreads();
 }
 
-struct Top2 { uint32_t k1, k2; };  // key = dist << 16 | position in the sorted key array; 0xFFFFFFFF = none
+struct TopK { uint32_t k[kTopK]; int ngated; };  // keys ascending; key = dist << 16 | position in the sorted array; 0xFFFFFFFF = none
 
-__device__ __forceinline__ void top2_insert(Top2& t, uint32_t k) {
-    if (k < t.k1) { t.k2 = t.k1; t.k1 = k; }
-    else if (k < t.k2) t.k2 = k;
-}
-
-__device__ __forceinline__ Top2 warp_top2(Top2 t) {
+__device__ __forceinline__ void topk_init(TopK& t) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t a1 = __shfl_xor_sync(0xffffffffu, t.k1, o), a2 = __shfl_xor_sync(0xffffffffu, t.k2, o);
-        top2_insert(t, a1);
-        top2_insert(t, a2);
+    for (int i = 0; i < kTopK; ++i) t.k[i] = 0xFFFFFFFFu;
+    t.ngated = 0;
+}
+
+__device__ __forceinline__ void topk_insert(TopK& t, uint32_t k) {   // insertion into the sorted kTopK-array (keys are unique)
+#pragma unroll
+    for (int i = 0; i < kTopK; ++i) {
+        const uint32_t lo = min(t.k[i], k);
+        k = max(t.k[i], k);
+        t.k[i] = lo;
     }
-    return t;
 }
 
 __device__ __forceinline__ int popc256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
@@ -110,14 +141,16 @@ __device__ __forceinline__ int popc256(const uint4& a0, const uint4& a1, const u
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
-// Warp-cooperative Frame::GetFeaturesInArea + the candidate loop shared by both matchers.
-//   use_claims : skip keypoints whose `claimed` flag is set (phase 3 rescans); phase 2 passes false
-//   ur_gate    : the stereo/RGB-D right-coordinate gate (ur_pred, ur_tol)
-// Returns the two smallest (dist, position) keys; *ncand accumulates |vIndices| (lane-0 value is the warp total).
-__device__ Top2 scan_window(const MatchCam& cam, const FrameSmem& s, const uint4* __restrict__ cur_desc, float x, float y, float r,
+// Frame::GetFeaturesInArea + the candidate loop shared by both matchers.  A group of `gsize` lanes (1 or kGroup) shares one
+// window: lane `gl` of the group takes the entries j = beg+gl, beg+gl+gsize, ... of every cell column; the caller min-reduces
+// the (dist, position) keys across the group, which gives exactly the sequential loop's best / second best.
+//   use_claims : skip keypoints whose `claimed` flag is set (phase-3 rescans); phase 2 passes false
+// Returns the kTopK smallest (dist, position) keys seen by this lane and how many candidates passed the gates;
+// *ncand accumulates this lane's share of |vIndices|.
+__device__ TopK scan_window(const MatchCam& cam, const FrameSmem& s, const uint4* __restrict__ cur_desc, float x, float y, float r,
                             int min_level, int max_level, const uint4& d0, const uint4& d1, bool use_claims, float ur_pred, float ur_tol,
-                            int* ncand) {
-    Top2 t; t.k1 = kNoKey; t.k2 = kNoKey;
+                            int* ncand, int gl = 0, int gsize = 1) {
+    TopK t; topk_init(t);
     const float w_inv = __fdiv_rn((float)kGridCols, __fsub_rn(cam.max_x, cam.min_x));
     const float h_inv = __fdiv_rn((float)kGridRows, __fsub_rn(cam.max_y, cam.min_y));
     const int min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, cam.min_x), r), w_inv)));
@@ -129,13 +162,12 @@ __device__ Top2 scan_window(const MatchCam& cam, const FrameSmem& s, const uint4
     const int max_cy = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, cam.min_y), r), h_inv)));
     if (max_cy < 0) return t;
     const bool check_levels = (min_level > 0) || (max_level >= 0);
-    const int lane = threadIdx.x & 31;
     int cnt = 0;
     for (int ix = min_cx; ix <= max_cx; ++ix) {
         // cells (ix, min_cy..max_cy) are contiguous in the sorted array
         const int beg = s.cell_start[ix * kGridRows + min_cy], end = s.cell_start[ix * kGridRows + max_cy + 1];
-        for (int j = beg + lane; j < end; j += 32) {
-            const int idx = (int)(s.keys[j] & 0xFFFFu);
+        for (int j = beg + gl; j < end; j += gsize) {
+            const int idx = s.order[j];
             const int o = s.oct[idx];
             if (check_levels) {
                 if (o < min_level) continue;
@@ -150,16 +182,28 @@ __device__ Top2 scan_window(const MatchCam& cam, const FrameSmem& s, const uint4
                 const float er = fabsf(__fsub_rn(ur_pred, ur));
                 if (er > ur_tol) continue;
             }
-            const int dist = popc256(d0, d1, __ldg(&cur_desc[2 * idx]), __ldg(&cur_desc[2 * idx + 1]));
-            top2_insert(t, ((uint32_t)dist << 16) | (uint32_t)j);
+            const uint32_t k = ((uint32_t)popc256(d0, d1, __ldg(&cur_desc[2 * idx]), __ldg(&cur_desc[2 * idx + 1])) << 16) | (uint32_t)j;
+            topk_insert(t, k);
+            ++t.ngated;
         }
     }
-    if (ncand) {
+    if (ncand) *ncand += cnt;
+    return t;
+}
+
+constexpr int kGroup = 4;   // lanes cooperating on one map point in phase 2
+
+__device__ __forceinline__ TopK group_topk(TopK t) {   // merge over the kGroup lanes of a group (xor butterfly stays inside it)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        *ncand += cnt;
+    for (int o = kGroup >> 1; o > 0; o >>= 1) {
+        uint32_t other[kTopK];
+#pragma unroll
+        for (int i = 0; i < kTopK; ++i) other[i] = __shfl_xor_sync(0xffffffffu, t.k[i], o);
+        t.ngated += __shfl_xor_sync(0xffffffffu, t.ngated, o);
+#pragma unroll
+        for (int i = 0; i < kTopK; ++i) topk_insert(t, other[i]);
     }
-    return warp_top2(t);
+    return t;
 }
 
 __device__ __forceinline__ void three_maxima(const int* hist, int& i1, int& i2, int& i3) {  // ORBmatcher.cc:1603-1644
@@ -175,7 +219,131 @@ __device__ __forceinline__ void three_maxima(const int* hist, int& i1, int& i2, 
     else if ((float)m3 < __fmul_rn(0.1f, (float)m1)) { i3 = -1; }
 }
 
+// First two candidates of a point's list whose keypoints are not claimed (claims only ever remove candidates, so this is what
+// the sequential loop would find); need_rescan: the list ran out although the window held more than kTopK candidates.
+__device__ __forceinline__ void select_unclaimed(const FrameSmem& s, const uint32_t (&cand)[kTopK], int ngated, int want, uint32_t& k1, uint32_t& k2,
+                                                 bool& need_rescan) {
+    k1 = kNoKey; k2 = kNoKey;
+    int found = 0;
+#pragma unroll
+    for (int c = 0; c < kTopK; ++c) {
+        const uint32_t key = cand[c];
+        if (key != kNoKey && !s.claimed[s.order[key & 0xFFFFu]]) {
+            if (found == 0) k1 = key; else if (found == 1) k2 = key;
+            ++found;
+        }
+    }
+    need_rescan = found < want && ngated > kTopK;
+}
+
+// Ordered resolution of one chunk of <= 32 points by one warp (lane == point).  `Policy` supplies:
+//   decide(keys, keypoints) -> accept + target keypoint, rescan() -> complete candidate list under the current claims,
+//   record(target) (histogram), commit(target) (writes the match and the claim).
+// Returns the number of accepted points in the chunk (warp-uniform).
+template <class Policy>
+__device__ int resolve_chunk(FrameSmem& s, Policy& pol, bool have_point, const uint32_t (&cand)[kTopK], int ngated) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1;
+    const int want = pol.uses_second() ? 2 : 1;
+    bool pending = have_point && cand[0] != kNoKey;
+    int accepted = 0;
+    for (;;) {
+        if (!__ballot_sync(0xffffffffu, pending)) break;
+        uint32_t k1 = kNoKey, k2 = kNoKey;
+        bool need_rescan = false, acc = false;
+        int i1 = -1, i2 = -1, target = -1;
+        if (pending) {
+            select_unclaimed(s, cand, ngated, want, k1, k2, need_rescan);
+            if (k1 != kNoKey) {
+                i1 = s.order[k1 & 0xFFFFu];
+                i2 = k2 != kNoKey ? (int)s.order[k2 & 0xFFFFu] : -1;
+                acc = pol.decide(k1, k2, i1, i2, target);
+            }
+        }
+        const bool claims = pending && !need_rescan && acc && pol.blocks_others();
+        {   // the lowest claiming lane per keypoint records a tentative claim
+            const unsigned same = __match_any_sync(0xffffffffu, claims ? target : -1 - lane);
+            if (claims && (same & lt) == 0) s.tent[target] = (uint8_t)(lane + 1);
+        }
+        __syncwarp();
+        bool blocked = false;
+        if (pending) {
+            blocked = need_rescan;
+            if (!blocked && k1 != kNoKey && (acc || !pol.reject_is_final())) {
+                const int t1 = s.tent[i1], t2 = (want == 2 && i2 >= 0) ? s.tent[i2] : 0;
+                blocked = (t1 != 0 && t1 - 1 < lane) || (t2 != 0 && t2 - 1 < lane);
+            }
+        }
+        const unsigned bm = __ballot_sync(0xffffffffu, blocked);
+        const int fb = bm ? __ffs(bm) - 1 : 32;
+        __syncwarp();
+        if (claims) s.tent[target] = 0;                                  // clear the scratch
+        __syncwarp();
+        // finalize every pending lane below the first blocked one
+        const bool fin = pending && lane < fb;
+        const bool fin_acc = fin && acc;
+        {
+            const unsigned fm = __ballot_sync(0xffffffffu, fin_acc);
+            if (fin_acc) {
+                const unsigned same = __match_any_sync(fm, target);
+                pol.record(target);                                       // histogram / events (order irrelevant)
+                if ((same >> lane) == 1u) pol.commit(target);             // last writer wins: highest lane of the group
+            }
+            accepted += __popc(fm);
+        }
+        if (fin) pending = false;
+        __syncwarp();
+        // the first blocked lane is next in sequence: decide it against the claims now in force
+        if (fb < 32) {
+            bool a2 = false;
+            if (lane == fb) {
+                uint32_t n1, n2; bool rs;
+                select_unclaimed(s, cand, ngated, want, n1, n2, rs);
+                if (rs) { const TopK t = pol.rescan(); n1 = t.k[0]; n2 = t.k[1]; }
+                int tgt = -1;
+                if (n1 != kNoKey) {
+                    const int j1 = s.order[n1 & 0xFFFFu];
+                    const int j2 = n2 != kNoKey ? (int)s.order[n2 & 0xFFFFu] : -1;
+                    a2 = pol.decide(n1, n2, j1, j2, tgt);
+                }
+                if (a2) { pol.record(tgt); pol.commit(tgt); }
+                pending = false;
+            }
+            accepted += __shfl_sync(0xffffffffu, a2 ? 1 : 0, fb);
+            __syncwarp();
+        }
+    }
+    return accepted;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
+struct LastPolicy {
+    const LastFrameArgs& A; FrameSmem& s; const uint4* cur_desc; const sgs_keypoint* kps; int32_t* cur_mp; int* hist; int* n_event;
+    int64_t lo; int point; PointPre pp;
+    __device__ bool uses_second() const { return false; }
+    __device__ bool reject_is_final() const { return true; }     // best distance > TH_HIGH: no candidate can be accepted
+    __device__ bool blocks_others() const { return ((A.last_flags[lo + point] >> 1) & 1) != 0; }
+    __device__ bool decide(uint32_t k1, uint32_t, int i1, int, int& target) const { target = i1; return (int)(k1 >> 16) <= kThHigh; }   // :1430
+    __device__ TopK rescan() const {
+        const uint4* dm = reinterpret_cast<const uint4*>(A.last_desc + 32 * (lo + point));
+        return scan_window(A.cam, s, cur_desc, pp.u, pp.v, pp.radius, pp.min_level, pp.max_level, __ldg(dm), __ldg(dm + 1), true,
+                           __fsub_rn(pp.u, __fmul_rn(A.cam.bf, pp.invz)), pp.radius, nullptr);
+    }
+    __device__ void record(int target) const {
+        if (!A.check_ori) return;
+        float rot = __fsub_rn(A.last_angle[lo + point], kps[target].angle);      // :1438-1443
+        if (rot < 0.f) rot = __fadd_rn(rot, 360.f);
+        int bin = (int)roundf(__fmul_rn(rot, (float)kHistoLen / 360.0f));
+        if (bin == kHistoLen) bin = 0;
+        atomicAdd(&hist[bin], 1);
+        A.events[lo + atomicAdd(n_event, 1)] = (bin << 16) | target;
+    }
+    __device__ void commit(int target) const {
+        cur_mp[target] = point;                                                   // :1432 last writer wins
+        s.claimed[target] = (A.last_flags[lo + point] >> 1) & 1;
+    }
+};
+
 __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __grid_constant__ LastFrameArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int hist[kHistoLen];
@@ -185,9 +353,8 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
     const int n = min(A.cur_n[f], A.cur_cap);
     const int nlast = min(A.last_n[f], A.last_cap);
     FrameSmem s;
-    carve(smem, A.cur_cap_pow2, s);
-    s.n = n; s.n_sort = 1;
-    while (s.n_sort < n) s.n_sort <<= 1;
+    carve(smem, A.cur_cap, s);
+    s.n = n;
     const sgs_keypoint* kps = A.cur_kps + (int64_t)f * A.cur_cap;
     const uint4* cur_desc = reinterpret_cast<const uint4*>(A.cur_desc + (int64_t)f * A.cur_cap * 32);
     int32_t* cur_mp = A.cur_mp + (int64_t)f * A.cur_cap;
@@ -215,16 +382,20 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const bool has = cur_mp[i] >= 0;
         s.claimed[i] = has ? (A.cur_mp_obs_in ? A.cur_mp_obs_in[(int64_t)f * A.cur_cap + i] : 1) : 0;
+        s.tent[i] = 0;
     }
     __syncthreads();
     const bool fwd = s_pose[12] != 0.f, bwd = s_pose[13] != 0.f;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     PointPre* pre = A.pre + lo;
     int ncand = 0;
-    // phase 2: optimistic scoring, one warp per last-frame point
-    for (int i = warp; i < nlast; i += nwarps) {
-        PointPre pp; pp.valid = 0; pp.best_key = kNoKey; pp.u = pp.v = pp.invz = pp.radius = 0.f; pp.min_level = pp.max_level = 0;
-        if (A.last_flags[lo + i] & 1) {
+    // phase 2: optimistic scoring, kGroup lanes per last-frame point (uniform trip count so that the group shuffles are safe)
+    const int gl = threadIdx.x & (kGroup - 1);
+    const int ngroups = blockDim.x / kGroup;
+    for (int i0 = 0; i0 < nlast; i0 += ngroups) {
+        const int i = i0 + threadIdx.x / kGroup;
+        PointPre pp; pp.valid = 0; pp.ngated = 0; pp.u = pp.v = pp.invz = pp.radius = 0.f; pp.min_level = pp.max_level = 0;
+        TopK t; topk_init(t);
+        if (i < nlast && (A.last_flags[lo + i] & 1)) {
             const float* X = A.last_xyz + 3 * (lo + i);
             float xc[3];
 #pragma unroll
@@ -244,75 +415,92 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
                     if (fwd) { mn = oct; mx = -1; } else if (bwd) { mn = 0; mx = oct; } else { mn = oct - 1; mx = oct + 1; }
                     pp.valid = 1; pp.u = u; pp.v = v; pp.invz = invz; pp.radius = radius; pp.min_level = mn; pp.max_level = mx;
                     const uint4* dm = reinterpret_cast<const uint4*>(A.last_desc + 32 * (lo + i));
-                    const uint4 d0 = __ldg(dm), d1 = __ldg(dm + 1);
                     const float ur_pred = __fsub_rn(u, __fmul_rn(A.cam.bf, invz));
-                    const Top2 t = scan_window(A.cam, s, cur_desc, u, v, radius, mn, mx, d0, d1, false, ur_pred, radius, &ncand);
-                    pp.best_key = t.k1;
+                    t = scan_window(A.cam, s, cur_desc, u, v, radius, mn, mx, __ldg(dm), __ldg(dm + 1), false, ur_pred, radius, &ncand, gl, kGroup);
                 }
             }
         }
-        if (lane == 0) pre[i] = pp;
+        t = group_topk(t);
+#pragma unroll
+        for (int c = 0; c < kTopK; ++c) pp.k[c] = t.k[c];
+        pp.ngated = (int16_t)min(t.ngated, 32767);
+        if (gl == 0 && i < nlast) pre[i] = pp;
     }
     __syncthreads();
-    // phase 3: sequential resolution by warp 0
-    if (warp == 0) {
-        int nmatch = 0, nevent = 0;
-        for (int i = 0; i < nlast; ++i) {
-            const PointPre pp = pre[i];
-            if (!pp.valid || pp.best_key == kNoKey) {
-                // no candidate survived the optimistic scan; with claims there are even fewer: nothing to do.
-                continue;
-            }
-            uint32_t key = pp.best_key;
-            int idx = (int)(s.keys[key & 0xFFFFu] & 0xFFFFu);
-            if (s.claimed[idx]) {
-                const uint4* dm = reinterpret_cast<const uint4*>(A.last_desc + 32 * (lo + i));
-                const uint4 d0 = __ldg(dm), d1 = __ldg(dm + 1);
-                const float ur_pred = __fsub_rn(pp.u, __fmul_rn(A.cam.bf, pp.invz));
-                const Top2 t = scan_window(A.cam, s, cur_desc, pp.u, pp.v, pp.radius, pp.min_level, pp.max_level, d0, d1, true, ur_pred, pp.radius, nullptr);
-                key = t.k1;
-                if (key == kNoKey) continue;
-                idx = (int)(s.keys[key & 0xFFFFu] & 0xFFFFu);
-            }
-            const int dist = (int)(key >> 16);
-            if (dist <= kThHigh) {
-                if (lane == 0) {
-                    cur_mp[idx] = i;                                                  // :1432 last writer wins
-                    s.claimed[idx] = (A.last_flags[lo + i] >> 1) & 1;
-                    if (A.check_ori) {
-                        float rot = __fsub_rn(A.last_angle[lo + i], kps[idx].angle);
-                        if (rot < 0.f) rot = __fadd_rn(rot, 360.f);
-                        int bin = (int)roundf(__fmul_rn(rot, (float)kHistoLen / 360.0f));
-                        if (bin == kHistoLen) bin = 0;
-                        hist[bin]++;
-                        A.events[lo + nevent] = (bin << 16) | idx;
-                    }
-                }
-                ++nmatch; ++nevent;
-                __syncwarp();
-            }
+    // phase 3: ordered resolution by warp 0, 32 points at a time
+    if (threadIdx.x < 32) {
+        int nmatch = 0;
+        for (int c0 = 0; c0 < nlast; c0 += 32) {
+            const int i = c0 + threadIdx.x;
+            LastPolicy pol{A, s, cur_desc, kps, cur_mp, hist, &s_nevent, lo, i, PointPre()};
+            bool have = false;
+            if (i < nlast) { pol.pp = pre[i]; have = pol.pp.valid != 0; }
+            else { for (int c = 0; c < kTopK; ++c) pol.pp.k[c] = kNoKey; }
+            nmatch += resolve_chunk(s, pol, have, pol.pp.k, pol.pp.ngated);
         }
-        if (lane == 0) { s_nmatch = nmatch; s_nevent = nevent; }
+        if (threadIdx.x == 0) s_nmatch = nmatch;
     }
     __syncthreads();
-    if (A.check_ori && threadIdx.x == 0) {
+    if (A.check_ori) {                                             // :1451-1470, order independent
         int i1, i2, i3;
         three_maxima(hist, i1, i2, i3);
-        int nm = s_nmatch;
-        for (int e = 0; e < s_nevent; ++e) {
+        int removed = 0;
+        for (int e = threadIdx.x; e < s_nevent; e += blockDim.x) {
             const int ev = A.events[lo + e];
             const int bin = ev >> 16, idx = ev & 0xFFFF;
-            if (bin != i1 && bin != i2 && bin != i3) { cur_mp[idx] = -1; --nm; }       // :1451-1470
+            if (bin != i1 && bin != i2 && bin != i3) { cur_mp[idx] = -1; ++removed; }
         }
-        s_nmatch = nm;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0 && removed) atomicSub(&s_nmatch, removed);
     }
     __syncthreads();
     // totals
-    if (lane == 0 && ncand) atomicAdd((unsigned long long*)&A.ncand[f], (unsigned long long)ncand);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+    if ((threadIdx.x & 31) == 0 && ncand) atomicAdd(&A.ncand[f], (unsigned long long)ncand);
     if (threadIdx.x == 0) A.nmatches[f] = s_nmatch;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+struct LocalPolicy {
+    const LocalMapArgs& A; FrameSmem& s; const uint4* cur_desc; int32_t* f_mp; uint8_t* f_obs; int64_t lo; int point;
+    __device__ bool uses_second() const { return true; }
+    __device__ bool reject_is_final() const { return false; }    // a ratio-test rejection can flip once a top-2 keypoint is claimed
+    __device__ bool blocks_others() const { return A.mp_obs[lo + point] != 0; }
+    __device__ bool decide(uint32_t k1, uint32_t k2, int i1, int i2, int& target) const {
+        target = i1;
+        const int best_dist = (int)(k1 >> 16);
+        if (best_dist > kThHigh) return false;                                                     // :116
+        const int best_level = s.oct[i1];
+        int best_level2 = -1, best_dist2 = 256;
+        if (i2 >= 0) { best_dist2 = (int)(k2 >> 16); best_level2 = s.oct[i2]; }
+        if (best_level == best_level2 && (float)best_dist > __fmul_rn(A.nnratio, (float)best_dist2)) return false;   // :118-119
+        return true;
+    }
+    __device__ void window(float& rr, int& lvl) const {
+        lvl = A.level[lo + point];
+        float r = ((double)A.view_cos[lo + point] > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos :131-137 (compared in double)
+        if (A.th != 1.0f) r = __fmul_rn(r, A.th);                           // bFactor :50,:67-68
+        rr = __fmul_rn(r, A.cam.scale[lvl]);
+    }
+    __device__ TopK rescan() const {
+        float rr; int lvl;
+        window(rr, lvl);
+        const uint4* dm = reinterpret_cast<const uint4*>(A.mp_desc + 32 * (lo + point));
+        return scan_window(A.cam, s, cur_desc, A.proj_x[lo + point], A.proj_y[lo + point], rr, lvl - 1, lvl, __ldg(dm), __ldg(dm + 1), true,
+                           A.proj_xr[lo + point], rr, nullptr);
+    }
+    __device__ void record(int) const {}
+    __device__ void commit(int target) const {
+        f_mp[target] = A.id_base + point;
+        const uint8_t ob = A.mp_obs[lo + point];
+        f_obs[target] = ob;
+        s.claimed[target] = ob ? 1 : 0;
+    }
+};
+
 __global__ void __launch_bounds__(kMatchThreads) match_localmap_kernel(const __grid_constant__ LocalMapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int s_nmatch;
@@ -320,84 +508,65 @@ __global__ void __launch_bounds__(kMatchThreads) match_localmap_kernel(const __g
     const int n = min(A.cur_n[f], A.cur_cap);
     const int nmp = min(A.mp_n[f], A.mp_cap);
     FrameSmem s;
-    carve(smem, A.cur_cap_pow2, s);
-    s.n = n; s.n_sort = 1;
-    while (s.n_sort < n) s.n_sort <<= 1;
+    carve(smem, A.cur_cap, s);
+    s.n = n;
     const sgs_keypoint* kps = A.cur_kps + (int64_t)f * A.cur_cap;
     const uint4* cur_desc = reinterpret_cast<const uint4*>(A.cur_desc + (int64_t)f * A.cur_cap * 32);
     int32_t* f_mp = A.f_mp + (int64_t)f * A.cur_cap;
     uint8_t* f_obs = A.f_mp_obs + (int64_t)f * A.cur_cap;
     const int64_t lo = (int64_t)f * A.mp_cap;
     build_frame_grid(A.cam, kps, A.cur_uright + (int64_t)f * A.cur_cap, n, s);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s.claimed[i] = (f_mp[i] >= 0 && f_obs[i]) ? 1 : 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { s.claimed[i] = (f_mp[i] >= 0 && f_obs[i]) ? 1 : 0; s.tent[i] = 0; }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const bool b_factor = A.th != 1.0f;
     LocalPre* pre = A.pre + lo;
     int ncand = 0;
-    for (int i = warp; i < nmp; i += nwarps) {
-        LocalPre pp; pp.k1 = kNoKey; pp.k2 = kNoKey;
-        if (A.mp_inview[lo + i]) {
-            const int lvl = A.level[lo + i];
-            float r = ((double)A.view_cos[lo + i] > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos :131-137 (compared in double)
-            if (b_factor) r = __fmul_rn(r, A.th);
-            const float rr = __fmul_rn(r, A.cam.scale[lvl]);
+    const int gl = threadIdx.x & (kGroup - 1);
+    const int ngroups = blockDim.x / kGroup;
+    for (int i0 = 0; i0 < nmp; i0 += ngroups) {
+        const int i = i0 + threadIdx.x / kGroup;
+        TopK t; topk_init(t);
+        if (i < nmp && A.mp_inview[lo + i]) {
+            LocalPolicy pol{A, s, cur_desc, f_mp, f_obs, lo, i};
+            float rr; int lvl;
+            pol.window(rr, lvl);
             const uint4* dm = reinterpret_cast<const uint4*>(A.mp_desc + 32 * (lo + i));
-            const Top2 t = scan_window(A.cam, s, cur_desc, A.proj_x[lo + i], A.proj_y[lo + i], rr, lvl - 1, lvl, __ldg(dm), __ldg(dm + 1), false,
-                                       A.proj_xr[lo + i], rr, &ncand);
-            pp.k1 = t.k1; pp.k2 = t.k2;
+            t = scan_window(A.cam, s, cur_desc, A.proj_x[lo + i], A.proj_y[lo + i], rr, lvl - 1, lvl, __ldg(dm), __ldg(dm + 1), false,
+                            A.proj_xr[lo + i], rr, &ncand, gl, kGroup);
         }
-        if (lane == 0) pre[i] = pp;
+        t = group_topk(t);
+        if (gl == 0 && i < nmp) {
+            LocalPre pp;
+#pragma unroll
+            for (int c = 0; c < kTopK; ++c) pp.k[c] = t.k[c];
+            pp.ngated = t.ngated;
+            pre[i] = pp;
+        }
     }
     __syncthreads();
-    if (warp == 0) {
+    if (threadIdx.x < 32) {
         int nmatch = 0;
-        for (int i = 0; i < nmp; ++i) {
-            LocalPre pp = pre[i];
-            if (pp.k1 == kNoKey) continue;
-            // the optimistic top-2 is exact unless one of the two keypoints has been claimed in the meantime
-            const int i1 = (int)(s.keys[pp.k1 & 0xFFFFu] & 0xFFFFu);
-            const int i2 = pp.k2 != kNoKey ? (int)(s.keys[pp.k2 & 0xFFFFu] & 0xFFFFu) : -1;
-            if (s.claimed[i1] || (i2 >= 0 && s.claimed[i2])) {
-                const int lvl = A.level[lo + i];
-                float r = ((double)A.view_cos[lo + i] > 0.998) ? 2.5f : 4.0f;
-                if (b_factor) r = __fmul_rn(r, A.th);
-                const float rr = __fmul_rn(r, A.cam.scale[lvl]);
-                const uint4* dm = reinterpret_cast<const uint4*>(A.mp_desc + 32 * (lo + i));
-                const Top2 t = scan_window(A.cam, s, cur_desc, A.proj_x[lo + i], A.proj_y[lo + i], rr, lvl - 1, lvl, __ldg(dm), __ldg(dm + 1), true,
-                                           A.proj_xr[lo + i], rr, nullptr);
-                pp.k1 = t.k1; pp.k2 = t.k2;
-                if (pp.k1 == kNoKey) continue;
-            }
-            const int best_dist = (int)(pp.k1 >> 16);
-            if (best_dist <= kThHigh) {
-                const int bi = (int)(s.keys[pp.k1 & 0xFFFFu] & 0xFFFFu);
-                const int best_level = s.oct[bi];
-                int best_level2 = -1, best_dist2 = 256;
-                if (pp.k2 != kNoKey) { best_dist2 = (int)(pp.k2 >> 16); best_level2 = s.oct[s.keys[pp.k2 & 0xFFFFu] & 0xFFFFu]; }
-                if (best_level == best_level2 && (float)best_dist > __fmul_rn(A.nnratio, (float)best_dist2)) continue;   // :118-119
-                if (lane == 0) {
-                    f_mp[bi] = A.id_base + i;
-                    const uint8_t ob = A.mp_obs[lo + i];
-                    f_obs[bi] = ob;
-                    s.claimed[bi] = ob ? 1 : 0;
-                }
-                ++nmatch;
-                __syncwarp();
-            }
+        for (int c0 = 0; c0 < nmp; c0 += 32) {
+            const int i = c0 + threadIdx.x;
+            LocalPolicy pol{A, s, cur_desc, f_mp, f_obs, lo, i};
+            LocalPre pp;
+            if (i < nmp) pp = pre[i];
+            else { for (int c = 0; c < kTopK; ++c) pp.k[c] = kNoKey; pp.ngated = 0; }
+            nmatch += resolve_chunk(s, pol, i < nmp, pp.k, pp.ngated);
         }
-        if (lane == 0) s_nmatch = nmatch;
+        if (threadIdx.x == 0) s_nmatch = nmatch;
     }
     __syncthreads();
-    if (lane == 0 && ncand) atomicAdd((unsigned long long*)&A.ncand[f], (unsigned long long)ncand);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+    if ((threadIdx.x & 31) == 0 && ncand) atomicAdd(&A.ncand[f], (unsigned long long)ncand);
     if (threadIdx.x == 0) A.nmatches[f] = s_nmatch;
 }
 
-size_t match_smem_bytes(int cap_pow2) { return (size_t)cap_pow2 * (4 + 4 + 4 + 4 + 1 + 1) + (kGridCells + 1) * 4 + 64; }
+size_t match_smem_bytes(int cap) { return frame_smem_bytes(cap); }
 
 int launch_match_lastframe(const LastFrameArgs& A, int nframes, cudaStream_t st) {
-    const size_t smem = match_smem_bytes(A.cur_cap_pow2);
-    if (smem > 200 * 1024) { set_error("match: cur_cap %d too large for shared memory", A.cur_cap); return SGS_ERR_UNSUPPORTED; }
+    const size_t smem = match_smem_bytes(A.cur_cap);
+    if (smem > 200 * 1024 || A.cur_cap > 65535) { set_error("match: cur_cap %d too large for shared memory", A.cur_cap); return SGS_ERR_UNSUPPORTED; }
     SGS_CUDA_TRY(cudaFuncSetAttribute(match_lastframe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     match_lastframe_kernel<<<nframes, kMatchThreads, smem, st>>>(A);
     SGS_CUDA_TRY(cudaGetLastError());
@@ -405,8 +574,8 @@ int launch_match_lastframe(const LastFrameArgs& A, int nframes, cudaStream_t st)
 }
 
 int launch_match_localmap(const LocalMapArgs& A, int nframes, cudaStream_t st) {
-    const size_t smem = match_smem_bytes(A.cur_cap_pow2);
-    if (smem > 200 * 1024) { set_error("match: cur_cap %d too large for shared memory", A.cur_cap); return SGS_ERR_UNSUPPORTED; }
+    const size_t smem = match_smem_bytes(A.cur_cap);
+    if (smem > 200 * 1024 || A.cur_cap > 65535) { set_error("match: cur_cap %d too large for shared memory", A.cur_cap); return SGS_ERR_UNSUPPORTED; }
     SGS_CUDA_TRY(cudaFuncSetAttribute(match_localmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     match_localmap_kernel<<<nframes, kMatchThreads, smem, st>>>(A);
     SGS_CUDA_TRY(cudaGetLastError());

@@ -14,14 +14,17 @@ struct MatchCam {                 // Frame statics (src/Frame.cc:176-196) + the 
     float scale[kMaxLevels];
 };
 
+constexpr int kTopK = 4;          // candidates kept per map point by the optimistic scan
+
 struct PointPre {                 // phase-2 result of one last-frame point
-    uint32_t best_key;            // dist << 16 | position in the sorted grid array; 0xFFFFFFFF = none
+    uint32_t k[kTopK];            // ascending (dist << 16 | position in the sorted grid array); 0xFFFFFFFF = none
     float u, v, invz, radius;
     int16_t min_level, max_level;
-    int32_t valid;
+    int16_t valid;
+    int16_t ngated;               // candidates that passed every gate except claims (complete list iff <= kTopK)
 };
 
-struct LocalPre { uint32_t k1, k2; };
+struct LocalPre { uint32_t k[kTopK]; int32_t ngated; };
 
 struct LastFrameArgs {
     MatchCam cam;
