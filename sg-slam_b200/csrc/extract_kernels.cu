@@ -336,34 +336,41 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ D
     const int f = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = blockIdx.x * 8 + warp;
-    // locate keypoint k of this frame: levels are concatenated 0..L-1 (:1076-1105)
-    int total = 0, level = -1, idx = 0;
-    for (int l = 0; l < P.nlevels; ++l) {
-        const int nl = min(P.kp_stage_n[f * P.nlevels + l], P.lv[l].kp_cap);
-        if (level < 0 && k < total + nl) { level = l; idx = k - total; }
-        total += nl;
-    }
+    // locate keypoint k of this frame: levels are concatenated 0..L-1 (:1076-1105); lane l holds the count of level l
+    int nl = 0;
+    if (lane < P.nlevels) nl = min(P.kp_stage_n[f * P.nlevels + lane], P.lv[lane].kp_cap);
+    int incl = nl;
+#pragma unroll
+    for (int o = 1; o < kMaxLevels; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, P.nlevels - 1);
+    const unsigned below = __ballot_sync(0xffffffffu, lane < P.nlevels && incl <= k);   // levels entirely before keypoint k
+    const int level = __popc(below);
+    const int idx = k - (level ? __shfl_sync(0xffffffffu, incl, level ? level - 1 : 0) : 0);
     if (k == 0 && lane == 0) {
         P.out_count[f] = min(total, P.out_cap);
         if (total > P.out_cap) atomicExch(P.error_flag, 2);
     }
-    if (level < 0 || k >= P.out_cap) return;
+    if (k >= total || k >= P.out_cap) return;
     const DevLevel& L = P.lv[level];
     const uint32_t c = P.kp_stage[(int64_t)f * P.kp_stage_per_frame + L.kp_off + idx];
     const int kx = qt_x(c) + kMinBorder, ky = qt_y(c) + kMinBorder;
-    // --- IC_Angle ---
+    // --- IC_Angle: lane == patch column u = lane-15; every row is one coalesced <= 31-byte segment ---
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int dy = lane - 15;
-        const int d = P.umax[dy < 0 ? -dy : dy];
-        const uint8_t* row = L.img + (int64_t)f * L.fstride + (int64_t)(ky + dy) * L.pitch + kx;
-        int s = 0;
-        for (int u = -d; u <= d; ++u) {
-            const int v = __ldg(row + u);
-            m10 += u * v;
-            s += v;
+    {
+        const int u = lane - 15;
+        const int au = u < 0 ? -u : u;
+        const uint8_t* ctr = L.img + (int64_t)f * L.fstride + (int64_t)ky * L.pitch + kx + u;
+        int colsum = 0;
+#pragma unroll
+        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+            const int d = P.umax[v < 0 ? -v : v];
+            if (lane < 31 && au <= d) {
+                const int val = __ldg(ctr + (int64_t)v * L.pitch);
+                colsum += val;
+                m01 += v * val;
+            }
         }
-        m01 = dy * s;
+        m10 = u * colsum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -374,7 +381,10 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ D
     // --- rotated BRIEF ---
     const float factor_pi = (float)(3.14159265358979323846 / (double)180.f);
     const float ang = __fmul_rn(angle, factor_pi);
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    float cs = 0.f;                                   // lane 0: cos, lane 1: sin (FP64 libm calls are long: do them once)
+    if (lane == 0) cs = (float)cos((double)ang);
+    if (lane == 1) cs = (float)sin((double)ang);
+    const float a = __shfl_sync(0xffffffffu, cs, 0), b = __shfl_sync(0xffffffffu, cs, 1);
     const uint8_t* center = L.blur + (int64_t)f * L.bfstride + (int64_t)ky * L.bpitch + kx;
     __align__(16) int8_t pat[32];
     *reinterpret_cast<int4*>(pat) = __ldg(reinterpret_cast<const int4*>(g_pattern + lane * 32));
