@@ -1,0 +1,105 @@
+// test_shim.cpp -- compiles the reference-shaped C++ headers (include/sgslam/*.h) without OpenCV and drives them on the GPU.
+// Scenario + expected results come from files written by tests/test_gpu_cpp_shim.py (expected = CPU oracle).
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <vector>
+
+#include "sgslam/FrameDynamic.h"
+#include "sgslam/ORBextractor.h"
+#include "sgslam/ORBmatcher.h"
+
+using namespace ORB_SLAM2;
+
+// ---- structs with the member names of the reference's MapPoint / Frame (include/MapPoint.h, include/Frame.h) -------------
+struct MapPoint {
+    cv::Mat pos, desc; int nobs = 1; bool bad = false;
+    bool mbTrackInView = false; float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackViewCos = 1; int mnTrackScaleLevel = 0;
+    cv::Mat GetWorldPos() { return pos; }
+    cv::Mat GetDescriptor() { return desc; }
+    int Observations() { return nobs; }
+    bool isBad() { return bad; }
+};
+struct Frame {
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+    std::vector<float> mvuRight;
+    cv::Mat mDescriptors, mTcw;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    std::vector<float> mvScaleFactors;
+    float mbf = 40.f;
+    static float fx, fy, cx, cy, mnMinX, mnMinY, mnMaxX, mnMaxY;
+};
+float Frame::fx = 535.4f, Frame::fy = 539.2f, Frame::cx = 320.1f, Frame::cy = 247.6f, Frame::mnMinX = 0, Frame::mnMinY = 0, Frame::mnMaxX = 640, Frame::mnMaxY = 480;
+
+template <class T> std::vector<T> rd(std::ifstream& f, size_t n) { std::vector<T> v(n); f.read(reinterpret_cast<char*>(v.data()), n * sizeof(T)); return v; }
+static int fail(const char* what) { std::printf("FAIL %s\n", what); return 1; }
+
+int main(int argc, char** argv) {
+    if (argc < 2) return fail("usage: test_shim <scenario.bin>");
+    std::ifstream f(argv[1], std::ios::binary);
+    int32_t hdr[8]; f.read(reinterpret_cast<char*>(hdr), sizeof hdr);
+    const int W = hdr[0], H = hdr[1], nkp = hdr[2], ncur = hdr[3], nlast = hdr[4], exp_nm = hdr[5], exp_keep = hdr[6];
+    // 1. extractor
+    std::vector<uint8_t> img = rd<uint8_t>(f, (size_t)W * H);
+    std::vector<cv::KeyPoint> exp_kps = rd<cv::KeyPoint>(f, nkp);
+    std::vector<uint8_t> exp_desc = rd<uint8_t>(f, (size_t)nkp * 32);
+    ORBextractor ex(1000, 1.2f, 8, 20, 7);
+    cv::Mat im(H, W, CV_8UC1, img.data(), W), d;
+    std::vector<cv::KeyPoint> kps;
+    ex(im, cv::Mat(), kps, d);
+    if ((int)kps.size() != nkp) return fail("extractor: keypoint count");
+    if (std::memcmp(kps.data(), exp_kps.data(), (size_t)nkp * sizeof(cv::KeyPoint))) return fail("extractor: keypoints");
+    for (int i = 0; i < nkp; ++i) if (std::memcmp(d.ptr<uint8_t>(i), &exp_desc[(size_t)i * 32], 32)) return fail("extractor: descriptors");
+    if (ex.GetLevels() != 8 || ex.GetScaleFactors().size() != 8) return fail("extractor: getters");
+    // 2. SearchByProjection(cur, last)
+    Frame cur, last;
+    cur.N = ncur; last.N = nlast;
+    cur.mvKeysUn = rd<cv::KeyPoint>(f, ncur); cur.mvKeys = cur.mvKeysUn;
+    cur.mvuRight = rd<float>(f, ncur);
+    std::vector<uint8_t> cd = rd<uint8_t>(f, (size_t)ncur * 32);
+    cur.mDescriptors = cv::Mat(ncur, 32, CV_8U, cd.data(), 32);
+    cur.mvScaleFactors = rd<float>(f, 8); last.mvScaleFactors = cur.mvScaleFactors;
+    std::vector<float> tc = rd<float>(f, 16), tl = rd<float>(f, 16);
+    cur.mTcw = cv::Mat(4, 4, CV_32F, tc.data(), 16); last.mTcw = cv::Mat(4, 4, CV_32F, tl.data(), 16);
+    cur.mvpMapPoints.assign(ncur, nullptr);
+    std::vector<uint8_t> has = rd<uint8_t>(f, nlast), obs = rd<uint8_t>(f, nlast);
+    std::vector<float> xyz = rd<float>(f, (size_t)nlast * 3);
+    std::vector<uint8_t> ld = rd<uint8_t>(f, (size_t)nlast * 32);
+    std::vector<int32_t> oct = rd<int32_t>(f, nlast);
+    std::vector<float> ang = rd<float>(f, nlast);
+    std::vector<int32_t> exp_mp = rd<int32_t>(f, ncur);
+    std::vector<MapPoint> pts(nlast);
+    last.mvKeys.resize(nlast); last.mvKeysUn.resize(nlast); last.mvpMapPoints.assign(nlast, nullptr); last.mvbOutlier.assign(nlast, false);
+    for (int i = 0; i < nlast; ++i) {
+        pts[i].pos = cv::Mat(3, 1, CV_32F, &xyz[(size_t)i * 3], 4); pts[i].desc = cv::Mat(1, 32, CV_8U, &ld[(size_t)i * 32], 32); pts[i].nobs = obs[i];
+        last.mvKeys[i].octave = oct[i]; last.mvKeysUn[i].angle = ang[i];
+        if (has[i]) last.mvpMapPoints[i] = &pts[i];
+    }
+    ORBmatcher matcher(0.9f, true);
+    const int nm = matcher.SearchByProjection(cur, last, 15.f, false);
+    if (nm != exp_nm) { std::printf("nmatches %d expected %d\n", nm, exp_nm); return fail("SearchByProjection: count"); }
+    for (int j = 0; j < ncur; ++j) {
+        const int got = cur.mvpMapPoints[j] ? (int)(cur.mvpMapPoints[j] - pts.data()) : -1;
+        if (got != exp_mp[j]) return fail("SearchByProjection: assignment");
+    }
+    // 3. dyn-reject compaction
+    const int nd = hdr[7];
+    std::vector<cv::KeyPoint> dk = rd<cv::KeyPoint>(f, nd);
+    std::vector<uint8_t> dd = rd<uint8_t>(f, (size_t)nd * 32);
+    std::vector<cv::Point2f> prev = rd<cv::Point2f>(f, nd);
+    std::vector<double> Fm = rd<double>(f, 9);
+    std::vector<float> bx = rd<float>(f, 8);
+    std::vector<uint8_t> exp_keepmask = rd<uint8_t>(f, nd);
+    cv::Mat ddm(nd, 32, CV_8U, dd.data(), 32); cv::Mat ddc = ddm.clone();
+    cv::Mat Fmat(3, 3, CV_64F, Fm.data(), 24);
+    std::vector<cv::Rect_<float> > boxes = {cv::Rect_<float>(bx[0], bx[1], bx[2], bx[3]), cv::Rect_<float>(bx[4], bx[5], bx[6], bx[7])};
+    std::vector<cv::KeyPoint> dk2 = dk;
+    const int kept = RmDynamicPointsGeometry(dk2, ddc, prev, Fmat, boxes, true, 1000);
+    if (kept != exp_keep || (int)dk2.size() != exp_keep) return fail("dynreject: count");
+    int w = 0;
+    for (int i = 0; i < nd; ++i) if (exp_keepmask[i]) { if (std::memcmp(&dk2[w], &dk[i], sizeof(cv::KeyPoint)) || std::memcmp(ddc.ptr<uint8_t>(w), &dd[(size_t)i * 32], 32)) return fail("dynreject: compaction"); ++w; }
+    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept\n", nkp, nm, kept, nd);
+    return 0;
+}
