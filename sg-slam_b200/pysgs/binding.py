@@ -71,6 +71,7 @@ ABI_SYMBOLS = [
     'sgs_match_project_lastframe_batch_device', 'sgs_match_project_localmap_batch_device',
     'sgs_dynreject', 'sgs_dynreject_batch_device',
     'sgs_tracker_create', 'sgs_tracker_destroy', 'sgs_tracker_max_keypoints', 'sgs_tracker_extract', 'sgs_tracker_track',
+    'sgs_tracker_extract_device', 'sgs_tracker_track_device', 'sgs_tracker_results_device', 'sgs_tracker_extractor',
     'sgs_extractor_set_profiling', 'sgs_extractor_stage_times',
 ]
 
