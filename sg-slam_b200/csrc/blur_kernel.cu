@@ -33,24 +33,34 @@ __global__ void __launch_bounds__(256) blur_tile_kernel(const uint8_t* __restric
     uint8_t* D = dst + (int64_t)blockIdx.z * dfstride;
     const int x0 = blockIdx.x * kBTW, y0 = blockIdx.y * kBTH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- 1. input tile -------------------------------------------------------------------------------------------------------
-    for (int r = warp; r < kBInRows; r += 8) {
-        const int gy_raw = y0 - 3 + r;
-        const int gy = refl101(min(gy_raw, h + 2), h);
-        const uint8_t* row = S + (int64_t)gy * spitch;
-        for (int wi = lane; wi < kBInWords; wi += 32) {
+    // ---- 1. input tile ------------------------------------------------------------------------------------------------------
+    // 1a: every word that lies completely inside the image row: one aligned 32-bit load (rows are reflected, columns are not)
+    for (int it = threadIdx.x; it < kBInRows * kBInWords; it += 256) {
+        const int r = it / kBInWords, wi = it - r * kBInWords;
+        const int x = x0 - 4 + 4 * wi;
+        if (aligned4 && x >= 0 && x + 3 < w) {
+            const int gy = refl101(min(y0 - 3 + r, h + 2), h);
+            in[it] = __ldg(reinterpret_cast<const uint32_t*>(S + (int64_t)gy * spitch + x));
+        }
+    }
+    // 1b: the few words that straddle the left/right image border (or everything when the source is not 4-byte aligned):
+    //     per-byte loads with reflect-101.  Words entirely beyond x = w+2 are never read by a stored output: skipped.
+    {
+        const int first_bad = aligned4 ? max(0, (w - 3 - (x0 - 4) + 3) >> 2) : 0;          // first word with x + 3 >= w
+        const int last_needed = min(kBInWords - 1, (w + 2 - (x0 - 4)) >> 2);               // word holding column w + 2
+        const int nright = max(0, last_needed - first_bad + 1);
+        const int nleft = (aligned4 && x0 == 0) ? 1 : 0;                                   // word 0 = columns -4..-1
+        const int per_row = nright + nleft;
+        for (int it = threadIdx.x; it < kBInRows * per_row; it += 256) {
+            const int r = it / per_row, k = it - r * per_row;
+            const int wi = (k < nleft) ? 0 : first_bad + (k - nleft);
+            if (nleft && k >= nleft && wi == 0) continue;                                   // word 0 already handled as the left word
+            const int gy = refl101(min(y0 - 3 + r, h + 2), h);
+            const uint8_t* row = S + (int64_t)gy * spitch;
             const int x = x0 - 4 + 4 * wi;
-            uint32_t v;
-            if (aligned4 && x >= 0 && x + 3 < w) {
-                v = __ldg(reinterpret_cast<const uint32_t*>(row + x));
-            } else {
-                v = 0;
+            uint32_t v = 0;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int gx = refl101(min(x + b, w + 2), w);
-                    v |= (uint32_t)__ldg(row + gx) << (8 * b);
-                }
-            }
+            for (int b = 0; b < 4; ++b) v |= (uint32_t)__ldg(row + refl101(min(x + b, w + 2), w)) << (8 * b);
             in[r * kBInWords + wi] = v;
         }
     }
