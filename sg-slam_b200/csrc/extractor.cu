@@ -91,7 +91,9 @@ int enqueue(sgs_extractor* ex, const uint8_t* d_l0, int pitch, int64_t fstride, 
     }
     SGS_CUDA_TRY(cudaMemsetAsync(ex->d_cand_count, 0, sizeof(int32_t) * (size_t)nframes * L, st));
     if (prof) cudaEventRecord(ex->ev[0], st);
-    for (int l = 1; l < L; ++l) launch_resize(P, l, st);
+    for (int l = 1; l < L; ++l) {
+        if (resize_tile_supported(P, l)) launch_resize_tile(P, l, st); else launch_resize(P, l, st);
+    }
     if (prof) cudaEventRecord(ex->ev[1], st);
     if (ex->fast_variant == 0) {
         launch_fast(P, ex->d_cells, (int)ex->plan.cells.size(), st);
