@@ -285,7 +285,8 @@ def main():
         B.check(B.lib().sgs_tracker_track_device(trk.h, NB, *[v(p) for p in track_ptrs(dv)], C.c_float(TH), 0, 1, v(st.cuda_stream)))
 
     def step_host():
-        trk.extract(h_frames.data_ptr(), NB, W * H, W, h_kps.data_ptr(), h_desc.data_ptr(), h_n.data_ptr())
+        # call 1: frames -> keypoints (what the host-side LK needs); descriptors stay on the device (desc = NULL)
+        trk.extract(h_frames.data_ptr(), NB, W * H, W, h_kps.data_ptr(), 0, h_n.data_ptr())
         trk.track(NB, track_ptrs(hp), TH, 0, 1, [h_out['kps'].data_ptr(), h_out['desc'].data_ptr(), h_out['ur'].data_ptr(), h_out['cnt'].data_ptr(),
                                                  h_out['mp'].data_ptr(), h_out['nm'].data_ptr()])
 
@@ -348,7 +349,7 @@ def main():
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         h2d = h_frames.numel() + sum(hp[k].numel() * hp[k].element_size() for k in keys_h) + hp['T'].numel() * 4
-        d2h = (h_kps.numel() + h_desc.numel() + h_n.numel() * 4) + sum(t.numel() * t.element_size() for t in h_out.values())
+        d2h = (h_kps.numel() + h_n.numel() * 4) + sum(t.numel() * t.element_size() for t in h_out.values())
         e2e = {'value': world * NB * args.steps / dt, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                'ms_per_step': 1e3 * dt / args.steps, 'note': 'sgs_tracker_extract + sgs_tracker_track with pinned host buffers; the host-side LK/RANSAC between the two calls is not included (not on the GPU yet)'}
 

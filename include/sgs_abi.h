@@ -95,7 +95,8 @@ SGS_API int sgs_extract(sgs_extractor* ex, const uint8_t* gray, int width, int h
                         uint8_t* desc, int cap, int* n);
 
 /* Same, for `nframes` independent host images laid out `frame_stride` bytes apart.  kps: [nframes][cap],
- * desc: [nframes][cap][32], n: [nframes].  Host<->device copies happen inside. */
+ * desc: [nframes][cap][32] (may be NULL: keypoints only), n: [nframes].  Host<->device copies happen inside; pinned caller
+ * buffers (input, and outputs with cap == sgs_extractor_max_keypoints) are used directly, without staging. */
 SGS_API int sgs_extract_batch(sgs_extractor* ex, const uint8_t* gray, int nframes, size_t frame_stride, int pitch,
                               sgs_keypoint* kps, uint8_t* desc, int cap, int* n);
 

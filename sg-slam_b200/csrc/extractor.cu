@@ -325,23 +325,32 @@ SGS_API int sgs_extractor_results_device(const sgs_extractor* ex, const sgs_keyp
 }
 
 SGS_API int sgs_extractor_fetch(sgs_extractor* ex, int nframes, sgs_keypoint* kps, uint8_t* desc, int cap, int* n, void* stream) {
-    if (!ex || !kps || !desc || !n) return fail_invalid("sgs_extractor_fetch: NULL argument");
+    if (!ex || !kps || !n) return fail_invalid("sgs_extractor_fetch: NULL argument");     // desc may be NULL: keypoints only
     if (nframes < 1 || nframes > ex->last_nframes) return fail_invalid("sgs_extractor_fetch: nframes exceeds the last call");
     SGS_CUDA_TRY(cudaSetDevice(ex->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ex->stream;
     const size_t K = (size_t)ex->plan.max_kp_per_frame;
+    // pinned caller buffers with the handle's own row capacity receive the device arrays directly (no staging copy)
+    cudaPointerAttributes ak, ad;
+    bool direct = (size_t)cap == K && cudaPointerGetAttributes(&ak, kps) == cudaSuccess && ak.type == cudaMemoryTypeHost;
+    if (direct && desc) direct = cudaPointerGetAttributes(&ad, desc) == cudaSuccess && ad.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    sgs_keypoint* hk = direct ? kps : ex->h_kps;
+    uint8_t* hd = direct ? desc : ex->h_desc;
     SGS_CUDA_TRY(cudaMemcpyAsync(ex->h_count, ex->d_out_count, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, st));
     SGS_CUDA_TRY(cudaMemcpyAsync(ex->h_error, ex->d_error, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(ex->h_kps, ex->d_out_kps, sizeof(sgs_keypoint) * K * nframes, cudaMemcpyDeviceToHost, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(ex->h_desc, ex->d_out_desc, 32 * K * nframes, cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(hk, ex->d_out_kps, sizeof(sgs_keypoint) * K * nframes, cudaMemcpyDeviceToHost, st));
+    if (desc) SGS_CUDA_TRY(cudaMemcpyAsync(hd, ex->d_out_desc, 32 * K * nframes, cudaMemcpyDeviceToHost, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
     if (*ex->h_error) { set_error("device capacity overflow (code %d)", *ex->h_error); cudaMemsetAsync(ex->d_error, 0, 4, st); return SGS_ERR_CAPACITY; }
     for (int f = 0; f < nframes; ++f) {
         const int c = ex->h_count[f];
         n[f] = c;
         if (c > cap) { set_error("frame %d has %d keypoints, caller capacity is %d", f, c, cap); return SGS_ERR_CAPACITY; }
-        std::memcpy(kps + (size_t)f * cap, ex->h_kps + (size_t)f * K, sizeof(sgs_keypoint) * c);
-        std::memcpy(desc + (size_t)f * cap * 32, ex->h_desc + (size_t)f * K * 32, (size_t)32 * c);
+        if (!direct) {
+            std::memcpy(kps + (size_t)f * cap, ex->h_kps + (size_t)f * K, sizeof(sgs_keypoint) * c);
+            if (desc) std::memcpy(desc + (size_t)f * cap * 32, ex->h_desc + (size_t)f * K * 32, (size_t)32 * c);
+        }
     }
     return SGS_OK;
 }
@@ -352,7 +361,7 @@ SGS_API int sgs_extract_batch(sgs_extractor* ex, const uint8_t* gray, int nframe
     if (nframes < 0 || nframes > ex->max_batch) return fail_invalid("sgs_extract_batch: nframes outside [0,max_batch]");
     if (nframes == 0) return SGS_OK;
     if (!gray) { for (int f = 0; f < nframes; ++f) n[f] = 0; return SGS_OK; }  // empty image: ORBextractor.cc:1048
-    if (!kps || !desc) return fail_invalid("sgs_extract_batch: NULL output");
+    if (!kps) return fail_invalid("sgs_extract_batch: NULL output");                  // desc == NULL: keypoints only
     const OrbPlan& PL = ex->plan;
     if (pitch < PL.width || frame_stride < (size_t)pitch * PL.height) return fail_invalid("sgs_extract_batch: pitch/frame_stride too small");
     SGS_CUDA_TRY(cudaSetDevice(ex->device));
