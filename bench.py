@@ -236,6 +236,7 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the single JSON line (NCCL prints its version banner to stdout)
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     NB = args.batch
