@@ -249,3 +249,21 @@ def dynreject(cur_xy, prev_xy, F, boxes, have_dyn, nfeatures):
     s = lib().sgo_dynreject(_p(cur), _p(prev), n, _p(Fm) if Fm is not None else None, _p(bx), len(bx), int(have_dyn), nfeatures,
                             _p(keep), _p(dist), C.byref(rest))
     return s, keep, dist, bool(rest.value)
+
+
+def lk_track(I, J, pts):
+    """calcOpticalFlowPyrLK(I, J, pts) with the reference's parameters (src/Frame.cc:445): returns the tracked points [n,2]."""
+    I = np.ascontiguousarray(I, np.uint8); J = np.ascontiguousarray(J, np.uint8)
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    out = np.zeros_like(p)
+    lib().sgo_lk_track(_p(I), _p(J), I.shape[1], I.shape[0], I.strides[0], _p(p), len(p), _p(out))
+    return out
+
+
+def lk_pyr_level(img, level):
+    img = np.ascontiguousarray(img, np.uint8)
+    w, h = C.c_int32(), C.c_int32()
+    lib().sgo_lk_pyr_level(_p(img), img.shape[1], img.shape[0], img.strides[0], level, None, C.byref(w), C.byref(h))
+    out = np.zeros((h.value, w.value), np.uint8)
+    lib().sgo_lk_pyr_level(_p(img), img.shape[1], img.shape[0], img.strides[0], level, _p(out), C.byref(w), C.byref(h))
+    return out

@@ -1042,4 +1042,139 @@ SGO_API int sgo_dynreject(const float* cur_xy, const float* prev_xy, int n, cons
     return sum;
 }
 
+// ---------------------------------------------------------------------------------------
+// cv::calcOpticalFlowPyrLK(prevImg = I, nextImg = J, prevPts, nextPts, status, err, winSize (21,21), maxLevel 3,
+// TermCriteria(COUNT|EPS, 30, 0.01)) as called at src/Frame.cc:445 (I = current gray, J = previous gray, prevPts = current
+// keypoints, nextPts = "Prepoint").  Restates OpenCV video/lkpyramid.cpp (buildOpticalFlowPyramid with REFLECT_101 borders,
+// cv::pyrDown 5x5, calcScharrDeriv, LKTrackerInvoker scalar path).  Float accumulations run in natural scalar order; OpenCV's
+// SIMD paths sum in another order, so agreement with cv2 is to ~1e-4 px on converged tracks (tests/test_lk.py), not bit-exact.
+// status/err are not produced: the reference ignores them (quirk Q4); a failed level leaves the running estimate untouched (A10).
+// ---------------------------------------------------------------------------------------
+namespace {
+
+inline int refl(int i, int n) { return reflect101(i, n); }
+
+struct LkLevel { int w, h; std::vector<uint8_t> px; inline int at(int x, int y) const { return px[(size_t)refl(y, h) * w + refl(x, w)]; } };
+
+// cv::pyrDown for CV_8U (imgproc/pyramids.cpp): separable [1 4 6 4 1], exact integer sums, (v + 128) >> 8, BORDER_REFLECT_101
+void pyr_down(const LkLevel& s, LkLevel& d) {
+    d.w = (s.w + 1) / 2; d.h = (s.h + 1) / 2; d.px.resize((size_t)d.w * d.h);
+    std::vector<int> row((size_t)s.h * d.w);
+    for (int y = 0; y < s.h; y++)
+        for (int x = 0; x < d.w; x++) {
+            const uint8_t* r = s.px.data() + (size_t)y * s.w;
+            row[(size_t)y * d.w + x] = r[refl(2 * x, s.w)] * 6 + (r[refl(2 * x - 1, s.w)] + r[refl(2 * x + 1, s.w)]) * 4 + r[refl(2 * x - 2, s.w)] + r[refl(2 * x + 2, s.w)];
+        }
+    for (int y = 0; y < d.h; y++)
+        for (int x = 0; x < d.w; x++) {
+            auto R = [&](int yy) { return row[(size_t)refl(yy, s.h) * d.w + x]; };
+            const int v = R(2 * y) * 6 + (R(2 * y - 1) + R(2 * y + 1)) * 4 + R(2 * y - 2) + R(2 * y + 2);
+            d.px[(size_t)y * d.w + x] = (uint8_t)((v + 128) >> 8);
+        }
+}
+
+// calcScharrDeriv at one pixel inside the image (reflect-101 at the image edge); zero outside (BORDER_CONSTANT copyMakeBorder)
+inline void scharr_at(const LkLevel& L, int x, int y, int& dx, int& dy) {
+    if (x < 0 || x >= L.w || y < 0 || y >= L.h) { dx = 0; dy = 0; return; }
+    auto t0 = [&](int xx) { return (L.at(xx, y - 1) + L.at(xx, y + 1)) * 3 + L.at(xx, y) * 10; };
+    auto t1 = [&](int xx) { return L.at(xx, y + 1) - L.at(xx, y - 1); };
+    // the horizontal border of the temporary rows is reflect-101 as well: trow[-1] = trow[1], trow[cols] = trow[cols-2]
+    const int xm = refl(x - 1, L.w), xp = refl(x + 1, L.w);
+    dx = (int16_t)(t0(xp) - t0(xm));
+    dy = (int16_t)((t1(xm) + t1(xp)) * 3 + t1(x) * 10);
+}
+
+inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+}  // namespace
+
+// pts / out: n x 2 float.  I, J: 8-bit gray images of the same size.  Returns 0.
+SGO_API int sgo_lk_track(const uint8_t* I0, const uint8_t* J0, int w, int h, int pitch, const float* pts, int n, float* out) {
+    const int WIN = 21, MAXLEVEL = 3, MAXCOUNT = 30;
+    const float EPS2 = (float)(0.01 * 0.01), MIN_EIG = 1e-4f;
+    std::vector<LkLevel> I(1), J(1);
+    I[0].w = J[0].w = w; I[0].h = J[0].h = h; I[0].px.resize((size_t)w * h); J[0].px.resize((size_t)w * h);
+    for (int y = 0; y < h; y++) { std::memcpy(&I[0].px[(size_t)y * w], I0 + (size_t)y * pitch, w); std::memcpy(&J[0].px[(size_t)y * w], J0 + (size_t)y * pitch, w); }
+    int maxLevel = 0;
+    for (int l = 1; l <= MAXLEVEL; l++) {   // buildOpticalFlowPyramid stops when the next level is not larger than the window
+        const int nw = (I[l - 1].w + 1) / 2, nh = (I[l - 1].h + 1) / 2;
+        if (nw <= WIN || nh <= WIN) break;
+        I.emplace_back(); J.emplace_back();
+        pyr_down(I[l - 1], I[l]); pyr_down(J[l - 1], J[l]);
+        maxLevel = l;
+    }
+    std::vector<float> nx(n), ny(n);
+    std::vector<short> Iw(WIN * WIN), dIx(WIN * WIN), dIy(WIN * WIN);
+    const float halfWin = (WIN - 1) * 0.5f;
+    for (int level = maxLevel; level >= 0; level--) {
+        const LkLevel& LI = I[level]; const LkLevel& LJ = J[level];
+        for (int p = 0; p < n; p++) {
+            float px = pts[2 * p] * (float)(1. / (1 << level)), py = pts[2 * p + 1] * (float)(1. / (1 << level));
+            float qx, qy;
+            if (level == maxLevel) { qx = px; qy = py; } else { qx = nx[p] * 2.f; qy = ny[p] * 2.f; }
+            nx[p] = qx; ny[p] = qy;
+            px -= halfWin; py -= halfWin;
+            const int ipx = (int)std::floor(px), ipy = (int)std::floor(py);
+            if (ipx < -WIN || ipx >= LI.w || ipy < -WIN || ipy >= LI.h) continue;
+            float a = px - ipx, b = py - ipy;
+            const int W_BITS = 14;
+            const float FLT_SCALE = 1.f / (1 << 20);
+            int iw00 = cvRoundF((1.f - a) * (1.f - b) * (1 << W_BITS)), iw01 = cvRoundF(a * (1.f - b) * (1 << W_BITS));
+            int iw10 = cvRoundF((1.f - a) * b * (1 << W_BITS)), iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+            float iA11 = 0, iA12 = 0, iA22 = 0;
+            for (int y = 0; y < WIN; y++)
+                for (int x = 0; x < WIN; x++) {
+                    const int X = ipx + x, Y = ipy + y;
+                    const int ival = descale(LI.at(X, Y) * iw00 + LI.at(X + 1, Y) * iw01 + LI.at(X, Y + 1) * iw10 + LI.at(X + 1, Y + 1) * iw11, W_BITS - 5);
+                    int d00x, d00y, d01x, d01y, d10x, d10y, d11x, d11y;
+                    scharr_at(LI, X, Y, d00x, d00y); scharr_at(LI, X + 1, Y, d01x, d01y); scharr_at(LI, X, Y + 1, d10x, d10y); scharr_at(LI, X + 1, Y + 1, d11x, d11y);
+                    const int ixval = descale(d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11, W_BITS);
+                    const int iyval = descale(d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11, W_BITS);
+                    Iw[y * WIN + x] = (short)ival; dIx[y * WIN + x] = (short)ixval; dIy[y * WIN + x] = (short)iyval;
+                    iA11 += (float)(ixval * ixval); iA12 += (float)(ixval * iyval); iA22 += (float)(iyval * iyval);
+                }
+            const float A11 = iA11 * FLT_SCALE, A12 = iA12 * FLT_SCALE, A22 = iA22 * FLT_SCALE;
+            float D = A11 * A22 - A12 * A12;
+            const float minEig = (A22 + A11 - std::sqrt((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * WIN * WIN);
+            if (minEig < MIN_EIG || D < FLT_EPSILON) continue;
+            D = 1.f / D;
+            qx -= halfWin; qy -= halfWin;
+            float pdx = 0, pdy = 0;
+            for (int j = 0; j < MAXCOUNT; j++) {
+                const int inx = (int)std::floor(qx), iny = (int)std::floor(qy);
+                if (inx < -WIN || inx >= LJ.w || iny < -WIN || iny >= LJ.h) break;
+                a = qx - inx; b = qy - iny;
+                iw00 = cvRoundF((1.f - a) * (1.f - b) * (1 << W_BITS)); iw01 = cvRoundF(a * (1.f - b) * (1 << W_BITS));
+                iw10 = cvRoundF((1.f - a) * b * (1 << W_BITS)); iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+                float ib1 = 0, ib2 = 0;
+                for (int y = 0; y < WIN; y++)
+                    for (int x = 0; x < WIN; x++) {
+                        const int X = inx + x, Y = iny + y;
+                        const int diff = descale(LJ.at(X, Y) * iw00 + LJ.at(X + 1, Y) * iw01 + LJ.at(X, Y + 1) * iw10 + LJ.at(X + 1, Y + 1) * iw11, W_BITS - 5) - Iw[y * WIN + x];
+                        ib1 += (float)(diff * dIx[y * WIN + x]); ib2 += (float)(diff * dIy[y * WIN + x]);
+                    }
+                const float b1 = ib1 * FLT_SCALE, b2 = ib2 * FLT_SCALE;
+                const float dx = (float)((A12 * b2 - A22 * b1) * D), dy = (float)((A12 * b1 - A11 * b2) * D);
+                qx += dx; qy += dy;
+                nx[p] = qx + halfWin; ny[p] = qy + halfWin;
+                if ((double)dx * dx + (double)dy * dy <= EPS2) break;
+                if (j > 0 && std::abs(dx + pdx) < 0.01 && std::abs(dy + pdy) < 0.01) { nx[p] -= dx * 0.5f; ny[p] -= dy * 0.5f; break; }
+                pdx = dx; pdy = dy;
+            }
+        }
+    }
+    for (int p = 0; p < n; p++) { out[2 * p] = nx[p]; out[2 * p + 1] = ny[p]; }
+    return 0;
+}
+
+// LK pyramid level (for the GPU parity gate): returns level `level` of cv::buildOpticalFlowPyramid without its border
+SGO_API int sgo_lk_pyr_level(const uint8_t* img, int w, int h, int pitch, int level, uint8_t* out, int32_t* ow, int32_t* oh) {
+    LkLevel cur; cur.w = w; cur.h = h; cur.px.resize((size_t)w * h);
+    for (int y = 0; y < h; y++) std::memcpy(&cur.px[(size_t)y * w], img + (size_t)y * pitch, w);
+    for (int l = 0; l < level; l++) { LkLevel nxt; pyr_down(cur, nxt); cur = std::move(nxt); }
+    *ow = cur.w; *oh = cur.h;
+    if (out) std::memcpy(out, cur.px.data(), cur.px.size());
+    return 0;
+}
+
 SGO_API int sgo_abi_version(void) { return 1; }

@@ -68,10 +68,10 @@ def stream_s2(nframes=16, w=640, h=480, seed=2, tex_w=1024, tex_h=768, person=Tr
     cx0, cy0 = (tex_w - w) / 2.0, (tex_h - h) / 2.0
     for k in range(nframes):
         t = k / max(1, nframes - 1) if nframes > 1 else 0.0
-        ph = 2 * np.pi * k / 96.0
-        ox = cx0 + 0.8 * cx0 * np.sin(ph)            # <= ~2.2 px/frame
+        ph = 2 * np.pi * k / 420.0
+        ox = cx0 + 0.8 * cx0 * np.sin(ph)            # <= ~2.3 px/frame
         oy = cy0 + 0.8 * cy0 * np.sin(1.7 * ph + 0.3)
-        roll = np.deg2rad(4.0) * np.sin(0.9 * ph)    # <= ~0.24 deg/frame
+        roll = np.deg2rad(4.0) * np.sin(0.9 * ph)    # <= ~0.06 deg/frame
         c, s = np.cos(roll), np.sin(roll)
         xc, yc = xx - w / 2.0, yy - h / 2.0
         xs = ox + w / 2.0 + c * xc - s * yc
