@@ -288,6 +288,24 @@ SGS_API int sgs_tracker_results_device(const sgs_tracker* t, const sgs_keypoint*
                                        const int32_t** nmatches, const uint64_t** ncand);
 SGS_API sgs_extractor* sgs_tracker_extractor(sgs_tracker* t);  /* the extractor owned by the tracker (tables, profiling) */
 
+/* ------------------------------------------------------------------------------------
+ * cv::calcOpticalFlowPyrLK as called at src/Frame.cc:445 (window 21x21, maxLevel 3, COUNT|EPS 30 / 0.01): tracks the CURRENT
+ * frame's keypoints into the PREVIOUS gray image.  Positions agree with OpenCV to ~1e-4 px (float summation order), status/err
+ * are not produced (the reference ignores them).
+ *   sgs_lk_track              : one host image pair, n points (x, y) -> out (x, y)
+ *   sgs_lk_track_batch_device : `nframes` device image pairs; points are the keypoints d_kps [F][cap] (counts [F]); writes
+ *                               d_prev_xy [F][cap][2] -- the `prev_xy` input of the dyn-reject stage
+ * ------------------------------------------------------------------------------------ */
+typedef struct sgs_lk sgs_lk;
+SGS_API int sgs_lk_create(int width, int height, int max_batch, int device, sgs_lk** out);
+SGS_API void sgs_lk_destroy(sgs_lk* k);
+SGS_API int sgs_lk_track(sgs_lk* k, const uint8_t* cur, const uint8_t* prev, int pitch, const float* pts, int n, float* out);
+SGS_API int sgs_lk_track_batch_device(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, int nframes, size_t frame_stride,
+                                      int pitch, const sgs_keypoint* d_kps, const int32_t* d_counts, int cap, float* d_prev_xy,
+                                      void* stream);
+/* parity accessor: pyramid level (1..3) of frame 0 of the last call; which = 0 current image, 1 previous image */
+SGS_API int sgs_lk_read_level(sgs_lk* k, int which, int level, uint8_t* out, int out_pitch);
+
 /* ---- measurement hooks (bench.py): per-stage device time of the extractor from CUDA events recorded on the launching
  * stream.  Stages: 0 pyramid, 1 FAST, 2 quadtree, 3 blur, 4 orientation+BRIEF.  ms_total5 accumulates over `ncalls`. */
 SGS_API int sgs_extractor_set_profiling(sgs_extractor* ex, int enable);

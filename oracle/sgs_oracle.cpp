@@ -1091,7 +1091,7 @@ inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 // pts / out: n x 2 float.  I, J: 8-bit gray images of the same size.  Returns 0.
 SGO_API int sgo_lk_track(const uint8_t* I0, const uint8_t* J0, int w, int h, int pitch, const float* pts, int n, float* out) {
     const int WIN = 21, MAXLEVEL = 3, MAXCOUNT = 30;
-    const float EPS2 = (float)(0.01 * 0.01), MIN_EIG = 1e-4f;
+    const float MIN_EIG = 1e-4f;
     std::vector<LkLevel> I(1), J(1);
     I[0].w = J[0].w = w; I[0].h = J[0].h = h; I[0].px.resize((size_t)w * h); J[0].px.resize((size_t)w * h);
     for (int y = 0; y < h; y++) { std::memcpy(&I[0].px[(size_t)y * w], I0 + (size_t)y * pitch, w); std::memcpy(&J[0].px[(size_t)y * w], J0 + (size_t)y * pitch, w); }
@@ -1157,7 +1157,7 @@ SGO_API int sgo_lk_track(const uint8_t* I0, const uint8_t* J0, int w, int h, int
                 const float dx = (float)((A12 * b2 - A22 * b1) * D), dy = (float)((A12 * b1 - A11 * b2) * D);
                 qx += dx; qy += dy;
                 nx[p] = qx + halfWin; ny[p] = qy + halfWin;
-                if ((double)dx * dx + (double)dy * dy <= EPS2) break;
+                if ((double)dx * dx + (double)dy * dy <= 0.01 * 0.01) break;                 // Point2f::ddot is double; epsilon is squared in double
                 if (j > 0 && std::abs(dx + pdx) < 0.01 && std::abs(dy + pdy) < 0.01) { nx[p] -= dx * 0.5f; ny[p] -= dy * 0.5f; break; }
                 pdx = dx; pdy = dy;
             }

@@ -1,0 +1,303 @@
+// lk_kernel.cu -- cv::calcOpticalFlowPyrLK as called by Frame::RmDynamicPointWithSemanticAndGeometry (src/Frame.cc:445):
+// I = current gray, J = previous gray, window 21x21, 4 pyramid levels, <= 30 iterations or |delta|^2 <= 1e-4.
+// Follows OpenCV video/lkpyramid.cpp: cv::pyrDown levels (bit-exact integers), Scharr derivatives of I (int16, zero outside the
+// image), 14-bit fixed-point bilinear window extraction, float 2x2 solve.  Sums of integer products are accumulated EXACTLY
+// (int64) and rounded once; OpenCV accumulates them in float in SIMD order, so positions agree to ~1e-4 px, not bit-for-bit
+// (tolerance stated in tests/test_gpu_lk.py).  status/err are not produced (the reference ignores them, quirk Q4); a level
+// that fails leaves the running estimate untouched.
+//
+// One warp per point; the warp keeps, in shared memory, the 24x24 raw patch of I, its 22x22 Scharr derivatives, the 21x21
+// interpolated window (I, Ix, Iy as int16) and the 22x22 patch of J of the current iteration.
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "sgs_common.h"
+
+namespace sgs {
+
+constexpr int kWin = 21, kLkMaxLevel = 3, kLkMaxCount = 30;
+constexpr int kLkWarps = 4;
+
+struct LkLevels {
+    const uint8_t* I[kLkMaxLevel + 1]; const uint8_t* J[kLkMaxLevel + 1];
+    int32_t w[kLkMaxLevel + 1], h[kLkMaxLevel + 1], pitch[kLkMaxLevel + 1];
+    int64_t fstride[kLkMaxLevel + 1];
+    int32_t pitchJ0; int64_t fstrideJ0;     // level 0 of J may have its own layout (caller buffers)
+    int32_t max_level;
+};
+
+__device__ __forceinline__ int lk_refl(int i, int n) {
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+// cv::pyrDown, CV_8U: separable [1 4 6 4 1], exact integer sums, (v + 128) >> 8, BORDER_REFLECT_101
+__global__ void __launch_bounds__(256) lk_pyrdown_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, int64_t sfstride,
+                                                         uint8_t* __restrict__ dst, int dw, int dh, int dpitch, int64_t dfstride) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    const uint8_t* S = src + (int64_t)blockIdx.z * sfstride;
+    int cx[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) cx[k] = lk_refl(2 * x - 2 + k, sw);
+    int v = 0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const uint8_t* row = S + (int64_t)lk_refl(2 * y - 2 + r, sh) * spitch;
+        const int hsum = __ldg(row + cx[2]) * 6 + (__ldg(row + cx[1]) + __ldg(row + cx[3])) * 4 + __ldg(row + cx[0]) + __ldg(row + cx[4]);
+        v += hsum * (r == 2 ? 6 : (r == 1 || r == 3) ? 4 : 1);
+    }
+    dst[(int64_t)blockIdx.z * dfstride + (int64_t)y * dpitch + x] = (uint8_t)((v + 128) >> 8);
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int lk_descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+__device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
+    w00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), 16384.f));
+    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), 16384.f));
+    w10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), 16384.f));
+    w11 = 16384 - w00 - w01 - w10;
+}
+
+// points come either from keypoints (kps != nullptr: kp.x, kp.y) or from a plain float2 array
+__global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_constant__ LkLevels L, const sgs_keypoint* __restrict__ kps,
+                                                                 const float2* __restrict__ pts, const int32_t* __restrict__ counts, int cap,
+                                                                 float2* __restrict__ out) {
+    __shared__ uint8_t s_raw[kLkWarps][24 * 24];
+    __shared__ int16_t s_dx[kLkWarps][22 * 22], s_dy[kLkWarps][22 * 22];
+    __shared__ int16_t s_iw[kLkWarps][kWin * kWin], s_ix[kLkWarps][kWin * kWin], s_iy[kLkWarps][kWin * kWin];
+    __shared__ uint8_t s_j[kLkWarps][22 * 24];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.y;
+    const int p = blockIdx.x * kLkWarps + warp;
+    const int n = counts ? min(counts[f], cap) : cap;
+    if (p >= n) return;
+    const int64_t pi = (int64_t)f * cap + p;
+    float ptx, pty;
+    if (kps) { ptx = kps[pi].x; pty = kps[pi].y; } else { const float2 q = pts[pi]; ptx = q.x; pty = q.y; }
+    uint8_t* raw = s_raw[warp]; int16_t* dxp = s_dx[warp]; int16_t* dyp = s_dy[warp];
+    int16_t* Iw = s_iw[warp]; int16_t* Ix = s_ix[warp]; int16_t* Iy = s_iy[warp]; uint8_t* jp = s_j[warp];
+    const float half_win = 10.f;                       // (winSize - 1) * 0.5
+    const float flt_scale = 1.f / (1 << 20);
+    float nx = 0.f, ny = 0.f;
+    for (int level = L.max_level; level >= 0; --level) {
+        const int lw = L.w[level], lh = L.h[level];
+        const uint8_t* Iimg = L.I[level] + (int64_t)f * L.fstride[level];
+        const int ipitch = L.pitch[level];
+        const uint8_t* Jimg = L.J[level] + (int64_t)f * (level == 0 ? L.fstrideJ0 : L.fstride[level]);
+        const int jpitch = level == 0 ? L.pitchJ0 : L.pitch[level];
+        const float sc = 1.f / (float)(1 << level);
+        float px = __fmul_rn(ptx, sc), py = __fmul_rn(pty, sc);
+        float qx, qy;
+        if (level == L.max_level) { qx = px; qy = py; } else { qx = __fmul_rn(nx, 2.f); qy = __fmul_rn(ny, 2.f); }
+        nx = qx; ny = qy;
+        px = __fsub_rn(px, half_win); py = __fsub_rn(py, half_win);
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -kWin || ipx >= lw || ipy < -kWin || ipy >= lh) continue;
+        int w00, w01, w10, w11;
+        lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+        // raw 24x24 patch of I around the window (one ring for the bilinear +1, one ring for Scharr), reflect-101 outside the image
+        __syncwarp();
+        for (int i = lane; i < 24 * 24; i += 32) {
+            const int yy = i / 24, xx = i - yy * 24;
+            raw[i] = __ldg(Iimg + (int64_t)lk_refl(ipy - 1 + yy, lh) * ipitch + lk_refl(ipx - 1 + xx, lw));
+        }
+        __syncwarp();
+        // Scharr derivatives at the 22x22 positions the bilinear window touches; zero outside the image (BORDER_CONSTANT)
+        for (int i = lane; i < 22 * 22; i += 32) {
+            const int yy = i / 22, xx = i - yy * 22;
+            const int X = ipx + xx, Y = ipy + yy;
+            int dx = 0, dy = 0;
+            if (X >= 0 && X < lw && Y >= 0 && Y < lh) {
+                const uint8_t* r0 = raw + yy * 24 + xx;            // raw(yy, xx) == image (Y-1, X-1)
+                const int a00 = r0[0], a01 = r0[1], a02 = r0[2], a10 = r0[24], a12 = r0[26], a20 = r0[48], a21 = r0[49], a22 = r0[50];
+                // t0(x) = 3 (s[y-1][x] + s[y+1][x]) + 10 s[y][x];  t1(x) = s[y+1][x] - s[y-1][x]
+                const int t0m = (a00 + a20) * 3 + a10 * 10, t0p = (a02 + a22) * 3 + a12 * 10;
+                const int t1m = a20 - a00, t1c = a21 - a01, t1p = a22 - a02;
+                dx = t0p - t0m;
+                dy = (t1m + t1p) * 3 + t1c * 10;
+            }
+            dxp[i] = (int16_t)dx; dyp[i] = (int16_t)dy;
+        }
+        __syncwarp();
+        long long a11 = 0, a12 = 0, a22 = 0;
+        for (int i = lane; i < kWin * kWin; i += 32) {
+            const int yy = i / kWin, xx = i - yy * kWin;
+            const uint8_t* r = raw + (yy + 1) * 24 + xx + 1;
+            const int ival = lk_descale(r[0] * w00 + r[1] * w01 + r[24] * w10 + r[25] * w11, 9);
+            const int16_t* gx = dxp + yy * 22 + xx; const int16_t* gy = dyp + yy * 22 + xx;
+            const int ixv = lk_descale(gx[0] * w00 + gx[1] * w01 + gx[22] * w10 + gx[23] * w11, 14);
+            const int iyv = lk_descale(gy[0] * w00 + gy[1] * w01 + gy[22] * w10 + gy[23] * w11, 14);
+            Iw[i] = (int16_t)ival; Ix[i] = (int16_t)ixv; Iy[i] = (int16_t)iyv;
+            a11 += (long long)(ixv * ixv); a12 += (long long)(ixv * iyv); a22 += (long long)(iyv * iyv);
+        }
+        const float A11 = __fmul_rn((float)warp_sum_ll(a11), flt_scale), A12 = __fmul_rn((float)warp_sum_ll(a12), flt_scale),
+                    A22 = __fmul_rn((float)warp_sum_ll(a22), flt_scale);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dd = __fsub_rn(A11, A22);
+        const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
+                                        (float)(2 * kWin * kWin));
+        if (min_eig < 1e-4f || D < 1.1920928955078125e-7f) continue;
+        D = __fdiv_rn(1.f, D);
+        qx = __fsub_rn(qx, half_win); qy = __fsub_rn(qy, half_win);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < kLkMaxCount; ++j) {
+            const int inx = (int)floorf(qx), iny = (int)floorf(qy);
+            if (inx < -kWin || inx >= lw || iny < -kWin || iny >= lh) break;
+            lk_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
+            __syncwarp();
+            for (int i = lane; i < 22 * 22; i += 32) {
+                const int yy = i / 22, xx = i - yy * 22;
+                jp[yy * 24 + xx] = __ldg(Jimg + (int64_t)lk_refl(iny + yy, lh) * jpitch + lk_refl(inx + xx, lw));
+            }
+            __syncwarp();
+            long long b1 = 0, b2 = 0;
+            for (int i = lane; i < kWin * kWin; i += 32) {
+                const int yy = i / kWin, xx = i - yy * kWin;
+                const uint8_t* r = jp + yy * 24 + xx;
+                const int diff = lk_descale(r[0] * w00 + r[1] * w01 + r[24] * w10 + r[25] * w11, 9) - Iw[i];
+                b1 += (long long)(diff * Ix[i]); b2 += (long long)(diff * Iy[i]);
+            }
+            const float B1 = __fmul_rn((float)warp_sum_ll(b1), flt_scale), B2 = __fmul_rn((float)warp_sum_ll(b2), flt_scale);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, B2), __fmul_rn(A22, B1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, B1), __fmul_rn(A11, B2)), D);
+            qx = __fadd_rn(qx, dx); qy = __fadd_rn(qy, dy);
+            nx = __fadd_rn(qx, half_win); ny = __fadd_rn(qy, half_win);
+            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= 0.01 * 0.01) break;        // Point2f::ddot is double
+            if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+                nx = __fsub_rn(nx, __fmul_rn(dx, 0.5f)); ny = __fsub_rn(ny, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+    }
+    if (lane == 0) out[pi] = make_float2(nx, ny);
+}
+
+}  // namespace sgs
+
+using namespace sgs;
+
+struct sgs_lk {
+    int device = 0, w = 0, h = 0, max_batch = 0, max_level = 0;
+    int lw[kLkMaxLevel + 1], lh[kLkMaxLevel + 1], lp[kLkMaxLevel + 1];
+    int64_t lfs[kLkMaxLevel + 1];
+    uint8_t* d_pyrI = nullptr; uint8_t* d_pyrJ = nullptr;     // levels 1..max_level, each [max_batch][h][pitch]
+    int64_t loff[kLkMaxLevel + 1];
+    // staging for the single-pair host API
+    uint8_t* d_img = nullptr; float* d_pts = nullptr; float* d_out = nullptr; int pts_cap = 0;
+    cudaStream_t st = nullptr;
+};
+
+namespace {
+int lk_bad(const char* m) { set_error("%s", m); return SGS_ERR_INVALID; }
+
+void build_pyramid(sgs_lk* k, const uint8_t* d_l0, int pitch0, int64_t fstride0, uint8_t* d_pyr, int nframes, cudaStream_t st) {
+    const uint8_t* src = d_l0; int sp = pitch0; int64_t sfs = fstride0;
+    for (int l = 1; l <= k->max_level; ++l) {
+        uint8_t* dst = d_pyr + k->loff[l];
+        dim3 grid((k->lw[l] + 31) / 32, (k->lh[l] + 7) / 8, nframes);
+        lk_pyrdown_kernel<<<grid, 256, 0, st>>>(src, k->lw[l - 1], k->lh[l - 1], sp, sfs, dst, k->lw[l], k->lh[l], k->lp[l], k->lfs[l]);
+        src = dst; sp = k->lp[l]; sfs = k->lfs[l];
+    }
+}
+
+int run_lk(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, int nframes, size_t frame_stride, int pitch, const sgs_keypoint* d_kps,
+           const float* d_pts, const int32_t* d_counts, int cap, float* d_out, cudaStream_t st) {
+    build_pyramid(k, d_cur, pitch, (int64_t)frame_stride, k->d_pyrI, nframes, st);
+    build_pyramid(k, d_prev, pitch, (int64_t)frame_stride, k->d_pyrJ, nframes, st);
+    LkLevels L;
+    L.max_level = k->max_level;
+    for (int l = 0; l <= k->max_level; ++l) {
+        L.w[l] = k->lw[l]; L.h[l] = k->lh[l];
+        if (l == 0) { L.I[0] = d_cur; L.J[0] = d_prev; L.pitch[0] = pitch; L.fstride[0] = (int64_t)frame_stride; }
+        else { L.I[l] = k->d_pyrI + k->loff[l]; L.J[l] = k->d_pyrJ + k->loff[l]; L.pitch[l] = k->lp[l]; L.fstride[l] = k->lfs[l]; }
+    }
+    for (int l = k->max_level + 1; l <= kLkMaxLevel; ++l) { L.I[l] = L.J[l] = nullptr; L.w[l] = L.h[l] = L.pitch[l] = 0; L.fstride[l] = 0; }
+    L.pitchJ0 = pitch; L.fstrideJ0 = (int64_t)frame_stride;
+    dim3 grid((cap + kLkWarps - 1) / kLkWarps, nframes);
+    lk_track_kernel<<<grid, kLkWarps * 32, 0, st>>>(L, d_kps, reinterpret_cast<const float2*>(d_pts), d_counts, cap, reinterpret_cast<float2*>(d_out));
+    SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+SGS_API void sgs_lk_destroy(sgs_lk* k) {
+    if (!k) return;
+    cudaSetDevice(k->device);
+    cudaFree(k->d_pyrI); cudaFree(k->d_pyrJ); cudaFree(k->d_img); cudaFree(k->d_pts); cudaFree(k->d_out);
+    if (k->st) cudaStreamDestroy(k->st);
+    delete k;
+}
+
+SGS_API int sgs_lk_create(int width, int height, int max_batch, int device, sgs_lk** out) {
+    if (!out || width < 24 || height < 24 || max_batch < 1) return lk_bad("sgs_lk_create: bad argument");
+    *out = nullptr;
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    sgs_lk* k = new sgs_lk();
+    k->device = device; k->w = width; k->h = height; k->max_batch = max_batch;
+    k->lw[0] = width; k->lh[0] = height; k->lp[0] = 0; k->lfs[0] = 0; k->loff[0] = 0;
+    int64_t off = 0;
+    k->max_level = 0;
+    for (int l = 1; l <= kLkMaxLevel; ++l) {     // buildOpticalFlowPyramid stops when a level would not be larger than the window
+        const int nw = (k->lw[l - 1] + 1) / 2, nh = (k->lh[l - 1] + 1) / 2;
+        if (nw <= kWin || nh <= kWin) break;
+        k->lw[l] = nw; k->lh[l] = nh; k->lp[l] = (nw + 15) & ~15; k->lfs[l] = (int64_t)k->lp[l] * nh; k->loff[l] = off;
+        off += k->lfs[l] * max_batch;
+        k->max_level = l;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&k->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&k->d_pyrI, (size_t)off + 256);
+    if (e == cudaSuccess) e = cudaMalloc(&k->d_pyrJ, (size_t)off + 256);
+    if (e != cudaSuccess) { set_error("sgs_lk_create: %s", cudaGetErrorString(e)); sgs_lk_destroy(k); return SGS_ERR_CUDA; }
+    *out = k;
+    return SGS_OK;
+}
+
+SGS_API int sgs_lk_track_batch_device(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, int nframes, size_t frame_stride, int pitch,
+                                      const sgs_keypoint* d_kps, const int32_t* d_counts, int cap, float* d_prev_xy, void* stream) {
+    if (!k || !d_cur || !d_prev || !d_kps || !d_counts || !d_prev_xy) return lk_bad("sgs_lk_track_batch_device: NULL argument");
+    if (nframes < 1 || nframes > k->max_batch || cap < 1) return lk_bad("sgs_lk_track_batch_device: nframes/cap out of range");
+    if (pitch < k->w || frame_stride < (size_t)pitch * k->h) return lk_bad("sgs_lk_track_batch_device: pitch/frame_stride too small");
+    return run_lk(k, d_cur, d_prev, nframes, frame_stride, pitch, d_kps, nullptr, d_counts, cap, d_prev_xy, stream ? (cudaStream_t)stream : k->st);
+}
+
+SGS_API int sgs_lk_track(sgs_lk* k, const uint8_t* cur, const uint8_t* prev, int pitch, const float* pts, int n, float* out) {
+    if (!k || !cur || !prev || n < 0 || (n > 0 && (!pts || !out))) return lk_bad("sgs_lk_track: bad argument");
+    if (n == 0) return SGS_OK;
+    SGS_CUDA_TRY(cudaSetDevice(k->device));
+    const int dp = (k->w + 15) & ~15;
+    if (!k->d_img) SGS_CUDA_TRY(cudaMalloc(&k->d_img, (size_t)2 * dp * k->h));
+    if (n > k->pts_cap) {
+        cudaFree(k->d_pts); cudaFree(k->d_out); k->d_pts = k->d_out = nullptr;
+        SGS_CUDA_TRY(cudaMalloc(&k->d_pts, 8 * (size_t)n)); SGS_CUDA_TRY(cudaMalloc(&k->d_out, 8 * (size_t)n));
+        k->pts_cap = n;
+    }
+    SGS_CUDA_TRY(cudaMemcpy2DAsync(k->d_img, dp, cur, pitch, k->w, k->h, cudaMemcpyHostToDevice, k->st));
+    SGS_CUDA_TRY(cudaMemcpy2DAsync(k->d_img + (size_t)dp * k->h, dp, prev, pitch, k->w, k->h, cudaMemcpyHostToDevice, k->st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(k->d_pts, pts, 8 * (size_t)n, cudaMemcpyHostToDevice, k->st));
+    int rc = run_lk(k, k->d_img, k->d_img + (size_t)dp * k->h, 1, (size_t)dp * k->h, dp, nullptr, k->d_pts, nullptr, n, k->d_out, k->st);
+    if (rc != SGS_OK) return rc;
+    SGS_CUDA_TRY(cudaMemcpyAsync(out, k->d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, k->st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(k->st));
+    return SGS_OK;
+}
+
+SGS_API int sgs_lk_read_level(sgs_lk* k, int which, int level, uint8_t* out, int out_pitch) {   // parity accessor: frame 0 of the last call
+    if (!k || !out || level < 1 || level > k->max_level) return lk_bad("sgs_lk_read_level: bad argument");
+    SGS_CUDA_TRY(cudaSetDevice(k->device));
+    SGS_CUDA_TRY(cudaStreamSynchronize(k->st));
+    SGS_CUDA_TRY(cudaMemcpy2D(out, out_pitch, (which ? k->d_pyrJ : k->d_pyrI) + k->loff[level], k->lp[level], k->lw[level], k->lh[level], cudaMemcpyDeviceToHost));
+    return SGS_OK;
+}
+
+}  // extern "C"

@@ -73,6 +73,7 @@ ABI_SYMBOLS = [
     'sgs_tracker_create', 'sgs_tracker_destroy', 'sgs_tracker_max_keypoints', 'sgs_tracker_extract', 'sgs_tracker_track',
     'sgs_tracker_extract_device', 'sgs_tracker_track_device', 'sgs_tracker_results_device', 'sgs_tracker_extractor',
     'sgs_extractor_set_profiling', 'sgs_extractor_stage_times',
+    'sgs_lk_create', 'sgs_lk_destroy', 'sgs_lk_track', 'sgs_lk_track_batch_device', 'sgs_lk_read_level',
 ]
 
 
@@ -348,3 +349,42 @@ class Tracker:
         out_ptrs: kps, desc, u_right (or 0), counts, cur_mp, nmatches   (all raw host addresses)"""
         v = C.c_void_p
         check(lib().sgs_tracker_track(self.h, nframes, *[v(p) for p in ptrs], C.c_float(th), int(mono), int(check_ori), *[v(p) for p in out_ptrs]))
+
+
+class LK:
+    """cv::calcOpticalFlowPyrLK with the reference's parameters (sgs_lk_* of include/sgs_abi.h)."""
+
+    def __init__(self, width, height, max_batch=1, device=0):
+        self.h = C.c_void_p()
+        self.width, self.height = width, height
+        check(lib().sgs_lk_create(width, height, max_batch, device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().sgs_lk_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def track(self, cur, prev, pts):
+        cur = np.ascontiguousarray(cur, np.uint8); prev = np.ascontiguousarray(prev, np.uint8)
+        p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        out = np.zeros_like(p)
+        check(lib().sgs_lk_track(self.h, _p(cur), _p(prev), cur.strides[0], _p(p), len(p), _p(out)))
+        return out
+
+    def read_level(self, which, level):
+        w, h = self.width, self.height
+        for _ in range(level):
+            w, h = (w + 1) // 2, (h + 1) // 2
+        out = np.zeros((h, w), np.uint8)
+        check(lib().sgs_lk_read_level(self.h, which, level, _p(out), w))
+        return out
+
+    def track_batch_device(self, d_cur, d_prev, nframes, frame_stride, pitch, d_kps, d_counts, cap, d_prev_xy, stream=0):
+        v = C.c_void_p
+        check(lib().sgs_lk_track_batch_device(self.h, v(d_cur), v(d_prev), nframes, C.c_size_t(frame_stride), pitch, v(d_kps), v(d_counts), cap, v(d_prev_xy), v(stream)))
