@@ -1,18 +1,21 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the B200-native SG-SLAM tracking hot path (driver contract in the task statement).
 
-One "step" = one pass of the hot path (ORB extract -> dynamic-feature rejection -> SearchByProjection against the last
-frame) over one batch of synthetic 640x480 frames per GPU (BASELINE.json configs[1]: "TUM fr3/walking_xyz-shaped synthetic
-640x480 stream, 1xB200, extract+match+dyn-reject").  Frames of independent streams are sharded over ranks with no
-data-path collective (weak scaling); one NCCL broadcast of the shared last-frame map database happens at start-up, untimed.
+One "step" = one pass of the hot path over one batch of synthetic 640x480 frames per GPU (BASELINE.json configs[1]: "TUM
+fr3/walking_xyz-shaped synthetic 640x480 stream, 1xB200, extract+match+dyn-reject"):
+
+    ORB extract  ->  LK optical flow to the previous frame  ->  dynamic-feature rejection (boxes + epipolar)  ->  SearchByProjection(cur, last)
+
+Frames of independent streams are sharded over ranks with no data-path collective (weak scaling); one NCCL broadcast of a shared
+vocabulary-sized descriptor table happens at start-up, untimed.
 
   value : whole-job frames/s with all inputs resident in HBM (device-timed with CUDA events on the launching stream)
   e2e   : same metric through the C-ABI front end with HOST (pinned) buffers, H2D/D2H inside the timed region
-  roofline     : dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM copy peak
-  cpu_baseline : the CPU oracle (port of the reference path) on this box's host cores, bounded sample
+  roofline     : dominant extractor kernel's algorithmic bytes / its CUDA-event time vs the measured HBM copy peak
+  cpu_baseline : the CPU oracle (port of the reference path, incl. LK) on this box's host cores, bounded sample
 
-LK optical flow and the RANSAC fundamental matrix (src/Frame.cc:445-472) are not on the GPU in this round: the step
-consumes precomputed previous-frame points and F ("what the step contains").
+Not on the GPU in this round, hence precomputed inputs of the step: the RANSAC fundamental matrix
+(src/Frame.cc:469-472; here a least-squares 8-point F from the static LK tracks, computed once on the host) and the detector boxes.
 """
 import argparse
 import ctypes as C
@@ -33,7 +36,9 @@ for p in (os.path.join(ROOT, 'sg-slam_b200'), os.path.join(ROOT, 'oracle'), os.p
 W, H, NFEAT = 640, 480, 1000
 ALG_BYTES_EXTRACT = 5_902_474          # algorithmic bytes per 640x480 frame, ORB extract
 ALG_BYTES_FAST_READ = 950_532          # sum of level pixels (FAST reads every level once)
+ALG_BYTES_LK = 4_200_000               # pyramids + window gathers of LK, ~4.2 MB per frame
 TH = 15.0                              # Tracking.cc:919-923 (RGB-D)
+LAUNCHES_PER_STEP = 17 + 4 + 2 + 1     # extract (7 resize, FAST, quadtree, 8 blur, describe) + LK (3 pyrDown, track) + dyn-reject/compact + match
 
 
 def log(*a):
@@ -60,17 +65,37 @@ def make_frames(nbatch, seed, unique=32):
     return frames, bx, unique
 
 
-def make_track_inputs(kps, desc, counts, boxes, cap, point_cap, unique):
-    """Per-frame inputs of the dyn-reject + match stage built from the extraction results (host side, untimed):
-    previous-frame points (what LK would return), F, person boxes, u_right from a synthetic depth plane, and the last-frame
-    map points = keypoints of the previous frame of the same stream back-projected with that depth."""
+def prev_index(nbatch, unique):
+    """Index (inside the batch) of the previous frame of the same stream; the first frame of a stream is its own predecessor."""
+    f = np.arange(nbatch, dtype=np.int32)
+    return np.where(f % unique != 0, f - 1, f).astype(np.int32)
+
+
+def fundamental_8pt(cur, prev):
+    """Least-squares normalised 8-point F with prev^T F cur = 0 (the convention of CheckEpiLineDistToRmDynamicPoint, src/Frame.cc:613-627).
+    Stands in for cv::findFundamentalMat(FM_RANSAC), which is not on the GPU in this round; computed once, outside every timed region."""
+    def norm(p):
+        c = p.mean(0); s = np.sqrt(2) / max(1e-9, np.sqrt(((p - c) ** 2).sum(1)).mean())
+        T = np.array([[s, 0, -s * c[0]], [0, s, -s * c[1]], [0, 0, 1.0]])
+        return (np.c_[p, np.ones(len(p))] @ T.T), T
+    a, Ta = norm(cur.astype(np.float64)); b, Tb = norm(prev.astype(np.float64))
+    A = np.einsum('ni,nj->nij', b, a).reshape(len(a), 9)
+    _, _, vt = np.linalg.svd(A, full_matrices=False)
+    Fm = vt[-1].reshape(3, 3)
+    u, s, v = np.linalg.svd(Fm); s[2] = 0
+    Fm = Tb.T @ (u @ np.diag(s) @ v) @ Ta
+    return Fm / np.abs(Fm).max()
+
+
+def make_track_inputs(kps, desc, counts, boxes, prev_xy, cap, point_cap, pidx):
+    """Per-frame inputs of the dyn-reject + match stage (host side, untimed): F from the static LK tracks, person boxes, u_right from
+    a synthetic depth plane, and the last-frame map points = keypoints of the previous frame back-projected with that depth."""
     from pysgs import synth
     import scenarios as S
     B = len(counts)
     cam = synth.TUM3
     depth = synth.depth_s1(W, H)
-    rng = np.random.RandomState(1234)
-    prev = np.zeros((B, cap, 2), np.float32); ur = np.full((B, cap), -1, np.float32)
+    ur = np.full((B, cap), -1, np.float32)
     F = np.zeros((B, 9), np.float64); nb = np.ones(B, np.int32); have = np.ones(B, np.uint8)
     bx = np.zeros((B, 4, 4), np.float32); bx[:, 0] = boxes
     lxyz = np.zeros((B, point_cap, 3), np.float32); ldesc = np.zeros((B, point_cap, 32), np.uint8)
@@ -80,17 +105,15 @@ def make_track_inputs(kps, desc, counts, boxes, cap, point_cap, unique):
     for f in range(B):
         n = counts[f]
         k = kps[f, :n]
-        flow = np.array([2.0 + 0.5 * np.sin(0.3 * f), 1.0 * np.cos(0.2 * f)])          # image-plane pan of this frame
-        t = flow / np.hypot(*flow)
-        F[f] = np.array([[0, 0, t[1]], [0, 0, -t[0]], [-t[1], t[0], 0]]).reshape(9)     # epipolar lines parallel to the pan
-        noise = rng.normal(0, 0.25, (n, 2))
-        p = np.stack([k['x'], k['y']], 1) + flow + noise
+        cur = np.stack([k['x'], k['y']], 1)
         inbox = (k['x'] > boxes[f, 0]) & (k['x'] < boxes[f, 0] + boxes[f, 2]) & (k['y'] > boxes[f, 1]) & (k['y'] < boxes[f, 1] + boxes[f, 3])
-        p[inbox] += np.array([-t[1], t[0]]) * rng.uniform(2.0, 6.0, (inbox.sum(), 1))  # the "person" moves off the epipolar lines
-        prev[f, :n] = p
+        if pidx[f] == f or (~inbox).sum() < 16:
+            F[f, 0] = np.nan                                                            # first frame of a stream: empty F (keep all, quirk Q11)
+        else:
+            F[f] = fundamental_8pt(cur[~inbox], prev_xy[f, :n][~inbox]).reshape(9)
         z = depth[np.clip(k['y'].astype(np.int64), 0, H - 1), np.clip(k['x'].astype(np.int64), 0, W - 1)]
         ur[f, :n] = k['x'] - np.float32(cam['bf']) / z
-        g = f - 1 if (f % unique) != 0 else f                                           # previous frame of the same stream
+        g = pidx[f]
         m = min(counts[g], point_cap)
         kk = kps[g, :m]
         zz = depth[np.clip(kk['y'].astype(np.int64), 0, H - 1), np.clip(kk['x'].astype(np.int64), 0, W - 1)]
@@ -99,7 +122,8 @@ def make_track_inputs(kps, desc, counts, boxes, cap, point_cap, unique):
         lflags[f, :m] = 1 | (2 * ((np.arange(m) % 5) != 0))                              # every 5th point is a temporal point (0 observations)
         ln[f] = m
     sf = S.scale_factors()
-    return dict(prev=prev, ur=ur, F=F, boxes=bx, nb=nb, have=have, lxyz=lxyz, ldesc=ldesc, lflags=lflags, loct=loct, lang=lang, ln=ln, T=T, sf=sf)
+    return dict(ur=ur, F=F, boxes=bx, nb=nb, have=have, lxyz=lxyz, ldesc=ldesc, lflags=lflags, loct=loct, lang=lang, ln=ln, T=T, sf=sf,
+                pidx=np.ascontiguousarray(pidx, np.int32))
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -129,8 +153,7 @@ class ClockSampler(threading.Thread):
         if not rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         sm = sorted(float(r[0]) for r in rows)
-        # "under load": samples above 60 % of the maximum seen, so idle gaps do not drag the median down
-        load = [v for v in sm if v >= 0.6 * sm[-1]] or sm
+        load = [v for v in sm if v >= 0.6 * sm[-1]] or sm      # "under load": idle gaps do not drag the median down
         reasons = []
         for i, name in ((3, 'hw_slowdown'), (4, 'hw_thermal_slowdown'), (5, 'sw_thermal_slowdown'), (6, 'sw_power_cap')):
             if any(r[i].lower().startswith('active') for r in rows):
@@ -147,51 +170,54 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_frames_per_s(frames, ti, nframes, cores):
-    """The CPU oracle (port of the reference path: extract + dyn-reject + SearchByProjection) on `nframes` frames with `cores`
-    worker threads (frames are independent; ctypes releases the GIL inside the C++ oracle)."""
+def cpu_one_frame(frames, ti, f, prev_override=None):
+    """The CPU oracle for one frame: extract -> LK -> dyn-reject -> SearchByProjection.  prev_override: use these previous-frame points
+    instead of the oracle's own LK result (to check the integer stages exactly against the GPU, whose LK differs in the last bits)."""
     import oracle as O
-    from concurrent.futures import ThreadPoolExecutor
     from pysgs import synth
     cam = synth.TUM3
+    k, d = O.extract(frames[f])
+    n = len(k)
+    cur = np.stack([k['x'], k['y']], 1)
+    lk = O.lk_track(frames[f], frames[ti['pidx'][f]], cur)
+    prev = lk if prev_override is None else prev_override[:n]
+    Fm = None if np.isnan(ti['F'][f, 0]) else ti['F'][f]
+    _, keep, _, restored = O.dynreject(cur, prev, Fm, ti['boxes'][f, :ti['nb'][f]], bool(ti['have'][f]), NFEAT)
+    sel = np.arange(n) if restored else np.nonzero(keep)[0]
+    fr = O.FrameArrays(k[sel], ti['ur'][f, :n][sel], d[sel], W, H, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], ti['sf'])
+    m = int(ti['ln'][f])
+    nm, mp, nc = O.search_by_projection_last(fr, ti['T'][f].reshape(4, 4), ti['T'][f].reshape(4, 4), ti['lflags'][f, :m] & 1, ti['lxyz'][f, :m],
+                                             ti['ldesc'][f, :m], (ti['lflags'][f, :m] >> 1) & 1, ti['loct'][f, :m], ti['lang'][f, :m], TH)
+    return dict(n=n, nsel=len(sel), nm=nm, mp=mp, k=k, d=d, sel=sel, lk=lk)
+
+
+def cpu_frames_per_s(frames, ti, nframes, cores):
+    import oracle as O
+    from concurrent.futures import ThreadPoolExecutor
     O.lib()
-
-    def one(f):
-        k, d = O.extract(frames[f])
-        n = len(k)
-        cur = np.stack([k['x'], k['y']], 1)
-        _, keep, _, restored = O.dynreject(cur, ti['prev'][f, :n], ti['F'][f], ti['boxes'][f, :ti['nb'][f]], bool(ti['have'][f]), NFEAT)
-        sel = np.arange(n) if restored else np.nonzero(keep)[0]
-        fr = O.FrameArrays(k[sel], ti['ur'][f, :n][sel], d[sel], W, H, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], ti['sf'])
-        m = int(ti['ln'][f])
-        nm, mp, nc = O.search_by_projection_last(fr, ti['T'][f].reshape(4, 4), ti['T'][f].reshape(4, 4), ti['lflags'][f, :m] & 1, ti['lxyz'][f, :m],
-                                                 ti['ldesc'][f, :m], (ti['lflags'][f, :m] >> 1) & 1, ti['loct'][f, :m], ti['lang'][f, :m], TH)
-        return n, len(sel), nm, mp, k, d, sel
-
     t0 = time.perf_counter()
     with ThreadPoolExecutor(cores) as ex:
-        res = list(ex.map(one, range(nframes)))
-    dt = time.perf_counter() - t0
-    return nframes / dt, res
+        res = list(ex.map(lambda f: cpu_one_frame(frames, ti, f), range(nframes)))   # ctypes releases the GIL inside the C++ oracle
+    return nframes / (time.perf_counter() - t0), res
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU path.  The reference cannot be compiled here (needs OpenCV/Eigen/ncnn/ROS,
     DESIGN.md), so this times the CPU oracle port with all host threads, on the same workload/config."""
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
+    if int(os.environ.get('RANK', '0')) != 0:
         return
+    import oracle as O
     cores = os.cpu_count() or 1
     per_step = max(cores, 8)
-    nb = per_step
-    frames, boxes, unique = make_frames(nb, seed=2, unique=min(32, nb))
-    import oracle as O
-    O.lib()
+    frames, boxes, unique = make_frames(per_step, seed=2, unique=min(32, per_step))
+    pidx = prev_index(per_step, unique)
     cap = NFEAT + 64
-    kps = np.zeros((nb, cap), O.KP_DTYPE); desc = np.zeros((nb, cap, 32), np.uint8); counts = np.zeros(nb, np.int32)
-    for f in range(nb):
+    kps = np.zeros((per_step, cap), O.KP_DTYPE); desc = np.zeros((per_step, cap, 32), np.uint8); counts = np.zeros(per_step, np.int32)
+    prev = np.zeros((per_step, cap, 2), np.float32)
+    for f in range(per_step):
         k, d = O.extract(frames[f]); counts[f] = len(k); kps[f, :len(k)] = k; desc[f, :len(k)] = d
-    ti = make_track_inputs(kps, desc, counts, boxes, cap, cap, unique)
+        prev[f, :len(k)] = O.lk_track(frames[f], frames[pidx[f]], np.stack([k['x'], k['y']], 1))
+    ti = make_track_inputs(kps, desc, counts, boxes, prev, cap, cap, pidx)
     for _ in range(args.warmup):
         cpu_frames_per_s(frames, ti, per_step, cores)
     t0 = time.perf_counter()
@@ -202,8 +228,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'frames/sec ORB extract+match+dyn-reject 640x480', 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-            'config': {'workload': 'S2 walking_xyz-shaped synthetic 640x480 stream, ORB 1000 features, extract+dyn-reject+SearchByProjection(th=15)',
-                       'frames_per_step': per_step, 'note': 'CPU oracle port of the reference path (reference itself needs OpenCV/ROS: unbuildable here)'},
+            'config': {'workload': 'S2 walking_xyz-shaped synthetic 640x480 stream, ORB 1000 features, extract + LK + dyn-reject + SearchByProjection(th=15)',
+                       'frames_per_step': per_step, 'note': 'CPU oracle port of the reference path (the reference itself needs OpenCV/ROS: unbuildable here)'},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': '%d frames per step x %d steps' % (per_step, args.steps)},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
@@ -213,7 +239,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=512, help='frames per GPU per step (512 x 307 KB = 157 MB of input > the 126 MB L2)')
@@ -241,10 +267,13 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     NB = args.batch
     warm = max(args.warmup, 3)
+    L = B.lib()
+    v = C.c_void_p
 
     # ---- workload + one-time set-up (untimed) -------------------------------------------------------------------------
     t_setup = time.time()
     frames, boxes, unique = make_frames(NB, seed=2 + rank)
+    pidx = prev_index(NB, unique)
     sf = S.scale_factors()
     cam = B.make_camera(W, H, synth.TUM3, sf)
     trk = B.Tracker(W, H, cam, NFEAT, 1.2, 8, 20, 7, max_batch=NB, point_cap=NFEAT + 64, max_boxes=4, device=local)
@@ -252,14 +281,23 @@ def main():
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
     h_frames = pin((NB, H, W), torch.uint8); h_frames.numpy()[:] = frames
     h_kps = pin((NB, cap, 28), torch.uint8); h_desc = pin((NB, cap, 32), torch.uint8); h_n = pin((NB,), torch.int32)
-    trk.extract(h_frames.data_ptr(), NB, W * H, W, h_kps.data_ptr(), h_desc.data_ptr(), h_n.data_ptr())
-    kps0 = h_kps.numpy().reshape(NB, cap * 28).view(B.KP_DTYPE).reshape(NB, cap).copy(); desc0 = h_desc.numpy().copy(); n0 = h_n.numpy().copy()
-    ti = make_track_inputs(kps0, desc0, n0, boxes, cap, pcap, unique)
-    # the shared "map database" (last-frame descriptors + positions): rank 0's copy is broadcast once over NVLink
-    keys_h = ['prev', 'ur', 'F', 'boxes', 'nb', 'have', 'lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln', 'T']
-    hp = {k: torch.from_numpy(np.ascontiguousarray(ti[k])).pin_memory() for k in keys_h}
-    dv = {k: v.cuda(non_blocking=True) for k, v in hp.items()}
     d_frames = h_frames.cuda()
+    d_pidx = torch.from_numpy(pidx).cuda()
+    st = torch.cuda.Stream()
+    L.sgs_tracker_extractor.restype = C.c_void_p
+    exh = v(L.sgs_tracker_extractor(trk.h))
+    torch.cuda.synchronize()
+    # set-up pass on the device: extract + LK; the results feed the host-side construction of F / u_right / last-frame points
+    B.check(L.sgs_tracker_extract_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(st.cuda_stream)))
+    B.check(L.sgs_tracker_lk_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(d_pidx.data_ptr()), v(st.cuda_stream)))
+    B.check(L.sgs_extractor_fetch(exh, NB, v(h_kps.data_ptr()), v(h_desc.data_ptr()), cap, v(h_n.data_ptr()), v(st.cuda_stream)))
+    kps0 = h_kps.numpy().reshape(NB, cap * 28).view(B.KP_DTYPE).reshape(NB, cap).copy(); desc0 = h_desc.numpy().copy(); n0 = h_n.numpy().copy()
+    pp = v(); B.check(L.sgs_tracker_prev_xy_device(trk.h, C.byref(pp)))
+    prev0 = B.memcpy_d2h(np.zeros((NB, cap, 2), np.float32), pp.value)
+    ti = make_track_inputs(kps0, desc0, n0, boxes, prev0, cap, pcap, pidx)
+    keys_h = ['ur', 'F', 'boxes', 'nb', 'have', 'lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln', 'T', 'pidx']
+    hp = {k: torch.from_numpy(np.ascontiguousarray(ti[k])).pin_memory() for k in keys_h}
+    dv = {k: t.cuda(non_blocking=True) for k, t in hp.items()}
     bcast_ms = None
     if dist is not None:
         voc = torch.from_numpy(synth.descriptors_s5(1_081_000, 5)).cuda()   # ORBvoc-sized node-descriptor table (34.6 MB), SURVEY section 5
@@ -269,27 +307,27 @@ def main():
         bcast_ms = e0.elapsed_time(e1)
     h_out = dict(kps=pin((NB, cap, 28), torch.uint8), desc=pin((NB, cap, 32), torch.uint8), ur=pin((NB, cap), torch.float32), cnt=pin((NB,), torch.int32),
                  mp=pin((NB, cap), torch.int32), nm=pin((NB,), torch.int32))
-    st = torch.cuda.Stream()
-    ex_handle = B.lib().sgs_tracker_extractor
-    ex_handle.restype = C.c_void_p
-    exh = C.c_void_p(ex_handle(trk.h))
     torch.cuda.synchronize()
     log('[bench] rank %d set-up %.1fs: %d frames/step, mean %.0f keypoints/frame' % (rank, time.time() - t_setup, NB, n0.mean()))
 
-    def track_ptrs(d):
-        return [d[k].data_ptr() for k in ('prev', 'ur', 'F', 'boxes', 'nb', 'have', 'lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln', 'T', 'T')]
+    def track_ptrs(d):   # u_right, F, boxes, nboxes, have_dyn, last_xyz, last_desc, last_flags, last_octave, last_angle, last_n, tcw_cur, tcw_last
+        return [d[k].data_ptr() for k in ('ur', 'F', 'boxes', 'nb', 'have', 'lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln', 'T', 'T')]
 
-    v = C.c_void_p
+    def dev_extract():
+        B.check(L.sgs_tracker_extract_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(st.cuda_stream)))
 
-    def step_device():
-        B.check(B.lib().sgs_tracker_extract_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(st.cuda_stream)))
-        B.check(B.lib().sgs_tracker_track_device(trk.h, NB, *[v(p) for p in track_ptrs(dv)], C.c_float(TH), 0, 1, v(st.cuda_stream)))
+    def dev_lk():
+        B.check(L.sgs_tracker_lk_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(d_pidx.data_ptr()), v(st.cuda_stream)))
+
+    def dev_track():
+        B.check(L.sgs_tracker_track_device(trk.h, NB, v(0), *[v(p) for p in track_ptrs(dv)], C.c_float(TH), 0, 1, v(st.cuda_stream)))
 
     def step_host():
-        # call 1: frames -> keypoints (what the host-side LK needs); descriptors stay on the device (desc = NULL)
+        # call 1: frames -> keypoints (descriptors stay on the device); call 2: LK + dyn-reject + match on the resident batch
         trk.extract(h_frames.data_ptr(), NB, W * H, W, h_kps.data_ptr(), 0, h_n.data_ptr())
-        trk.track(NB, track_ptrs(hp), TH, 0, 1, [h_out['kps'].data_ptr(), h_out['desc'].data_ptr(), h_out['ur'].data_ptr(), h_out['cnt'].data_ptr(),
-                                                 h_out['mp'].data_ptr(), h_out['nm'].data_ptr()])
+        B.check(L.sgs_tracker_track_lk(trk.h, NB, v(hp['pidx'].data_ptr()), *[v(p) for p in track_ptrs(hp)], C.c_float(TH), 0, 1,
+                                       v(h_out['kps'].data_ptr()), v(h_out['desc'].data_ptr()), v(h_out['ur'].data_ptr()), v(h_out['cnt'].data_ptr()),
+                                       v(h_out['mp'].data_ptr()), v(h_out['nm'].data_ptr())))
 
     def barrier():
         torch.cuda.synchronize()
@@ -307,35 +345,32 @@ def main():
     # ---- device-resident leg (value) ----------------------------------------------------------------------------------
     with torch.cuda.stream(st):
         for _ in range(warm):
-            step_device()
+            dev_extract(); dev_lk(); dev_track()
     barrier()
-    B.check(B.lib().sgs_extractor_set_profiling(exh, 1))
+    B.check(L.sgs_extractor_set_profiling(exh, 1))
     sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     barrier()
     with torch.cuda.stream(st):
         ev[0].record(st)
         for i in range(args.steps):
-            B.check(B.lib().sgs_tracker_extract_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(st.cuda_stream)))
-            ev[3 * i + 1].record(st)
-            B.check(B.lib().sgs_tracker_track_device(trk.h, NB, *[v(p) for p in track_ptrs(dv)], C.c_float(TH), 0, 1, v(st.cuda_stream)))
-            ev[3 * i + 2].record(st)
-            ev[3 * i + 3].record(st)
+            dev_extract(); ev[3 * i + 1].record(st)
+            dev_lk(); ev[3 * i + 2].record(st)
+            dev_track(); ev[3 * i + 3].record(st)
     barrier()
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[3 * args.steps]))
     extract_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)) / args.steps
-    track_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)) / args.steps
+    lk_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)) / args.steps
+    track_ms = sum(ev[3 * i + 2].elapsed_time(ev[3 * i + 3]) for i in range(args.steps)) / args.steps
     clocks = sampler.stop()
     ms5 = (C.c_double * 5)(); ncalls = C.c_int()
-    B.check(B.lib().sgs_extractor_stage_times(exh, ms5, C.byref(ncalls)))
+    B.check(L.sgs_extractor_stage_times(exh, ms5, C.byref(ncalls)))
     stage_ms = [ms5[i] / max(1, ncalls.value) for i in range(5)]
-    B.check(B.lib().sgs_extractor_set_profiling(exh, 0))
+    B.check(L.sgs_extractor_set_profiling(exh, 0))
     value = world * NB * args.steps / (total_ms * 1e-3)
+    prev_dev = B.memcpy_d2h(np.zeros((NB, cap, 2), np.float32), pp.value)     # LK output of the last device step
 
-    # results of the last device step: parity spot-check against the host path + counters for the byte accounting
-    rp = [C.c_void_p() for _ in range(7)]
-    B.check(B.lib().sgs_tracker_results_device(trk.h, *[C.byref(x) for x in rp]))
-    step_host()   # also the e2e warm-up
+    step_host()   # e2e warm-up; its outputs are also used for the parity spot-check below
     counts_after = h_out['cnt'].numpy().copy(); nmatch = h_out['nm'].numpy().copy()
 
     # ---- e2e leg: host buffers through the C ABI, copies inside the timed region ----------------------------------------
@@ -352,42 +387,52 @@ def main():
         h2d = h_frames.numel() + sum(hp[k].numel() * hp[k].element_size() for k in keys_h) + hp['T'].numel() * 4
         d2h = (h_kps.numel() + h_n.numel() * 4) + sum(t.numel() * t.element_size() for t in h_out.values())
         e2e = {'value': world * NB * args.steps / dt, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'ms_per_step': 1e3 * dt / args.steps, 'note': 'sgs_tracker_extract + sgs_tracker_track with pinned host buffers; the host-side LK/RANSAC between the two calls is not included (not on the GPU yet)'}
+               'ms_per_step': 1e3 * dt / args.steps,
+               'note': 'sgs_tracker_extract (host frames -> host keypoints) + sgs_tracker_track_lk (LK + dyn-reject + match on the resident batch) with pinned host buffers'}
 
-    # ---- roofline of the dominant kernel --------------------------------------------------------------------------------
+    # ---- roofline of the dominant extractor kernel ------------------------------------------------------------------------
     peaks, peak_kind = measured_peaks()
-    names = ['pyramid(7 launches)', 'fast_cells_kernel', 'quadtree_kernel', 'blur(8 launches)', 'describe_kernel']
+    names = ['pyramid(7 launches)', 'fast_warp_cells_kernel', 'quadtree_kernel', 'blur(8 launches)', 'describe_kernel']
     dom = int(np.argmax(stage_ms))
-    # FAST candidate total of one step (for the algorithmic bytes written by the FAST kernel)
     ncand_frame0 = 0
     for l in range(8):
         nn = C.c_int()
-        B.lib().sgs_extractor_read_candidates(exh, 0, l, None, 0, C.byref(nn))   # count only (returns SGS_ERR_CAPACITY by design)
+        L.sgs_extractor_read_candidates(exh, 0, l, None, 0, C.byref(nn))   # count only (returns SGS_ERR_CAPACITY by design)
         ncand_frame0 += nn.value
-    alg = {0: 1_569_878, 1: ALG_BYTES_FAST_READ + 4 * ncand_frame0, 2: 8 * ncand_frame0 + 4 * int(n0.mean()), 3: 1_901_064, 4: 749 * int(n0.mean()) + 544 * int(n0.mean()) + 60 * int(n0.mean())}
+    nk = int(n0.mean())
+    alg = {0: 1_569_878, 1: ALG_BYTES_FAST_READ + 4 * ncand_frame0, 2: 8 * ncand_frame0 + 4 * nk, 3: 1_901_064, 4: (749 + 544 + 60) * nk}
     dom_bytes = alg[dom] * NB
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
+    step_alg_bytes = (ALG_BYTES_EXTRACT + ALG_BYTES_LK + 76 * nk + 56 * nk + 44 * 8 * nk) * NB
     roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
-                'traffic': None, 'peak_kind': peak_kind + ' copy bandwidth (MEASURED_PEAKS.json)' if peak_kind == 'measured' else 'fallback 6650 GB/s',
+                'traffic': None, 'peak_kind': ('measured copy bandwidth (MEASURED_PEAKS.json)' if peak_kind == 'measured' else 'fallback 6650 GB/s'),
                 'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': stage_ms[dom],
-                'stage_ms': dict(zip(names, [round(x, 4) for x in stage_ms])), 'extract_ms': extract_ms, 'dynreject_match_ms': track_ms,
+                'stage_ms': dict(zip(names, [round(x, 4) for x in stage_ms])), 'extract_ms': extract_ms, 'lk_ms': lk_ms, 'dynreject_match_ms': track_ms,
                 'extract_alg_gbs': ALG_BYTES_EXTRACT * NB / (extract_ms * 1e-3) / 1e9,
-                'extract_frac_of_hbm': ALG_BYTES_EXTRACT * NB / (extract_ms * 1e-3) / 1e9 / peaks['hbm_gbs']}
+                'extract_frac_of_hbm': ALG_BYTES_EXTRACT * NB / (extract_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                'step_alg_gbs': step_alg_bytes / (total_ms / args.steps * 1e-3) / 1e9,
+                'step_frac_of_hbm': step_alg_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                'note': 'every kernel of the step is instruction-issue / latency bound (DRAM throughput 1-12 % in profiles/): the HBM fraction is reported as asked, the binding roof is the integer ALU / issue rate'}
 
-    # ---- CPU baseline on this box's host cores (rank 0 only, N=1 only) ----------------------------------------------------
+    # ---- CPU baseline on this box's host cores (rank 0 only, N=1 only) + parity of the sample -------------------------------
     cpu = None
     if rank == 0 and world == 1:
         cores = os.cpu_count() or 1
         ns = min(args.cpu_sample, NB)
         cpu_fps, res = cpu_frames_per_s(frames, ti, ns, cores)
-        # parity of the sample: the oracle's result for these frames equals what the GPU returned through the host path
         kps_h = h_out['kps'].numpy().reshape(NB, cap * 28).view(B.KP_DTYPE).reshape(NB, cap)
         ok = True
-        for f, (n, nsel, nm, mp, k, d, sel) in enumerate(res):
-            ok &= int(counts_after[f]) == nsel and int(nmatch[f]) == nm and kps_h[f, :nsel].tobytes() == k[sel].tobytes()
-            ok &= bool(np.array_equal(h_out['desc'].numpy()[f, :nsel], d[sel])) and bool(np.array_equal(h_out['mp'].numpy()[f, :nsel], mp))
+        lk_err = []
+        for f, r in enumerate(res):
+            n = r['n']
+            ok &= int(n0[f]) == n and kps0[f, :n].tobytes() == r['k'].tobytes() and bool(np.array_equal(desc0[f, :n], r['d']))   # extraction: bit-exact
+            lk_err.append(np.abs(prev_dev[f, :n] - r['lk']).max(1))                                                                 # LK: tolerance
+            rr = cpu_one_frame(frames, ti, f, prev_override=prev_dev[f])                                                            # integer stages given the GPU's LK
+            ok &= int(counts_after[f]) == rr['nsel'] and int(nmatch[f]) == rr['nm'] and kps_h[f, :rr['nsel']].tobytes() == rr['k'][rr['sel']].tobytes()
+            ok &= bool(np.array_equal(h_out['desc'].numpy()[f, :rr['nsel']], rr['d'][rr['sel']])) and bool(np.array_equal(h_out['mp'].numpy()[f, :rr['nsel']], rr['mp']))
+        e = np.concatenate(lk_err)
         cpu = {'value': cpu_fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': '%d frames of the same batch, %d worker threads' % (ns, cores),
-               'parity_with_gpu_on_sample': bool(ok)}
+               'parity_with_gpu_on_sample': bool(ok), 'lk_abs_err_px': {'median': float(np.median(e)), 'p99': float(np.quantile(e, 0.99)), 'max': float(e.max())}}
         if not ok:
             log('[bench] WARNING: GPU results differ from the oracle on the CPU sample')
 
@@ -395,12 +440,12 @@ def main():
         line = {'metric': 'frames/sec ORB extract+match+dyn-reject 640x480', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': warm, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
                 'data': 'synthetic',
-                'config': {'workload': 'S2 walking_xyz-shaped synthetic 640x480 stream (BASELINE configs[1]), ORB 1000 features / 8 levels / 1.2, extract + dyn-reject(geometry) + SearchByProjection(th=15)',
+                'config': {'workload': 'S2 walking_xyz-shaped synthetic 640x480 stream (BASELINE configs[1]), ORB 1000 features / 8 levels / 1.2: extract + LK(21x21, 4 levels) + dyn-reject(boxes + epipolar) + SearchByProjection(th=15)',
                            'frames_per_gpu_per_step': NB, 'l2_policy': 'inputs larger than L2: %d frames x 307200 B = %.0f MB per step (+ %.0f MB pyramid traffic)' % (NB, NB * 0.3072, NB * 0.95),
                            'sharding': 'independent streams per rank, no data-path collective; one untimed ncclBroadcast of the map/vocabulary table at start-up',
                            'mean_keypoints': float(n0.mean()), 'mean_after_dynreject': float(counts_after.mean()), 'mean_matches': float(nmatch.mean()),
-                           'not_in_step': 'LK optical flow + RANSAC F (src/Frame.cc:445-472) and the detector: inputs precomputed'},
-                'clocks': clocks, 'e2e': e2e, 'gpu_launches': 21 * args.steps, 'roofline': roofline, 'cpu_baseline': cpu}
+                           'not_in_step': 'RANSAC F (src/Frame.cc:469-472; an 8-point F is precomputed on the host) and the detector (boxes precomputed)'},
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps, 'roofline': roofline, 'cpu_baseline': cpu}
         if bcast_ms is not None:
             line['config']['startup_broadcast_ms'] = bcast_ms
         print(json.dumps(line), flush=True)

@@ -287,6 +287,22 @@ SGS_API int sgs_tracker_results_device(const sgs_tracker* t, const sgs_keypoint*
                                        const float** u_right, const int32_t** counts, const int32_t** cur_mp,
                                        const int32_t** nmatches, const uint64_t** ncand);
 SGS_API sgs_extractor* sgs_tracker_extractor(sgs_tracker* t);  /* the extractor owned by the tracker (tables, profiling) */
+/* LK inside the tracker: tracks the keypoints of the last extract call into the previous image of each frame
+ * (d_frames[d_prev_index[f]], the same device batch that was extracted) and keeps the result as the `prev_xy` of the next
+ * sgs_tracker_track_device call made with prev_xy == NULL.  sgs_tracker_prev_xy_device returns that buffer [F][cap][2]. */
+SGS_API int sgs_tracker_lk_device(sgs_tracker* t, const uint8_t* d_frames, int nframes, size_t frame_stride, int pitch,
+                                  const int32_t* d_prev_index, void* stream);
+SGS_API int sgs_tracker_prev_xy_device(const sgs_tracker* t, const float** d_prev_xy);
+/* Host-buffer variant of sgs_tracker_track with the LK stage on the GPU: prev_index [F] (host) replaces prev_xy; the frames are
+ * the ones uploaded by the preceding sgs_tracker_extract call (they are still resident on the device). */
+SGS_API int sgs_tracker_track_lk(sgs_tracker* t, int nframes, const int32_t* prev_index, const float* u_right, const double* F,
+                                 const sgs_rect* boxes, const int32_t* nboxes, const uint8_t* have_dyn, const float* last_xyz,
+                                 const uint8_t* last_desc, const uint8_t* last_flags, const int32_t* last_octave,
+                                 const float* last_angle, const int32_t* last_n, const float* tcw_cur, const float* tcw_last,
+                                 float th, int mono, int check_orientation, sgs_keypoint* kps_out, uint8_t* desc_out,
+                                 float* u_right_out, int32_t* counts_out, int32_t* cur_mp_out, int32_t* nmatches_out);
+/* level 0 of the extractor's own pyramid (the frames of the last host-API extract call), for device-side consumers */
+SGS_API int sgs_extractor_level0_device(const sgs_extractor* ex, const uint8_t** d_frames, int* pitch, size_t* frame_stride);
 
 /* ------------------------------------------------------------------------------------
  * cv::calcOpticalFlowPyrLK as called at src/Frame.cc:445 (window 21x21, maxLevel 3, COUNT|EPS 30 / 0.01): tracks the CURRENT
@@ -294,17 +310,22 @@ SGS_API sgs_extractor* sgs_tracker_extractor(sgs_tracker* t);  /* the extractor 
  * are not produced (the reference ignores them).
  *   sgs_lk_track              : one host image pair, n points (x, y) -> out (x, y)
  *   sgs_lk_track_batch_device : `nframes` device image pairs; points are the keypoints d_kps [F][cap] (counts [F]); writes
- *                               d_prev_xy [F][cap][2] -- the `prev_xy` input of the dyn-reject stage
+ *                               d_prev_xy [F][cap][2] -- the `prev_xy` input of the dyn-reject stage.  The previous images are
+ *                               either a second array d_prev [F] or, when d_prev_index [F] is given, frames of d_cur itself
+ *                               (previous image of frame f = d_cur[d_prev_index[f]]; consecutive frames of streams in one batch)
  * ------------------------------------------------------------------------------------ */
 typedef struct sgs_lk sgs_lk;
 SGS_API int sgs_lk_create(int width, int height, int max_batch, int device, sgs_lk** out);
 SGS_API void sgs_lk_destroy(sgs_lk* k);
 SGS_API int sgs_lk_track(sgs_lk* k, const uint8_t* cur, const uint8_t* prev, int pitch, const float* pts, int n, float* out);
-SGS_API int sgs_lk_track_batch_device(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, int nframes, size_t frame_stride,
-                                      int pitch, const sgs_keypoint* d_kps, const int32_t* d_counts, int cap, float* d_prev_xy,
-                                      void* stream);
+SGS_API int sgs_lk_track_batch_device(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, const int32_t* d_prev_index,
+                                      int nframes, size_t frame_stride, int pitch, const sgs_keypoint* d_kps,
+                                      const int32_t* d_counts, int cap, float* d_prev_xy, void* stream);
 /* parity accessor: pyramid level (1..3) of frame 0 of the last call; which = 0 current image, 1 previous image */
 SGS_API int sgs_lk_read_level(sgs_lk* k, int which, int level, uint8_t* out, int out_pitch);
+
+/* harness helper: synchronous device -> host copy of a buffer returned by one of the *_device accessors */
+SGS_API int sgs_memcpy_d2h(void* dst, const void* d_src, size_t bytes);
 
 /* ---- measurement hooks (bench.py): per-stage device time of the extractor from CUDA events recorded on the launching
  * stream.  Stages: 0 pyramid, 1 FAST, 2 quadtree, 3 blur, 4 orientation+BRIEF.  ms_total5 accumulates over `ncalls`. */

@@ -397,6 +397,20 @@ SGS_API int sgs_extract(sgs_extractor* ex, const uint8_t* gray, int width, int h
     return sgs_extract_batch(ex, gray, 1, (size_t)pitch * height, pitch, kps, desc, cap, n);
 }
 
+SGS_API int sgs_memcpy_d2h(void* dst, const void* d_src, size_t bytes) {   // harness helper: plain synchronous device -> host copy
+    if (!dst || !d_src) return fail_invalid("sgs_memcpy_d2h: NULL");
+    SGS_CUDA_TRY(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return SGS_OK;
+}
+
+SGS_API int sgs_extractor_level0_device(const sgs_extractor* ex, const uint8_t** d_frames, int* pitch, size_t* frame_stride) {
+    if (!ex) return fail_invalid("sgs_extractor_level0_device: NULL handle");
+    if (d_frames) *d_frames = ex->d_pyr;
+    if (pitch) *pitch = ex->plan.lv[0].pitch;
+    if (frame_stride) *frame_stride = (size_t)ex->plan.lv[0].frame_stride;
+    return SGS_OK;
+}
+
 SGS_API int sgs_extractor_read_level(sgs_extractor* ex, int frame, int level, int blurred, uint8_t* out, int out_pitch) {
     if (!ex || !out || level < 0 || level >= ex->plan.nlevels || frame < 0 || frame >= ex->last_nframes) return fail_invalid("sgs_extractor_read_level: bad argument");
     if (level == 0 && !blurred && ex->last_level0_external) return fail_invalid("sgs_extractor_read_level: level 0 aliases the caller's buffer");

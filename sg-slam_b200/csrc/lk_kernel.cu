@@ -69,7 +69,7 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
 // points come either from keypoints (kps != nullptr: kp.x, kp.y) or from a plain float2 array
 __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_constant__ LkLevels L, const sgs_keypoint* __restrict__ kps,
                                                                  const float2* __restrict__ pts, const int32_t* __restrict__ counts, int cap,
-                                                                 float2* __restrict__ out) {
+                                                                 const int32_t* __restrict__ prev_index, float2* __restrict__ out) {
     __shared__ uint8_t s_raw[kLkWarps][24 * 24];
     __shared__ int16_t s_dx[kLkWarps][22 * 22], s_dy[kLkWarps][22 * 22];
     __shared__ int16_t s_iw[kLkWarps][kWin * kWin], s_ix[kLkWarps][kWin * kWin], s_iy[kLkWarps][kWin * kWin];
@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
     const int p = blockIdx.x * kLkWarps + warp;
     const int n = counts ? min(counts[f], cap) : cap;
     if (p >= n) return;
+    const int fj = prev_index ? prev_index[f] : f;       // frame of the batch that plays the role of the previous image
     const int64_t pi = (int64_t)f * cap + p;
     float ptx, pty;
     if (kps) { ptx = kps[pi].x; pty = kps[pi].y; } else { const float2 q = pts[pi]; ptx = q.x; pty = q.y; }
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
         const int lw = L.w[level], lh = L.h[level];
         const uint8_t* Iimg = L.I[level] + (int64_t)f * L.fstride[level];
         const int ipitch = L.pitch[level];
-        const uint8_t* Jimg = L.J[level] + (int64_t)f * (level == 0 ? L.fstrideJ0 : L.fstride[level]);
+        const uint8_t* Jimg = L.J[level] + (int64_t)fj * (level == 0 ? L.fstrideJ0 : L.fstride[level]);
         const int jpitch = level == 0 ? L.pitchJ0 : L.pitch[level];
         const float sc = 1.f / (float)(1 << level);
         float px = __fmul_rn(ptx, sc), py = __fmul_rn(pty, sc);
@@ -209,21 +210,22 @@ void build_pyramid(sgs_lk* k, const uint8_t* d_l0, int pitch0, int64_t fstride0,
     }
 }
 
-int run_lk(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, int nframes, size_t frame_stride, int pitch, const sgs_keypoint* d_kps,
-           const float* d_pts, const int32_t* d_counts, int cap, float* d_out, cudaStream_t st) {
+int run_lk(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, const int32_t* d_prev_index, int nframes, size_t frame_stride, int pitch,
+           const sgs_keypoint* d_kps, const float* d_pts, const int32_t* d_counts, int cap, float* d_out, cudaStream_t st) {
     build_pyramid(k, d_cur, pitch, (int64_t)frame_stride, k->d_pyrI, nframes, st);
-    build_pyramid(k, d_prev, pitch, (int64_t)frame_stride, k->d_pyrJ, nframes, st);
+    const bool same_batch = d_prev_index != nullptr;     // previous images are other frames of the same batch: one pyramid serves both roles
+    if (!same_batch) build_pyramid(k, d_prev, pitch, (int64_t)frame_stride, k->d_pyrJ, nframes, st);
     LkLevels L;
     L.max_level = k->max_level;
     for (int l = 0; l <= k->max_level; ++l) {
         L.w[l] = k->lw[l]; L.h[l] = k->lh[l];
-        if (l == 0) { L.I[0] = d_cur; L.J[0] = d_prev; L.pitch[0] = pitch; L.fstride[0] = (int64_t)frame_stride; }
-        else { L.I[l] = k->d_pyrI + k->loff[l]; L.J[l] = k->d_pyrJ + k->loff[l]; L.pitch[l] = k->lp[l]; L.fstride[l] = k->lfs[l]; }
+        if (l == 0) { L.I[0] = d_cur; L.J[0] = same_batch ? d_cur : d_prev; L.pitch[0] = pitch; L.fstride[0] = (int64_t)frame_stride; }
+        else { L.I[l] = k->d_pyrI + k->loff[l]; L.J[l] = (same_batch ? k->d_pyrI : k->d_pyrJ) + k->loff[l]; L.pitch[l] = k->lp[l]; L.fstride[l] = k->lfs[l]; }
     }
     for (int l = k->max_level + 1; l <= kLkMaxLevel; ++l) { L.I[l] = L.J[l] = nullptr; L.w[l] = L.h[l] = L.pitch[l] = 0; L.fstride[l] = 0; }
     L.pitchJ0 = pitch; L.fstrideJ0 = (int64_t)frame_stride;
     dim3 grid((cap + kLkWarps - 1) / kLkWarps, nframes);
-    lk_track_kernel<<<grid, kLkWarps * 32, 0, st>>>(L, d_kps, reinterpret_cast<const float2*>(d_pts), d_counts, cap, reinterpret_cast<float2*>(d_out));
+    lk_track_kernel<<<grid, kLkWarps * 32, 0, st>>>(L, d_kps, reinterpret_cast<const float2*>(d_pts), d_counts, cap, d_prev_index, reinterpret_cast<float2*>(d_out));
     SGS_CUDA_TRY(cudaGetLastError());
     return SGS_OK;
 }
@@ -263,12 +265,13 @@ SGS_API int sgs_lk_create(int width, int height, int max_batch, int device, sgs_
     return SGS_OK;
 }
 
-SGS_API int sgs_lk_track_batch_device(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, int nframes, size_t frame_stride, int pitch,
-                                      const sgs_keypoint* d_kps, const int32_t* d_counts, int cap, float* d_prev_xy, void* stream) {
-    if (!k || !d_cur || !d_prev || !d_kps || !d_counts || !d_prev_xy) return lk_bad("sgs_lk_track_batch_device: NULL argument");
+SGS_API int sgs_lk_track_batch_device(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, const int32_t* d_prev_index, int nframes,
+                                      size_t frame_stride, int pitch, const sgs_keypoint* d_kps, const int32_t* d_counts, int cap, float* d_prev_xy,
+                                      void* stream) {
+    if (!k || !d_cur || (!d_prev && !d_prev_index) || !d_kps || !d_counts || !d_prev_xy) return lk_bad("sgs_lk_track_batch_device: NULL argument");
     if (nframes < 1 || nframes > k->max_batch || cap < 1) return lk_bad("sgs_lk_track_batch_device: nframes/cap out of range");
     if (pitch < k->w || frame_stride < (size_t)pitch * k->h) return lk_bad("sgs_lk_track_batch_device: pitch/frame_stride too small");
-    return run_lk(k, d_cur, d_prev, nframes, frame_stride, pitch, d_kps, nullptr, d_counts, cap, d_prev_xy, stream ? (cudaStream_t)stream : k->st);
+    return run_lk(k, d_cur, d_prev, d_prev_index, nframes, frame_stride, pitch, d_kps, nullptr, d_counts, cap, d_prev_xy, stream ? (cudaStream_t)stream : k->st);
 }
 
 SGS_API int sgs_lk_track(sgs_lk* k, const uint8_t* cur, const uint8_t* prev, int pitch, const float* pts, int n, float* out) {
@@ -285,7 +288,7 @@ SGS_API int sgs_lk_track(sgs_lk* k, const uint8_t* cur, const uint8_t* prev, int
     SGS_CUDA_TRY(cudaMemcpy2DAsync(k->d_img, dp, cur, pitch, k->w, k->h, cudaMemcpyHostToDevice, k->st));
     SGS_CUDA_TRY(cudaMemcpy2DAsync(k->d_img + (size_t)dp * k->h, dp, prev, pitch, k->w, k->h, cudaMemcpyHostToDevice, k->st));
     SGS_CUDA_TRY(cudaMemcpyAsync(k->d_pts, pts, 8 * (size_t)n, cudaMemcpyHostToDevice, k->st));
-    int rc = run_lk(k, k->d_img, k->d_img + (size_t)dp * k->h, 1, (size_t)dp * k->h, dp, nullptr, k->d_pts, nullptr, n, k->d_out, k->st);
+    int rc = run_lk(k, k->d_img, k->d_img + (size_t)dp * k->h, nullptr, 1, (size_t)dp * k->h, dp, nullptr, k->d_pts, nullptr, n, k->d_out, k->st);
     if (rc != SGS_OK) return rc;
     SGS_CUDA_TRY(cudaMemcpyAsync(out, k->d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, k->st));
     SGS_CUDA_TRY(cudaStreamSynchronize(k->st));

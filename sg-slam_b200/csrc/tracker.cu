@@ -17,6 +17,9 @@ struct sgs_tracker {
     sgs_camera cam{};
     sgs_extractor* ex = nullptr;
     sgs_matcher* mt = nullptr;
+    sgs_lk* lk = nullptr;
+    int width = 0, height = 0;
+    int32_t* d_pidx = nullptr;
     cudaStream_t st = nullptr;
     // device inputs of track()
     float* d_prev = nullptr; float* d_uright_in = nullptr; double* d_F = nullptr; sgs_rect* d_boxes = nullptr; int32_t* d_nboxes = nullptr;
@@ -73,6 +76,8 @@ SGS_API void sgs_tracker_destroy(sgs_tracker* t) {
     cudaSetDevice(t->device);
     if (t->ex) sgs_extractor_destroy(t->ex);
     if (t->mt) sgs_matcher_destroy(t->mt);
+    if (t->lk) sgs_lk_destroy(t->lk);
+    if (t->d_pidx) cudaFree(t->d_pidx);
     void* ptrs[] = {t->d_prev, t->d_uright_in, t->d_F, t->d_boxes, t->d_nboxes, t->d_have, t->d_lxyz, t->d_ldesc, t->d_lflags, t->d_loct, t->d_lang,
                     t->d_ln, t->d_tc, t->d_tl, t->d_kps2, t->d_desc2, t->d_cnt2, t->d_keep, t->d_uright2, t->d_mp, t->d_nm, t->d_ncand};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -92,6 +97,10 @@ SGS_API int sgs_tracker_create(const sgs_orb_params* params, int width, int heig
     sgs_extractor_max_keypoints(t->ex, &t->cap);
     rc = sgs_matcher_create(device, max_batch, t->cap, point_cap, &t->mt);
     if (rc != SGS_OK) { sgs_tracker_destroy(t); return rc; }
+    t->width = width; t->height = height;
+    rc = sgs_lk_create(width, height, max_batch, device, &t->lk);
+    if (rc != SGS_OK) { sgs_tracker_destroy(t); return rc; }
+    if (cudaMalloc(&t->d_pidx, sizeof(int32_t) * (size_t)max_batch) != cudaSuccess) { set_error("sgs_tracker_create: cudaMalloc failed"); sgs_tracker_destroy(t); return SGS_ERR_CUDA; }
     const size_t B = max_batch, K = t->cap, M = point_cap;
     cudaError_t e = cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking);
 #define A(call) if (e == cudaSuccess) e = (call)
@@ -133,9 +142,10 @@ SGS_API int sgs_tracker_track_device(sgs_tracker* t, int nframes, const float* p
                                      const int32_t* nboxes, const uint8_t* have_dyn, const float* last_xyz, const uint8_t* last_desc,
                                      const uint8_t* last_flags, const int32_t* last_octave, const float* last_angle, const int32_t* last_n,
                                      const float* tcw_cur, const float* tcw_last, float th, int mono, int check_orientation, void* stream) {
-    if (!t || !prev_xy || !u_right || !F || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle ||
+    if (!t || !u_right || !F || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle ||
         !last_n || !tcw_cur || !tcw_last) return bad("sgs_tracker_track_device: NULL argument");
     if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_track_device: nframes exceeds the last extract call");
+    if (!prev_xy) prev_xy = t->d_prev;      // filled by sgs_tracker_lk_device
     cudaStream_t st = stream ? (cudaStream_t)stream : t->st;
     const sgs_keypoint* d_kps; const uint8_t* d_desc; const int32_t* d_cnt; int cap = 0;
     sgs_extractor_results_device(t->ex, &d_kps, &d_desc, &d_cnt, &cap);
@@ -201,5 +211,60 @@ SGS_API int sgs_tracker_track(sgs_tracker* t, int nframes, const float* prev_xy,
 }
 
 SGS_API sgs_extractor* sgs_tracker_extractor(sgs_tracker* t) { return t ? t->ex : nullptr; }
+
+SGS_API int sgs_tracker_lk_device(sgs_tracker* t, const uint8_t* d_frames, int nframes, size_t frame_stride, int pitch, const int32_t* d_prev_index,
+                                  void* stream) {
+    if (!t || !d_frames || !d_prev_index) return bad("sgs_tracker_lk_device: NULL argument");
+    if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_lk_device: nframes exceeds the last extract call");
+    const sgs_keypoint* d_kps; const uint8_t* d_desc; const int32_t* d_cnt; int cap = 0;
+    sgs_extractor_results_device(t->ex, &d_kps, &d_desc, &d_cnt, &cap);
+    return sgs_lk_track_batch_device(t->lk, d_frames, nullptr, d_prev_index, nframes, frame_stride, pitch, d_kps, d_cnt, cap, t->d_prev,
+                                     stream ? stream : (void*)t->st);
+}
+
+SGS_API int sgs_tracker_prev_xy_device(const sgs_tracker* t, const float** d_prev_xy) {
+    if (!t || !d_prev_xy) return bad("sgs_tracker_prev_xy_device: NULL");
+    *d_prev_xy = t->d_prev;
+    return SGS_OK;
+}
+
+SGS_API int sgs_tracker_track_lk(sgs_tracker* t, int nframes, const int32_t* prev_index, const float* u_right, const double* F, const sgs_rect* boxes,
+                                 const int32_t* nboxes, const uint8_t* have_dyn, const float* last_xyz, const uint8_t* last_desc,
+                                 const uint8_t* last_flags, const int32_t* last_octave, const float* last_angle, const int32_t* last_n,
+                                 const float* tcw_cur, const float* tcw_last, float th, int mono, int check_orientation, sgs_keypoint* kps_out,
+                                 uint8_t* desc_out, float* u_right_out, int32_t* counts_out, int32_t* cur_mp_out, int32_t* nmatches_out) {
+    if (!t || !prev_index) return bad("sgs_tracker_track_lk: NULL argument");
+    if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_track_lk: nframes exceeds the last sgs_tracker_extract call");
+    SGS_CUDA_TRY(cudaSetDevice(t->device));
+    for (int f = 0; f < nframes; ++f) if (prev_index[f] < 0 || prev_index[f] >= nframes) return bad("sgs_tracker_track_lk: prev_index out of range");
+    SGS_CUDA_TRY(cudaMemcpyAsync(t->d_pidx, prev_index, sizeof(int32_t) * (size_t)nframes, cudaMemcpyHostToDevice, t->st));
+    const uint8_t* d_frames; int pitch; size_t fstride;
+    sgs_extractor_level0_device(t->ex, &d_frames, &pitch, &fstride);
+    int rc = sgs_tracker_lk_device(t, d_frames, nframes, fstride, pitch, t->d_pidx, t->st);
+    if (rc != SGS_OK) return rc;
+    // same as sgs_tracker_track from here on, with prev_xy already on the device
+    if (!u_right || !F || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle || !last_n || !tcw_cur ||
+        !tcw_last || !kps_out || !desc_out || !counts_out || !cur_mp_out || !nmatches_out) return bad("sgs_tracker_track_lk: NULL argument");
+    const size_t B = nframes, K = t->cap, M = t->point_cap;
+    cudaStream_t st = t->st;
+#define H2D(dst, src, bytes) SGS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st))
+    H2D(t->d_uright_in, u_right, B * K * 4); H2D(t->d_F, F, B * 72);
+    if (boxes) H2D(t->d_boxes, boxes, B * t->max_boxes * sizeof(sgs_rect));
+    H2D(t->d_nboxes, nboxes, B * 4); H2D(t->d_have, have_dyn, B);
+    H2D(t->d_lxyz, last_xyz, B * M * 12); H2D(t->d_ldesc, last_desc, B * M * 32); H2D(t->d_lflags, last_flags, B * M);
+    H2D(t->d_loct, last_octave, B * M * 4); H2D(t->d_lang, last_angle, B * M * 4); H2D(t->d_ln, last_n, B * 4);
+    H2D(t->d_tc, tcw_cur, B * 64); H2D(t->d_tl, tcw_last, B * 64);
+#undef H2D
+    rc = sgs_tracker_track_device(t, nframes, nullptr, t->d_uright_in, t->d_F, t->d_boxes, t->d_nboxes, t->d_have, t->d_lxyz, t->d_ldesc, t->d_lflags,
+                                  t->d_loct, t->d_lang, t->d_ln, t->d_tc, t->d_tl, th, mono, check_orientation, st);
+    if (rc != SGS_OK) return rc;
+#define D2H(dst, src, bytes) SGS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st))
+    D2H(kps_out, t->d_kps2, B * K * sizeof(sgs_keypoint)); D2H(desc_out, t->d_desc2, B * K * 32); D2H(counts_out, t->d_cnt2, B * 4);
+    if (u_right_out) D2H(u_right_out, t->d_uright2, B * K * 4);
+    D2H(cur_mp_out, t->d_mp, B * K * 4); D2H(nmatches_out, t->d_nm, B * 4);
+#undef D2H
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    return SGS_OK;
+}
 
 }  // extern "C"

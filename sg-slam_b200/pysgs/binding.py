@@ -74,6 +74,7 @@ ABI_SYMBOLS = [
     'sgs_tracker_extract_device', 'sgs_tracker_track_device', 'sgs_tracker_results_device', 'sgs_tracker_extractor',
     'sgs_extractor_set_profiling', 'sgs_extractor_stage_times',
     'sgs_lk_create', 'sgs_lk_destroy', 'sgs_lk_track', 'sgs_lk_track_batch_device', 'sgs_lk_read_level',
+    'sgs_tracker_lk_device', 'sgs_tracker_prev_xy_device', 'sgs_tracker_track_lk', 'sgs_extractor_level0_device', 'sgs_memcpy_d2h',
 ]
 
 
@@ -387,4 +388,9 @@ class LK:
 
     def track_batch_device(self, d_cur, d_prev, nframes, frame_stride, pitch, d_kps, d_counts, cap, d_prev_xy, stream=0):
         v = C.c_void_p
-        check(lib().sgs_lk_track_batch_device(self.h, v(d_cur), v(d_prev), nframes, C.c_size_t(frame_stride), pitch, v(d_kps), v(d_counts), cap, v(d_prev_xy), v(stream)))
+        check(lib().sgs_lk_track_batch_device(self.h, v(d_cur), v(d_prev), v(0), nframes, C.c_size_t(frame_stride), pitch, v(d_kps), v(d_counts), cap, v(d_prev_xy), v(stream)))
+
+
+def memcpy_d2h(dst_array, d_ptr):
+    check(lib().sgs_memcpy_d2h(_p(dst_array), C.c_void_p(d_ptr), C.c_size_t(dst_array.nbytes)))
+    return dst_array
