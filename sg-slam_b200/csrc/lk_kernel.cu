@@ -6,8 +6,8 @@
 // (tolerance stated in tests/test_gpu_lk.py).  status/err are not produced (the reference ignores them, quirk Q4); a level
 // that fails leaves the running estimate untouched.
 //
-// One warp per point; the warp keeps, in shared memory, the 24x24 raw patch of I, its 22x22 Scharr derivatives, the 21x21
-// interpolated window (I, Ix, Iy as int16) and the 22x22 patch of J of the current iteration.
+// One warp per point; the 21x21 window is tiled over the lanes (7x2 pixels each + one pixel of the last column) and lives in
+// registers for the whole level; no shared memory.
 #include <cuda_runtime.h>
 
 #include <vector>
@@ -51,10 +51,24 @@ __global__ void __launch_bounds__(256) lk_pyrdown_kernel(const uint8_t* __restri
     dst[(int64_t)blockIdx.z * dfstride + (int64_t)y * dpitch + x] = (uint8_t)((v + 128) >> 8);
 }
 
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+// Exact warp sums of per-lane int32 partials.  |partial| < 15 * 8160 * 4080 < 2^28.9, so the first stages stay in int32 (4 lanes for
+// the mismatch sums, 8 lanes for the gradient sums whose terms are < 4080^2) before widening.
+__device__ __forceinline__ long long warp_sum_grad(int v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
+    long long w = v;
+    w += __shfl_xor_sync(0xffffffffu, w, 2); w += __shfl_xor_sync(0xffffffffu, w, 1);
+    return w;
+}
+// two sums at once: after the first exchange lanes 0..15 carry s1 and lanes 16..31 carry s2; every lane gets both totals as float
+__device__ __forceinline__ void warp_sum_pair(int s1, int s2, int lane, float scale, float& B1, float& B2) {
+    const bool hi = lane >= 16;
+    const int give = hi ? s1 : s2, keep = hi ? s2 : s1;
+    int v = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    long long w = v;
+    w += __shfl_xor_sync(0xffffffffu, w, 4); w += __shfl_xor_sync(0xffffffffu, w, 2); w += __shfl_xor_sync(0xffffffffu, w, 1);
+    const float mine = __fmul_rn((float)w, scale), other = __shfl_xor_sync(0xffffffffu, mine, 16);
+    B1 = hi ? other : mine; B2 = hi ? mine : other;
 }
 
 __device__ __forceinline__ int lk_descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
@@ -66,14 +80,156 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
     w11 = 16384 - w00 - w01 - w10;
 }
 
+
+// Window set-up of one level, in the tiled ownership of lk_mismatch_tiles (see there): each lane loads the 10x5 raw bytes of I under
+// its 7x2 window pixels (reflect-101 outside the image), forms the Scharr rows it needs (8x3; zero where the derivative position is
+// outside the image, BORDER_CONSTANT) and interpolates I, Ix, Iy with the 14-bit weights; lanes 0..20 do the same for their pixel of
+// window column 20.  Outputs stay in registers: C = 256 - 512 Iw, GX = Ix, GY = Iy; s11/s12/s22 are this lane's share of the
+// gradient matrix (exact in int32: 15 terms of < 2^24.1).  kInside: the whole 24x24 raw patch lies inside the image.
+template <bool kInside>
+__device__ __forceinline__ void lk_setup_tiles(const uint8_t* __restrict__ img, int pitch, int lw, int lh, int ipx, int ipy,
+                                               int k2, int g7, int erow, int lane, int w00, int w01, int w10, int w11,
+                                               int (&C)[14], int (&GX)[14], int (&GY)[14], int& Ce, int& GXe, int& GYe,
+                                               int& s11, int& s12, int& s22) {
+    int R[10][5], E[4][4];
+    if (kInside) {
+        const uint8_t* p = img + (int64_t)(ipy - 1 + g7) * pitch + (ipx - 1 + k2);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+#pragma unroll
+            for (int x = 0; x < 5; ++x) R[r][x] = __ldg(p + x);
+            p += pitch;
+        }
+        const uint8_t* q = img + (int64_t)(ipy - 1 + erow) * pitch + (ipx + 19);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) E[r][x] = __ldg(q + x);
+            q += pitch;
+        }
+    } else {
+        int cx[5], ce[4];
+#pragma unroll
+        for (int x = 0; x < 5; ++x) cx[x] = lk_refl(ipx - 1 + k2 + x, lw);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) ce[x] = lk_refl(ipx + 19 + x, lw);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint8_t* p = img + (int64_t)lk_refl(ipy - 1 + g7 + r, lh) * pitch;
+#pragma unroll
+            for (int x = 0; x < 5; ++x) R[r][x] = __ldg(p + cx[x]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint8_t* q = img + (int64_t)lk_refl(ipy - 1 + erow + r, lh) * pitch;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) E[r][x] = __ldg(q + ce[x]);
+        }
+    }
+    // Scharr: t0(x) = 3 (s[y-1][x] + s[y+1][x]) + 10 s[y][x],  t1(x) = s[y+1][x] - s[y-1][x];  dx = t0(x+1) - t0(x-1),
+    // dy = 3 (t1(x-1) + t1(x+1)) + 10 t1(x)
+    int Gx[8][3], Gy[8][3];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        int t0[5], t1[5];
+#pragma unroll
+        for (int x = 0; x < 5; ++x) { t0[x] = (R[d][x] + R[d + 2][x]) * 3 + R[d + 1][x] * 10; t1[x] = R[d + 2][x] - R[d][x]; }
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            int gx = t0[x + 2] - t0[x], gy = (t1[x] + t1[x + 2]) * 3 + t1[x + 1] * 10;
+            if (!kInside) {
+                const bool in = (unsigned)(ipx + k2 + x) < (unsigned)lw && (unsigned)(ipy + g7 + d) < (unsigned)lh;
+                gx = in ? gx : 0; gy = in ? gy : 0;
+            }
+            Gx[d][x] = gx; Gy[d][x] = gy;
+        }
+    }
+    int a11 = 0, a12 = 0, a22 = 0;
+#pragma unroll
+    for (int r = 0; r < 7; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int ival = (R[r + 1][c + 1] * w00 + R[r + 1][c + 2] * w01 + R[r + 2][c + 1] * w10 + R[r + 2][c + 2] * w11 + 256) >> 9;
+            const int ixv = (Gx[r][c] * w00 + Gx[r][c + 1] * w01 + Gx[r + 1][c] * w10 + Gx[r + 1][c + 1] * w11 + 8192) >> 14;
+            const int iyv = (Gy[r][c] * w00 + Gy[r][c + 1] * w01 + Gy[r + 1][c] * w10 + Gy[r + 1][c + 1] * w11 + 8192) >> 14;
+            C[2 * r + c] = 256 - 512 * ival; GX[2 * r + c] = ixv; GY[2 * r + c] = iyv;
+            a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv;
+        }
+    if (lane >= 30) a11 = a12 = a22 = 0;
+    // the pixel of column 20
+    int ex[2][2], ey[2][2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        int t0[4], t1[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { t0[x] = (E[d][x] + E[d + 2][x]) * 3 + E[d + 1][x] * 10; t1[x] = E[d + 2][x] - E[d][x]; }
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            int gx = t0[x + 2] - t0[x], gy = (t1[x] + t1[x + 2]) * 3 + t1[x + 1] * 10;
+            if (!kInside) {
+                const bool in = (unsigned)(ipx + 20 + x) < (unsigned)lw && (unsigned)(ipy + erow + d) < (unsigned)lh;
+                gx = in ? gx : 0; gy = in ? gy : 0;
+            }
+            ex[d][x] = gx; ey[d][x] = gy;
+        }
+    }
+    const int ival = (E[1][1] * w00 + E[1][2] * w01 + E[2][1] * w10 + E[2][2] * w11 + 256) >> 9;
+    const int ixv = (ex[0][0] * w00 + ex[0][1] * w01 + ex[1][0] * w10 + ex[1][1] * w11 + 8192) >> 14;
+    const int iyv = (ey[0][0] * w00 + ey[0][1] * w01 + ey[1][0] * w10 + ey[1][1] * w11 + 8192) >> 14;
+    Ce = 256 - 512 * ival; GXe = lane < kWin ? ixv : 0; GYe = lane < kWin ? iyv : 0;
+    s11 = a11 + GXe * GXe; s12 = a12 + GXe * GYe; s22 = a22 + GYe * GYe;
+}
+
+// Mismatch vector of one iteration.  The 21x21 window is tiled over the warp: lane = 10 g + k (k < 10, g < 3) owns window columns
+// 2k, 2k+1 of rows 7g .. 7g+6 (14 pixels, held in registers: C = 256 - 512 Iw folds the descale rounding and the subtraction of the
+// template into the first multiply-add), and lanes 0..20 each own one pixel of the left-over column 20.  Lanes 30, 31 carry zero
+// gradients.  Every lane loads its own 8x3 (+2x2) bytes of J; the sums per lane are < 15 * 2^25: exact in int32.
+template <bool kInside>
+__device__ __forceinline__ void lk_mismatch_tiles(const uint8_t* __restrict__ img, int pitch, int lw, int lh, int inx, int iny,
+                                                  int k2, int g7, int erow, bool lane30, int w00, int w01, int w10, int w11,
+                                                  const int (&C)[14], const int (&GX)[14], const int (&GY)[14], int Ce, int GXe, int GYe,
+                                                  int& s1, int& s2) {
+    int v[8][3];
+    int e00, e01, e10, e11;
+    if (kInside) {
+        const uint8_t* p = img + (int64_t)(iny + g7) * pitch + (inx + k2);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            v[r][0] = __ldg(p); v[r][1] = __ldg(p + 1); v[r][2] = __ldg(p + 2);
+            p += pitch;
+        }
+        const uint8_t* q = img + (int64_t)(iny + erow) * pitch + (inx + 20);
+        e00 = __ldg(q); e01 = __ldg(q + 1); e10 = __ldg(q + pitch); e11 = __ldg(q + pitch + 1);
+    } else {
+        const int x0 = lk_refl(inx + k2, lw), x1 = lk_refl(inx + k2 + 1, lw), x2 = lk_refl(inx + k2 + 2, lw);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint8_t* p = img + (int64_t)lk_refl(iny + g7 + r, lh) * pitch;
+            v[r][0] = __ldg(p + x0); v[r][1] = __ldg(p + x1); v[r][2] = __ldg(p + x2);
+        }
+        const int xe0 = lk_refl(inx + 20, lw), xe1 = lk_refl(inx + 21, lw);
+        const uint8_t* q0 = img + (int64_t)lk_refl(iny + erow, lh) * pitch;
+        const uint8_t* q1 = img + (int64_t)lk_refl(iny + erow + 1, lh) * pitch;
+        e00 = __ldg(q0 + xe0); e01 = __ldg(q0 + xe1); e10 = __ldg(q1 + xe0); e11 = __ldg(q1 + xe1);
+    }
+    int a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const int da = (v[r][0] * w00 + v[r][1] * w01 + v[r + 1][0] * w10 + v[r + 1][1] * w11 + C[2 * r]) >> 9;
+        const int db = (v[r][1] * w00 + v[r][2] * w01 + v[r + 1][1] * w10 + v[r + 1][2] * w11 + C[2 * r + 1]) >> 9;
+        a1 += da * GX[2 * r]; a2 += da * GY[2 * r];
+        b1 += db * GX[2 * r + 1]; b2 += db * GY[2 * r + 1];
+    }
+    const int de = (e00 * w00 + e01 * w01 + e10 * w10 + e11 * w11 + Ce) >> 9;
+    if (lane30) { a1 = 0; a2 = 0; b1 = 0; b2 = 0; }
+    s1 = a1 + b1 + de * GXe; s2 = a2 + b2 + de * GYe;
+}
+
 // points come either from keypoints (kps != nullptr: kp.x, kp.y) or from a plain float2 array
+// (128 registers per thread: forcing more resident blocks spills the register window and measured 15-30 % slower)
 __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_constant__ LkLevels L, const sgs_keypoint* __restrict__ kps,
                                                                  const float2* __restrict__ pts, const int32_t* __restrict__ counts, int cap,
                                                                  const int32_t* __restrict__ prev_index, float2* __restrict__ out) {
-    __shared__ uint8_t s_raw[kLkWarps][24 * 24];
-    __shared__ int16_t s_dx[kLkWarps][22 * 22], s_dy[kLkWarps][22 * 22];
-    __shared__ int16_t s_iw[kLkWarps][kWin * kWin], s_ix[kLkWarps][kWin * kWin], s_iy[kLkWarps][kWin * kWin];
-    __shared__ uint8_t s_j[kLkWarps][22 * 24];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
     const int p = blockIdx.x * kLkWarps + warp;
@@ -83,8 +239,8 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
     const int64_t pi = (int64_t)f * cap + p;
     float ptx, pty;
     if (kps) { ptx = kps[pi].x; pty = kps[pi].y; } else { const float2 q = pts[pi]; ptx = q.x; pty = q.y; }
-    uint8_t* raw = s_raw[warp]; int16_t* dxp = s_dx[warp]; int16_t* dyp = s_dy[warp];
-    int16_t* Iw = s_iw[warp]; int16_t* Ix = s_ix[warp]; int16_t* Iy = s_iy[warp]; uint8_t* jp = s_j[warp];
+    const int tl = min(lane, 29);
+    const int k2 = 2 * (tl % 10), g7 = 7 * (tl / 10), erow = min(lane, kWin - 1);      // this lane's tile of the window (see lk_mismatch_tiles)
     const float half_win = 10.f;                       // (winSize - 1) * 0.5
     const float flt_scale = 1.f / (1 << 20);
     float nx = 0.f, ny = 0.f;
@@ -104,43 +260,14 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
         if (ipx < -kWin || ipx >= lw || ipy < -kWin || ipy >= lh) continue;
         int w00, w01, w10, w11;
         lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
-        // raw 24x24 patch of I around the window (one ring for the bilinear +1, one ring for Scharr), reflect-101 outside the image
-        __syncwarp();
-        for (int i = lane; i < 24 * 24; i += 32) {
-            const int yy = i / 24, xx = i - yy * 24;
-            raw[i] = __ldg(Iimg + (int64_t)lk_refl(ipy - 1 + yy, lh) * ipitch + lk_refl(ipx - 1 + xx, lw));
-        }
-        __syncwarp();
-        // Scharr derivatives at the 22x22 positions the bilinear window touches; zero outside the image (BORDER_CONSTANT)
-        for (int i = lane; i < 22 * 22; i += 32) {
-            const int yy = i / 22, xx = i - yy * 22;
-            const int X = ipx + xx, Y = ipy + yy;
-            int dx = 0, dy = 0;
-            if (X >= 0 && X < lw && Y >= 0 && Y < lh) {
-                const uint8_t* r0 = raw + yy * 24 + xx;            // raw(yy, xx) == image (Y-1, X-1)
-                const int a00 = r0[0], a01 = r0[1], a02 = r0[2], a10 = r0[24], a12 = r0[26], a20 = r0[48], a21 = r0[49], a22 = r0[50];
-                // t0(x) = 3 (s[y-1][x] + s[y+1][x]) + 10 s[y][x];  t1(x) = s[y+1][x] - s[y-1][x]
-                const int t0m = (a00 + a20) * 3 + a10 * 10, t0p = (a02 + a22) * 3 + a12 * 10;
-                const int t1m = a20 - a00, t1c = a21 - a01, t1p = a22 - a02;
-                dx = t0p - t0m;
-                dy = (t1m + t1p) * 3 + t1c * 10;
-            }
-            dxp[i] = (int16_t)dx; dyp[i] = (int16_t)dy;
-        }
-        __syncwarp();
-        long long a11 = 0, a12 = 0, a22 = 0;
-        for (int i = lane; i < kWin * kWin; i += 32) {
-            const int yy = i / kWin, xx = i - yy * kWin;
-            const uint8_t* r = raw + (yy + 1) * 24 + xx + 1;
-            const int ival = lk_descale(r[0] * w00 + r[1] * w01 + r[24] * w10 + r[25] * w11, 9);
-            const int16_t* gx = dxp + yy * 22 + xx; const int16_t* gy = dyp + yy * 22 + xx;
-            const int ixv = lk_descale(gx[0] * w00 + gx[1] * w01 + gx[22] * w10 + gx[23] * w11, 14);
-            const int iyv = lk_descale(gy[0] * w00 + gy[1] * w01 + gy[22] * w10 + gy[23] * w11, 14);
-            Iw[i] = (int16_t)ival; Ix[i] = (int16_t)ixv; Iy[i] = (int16_t)iyv;
-            a11 += (long long)(ixv * ixv); a12 += (long long)(ixv * iyv); a22 += (long long)(iyv * iyv);
-        }
-        const float A11 = __fmul_rn((float)warp_sum_ll(a11), flt_scale), A12 = __fmul_rn((float)warp_sum_ll(a12), flt_scale),
-                    A22 = __fmul_rn((float)warp_sum_ll(a22), flt_scale);
+        int s11, s12, s22;
+        int C[14], GX[14], GY[14], Ce, GXe, GYe;
+        if (ipx >= 1 && ipx + 22 < lw && ipy >= 1 && ipy + 22 < lh)
+            lk_setup_tiles<true>(Iimg, ipitch, lw, lh, ipx, ipy, k2, g7, erow, lane, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s11, s12, s22);
+        else
+            lk_setup_tiles<false>(Iimg, ipitch, lw, lh, ipx, ipy, k2, g7, erow, lane, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s11, s12, s22);
+        const float A11 = __fmul_rn((float)warp_sum_grad(s11), flt_scale), A12 = __fmul_rn((float)warp_sum_grad(s12), flt_scale),
+                    A22 = __fmul_rn((float)warp_sum_grad(s22), flt_scale);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dd = __fsub_rn(A11, A22);
         const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
@@ -153,20 +280,13 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
             const int inx = (int)floorf(qx), iny = (int)floorf(qy);
             if (inx < -kWin || inx >= lw || iny < -kWin || iny >= lh) break;
             lk_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
-            __syncwarp();
-            for (int i = lane; i < 22 * 22; i += 32) {
-                const int yy = i / 22, xx = i - yy * 22;
-                jp[yy * 24 + xx] = __ldg(Jimg + (int64_t)lk_refl(iny + yy, lh) * jpitch + lk_refl(inx + xx, lw));
-            }
-            __syncwarp();
-            long long b1 = 0, b2 = 0;
-            for (int i = lane; i < kWin * kWin; i += 32) {
-                const int yy = i / kWin, xx = i - yy * kWin;
-                const uint8_t* r = jp + yy * 24 + xx;
-                const int diff = lk_descale(r[0] * w00 + r[1] * w01 + r[24] * w10 + r[25] * w11, 9) - Iw[i];
-                b1 += (long long)(diff * Ix[i]); b2 += (long long)(diff * Iy[i]);
-            }
-            const float B1 = __fmul_rn((float)warp_sum_ll(b1), flt_scale), B2 = __fmul_rn((float)warp_sum_ll(b2), flt_scale);
+            int s1, s2;
+            if (inx >= 0 && inx + 21 < lw && iny >= 0 && iny + 21 < lh)
+                lk_mismatch_tiles<true>(Jimg, jpitch, lw, lh, inx, iny, k2, g7, erow, lane >= 30, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s1, s2);
+            else
+                lk_mismatch_tiles<false>(Jimg, jpitch, lw, lh, inx, iny, k2, g7, erow, lane >= 30, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s1, s2);
+            float B1, B2;
+            warp_sum_pair(s1, s2, lane, flt_scale, B1, B2);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, B2), __fmul_rn(A22, B1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, B1), __fmul_rn(A11, B2)), D);
             qx = __fadd_rn(qx, dx); qy = __fadd_rn(qy, dy);
