@@ -267,3 +267,34 @@ def lk_pyr_level(img, level):
     out = np.zeros((h.value, w.value), np.uint8)
     lib().sgo_lk_pyr_level(_p(img), img.shape[1], img.shape[0], img.strides[0], level, _p(out), C.byref(w), C.byref(h))
     return out
+
+
+def run7point(m1, m2):
+    """fundam.cpp run7Point on 7 point pairs: list of 3x3 double matrices (1..3)."""
+    a = np.ascontiguousarray(m1, np.float32).reshape(7, 2); b = np.ascontiguousarray(m2, np.float32).reshape(7, 2)
+    F = np.zeros(27, np.float64)
+    lib().sgo_run7point.restype = C.c_int
+    n = lib().sgo_run7point(_p(a), _p(b), _p(F))
+    return [F[9 * k:9 * k + 9].reshape(3, 3).copy() for k in range(max(n, 0))]
+
+
+def find_fundamental_ransac(pts1, pts2, thresh=1.0, confidence=0.99, max_iters=1000):
+    """cv::findFundamentalMat(pts1, pts2, FM_RANSAC, thresh, confidence) (src/Frame.cc:469-472).
+    Returns (F 3x3 float64 or None, mask uint8 [n], info int32 [3] = iterations run, inliers, final niters)."""
+    a = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2); b = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+    F = np.zeros(9, np.float64); mask = np.zeros(len(a), np.uint8); info = np.zeros(3, np.int32)
+    fn = lib().sgo_find_fundamental_ransac
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    ok = fn(_p(a), _p(b), len(a), float(thresh), float(confidence), int(max_iters), _p(F), _p(mask), _p(info))
+    return (F.reshape(3, 3) if ok else None), mask, info
+
+
+def select_static_pairs(cur, prev, boxes, prev_have_dyn):
+    """src/Frame.cc:454-472: the point pairs handed to findFundamentalMat."""
+    a = np.ascontiguousarray(cur, np.float32).reshape(-1, 2); b = np.ascontiguousarray(prev, np.float32).reshape(-1, 2)
+    bx = np.ascontiguousarray(boxes, np.float32).reshape(-1, 4)
+    s1 = np.zeros_like(a); s2 = np.zeros_like(b)
+    lib().sgo_select_static_pairs.restype = C.c_int
+    n = lib().sgo_select_static_pairs(_p(a), _p(b), len(a), _p(bx), len(bx), int(bool(prev_have_dyn)), _p(s1), _p(s2))
+    return s1[:n], s2[:n]

@@ -1086,6 +1086,24 @@ inline void scharr_at(const LkLevel& L, int x, int y, int& dx, int& dy) {
 
 inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
+// What buildOpticalFlowPyramid(withDerivatives) hands the tracker: the level with a REFLECT_101 border and its Scharr derivative
+// image with a zero border, so the window loops below read straight through the image edge like OpenCV's do.
+struct LkPadded {
+    static constexpr int PAD = 23;            // the window reaches 21 px before and 22 px past the image
+    int w = 0, h = 0, stride = 0;
+    std::vector<uint8_t> px; std::vector<int16_t> dx, dy;
+    inline const uint8_t* at(int x, int y) const { return px.data() + (size_t)(y + PAD) * stride + (x + PAD); }
+    inline size_t idx(int x, int y) const { return (size_t)(y + PAD) * stride + (x + PAD); }
+    void build(const LkLevel& L) {
+        w = L.w; h = L.h; stride = w + 2 * PAD;
+        px.assign((size_t)stride * (h + 2 * PAD), 0); dx.assign(px.size(), 0); dy.assign(px.size(), 0);
+        for (int y = -PAD; y < h + PAD; y++)
+            for (int x = -PAD; x < w + PAD; x++) px[idx(x, y)] = (uint8_t)L.at(x, y);
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) { int gx, gy; scharr_at(L, x, y, gx, gy); dx[idx(x, y)] = (int16_t)gx; dy[idx(x, y)] = (int16_t)gy; }
+    }
+};
+
 }  // namespace
 
 // pts / out: n x 2 float.  I, J: 8-bit gray images of the same size.  Returns 0.
@@ -1103,11 +1121,13 @@ SGO_API int sgo_lk_track(const uint8_t* I0, const uint8_t* J0, int w, int h, int
         pyr_down(I[l - 1], I[l]); pyr_down(J[l - 1], J[l]);
         maxLevel = l;
     }
+    std::vector<LkPadded> PI(maxLevel + 1), PJ(maxLevel + 1);
+    for (int l = 0; l <= maxLevel; l++) { PI[l].build(I[l]); PJ[l].build(J[l]); }
     std::vector<float> nx(n), ny(n);
     std::vector<short> Iw(WIN * WIN), dIx(WIN * WIN), dIy(WIN * WIN);
     const float halfWin = (WIN - 1) * 0.5f;
     for (int level = maxLevel; level >= 0; level--) {
-        const LkLevel& LI = I[level]; const LkLevel& LJ = J[level];
+        const LkPadded& LI = PI[level]; const LkPadded& LJ = PJ[level];
         for (int p = 0; p < n; p++) {
             float px = pts[2 * p] * (float)(1. / (1 << level)), py = pts[2 * p + 1] * (float)(1. / (1 << level));
             float qx, qy;
@@ -1122,17 +1142,18 @@ SGO_API int sgo_lk_track(const uint8_t* I0, const uint8_t* J0, int w, int h, int
             int iw00 = cvRoundF((1.f - a) * (1.f - b) * (1 << W_BITS)), iw01 = cvRoundF(a * (1.f - b) * (1 << W_BITS));
             int iw10 = cvRoundF((1.f - a) * b * (1 << W_BITS)), iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
             float iA11 = 0, iA12 = 0, iA22 = 0;
-            for (int y = 0; y < WIN; y++)
+            const int st = LI.stride;
+            for (int y = 0; y < WIN; y++) {
+                const size_t o = LI.idx(ipx, ipy + y);
+                const uint8_t* src = LI.px.data() + o; const int16_t* gx = LI.dx.data() + o; const int16_t* gy = LI.dy.data() + o;
                 for (int x = 0; x < WIN; x++) {
-                    const int X = ipx + x, Y = ipy + y;
-                    const int ival = descale(LI.at(X, Y) * iw00 + LI.at(X + 1, Y) * iw01 + LI.at(X, Y + 1) * iw10 + LI.at(X + 1, Y + 1) * iw11, W_BITS - 5);
-                    int d00x, d00y, d01x, d01y, d10x, d10y, d11x, d11y;
-                    scharr_at(LI, X, Y, d00x, d00y); scharr_at(LI, X + 1, Y, d01x, d01y); scharr_at(LI, X, Y + 1, d10x, d10y); scharr_at(LI, X + 1, Y + 1, d11x, d11y);
-                    const int ixval = descale(d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11, W_BITS);
-                    const int iyval = descale(d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11, W_BITS);
+                    const int ival = descale(src[x] * iw00 + src[x + 1] * iw01 + src[x + st] * iw10 + src[x + st + 1] * iw11, W_BITS - 5);
+                    const int ixval = descale(gx[x] * iw00 + gx[x + 1] * iw01 + gx[x + st] * iw10 + gx[x + st + 1] * iw11, W_BITS);
+                    const int iyval = descale(gy[x] * iw00 + gy[x + 1] * iw01 + gy[x + st] * iw10 + gy[x + st + 1] * iw11, W_BITS);
                     Iw[y * WIN + x] = (short)ival; dIx[y * WIN + x] = (short)ixval; dIy[y * WIN + x] = (short)iyval;
                     iA11 += (float)(ixval * ixval); iA12 += (float)(ixval * iyval); iA22 += (float)(iyval * iyval);
                 }
+            }
             const float A11 = iA11 * FLT_SCALE, A12 = iA12 * FLT_SCALE, A22 = iA22 * FLT_SCALE;
             float D = A11 * A22 - A12 * A12;
             const float minEig = (A22 + A11 - std::sqrt((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * WIN * WIN);
@@ -1147,12 +1168,14 @@ SGO_API int sgo_lk_track(const uint8_t* I0, const uint8_t* J0, int w, int h, int
                 iw00 = cvRoundF((1.f - a) * (1.f - b) * (1 << W_BITS)); iw01 = cvRoundF(a * (1.f - b) * (1 << W_BITS));
                 iw10 = cvRoundF((1.f - a) * b * (1 << W_BITS)); iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
                 float ib1 = 0, ib2 = 0;
-                for (int y = 0; y < WIN; y++)
+                const int sj = LJ.stride;
+                for (int y = 0; y < WIN; y++) {
+                    const uint8_t* src = LJ.at(inx, iny + y);
                     for (int x = 0; x < WIN; x++) {
-                        const int X = inx + x, Y = iny + y;
-                        const int diff = descale(LJ.at(X, Y) * iw00 + LJ.at(X + 1, Y) * iw01 + LJ.at(X, Y + 1) * iw10 + LJ.at(X + 1, Y + 1) * iw11, W_BITS - 5) - Iw[y * WIN + x];
+                        const int diff = descale(src[x] * iw00 + src[x + 1] * iw01 + src[x + sj] * iw10 + src[x + sj + 1] * iw11, W_BITS - 5) - Iw[y * WIN + x];
                         ib1 += (float)(diff * dIx[y * WIN + x]); ib2 += (float)(diff * dIy[y * WIN + x]);
                     }
+                }
                 const float b1 = ib1 * FLT_SCALE, b2 = ib2 * FLT_SCALE;
                 const float dx = (float)((A12 * b2 - A22 * b1) * D), dy = (float)((A12 * b1 - A11 * b2) * D);
                 qx += dx; qy += dy;

@@ -1,0 +1,52 @@
+"""Oracle of cv::findFundamentalMat(FM_RANSAC, 1.0, 0.99) (src/Frame.cc:469-472) against golden vectors produced by the real cv2
+(tests/golden/make_golden_fm.py).  Tolerance: F is a float64 result scaled to F33 = 1; entries agree to 1e-9 absolute (the
+solvers differ only in rounding); inlier masks must be identical."""
+import os
+
+import numpy as np
+
+import oracle as O
+
+G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fm_ransac.npz'))
+F_TOL = 1e-9
+
+
+def test_seven_point_solutions_match_cv2():
+    for i in range(int(G['n_seven'])):
+        want = G[f's{i}_F'].reshape(-1, 3, 3)
+        got = O.run7point(G[f's{i}_m1'], G[f's{i}_m2'])
+        assert len(got) == len(want)
+        for a, b in zip(got, want):          # same order: the root order decides which of two equally good models wins
+            assert np.abs(a - b).max() <= F_TOL * max(1.0, np.abs(b).max())
+
+
+def test_ransac_matches_cv2():
+    for i in range(int(G['n_ransac'])):
+        m1, m2 = G[f'r{i}_m1'], G[f'r{i}_m2']
+        F, mask, info = O.find_fundamental_ransac(m1, m2, 1.0, 0.99)
+        assert F is not None
+        assert np.abs(F - G[f'r{i}_F']).max() <= F_TOL * max(1.0, np.abs(G[f'r{i}_F']).max()), i
+        assert np.array_equal(mask, G[f'r{i}_mask']), i
+        assert info[1] == int(mask.sum()) and 0 < info[0] <= 1000
+
+
+def test_fewer_than_15_points_is_not_ransac():
+    m1, m2 = G['r1_m1'][:14], G['r1_m2'][:14]
+    F, _, _ = O.find_fundamental_ransac(m1, m2)
+    assert F is None        # OpenCV switches to LMedS below 15 points; not restated
+
+
+def test_select_static_pairs():
+    rs = np.random.RandomState(3)
+    cur = rs.uniform(0, 640, (200, 2)).astype(np.float32); prev = cur + rs.normal(0, 1, cur.shape).astype(np.float32)
+    boxes = np.array([[100, 100, 200, 150], [400, 50, 100, 300]], np.float32)
+    s1, s2 = O.select_static_pairs(cur, prev, boxes, True)
+    inb = np.zeros(len(prev), bool)
+    for b in boxes:
+        inb |= (prev[:, 0] > b[0]) & (prev[:, 0] < b[0] + b[2]) & (prev[:, 1] > b[1]) & (prev[:, 1] < b[1] + b[3])
+    assert np.array_equal(s2, prev[~inb]) and np.array_equal(s1, cur[~inb])
+    s1, s2 = O.select_static_pairs(cur, prev, boxes, False)
+    assert len(s1) == 200
+    big = np.array([[-10, -10, 2000, 2000]], np.float32)     # everything dynamic: <= 20 survivors -> all pairs
+    s1, s2 = O.select_static_pairs(cur, prev, big, True)
+    assert len(s1) == 200
