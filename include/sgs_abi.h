@@ -246,6 +246,27 @@ SGS_API int sgs_dynreject_batch_device(const sgs_keypoint* d_kps, const uint8_t*
                                        void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * cv::findFundamentalMat(points1, points2, cv::FM_RANSAC, 1.0, 0.99) as called at src/Frame.cc:469-472 (points1 = current
+ * keypoints, points2 = their LK-tracked positions in the previous frame), including the selection in front of it
+ * (src/Frame.cc:454-468: when the previous frame had dynamic boxes and more than 20 pairs have their PREVIOUS point outside
+ * them, only those pairs are used).  F: 3x3 row-major double scaled to F33 = 1; a NaN in F[0] == empty matrix.
+ *   info (4 x int32, may be NULL): pairs used, inliers of F, iterations run, status (0 ok, 1 fewer than 15 pairs -- OpenCV
+ *   would run LMedS / plain 7-point, not provided --, 2 no model found, 3 no previous frame).
+ *   sgs_fundamental_ransac       : host pointers, one point set, no box selection; mask [n] may be NULL.
+ *   sgs_fundamental_batch_device : device pointers, `nframes` frames: d_kps [F][cap], d_prev_xy [F][cap][2], d_counts [F],
+ *                                  previous-frame boxes d_prev_boxes [F][max_boxes] / d_prev_nboxes [F] / d_prev_have_dyn [F]
+ *                                  (all three may be NULL); d_prev_index (may be NULL): row of the batch whose boxes are the
+ *                                  previous frame's, d_prev_index[f] == f marks "no previous frame"; d_F [F][9], d_info [F][4].
+ * ------------------------------------------------------------------------------------ */
+SGS_API int sgs_fundamental_ransac(const float* pts1_xy, const float* pts2_xy, int n, double ransac_thresh, double confidence,
+                                   int max_iters, double* F, uint8_t* mask, int32_t* info, int device);
+SGS_API int sgs_fundamental_batch_device(const sgs_keypoint* d_kps, const float* d_prev_xy, const int32_t* d_counts, int cap,
+                                         int nframes, const sgs_rect* d_prev_boxes, const int32_t* d_prev_nboxes,
+                                         const uint8_t* d_prev_have_dyn, int max_boxes, const int32_t* d_prev_index,
+                                         double ransac_thresh, double confidence, int max_iters, double* d_F, int32_t* d_info,
+                                         void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Batched front end with HOST buffers: the part of Frame::Frame (RGB-D ctor, src/Frame.cc:129-198) and
  * Tracking::TrackWithMotionModel (src/Tracking.cc:906-931) that runs on the GPU, for `nframes` independent frames.
  *   sgs_tracker_extract : ExtractORB (src/Frame.cc:146).  Keypoints/descriptors return to the host, which runs
@@ -293,6 +314,15 @@ SGS_API sgs_extractor* sgs_tracker_extractor(sgs_tracker* t);  /* the extractor 
 SGS_API int sgs_tracker_lk_device(sgs_tracker* t, const uint8_t* d_frames, int nframes, size_t frame_stride, int pitch,
                                   const int32_t* d_prev_index, void* stream);
 SGS_API int sgs_tracker_prev_xy_device(const sgs_tracker* t, const float** d_prev_xy);
+/* findFundamentalMat on the GPU for the frames of the last extract call, from the keypoints and the LK result held by the
+ * tracker (sgs_tracker_lk_device must have run).  d_boxes / d_nboxes / d_have_dyn are the per-frame detector boxes of the BATCH
+ * (the same arrays sgs_tracker_track_device takes); d_prev_index [F] selects, per frame, the row that is its previous frame
+ * (== own row: no previous frame, F = NaN -> every keypoint is kept).  The result is used by the next
+ * sgs_tracker_track_device / sgs_tracker_track_lk call made with F == NULL; sgs_tracker_fundamental_device_ptr exposes it
+ * (d_F [F][9] double, d_info [F][4] int32, see sgs_fundamental_batch_device). */
+SGS_API int sgs_tracker_fundamental_device(sgs_tracker* t, int nframes, const sgs_rect* d_boxes, const int32_t* d_nboxes,
+                                           const uint8_t* d_have_dyn, const int32_t* d_prev_index, void* stream);
+SGS_API int sgs_tracker_fundamental_device_ptr(const sgs_tracker* t, const double** d_F, const int32_t** d_info);
 /* Host-buffer variant of sgs_tracker_track with the LK stage on the GPU: prev_index [F] (host) replaces prev_xy; the frames are
  * the ones uploaded by the preceding sgs_tracker_extract call (they are still resident on the device). */
 SGS_API int sgs_tracker_track_lk(sgs_tracker* t, int nframes, const int32_t* prev_index, const float* u_right, const double* F,

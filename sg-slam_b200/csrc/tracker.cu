@@ -20,6 +20,7 @@ struct sgs_tracker {
     sgs_lk* lk = nullptr;
     int width = 0, height = 0;
     int32_t* d_pidx = nullptr;
+    double* d_Fgpu = nullptr; int32_t* d_finfo = nullptr;     // findFundamentalMat on the device
     cudaStream_t st = nullptr;
     // device inputs of track()
     float* d_prev = nullptr; float* d_uright_in = nullptr; double* d_F = nullptr; sgs_rect* d_boxes = nullptr; int32_t* d_nboxes = nullptr;
@@ -79,7 +80,7 @@ SGS_API void sgs_tracker_destroy(sgs_tracker* t) {
     if (t->lk) sgs_lk_destroy(t->lk);
     if (t->d_pidx) cudaFree(t->d_pidx);
     void* ptrs[] = {t->d_prev, t->d_uright_in, t->d_F, t->d_boxes, t->d_nboxes, t->d_have, t->d_lxyz, t->d_ldesc, t->d_lflags, t->d_loct, t->d_lang,
-                    t->d_ln, t->d_tc, t->d_tl, t->d_kps2, t->d_desc2, t->d_cnt2, t->d_keep, t->d_uright2, t->d_mp, t->d_nm, t->d_ncand};
+                    t->d_ln, t->d_tc, t->d_tl, t->d_kps2, t->d_desc2, t->d_cnt2, t->d_keep, t->d_uright2, t->d_mp, t->d_nm, t->d_ncand, t->d_Fgpu, t->d_finfo};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (t->st) cudaStreamDestroy(t->st);
     delete t;
@@ -109,7 +110,7 @@ SGS_API int sgs_tracker_create(const sgs_orb_params* params, int width, int heig
     A(dalloc(&t->d_lflags, B * M)); A(dalloc(&t->d_loct, B * M)); A(dalloc(&t->d_lang, B * M)); A(dalloc(&t->d_ln, B));
     A(dalloc(&t->d_tc, B * 16)); A(dalloc(&t->d_tl, B * 16)); A(dalloc(&t->d_kps2, B * K)); A(dalloc(&t->d_desc2, B * K * 32));
     A(dalloc(&t->d_cnt2, B)); A(dalloc(&t->d_keep, B * K)); A(dalloc(&t->d_uright2, B * K)); A(dalloc(&t->d_mp, B * K)); A(dalloc(&t->d_nm, B));
-    A(dalloc(&t->d_ncand, B));
+    A(dalloc(&t->d_ncand, B)); A(dalloc(&t->d_Fgpu, B * 9)); A(dalloc(&t->d_finfo, B * 4));
 #undef A
     if (e != cudaSuccess) { set_error("sgs_tracker_create: %s", cudaGetErrorString(e)); sgs_tracker_destroy(t); return SGS_ERR_CUDA; }
     *out = t;
@@ -142,8 +143,9 @@ SGS_API int sgs_tracker_track_device(sgs_tracker* t, int nframes, const float* p
                                      const int32_t* nboxes, const uint8_t* have_dyn, const float* last_xyz, const uint8_t* last_desc,
                                      const uint8_t* last_flags, const int32_t* last_octave, const float* last_angle, const int32_t* last_n,
                                      const float* tcw_cur, const float* tcw_last, float th, int mono, int check_orientation, void* stream) {
-    if (!t || !u_right || !F || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle ||
+    if (!t || !u_right || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle ||
         !last_n || !tcw_cur || !tcw_last) return bad("sgs_tracker_track_device: NULL argument");
+    if (!F) F = t->d_Fgpu;                  // filled by sgs_tracker_fundamental_device
     if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_track_device: nframes exceeds the last extract call");
     if (!prev_xy) prev_xy = t->d_prev;      // filled by sgs_tracker_lk_device
     cudaStream_t st = stream ? (cudaStream_t)stream : t->st;
@@ -222,6 +224,24 @@ SGS_API int sgs_tracker_lk_device(sgs_tracker* t, const uint8_t* d_frames, int n
                                      stream ? stream : (void*)t->st);
 }
 
+SGS_API int sgs_tracker_fundamental_device(sgs_tracker* t, int nframes, const sgs_rect* d_boxes, const int32_t* d_nboxes, const uint8_t* d_have_dyn,
+                                           const int32_t* d_prev_index, void* stream) {
+    if (!t || !d_nboxes || !d_have_dyn || !d_prev_index) return bad("sgs_tracker_fundamental_device: NULL argument");
+    if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_fundamental_device: nframes exceeds the last extract call");
+    const sgs_keypoint* d_kps; const uint8_t* d_desc; const int32_t* d_cnt; int cap = 0;
+    sgs_extractor_results_device(t->ex, &d_kps, &d_desc, &d_cnt, &cap);
+    // parameters of the reference call: FM_RANSAC, 1.0, 0.99 (src/Frame.cc:470,472); OpenCV's default of 1000 iterations
+    return sgs_fundamental_batch_device(d_kps, t->d_prev, d_cnt, cap, nframes, d_boxes ? d_boxes : t->d_boxes, d_nboxes, d_have_dyn, t->max_boxes,
+                                        d_prev_index, 1.0, 0.99, 1000, t->d_Fgpu, t->d_finfo, stream ? stream : (void*)t->st);
+}
+
+SGS_API int sgs_tracker_fundamental_device_ptr(const sgs_tracker* t, const double** d_F, const int32_t** d_info) {
+    if (!t) return bad("sgs_tracker_fundamental_device_ptr: NULL");
+    if (d_F) *d_F = t->d_Fgpu;
+    if (d_info) *d_info = t->d_finfo;
+    return SGS_OK;
+}
+
 SGS_API int sgs_tracker_prev_xy_device(const sgs_tracker* t, const float** d_prev_xy) {
     if (!t || !d_prev_xy) return bad("sgs_tracker_prev_xy_device: NULL");
     *d_prev_xy = t->d_prev;
@@ -243,19 +263,24 @@ SGS_API int sgs_tracker_track_lk(sgs_tracker* t, int nframes, const int32_t* pre
     int rc = sgs_tracker_lk_device(t, d_frames, nframes, fstride, pitch, t->d_pidx, t->st);
     if (rc != SGS_OK) return rc;
     // same as sgs_tracker_track from here on, with prev_xy already on the device
-    if (!u_right || !F || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle || !last_n || !tcw_cur ||
+    if (!u_right || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle || !last_n || !tcw_cur ||
         !tcw_last || !kps_out || !desc_out || !counts_out || !cur_mp_out || !nmatches_out) return bad("sgs_tracker_track_lk: NULL argument");
     const size_t B = nframes, K = t->cap, M = t->point_cap;
     cudaStream_t st = t->st;
 #define H2D(dst, src, bytes) SGS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st))
-    H2D(t->d_uright_in, u_right, B * K * 4); H2D(t->d_F, F, B * 72);
+    H2D(t->d_uright_in, u_right, B * K * 4);
+    if (F) H2D(t->d_F, F, B * 72);
     if (boxes) H2D(t->d_boxes, boxes, B * t->max_boxes * sizeof(sgs_rect));
     H2D(t->d_nboxes, nboxes, B * 4); H2D(t->d_have, have_dyn, B);
     H2D(t->d_lxyz, last_xyz, B * M * 12); H2D(t->d_ldesc, last_desc, B * M * 32); H2D(t->d_lflags, last_flags, B * M);
     H2D(t->d_loct, last_octave, B * M * 4); H2D(t->d_lang, last_angle, B * M * 4); H2D(t->d_ln, last_n, B * 4);
     H2D(t->d_tc, tcw_cur, B * 64); H2D(t->d_tl, tcw_last, B * 64);
 #undef H2D
-    rc = sgs_tracker_track_device(t, nframes, nullptr, t->d_uright_in, t->d_F, t->d_boxes, t->d_nboxes, t->d_have, t->d_lxyz, t->d_ldesc, t->d_lflags,
+    if (!F) {       // F == NULL: findFundamentalMat on the device, previous-frame boxes = the boxes of row prev_index[f]
+        rc = sgs_tracker_fundamental_device(t, nframes, t->d_boxes, t->d_nboxes, t->d_have, t->d_pidx, st);
+        if (rc != SGS_OK) return rc;
+    }
+    rc = sgs_tracker_track_device(t, nframes, nullptr, t->d_uright_in, F ? t->d_F : nullptr, t->d_boxes, t->d_nboxes, t->d_have, t->d_lxyz, t->d_ldesc, t->d_lflags,
                                   t->d_loct, t->d_lang, t->d_ln, t->d_tc, t->d_tl, th, mono, check_orientation, st);
     if (rc != SGS_OK) return rc;
 #define D2H(dst, src, bytes) SGS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st))

@@ -75,6 +75,7 @@ ABI_SYMBOLS = [
     'sgs_extractor_set_profiling', 'sgs_extractor_stage_times',
     'sgs_lk_create', 'sgs_lk_destroy', 'sgs_lk_track', 'sgs_lk_track_batch_device', 'sgs_lk_read_level',
     'sgs_tracker_lk_device', 'sgs_tracker_prev_xy_device', 'sgs_tracker_track_lk', 'sgs_extractor_level0_device', 'sgs_memcpy_d2h',
+    'sgs_fundamental_ransac', 'sgs_fundamental_batch_device', 'sgs_tracker_fundamental_device', 'sgs_tracker_fundamental_device_ptr',
 ]
 
 
@@ -389,6 +390,21 @@ class LK:
     def track_batch_device(self, d_cur, d_prev, nframes, frame_stride, pitch, d_kps, d_counts, cap, d_prev_xy, stream=0):
         v = C.c_void_p
         check(lib().sgs_lk_track_batch_device(self.h, v(d_cur), v(d_prev), v(0), nframes, C.c_size_t(frame_stride), pitch, v(d_kps), v(d_counts), cap, v(d_prev_xy), v(stream)))
+
+
+def fundamental_ransac(pts1, pts2, thresh=1.0, confidence=0.99, max_iters=1000, device=0):
+    """cv::findFundamentalMat(pts1, pts2, FM_RANSAC, thresh, confidence) on the GPU.  Returns (F 3x3 or None, mask, info[4])."""
+    a = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2); b = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+    F = np.zeros(9, np.float64); mask = np.zeros(len(a), np.uint8); info = np.zeros(4, np.int32)
+    check(lib().sgs_fundamental_ransac(_p(a), _p(b), len(a), C.c_double(thresh), C.c_double(confidence), int(max_iters), _p(F), _p(mask), _p(info), device))
+    return (None if np.isnan(F[0]) else F.reshape(3, 3)), mask, info
+
+
+def fundamental_batch_device(d_kps, d_prev_xy, d_counts, cap, nframes, d_boxes, d_nboxes, d_have, max_boxes, d_prev_index, d_F, d_info,
+                             thresh=1.0, confidence=0.99, max_iters=1000, stream=0):
+    v = C.c_void_p
+    check(lib().sgs_fundamental_batch_device(v(d_kps), v(d_prev_xy), v(d_counts), cap, nframes, v(d_boxes), v(d_nboxes), v(d_have), max_boxes,
+                                             v(d_prev_index), C.c_double(thresh), C.c_double(confidence), int(max_iters), v(d_F), v(d_info), v(stream)))
 
 
 def memcpy_d2h(dst_array, d_ptr):

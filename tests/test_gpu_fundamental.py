@@ -1,0 +1,109 @@
+"""GPU parity of findFundamentalMat(FM_RANSAC, 1.0, 0.99) (src/Frame.cc:469-472) through the C ABI against the cv2 golden vectors
+and the CPU oracle.  F is float64 scaled to F33 = 1: tolerance 1e-9 absolute on its entries (the GPU orthonormalises the 7x9
+system by Gram-Schmidt where OpenCV runs Jacobi sweeps; everything else is the same arithmetic); inlier masks, inlier counts and
+the number of iterations run must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle as O  # noqa: E402
+from pysgs import binding as B  # noqa: E402
+
+F_TOL = 1e-9
+
+
+def _same(F, Fref):
+    return np.abs(F - Fref).max() <= F_TOL * max(1.0, np.abs(Fref).max())
+
+
+def test_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'fm_ransac.npz'))
+    for i in range(int(g['n_ransac'])):
+        F, mask, info = B.fundamental_ransac(g[f'r{i}_m1'], g[f'r{i}_m2'])
+        assert F is not None and _same(F, g[f'r{i}_F']), i
+        assert np.array_equal(mask, g[f'r{i}_mask']), i
+        assert info[0] == len(mask) and info[1] == int(mask.sum()) and info[3] == 0
+
+
+def _scene(rs, n, noise, outlier_frac):
+    import math
+    X = np.c_[rs.uniform(-2, 2, n), rs.uniform(-1.5, 1.5, n), rs.uniform(2, 6, n)]
+    K = np.array([[535.4, 0, 320.1], [0, 539.2, 247.6], [0, 0, 1]])
+    ang = rs.uniform(-0.03, 0.03)
+    R = np.array([[math.cos(ang), 0, math.sin(ang)], [0, 1, 0], [-math.sin(ang), 0, math.cos(ang)]])
+    t = rs.uniform(-0.05, 0.05, 3)
+    p1 = (K @ X.T).T; p1 = p1[:, :2] / p1[:, 2:]
+    X2 = (R @ X.T).T + t; p2 = (K @ X2.T).T; p2 = p2[:, :2] / p2[:, 2:]
+    p1 = p1 + rs.normal(0, noise, p1.shape); p2 = p2 + rs.normal(0, noise, p2.shape)
+    nout = int(n * outlier_frac)
+    p2[:nout] += rs.uniform(-40, 40, (nout, 2))
+    perm = rs.permutation(n)
+    return p1[perm].astype(np.float32), p2[perm].astype(np.float32)
+
+
+def test_random_scenes_against_oracle():
+    rs = np.random.RandomState(77)
+    for trial in range(24):
+        n = int(rs.choice([15, 16, 30, 100, 500, 1000, 1500]))
+        m1, m2 = _scene(rs, n, rs.choice([0.05, 0.3, 0.8]), rs.choice([0.0, 0.1, 0.3, 0.5, 0.65]))
+        Fo, mo, io = O.find_fundamental_ransac(m1, m2)
+        F, mask, info = B.fundamental_ransac(m1, m2)
+        assert (F is None) == (Fo is None), trial
+        if Fo is not None:
+            assert _same(F, Fo), (trial, n, np.abs(F - Fo).max())
+            assert np.array_equal(mask, mo), trial
+            assert info[1] == io[1] and info[2] == io[0], (trial, info, io)      # inliers, iterations run
+
+
+def test_degenerate_inputs():
+    rs = np.random.RandomState(3)
+    m1, m2 = _scene(rs, 14, 0.2, 0.0)
+    F, mask, info = B.fundamental_ransac(m1, m2)
+    assert F is None and info[3] == 1                   # fewer than 15 pairs: not RANSAC in OpenCV, not provided here
+    pts = np.tile(np.array([[100.0, 100.0]], np.float32), (40, 1))      # all points identical: every sample is collinear
+    F, mask, info = B.fundamental_ransac(pts, pts)
+    Fo, _, _ = O.find_fundamental_ransac(pts, pts)
+    assert F is None and Fo is None
+    line = np.stack([np.linspace(0, 600, 50), np.linspace(10, 400, 50)], 1).astype(np.float32)
+    F, _, _ = B.fundamental_ransac(line, line + 1)
+    Fo, _, _ = O.find_fundamental_ransac(line, line + 1)
+    assert (F is None) == (Fo is None)
+
+
+def test_batch_device_with_previous_boxes():
+    import torch
+    rs = np.random.RandomState(11)
+    nframes, cap, max_boxes = 6, 1100, 4
+    kps = np.zeros((nframes, cap), dtype=np.dtype([('x', 'f4'), ('y', 'f4'), ('size', 'f4'), ('angle', 'f4'), ('response', 'f4'), ('octave', 'i4'), ('class_id', 'i4')]))
+    prev = np.zeros((nframes, cap, 2), np.float32)
+    counts = np.array([1000, 800, 1100, 14, 300, 500], np.int32)
+    boxes = np.zeros((nframes, max_boxes, 4), np.float32); nboxes = np.zeros(nframes, np.int32); have = np.zeros(nframes, np.uint8)
+    prev_index = np.array([0, 0, 1, 2, 3, 4], np.int32)          # frame 0 has no previous frame
+    for f in range(nframes):
+        m1, m2 = _scene(rs, int(counts[f]), 0.3, 0.2)
+        kps['x'][f, :counts[f]] = m1[:, 0]; kps['y'][f, :counts[f]] = m1[:, 1]; prev[f, :counts[f]] = m2
+    boxes[0, 0] = [200, 100, 160, 320]; nboxes[0] = 1; have[0] = 1
+    boxes[1, 0] = [50, 50, 100, 100]; boxes[1, 1] = [300, 200, 200, 200]; nboxes[1] = 2; have[1] = 1
+    boxes[4, 0] = [-10, -10, 2000, 2000]; nboxes[4] = 1; have[4] = 1      # swallows every point -> <= 20 survivors -> all pairs
+    dev = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).cuda()
+    d_kps, d_prev, d_cnt, d_boxes, d_nb, d_have, d_pi = map(dev, (kps, prev, counts, boxes, nboxes, have, prev_index))
+    d_F = torch.zeros(nframes * 9, dtype=torch.float64, device='cuda'); d_info = torch.zeros(nframes * 4, dtype=torch.int32, device='cuda')
+    B.fundamental_batch_device(d_kps.data_ptr(), d_prev.data_ptr(), d_cnt.data_ptr(), cap, nframes, d_boxes.data_ptr(), d_nb.data_ptr(), d_have.data_ptr(),
+                               max_boxes, d_pi.data_ptr(), d_F.data_ptr(), d_info.data_ptr())
+    torch.cuda.synchronize()
+    F = d_F.cpu().numpy().reshape(nframes, 3, 3); info = d_info.cpu().numpy().reshape(nframes, 4)
+    assert np.isnan(F[0]).all() and info[0, 3] == 3
+    for f in range(1, nframes):
+        n = int(counts[f]); pf = int(prev_index[f])
+        cur = np.stack([kps['x'][f, :n], kps['y'][f, :n]], 1)
+        s1, s2 = O.select_static_pairs(cur, prev[f, :n], boxes[pf, :nboxes[pf]], have[pf])
+        Fo, mo, io = O.find_fundamental_ransac(s1, s2)
+        assert info[f, 0] == len(s1), (f, info[f], len(s1))
+        if Fo is None:
+            assert np.isnan(F[f]).all()
+        else:
+            assert _same(F[f], Fo), f
+            assert info[f, 1] == io[1] and info[f, 2] == io[0]
