@@ -38,7 +38,7 @@ ALG_BYTES_EXTRACT = 5_902_474          # algorithmic bytes per 6
 ALG_BYTES_FAST_READ = 950_532          # sum of level pixels (FAST reads every level once)
 ALG_BYTES_LK = 4_200_000               # pyramids + window gathers of LK, ~4.2 MB per frame
 TH = 15.0                              # Tracking.cc:919-923 (RGB-D)
-LAUNCHES_PER_STEP = 17 + 4 + 2 + 1     # extract (7 resize, FAST, quadtree, 8 blur, describe) + LK (3 pyrDown, track) + dyn-reject/compact + match
+LAUNCHES_PER_STEP = 18 + 4 + 1 + 2 + 1     # extract (7 resize, FAST, quadtree, 8 blur, describe) + LK (3 pyrDown, track) + RANSAC F + dyn-reject/compact + match
 
 
 def log(*a):
@@ -71,32 +71,17 @@ def prev_index(nbatch, unique):
     return np.where(f % unique != 0, f - 1, f).astype(np.int32)
 
 
-def fundamental_8pt(cur, prev):
-    """Least-squares normalised 8-point F with prev^T F cur = 0 (the convention of CheckEpiLineDistToRmDynamicPoint, src/Frame.cc:613-627).
-    Stands in for cv::findFundamentalMat(FM_RANSAC), which is not on the GPU in this round; computed once, outside every timed region."""
-    def norm(p):
-        c = p.mean(0); s = np.sqrt(2) / max(1e-9, np.sqrt(((p - c) ** 2).sum(1)).mean())
-        T = np.array([[s, 0, -s * c[0]], [0, s, -s * c[1]], [0, 0, 1.0]])
-        return (np.c_[p, np.ones(len(p))] @ T.T), T
-    a, Ta = norm(cur.astype(np.float64)); b, Tb = norm(prev.astype(np.float64))
-    A = np.einsum('ni,nj->nij', b, a).reshape(len(a), 9)
-    _, _, vt = np.linalg.svd(A, full_matrices=False)
-    Fm = vt[-1].reshape(3, 3)
-    u, s, v = np.linalg.svd(Fm); s[2] = 0
-    Fm = Tb.T @ (u @ np.diag(s) @ v) @ Ta
-    return Fm / np.abs(Fm).max()
-
-
 def make_track_inputs(kps, desc, counts, boxes, prev_xy, cap, point_cap, pidx):
-    """Per-frame inputs of the dyn-reject + match stage (host side, untimed): F from the static LK tracks, person boxes, u_right from
-    a synthetic depth plane, and the last-frame map points = keypoints of the previous frame back-projected with that depth."""
+    """Per-frame inputs of the dyn-reject + match stage (host side, untimed): person boxes, u_right from a synthetic depth plane, and
+    the last-frame map points = keypoints of the previous frame back-projected with that depth.  F is NOT an input any more:
+    findFundamentalMat runs inside the step, on the GPU."""
     from pysgs import synth
     import scenarios as S
     B = len(counts)
     cam = synth.TUM3
     depth = synth.depth_s1(W, H)
     ur = np.full((B, cap), -1, np.float32)
-    F = np.zeros((B, 9), np.float64); nb = np.ones(B, np.int32); have = np.ones(B, np.uint8)
+    nb = np.ones(B, np.int32); have = np.ones(B, np.uint8)
     bx = np.zeros((B, 4, 4), np.float32); bx[:, 0] = boxes
     lxyz = np.zeros((B, point_cap, 3), np.float32); ldesc = np.zeros((B, point_cap, 32), np.uint8)
     lflags = np.zeros((B, point_cap), np.uint8); loct = np.zeros((B, point_cap), np.int32); lang = np.zeros((B, point_cap), np.float32)
@@ -105,12 +90,6 @@ def make_track_inputs(kps, desc, counts, boxes, prev_xy, cap, point_cap, pidx):
     for f in range(B):
         n = counts[f]
         k = kps[f, :n]
-        cur = np.stack([k['x'], k['y']], 1)
-        inbox = (k['x'] > boxes[f, 0]) & (k['x'] < boxes[f, 0] + boxes[f, 2]) & (k['y'] > boxes[f, 1]) & (k['y'] < boxes[f, 1] + boxes[f, 3])
-        if pidx[f] == f or (~inbox).sum() < 16:
-            F[f, 0] = np.nan                                                            # first frame of a stream: empty F (keep all, quirk Q11)
-        else:
-            F[f] = fundamental_8pt(cur[~inbox], prev_xy[f, :n][~inbox]).reshape(9)
         z = depth[np.clip(k['y'].astype(np.int64), 0, H - 1), np.clip(k['x'].astype(np.int64), 0, W - 1)]
         ur[f, :n] = k['x'] - np.float32(cam['bf']) / z
         g = pidx[f]
@@ -122,7 +101,7 @@ def make_track_inputs(kps, desc, counts, boxes, prev_xy, cap, point_cap, pidx):
         lflags[f, :m] = 1 | (2 * ((np.arange(m) % 5) != 0))                              # every 5th point is a temporal point (0 observations)
         ln[f] = m
     sf = S.scale_factors()
-    return dict(ur=ur, F=F, boxes=bx, nb=nb, have=have, lxyz=lxyz, ldesc=ldesc, lflags=lflags, loct=loct, lang=lang, ln=ln, T=T, sf=sf,
+    return dict(ur=ur, boxes=bx, nb=nb, have=have, lxyz=lxyz, ldesc=ldesc, lflags=lflags, loct=loct, lang=lang, ln=ln, T=T, sf=sf,
                 pidx=np.ascontiguousarray(pidx, np.int32))
 
 
@@ -170,25 +149,33 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_one_frame(frames, ti, f, prev_override=None):
-    """The CPU oracle for one frame: extract -> LK -> dyn-reject -> SearchByProjection.  prev_override: use these previous-frame points
-    instead of the oracle's own LK result (to check the integer stages exactly against the GPU, whose LK differs in the last bits)."""
+def cpu_one_frame(frames, ti, f, prev_override=None, F_override=None):
+    """The CPU oracle for one frame: extract -> LK -> findFundamentalMat(RANSAC) -> dyn-reject -> SearchByProjection.
+    prev_override / F_override: use the GPU's LK points / F instead of the oracle's own (LK and F agree with the GPU to a tolerance only;
+    given the same LK points and F, the integer stages behind them must agree exactly)."""
     import oracle as O
     from pysgs import synth
     cam = synth.TUM3
     k, d = O.extract(frames[f])
     n = len(k)
     cur = np.stack([k['x'], k['y']], 1)
-    lk = O.lk_track(frames[f], frames[ti['pidx'][f]], cur)
+    g = int(ti['pidx'][f])
+    lk = O.lk_track(frames[f], frames[g], cur)
     prev = lk if prev_override is None else prev_override[:n]
-    Fm = None if np.isnan(ti['F'][f, 0]) else ti['F'][f]
-    _, keep, _, restored = O.dynreject(cur, prev, Fm, ti['boxes'][f, :ti['nb'][f]], bool(ti['have'][f]), NFEAT)
+    Fm = None
+    if g != f:                                              # the first frame of a stream has no previous frame: nothing is rejected
+        s1, s2 = O.select_static_pairs(cur, prev, ti['boxes'][g, :ti['nb'][g]], bool(ti['have'][g]))
+        Fm, _, _ = O.find_fundamental_ransac(s1, s2, 1.0, 0.99)
+    Fo = Fm
+    if F_override is not None:
+        Fm = None if np.isnan(F_override[0]) else F_override.reshape(3, 3)
+    _, keep, _, restored = O.dynreject(cur, prev, None if Fm is None else Fm.reshape(9), ti['boxes'][f, :ti['nb'][f]], bool(ti['have'][f]), NFEAT)
     sel = np.arange(n) if restored else np.nonzero(keep)[0]
     fr = O.FrameArrays(k[sel], ti['ur'][f, :n][sel], d[sel], W, H, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], ti['sf'])
     m = int(ti['ln'][f])
     nm, mp, nc = O.search_by_projection_last(fr, ti['T'][f].reshape(4, 4), ti['T'][f].reshape(4, 4), ti['lflags'][f, :m] & 1, ti['lxyz'][f, :m],
                                              ti['ldesc'][f, :m], (ti['lflags'][f, :m] >> 1) & 1, ti['loct'][f, :m], ti['lang'][f, :m], TH)
-    return dict(n=n, nsel=len(sel), nm=nm, mp=mp, k=k, d=d, sel=sel, lk=lk)
+    return dict(n=n, nsel=len(sel), nm=nm, mp=mp, k=k, d=d, sel=sel, lk=lk, F=Fo)
 
 
 def cpu_frames_per_s(frames, ti, nframes, cores):
@@ -228,7 +215,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'frames/sec ORB extract+match+dyn-reject 640x480', 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-            'config': {'workload': 'S2 walking_xyz-shaped synthetic 640x480 stream, ORB 1000 features, extract + LK + dyn-reject + SearchByProjection(th=15)',
+            'config': {'workload': 'S2 walking_xyz-shaped synthetic 640x480 stream, ORB 1000 features, extract + LK + findFundamentalMat(RANSAC) + dyn-reject + SearchByProjection(th=15)',
                        'frames_per_step': per_step, 'note': 'CPU oracle port of the reference path (the reference itself needs OpenCV/ROS: unbuildable here)'},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': '%d frames per step x %d steps' % (per_step, args.steps)},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -287,7 +274,7 @@ def main():
     L.sgs_tracker_extractor.restype = C.c_void_p
     exh = v(L.sgs_tracker_extractor(trk.h))
     torch.cuda.synchronize()
-    # set-up pass on the device: extract + LK; the results feed the host-side construction of F / u_right / last-frame points
+    # set-up pass on the device: extract + LK; the results feed the host-side construction of u_right / last-frame points
     B.check(L.sgs_tracker_extract_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(st.cuda_stream)))
     B.check(L.sgs_tracker_lk_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(d_pidx.data_ptr()), v(st.cuda_stream)))
     B.check(L.sgs_extractor_fetch(exh, NB, v(h_kps.data_ptr()), v(h_desc.data_ptr()), cap, v(h_n.data_ptr()), v(st.cuda_stream)))
@@ -295,7 +282,7 @@ def main():
     pp = v(); B.check(L.sgs_tracker_prev_xy_device(trk.h, C.byref(pp)))
     prev0 = B.memcpy_d2h(np.zeros((NB, cap, 2), np.float32), pp.value)
     ti = make_track_inputs(kps0, desc0, n0, boxes, prev0, cap, pcap, pidx)
-    keys_h = ['ur', 'F', 'boxes', 'nb', 'have', 'lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln', 'T', 'pidx']
+    keys_h = ['ur', 'boxes', 'nb', 'have', 'lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln', 'T', 'pidx']
     hp = {k: torch.from_numpy(np.ascontiguousarray(ti[k])).pin_memory() for k in keys_h}
     dv = {k: t.cuda(non_blocking=True) for k, t in hp.items()}
     bcast_ms = None
@@ -310,8 +297,8 @@ def main():
     torch.cuda.synchronize()
     log('[bench] rank %d set-up %.1fs: %d frames/step, mean %.0f keypoints/frame' % (rank, time.time() - t_setup, NB, n0.mean()))
 
-    def track_ptrs(d):   # u_right, F, boxes, nboxes, have_dyn, last_xyz, last_desc, last_flags, last_octave, last_angle, last_n, tcw_cur, tcw_last
-        return [d[k].data_ptr() for k in ('ur', 'F', 'boxes', 'nb', 'have', 'lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln', 'T', 'T')]
+    def track_ptrs(d):   # u_right, F (NULL: the one computed on the device), boxes, nboxes, have_dyn, last_xyz, last_desc, last_flags, last_octave, last_angle, last_n, tcw_cur, tcw_last
+        return [d['ur'].data_ptr(), 0] + [d[k].data_ptr() for k in ('boxes', 'nb', 'have', 'lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln', 'T', 'T')]
 
     def dev_extract():
         B.check(L.sgs_tracker_extract_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(st.cuda_stream)))
@@ -319,11 +306,15 @@ def main():
     def dev_lk():
         B.check(L.sgs_tracker_lk_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(d_pidx.data_ptr()), v(st.cuda_stream)))
 
+    def dev_fm():
+        B.check(L.sgs_tracker_fundamental_device(trk.h, NB, v(dv['boxes'].data_ptr()), v(dv['nb'].data_ptr()), v(dv['have'].data_ptr()),
+                                                 v(d_pidx.data_ptr()), v(st.cuda_stream)))
+
     def dev_track():
         B.check(L.sgs_tracker_track_device(trk.h, NB, v(0), *[v(p) for p in track_ptrs(dv)], C.c_float(TH), 0, 1, v(st.cuda_stream)))
 
     def step_host():
-        # call 1: frames -> keypoints (descriptors stay on the device); call 2: LK + dyn-reject + match on the resident batch
+        # call 1: frames -> keypoints (descriptors stay on the device); call 2: LK + RANSAC F + dyn-reject + match on the resident batch
         trk.extract(h_frames.data_ptr(), NB, W * H, W, h_kps.data_ptr(), 0, h_n.data_ptr())
         B.check(L.sgs_tracker_track_lk(trk.h, NB, v(hp['pidx'].data_ptr()), *[v(p) for p in track_ptrs(hp)], C.c_float(TH), 0, 1,
                                        v(h_out['kps'].data_ptr()), v(h_out['desc'].data_ptr()), v(h_out['ur'].data_ptr()), v(h_out['cnt'].data_ptr()),
@@ -345,23 +336,25 @@ def main():
     # ---- device-resident leg (value) ----------------------------------------------------------------------------------
     with torch.cuda.stream(st):
         for _ in range(warm):
-            dev_extract(); dev_lk(); dev_track()
+            dev_extract(); dev_lk(); dev_fm(); dev_track()
     barrier()
     B.check(L.sgs_extractor_set_profiling(exh, 1))
     sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * args.steps + 1)]
     barrier()
     with torch.cuda.stream(st):
         ev[0].record(st)
         for i in range(args.steps):
-            dev_extract(); ev[3 * i + 1].record(st)
-            dev_lk(); ev[3 * i + 2].record(st)
-            dev_track(); ev[3 * i + 3].record(st)
+            dev_extract(); ev[4 * i + 1].record(st)
+            dev_lk(); ev[4 * i + 2].record(st)
+            dev_fm(); ev[4 * i + 3].record(st)
+            dev_track(); ev[4 * i + 4].record(st)
     barrier()
-    total_ms = max_over_ranks(ev[0].elapsed_time(ev[3 * args.steps]))
-    extract_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)) / args.steps
-    lk_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)) / args.steps
-    track_ms = sum(ev[3 * i + 2].elapsed_time(ev[3 * i + 3]) for i in range(args.steps)) / args.steps
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[4 * args.steps]))
+    extract_ms = sum(ev[4 * i].elapsed_time(ev[4 * i + 1]) for i in range(args.steps)) / args.steps
+    lk_ms = sum(ev[4 * i + 1].elapsed_time(ev[4 * i + 2]) for i in range(args.steps)) / args.steps
+    fm_ms = sum(ev[4 * i + 2].elapsed_time(ev[4 * i + 3]) for i in range(args.steps)) / args.steps
+    track_ms = sum(ev[4 * i + 3].elapsed_time(ev[4 * i + 4]) for i in range(args.steps)) / args.steps
     clocks = sampler.stop()
     ms5 = (C.c_double * 5)(); ncalls = C.c_int()
     B.check(L.sgs_extractor_stage_times(exh, ms5, C.byref(ncalls)))
@@ -369,9 +362,12 @@ def main():
     B.check(L.sgs_extractor_set_profiling(exh, 0))
     value = world * NB * args.steps / (total_ms * 1e-3)
     prev_dev = B.memcpy_d2h(np.zeros((NB, cap, 2), np.float32), pp.value)     # LK output of the last device step
+    pF, pI = v(), v()
+    B.check(L.sgs_tracker_fundamental_device_ptr(trk.h, C.byref(pF), C.byref(pI)))
 
     step_host()   # e2e warm-up; its outputs are also used for the parity spot-check below
     counts_after = h_out['cnt'].numpy().copy(); nmatch = h_out['nm'].numpy().copy()
+    F_dev = B.memcpy_d2h(np.zeros((NB, 9), np.float64), pF.value); F_info = B.memcpy_d2h(np.zeros((NB, 4), np.int32), pI.value)
 
     # ---- e2e leg: host buffers through the C ABI, copies inside the timed region ----------------------------------------
     e2e = None
@@ -388,7 +384,7 @@ def main():
         d2h = (h_kps.numel() + h_n.numel() * 4) + sum(t.numel() * t.element_size() for t in h_out.values())
         e2e = {'value': world * NB * args.steps / dt, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                'ms_per_step': 1e3 * dt / args.steps,
-               'note': 'sgs_tracker_extract (host frames -> host keypoints) + sgs_tracker_track_lk (LK + dyn-reject + match on the resident batch) with pinned host buffers'}
+               'note': 'sgs_tracker_extract (host frames -> host keypoints) + sgs_tracker_track_lk (LK + RANSAC F + dyn-reject + match on the resident batch) with pinned host buffers'}
 
     # ---- roofline of the dominant extractor kernel ------------------------------------------------------------------------
     peaks, peak_kind = measured_peaks()
@@ -407,7 +403,7 @@ def main():
     roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
                 'traffic': None, 'peak_kind': ('measured copy bandwidth (MEASURED_PEAKS.json)' if peak_kind == 'measured' else 'fallback 6650 GB/s'),
                 'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': stage_ms[dom],
-                'stage_ms': dict(zip(names, [round(x, 4) for x in stage_ms])), 'extract_ms': extract_ms, 'lk_ms': lk_ms, 'dynreject_match_ms': track_ms,
+                'stage_ms': dict(zip(names, [round(x, 4) for x in stage_ms])), 'extract_ms': extract_ms, 'lk_ms': lk_ms, 'fundamental_ransac_ms': fm_ms, 'dynreject_match_ms': track_ms,
                 'extract_alg_gbs': ALG_BYTES_EXTRACT * NB / (extract_ms * 1e-3) / 1e9,
                 'extract_frac_of_hbm': ALG_BYTES_EXTRACT * NB / (extract_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
                 'step_alg_gbs': step_alg_bytes / (total_ms / args.steps * 1e-3) / 1e9,
@@ -423,16 +419,22 @@ def main():
         kps_h = h_out['kps'].numpy().reshape(NB, cap * 28).view(B.KP_DTYPE).reshape(NB, cap)
         ok = True
         lk_err = []
+        f_err = []
         for f, r in enumerate(res):
             n = r['n']
             ok &= int(n0[f]) == n and kps0[f, :n].tobytes() == r['k'].tobytes() and bool(np.array_equal(desc0[f, :n], r['d']))   # extraction: bit-exact
             lk_err.append(np.abs(prev_dev[f, :n] - r['lk']).max(1))                                                                 # LK: tolerance
-            rr = cpu_one_frame(frames, ti, f, prev_override=prev_dev[f])                                                            # integer stages given the GPU's LK
+            rr = cpu_one_frame(frames, ti, f, prev_override=prev_dev[f], F_override=F_dev[f])                                       # F given the GPU's LK; integer stages given the GPU's LK and F
+            if rr['F'] is None:
+                ok &= bool(np.isnan(F_dev[f, 0]))
+            else:
+                f_err.append(float(np.abs(rr['F'].reshape(9) - F_dev[f]).max() / max(1.0, np.abs(rr['F']).max()))); ok &= f_err[-1] <= 1e-9
             ok &= int(counts_after[f]) == rr['nsel'] and int(nmatch[f]) == rr['nm'] and kps_h[f, :rr['nsel']].tobytes() == rr['k'][rr['sel']].tobytes()
             ok &= bool(np.array_equal(h_out['desc'].numpy()[f, :rr['nsel']], rr['d'][rr['sel']])) and bool(np.array_equal(h_out['mp'].numpy()[f, :rr['nsel']], rr['mp']))
         e = np.concatenate(lk_err)
         cpu = {'value': cpu_fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': '%d frames of the same batch, %d worker threads' % (ns, cores),
-               'parity_with_gpu_on_sample': bool(ok), 'lk_abs_err_px': {'median': float(np.median(e)), 'p99': float(np.quantile(e, 0.99)), 'max': float(e.max())}}
+               'parity_with_gpu_on_sample': bool(ok), 'lk_abs_err_px': {'median': float(np.median(e)), 'p99': float(np.quantile(e, 0.99)), 'max': float(e.max())},
+               'F_rel_err_max': (max(f_err) if f_err else None)}
         if not ok:
             log('[bench] WARNING: GPU results differ from the oracle on the CPU sample')
 
@@ -440,11 +442,12 @@ def main():
         line = {'metric': 'frames/sec ORB extract+match+dyn-reject 640x480', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': warm, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
                 'data': 'synthetic',
-                'config': {'workload': 'S2 walking_xyz-shaped synthetic 640x480 stream (BASELINE configs[1]), ORB 1000 features / 8 levels / 1.2: extract + LK(21x21, 4 levels) + dyn-reject(boxes + epipolar) + SearchByProjection(th=15)',
+                'config': {'workload': 'S2 walking_xyz-shaped synthetic 640x480 stream (BASELINE configs[1]), ORB 1000 features / 8 levels / 1.2: extract + LK(21x21, 4 levels) + findFundamentalMat(RANSAC 1.0/0.99) + dyn-reject(boxes + epipolar) + SearchByProjection(th=15)',
                            'frames_per_gpu_per_step': NB, 'l2_policy': 'inputs larger than L2: %d frames x 307200 B = %.0f MB per step (+ %.0f MB pyramid traffic)' % (NB, NB * 0.3072, NB * 0.95),
                            'sharding': 'independent streams per rank, no data-path collective; one untimed ncclBroadcast of the map/vocabulary table at start-up',
                            'mean_keypoints': float(n0.mean()), 'mean_after_dynreject': float(counts_after.mean()), 'mean_matches': float(nmatch.mean()),
-                           'not_in_step': 'RANSAC F (src/Frame.cc:469-472; an 8-point F is precomputed on the host) and the detector (boxes precomputed)'},
+                           'ransac_iterations_mean': float(F_info[:, 2].mean()), 'ransac_inlier_ratio_mean': float((F_info[:, 1] / np.maximum(1, F_info[:, 0])).mean()),
+                           'not_in_step': 'the detector (boxes precomputed)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps, 'roofline': roofline, 'cpu_baseline': cpu}
         if bcast_ms is not None:
             line['config']['startup_broadcast_ms'] = bcast_ms
