@@ -6,7 +6,12 @@
 //                            mvPotentialDynamicBorderForRmDynamicFeature, mbHaveDynamicObjectForRmDynamicFeature,
 //                            mpORBextractorLeft->GetnFeatures());
 //
-// calcOpticalFlowPyrLK and findFundamentalMat (src/Frame.cc:445-472) stay where they are (host OpenCV) in this round.
+// and the two OpenCV calls in front of it (src/Frame.cc:445 and :469-472) by
+//
+//     ORB_SLAM2::CalcOpticalFlowPyrLK(imGray, imGrayPre, Curpoint, Prepoint);                 // cv::calcOpticalFlowPyrLK(..., Size(21,21), 3, {30, 0.01})
+//     FundMat = ORB_SLAM2::FindFundamentalMatRansac(CurpointRmDynamic, PrepointRmDynamic);     // cv::findFundamentalMat(..., FM_RANSAC, 1.0, 0.99)
+//
+// (status / err of LK are not produced: the reference never reads them, quirk Q4.)
 #pragma once
 #include <stdexcept>
 #include <string>
@@ -44,6 +49,43 @@ inline int RmDynamicPointsGeometry(std::vector<cv::KeyPoint>& keys, cv::Mat& des
         descriptors = out;
     }
     return nkeep;
+}
+
+// cv::calcOpticalFlowPyrLK(imGray, imGrayPre, Curpoint, Prepoint, State, Err, cv::Size(21, 21), 3, {COUNT|EPS, 30, 0.01}) (src/Frame.cc:445).
+// One sgs_lk handle per image size is kept for the life of the process (the reference keeps imGrayPre in a file-scope global the same way).
+inline void CalcOpticalFlowPyrLK(const cv::Mat& imGray, const cv::Mat& imGrayPre, const std::vector<cv::Point2f>& curpoints, std::vector<cv::Point2f>& prepoints,
+                                 int device = 0) {
+    static sgs_lk* lk = nullptr;
+    static int lw = 0, lh = 0;
+    if (imGray.rows != imGrayPre.rows || imGray.cols != imGrayPre.cols) throw std::runtime_error("sgs: LK images differ in size");
+    if (!lk || lw != imGray.cols || lh != imGray.rows) {
+        if (lk) sgs_lk_destroy(lk);
+        lk = nullptr;
+        if (sgs_lk_create(imGray.cols, imGray.rows, 1, device, &lk) != SGS_OK) throw std::runtime_error(std::string("sgs: ") + sgs_last_error());
+        lw = imGray.cols; lh = imGray.rows;
+    }
+    prepoints.resize(curpoints.size());
+    if (curpoints.empty()) return;
+    static_assert(sizeof(cv::Point2f) == 8, "cv::Point2f layout");
+    if (imGray.step != imGrayPre.step) throw std::runtime_error("sgs: LK images differ in row stride");
+    if (sgs_lk_track(lk, imGray.ptr<uint8_t>(), imGrayPre.ptr<uint8_t>(), (int)imGray.step, &curpoints[0].x, (int)curpoints.size(), &prepoints[0].x) != SGS_OK)
+        throw std::runtime_error(std::string("sgs: ") + sgs_last_error());
+}
+
+// cv::findFundamentalMat(points1, points2, cv::FM_RANSAC, 1.0, 0.99) (src/Frame.cc:470,472): 3x3 CV_64F, or an empty Mat when OpenCV would
+// return one (no model) -- and also for 7..14 pairs, where OpenCV switches to the plain 7-point / LMedS estimators that are not provided.
+inline cv::Mat FindFundamentalMatRansac(const std::vector<cv::Point2f>& points1, const std::vector<cv::Point2f>& points2, double ransacThresh = 1.0,
+                                        double confidence = 0.99, int device = 0) {
+    cv::Mat F;
+    const int n = (int)points1.size();
+    if (n < 7 || points2.size() != points1.size()) return F;
+    double Fm[9];
+    if (sgs_fundamental_ransac(&points1[0].x, &points2[0].x, n, ransacThresh, confidence, 1000, Fm, nullptr, nullptr, device) != SGS_OK)
+        throw std::runtime_error(std::string("sgs: ") + sgs_last_error());
+    if (Fm[0] != Fm[0]) return F;            // NaN == empty matrix
+    F.create(3, 3, CV_64F);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F.at<double>(r, c) = Fm[3 * r + c];
+    return F;
 }
 
 }  // namespace ORB_SLAM2

@@ -16,7 +16,7 @@ struct FastTmaMaps { CUtensorMap m[kMaxLevels]; };
 struct FastLaunchPlan { int tp = 0, th = 0, list_cap = 0, warp_stride = 0; size_t smem_bytes = 0; };
 FastLaunchPlan make_fast_launch_plan(const OrbPlan& PL);
 cudaError_t configure_fast_smem(size_t smem_bytes);
-void launch_fast_v2(const DevPlan& P, const FastTmaMaps& M, bool use_tma, const FastLaunchPlan& fp, const FastCell* d_cells, int ncells, cudaStream_t st);
+void launch_fast_v2(const DevPlan& P, const FastTmaMaps& M, bool use_tma, const FastLaunchPlan& fp, const FastCell* d_cells, int ncells, int frame0, cudaStream_t st);
 bool encode_level_map(CUtensorMap* out, const void* base, int w, int h, int pitch, int64_t fstride, int nframes, int box_w, int box_h);
 void launch_quadtree(const DevPlan& P, int smem_key_cap, int node_cap, size_t smem_bytes, uint64_t* key_scratch, int64_t key_scratch_fstride,
                      const int64_t* d_key_scratch_off, cudaStream_t st);

@@ -3,6 +3,8 @@
 // extract_kernels.cu on one stream.  Replaces ORB_SLAM2::ORBextractor (include/ORBextractor.h:45-105).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -16,6 +18,9 @@ struct sgs_extractor {
     int device = 0;
     int max_batch = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // host -> device copies of the chunked host path run here, ahead of the kernels
+    cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t chunk_done = nullptr;
     DevPlan dev{};                 // template; nframes / level-0 pointers patched per call
     // device allocations
     uint8_t* d_pyr = nullptr;      // own pyramid: levels 0..L-1, each [max_batch][h][pitch]
@@ -62,6 +67,9 @@ int fail_invalid(const char* msg) { set_error("%s", msg); return SGS_ERR_INVALID
 void free_all(sgs_extractor* ex) {
     if (!ex) return;
     cudaSetDevice(ex->device);
+    if (ex->copy_stream) cudaStreamDestroy(ex->copy_stream);
+    for (auto& e : ex->chunk_ev) if (e) cudaEventDestroy(e);
+    if (ex->chunk_done) cudaEventDestroy(ex->chunk_done);
     cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cand); cudaFree(ex->d_cand_count); cudaFree(ex->d_kp_stage);
     cudaFree(ex->d_kp_stage_n); cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_error);
     cudaFree(ex->d_cells); cudaFree(ex->d_tabs); cudaFree(ex->d_key_scratch); cudaFree(ex->d_key_scratch_off);
@@ -75,13 +83,30 @@ void free_all(sgs_extractor* ex) {
     delete ex;
 }
 
-// Enqueue the whole pipeline for `nframes` frames whose level 0 is (d_l0, pitch, fstride).
-int enqueue(sgs_extractor* ex, const uint8_t* d_l0, int pitch, int64_t fstride, int nframes, cudaStream_t st) {
+// Enqueue the whole pipeline for frames [frame0, frame0 + nframes) of a batch whose level 0 is (d_l0, pitch, fstride).  A chunk
+// (frame0 > 0 or fewer frames than the batch) works on the same buffers through shifted base pointers; only the TMA tensor maps
+// keep addressing the whole batch (`map_frames` frames) and take frame0 as a coordinate offset.
+int enqueue(sgs_extractor* ex, const uint8_t* d_l0, int pitch, int64_t fstride, int nframes, cudaStream_t st, int frame0 = 0, int map_frames = 0,
+            bool allow_prof = true) {
     DevPlan P = ex->dev;
     P.nframes = nframes;
     P.lv[0].img = d_l0; P.lv[0].pitch = pitch; P.lv[0].fstride = fstride;
     const int L = P.nlevels;
-    const bool prof = ex->profiling;
+    if (map_frames <= 0) map_frames = frame0 + nframes;
+    uint64_t* key_scratch = ex->d_key_scratch;
+    if (frame0 > 0) {
+        for (int l = 0; l < L; ++l) {
+            DevLevel& v = P.lv[l];
+            v.img += (int64_t)frame0 * v.fstride;
+            if (v.img_w) v.img_w += (int64_t)frame0 * v.fstride;
+            v.blur += (int64_t)frame0 * v.bfstride;
+            v.cand += (int64_t)frame0 * P.cand_fstride;
+        }
+        P.cand_count += (int64_t)frame0 * L; P.kp_stage += (int64_t)frame0 * P.kp_stage_per_frame; P.kp_stage_n += (int64_t)frame0 * L;
+        P.out_kps += (int64_t)frame0 * P.out_cap; P.out_desc += (int64_t)frame0 * P.out_cap * 32; P.out_count += frame0;
+        if (key_scratch) key_scratch += (int64_t)frame0 * ex->key_scratch_fstride;
+    }
+    const bool prof = ex->profiling && allow_prof;
     if (prof && ex->stage_pending) {  // fold the previous call's events before reusing them
         if (cudaEventSynchronize(ex->ev[5]) == cudaSuccess) {
             for (int i = 0; i < 5; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ex->ev[i], ex->ev[i + 1]); ex->stage_ms_acc[i] += ms; }
@@ -89,7 +114,7 @@ int enqueue(sgs_extractor* ex, const uint8_t* d_l0, int pitch, int64_t fstride, 
         }
         ex->stage_pending = false;
     }
-    SGS_CUDA_TRY(cudaMemsetAsync(ex->d_cand_count, 0, sizeof(int32_t) * (size_t)nframes * L, st));
+    SGS_CUDA_TRY(cudaMemsetAsync(P.cand_count, 0, sizeof(int32_t) * (size_t)nframes * L, st));
     if (prof) cudaEventRecord(ex->ev[0], st);
     for (int l = 1; l < L; ++l) {
         if (resize_tile_supported(P, l)) launch_resize_tile(P, l, st); else launch_resize(P, l, st);
@@ -99,21 +124,21 @@ int enqueue(sgs_extractor* ex, const uint8_t* d_l0, int pitch, int64_t fstride, 
         launch_fast(P, ex->d_cells, (int)ex->plan.cells.size(), st);
     } else {
         bool tma = ex->fast_variant == 2 && ex->maps_ok;
-        if (tma && !(ex->map0_ok && ex->map0_ptr == d_l0 && ex->map0_pitch == pitch && ex->map0_fstride == fstride && ex->map0_frames >= nframes)) {
-            ex->map0_ok = encode_level_map(&ex->fast_maps.m[0], d_l0, P.lv[0].w, P.lv[0].h, pitch, fstride, nframes, ex->fast_plan.tp, ex->fast_plan.th);
-            ex->map0_ptr = d_l0; ex->map0_pitch = pitch; ex->map0_fstride = fstride; ex->map0_frames = nframes;
+        if (tma && !(ex->map0_ok && ex->map0_ptr == d_l0 && ex->map0_pitch == pitch && ex->map0_fstride == fstride && ex->map0_frames >= map_frames)) {
+            ex->map0_ok = encode_level_map(&ex->fast_maps.m[0], d_l0, P.lv[0].w, P.lv[0].h, pitch, fstride, map_frames, ex->fast_plan.tp, ex->fast_plan.th);
+            ex->map0_ptr = d_l0; ex->map0_pitch = pitch; ex->map0_fstride = fstride; ex->map0_frames = map_frames;
         }
-        launch_fast_v2(P, ex->fast_maps, tma && ex->map0_ok, ex->fast_plan, ex->d_cells, (int)ex->plan.cells.size(), st);
+        launch_fast_v2(P, ex->fast_maps, tma && ex->map0_ok, ex->fast_plan, ex->d_cells, (int)ex->plan.cells.size(), frame0, st);
     }
     if (prof) cudaEventRecord(ex->ev[2], st);
-    launch_quadtree(P, ex->smem_key_cap, ex->node_cap, ex->qt_smem, ex->d_key_scratch, ex->key_scratch_fstride, ex->d_key_scratch_off, st);
+    launch_quadtree(P, ex->smem_key_cap, ex->node_cap, ex->qt_smem, key_scratch, ex->key_scratch_fstride, ex->d_key_scratch_off, st);
     if (prof) cudaEventRecord(ex->ev[3], st);
     for (int l = 0; l < L; ++l) launch_blur(P, l, st);
     if (prof) cudaEventRecord(ex->ev[4], st);
     launch_describe(P, st);
     if (prof) { cudaEventRecord(ex->ev[5], st); ex->stage_pending = true; }
     SGS_CUDA_TRY(cudaGetLastError());
-    ex->last_nframes = nframes;
+    ex->last_nframes = frame0 + nframes;
     ex->last_stream = st;
     return SGS_OK;
 }
@@ -153,6 +178,9 @@ SGS_API int sgs_extractor_create(const sgs_orb_params* params, int width, int he
     } while (0)
     TRY_OR_FREE(cudaSetDevice(device));
     TRY_OR_FREE(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
+    TRY_OR_FREE(cudaStreamCreateWithFlags(&ex->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ex->chunk_ev) TRY_OR_FREE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    TRY_OR_FREE(cudaEventCreateWithFlags(&ex->chunk_done, cudaEventDisableTiming));
     const OrbPlan& PL = ex->plan;
     const int L = PL.nlevels;
     const int64_t B = max_batch;
@@ -371,6 +399,30 @@ SGS_API int sgs_extract_batch(sgs_extractor* ex, const uint8_t* gray, int nframe
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, gray) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
+    if (pinned && nframes >= 64) {
+        // large pinned batches: the frames go up in chunks on the copy stream while the kernels of the previous chunk run
+        const int nchunks = nframes >= 256 ? 4 : 2;
+        const int per = (nframes + nchunks - 1) / nchunks;
+        SGS_CUDA_TRY(cudaEventRecord(ex->chunk_done, st));                     // work already queued on st may still read the staging buffer
+        SGS_CUDA_TRY(cudaStreamWaitEvent(ex->copy_stream, ex->chunk_done, 0));
+        for (int c = 0, f0 = 0; f0 < nframes; ++c, f0 += per) {
+            const int nf = std::min(per, nframes - f0);
+            if (frame_stride == (size_t)pitch * PL.height) {
+                SGS_CUDA_TRY(cudaMemcpy2DAsync(ex->d_pyr + (size_t)f0 * g0.frame_stride, g0.pitch, gray + (size_t)f0 * frame_stride, pitch, PL.width,
+                                               (size_t)PL.height * nf, cudaMemcpyHostToDevice, ex->copy_stream));
+            } else {
+                for (int f = f0; f < f0 + nf; ++f)
+                    SGS_CUDA_TRY(cudaMemcpy2DAsync(ex->d_pyr + (size_t)f * g0.frame_stride, g0.pitch, gray + (size_t)f * frame_stride, pitch, PL.width, PL.height,
+                                                   cudaMemcpyHostToDevice, ex->copy_stream));
+            }
+            SGS_CUDA_TRY(cudaEventRecord(ex->chunk_ev[c], ex->copy_stream));
+            SGS_CUDA_TRY(cudaStreamWaitEvent(st, ex->chunk_ev[c], 0));
+            const int rc = enqueue(ex, ex->d_pyr, g0.pitch, g0.frame_stride, nf, st, f0, nframes, false);
+            if (rc != SGS_OK) return rc;
+        }
+        ex->last_level0_external = false;
+        return sgs_extractor_fetch(ex, nframes, kps, desc, cap, n, st);
+    }
     if (pinned) {
         if (frame_stride == (size_t)pitch * PL.height) {
             SGS_CUDA_TRY(cudaMemcpy2DAsync(ex->d_pyr, g0.pitch, gray, pitch, PL.width, (size_t)PL.height * nframes, cudaMemcpyHostToDevice, st));

@@ -31,6 +31,7 @@ struct FastTileGeom {
     int32_t list_cap;        // entries of the per-warp position list
     int32_t warp_stride;     // bytes of shared memory per warp (multiple of 128)
     int32_t use_tma;
+    int32_t frame0;          // frame index of P's frame 0 inside the tensor maps (chunked calls shift P's pointers, the maps stay whole)
 };
 
 // ---- exact FAST score -------------------------------------------------------------------------------------------------------
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) fast_warp_cells_kernel(const 
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(TP * G.th)) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&M.m[c.level])), "r"(xa), "r"((int)c.y0), "r"(f), "r"(mb)
+                         ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&M.m[c.level])), "r"(xa), "r"((int)c.y0), "r"(f + G.frame0), "r"(mb)
                          : "memory");
         }
     } else {
@@ -280,11 +281,11 @@ cudaError_t configure_fast_smem(size_t smem_bytes) {
     return cudaFuncSetAttribute(fast_warp_cells_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
 }
 
-void launch_fast_v2(const DevPlan& P, const FastTmaMaps& M, bool use_tma, const FastLaunchPlan& fp, const FastCell* d_cells, int ncells, cudaStream_t st) {
+void launch_fast_v2(const DevPlan& P, const FastTmaMaps& M, bool use_tma, const FastLaunchPlan& fp, const FastCell* d_cells, int ncells, int frame0, cudaStream_t st) {
     const int nitems = ncells * P.nframes;
     const int nblocks = (nitems + kFastWarps - 1) / kFastWarps;
     FastTileGeom G;
-    G.tp = fp.tp; G.th = fp.th; G.list_cap = fp.list_cap; G.warp_stride = fp.warp_stride; G.use_tma = use_tma ? 1 : 0;
+    G.tp = fp.tp; G.th = fp.th; G.list_cap = fp.list_cap; G.warp_stride = fp.warp_stride; G.use_tma = use_tma ? 1 : 0; G.frame0 = frame0;
     if (use_tma) fast_warp_cells_kernel<true><<<nblocks, kFastWarps * 32, fp.smem_bytes, st>>>(P, M, d_cells, ncells, nitems, G);
     else fast_warp_cells_kernel<false><<<nblocks, kFastWarps * 32, fp.smem_bytes, st>>>(P, M, d_cells, ncells, nitems, G);
 }

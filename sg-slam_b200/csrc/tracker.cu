@@ -22,6 +22,7 @@ struct sgs_tracker {
     int32_t* d_pidx = nullptr;
     double* d_Fgpu = nullptr; int32_t* d_finfo = nullptr;     // findFundamentalMat on the device
     cudaStream_t st = nullptr;
+    cudaStream_t copy_st = nullptr; cudaEvent_t copy_ev = nullptr;      // input uploads of sgs_tracker_track_lk run beside the LK kernels
     // device inputs of track()
     float* d_prev = nullptr; float* d_uright_in = nullptr; double* d_F = nullptr; sgs_rect* d_boxes = nullptr; int32_t* d_nboxes = nullptr;
     uint8_t* d_have = nullptr;
@@ -83,6 +84,8 @@ SGS_API void sgs_tracker_destroy(sgs_tracker* t) {
                     t->d_ln, t->d_tc, t->d_tl, t->d_kps2, t->d_desc2, t->d_cnt2, t->d_keep, t->d_uright2, t->d_mp, t->d_nm, t->d_ncand, t->d_Fgpu, t->d_finfo};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (t->st) cudaStreamDestroy(t->st);
+    if (t->copy_st) cudaStreamDestroy(t->copy_st);
+    if (t->copy_ev) cudaEventDestroy(t->copy_ev);
     delete t;
 }
 
@@ -104,6 +107,8 @@ SGS_API int sgs_tracker_create(const sgs_orb_params* params, int width, int heig
     if (cudaMalloc(&t->d_pidx, sizeof(int32_t) * (size_t)max_batch) != cudaSuccess) { set_error("sgs_tracker_create: cudaMalloc failed"); sgs_tracker_destroy(t); return SGS_ERR_CUDA; }
     const size_t B = max_batch, K = t->cap, M = point_cap;
     cudaError_t e = cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->copy_st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->copy_ev, cudaEventDisableTiming);
 #define A(call) if (e == cudaSuccess) e = (call)
     A(dalloc(&t->d_prev, B * K * 2)); A(dalloc(&t->d_uright_in, B * K)); A(dalloc(&t->d_F, B * 9)); A(dalloc(&t->d_boxes, B * t->max_boxes));
     A(dalloc(&t->d_nboxes, B)); A(dalloc(&t->d_have, B)); A(dalloc(&t->d_lxyz, B * M * 3)); A(dalloc(&t->d_ldesc, B * M * 32));
@@ -257,29 +262,33 @@ SGS_API int sgs_tracker_track_lk(sgs_tracker* t, int nframes, const int32_t* pre
     if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_track_lk: nframes exceeds the last sgs_tracker_extract call");
     SGS_CUDA_TRY(cudaSetDevice(t->device));
     for (int f = 0; f < nframes; ++f) if (prev_index[f] < 0 || prev_index[f] >= nframes) return bad("sgs_tracker_track_lk: prev_index out of range");
-    SGS_CUDA_TRY(cudaMemcpyAsync(t->d_pidx, prev_index, sizeof(int32_t) * (size_t)nframes, cudaMemcpyHostToDevice, t->st));
-    const uint8_t* d_frames; int pitch; size_t fstride;
-    sgs_extractor_level0_device(t->ex, &d_frames, &pitch, &fstride);
-    int rc = sgs_tracker_lk_device(t, d_frames, nframes, fstride, pitch, t->d_pidx, t->st);
-    if (rc != SGS_OK) return rc;
-    // same as sgs_tracker_track from here on, with prev_xy already on the device
     if (!u_right || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle || !last_n || !tcw_cur ||
         !tcw_last || !kps_out || !desc_out || !counts_out || !cur_mp_out || !nmatches_out) return bad("sgs_tracker_track_lk: NULL argument");
     const size_t B = nframes, K = t->cap, M = t->point_cap;
     cudaStream_t st = t->st;
-#define H2D(dst, src, bytes) SGS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st))
-    H2D(t->d_uright_in, u_right, B * K * 4);
-    if (F) H2D(t->d_F, F, B * 72);
-    if (boxes) H2D(t->d_boxes, boxes, B * t->max_boxes * sizeof(sgs_rect));
-    H2D(t->d_nboxes, nboxes, B * 4); H2D(t->d_have, have_dyn, B);
-    H2D(t->d_lxyz, last_xyz, B * M * 12); H2D(t->d_ldesc, last_desc, B * M * 32); H2D(t->d_lflags, last_flags, B * M);
-    H2D(t->d_loct, last_octave, B * M * 4); H2D(t->d_lang, last_angle, B * M * 4); H2D(t->d_ln, last_n, B * 4);
-    H2D(t->d_tc, tcw_cur, B * 64); H2D(t->d_tl, tcw_last, B * 64);
+    // what LK and the F estimate need goes first on the compute stream; the bulk of the inputs (last-frame points, u_right) is uploaded on
+    // the copy stream while those kernels run
+#define H2D(dst, src, bytes, s) SGS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s))
+    H2D(t->d_pidx, prev_index, sizeof(int32_t) * B, st);
+    if (F) H2D(t->d_F, F, B * 72, st);
+    if (boxes) H2D(t->d_boxes, boxes, B * t->max_boxes * sizeof(sgs_rect), st);
+    H2D(t->d_nboxes, nboxes, B * 4, st); H2D(t->d_have, have_dyn, B, st);
+    cudaStream_t cs = t->copy_st;
+    H2D(t->d_uright_in, u_right, B * K * 4, cs);
+    H2D(t->d_lxyz, last_xyz, B * M * 12, cs); H2D(t->d_ldesc, last_desc, B * M * 32, cs); H2D(t->d_lflags, last_flags, B * M, cs);
+    H2D(t->d_loct, last_octave, B * M * 4, cs); H2D(t->d_lang, last_angle, B * M * 4, cs); H2D(t->d_ln, last_n, B * 4, cs);
+    H2D(t->d_tc, tcw_cur, B * 64, cs); H2D(t->d_tl, tcw_last, B * 64, cs);
 #undef H2D
+    SGS_CUDA_TRY(cudaEventRecord(t->copy_ev, cs));
+    const uint8_t* d_frames; int pitch; size_t fstride;
+    sgs_extractor_level0_device(t->ex, &d_frames, &pitch, &fstride);
+    int rc = sgs_tracker_lk_device(t, d_frames, nframes, fstride, pitch, t->d_pidx, st);
+    if (rc != SGS_OK) return rc;
     if (!F) {       // F == NULL: findFundamentalMat on the device, previous-frame boxes = the boxes of row prev_index[f]
         rc = sgs_tracker_fundamental_device(t, nframes, t->d_boxes, t->d_nboxes, t->d_have, t->d_pidx, st);
         if (rc != SGS_OK) return rc;
     }
+    SGS_CUDA_TRY(cudaStreamWaitEvent(st, t->copy_ev, 0));
     rc = sgs_tracker_track_device(t, nframes, nullptr, t->d_uright_in, F ? t->d_F : nullptr, t->d_boxes, t->d_nboxes, t->d_have, t->d_lxyz, t->d_ldesc, t->d_lflags,
                                   t->d_loct, t->d_lang, t->d_ln, t->d_tc, t->d_tl, th, mono, check_orientation, st);
     if (rc != SGS_OK) return rc;

@@ -1,5 +1,7 @@
 // test_shim.cpp -- compiles the reference-shaped C++ headers (include/sgslam/*.h) without OpenCV and drives them on the GPU.
 // Scenario + expected results come from files written by tests/test_gpu_cpp_shim.py (expected = CPU oracle).
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -100,6 +102,27 @@ int main(int argc, char** argv) {
     if (kept != exp_keep || (int)dk2.size() != exp_keep) return fail("dynreject: count");
     int w = 0;
     for (int i = 0; i < nd; ++i) if (exp_keepmask[i]) { if (std::memcmp(&dk2[w], &dk[i], sizeof(cv::KeyPoint)) || std::memcmp(ddc.ptr<uint8_t>(w), &dd[(size_t)i * 32], 32)) return fail("dynreject: compaction"); ++w; }
-    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept\n", nkp, nm, kept, nd);
+    // 4. LK + findFundamentalMat shims (tolerances of tests/test_gpu_lk.py / test_gpu_fundamental.py)
+    int32_t nlk = 0; f.read(reinterpret_cast<char*>(&nlk), 4);
+    std::vector<uint8_t> im1 = rd<uint8_t>(f, (size_t)W * H), im0 = rd<uint8_t>(f, (size_t)W * H);
+    std::vector<cv::Point2f> cpts = rd<cv::Point2f>(f, nlk), exp_trk = rd<cv::Point2f>(f, nlk);
+    std::vector<double> expF = rd<double>(f, 9);
+    std::vector<cv::Point2f> ppts;
+    CalcOpticalFlowPyrLK(cv::Mat(H, W, CV_8UC1, im1.data(), W), cv::Mat(H, W, CV_8UC1, im0.data(), W), cpts, ppts);
+    int far = 0;
+    for (int i = 0; i < nlk; ++i) {
+        const float e = std::max(std::fabs(ppts[i].x - exp_trk[i].x), std::fabs(ppts[i].y - exp_trk[i].y));
+        if (e > 0.25f) return fail("LK: track");
+        if (e > 0.02f) ++far;
+    }
+    if (far > std::max(1, nlk * 3 / 1000)) return fail("LK: too many loose tracks");
+    cv::Mat Fg = FindFundamentalMatRansac(cpts, exp_trk);          // on the expected tracks, so F is comparable entry by entry
+    if (Fg.empty()) return fail("findFundamentalMat: empty");
+    double fmax = 1.0;
+    for (int i = 0; i < 9; ++i) fmax = std::max(fmax, std::fabs(expF[i]));
+    for (int i = 0; i < 9; ++i) if (std::fabs(Fg.at<double>(i / 3, i % 3) - expF[i]) > 1e-9 * fmax) return fail("findFundamentalMat: F");
+    if (!FindFundamentalMatRansac(std::vector<cv::Point2f>(cpts.begin(), cpts.begin() + 10), std::vector<cv::Point2f>(exp_trk.begin(), exp_trk.begin() + 10)).empty())
+        return fail("findFundamentalMat: fewer than 15 pairs must come back empty");
+    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok\n", nkp, nm, kept, nd, nlk);
     return 0;
 }

@@ -47,6 +47,15 @@ def test_shim_on_gpu(tmp_path):
         s['last_desc'].tofile(f); s['last_oct'].astype(np.int32).tofile(f); s['last_angle'].astype(np.float32).tofile(f); mp.astype(np.int32).tofile(f)
         dk.tofile(f); desc.tofile(f); d['prev'].astype(np.float32).tofile(f); d['F'].astype(np.float64).tofile(f)
         d['boxes'].astype(np.float32).tofile(f); keep.astype(np.uint8).tofile(f)
+        # 4. LK + findFundamentalMat shims: a second frame of the stream, the oracle's tracks and its F on them
+        frames, _ = synth.stream_s2(2, 640, 480, seed=9)
+        k2, _ = O.extract(frames[1])
+        pts = np.stack([k2['x'], k2['y']], 1).astype(np.float32)
+        trk = O.lk_track(frames[1], frames[0], pts)
+        Fo, _, _ = O.find_fundamental_ransac(pts, trk)
+        assert Fo is not None
+        np.array([len(pts)], np.int32).tofile(f); frames[1].tofile(f); frames[0].tofile(f); pts.tofile(f); trk.astype(np.float32).tofile(f)
+        Fo.astype(np.float64).tofile(f)
     out = subprocess.run([exe, str(path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'OK shim' in out.stdout

@@ -1,4 +1,5 @@
 """GPU parity: the CUDA extractor (through the C ABI) against the CPU oracle and the golden fixtures.  Bit-exact."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -143,5 +144,30 @@ def test_device_resident_batch_with_torch():
             ko, do = O.extract(frames[f])
             assert counts[f] == len(ko)
             assert kps[f, :counts[f]].tobytes() == ko.tobytes() and np.array_equal(desc[f, :counts[f]], do)
+    finally:
+        ex.close()
+
+
+def test_large_pinned_batch_goes_up_in_chunks():
+    """>= 64 pinned frames take the chunked upload path (copy stream ahead of the kernels): results must equal the unchunked ones."""
+    import torch
+    base, _ = synth.stream_s2(6, 640, 480, seed=12)
+    nf = 70          # two chunks of 35
+    frames = np.stack([np.roll(base[i % 6], 3 * (i // 6), 1) for i in range(nf)])
+    ex = B.Extractor(640, 480, max_batch=nf)
+    try:
+        ref_k, ref_d, ref_n = ex.extract_batch(frames)                       # pageable input: staging path, one enqueue
+        pin = torch.from_numpy(frames).pin_memory()
+        hk = torch.zeros((nf, ex.cap, 28), dtype=torch.uint8).pin_memory(); hd = torch.zeros((nf, ex.cap, 32), dtype=torch.uint8).pin_memory()
+        n = np.zeros(nf, np.int32)
+        B.check(B.lib().sgs_extract_batch(ex.h, C.c_void_p(pin.data_ptr()), nf, C.c_size_t(640 * 480), 640, C.c_void_p(hk.data_ptr()), C.c_void_p(hd.data_ptr()), ex.cap,
+                                          n.ctypes.data_as(C.c_void_p)))
+        assert np.array_equal(n, ref_n)
+        k = hk.numpy().reshape(nf, ex.cap * 28).view(B.KP_DTYPE).reshape(nf, ex.cap)
+        for f in range(nf):
+            assert k[f, :n[f]].tobytes() == ref_k[f, :n[f]].tobytes() and np.array_equal(hd.numpy()[f, :n[f]], ref_d[f, :n[f]]), f
+        for f in (0, 34, 35, 69):
+            ok, od = O.extract(frames[f])
+            assert k[f, :n[f]].tobytes() == ok.tobytes() and np.array_equal(hd.numpy()[f, :n[f]], od)
     finally:
         ex.close()
