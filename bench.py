@@ -36,7 +36,8 @@ for p in (os.path.join(ROOT, 'sg-slam_b200'), os.path.join(ROOT, 'oracle'), os.p
 W, H, NFEAT = 640, 480, 1000
 ALG_BYTES_EXTRACT = 5_902_474          # algorithmic bytes per 640x480 frame, ORB extract
 ALG_BYTES_FAST_READ = 950_532          # sum of level pixels (FAST reads every level once)
-ALG_BYTES_LK = 4_200_000               # pyramids + window gathers of LK, ~4.2 MB per frame
+ALG_BYTES_LK_PYR = 504_000             # one cv::pyrDown pyramid per frame (each frame is also the previous frame of the next): read L0..L2, write L1..L3
+ALG_BYTES_LK = ALG_BYTES_LK_PYR + 1000 * 4 * 2 * 529   # + N points x 4 levels x 2 images x 23^2 window bytes (~4.2 MB + pyramid)
 TH = 15.0                              # Tracking.cc:919-923 (RGB-D)
 LAUNCHES_PER_STEP = 18 + 4 + 1 + 2 + 1     # extract (7 resize, FAST, quadtree, 8 blur, describe) + LK (3 pyrDown, track) + RANSAC F + dyn-reject/compact + match
 
@@ -339,6 +340,9 @@ def main():
             dev_extract(); dev_lk(); dev_fm(); dev_track()
     barrier()
     B.check(L.sgs_extractor_set_profiling(exh, 1))
+    L.sgs_tracker_lk.restype = C.c_void_p
+    lkh = v(L.sgs_tracker_lk(trk.h))
+    B.check(L.sgs_lk_set_profiling(lkh, 1))
     sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * args.steps + 1)]
     barrier()
@@ -360,6 +364,10 @@ def main():
     B.check(L.sgs_extractor_stage_times(exh, ms5, C.byref(ncalls)))
     stage_ms = [ms5[i] / max(1, ncalls.value) for i in range(5)]
     B.check(L.sgs_extractor_set_profiling(exh, 0))
+    ms2 = (C.c_double * 2)()
+    B.check(L.sgs_lk_stage_times(lkh, ms2, C.byref(ncalls)))
+    lk_pyr_ms, lk_track_ms = ms2[0] / max(1, ncalls.value), ms2[1] / max(1, ncalls.value)
+    B.check(L.sgs_lk_set_profiling(lkh, 0))
     value = world * NB * args.steps / (total_ms * 1e-3)
     prev_dev = B.memcpy_d2h(np.zeros((NB, cap, 2), np.float32), pp.value)     # LK output of the last device step
     pF, pI = v(), v()
@@ -386,29 +394,44 @@ def main():
                'ms_per_step': 1e3 * dt / args.steps,
                'note': 'sgs_tracker_extract (host frames -> host keypoints) + sgs_tracker_track_lk (LK + RANSAC F + dyn-reject + match on the resident batch) with pinned host buffers'}
 
-    # ---- roofline of the dominant extractor kernel ------------------------------------------------------------------------
+    # ---- roofline of the dominant kernel of the step (all timed live with CUDA events on the launching stream) -----------------
     peaks, peak_kind = measured_peaks()
     names = ['pyramid(7 launches)', 'fast_warp_cells_kernel', 'quadtree_kernel', 'blur(8 launches)', 'describe_kernel']
-    dom = int(np.argmax(stage_ms))
     ncand_frame0 = 0
     for l in range(8):
         nn = C.c_int()
         L.sgs_extractor_read_candidates(exh, 0, l, None, 0, C.byref(nn))   # count only (returns SGS_ERR_CAPACITY by design)
         ncand_frame0 += nn.value
     nk = int(n0.mean())
-    alg = {0: 1_569_878, 1: ALG_BYTES_FAST_READ + 4 * ncand_frame0, 2: 8 * ncand_frame0 + 4 * nk, 3: 1_901_064, 4: (749 + 544 + 60) * nk}
+    # algorithmic bytes per frame: extractor stages as listed there; LK tracker = N points x 4 levels x 2 images x 23^2 B
+    alg = {'pyramid(7 launches)': 1_569_878, 'fast_warp_cells_kernel': ALG_BYTES_FAST_READ + 4 * ncand_frame0, 'quadtree_kernel': 8 * ncand_frame0 + 4 * nk,
+           'blur(8 launches)': 1_901_064, 'describe_kernel': (749 + 544 + 60) * nk, 'lk_pyrdown(3 launches)': ALG_BYTES_LK_PYR,
+           'lk_track_kernel': nk * 4 * 2 * 529, 'fm_ransac_kernel': 16 * nk + 72, 'dynreject+compact+match(3 launches)': 76 * nk + 56 * nk + 44 * 8 * nk}
+    all_ms = dict(zip(names, stage_ms))
+    all_ms.update({'lk_pyrdown(3 launches)': lk_pyr_ms, 'lk_track_kernel': lk_track_ms, 'fm_ransac_kernel': fm_ms, 'dynreject+compact+match(3 launches)': track_ms})
+    dom = max(('fast_warp_cells_kernel', 'quadtree_kernel', 'describe_kernel', 'lk_track_kernel', 'fm_ransac_kernel'), key=lambda k: all_ms[k])   # single-launch kernels
     dom_bytes = alg[dom] * NB
-    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
-    step_alg_bytes = (ALG_BYTES_EXTRACT + ALG_BYTES_LK + 76 * nk + 56 * nk + 44 * 8 * nk) * NB
-    roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
-                'traffic': None, 'peak_kind': ('measured copy bandwidth (MEASURED_PEAKS.json)' if peak_kind == 'measured' else 'fallback 6650 GB/s'),
-                'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': stage_ms[dom],
-                'stage_ms': dict(zip(names, [round(x, 4) for x in stage_ms])), 'extract_ms': extract_ms, 'lk_ms': lk_ms, 'fundamental_ransac_ms': fm_ms, 'dynreject_match_ms': track_ms,
+    achieved = dom_bytes / (all_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    try:        # dram__bytes_read + write of that kernel from the committed ncu --set full capture (profiles/), per launch
+        txt = open(os.path.join(ROOT, 'profiles', 'r01c_ncu_full_summary.txt')).read().split('=== ')
+        blk = [b for b in txt if b.startswith(dom)][0]
+        rd = float([l for l in blk.splitlines() if 'dram__bytes_read.sum' in l][0].split()[-1]); wr = float([l for l in blk.splitlines() if 'dram__bytes_write.sum' in l][0].split()[-1])
+        traffic = int((rd + wr) * 1e6)          # the summary prints Mbyte for a 512-frame launch
+    except Exception:
+        pass
+    step_alg_bytes = (ALG_BYTES_EXTRACT + ALG_BYTES_LK + 16 * nk + 76 * nk + 56 * nk + 44 * 8 * nk) * NB
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
+                'traffic': traffic, 'peak_kind': ('measured copy bandwidth (MEASURED_PEAKS.json)' if peak_kind == 'measured' else 'fallback 6650 GB/s'),
+                'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': all_ms[dom],
+                'stage_ms': {k: round(x, 4) for k, x in all_ms.items()}, 'extract_ms': extract_ms, 'lk_ms': lk_ms, 'fundamental_ransac_ms': fm_ms,
+                'dynreject_match_ms': track_ms,
+                'per_kernel_alg_gbs': {k: round(alg[k] * NB / (all_ms[k] * 1e-3) / 1e9, 1) for k in all_ms},
                 'extract_alg_gbs': ALG_BYTES_EXTRACT * NB / (extract_ms * 1e-3) / 1e9,
                 'extract_frac_of_hbm': ALG_BYTES_EXTRACT * NB / (extract_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
                 'step_alg_gbs': step_alg_bytes / (total_ms / args.steps * 1e-3) / 1e9,
                 'step_frac_of_hbm': step_alg_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                'note': 'every kernel of the step is instruction-issue / latency bound (DRAM throughput 1-12 % in profiles/): the HBM fraction is reported as asked, the binding roof is the integer ALU / issue rate'}
+                'note': 'every kernel of the step is instruction-issue / latency bound (DRAM throughput 0.4-18 % in profiles/): the HBM fraction is reported as asked, the binding roof is the integer ALU / issue rate (lk_track_kernel: 55 % issue-active at 16 warps/SM)'}
 
     # ---- CPU baseline on this box's host cores (rank 0 only, N=1 only) + parity of the sample -------------------------------
     cpu = None

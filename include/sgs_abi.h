@@ -353,6 +353,11 @@ SGS_API int sgs_lk_track_batch_device(sgs_lk* k, const uint8_t* d_cur, const uin
                                       const int32_t* d_counts, int cap, float* d_prev_xy, void* stream);
 /* parity accessor: pyramid level (1..3) of frame 0 of the last call; which = 0 current image, 1 previous image */
 SGS_API int sgs_lk_read_level(sgs_lk* k, int which, int level, uint8_t* out, int out_pitch);
+/* Stage timing with CUDA events on the launching stream, like sgs_extractor_set_profiling / _stage_times:
+ * ms_total2 = accumulated {pyramid build (cv::pyrDown levels), lk_track_kernel} over *ncalls calls. */
+SGS_API int sgs_lk_set_profiling(sgs_lk* k, int enable);
+SGS_API int sgs_lk_stage_times(sgs_lk* k, double* ms_total2, int* ncalls);
+SGS_API sgs_lk* sgs_tracker_lk(sgs_tracker* t);                 /* the LK handle owned by the tracker (profiling) */
 
 /* harness helper: synchronous device -> host copy of a buffer returned by one of the *_device accessors */
 SGS_API int sgs_memcpy_d2h(void* dst, const void* d_src, size_t bytes);

@@ -315,6 +315,8 @@ struct sgs_lk {
     // staging for the single-pair host API
     uint8_t* d_img = nullptr; float* d_pts = nullptr; float* d_out = nullptr; int pts_cap = 0;
     cudaStream_t st = nullptr;
+    // optional stage timing (pyramid build, tracker), same contract as sgs_extractor_set_profiling
+    bool profiling = false, pending = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; double ms_acc[2] = {0, 0}; int calls = 0;
 };
 
 namespace {
@@ -332,6 +334,15 @@ void build_pyramid(sgs_lk* k, const uint8_t* d_l0, int pitch0, int64_t fstride0,
 
 int run_lk(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, const int32_t* d_prev_index, int nframes, size_t frame_stride, int pitch,
            const sgs_keypoint* d_kps, const float* d_pts, const int32_t* d_counts, int cap, float* d_out, cudaStream_t st) {
+    const bool prof = k->profiling;
+    if (prof && k->pending) {
+        if (cudaEventSynchronize(k->ev[2]) == cudaSuccess) {
+            for (int i = 0; i < 2; ++i) { float ms = 0; cudaEventElapsedTime(&ms, k->ev[i], k->ev[i + 1]); k->ms_acc[i] += ms; }
+            k->calls++;
+        }
+        k->pending = false;
+    }
+    if (prof) cudaEventRecord(k->ev[0], st);
     build_pyramid(k, d_cur, pitch, (int64_t)frame_stride, k->d_pyrI, nframes, st);
     const bool same_batch = d_prev_index != nullptr;     // previous images are other frames of the same batch: one pyramid serves both roles
     if (!same_batch) build_pyramid(k, d_prev, pitch, (int64_t)frame_stride, k->d_pyrJ, nframes, st);
@@ -344,8 +355,10 @@ int run_lk(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, const int32_t
     }
     for (int l = k->max_level + 1; l <= kLkMaxLevel; ++l) { L.I[l] = L.J[l] = nullptr; L.w[l] = L.h[l] = L.pitch[l] = 0; L.fstride[l] = 0; }
     L.pitchJ0 = pitch; L.fstrideJ0 = (int64_t)frame_stride;
+    if (prof) cudaEventRecord(k->ev[1], st);
     dim3 grid((cap + kLkWarps - 1) / kLkWarps, nframes);
     lk_track_kernel<<<grid, kLkWarps * 32, 0, st>>>(L, d_kps, reinterpret_cast<const float2*>(d_pts), d_counts, cap, d_prev_index, reinterpret_cast<float2*>(d_out));
+    if (prof) { cudaEventRecord(k->ev[2], st); k->pending = true; }
     SGS_CUDA_TRY(cudaGetLastError());
     return SGS_OK;
 }
@@ -353,9 +366,28 @@ int run_lk(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, const int32_t
 
 extern "C" {
 
+SGS_API int sgs_lk_set_profiling(sgs_lk* k, int enable) {
+    if (!k) return lk_bad("sgs_lk_set_profiling: NULL");
+    SGS_CUDA_TRY(cudaSetDevice(k->device));
+    if (enable && !k->ev[0]) for (auto& e : k->ev) SGS_CUDA_TRY(cudaEventCreate(&e));
+    k->profiling = enable != 0; k->pending = false; k->ms_acc[0] = k->ms_acc[1] = 0; k->calls = 0;
+    return SGS_OK;
+}
+
+SGS_API int sgs_lk_stage_times(sgs_lk* k, double* ms_total2, int* ncalls) {
+    if (!k || !ms_total2 || !ncalls) return lk_bad("sgs_lk_stage_times: NULL");
+    if (k->pending && cudaEventSynchronize(k->ev[2]) == cudaSuccess) {
+        for (int i = 0; i < 2; ++i) { float ms = 0; cudaEventElapsedTime(&ms, k->ev[i], k->ev[i + 1]); k->ms_acc[i] += ms; }
+        k->calls++; k->pending = false;
+    }
+    ms_total2[0] = k->ms_acc[0]; ms_total2[1] = k->ms_acc[1]; *ncalls = k->calls;
+    return SGS_OK;
+}
+
 SGS_API void sgs_lk_destroy(sgs_lk* k) {
     if (!k) return;
     cudaSetDevice(k->device);
+    for (auto& e : k->ev) if (e) cudaEventDestroy(e);
     cudaFree(k->d_pyrI); cudaFree(k->d_pyrJ); cudaFree(k->d_img); cudaFree(k->d_pts); cudaFree(k->d_out);
     if (k->st) cudaStreamDestroy(k->st);
     delete k;

@@ -218,6 +218,7 @@ SGS_API int sgs_tracker_track(sgs_tracker* t, int nframes, const float* prev_xy,
 }
 
 SGS_API sgs_extractor* sgs_tracker_extractor(sgs_tracker* t) { return t ? t->ex : nullptr; }
+SGS_API sgs_lk* sgs_tracker_lk(sgs_tracker* t) { return t ? t->lk : nullptr; }
 
 SGS_API int sgs_tracker_lk_device(sgs_tracker* t, const uint8_t* d_frames, int nframes, size_t frame_stride, int pitch, const int32_t* d_prev_index,
                                   void* stream) {

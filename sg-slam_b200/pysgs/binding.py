@@ -75,6 +75,7 @@ ABI_SYMBOLS = [
     'sgs_extractor_set_profiling', 'sgs_extractor_stage_times',
     'sgs_lk_create', 'sgs_lk_destroy', 'sgs_lk_track', 'sgs_lk_track_batch_device', 'sgs_lk_read_level',
     'sgs_tracker_lk_device', 'sgs_tracker_prev_xy_device', 'sgs_tracker_track_lk', 'sgs_extractor_level0_device', 'sgs_memcpy_d2h',
+    'sgs_lk_set_profiling', 'sgs_lk_stage_times', 'sgs_tracker_lk',
     'sgs_fundamental_ransac', 'sgs_fundamental_batch_device', 'sgs_tracker_fundamental_device', 'sgs_tracker_fundamental_device_ptr',
 ]
 
