@@ -36,10 +36,11 @@ for p in (os.path.join(ROOT, 'sg-slam_b200'), os.path.join(ROOT, 'oracle'), os.p
 W, H, NFEAT = 640, 480, 1000
 ALG_BYTES_EXTRACT = 5_902_474          # algorithmic bytes per 640x480 frame, ORB extract
 ALG_BYTES_FAST_READ = 950_532          # sum of level pixels (FAST reads every level once)
-ALG_BYTES_LK_PYR = 504_000             # one cv::pyrDown pyramid per frame (each frame is also the previous frame of the next): read L0..L2, write L1..L3
+ALG_BYTES_LK_PYR = 408_000 * 6 + 403_200   # one padded pyramid + derivative planes per frame (each frame is also the previous frame of the next):
+                                           # per level pixel 1 B read + 1 B write + 4 B derivative, + cv::pyrDown reading L0..L2
 ALG_BYTES_LK = ALG_BYTES_LK_PYR + 1000 * 4 * 2 * 529   # + N points x 4 levels x 2 images x 23^2 window bytes (~4.2 MB + pyramid)
 TH = 15.0                              # Tracking.cc:919-923 (RGB-D)
-LAUNCHES_PER_STEP = 18 + 4 + 1 + 2 + 1     # extract (7 resize, FAST, quadtree, 8 blur, describe) + LK (3 pyrDown, track) + RANSAC F + dyn-reject/compact + match
+LAUNCHES_PER_STEP = 18 + 12 + 1 + 2 + 1    # extract (7 resize, FAST, quadtree, 8 blur, describe) + LK (3 pyrDown, 4 Scharr, 4 border, track) + RANSAC F + dyn-reject/compact + match
 
 
 def log(*a):
@@ -405,10 +406,10 @@ def main():
     nk = int(n0.mean())
     # algorithmic bytes per frame: extractor stages as listed there; LK tracker = N points x 4 levels x 2 images x 23^2 B
     alg = {'pyramid(7 launches)': 1_569_878, 'fast_warp_cells_kernel': ALG_BYTES_FAST_READ + 4 * ncand_frame0, 'quadtree_kernel': 8 * ncand_frame0 + 4 * nk,
-           'blur(8 launches)': 1_901_064, 'describe_kernel': (749 + 544 + 60) * nk, 'lk_pyrdown(3 launches)': ALG_BYTES_LK_PYR,
+           'blur(8 launches)': 1_901_064, 'describe_kernel': (749 + 544 + 60) * nk, 'lk_pyramid+deriv(11 launches)': ALG_BYTES_LK_PYR,
            'lk_track_kernel': nk * 4 * 2 * 529, 'fm_ransac_kernel': 16 * nk + 72, 'dynreject+compact+match(3 launches)': 76 * nk + 56 * nk + 44 * 8 * nk}
     all_ms = dict(zip(names, stage_ms))
-    all_ms.update({'lk_pyrdown(3 launches)': lk_pyr_ms, 'lk_track_kernel': lk_track_ms, 'fm_ransac_kernel': fm_ms, 'dynreject+compact+match(3 launches)': track_ms})
+    all_ms.update({'lk_pyramid+deriv(11 launches)': lk_pyr_ms, 'lk_track_kernel': lk_track_ms, 'fm_ransac_kernel': fm_ms, 'dynreject+compact+match(3 launches)': track_ms})
     dom = max(('fast_warp_cells_kernel', 'quadtree_kernel', 'describe_kernel', 'lk_track_kernel', 'fm_ransac_kernel'), key=lambda k: all_ms[k])   # single-launch kernels
     dom_bytes = alg[dom] * NB
     achieved = dom_bytes / (all_ms[dom] * 1e-3) / 1e9

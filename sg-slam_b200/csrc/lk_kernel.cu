@@ -2,14 +2,17 @@
 // I = current gray, J = previous gray, window 21x21, 4 pyramid levels, <= 30 iterations or |delta|^2 <= 1e-4.
 // Follows OpenCV video/lkpyramid.cpp: cv::pyrDown levels (bit-exact integers), Scharr derivatives of I (int16, zero outside the
 // image), 14-bit fixed-point bilinear window extraction, float 2x2 solve.  Sums of integer products are accumulated EXACTLY
-// (int64) and rounded once; OpenCV accumulates them in float in SIMD order, so positions agree to ~1e-4 px, not bit-for-bit
+// (int32/int64) and rounded once; OpenCV accumulates them in float in SIMD order, so positions agree to ~1e-4 px, not bit-for-bit
 // (tolerance stated in tests/test_gpu_lk.py).  status/err are not produced (the reference ignores them, quirk Q4); a level
 // that fails leaves the running estimate untouched.
 //
+// Like buildOpticalFlowPyramid, every level is stored with a border of kLkPad pixels (REFLECT_101) and has a derivative image
+// (dx | dy << 16, zero border), so the tracker reads windows straight through the image edge without any per-pixel border logic.
 // One warp per point; the 21x21 window is tiled over the lanes (7x2 pixels each + one pixel of the last column) and lives in
 // registers for the whole level; no shared memory.
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <vector>
 
 #include "sgs_common.h"
@@ -19,11 +22,12 @@ namespace sgs {
 constexpr int kWin = 21, kLkMaxLevel = 3, kLkMaxCount = 30;
 constexpr int kLkWarps = 4;
 
-struct LkLevels {
-    const uint8_t* I[kLkMaxLevel + 1]; const uint8_t* J[kLkMaxLevel + 1];
-    int32_t w[kLkMaxLevel + 1], h[kLkMaxLevel + 1], pitch[kLkMaxLevel + 1];
-    int64_t fstride[kLkMaxLevel + 1];
-    int32_t pitchJ0; int64_t fstrideJ0;     // level 0 of J may have its own layout (caller buffers)
+constexpr int kLkPad = 24;            // the window reaches 22 px past the image on every side
+
+struct LkLevels {                     // pointers address pixel (0, 0) of frame 0 of each padded level
+    const uint8_t* I[kLkMaxLevel + 1]; const uint8_t* J[kLkMaxLevel + 1]; const uint32_t* D[kLkMaxLevel + 1];
+    int32_t w[kLkMaxLevel + 1], h[kLkMaxLevel + 1], pitch[kLkMaxLevel + 1];      // pitch in pixels, shared by image and derivative planes
+    int64_t fstride[kLkMaxLevel + 1];                                            // pixels between frames
     int32_t max_level;
 };
 
@@ -53,6 +57,65 @@ __global__ void __launch_bounds__(256) lk_pyrdown_kernel(const uint8_t* __restri
 
 // Exact warp sums of per-lane int32 partials.  |partial| < 15 * 8160 * 4080 < 2^28.9, so the first stages stay in int32 (4 lanes for
 // the mismatch sums, 8 lanes for the gradient sums whose terms are < 4080^2) before widening.
+// Interior of a padded level: optional copy from an unpadded source (level 0; src == dst interior when cv::pyrDown already wrote it)
+// and the Scharr derivatives (calcScharrDeriv: REFLECT_101 at the image edge) stored as dx | dy << 16.
+//   t0(x) = 3 (s[y-1][x] + s[y+1][x]) + 10 s[y][x],  t1(x) = s[y+1][x] - s[y-1][x];  dx = t0(x+1) - t0(x-1),  dy = 3 (t1(x-1) + t1(x+1)) + 10 t1(x)
+// kVec: four pixels per thread from aligned 32-bit loads (needs 4-byte aligned rows and w % 4 == 0); otherwise one pixel per thread.
+template <bool kVec>
+__global__ void __launch_bounds__(256) lk_interior_kernel(const uint8_t* __restrict__ src, int spitch, int64_t sfstride, uint8_t* dst, bool copy,
+                                                          uint32_t* __restrict__ deriv, int w, int h, int pitch, int64_t fstride) {
+    const int tx = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int X = kVec ? 4 * tx : tx;
+    if (X >= w || Y >= h) return;
+    const uint8_t* S = src + (int64_t)blockIdx.z * sfstride;
+    const int ym = Y == 0 ? (h > 1 ? 1 : 0) : Y - 1, yp = Y == h - 1 ? (h > 1 ? h - 2 : 0) : Y + 1;
+    const uint8_t* r0 = S + (int64_t)ym * spitch; const uint8_t* r1 = S + (int64_t)Y * spitch; const uint8_t* r2 = S + (int64_t)yp * spitch;
+    const int64_t o = (int64_t)blockIdx.z * fstride + (int64_t)Y * pitch + X;
+    if (kVec) {
+        const int xm = X == 0 ? 1 : X - 1, xp = X + 4 >= w ? w - 2 : X + 4;
+        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(r0 + X)), w1 = __ldg(reinterpret_cast<const uint32_t*>(r1 + X)),
+                       w2 = __ldg(reinterpret_cast<const uint32_t*>(r2 + X));
+        int a[6], b[6], c[6];          // columns X-1 .. X+4 of the three rows
+        a[0] = __ldg(r0 + xm); b[0] = __ldg(r1 + xm); c[0] = __ldg(r2 + xm);
+        a[5] = __ldg(r0 + xp); b[5] = __ldg(r1 + xp); c[5] = __ldg(r2 + xp);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i + 1] = (w0 >> (8 * i)) & 255; b[i + 1] = (w1 >> (8 * i)) & 255; c[i + 1] = (w2 >> (8 * i)) & 255; }
+        int t0[6], t1[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { t0[i] = (a[i] + c[i]) * 3 + b[i] * 10; t1[i] = c[i] - a[i]; }
+        uint4 d;
+        uint32_t* dp = &d.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int dx = t0[i + 2] - t0[i], dy = (t1[i] + t1[i + 2]) * 3 + t1[i + 1] * 10;
+            dp[i] = ((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16);
+        }
+        *reinterpret_cast<uint4*>(deriv + o) = d;
+        if (copy) *reinterpret_cast<uint32_t*>(dst + o) = w1;
+    } else {
+        const int xm = X == 0 ? (w > 1 ? 1 : 0) : X - 1, xp = X == w - 1 ? (w > 1 ? w - 2 : 0) : X + 1;
+        const int t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10, t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10;
+        const int t1m = r2[xm] - r0[xm], t1c = r2[X] - r0[X], t1p = r2[xp] - r0[xp];
+        const int dx = t0p - t0m, dy = (t1m + t1p) * 3 + t1c * 10;
+        deriv[o] = ((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16);
+        if (copy) dst[o] = r1[X];
+    }
+}
+
+// REFLECT_101 border of a padded level from its interior.  One thread per border pixel: `band` rows above and below the image span
+// the padded width, the side bands span the image rows.
+__global__ void __launch_bounds__(256) lk_border_kernel(uint8_t* dst, int w, int h, int pitch, int64_t fstride) {
+    const int pw = w + 2 * kLkPad;
+    const int n_tb = 2 * kLkPad * pw, n_side = 2 * kLkPad * h;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_tb + n_side) return;
+    int X, Y;
+    if (i < n_tb) { const int r = i / pw; X = i - r * pw - kLkPad; Y = r < kLkPad ? r - kLkPad : h + (r - kLkPad); }
+    else { const int j = i - n_tb; const int r = j / (2 * kLkPad), c = j - r * (2 * kLkPad); Y = r; X = c < kLkPad ? c - kLkPad : w + (c - kLkPad); }
+    uint8_t* F = dst + (int64_t)blockIdx.z * fstride;
+    F[(int64_t)Y * pitch + X] = F[(int64_t)lk_refl(Y, h) * pitch + lk_refl(X, w)];
+}
+
 __device__ __forceinline__ long long warp_sum_grad(int v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
     long long w = v;
@@ -81,67 +144,27 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
 }
 
 
-// Window set-up of one level, in the tiled ownership of lk_mismatch_tiles (see there): each lane loads the 10x5 raw bytes of I under
-// its 7x2 window pixels (reflect-101 outside the image), forms the Scharr rows it needs (8x3; zero where the derivative position is
-// outside the image, BORDER_CONSTANT) and interpolates I, Ix, Iy with the 14-bit weights; lanes 0..20 do the same for their pixel of
-// window column 20.  Outputs stay in registers: C = 256 - 512 Iw, GX = Ix, GY = Iy; s11/s12/s22 are this lane's share of the
-// gradient matrix (exact in int32: 15 terms of < 2^24.1).  kInside: the whole 24x24 raw patch lies inside the image.
-template <bool kInside>
-__device__ __forceinline__ void lk_setup_tiles(const uint8_t* __restrict__ img, int pitch, int lw, int lh, int ipx, int ipy,
+// Window set-up of one level, in the tiled ownership of lk_mismatch_tiles (see there): each lane reads the 8x3 pixels of I and the
+// 8x3 derivative words under its 7x2 window pixels (+ 2x2 for its pixel of column 20) from the padded planes and interpolates I, Ix,
+// Iy with the 14-bit weights.  Outputs stay in registers: C = 256 - 512 Iw, GX = Ix, GY = Iy; s11/s12/s22 are this lane's share of
+// the gradient matrix (exact in int32: 15 terms of < 2^24.1).
+__device__ __forceinline__ void lk_setup_tiles(const uint8_t* __restrict__ img, const uint32_t* __restrict__ der, int pitch, int ipx, int ipy,
                                                int k2, int g7, int erow, int lane, int w00, int w01, int w10, int w11,
                                                int (&C)[14], int (&GX)[14], int (&GY)[14], int& Ce, int& GXe, int& GYe,
                                                int& s11, int& s12, int& s22) {
-    int R[10][5], E[4][4];
-    if (kInside) {
-        const uint8_t* p = img + (int64_t)(ipy - 1 + g7) * pitch + (ipx - 1 + k2);
+    int R[8][3], Dx[8][3], Dy[8][3];
+    {
+        const int64_t o = (int64_t)(ipy + g7) * pitch + (ipx + k2);
+        const uint8_t* p = img + o; const uint32_t* q = der + o;
 #pragma unroll
-        for (int r = 0; r < 10; ++r) {
+        for (int r = 0; r < 8; ++r) {
 #pragma unroll
-            for (int x = 0; x < 5; ++x) R[r][x] = __ldg(p + x);
-            p += pitch;
-        }
-        const uint8_t* q = img + (int64_t)(ipy - 1 + erow) * pitch + (ipx + 19);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-#pragma unroll
-            for (int x = 0; x < 4; ++x) E[r][x] = __ldg(q + x);
-            q += pitch;
-        }
-    } else {
-        int cx[5], ce[4];
-#pragma unroll
-        for (int x = 0; x < 5; ++x) cx[x] = lk_refl(ipx - 1 + k2 + x, lw);
-#pragma unroll
-        for (int x = 0; x < 4; ++x) ce[x] = lk_refl(ipx + 19 + x, lw);
-#pragma unroll
-        for (int r = 0; r < 10; ++r) {
-            const uint8_t* p = img + (int64_t)lk_refl(ipy - 1 + g7 + r, lh) * pitch;
-#pragma unroll
-            for (int x = 0; x < 5; ++x) R[r][x] = __ldg(p + cx[x]);
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint8_t* q = img + (int64_t)lk_refl(ipy - 1 + erow + r, lh) * pitch;
-#pragma unroll
-            for (int x = 0; x < 4; ++x) E[r][x] = __ldg(q + ce[x]);
-        }
-    }
-    // Scharr: t0(x) = 3 (s[y-1][x] + s[y+1][x]) + 10 s[y][x],  t1(x) = s[y+1][x] - s[y-1][x];  dx = t0(x+1) - t0(x-1),
-    // dy = 3 (t1(x-1) + t1(x+1)) + 10 t1(x)
-    int Gx[8][3], Gy[8][3];
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-        int t0[5], t1[5];
-#pragma unroll
-        for (int x = 0; x < 5; ++x) { t0[x] = (R[d][x] + R[d + 2][x]) * 3 + R[d + 1][x] * 10; t1[x] = R[d + 2][x] - R[d][x]; }
-#pragma unroll
-        for (int x = 0; x < 3; ++x) {
-            int gx = t0[x + 2] - t0[x], gy = (t1[x] + t1[x + 2]) * 3 + t1[x + 1] * 10;
-            if (!kInside) {
-                const bool in = (unsigned)(ipx + k2 + x) < (unsigned)lw && (unsigned)(ipy + g7 + d) < (unsigned)lh;
-                gx = in ? gx : 0; gy = in ? gy : 0;
+            for (int x = 0; x < 3; ++x) {
+                R[r][x] = __ldg(p + x);
+                const uint32_t d = __ldg(q + x);
+                Dx[r][x] = (int)(short)(d & 0xffffu); Dy[r][x] = (int)d >> 16;
             }
-            Gx[d][x] = gx; Gy[d][x] = gy;
+            p += pitch; q += pitch;
         }
     }
     int a11 = 0, a12 = 0, a22 = 0;
@@ -149,69 +172,42 @@ __device__ __forceinline__ void lk_setup_tiles(const uint8_t* __restrict__ img, 
     for (int r = 0; r < 7; ++r)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int ival = (R[r + 1][c + 1] * w00 + R[r + 1][c + 2] * w01 + R[r + 2][c + 1] * w10 + R[r + 2][c + 2] * w11 + 256) >> 9;
-            const int ixv = (Gx[r][c] * w00 + Gx[r][c + 1] * w01 + Gx[r + 1][c] * w10 + Gx[r + 1][c + 1] * w11 + 8192) >> 14;
-            const int iyv = (Gy[r][c] * w00 + Gy[r][c + 1] * w01 + Gy[r + 1][c] * w10 + Gy[r + 1][c + 1] * w11 + 8192) >> 14;
+            const int ival = (R[r][c] * w00 + R[r][c + 1] * w01 + R[r + 1][c] * w10 + R[r + 1][c + 1] * w11 + 256) >> 9;
+            const int ixv = (Dx[r][c] * w00 + Dx[r][c + 1] * w01 + Dx[r + 1][c] * w10 + Dx[r + 1][c + 1] * w11 + 8192) >> 14;
+            const int iyv = (Dy[r][c] * w00 + Dy[r][c + 1] * w01 + Dy[r + 1][c] * w10 + Dy[r + 1][c + 1] * w11 + 8192) >> 14;
             C[2 * r + c] = 256 - 512 * ival; GX[2 * r + c] = ixv; GY[2 * r + c] = iyv;
             a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv;
         }
     if (lane >= 30) a11 = a12 = a22 = 0;
     // the pixel of column 20
-    int ex[2][2], ey[2][2];
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-        int t0[4], t1[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) { t0[x] = (E[d][x] + E[d + 2][x]) * 3 + E[d + 1][x] * 10; t1[x] = E[d + 2][x] - E[d][x]; }
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-            int gx = t0[x + 2] - t0[x], gy = (t1[x] + t1[x + 2]) * 3 + t1[x + 1] * 10;
-            if (!kInside) {
-                const bool in = (unsigned)(ipx + 20 + x) < (unsigned)lw && (unsigned)(ipy + erow + d) < (unsigned)lh;
-                gx = in ? gx : 0; gy = in ? gy : 0;
-            }
-            ex[d][x] = gx; ey[d][x] = gy;
-        }
-    }
-    const int ival = (E[1][1] * w00 + E[1][2] * w01 + E[2][1] * w10 + E[2][2] * w11 + 256) >> 9;
-    const int ixv = (ex[0][0] * w00 + ex[0][1] * w01 + ex[1][0] * w10 + ex[1][1] * w11 + 8192) >> 14;
-    const int iyv = (ey[0][0] * w00 + ey[0][1] * w01 + ey[1][0] * w10 + ey[1][1] * w11 + 8192) >> 14;
+    const int64_t oe = (int64_t)(ipy + erow) * pitch + (ipx + 20);
+    const uint8_t* pe = img + oe; const uint32_t* qe = der + oe;
+    const int e00 = __ldg(pe), e01 = __ldg(pe + 1), e10 = __ldg(pe + pitch), e11 = __ldg(pe + pitch + 1);
+    const uint32_t d00 = __ldg(qe), d01 = __ldg(qe + 1), d10 = __ldg(qe + pitch), d11 = __ldg(qe + pitch + 1);
+    const int ival = (e00 * w00 + e01 * w01 + e10 * w10 + e11 * w11 + 256) >> 9;
+    const int ixv = ((int)(short)(d00 & 0xffffu) * w00 + (int)(short)(d01 & 0xffffu) * w01 + (int)(short)(d10 & 0xffffu) * w10 + (int)(short)(d11 & 0xffffu) * w11 + 8192) >> 14;
+    const int iyv = (((int)d00 >> 16) * w00 + ((int)d01 >> 16) * w01 + ((int)d10 >> 16) * w10 + ((int)d11 >> 16) * w11 + 8192) >> 14;
     Ce = 256 - 512 * ival; GXe = lane < kWin ? ixv : 0; GYe = lane < kWin ? iyv : 0;
     s11 = a11 + GXe * GXe; s12 = a12 + GXe * GYe; s22 = a22 + GYe * GYe;
 }
 
 // Mismatch vector of one iteration.  The 21x21 window is tiled over the warp: lane = 10 g + k (k < 10, g < 3) owns window columns
 // 2k, 2k+1 of rows 7g .. 7g+6 (14 pixels, held in registers: C = 256 - 512 Iw folds the descale rounding and the subtraction of the
-// template into the first multiply-add), and lanes 0..20 each own one pixel of the left-over column 20.  Lanes 30, 31 carry zero
-// gradients.  Every lane loads its own 8x3 (+2x2) bytes of J; the sums per lane are < 15 * 2^25: exact in int32.
-template <bool kInside>
-__device__ __forceinline__ void lk_mismatch_tiles(const uint8_t* __restrict__ img, int pitch, int lw, int lh, int inx, int iny,
-                                                  int k2, int g7, int erow, bool lane30, int w00, int w01, int w10, int w11,
-                                                  const int (&C)[14], const int (&GX)[14], const int (&GY)[14], int Ce, int GXe, int GYe,
-                                                  int& s1, int& s2) {
+// template into the first multiply-add), and lanes 0..20 each own one pixel of the left-over column 20.  Lanes 30, 31 repeat the
+// work of lane 29 and are masked out.  Every lane loads its own 8x3 (+2x2) bytes of J from the padded plane; the sums per lane are
+// < 15 * 2^25: exact in int32.
+__device__ __forceinline__ void lk_mismatch_tiles(const uint8_t* __restrict__ img, int pitch, int inx, int iny, int k2, int g7, int erow, bool lane30,
+                                                  int w00, int w01, int w10, int w11, const int (&C)[14], const int (&GX)[14], const int (&GY)[14],
+                                                  int Ce, int GXe, int GYe, int& s1, int& s2) {
     int v[8][3];
-    int e00, e01, e10, e11;
-    if (kInside) {
-        const uint8_t* p = img + (int64_t)(iny + g7) * pitch + (inx + k2);
+    const uint8_t* p = img + (int64_t)(iny + g7) * pitch + (inx + k2);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            v[r][0] = __ldg(p); v[r][1] = __ldg(p + 1); v[r][2] = __ldg(p + 2);
-            p += pitch;
-        }
-        const uint8_t* q = img + (int64_t)(iny + erow) * pitch + (inx + 20);
-        e00 = __ldg(q); e01 = __ldg(q + 1); e10 = __ldg(q + pitch); e11 = __ldg(q + pitch + 1);
-    } else {
-        const int x0 = lk_refl(inx + k2, lw), x1 = lk_refl(inx + k2 + 1, lw), x2 = lk_refl(inx + k2 + 2, lw);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const uint8_t* p = img + (int64_t)lk_refl(iny + g7 + r, lh) * pitch;
-            v[r][0] = __ldg(p + x0); v[r][1] = __ldg(p + x1); v[r][2] = __ldg(p + x2);
-        }
-        const int xe0 = lk_refl(inx + 20, lw), xe1 = lk_refl(inx + 21, lw);
-        const uint8_t* q0 = img + (int64_t)lk_refl(iny + erow, lh) * pitch;
-        const uint8_t* q1 = img + (int64_t)lk_refl(iny + erow + 1, lh) * pitch;
-        e00 = __ldg(q0 + xe0); e01 = __ldg(q0 + xe1); e10 = __ldg(q1 + xe0); e11 = __ldg(q1 + xe1);
+    for (int r = 0; r < 8; ++r) {
+        v[r][0] = __ldg(p); v[r][1] = __ldg(p + 1); v[r][2] = __ldg(p + 2);
+        p += pitch;
     }
+    const uint8_t* q = img + (int64_t)(iny + erow) * pitch + (inx + 20);
+    const int e00 = __ldg(q), e01 = __ldg(q + 1), e10 = __ldg(q + pitch), e11 = __ldg(q + pitch + 1);
     int a1 = 0, a2 = 0, b1 = 0, b2 = 0;
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
@@ -220,13 +216,13 @@ __device__ __forceinline__ void lk_mismatch_tiles(const uint8_t* __restrict__ im
         a1 += da * GX[2 * r]; a2 += da * GY[2 * r];
         b1 += db * GX[2 * r + 1]; b2 += db * GY[2 * r + 1];
     }
-    const int de = (e00 * w00 + e01 * w01 + e10 * w10 + e11 * w11 + Ce) >> 9;
     if (lane30) { a1 = 0; a2 = 0; b1 = 0; b2 = 0; }
+    const int de = (e00 * w00 + e01 * w01 + e10 * w10 + e11 * w11 + Ce) >> 9;
     s1 = a1 + b1 + de * GXe; s2 = a2 + b2 + de * GYe;
 }
 
 // points come either from keypoints (kps != nullptr: kp.x, kp.y) or from a plain float2 array
-// (128 registers per thread: forcing more resident blocks spills the register window and measured 15-30 % slower)
+// (111 registers: 4 blocks of 4 warps per SM; asking for 5 or 6 resident blocks measured equal / 10 % slower)
 __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_constant__ LkLevels L, const sgs_keypoint* __restrict__ kps,
                                                                  const float2* __restrict__ pts, const int32_t* __restrict__ counts, int cap,
                                                                  const int32_t* __restrict__ prev_index, float2* __restrict__ out) {
@@ -246,10 +242,10 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
     float nx = 0.f, ny = 0.f;
     for (int level = L.max_level; level >= 0; --level) {
         const int lw = L.w[level], lh = L.h[level];
+        const int pitch = L.pitch[level];
         const uint8_t* Iimg = L.I[level] + (int64_t)f * L.fstride[level];
-        const int ipitch = L.pitch[level];
-        const uint8_t* Jimg = L.J[level] + (int64_t)fj * (level == 0 ? L.fstrideJ0 : L.fstride[level]);
-        const int jpitch = level == 0 ? L.pitchJ0 : L.pitch[level];
+        const uint32_t* Dimg = L.D[level] + (int64_t)f * L.fstride[level];
+        const uint8_t* Jimg = L.J[level] + (int64_t)fj * L.fstride[level];
         const float sc = 1.f / (float)(1 << level);
         float px = __fmul_rn(ptx, sc), py = __fmul_rn(pty, sc);
         float qx, qy;
@@ -262,10 +258,7 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
         lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
         int s11, s12, s22;
         int C[14], GX[14], GY[14], Ce, GXe, GYe;
-        if (ipx >= 1 && ipx + 22 < lw && ipy >= 1 && ipy + 22 < lh)
-            lk_setup_tiles<true>(Iimg, ipitch, lw, lh, ipx, ipy, k2, g7, erow, lane, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s11, s12, s22);
-        else
-            lk_setup_tiles<false>(Iimg, ipitch, lw, lh, ipx, ipy, k2, g7, erow, lane, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s11, s12, s22);
+        lk_setup_tiles(Iimg, Dimg, pitch, ipx, ipy, k2, g7, erow, lane, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s11, s12, s22);
         const float A11 = __fmul_rn((float)warp_sum_grad(s11), flt_scale), A12 = __fmul_rn((float)warp_sum_grad(s12), flt_scale),
                     A22 = __fmul_rn((float)warp_sum_grad(s22), flt_scale);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
@@ -281,10 +274,7 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
             if (inx < -kWin || inx >= lw || iny < -kWin || iny >= lh) break;
             lk_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
             int s1, s2;
-            if (inx >= 0 && inx + 21 < lw && iny >= 0 && iny + 21 < lh)
-                lk_mismatch_tiles<true>(Jimg, jpitch, lw, lh, inx, iny, k2, g7, erow, lane >= 30, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s1, s2);
-            else
-                lk_mismatch_tiles<false>(Jimg, jpitch, lw, lh, inx, iny, k2, g7, erow, lane >= 30, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s1, s2);
+            lk_mismatch_tiles(Jimg, pitch, inx, iny, k2, g7, erow, lane >= 30, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s1, s2);
             float B1, B2;
             warp_sum_pair(s1, s2, lane, flt_scale, B1, B2);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, B2), __fmul_rn(A22, B1)), D);
@@ -308,10 +298,12 @@ using namespace sgs;
 
 struct sgs_lk {
     int device = 0, w = 0, h = 0, max_batch = 0, max_level = 0;
-    int lw[kLkMaxLevel + 1], lh[kLkMaxLevel + 1], lp[kLkMaxLevel + 1];
-    int64_t lfs[kLkMaxLevel + 1];
-    uint8_t* d_pyrI = nullptr; uint8_t* d_pyrJ = nullptr;     // levels 1..max_level, each [max_batch][h][pitch]
-    int64_t loff[kLkMaxLevel + 1];
+    int lw[kLkMaxLevel + 1], lh[kLkMaxLevel + 1], lp[kLkMaxLevel + 1];      // level sizes; lp = padded pitch in pixels
+    int64_t lfs[kLkMaxLevel + 1], loff[kLkMaxLevel + 1];                    // pixels per padded frame; offset of the level inside a pyramid buffer
+    int64_t lorg[kLkMaxLevel + 1];                                          // offset of pixel (0, 0) inside a padded frame
+    int64_t pyr_elems = 0;
+    uint8_t* d_pyrI = nullptr; uint8_t* d_pyrJ = nullptr;     // padded levels 0..max_level, each [max_batch][h + 2 pad][pitch]
+    uint32_t* d_der = nullptr;                                // derivative planes of I, same geometry (borders stay zero)
     // staging for the single-pair host API
     uint8_t* d_img = nullptr; float* d_pts = nullptr; float* d_out = nullptr; int pts_cap = 0;
     cudaStream_t st = nullptr;
@@ -322,13 +314,43 @@ struct sgs_lk {
 namespace {
 int lk_bad(const char* m) { set_error("%s", m); return SGS_ERR_INVALID; }
 
-void build_pyramid(sgs_lk* k, const uint8_t* d_l0, int pitch0, int64_t fstride0, uint8_t* d_pyr, int nframes, cudaStream_t st) {
-    const uint8_t* src = d_l0; int sp = pitch0; int64_t sfs = fstride0;
-    for (int l = 1; l <= k->max_level; ++l) {
-        uint8_t* dst = d_pyr + k->loff[l];
-        dim3 grid((k->lw[l] + 31) / 32, (k->lh[l] + 7) / 8, nframes);
-        lk_pyrdown_kernel<<<grid, 256, 0, st>>>(src, k->lw[l - 1], k->lh[l - 1], sp, sfs, dst, k->lw[l], k->lh[l], k->lp[l], k->lfs[l]);
-        src = dst; sp = k->lp[l]; sfs = k->lfs[l];
+// padded pyramid (+ derivative planes when d_der != nullptr) of `nframes` images
+void build_pyramid(sgs_lk* k, const uint8_t* d_l0, int pitch0, int64_t fstride0, uint8_t* d_pyr, uint32_t* d_der, int nframes, cudaStream_t st) {
+    for (int l = 0; l <= k->max_level; ++l) {
+        uint8_t* dst = d_pyr + k->loff[l] + k->lorg[l];
+        const int w = k->lw[l], h = k->lh[l];
+        if (l > 0) {
+            const uint8_t* src = d_pyr + k->loff[l - 1] + k->lorg[l - 1];
+            dim3 grid((w + 31) / 32, (h + 7) / 8, nframes);
+            lk_pyrdown_kernel<<<grid, 256, 0, st>>>(src, k->lw[l - 1], k->lh[l - 1], k->lp[l - 1], k->lfs[l - 1], dst, w, h, k->lp[l], k->lfs[l]);
+        }
+        const uint8_t* src = l == 0 ? d_l0 : dst;
+        const int sp = l == 0 ? pitch0 : k->lp[l];
+        const int64_t sfs = l == 0 ? fstride0 : k->lfs[l];
+        if (d_der) {
+            uint32_t* der = d_der + k->loff[l] + k->lorg[l];
+            const bool vec = (w & 3) == 0 && w >= 8 && (((uintptr_t)src | (uintptr_t)sp | (uintptr_t)sfs) & 3) == 0;
+            if (vec) {
+                dim3 grid((w / 4 + 31) / 32, (h + 7) / 8, nframes);
+                lk_interior_kernel<true><<<grid, 256, 0, st>>>(src, sp, sfs, dst, l == 0, der, w, h, k->lp[l], k->lfs[l]);
+            } else {
+                dim3 grid((w + 31) / 32, (h + 7) / 8, nframes);
+                lk_interior_kernel<false><<<grid, 256, 0, st>>>(src, sp, sfs, dst, l == 0, der, w, h, k->lp[l], k->lfs[l]);
+            }
+        } else if (l == 0) {
+            cudaMemcpy3DParms c = {};
+            c.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(d_l0), (size_t)pitch0, (size_t)w, (size_t)(fstride0 / pitch0));
+            c.dstPtr = make_cudaPitchedPtr(dst - k->lorg[0], (size_t)k->lp[0], (size_t)k->lp[0], (size_t)(h + 2 * kLkPad));
+            c.dstPos = make_cudaPos(kLkPad, kLkPad, 0);
+            c.extent = make_cudaExtent((size_t)w, (size_t)h, (size_t)nframes);
+            c.kind = cudaMemcpyDeviceToDevice;
+            if (fstride0 % pitch0 == 0) cudaMemcpy3DAsync(&c, st);
+            else for (int f = 0; f < nframes; ++f)
+                cudaMemcpy2DAsync(dst + (int64_t)f * k->lfs[0], (size_t)k->lp[0], d_l0 + (int64_t)f * fstride0, (size_t)pitch0, (size_t)w, (size_t)h, cudaMemcpyDeviceToDevice, st);
+        }
+        const int nborder = 2 * kLkPad * (w + 2 * kLkPad) + 2 * kLkPad * h;
+        dim3 gb((nborder + 255) / 256, 1, nframes);
+        lk_border_kernel<<<gb, 256, 0, st>>>(dst, w, h, k->lp[l], k->lfs[l]);
     }
 }
 
@@ -343,18 +365,18 @@ int run_lk(sgs_lk* k, const uint8_t* d_cur, const uint8_t* d_prev, const int32_t
         k->pending = false;
     }
     if (prof) cudaEventRecord(k->ev[0], st);
-    build_pyramid(k, d_cur, pitch, (int64_t)frame_stride, k->d_pyrI, nframes, st);
+    build_pyramid(k, d_cur, pitch, (int64_t)frame_stride, k->d_pyrI, k->d_der, nframes, st);
     const bool same_batch = d_prev_index != nullptr;     // previous images are other frames of the same batch: one pyramid serves both roles
-    if (!same_batch) build_pyramid(k, d_prev, pitch, (int64_t)frame_stride, k->d_pyrJ, nframes, st);
+    if (!same_batch) build_pyramid(k, d_prev, pitch, (int64_t)frame_stride, k->d_pyrJ, nullptr, nframes, st);
     LkLevels L;
     L.max_level = k->max_level;
-    for (int l = 0; l <= k->max_level; ++l) {
-        L.w[l] = k->lw[l]; L.h[l] = k->lh[l];
-        if (l == 0) { L.I[0] = d_cur; L.J[0] = same_batch ? d_cur : d_prev; L.pitch[0] = pitch; L.fstride[0] = (int64_t)frame_stride; }
-        else { L.I[l] = k->d_pyrI + k->loff[l]; L.J[l] = (same_batch ? k->d_pyrI : k->d_pyrJ) + k->loff[l]; L.pitch[l] = k->lp[l]; L.fstride[l] = k->lfs[l]; }
+    for (int l = 0; l <= kLkMaxLevel; ++l) {
+        if (l <= k->max_level) {
+            const int64_t o = k->loff[l] + k->lorg[l];
+            L.w[l] = k->lw[l]; L.h[l] = k->lh[l]; L.pitch[l] = k->lp[l]; L.fstride[l] = k->lfs[l];
+            L.I[l] = k->d_pyrI + o; L.J[l] = (same_batch ? k->d_pyrI : k->d_pyrJ) + o; L.D[l] = k->d_der + o;
+        } else { L.I[l] = L.J[l] = nullptr; L.D[l] = nullptr; L.w[l] = L.h[l] = L.pitch[l] = 0; L.fstride[l] = 0; }
     }
-    for (int l = k->max_level + 1; l <= kLkMaxLevel; ++l) { L.I[l] = L.J[l] = nullptr; L.w[l] = L.h[l] = L.pitch[l] = 0; L.fstride[l] = 0; }
-    L.pitchJ0 = pitch; L.fstrideJ0 = (int64_t)frame_stride;
     if (prof) cudaEventRecord(k->ev[1], st);
     dim3 grid((cap + kLkWarps - 1) / kLkWarps, nframes);
     lk_track_kernel<<<grid, kLkWarps * 32, 0, st>>>(L, d_kps, reinterpret_cast<const float2*>(d_pts), d_counts, cap, d_prev_index, reinterpret_cast<float2*>(d_out));
@@ -388,7 +410,7 @@ SGS_API void sgs_lk_destroy(sgs_lk* k) {
     if (!k) return;
     cudaSetDevice(k->device);
     for (auto& e : k->ev) if (e) cudaEventDestroy(e);
-    cudaFree(k->d_pyrI); cudaFree(k->d_pyrJ); cudaFree(k->d_img); cudaFree(k->d_pts); cudaFree(k->d_out);
+    cudaFree(k->d_pyrI); cudaFree(k->d_pyrJ); cudaFree(k->d_der); cudaFree(k->d_img); cudaFree(k->d_pts); cudaFree(k->d_out);
     if (k->st) cudaStreamDestroy(k->st);
     delete k;
 }
@@ -399,19 +421,27 @@ SGS_API int sgs_lk_create(int width, int height, int max_batch, int device, sgs_
     SGS_CUDA_TRY(cudaSetDevice(device));
     sgs_lk* k = new sgs_lk();
     k->device = device; k->w = width; k->h = height; k->max_batch = max_batch;
-    k->lw[0] = width; k->lh[0] = height; k->lp[0] = 0; k->lfs[0] = 0; k->loff[0] = 0;
     int64_t off = 0;
     k->max_level = 0;
-    for (int l = 1; l <= kLkMaxLevel; ++l) {     // buildOpticalFlowPyramid stops when a level would not be larger than the window
-        const int nw = (k->lw[l - 1] + 1) / 2, nh = (k->lh[l - 1] + 1) / 2;
-        if (nw <= kWin || nh <= kWin) break;
-        k->lw[l] = nw; k->lh[l] = nh; k->lp[l] = (nw + 15) & ~15; k->lfs[l] = (int64_t)k->lp[l] * nh; k->loff[l] = off;
+    for (int l = 0; l <= kLkMaxLevel; ++l) {     // buildOpticalFlowPyramid stops when a level would not be larger than the window
+        if (l == 0) { k->lw[0] = width; k->lh[0] = height; }
+        else {
+            const int nw = (k->lw[l - 1] + 1) / 2, nh = (k->lh[l - 1] + 1) / 2;
+            if (nw <= kWin || nh <= kWin) break;
+            k->lw[l] = nw; k->lh[l] = nh; k->max_level = l;
+        }
+        k->lp[l] = (k->lw[l] + 2 * kLkPad + 15) & ~15;
+        k->lfs[l] = (int64_t)k->lp[l] * (k->lh[l] + 2 * kLkPad);
+        k->lorg[l] = (int64_t)kLkPad * k->lp[l] + kLkPad;
+        k->loff[l] = off;
         off += k->lfs[l] * max_batch;
-        k->max_level = l;
     }
+    k->pyr_elems = off;
     cudaError_t e = cudaStreamCreateWithFlags(&k->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&k->d_pyrI, (size_t)off + 256);
     if (e == cudaSuccess) e = cudaMalloc(&k->d_pyrJ, (size_t)off + 256);
+    if (e == cudaSuccess) e = cudaMalloc(&k->d_der, 4 * (size_t)off + 256);
+    if (e == cudaSuccess) e = cudaMemset(k->d_der, 0, 4 * (size_t)off + 256);        // the borders of the derivative planes are never written again
     if (e != cudaSuccess) { set_error("sgs_lk_create: %s", cudaGetErrorString(e)); sgs_lk_destroy(k); return SGS_ERR_CUDA; }
     *out = k;
     return SGS_OK;
@@ -451,7 +481,8 @@ SGS_API int sgs_lk_read_level(sgs_lk* k, int which, int level, uint8_t* out, int
     if (!k || !out || level < 1 || level > k->max_level) return lk_bad("sgs_lk_read_level: bad argument");
     SGS_CUDA_TRY(cudaSetDevice(k->device));
     SGS_CUDA_TRY(cudaStreamSynchronize(k->st));
-    SGS_CUDA_TRY(cudaMemcpy2D(out, out_pitch, (which ? k->d_pyrJ : k->d_pyrI) + k->loff[level], k->lp[level], k->lw[level], k->lh[level], cudaMemcpyDeviceToHost));
+    SGS_CUDA_TRY(cudaMemcpy2D(out, out_pitch, (which ? k->d_pyrJ : k->d_pyrI) + k->loff[level] + k->lorg[level], k->lp[level], k->lw[level], k->lh[level],
+                              cudaMemcpyDeviceToHost));
     return SGS_OK;
 }
 
