@@ -55,8 +55,6 @@ __global__ void __launch_bounds__(256) lk_pyrdown_kernel(const uint8_t* __restri
     dst[(int64_t)blockIdx.z * dfstride + (int64_t)y * dpitch + x] = (uint8_t)((v + 128) >> 8);
 }
 
-// Exact warp sums of per-lane int32 partials.  |partial| < 15 * 8160 * 4080 < 2^28.9, so the first stages stay in int32 (4 lanes for
-// the mismatch sums, 8 lanes for the gradient sums whose terms are < 4080^2) before widening.
 // Interior of a padded level: optional copy from an unpadded source (level 0; src == dst interior when cv::pyrDown already wrote it)
 // and the Scharr derivatives (calcScharrDeriv: REFLECT_101 at the image edge) stored as dx | dy << 16.
 //   t0(x) = 3 (s[y-1][x] + s[y+1][x]) + 10 s[y][x],  t1(x) = s[y+1][x] - s[y-1][x];  dx = t0(x+1) - t0(x-1),  dy = 3 (t1(x-1) + t1(x+1)) + 10 t1(x)
@@ -116,22 +114,11 @@ __global__ void __launch_bounds__(256) lk_border_kernel(uint8_t* dst, int w, int
     F[(int64_t)Y * pitch + X] = F[(int64_t)lk_refl(Y, h) * pitch + lk_refl(X, w)];
 }
 
-__device__ __forceinline__ long long warp_sum_grad(int v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 16); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
-    long long w = v;
-    w += __shfl_xor_sync(0xffffffffu, w, 2); w += __shfl_xor_sync(0xffffffffu, w, 1);
-    return w;
-}
-// two sums at once: after the first exchange lanes 0..15 carry s1 and lanes 16..31 carry s2; every lane gets both totals as float
-__device__ __forceinline__ void warp_sum_pair(int s1, int s2, int lane, float scale, float& B1, float& B2) {
-    const bool hi = lane >= 16;
-    const int give = hi ? s1 : s2, keep = hi ? s2 : s1;
-    int v = keep + __shfl_xor_sync(0xffffffffu, give, 16);
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    long long w = v;
-    w += __shfl_xor_sync(0xffffffffu, w, 4); w += __shfl_xor_sync(0xffffffffu, w, 2); w += __shfl_xor_sync(0xffffffffu, w, 1);
-    const float mine = __fmul_rn((float)w, scale), other = __shfl_xor_sync(0xffffffffu, mine, 16);
-    B1 = hi ? other : mine; B2 = hi ? mine : other;
+// Exact warp sum of per-lane int32 partials with the hardware reduction (redux.sync): |partial| < 2^29, so the low 16 bits and the
+// (signed) high part are reduced separately in int32 without overflow and recombined in int64.  Every lane gets the total.
+__device__ __forceinline__ long long warp_sum_exact(int v) {
+    const int lo = __reduce_add_sync(0xffffffffu, v & 0xffff), hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    return (long long)hi * 65536 + lo;
 }
 
 __device__ __forceinline__ int lk_descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
@@ -194,12 +181,9 @@ __device__ __forceinline__ void lk_setup_tiles(const uint8_t* __restrict__ img, 
 // Mismatch vector of one iteration.  The 21x21 window is tiled over the warp: lane = 10 g + k (k < 10, g < 3) owns window columns
 // 2k, 2k+1 of rows 7g .. 7g+6 (14 pixels, held in registers: C = 256 - 512 Iw folds the descale rounding and the subtraction of the
 // template into the first multiply-add), and lanes 0..20 each own one pixel of the left-over column 20.  Lanes 30, 31 repeat the
-// work of lane 29 and are masked out.  Every lane loads its own 8x3 (+2x2) bytes of J from the padded plane; the sums per lane are
-// < 15 * 2^25: exact in int32.
-__device__ __forceinline__ void lk_mismatch_tiles(const uint8_t* __restrict__ img, int pitch, int inx, int iny, int k2, int g7, int erow, bool lane30,
-                                                  int w00, int w01, int w10, int w11, const int (&C)[14], const int (&GX)[14], const int (&GY)[14],
-                                                  int Ce, int GXe, int GYe, int& s1, int& s2) {
-    int v[8][3];
+// work of lane 29 and are masked out.  Every lane loads its own 8x3 (+2x2) bytes of J from the padded plane and keeps them while the
+// iterations stay on the same integer position (the usual case: steps are sub-pixel); the sums per lane are < 15 * 2^25: exact in int32.
+__device__ __forceinline__ void lk_load_j_tile(const uint8_t* __restrict__ img, int pitch, int inx, int iny, int k2, int g7, int erow, int (&v)[8][3], int (&e)[4]) {
     const uint8_t* p = img + (int64_t)(iny + g7) * pitch + (inx + k2);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -207,7 +191,11 @@ __device__ __forceinline__ void lk_mismatch_tiles(const uint8_t* __restrict__ im
         p += pitch;
     }
     const uint8_t* q = img + (int64_t)(iny + erow) * pitch + (inx + 20);
-    const int e00 = __ldg(q), e01 = __ldg(q + 1), e10 = __ldg(q + pitch), e11 = __ldg(q + pitch + 1);
+    e[0] = __ldg(q); e[1] = __ldg(q + 1); e[2] = __ldg(q + pitch); e[3] = __ldg(q + pitch + 1);
+}
+
+__device__ __forceinline__ void lk_mismatch_tiles(const int (&v)[8][3], const int (&e)[4], bool lane30, int w00, int w01, int w10, int w11,
+                                                  const int (&C)[14], const int (&GX)[14], const int (&GY)[14], int Ce, int GXe, int GYe, int& s1, int& s2) {
     int a1 = 0, a2 = 0, b1 = 0, b2 = 0;
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
@@ -217,7 +205,7 @@ __device__ __forceinline__ void lk_mismatch_tiles(const uint8_t* __restrict__ im
         b1 += db * GX[2 * r + 1]; b2 += db * GY[2 * r + 1];
     }
     if (lane30) { a1 = 0; a2 = 0; b1 = 0; b2 = 0; }
-    const int de = (e00 * w00 + e01 * w01 + e10 * w10 + e11 * w11 + Ce) >> 9;
+    const int de = (e[0] * w00 + e[1] * w01 + e[2] * w10 + e[3] * w11 + Ce) >> 9;
     s1 = a1 + b1 + de * GXe; s2 = a2 + b2 + de * GYe;
 }
 
@@ -259,8 +247,8 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
         int s11, s12, s22;
         int C[14], GX[14], GY[14], Ce, GXe, GYe;
         lk_setup_tiles(Iimg, Dimg, pitch, ipx, ipy, k2, g7, erow, lane, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s11, s12, s22);
-        const float A11 = __fmul_rn((float)warp_sum_grad(s11), flt_scale), A12 = __fmul_rn((float)warp_sum_grad(s12), flt_scale),
-                    A22 = __fmul_rn((float)warp_sum_grad(s22), flt_scale);
+        const float A11 = __fmul_rn((float)warp_sum_exact(s11), flt_scale), A12 = __fmul_rn((float)warp_sum_exact(s12), flt_scale),
+                    A22 = __fmul_rn((float)warp_sum_exact(s22), flt_scale);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dd = __fsub_rn(A11, A22);
         const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
@@ -269,14 +257,15 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
         D = __fdiv_rn(1.f, D);
         qx = __fsub_rn(qx, half_win); qy = __fsub_rn(qy, half_win);
         float pdx = 0.f, pdy = 0.f;
+        int jv[8][3], je[4], tile_x = 0x7fffffff, tile_y = 0x7fffffff;
         for (int j = 0; j < kLkMaxCount; ++j) {
             const int inx = (int)floorf(qx), iny = (int)floorf(qy);
             if (inx < -kWin || inx >= lw || iny < -kWin || iny >= lh) break;
             lk_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
+            if (inx != tile_x || iny != tile_y) { lk_load_j_tile(Jimg, pitch, inx, iny, k2, g7, erow, jv, je); tile_x = inx; tile_y = iny; }
             int s1, s2;
-            lk_mismatch_tiles(Jimg, pitch, inx, iny, k2, g7, erow, lane >= 30, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s1, s2);
-            float B1, B2;
-            warp_sum_pair(s1, s2, lane, flt_scale, B1, B2);
+            lk_mismatch_tiles(jv, je, lane >= 30, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s1, s2);
+            const float B1 = __fmul_rn((float)warp_sum_exact(s1), flt_scale), B2 = __fmul_rn((float)warp_sum_exact(s2), flt_scale);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, B2), __fmul_rn(A22, B1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, B1), __fmul_rn(A11, B2)), D);
             qx = __fadd_rn(qx, dx); qy = __fadd_rn(qy, dy);
