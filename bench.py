@@ -379,6 +379,8 @@ def main():
     F_dev = B.memcpy_d2h(np.zeros((NB, 9), np.float64), pF.value); F_info = B.memcpy_d2h(np.zeros((NB, 4), np.int32), pI.value)
 
     # ---- e2e leg: host buffers through the C ABI, copies inside the timed region ----------------------------------------
+    # (a) one tracker handle, synchronous calls back to back; (b) the same work split over two handles driven by two host threads,
+    # so that the copies of one half overlap the kernels of the other (what a multi-camera server does).  (b) is the headline e2e.
     e2e = None
     if not args.no_e2e:
         for _ in range(2):
@@ -388,11 +390,57 @@ def main():
         for _ in range(args.steps):
             step_host()
         torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
+        dt1 = max_over_ranks(time.perf_counter() - t0)
         h2d = h_frames.numel() + sum(hp[k].numel() * hp[k].element_size() for k in keys_h) + hp['T'].numel() * 4
         d2h = (h_kps.numel() + h_n.numel() * 4) + sum(t.numel() * t.element_size() for t in h_out.values())
+        dt, mode = dt1, 'one tracker handle, synchronous calls'
+        if NB % (2 * unique) == 0 and NB >= 128:
+            HB = NB // 2
+            halves = []
+            for hx in range(2):
+                tk = B.Tracker(W, H, cam, NFEAT, 1.2, 8, 20, 7, max_batch=HB, point_cap=NFEAT + 64, max_boxes=4, device=local)
+                sl = slice(hx * HB, (hx + 1) * HB)
+                hpi = {k: hp[k][sl] for k in keys_h}
+                hpi['pidx'] = torch.from_numpy(np.ascontiguousarray(pidx[sl] - hx * HB)).pin_memory()
+                halves.append((tk, sl, hpi))
+
+            def half_step(hx):
+                tk, sl, hpi = halves[hx]
+                tk.extract(h_frames[sl].data_ptr(), HB, W * H, W, h_kps[sl].data_ptr(), 0, h_n[sl].data_ptr())
+                B.check(L.sgs_tracker_track_lk(tk.h, HB, v(hpi['pidx'].data_ptr()), *[v(p) for p in track_ptrs(hpi)], C.c_float(TH), 0, 1,
+                                               v(h_out['kps'][sl].data_ptr()), v(h_out['desc'][sl].data_ptr()), v(h_out['ur'][sl].data_ptr()),
+                                               v(h_out['cnt'][sl].data_ptr()), v(h_out['mp'][sl].data_ptr()), v(h_out['nm'][sl].data_ptr())))
+
+            def worker(hx, nsteps, gate):
+                torch.cuda.set_device(local)
+                gate.wait()
+                for _ in range(nsteps):
+                    half_step(hx)
+
+            def run_pair(nsteps):
+                gate = threading.Barrier(3)
+                th = [threading.Thread(target=worker, args=(hx, nsteps, gate)) for hx in range(2)]
+                for t in th:
+                    t.start()
+                barrier()
+                gate.wait()
+                t0 = time.perf_counter()
+                for t in th:
+                    t.join()
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0
+            ref_cnt = h_out['cnt'].numpy().copy(); ref_nm = h_out['nm'].numpy().copy()
+            run_pair(2)
+            same = bool(np.array_equal(ref_cnt, h_out['cnt'].numpy()) and np.array_equal(ref_nm, h_out['nm'].numpy()))
+            dt2 = max_over_ranks(run_pair(args.steps))
+            if not same:
+                log('[bench] WARNING: two-handle e2e results differ from the single-handle ones')
+            elif dt2 < dt1:
+                dt, mode = dt2, 'two tracker handles (%d frames each per call) driven by two host threads' % HB
+            for tk, _, _ in halves:
+                tk.close()
         e2e = {'value': world * NB * args.steps / dt, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'ms_per_step': 1e3 * dt / args.steps,
+               'ms_per_step': 1e3 * dt / args.steps, 'mode': mode, 'single_handle_value': world * NB * args.steps / dt1,
                'note': 'sgs_tracker_extract (host frames -> host keypoints) + sgs_tracker_track_lk (LK + RANSAC F + dyn-reject + match on the resident batch) with pinned host buffers'}
 
     # ---- roofline of the dominant kernel of the step (all timed live with CUDA events on the launching stream) -----------------
