@@ -36,23 +36,37 @@ __device__ __forceinline__ int lk_refl(int i, int n) {
     return i;
 }
 
-// cv::pyrDown, CV_8U: separable [1 4 6 4 1], exact integer sums, (v + 128) >> 8, BORDER_REFLECT_101
-__global__ void __launch_bounds__(256) lk_pyrdown_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, int64_t sfstride,
+// cv::pyrDown, CV_8U: separable [1 4 6 4 1], exact integer sums, (v + 128) >> 8, BORDER_REFLECT_101.  The source is a padded level
+// whose border is already filled, so the 5x5 taps need no border logic.  Four outputs per thread: source columns 8 tx - 4 .. 8 tx + 11
+// arrive as four aligned words per row (pixel (0, 0) of a padded plane is 8-byte aligned, rows are 16-byte multiples).
+__global__ void __launch_bounds__(256) lk_pyrdown_kernel(const uint8_t* __restrict__ src, int spitch, int64_t sfstride,
                                                          uint8_t* __restrict__ dst, int dw, int dh, int dpitch, int64_t dfstride) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= dw || y >= dh) return;
-    const uint8_t* S = src + (int64_t)blockIdx.z * sfstride;
-    int cx[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) cx[k] = lk_refl(2 * x - 2 + k, sw);
-    int v = 0;
+    const int tx = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int x0 = 4 * tx;
+    if (x0 >= dw || y >= dh) return;
+    const uint8_t* S = src + (int64_t)blockIdx.z * sfstride + (int64_t)(2 * y - 2) * spitch + (2 * x0 - 4);
+    int acc[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
-        const uint8_t* row = S + (int64_t)lk_refl(2 * y - 2 + r, sh) * spitch;
-        const int hsum = __ldg(row + cx[2]) * 6 + (__ldg(row + cx[1]) + __ldg(row + cx[3])) * 4 + __ldg(row + cx[0]) + __ldg(row + cx[4]);
-        v += hsum * (r == 2 ? 6 : (r == 1 || r == 3) ? 4 : 1);
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(S + (int64_t)r * spitch);       // 4-byte aligned (8 tx - 4 past an 8-aligned origin)
+        const uint4 q = make_uint4(__ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3));
+        int b[11];          // source columns 2 x0 - 2 .. 2 x0 + 8
+        b[0] = (q.x >> 16) & 255; b[1] = q.x >> 24;
+        b[2] = q.y & 255; b[3] = (q.y >> 8) & 255; b[4] = (q.y >> 16) & 255; b[5] = q.y >> 24;
+        b[6] = q.z & 255; b[7] = (q.z >> 8) & 255; b[8] = (q.z >> 16) & 255; b[9] = q.z >> 24;
+        b[10] = q.w & 255;
+        const int wr = r == 2 ? 6 : (r == 1 || r == 3) ? 4 : 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += (b[2 * i + 2] * 6 + (b[2 * i + 1] + b[2 * i + 3]) * 4 + b[2 * i] + b[2 * i + 4]) * wr;
     }
-    dst[(int64_t)blockIdx.z * dfstride + (int64_t)y * dpitch + x] = (uint8_t)((v + 128) >> 8);
+    uint8_t* D = dst + (int64_t)blockIdx.z * dfstride + (int64_t)y * dpitch + x0;
+    if (x0 + 3 < dw) {
+        *reinterpret_cast<uint32_t*>(D) = (uint32_t)((acc[0] + 128) >> 8) | ((uint32_t)((acc[1] + 128) >> 8) << 8) | ((uint32_t)((acc[2] + 128) >> 8) << 16) |
+                                          ((uint32_t)((acc[3] + 128) >> 8) << 24);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (x0 + i < dw) D[i] = (uint8_t)((acc[i] + 128) >> 8);
+    }
 }
 
 // Interior of a padded level: optional copy from an unpadded source (level 0; src == dst interior when cv::pyrDown already wrote it)
@@ -310,8 +324,8 @@ void build_pyramid(sgs_lk* k, const uint8_t* d_l0, int pitch0, int64_t fstride0,
         const int w = k->lw[l], h = k->lh[l];
         if (l > 0) {
             const uint8_t* src = d_pyr + k->loff[l - 1] + k->lorg[l - 1];
-            dim3 grid((w + 31) / 32, (h + 7) / 8, nframes);
-            lk_pyrdown_kernel<<<grid, 256, 0, st>>>(src, k->lw[l - 1], k->lh[l - 1], k->lp[l - 1], k->lfs[l - 1], dst, w, h, k->lp[l], k->lfs[l]);
+            dim3 grid(((w + 3) / 4 + 31) / 32, (h + 7) / 8, nframes);
+            lk_pyrdown_kernel<<<grid, 256, 0, st>>>(src, k->lp[l - 1], k->lfs[l - 1], dst, w, h, k->lp[l], k->lfs[l]);
         }
         const uint8_t* src = l == 0 ? d_l0 : dst;
         const int sp = l == 0 ? pitch0 : k->lp[l];
