@@ -40,7 +40,7 @@ ALG_BYTES_LK_PYR = 408_000 * 6 + 403_200   # one padded pyramid + derivative pla
                                            # per level pixel 1 B read + 1 B write + 4 B derivative, + cv::pyrDown reading L0..L2
 ALG_BYTES_LK = ALG_BYTES_LK_PYR + 1000 * 4 * 2 * 529   # + N points x 4 levels x 2 images x 23^2 window bytes (~4.2 MB + pyramid)
 TH = 15.0                              # Tracking.cc:919-923 (RGB-D)
-LAUNCHES_PER_STEP = 18 + 12 + 1 + 2 + 1    # extract (7 resize, FAST, quadtree, 8 blur, describe) + LK (3 pyrDown, 4 Scharr, 4 border, track) + RANSAC F + dyn-reject/compact + match
+LAUNCHES_PER_STEP = 18 + 12 + 1 + 3 + 1    # extract (7 resize, FAST, quadtree, 8 blur, describe) + LK (3 pyrDown, 4 Scharr, 4 border, track) + RANSAC F + depth lookup/dyn-reject/compact + match
 
 
 def log(*a):
@@ -308,12 +308,18 @@ def main():
     def dev_lk():
         B.check(L.sgs_tracker_lk_device(trk.h, v(d_frames.data_ptr()), NB, C.c_size_t(W * H), W, v(d_pidx.data_ptr()), v(st.cuda_stream)))
 
+    d_depth = torch.from_numpy(synth.depth_s1(W, H).astype(np.float32)).cuda()      # one synthetic depth plane shared by every frame
+
+    def dev_stereo():   # Frame::ComputeStereoFromRGBD on the device (u_right of the unfiltered keypoints)
+        B.check(L.sgs_tracker_stereo_device(trk.h, NB, v(d_depth.data_ptr()), C.c_size_t(0), W, v(st.cuda_stream)))
+
     def dev_fm():
         B.check(L.sgs_tracker_fundamental_device(trk.h, NB, v(dv['boxes'].data_ptr()), v(dv['nb'].data_ptr()), v(dv['have'].data_ptr()),
                                                  v(d_pidx.data_ptr()), v(st.cuda_stream)))
 
     def dev_track():
-        B.check(L.sgs_tracker_track_device(trk.h, NB, v(0), *[v(p) for p in track_ptrs(dv)], C.c_float(TH), 0, 1, v(st.cuda_stream)))
+        ptrs = track_ptrs(dv); ptrs[0] = 0          # u_right == NULL: the one computed by dev_stereo
+        B.check(L.sgs_tracker_track_device(trk.h, NB, v(0), *[v(p) for p in ptrs], C.c_float(TH), 0, 1, v(st.cuda_stream)))
 
     def step_host():
         # call 1: frames -> keypoints (descriptors stay on the device); call 2: LK + RANSAC F + dyn-reject + match on the resident batch
@@ -338,7 +344,7 @@ def main():
     # ---- device-resident leg (value) ----------------------------------------------------------------------------------
     with torch.cuda.stream(st):
         for _ in range(warm):
-            dev_extract(); dev_lk(); dev_fm(); dev_track()
+            dev_extract(); dev_lk(); dev_fm(); dev_stereo(); dev_track()
     barrier()
     B.check(L.sgs_extractor_set_profiling(exh, 1))
     L.sgs_tracker_lk.restype = C.c_void_p
@@ -353,7 +359,7 @@ def main():
             dev_extract(); ev[4 * i + 1].record(st)
             dev_lk(); ev[4 * i + 2].record(st)
             dev_fm(); ev[4 * i + 3].record(st)
-            dev_track(); ev[4 * i + 4].record(st)
+            dev_stereo(); dev_track(); ev[4 * i + 4].record(st)
     barrier()
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[4 * args.steps]))
     extract_ms = sum(ev[4 * i].elapsed_time(ev[4 * i + 1]) for i in range(args.steps)) / args.steps
@@ -455,9 +461,9 @@ def main():
     # algorithmic bytes per frame: extractor stages as listed there; LK tracker = N points x 4 levels x 2 images x 23^2 B
     alg = {'pyramid(7 launches)': 1_569_878, 'fast_warp_cells_kernel': ALG_BYTES_FAST_READ + 4 * ncand_frame0, 'quadtree_kernel': 8 * ncand_frame0 + 4 * nk,
            'blur(8 launches)': 1_901_064, 'describe_kernel': (749 + 544 + 60) * nk, 'lk_pyramid+deriv(11 launches)': ALG_BYTES_LK_PYR,
-           'lk_track_kernel': nk * 4 * 2 * 529, 'fm_ransac_kernel': 16 * nk + 72, 'dynreject+compact+match(3 launches)': 76 * nk + 56 * nk + 44 * 8 * nk}
+           'lk_track_kernel': nk * 4 * 2 * 529, 'fm_ransac_kernel': 16 * nk + 72, 'stereo+dynreject+compact+match(4 launches)': 76 * nk + 56 * nk + 44 * 8 * nk}
     all_ms = dict(zip(names, stage_ms))
-    all_ms.update({'lk_pyramid+deriv(11 launches)': lk_pyr_ms, 'lk_track_kernel': lk_track_ms, 'fm_ransac_kernel': fm_ms, 'dynreject+compact+match(3 launches)': track_ms})
+    all_ms.update({'lk_pyramid+deriv(11 launches)': lk_pyr_ms, 'lk_track_kernel': lk_track_ms, 'fm_ransac_kernel': fm_ms, 'stereo+dynreject+compact+match(4 launches)': track_ms})
     dom = max(('fast_warp_cells_kernel', 'quadtree_kernel', 'describe_kernel', 'lk_track_kernel', 'fm_ransac_kernel'), key=lambda k: all_ms[k])   # single-launch kernels
     dom_bytes = alg[dom] * NB
     achieved = dom_bytes / (all_ms[dom] * 1e-3) / 1e9

@@ -219,6 +219,32 @@ typedef struct sgs_localmap_batch {       /* SearchByProjection(Frame&, vector<M
 SGS_API int sgs_match_project_localmap_batch_device(sgs_matcher* m, const sgs_localmap_batch* args, int nframes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Frame geometry between the extractor and the matchers (device pointers, `nframes` frames, work enqueued on `stream`):
+ *   sgs_stereo_from_depth_batch_device : Frame::ComputeStereoFromRGBD (src/Frame.cc:893-914).  d_depth: float depth images
+ *       [F][h][depth_pitch] (elements; depth_frame_stride 0 shares one image); d_kps_un NULL = undistorted keypoints equal the
+ *       distorted ones; outputs d_u_right [F][cap] (mvuRight, -1 without depth) and optional d_depth_out (mvDepth).
+ *   sgs_frustum_batch_device           : Frame::isInFrustum (src/Frame.cc:296-352) + MapPoint::PredictScale (src/MapPoint.cc:400-418)
+ *       for every local-map point: fills the per-point inputs of sgs_match_project_localmap* (mbTrackInView, mTrackProjX/Y/XR,
+ *       mnTrackScaleLevel, mTrackViewCos).  mp_min_dist / mp_max_dist are mfMinDistance / mfMaxDistance (the 0.8 / 1.2 factors
+ *       of Get{Min,Max}DistanceInvariance are applied inside); log(scaleFactor) is taken from cam.scale_factors[1].
+ * ------------------------------------------------------------------------------------ */
+typedef struct sgs_frustum_batch {
+    sgs_camera cam;
+    const float* tcw;             /* [F][16] row-major */
+    const float* mp_xyz;          /* [F][point_cap][3]  GetWorldPos() */
+    const float* mp_normal;       /* [F][point_cap][3]  GetNormal() */
+    const float* mp_min_dist; const float* mp_max_dist;   /* [F][point_cap] */
+    const int32_t* mp_n;          /* [F] */
+    int32_t point_cap;
+    float viewing_cos_limit;      /* 0.5 at src/Tracking.cc:1282 */
+    uint8_t* mp_inview; float* proj_x; float* proj_y; float* proj_xr; int32_t* level; float* view_cos;   /* out [F][point_cap] */
+} sgs_frustum_batch;
+SGS_API int sgs_stereo_from_depth_batch_device(const sgs_keypoint* d_kps, const sgs_keypoint* d_kps_un, const int32_t* d_counts, int cap,
+                                               int nframes, const float* d_depth, size_t depth_frame_stride, int depth_pitch, float bf,
+                                               float* d_u_right, float* d_depth_out, void* stream);
+SGS_API int sgs_frustum_batch_device(const sgs_frustum_batch* args, int nframes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Frame: dynamic-feature rejection, geometry half
  * Frame::RmDynamicPointWithSemanticAndGeometry "version3" loop (src/Frame.cc:560-604) +
  * CheckEpiLineDistToRmDynamicPoint (:613-627) + isInDynamicRegion (:629-652).
@@ -323,6 +349,10 @@ SGS_API int sgs_tracker_prev_xy_device(const sgs_tracker* t, const float** d_pre
 SGS_API int sgs_tracker_fundamental_device(sgs_tracker* t, int nframes, const sgs_rect* d_boxes, const int32_t* d_nboxes,
                                            const uint8_t* d_have_dyn, const int32_t* d_prev_index, void* stream);
 SGS_API int sgs_tracker_fundamental_device_ptr(const sgs_tracker* t, const double** d_F, const int32_t** d_info);
+/* Frame::ComputeStereoFromRGBD for the frames of the last extract call (see sgs_stereo_from_depth_batch_device); the result is the
+ * u_right used by the next sgs_tracker_track_device call made with u_right == NULL. */
+SGS_API int sgs_tracker_stereo_device(sgs_tracker* t, int nframes, const float* d_depth, size_t depth_frame_stride, int depth_pitch,
+                                      void* stream);
 /* Host-buffer variant of sgs_tracker_track with the LK stage on the GPU: prev_index [F] (host) replaces prev_xy; the frames are
  * the ones uploaded by the preceding sgs_tracker_extract call (they are still resident on the device). */
 SGS_API int sgs_tracker_track_lk(sgs_tracker* t, int nframes, const int32_t* prev_index, const float* u_right, const double* F,

@@ -298,3 +298,26 @@ def select_static_pairs(cur, prev, boxes, prev_have_dyn):
     lib().sgo_select_static_pairs.restype = C.c_int
     n = lib().sgo_select_static_pairs(_p(a), _p(b), len(a), _p(bx), len(bx), int(bool(prev_have_dyn)), _p(s1), _p(s2))
     return s1[:n], s2[:n]
+
+
+def stereo_from_rgbd(kps, depth, bf, kps_un=None):
+    """Frame::ComputeStereoFromRGBD (src/Frame.cc:893-914): (u_right, depth) per keypoint."""
+    k = np.ascontiguousarray(kps); d = np.ascontiguousarray(depth, np.float32)
+    ur = np.zeros(len(k), np.float32); dz = np.zeros(len(k), np.float32)
+    ku = None if kps_un is None else np.ascontiguousarray(kps_un)
+    lib().sgo_stereo_from_rgbd(_p(k), _p(ku) if ku is not None else None, len(k), _p(d), d.strides[0] // 4, C.c_float(bf), _p(ur), _p(dz))
+    return ur, dz
+
+
+def is_in_frustum(Tcw, cam, nlevels, log_scale_factor, xyz, normal, min_dist, max_dist, viewing_cos_limit=0.5):
+    """Frame::isInFrustum for n map points.  cam = (fx, fy, cx, cy, bf, minX, minY, maxX, maxY).
+    Returns dict(inview, proj_x, proj_y, proj_xr, level, view_cos)."""
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16); cm = np.ascontiguousarray(cam, np.float32)
+    X = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3); N = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    mn = np.ascontiguousarray(min_dist, np.float32); mx = np.ascontiguousarray(max_dist, np.float32)
+    n = len(X)
+    out = dict(inview=np.zeros(n, np.uint8), proj_x=np.zeros(n, np.float32), proj_y=np.zeros(n, np.float32), proj_xr=np.zeros(n, np.float32),
+               level=np.zeros(n, np.int32), view_cos=np.zeros(n, np.float32))
+    lib().sgo_is_in_frustum(_p(T), _p(cm), int(nlevels), C.c_float(log_scale_factor), C.c_float(viewing_cos_limit), n, _p(X), _p(N), _p(mn), _p(mx),
+                            _p(out['inview']), _p(out['proj_x']), _p(out['proj_y']), _p(out['proj_xr']), _p(out['level']), _p(out['view_cos']))
+    return out

@@ -885,13 +885,13 @@ SGO_API int sgo_search_by_projection_last(const SgoFrame* cur, const float* Tcw_
     for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) { Rcw[3 * r + c] = Tcw_cur[4 * r + c]; Rlw[3 * r + c] = Tcw_last[4 * r + c]; }
         tcw[r] = Tcw_cur[4 * r + 3]; tlw[r] = Tcw_last[4 * r + 3]; }
     float twc[3], tlc[3];
-    for (int r = 0; r < 3; r++) {  // cv::Mat gemm for float accumulates in double then casts (matmul.cpp GEMMSingleMul)
+    for (int r = 0; r < 3; r++) {  // -Rcw.t()*tcw: transposed gemm takes the general path, double accumulator then one cast (GEMMSingleMul)
         double acc = 0; for (int k = 0; k < 3; k++) acc += (double)(-Rcw[3 * k + r]) * (double)tcw[k];
         twc[r] = (float)acc;
     }
-    for (int r = 0; r < 3; r++) {
-        double acc = 0; for (int k = 0; k < 3; k++) acc += (double)Rlw[3 * r + k] * (double)twc[k];
-        tlc[r] = (float)(acc + (double)tlw[r]);  // MatExpr A*B+C == gemm(A,B,1,C,1): one rounding
+    for (int r = 0; r < 3; r++) {   // MatExpr A*B+C == gemm(A,B,1,C,1) with flags == 0: OpenCV's small-matrix path sums float products in float,
+        const float acc = Rlw[3 * r] * twc[0] + Rlw[3 * r + 1] * twc[1] + Rlw[3 * r + 2] * twc[2];          // left to right (pinned against cv2.gemm)
+        tlc[r] = (float)((double)acc + (double)tlw[r]);
     }
     const bool bForward = tlc[2] > F.b && !bMono;
     const bool bBackward = -tlc[2] > F.b && !bMono;
@@ -903,9 +903,9 @@ SGO_API int sgo_search_by_projection_last(const SgoFrame* cur, const float* Tcw_
         if (!last_has_mp[i]) continue;
         const float* Xw = last_xyz + 3 * i;
         float x3Dc[3];
-        for (int r = 0; r < 3; r++) {
-            double acc = 0; for (int k = 0; k < 3; k++) acc += (double)Rcw[3 * r + k] * (double)Xw[k];
-            x3Dc[r] = (float)(acc + (double)tcw[r]);  // gemm(Rcw, x3Dw, 1, tcw, 1), double accumulator
+        for (int r = 0; r < 3; r++) {   // gemm(Rcw, x3Dw, 1, tcw, 1): small-matrix path, float accumulation
+            const float acc = Rcw[3 * r] * Xw[0] + Rcw[3 * r + 1] * Xw[1] + Rcw[3 * r + 2] * Xw[2];
+            x3Dc[r] = (float)((double)acc + (double)tcw[r]);
         }
         const float xc = x3Dc[0], yc = x3Dc[1];
         const float invzc = (float)(1.0 / x3Dc[2]);  // :1369 (double division, stored to float)

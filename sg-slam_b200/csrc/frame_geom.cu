@@ -1,0 +1,105 @@
+// frame_geom.cu -- two per-point pieces of the Frame class that sit between the extractor and the matchers:
+//   Frame::ComputeStereoFromRGBD (src/Frame.cc:893-914): depth lookup at the (distorted) keypoint, uRight = xUn - bf / d;
+//   Frame::isInFrustum (src/Frame.cc:296-352) + MapPoint::PredictScale (src/MapPoint.cc:400-418): the projection that fills
+//   mbTrackInView / mTrackProjX / mTrackProjY / mTrackProjXR / mnTrackScaleLevel / mTrackViewCos for
+//   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129).
+// cv::Mat float arithmetic is reproduced as OpenCV evaluates it (pinned against cv2): a plain 3x3 * 3x1 gemm sums float products in
+// float, transposed gemm / cv::norm / Mat::dot accumulate in double and round once; scalar float expressions are individually rounded (-fmad=false).  The only non-bit-exact piece is logf in PredictScale
+// (device log vs glibc logf): the predicted level can differ when log(ratio)/log(scaleFactor) falls within an ulp of an integer.
+#include <cuda_runtime.h>
+
+#include "sgs_common.h"
+
+namespace sgs {
+
+__global__ void __launch_bounds__(256) stereo_from_depth_kernel(const sgs_keypoint* __restrict__ kps, const sgs_keypoint* __restrict__ kps_un,
+                                                                const int32_t* __restrict__ counts, int cap, const float* __restrict__ depth,
+                                                                int64_t depth_fstride, int depth_pitch, float bf, float* __restrict__ u_right,
+                                                                float* __restrict__ depth_out) {
+    const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= cap) return;
+    const int64_t o = (int64_t)f * cap + i;
+    float ur = -1.f, dz = -1.f;
+    if (i < min(counts[f], cap)) {
+        const sgs_keypoint k = kps[o];
+        const float d = __ldg(depth + (int64_t)f * depth_fstride + (int64_t)(int)k.y * depth_pitch + (int)k.x);
+        if (d > 0) { dz = d; ur = __fsub_rn(kps_un ? kps_un[o].x : k.x, __fdiv_rn(bf, d)); }
+    }
+    u_right[o] = ur;
+    if (depth_out) depth_out[o] = dz;
+}
+
+__global__ void __launch_bounds__(256) frustum_kernel(const sgs_frustum_batch A, int nlevels, float log_sf) {
+    const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    const int n = min(A.mp_n[f], A.point_cap);
+    if (i >= A.point_cap) return;
+    const int64_t o = (int64_t)f * A.point_cap + i;
+    uint8_t in = 0; float pu = 0.f, pv = 0.f, pxr = 0.f, vcos = 0.f; int lvl = 0;
+    if (i < n) {
+        const float* T = A.tcw + (int64_t)f * 16;
+        const float R0 = T[0], R1 = T[1], R2 = T[2], R3 = T[4], R4 = T[5], R5 = T[6], R6 = T[8], R7 = T[9], R8 = T[10], t0 = T[3], t1 = T[7], t2 = T[11];
+        // mOw = -Rcw^T tcw: transposed gemm = general path, double accumulator, one rounding
+        const float Ox = (float)(((double)(-R0) * t0 + (double)(-R3) * t1) + (double)(-R6) * t2);
+        const float Oy = (float)(((double)(-R1) * t0 + (double)(-R4) * t1) + (double)(-R7) * t2);
+        const float Oz = (float)(((double)(-R2) * t0 + (double)(-R5) * t1) + (double)(-R8) * t2);
+        const float X = A.mp_xyz[3 * o], Y = A.mp_xyz[3 * o + 1], Z = A.mp_xyz[3 * o + 2];
+        // mRcw * P + mtcw: OpenCV's small-matrix gemm path (float products summed in float, then (float)((double)sum + (double)c))
+        const float PcX = (float)((double)__fadd_rn(__fadd_rn(__fmul_rn(R0, X), __fmul_rn(R1, Y)), __fmul_rn(R2, Z)) + (double)t0);
+        const float PcY = (float)((double)__fadd_rn(__fadd_rn(__fmul_rn(R3, X), __fmul_rn(R4, Y)), __fmul_rn(R5, Z)) + (double)t1);
+        const float PcZ = (float)((double)__fadd_rn(__fadd_rn(__fmul_rn(R6, X), __fmul_rn(R7, Y)), __fmul_rn(R8, Z)) + (double)t2);
+        bool ok = !(PcZ < 0.0f);
+        const float invz = __fdiv_rn(1.0f, PcZ);
+        const float u = __fadd_rn(__fmul_rn(__fmul_rn(A.cam.fx, PcX), invz), A.cam.cx), v = __fadd_rn(__fmul_rn(__fmul_rn(A.cam.fy, PcY), invz), A.cam.cy);
+        ok = ok && !(u < A.cam.min_x || u > A.cam.max_x) && !(v < A.cam.min_y || v > A.cam.max_y);
+        const float maxD = __fmul_rn(1.2f, A.mp_max_dist[o]), minD = __fmul_rn(0.8f, A.mp_min_dist[o]);
+        const float Px = __fsub_rn(X, Ox), Py = __fsub_rn(Y, Oy), Pz = __fsub_rn(Z, Oz);
+        const float dist = (float)sqrt(((double)Px * Px + (double)Py * Py) + (double)Pz * Pz);
+        ok = ok && !(dist < minD || dist > maxD);
+        const float nx = A.mp_normal[3 * o], ny = A.mp_normal[3 * o + 1], nz = A.mp_normal[3 * o + 2];
+        const float vc = (float)((((double)Px * nx + (double)Py * ny) + (double)Pz * nz) / (double)dist);
+        ok = ok && !(vc < A.viewing_cos_limit);
+        if (ok) {
+            const float ratio = __fdiv_rn(A.mp_max_dist[o], dist);
+            int ns = (int)ceilf(__fdiv_rn((float)log((double)ratio), log_sf));
+            ns = ns < 0 ? 0 : (ns >= nlevels ? nlevels - 1 : ns);
+            in = 1; pu = u; pv = v; pxr = __fsub_rn(u, __fmul_rn(A.cam.bf, invz)); lvl = ns; vcos = vc;
+        }
+    }
+    A.mp_inview[o] = in; A.proj_x[o] = pu; A.proj_y[o] = pv; A.proj_xr[o] = pxr; A.level[o] = lvl; A.view_cos[o] = vcos;
+}
+
+}  // namespace sgs
+
+using namespace sgs;
+
+extern "C" {
+
+SGS_API int sgs_stereo_from_depth_batch_device(const sgs_keypoint* d_kps, const sgs_keypoint* d_kps_un, const int32_t* d_counts, int cap, int nframes,
+                                               const float* d_depth, size_t depth_frame_stride, int depth_pitch, float bf, float* d_u_right,
+                                               float* d_depth_out, void* stream) {
+    if (!d_kps || !d_counts || !d_depth || !d_u_right || cap < 1 || nframes < 1 || depth_pitch < 1) {
+        set_error("sgs_stereo_from_depth_batch_device: bad argument"); return SGS_ERR_INVALID;
+    }
+    dim3 grid((cap + 255) / 256, nframes);
+    stereo_from_depth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_kps, d_kps_un, d_counts, cap, d_depth, (int64_t)depth_frame_stride, depth_pitch, bf,
+                                                                     d_u_right, d_depth_out);
+    SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+
+SGS_API int sgs_frustum_batch_device(const sgs_frustum_batch* a, int nframes, void* stream) {
+    if (!a || !a->tcw || !a->mp_xyz || !a->mp_normal || !a->mp_min_dist || !a->mp_max_dist || !a->mp_n || !a->mp_inview || !a->proj_x || !a->proj_y ||
+        !a->proj_xr || !a->level || !a->view_cos || a->point_cap < 1 || nframes < 1) {
+        set_error("sgs_frustum_batch_device: bad argument"); return SGS_ERR_INVALID;
+    }
+    if (a->cam.nlevels < 1 || a->cam.nlevels > 16 || !(a->cam.scale_factors[1] > 1.f) && a->cam.nlevels > 1) {
+        set_error("sgs_frustum_batch_device: camera scale table missing"); return SGS_ERR_INVALID;
+    }
+    const float log_sf = logf(a->cam.nlevels > 1 ? a->cam.scale_factors[1] : 1.2f);      // mfLogScaleFactor = log(mfScaleFactor), src/Frame.cc:139
+    dim3 grid((a->point_cap + 255) / 256, nframes);
+    frustum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a, a->cam.nlevels, log_sf);
+    SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+
+}  // extern "C"

@@ -362,7 +362,9 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
     if (threadIdx.x < kHistoLen) hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         s_nmatch = 0; s_nevent = 0;
-        // Rcw, tcw, twc = -Rcw^T tcw, tlc = Rlw twc + tlw : cv::Mat float gemm = double accumulation, one rounding (:1342-1351)
+        // Rcw, tcw, twc = -Rcw^T tcw, tlc = Rlw twc + tlw (:1342-1351).  cv::gemm on CV_32F: the transposed product takes the general path
+        // (double accumulator, one rounding); a plain 3x3 * 3x1 (+ C) takes OpenCV's small-matrix path: float products summed in float,
+        // left to right, then (float)((double)sum + (double)c).  Pinned against cv2.gemm (tests/golden/make_golden_frustum.py).
         const float* Tc = A.tcw_cur + 16 * f; const float* Tl = A.tcw_last + 16 * f;
         float twc[3];
         for (int r = 0; r < 3; ++r) {
@@ -370,9 +372,8 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
             for (int k = 0; k < 3; ++k) acc = __dadd_rn(acc, __dmul_rn((double)(-Tc[4 * k + r]), (double)Tc[4 * k + 3]));
             twc[r] = (float)acc;
         }
-        double acc = 0.0;
-        for (int k = 0; k < 3; ++k) acc = __dadd_rn(acc, __dmul_rn((double)Tl[8 + k], (double)twc[k]));
-        const float tlc2 = (float)__dadd_rn(acc, (double)Tl[11]);
+        const float acc = __fadd_rn(__fadd_rn(__fmul_rn(Tl[8], twc[0]), __fmul_rn(Tl[9], twc[1])), __fmul_rn(Tl[10], twc[2]));
+        const float tlc2 = (float)__dadd_rn((double)acc, (double)Tl[11]);
         const float mb = __fdiv_rn(A.cam.bf, A.cam.fx);       // Frame.cc:196
         for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) s_pose[3 * r + c] = Tc[4 * r + c]; s_pose[9 + r] = Tc[4 * r + 3]; }
         s_pose[12] = (tlc2 > mb && !A.mono) ? 1.f : 0.f;
@@ -399,10 +400,9 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
             const float* X = A.last_xyz + 3 * (lo + i);
             float xc[3];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                double acc = 0.0;
-                for (int k = 0; k < 3; ++k) acc = __dadd_rn(acc, __dmul_rn((double)s_pose[3 * r + k], (double)X[k]));
-                xc[r] = (float)__dadd_rn(acc, (double)s_pose[9 + r]);
+            for (int r = 0; r < 3; ++r) {      // Rcw * x3Dw + tcw: small-matrix gemm path (float accumulation)
+                const float acc = __fadd_rn(__fadd_rn(__fmul_rn(s_pose[3 * r], X[0]), __fmul_rn(s_pose[3 * r + 1], X[1])), __fmul_rn(s_pose[3 * r + 2], X[2]));
+                xc[r] = (float)__dadd_rn((double)acc, (double)s_pose[9 + r]);
             }
             const float invz = (float)__ddiv_rn(1.0, (double)xc[2]);                       // :1369
             if (!(invz < 0.f)) {

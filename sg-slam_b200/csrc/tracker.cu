@@ -148,8 +148,9 @@ SGS_API int sgs_tracker_track_device(sgs_tracker* t, int nframes, const float* p
                                      const int32_t* nboxes, const uint8_t* have_dyn, const float* last_xyz, const uint8_t* last_desc,
                                      const uint8_t* last_flags, const int32_t* last_octave, const float* last_angle, const int32_t* last_n,
                                      const float* tcw_cur, const float* tcw_last, float th, int mono, int check_orientation, void* stream) {
-    if (!t || !u_right || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle ||
+    if (!t || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle ||
         !last_n || !tcw_cur || !tcw_last) return bad("sgs_tracker_track_device: NULL argument");
+    if (!u_right) u_right = t->d_uright_in;      // filled by sgs_tracker_stereo_device
     if (!F) F = t->d_Fgpu;                  // filled by sgs_tracker_fundamental_device
     if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_track_device: nframes exceeds the last extract call");
     if (!prev_xy) prev_xy = t->d_prev;      // filled by sgs_tracker_lk_device
@@ -239,6 +240,15 @@ SGS_API int sgs_tracker_fundamental_device(sgs_tracker* t, int nframes, const sg
     // parameters of the reference call: FM_RANSAC, 1.0, 0.99 (src/Frame.cc:470,472); OpenCV's default of 1000 iterations
     return sgs_fundamental_batch_device(d_kps, t->d_prev, d_cnt, cap, nframes, d_boxes ? d_boxes : t->d_boxes, d_nboxes, d_have_dyn, t->max_boxes,
                                         d_prev_index, 1.0, 0.99, 1000, t->d_Fgpu, t->d_finfo, stream ? stream : (void*)t->st);
+}
+
+SGS_API int sgs_tracker_stereo_device(sgs_tracker* t, int nframes, const float* d_depth, size_t depth_frame_stride, int depth_pitch, void* stream) {
+    if (!t || !d_depth) return bad("sgs_tracker_stereo_device: NULL argument");
+    if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_stereo_device: nframes exceeds the last extract call");
+    const sgs_keypoint* d_kps; const uint8_t* d_desc; const int32_t* d_cnt; int cap = 0;
+    sgs_extractor_results_device(t->ex, &d_kps, &d_desc, &d_cnt, &cap);
+    return sgs_stereo_from_depth_batch_device(d_kps, nullptr, d_cnt, cap, nframes, d_depth, depth_frame_stride, depth_pitch, t->cam.bf, t->d_uright_in, nullptr,
+                                              stream ? stream : (void*)t->st);
 }
 
 SGS_API int sgs_tracker_fundamental_device_ptr(const sgs_tracker* t, const double** d_F, const int32_t** d_info) {

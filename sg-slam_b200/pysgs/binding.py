@@ -52,6 +52,12 @@ class LastFrameBatch(C.Structure):
                 ('cur_mp', C.c_void_p), ('cur_mp_obs_in', C.c_void_p), ('nmatches', C.c_void_p), ('ncand', C.c_void_p)]
 
 
+class FrustumBatch(C.Structure):
+    _fields_ = [('cam', Camera), ('tcw', C.c_void_p), ('mp_xyz', C.c_void_p), ('mp_normal', C.c_void_p), ('mp_min_dist', C.c_void_p), ('mp_max_dist', C.c_void_p),
+                ('mp_n', C.c_void_p), ('point_cap', C.c_int32), ('viewing_cos_limit', C.c_float), ('mp_inview', C.c_void_p), ('proj_x', C.c_void_p),
+                ('proj_y', C.c_void_p), ('proj_xr', C.c_void_p), ('level', C.c_void_p), ('view_cos', C.c_void_p)]
+
+
 class LocalMapBatch(C.Structure):
     _fields_ = [('cam', Camera),
                 ('cur_kps', C.c_void_p), ('cur_desc', C.c_void_p), ('cur_uright', C.c_void_p), ('cur_n', C.c_void_p),
@@ -76,6 +82,7 @@ ABI_SYMBOLS = [
     'sgs_lk_create', 'sgs_lk_destroy', 'sgs_lk_track', 'sgs_lk_track_batch_device', 'sgs_lk_read_level',
     'sgs_tracker_lk_device', 'sgs_tracker_prev_xy_device', 'sgs_tracker_track_lk', 'sgs_extractor_level0_device', 'sgs_memcpy_d2h',
     'sgs_lk_set_profiling', 'sgs_lk_stage_times', 'sgs_tracker_lk',
+    'sgs_stereo_from_depth_batch_device', 'sgs_frustum_batch_device', 'sgs_tracker_stereo_device',
     'sgs_fundamental_ransac', 'sgs_fundamental_batch_device', 'sgs_tracker_fundamental_device', 'sgs_tracker_fundamental_device_ptr',
 ]
 

@@ -1,0 +1,108 @@
+"""GPU parity of Frame::isInFrustum (+ MapPoint::PredictScale) and Frame::ComputeStereoFromRGBD through the C ABI against the golden
+vectors made with the real cv2 primitives and against the CPU oracle.  Floats bit-identical; the predicted level may differ only where
+log(ratio)/log(scaleFactor) is within 1e-5 of an integer (device log vs glibc logf)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle as O  # noqa: E402
+import scenarios as S  # noqa: E402
+from pysgs import binding as B  # noqa: E402
+from pysgs import synth  # noqa: E402
+
+
+def _frustum_gpu(Tcw, cam9, xyz, normal, mind, maxd, counts, point_cap, limit=0.5):
+    import torch
+    F = len(counts)
+    sf = S.scale_factors()
+    cam = B.make_camera(640, 480, dict(fx=cam9[0], fy=cam9[1], cx=cam9[2], cy=cam9[3], bf=cam9[4]), sf)
+    cam.min_x, cam.min_y, cam.max_x, cam.max_y = [float(x) for x in cam9[5:9]]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d = dict(tcw=dev(Tcw.astype(np.float32)), xyz=dev(xyz), nrm=dev(normal), mn=dev(mind), mx=dev(maxd), n=dev(np.asarray(counts, np.int32)))
+    o = dict(inview=torch.zeros((F, point_cap), dtype=torch.uint8, device='cuda'), proj_x=torch.zeros((F, point_cap), device='cuda'),
+             proj_y=torch.zeros((F, point_cap), device='cuda'), proj_xr=torch.zeros((F, point_cap), device='cuda'),
+             level=torch.zeros((F, point_cap), dtype=torch.int32, device='cuda'), view_cos=torch.zeros((F, point_cap), device='cuda'))
+    a = B.FrustumBatch()
+    a.cam = cam
+    a.tcw, a.mp_xyz, a.mp_normal, a.mp_min_dist, a.mp_max_dist, a.mp_n = [t.data_ptr() for t in (d['tcw'], d['xyz'], d['nrm'], d['mn'], d['mx'], d['n'])]
+    a.point_cap = point_cap; a.viewing_cos_limit = limit
+    a.mp_inview, a.proj_x, a.proj_y, a.proj_xr, a.level, a.view_cos = [o[k].data_ptr() for k in ('inview', 'proj_x', 'proj_y', 'proj_xr', 'level', 'view_cos')]
+    B.check(B.lib().sgs_frustum_batch_device(C.byref(a), F, C.c_void_p(0)))
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in o.items()}
+
+
+def _same(out, ref, level_arg=None):
+    assert np.array_equal(out['inview'], ref['inview'])
+    for k in ('proj_x', 'proj_y', 'proj_xr', 'view_cos'):
+        assert out[k].tobytes() == ref[k].tobytes(), k
+    diff = np.nonzero(out['level'] != ref['level'])[0]
+    assert len(diff) <= max(2, len(out['level']) // 100000)
+    if level_arg is not None and len(diff):
+        assert np.all(np.abs(level_arg[diff] - np.round(level_arg[diff])) < 1e-5)
+
+
+def test_frustum_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'frustum.npz'))
+    n = len(g['xyz'])
+    out = _frustum_gpu(g['Tcw'].reshape(1, 16), g['cam'], g['xyz'].reshape(1, n, 3), g['normal'].reshape(1, n, 3), g['min_dist'].reshape(1, n),
+                       g['max_dist'].reshape(1, n), [n], n)
+    _same({k: v[0] for k, v in out.items()}, g, g['level_arg'])
+
+
+def test_frustum_batch_against_oracle():
+    rs = np.random.RandomState(5)
+    F, cap = 5, 3000
+    counts = [3000, 1, 2999, 0, 1234]
+    cam9 = np.array([535.4, 539.2, 320.1, 247.6, 40.0, 0, 0, 640, 480], np.float32)
+    Tcw = np.zeros((F, 16), np.float32); xyz = np.zeros((F, cap, 3), np.float32); nrm = np.zeros((F, cap, 3), np.float32)
+    mn = np.zeros((F, cap), np.float32); mx = np.zeros((F, cap), np.float32)
+    for f in range(F):
+        a = rs.uniform(-0.4, 0.4); T = np.eye(4, dtype=np.float32)
+        T[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32); T[:3, 3] = rs.uniform(-0.5, 0.5, 3)
+        Tcw[f] = T.reshape(16)
+        z = rs.uniform(-1, 8, cap); pc = np.c_[rs.uniform(-0.8, 0.8, cap) * z, rs.uniform(-0.6, 0.6, cap) * z, z]
+        xyz[f] = ((pc - T[:3, 3].astype(np.float64)) @ T[:3, :3].astype(np.float64)).astype(np.float32)
+        cen = -T[:3, :3].T.astype(np.float64) @ T[:3, 3].astype(np.float64)
+        tc = xyz[f].astype(np.float64) - cen; d0 = np.linalg.norm(tc, axis=1)
+        nn = tc / d0[:, None] + rs.normal(0, 0.5, (cap, 3)); nrm[f] = (nn / np.linalg.norm(nn, axis=1, keepdims=True)).astype(np.float32)
+        mx[f] = (d0 * rs.uniform(0.5, 5, cap)).astype(np.float32); mn[f] = (mx[f] / 1.2 ** rs.randint(2, 9, cap)).astype(np.float32)
+    out = _frustum_gpu(Tcw, cam9, xyz, nrm, mn, mx, counts, cap)
+    logsf = float(np.float32(np.log(np.float32(1.2))))
+    for f in range(F):
+        n = counts[f]
+        ref = O.is_in_frustum(Tcw[f], cam9, 8, logsf, xyz[f, :n], nrm[f, :n], mn[f, :n], mx[f, :n], 0.5)
+        _same({k: v[f, :n] for k, v in out.items()}, ref)
+        assert not out['inview'][f, n:].any()          # rows past the count are cleared
+
+
+def test_stereo_from_depth():
+    import torch
+    rs = np.random.RandomState(4)
+    F, cap = 3, 1100
+    depth = (0.5 + rs.uniform(0, 4, (F, 480, 640))).astype(np.float32); depth[rs.uniform(size=depth.shape) < 0.15] = 0
+    kps = np.zeros((F, cap), B.KP_DTYPE); counts = np.array([1100, 700, 0], np.int32)
+    kps['x'] = rs.uniform(0, 639.99, (F, cap)); kps['y'] = rs.uniform(0, 479.99, (F, cap))
+    dk = torch.from_numpy(kps.view(np.uint8).reshape(-1)).cuda(); dd = torch.from_numpy(depth).cuda(); dc = torch.from_numpy(counts).cuda()
+    ur = torch.zeros((F, cap), device='cuda'); dz = torch.zeros((F, cap), device='cuda')
+    v = C.c_void_p
+    B.check(B.lib().sgs_stereo_from_depth_batch_device(v(dk.data_ptr()), v(0), v(dc.data_ptr()), cap, F, v(dd.data_ptr()), C.c_size_t(640 * 480), 640,
+                                                       C.c_float(40.0), v(ur.data_ptr()), v(dz.data_ptr()), v(0)))
+    torch.cuda.synchronize()
+    ur = ur.cpu().numpy(); dz = dz.cpu().numpy()
+    for f in range(F):
+        n = counts[f]
+        ru, rd = O.stereo_from_rgbd(kps[f, :n], depth[f], 40.0)
+        assert ur[f, :n].tobytes() == ru.tobytes() and dz[f, :n].tobytes() == rd.tobytes()
+        assert np.all(ur[f, n:] == -1)
+    # one shared depth image (frame stride 0): every frame looks up frame 0's depth
+    ur2 = torch.zeros((F, cap), device='cuda')
+    B.check(B.lib().sgs_stereo_from_depth_batch_device(v(dk.data_ptr()), v(0), v(dc.data_ptr()), cap, F, v(dd.data_ptr()), C.c_size_t(0), 640,
+                                                       C.c_float(40.0), v(ur2.data_ptr()), v(0), v(0)))
+    torch.cuda.synchronize()
+    ru, _ = O.stereo_from_rgbd(kps[1, :counts[1]], depth[0], 40.0)
+    assert ur2.cpu().numpy()[1, :counts[1]].tobytes() == ru.tobytes()
