@@ -243,6 +243,10 @@ SGS_API int sgs_stereo_from_depth_batch_device(const sgs_keypoint* d_kps, const 
                                                int nframes, const float* d_depth, size_t depth_frame_stride, int depth_pitch, float bf,
                                                float* d_u_right, float* d_depth_out, void* stream);
 SGS_API int sgs_frustum_batch_device(const sgs_frustum_batch* args, int nframes, void* stream);
+/* host-pointer variant, one frame, n points (arrays of n / 3 n elements) */
+SGS_API int sgs_frustum(const sgs_camera* cam, const float* tcw, int n, const float* xyz, const float* normal, const float* min_dist,
+                        const float* max_dist, float viewing_cos_limit, uint8_t* inview, float* proj_x, float* proj_y, float* proj_xr,
+                        int32_t* level, float* view_cos, int device);
 
 /* ------------------------------------------------------------------------------------
  * Frame: dynamic-feature rejection, geometry half

@@ -102,4 +102,40 @@ SGS_API int sgs_frustum_batch_device(const sgs_frustum_batch* a, int nframes, vo
     return SGS_OK;
 }
 
+// host-pointer variant for one frame (the reference calls isInFrustum per local-map point in Tracking::SearchLocalPoints, src/Tracking.cc:1262-1290)
+SGS_API int sgs_frustum(const sgs_camera* cam, const float* tcw, int n, const float* xyz, const float* normal, const float* min_dist, const float* max_dist,
+                        float viewing_cos_limit, uint8_t* inview, float* proj_x, float* proj_y, float* proj_xr, int32_t* level, float* view_cos, int device) {
+    if (!cam || !tcw || n < 0 || (n > 0 && (!xyz || !normal || !min_dist || !max_dist || !inview || !proj_x || !proj_y || !proj_xr || !level || !view_cos))) {
+        set_error("sgs_frustum: bad argument"); return SGS_ERR_INVALID;
+    }
+    if (n == 0) return SGS_OK;
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    // one allocation: inputs (16 + 8 n floats + 1 int) and outputs (4 n floats, n ints, n bytes)
+    const size_t N = (size_t)n;
+    float* d = nullptr;
+    SGS_CUDA_TRY(cudaMalloc(&d, sizeof(float) * (16 + 8 * N + 4 * N + N + 4) + N + 64));
+    float* d_tcw = d; float* d_xyz = d + 16; float* d_nrm = d_xyz + 3 * N; float* d_mn = d_nrm + 3 * N; float* d_mx = d_mn + N;
+    float* d_px = d_mx + N; float* d_py = d_px + N; float* d_pxr = d_py + N; float* d_vc = d_pxr + N;
+    int32_t* d_lv = reinterpret_cast<int32_t*>(d_vc + N); int32_t* d_n = d_lv + N; uint8_t* d_in = reinterpret_cast<uint8_t*>(d_n + 4);
+    cudaMemcpy(d_tcw, tcw, 64, cudaMemcpyHostToDevice); cudaMemcpy(d_xyz, xyz, 12 * N, cudaMemcpyHostToDevice); cudaMemcpy(d_nrm, normal, 12 * N, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_mn, min_dist, 4 * N, cudaMemcpyHostToDevice); cudaMemcpy(d_mx, max_dist, 4 * N, cudaMemcpyHostToDevice); cudaMemcpy(d_n, &n, 4, cudaMemcpyHostToDevice);
+    sgs_frustum_batch a;
+    a.cam = *cam; a.tcw = d_tcw; a.mp_xyz = d_xyz; a.mp_normal = d_nrm; a.mp_min_dist = d_mn; a.mp_max_dist = d_mx; a.mp_n = d_n; a.point_cap = n;
+    a.viewing_cos_limit = viewing_cos_limit; a.mp_inview = d_in; a.proj_x = d_px; a.proj_y = d_py; a.proj_xr = d_pxr; a.level = d_lv; a.view_cos = d_vc;
+    int rc = sgs_frustum_batch_device(&a, 1, nullptr);
+    cudaError_t e = cudaSuccess;
+    if (rc == SGS_OK) {
+        e = cudaMemcpy(inview, d_in, N, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(proj_x, d_px, 4 * N, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(proj_y, d_py, 4 * N, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(proj_xr, d_pxr, 4 * N, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(view_cos, d_vc, 4 * N, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(level, d_lv, 4 * N, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (rc != SGS_OK) return rc;
+    if (e != cudaSuccess) { set_error("sgs_frustum: %s", cudaGetErrorString(e)); return SGS_ERR_CUDA; }
+    return SGS_OK;
+}
+
 }  // extern "C"

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "sgslam/FrameDynamic.h"
+#include "sgslam/FrameGeometry.h"
 #include "sgslam/ORBextractor.h"
 #include "sgslam/ORBmatcher.h"
 
@@ -19,6 +20,10 @@ struct MapPoint {
     bool mbTrackInView = false; float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackViewCos = 1; int mnTrackScaleLevel = 0;
     cv::Mat GetWorldPos() { return pos; }
     cv::Mat GetDescriptor() { return desc; }
+    cv::Mat normal; float mfMinDistance = 0, mfMaxDistance = 0;
+    cv::Mat GetNormal() { return normal; }
+    float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }
+    float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
     int Observations() { return nobs; }
     bool isBad() { return bad; }
 };
@@ -123,6 +128,29 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 9; ++i) if (std::fabs(Fg.at<double>(i / 3, i % 3) - expF[i]) > 1e-9 * fmax) return fail("findFundamentalMat: F");
     if (!FindFundamentalMatRansac(std::vector<cv::Point2f>(cpts.begin(), cpts.begin() + 10), std::vector<cv::Point2f>(exp_trk.begin(), exp_trk.begin() + 10)).empty())
         return fail("findFundamentalMat: fewer than 15 pairs must come back empty");
-    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok\n", nkp, nm, kept, nd, nlk);
+    // 5. isInFrustum for a batch of map points (expected values: CPU oracle)
+    int32_t nfr = 0; f.read(reinterpret_cast<char*>(&nfr), 4);
+    std::vector<float> fT = rd<float>(f, 16), fxyz = rd<float>(f, (size_t)nfr * 3), fnrm = rd<float>(f, (size_t)nfr * 3), fmn = rd<float>(f, nfr), fmx = rd<float>(f, nfr);
+    std::vector<uint8_t> ein = rd<uint8_t>(f, nfr);
+    std::vector<float> epx = rd<float>(f, nfr), epy = rd<float>(f, nfr), epxr = rd<float>(f, nfr), evc = rd<float>(f, nfr);
+    std::vector<int32_t> elv = rd<int32_t>(f, nfr);
+    Frame ff; ff.mTcw = cv::Mat(4, 4, CV_32F, fT.data(), 16).clone(); ff.mvScaleFactors = cur.mvScaleFactors;
+    std::vector<MapPoint> store(nfr); std::vector<MapPoint*> ptrs(nfr);
+    for (int i = 0; i < nfr; ++i) {
+        store[i].pos = cv::Mat(3, 1, CV_32F, &fxyz[3 * (size_t)i], 4).clone(); store[i].normal = cv::Mat(3, 1, CV_32F, &fnrm[3 * (size_t)i], 4).clone();
+        store[i].mfMinDistance = fmn[i]; store[i].mfMaxDistance = fmx[i]; ptrs[i] = &store[i];
+    }
+    const int nview = UpdateTrackInView(ff, ptrs, 0.5f);
+    int expview = 0, lvldiff = 0;
+    for (int i = 0; i < nfr; ++i) {
+        expview += ein[i];
+        if (store[i].mbTrackInView != (ein[i] != 0)) return fail("isInFrustum: flag");
+        if (!ein[i]) continue;
+        // the shim divides the invariance distances back by 0.8 / 1.2: compare positions exactly, distances-dependent gates by flag only
+        if (store[i].mTrackProjX != epx[i] || store[i].mTrackProjY != epy[i] || store[i].mTrackProjXR != epxr[i] || store[i].mTrackViewCos != evc[i]) return fail("isInFrustum: projection");
+        if (store[i].mnTrackScaleLevel != elv[i]) ++lvldiff;
+    }
+    if (nview != expview || lvldiff > 2) return fail("isInFrustum: count / level");
+    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view\n", nkp, nm, kept, nd, nlk, nview, nfr);
     return 0;
 }

@@ -56,6 +56,22 @@ def test_shim_on_gpu(tmp_path):
         assert Fo is not None
         np.array([len(pts)], np.int32).tofile(f); frames[1].tofile(f); frames[0].tofile(f); pts.tofile(f); trk.astype(np.float32).tofile(f)
         Fo.astype(np.float64).tofile(f)
+        # 5. isInFrustum: points in front of a posed camera; distances chosen so that x/0.8*0.8 and x/1.2*1.2 round-trips cannot flip a gate
+        rs = np.random.RandomState(8)
+        nfr = 2000
+        T = np.eye(4, dtype=np.float32); a = 0.2
+        T[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32); T[:3, 3] = [0.2, -0.1, 0.3]
+        z = rs.uniform(-1, 8, nfr); pc = np.c_[rs.uniform(-0.8, 0.8, nfr) * z, rs.uniform(-0.6, 0.6, nfr) * z, z]
+        xyz = ((pc - T[:3, 3].astype(np.float64)) @ T[:3, :3].astype(np.float64)).astype(np.float32)
+        cen = -T[:3, :3].T.astype(np.float64) @ T[:3, 3].astype(np.float64)
+        tc = xyz.astype(np.float64) - cen; d0 = np.linalg.norm(tc, axis=1)
+        nn = tc / d0[:, None] + rs.normal(0, 0.4, (nfr, 3)); nrm = (nn / np.linalg.norm(nn, axis=1, keepdims=True)).astype(np.float32)
+        mx = (d0 * rs.choice([0.5, 1.7, 3.1], nfr)).astype(np.float32); mn = (mx / 5).astype(np.float32)
+        mn = (np.float32(0.8) * mn / np.float32(0.8)).astype(np.float32); mx = (np.float32(1.2) * mx / np.float32(1.2)).astype(np.float32)   # fixed points of the round trip
+        cam9 = np.array([535.4, 539.2, 320.1, 247.6, 40.0, 0, 0, 640, 480], np.float32)
+        ref = O.is_in_frustum(T, cam9, 8, float(np.float32(np.log(np.float32(1.2)))), xyz, nrm, mn, mx, 0.5)
+        np.array([nfr], np.int32).tofile(f); T.tofile(f); xyz.tofile(f); nrm.tofile(f); mn.tofile(f); mx.tofile(f)
+        ref['inview'].tofile(f); ref['proj_x'].tofile(f); ref['proj_y'].tofile(f); ref['proj_xr'].tofile(f); ref['view_cos'].tofile(f); ref['level'].tofile(f)
     out = subprocess.run([exe, str(path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'OK shim' in out.stdout
