@@ -208,6 +208,25 @@ typedef struct sgs_lastframe_batch {      /* SearchByProjection(Frame&, const Fr
 } sgs_lastframe_batch;
 SGS_API int sgs_match_project_lastframe_batch_device(sgs_matcher* m, const sgs_lastframe_batch* args, int nframes, void* stream);
 
+typedef struct sgs_keyframe_batch {       /* SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:1474 (relocalisation) */
+    sgs_camera cam;
+    const sgs_keypoint* cur_kps; const uint8_t* cur_desc; const float* cur_uright; const int32_t* cur_n;   /* cur_uright is not read by the search but must be valid */
+    const float* kf_xyz;          /* [F][point_cap][3]  map points of the key frame, in key-frame keypoint order */
+    const uint8_t* kf_desc;       /* [F][point_cap][32] MapPoint::GetDescriptor() */
+    const uint8_t* kf_valid;      /* 1: map point exists, !isBad(), not in sAlreadyFound */
+    const float* kf_angle;        /* pKF->mvKeysUn[i].angle */
+    const float* kf_min_dist; const float* kf_max_dist;   /* mfMinDistance / mfMaxDistance (raw) */
+    const int32_t* kf_n;          /* [F] */
+    const float* tcw_cur;         /* [F][16] */
+    float th; int32_t orb_dist, check_orientation;
+    int32_t* cur_mp;              /* in/out [F][cur_cap]: >= 0 means CurrentFrame.mvpMapPoints[j] is set; new matches write the key-frame index */
+    int32_t* nmatches; uint64_t* ncand;
+} sgs_keyframe_batch;
+SGS_API int sgs_match_project_keyframe_batch_device(sgs_matcher* m, const sgs_keyframe_batch* args, int nframes, void* stream);
+SGS_API int sgs_match_project_keyframe(const sgs_frame_view* cur, const float* tcw_cur, int nkf, const uint8_t* kf_valid, const float* kf_xyz,
+                                       const uint8_t* kf_desc, const float* kf_angle, const float* kf_min_dist, const float* kf_max_dist,
+                                       float th, int orb_dist, int check_orientation, int32_t* cur_mp_inout, int* nmatches, int device);
+
 typedef struct sgs_localmap_batch {       /* SearchByProjection(Frame&, vector<MapPoint*>&, th), src/ORBmatcher.cc:45 */
     sgs_camera cam;
     const sgs_keypoint* cur_kps; const uint8_t* cur_desc; const float* cur_uright; const int32_t* cur_n;

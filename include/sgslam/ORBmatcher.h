@@ -10,6 +10,7 @@
 // Covered here (tracking thread, every frame): SearchByProjection(Frame&, const Frame&, th, bMono)   src/ORBmatcher.cc:1332-1472
 //                                              SearchByProjection(Frame&, vector<MapPoint*>&, th)     src/ORBmatcher.cc:45-129
 //                                              DescriptorDistance                                      src/ORBmatcher.cc:1649-1665
+//                                              SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist)  src/ORBmatcher.cc:1474-1601
 // The mapping / loop-closing variants (SearchByBoW, Fuse, SearchBySim3, ...) are SURVEY section 8(f) "next" rows.
 #pragma once
 #include <stdexcept>
@@ -94,6 +95,38 @@ public:
                                          mfNNratio, 0, fmp.data(), fobs.data(), &nmatches, device_));
         for (int j = 0; j < n; ++j)
             if (fmp[j] >= 0 && fmp[j] < nmp) F.mvpMapPoints[j] = vpMapPoints[fmp[j]];
+        return nmatches;
+    }
+
+    // Project MapPoints seen in KeyFrame into the Frame and search matches (Tracking::Relocalization, src/Tracking.cc:1494,1508).
+    template <class FrameT, class KeyFrameT, class SetT>
+    int SearchByProjection(FrameT& CurrentFrame, KeyFrameT* pKF, const SetT& sAlreadyFound, const float th, const int ORBdist) {
+        const int n = CurrentFrame.N;
+        const auto vpMPs = pKF->GetMapPointMatches();
+        const int nkf = (int)vpMPs.size();
+        std::vector<float> scale(CurrentFrame.mvScaleFactors.begin(), CurrentFrame.mvScaleFactors.end());
+        sgs_frame_view fv = view(CurrentFrame, scale);
+        std::vector<uint8_t> valid(nkf, 0), desc((size_t)nkf * 32, 0);
+        std::vector<float> xyz((size_t)nkf * 3, 0.f), ang(nkf, 0.f), mn(nkf, 0.f), mx(nkf, 0.f);
+        for (int i = 0; i < nkf; ++i) {
+            auto* pMP = vpMPs[i];
+            if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+            valid[i] = 1;
+            const cv::Mat P = pMP->GetWorldPos(), d = pMP->GetDescriptor();
+            for (int k = 0; k < 3; ++k) xyz[3 * (size_t)i + k] = P.template at<float>(k, 0);
+            std::memcpy(&desc[(size_t)i * 32], d.template ptr<uint8_t>(), 32);
+            ang[i] = pKF->mvKeysUn[i].angle;
+            mn[i] = pMP->GetMinDistanceInvariance() / 0.8f; mx[i] = pMP->GetMaxDistanceInvariance() / 1.2f;      // raw mfMinDistance / mfMaxDistance
+        }
+        std::vector<int32_t> cmp(n, -1);
+        for (int j = 0; j < n; ++j) if (CurrentFrame.mvpMapPoints[j]) cmp[j] = nkf + j;
+        float T[16];
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[4 * r + c] = CurrentFrame.mTcw.template at<float>(r, c);
+        int nmatches = 0;
+        check(sgs_match_project_keyframe(&fv, T, nkf, valid.data(), xyz.data(), desc.data(), ang.data(), mn.data(), mx.data(), th, ORBdist,
+                                         mbCheckOrientation ? 1 : 0, cmp.data(), &nmatches, device_));
+        for (int j = 0; j < n; ++j)
+            if (cmp[j] >= 0 && cmp[j] < nkf) CurrentFrame.mvpMapPoints[j] = vpMPs[cmp[j]];
         return nmatches;
     }
 

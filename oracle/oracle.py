@@ -227,6 +227,24 @@ def search_by_projection_last(cur, Tcw_cur, Tcw_last, last_has_mp, last_xyz, las
     return nm, mp, ncand.value
 
 
+def search_by_projection_kf(cur, Tcw_cur, kf_valid, kf_xyz, kf_desc, kf_angle, min_dist, max_dist, th, orb_dist, check_ori=True, cur_mp=None,
+                            log_scale_factor=None):
+    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1474-1601): returns (nmatches, cur_mp, ncand)."""
+    n = len(kf_valid)
+    Tc = np.ascontiguousarray(Tcw_cur, np.float32)
+    a = [np.ascontiguousarray(kf_valid, np.uint8), np.ascontiguousarray(kf_xyz, np.float32), np.ascontiguousarray(kf_desc, np.uint8),
+         np.ascontiguousarray(kf_angle, np.float32), np.ascontiguousarray(min_dist, np.float32), np.ascontiguousarray(max_dist, np.float32)]
+    mp = np.full(cur.c.N, -1, np.int32) if cur_mp is None else np.ascontiguousarray(cur_mp, np.int32).copy()
+    if log_scale_factor is None:
+        log_scale_factor = float(np.float32(np.log(np.float32(1.2))))
+    ncand = C.c_int64()
+    fn = lib().sgo_search_by_projection_kf
+    fn.restype = C.c_int
+    nm = fn(C.byref(cur.c), _p(Tc), n, *[_p(x) for x in a], C.c_float(th), int(orb_dist), int(check_ori), C.c_float(log_scale_factor), _p(mp),
+            C.byref(ncand))
+    return nm, mp, ncand.value
+
+
 def search_by_projection_local(fr, inview, projx, projy, projxr, level, viewcos, mp_desc, mp_obs, th, nnratio,
                                f_mp, f_mp_obs, id_base=0):
     n = len(inview)

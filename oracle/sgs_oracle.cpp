@@ -956,6 +956,79 @@ SGO_API int sgo_search_by_projection_last(const SgoFrame* cur, const float* Tcw_
     return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist),
+// src/ORBmatcher.cc:1474-1601 (Tracking::Relocalization, src/Tracking.cc:1494,1508).  kf_valid[i]: pKF's i-th map point exists, is not bad and
+// is not in sAlreadyFound; kf_angle[i] = pKF->mvKeysUn[i].angle; min/max_dist are mfMinDistance / mfMaxDistance (raw).
+// cur_mp_inout[j] >= 0: CurrentFrame.mvpMapPoints[j] is set (any such keypoint is skipped, :1543-1544).  New matches write the index i.
+SGO_API int sgo_search_by_projection_kf(const SgoFrame* cur, const float* Tcw_cur, int nkf, const uint8_t* kf_valid, const float* kf_xyz,
+                                        const uint8_t* kf_desc, const float* kf_angle, const float* min_dist, const float* max_dist, float th,
+                                        int ORBdist, int checkOri, float log_scale_factor, int32_t* cur_mp_inout, int64_t* ncand_out) {
+    FrameView F = to_view(cur); Grid g; build_grid(F, g);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = HISTO_LENGTH / 360.0f;
+    float Rcw[9], tcw[3], Ow[3];
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) Rcw[3 * r + c] = Tcw_cur[4 * r + c]; tcw[r] = Tcw_cur[4 * r + 3]; }
+    for (int r = 0; r < 3; r++) {   // Ow = -Rcw.t()*tcw: transposed gemm, double accumulator
+        double acc = 0; for (int k = 0; k < 3; k++) acc += (double)(-Rcw[3 * k + r]) * (double)tcw[k];
+        Ow[r] = (float)acc;
+    }
+    std::vector<int> cand;
+    int64_t ncand = 0;
+    for (int i = 0; i < nkf; i++) {
+        if (!kf_valid[i]) continue;
+        const float* Xw = kf_xyz + 3 * i;
+        float x3Dc[3];
+        for (int r = 0; r < 3; r++) {   // gemm(Rcw, x3Dw, 1, tcw, 1): small-matrix path, float accumulation
+            const float acc = Rcw[3 * r] * Xw[0] + Rcw[3 * r + 1] * Xw[1] + Rcw[3 * r + 2] * Xw[2];
+            x3Dc[r] = (float)((double)acc + (double)tcw[r]);
+        }
+        const float xc = x3Dc[0], yc = x3Dc[1];
+        const float invzc = (float)(1.0 / x3Dc[2]);                 // :1506, no sign test in this variant
+        const float u = F.fx * xc * invzc + F.cx;
+        const float v = F.fy * yc * invzc + F.cy;
+        if (u < F.minX || u > F.maxX) continue;
+        if (v < F.minY || v > F.maxY) continue;
+        const float PO[3] = {Xw[0] - Ow[0], Xw[1] - Ow[1], Xw[2] - Ow[2]};
+        const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+        const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const float ratio = max_dist[i] / dist3D;                   // MapPoint::PredictScale (src/MapPoint.cc:400-418)
+        int nPredictedLevel = (int)std::ceil(std::log(ratio) / log_scale_factor);
+        if (nPredictedLevel < 0) nPredictedLevel = 0; else if (nPredictedLevel >= F.nlevels) nPredictedLevel = F.nlevels - 1;
+        const float radius = th * F.scaleFactors[nPredictedLevel];
+        features_in_area(F, g, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1, cand);
+        if (cand.empty()) continue;
+        ncand += (int64_t)cand.size();
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : cand) {
+            if (cur_mp_inout[i2] >= 0) continue;                    // :1543-1544
+            const int dist = descriptor_distance(kf_desc + 32 * (size_t)i, F.desc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= ORBdist) {
+            cur_mp_inout[bestIdx2] = i;
+            nmatches++;
+            if (checkOri) {
+                float rot = kf_angle[i] - F.keysUn[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int j : rotHist[i]) { cur_mp_inout[j] = -1; nmatches--; }
+    }
+    if (ncand_out) *ncand_out = ncand;
+    return nmatches;
+}
+
 // ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th), src/ORBmatcher.cc:45-129, with the
 // per-point fields that Frame::isInFrustum (src/Frame.cc:296-352) fills given as flat arrays:
 //   mp_inview[i] (mbTrackInView && !isBad()), projx/projy/projxr, level (mnTrackScaleLevel), viewcos, desc.

@@ -322,12 +322,12 @@ struct LastPolicy {
     int64_t lo; int point; PointPre pp;
     __device__ bool uses_second() const { return false; }
     __device__ bool reject_is_final() const { return true; }     // best distance > TH_HIGH: no candidate can be accepted
-    __device__ bool blocks_others() const { return ((A.last_flags[lo + point] >> 1) & 1) != 0; }
-    __device__ bool decide(uint32_t k1, uint32_t, int i1, int, int& target) const { target = i1; return (int)(k1 >> 16) <= kThHigh; }   // :1430
+    __device__ bool blocks_others() const { return A.kf_mode || ((A.last_flags[lo + point] >> 1) & 1) != 0; }
+    __device__ bool decide(uint32_t k1, uint32_t, int i1, int, int& target) const { target = i1; return (int)(k1 >> 16) <= A.orb_dist; }   // :1430 / :1559
     __device__ TopK rescan() const {
         const uint4* dm = reinterpret_cast<const uint4*>(A.last_desc + 32 * (lo + point));
         return scan_window(A.cam, s, cur_desc, pp.u, pp.v, pp.radius, pp.min_level, pp.max_level, __ldg(dm), __ldg(dm + 1), true,
-                           __fsub_rn(pp.u, __fmul_rn(A.cam.bf, pp.invz)), pp.radius, nullptr);
+                           __fsub_rn(pp.u, __fmul_rn(A.cam.bf, pp.invz)), A.kf_mode ? __int_as_float(0x7f800000) : pp.radius, nullptr);
     }
     __device__ void record(int target) const {
         if (!A.check_ori) return;
@@ -340,7 +340,7 @@ struct LastPolicy {
     }
     __device__ void commit(int target) const {
         cur_mp[target] = point;                                                   // :1432 last writer wins
-        s.claimed[target] = (A.last_flags[lo + point] >> 1) & 1;
+        s.claimed[target] = A.kf_mode ? 1 : ((A.last_flags[lo + point] >> 1) & 1);     // KeyFrame variant: any assigned keypoint is skipped (:1543)
     }
 };
 
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int hist[kHistoLen];
     __shared__ int s_nmatch, s_nevent;
-    __shared__ float s_pose[16];     // Rcw (9), tcw (3), forward/backward flags
+    __shared__ float s_pose[20];     // Rcw (9), tcw (3), forward/backward flags, Ow (3)
     const int f = blockIdx.x;
     const int n = min(A.cur_n[f], A.cur_cap);
     const int nlast = min(A.last_n[f], A.last_cap);
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
         // Rcw, tcw, twc = -Rcw^T tcw, tlc = Rlw twc + tlw (:1342-1351).  cv::gemm on CV_32F: the transposed product takes the general path
         // (double accumulator, one rounding); a plain 3x3 * 3x1 (+ C) takes OpenCV's small-matrix path: float products summed in float,
         // left to right, then (float)((double)sum + (double)c).  Pinned against cv2.gemm (tests/golden/make_golden_frustum.py).
-        const float* Tc = A.tcw_cur + 16 * f; const float* Tl = A.tcw_last + 16 * f;
+        const float* Tc = A.tcw_cur + 16 * f; const float* Tl = A.kf_mode ? Tc : A.tcw_last + 16 * f;
         float twc[3];
         for (int r = 0; r < 3; ++r) {
             double acc = 0.0;
@@ -376,8 +376,9 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
         const float tlc2 = (float)__dadd_rn((double)acc, (double)Tl[11]);
         const float mb = __fdiv_rn(A.cam.bf, A.cam.fx);       // Frame.cc:196
         for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) s_pose[3 * r + c] = Tc[4 * r + c]; s_pose[9 + r] = Tc[4 * r + 3]; }
-        s_pose[12] = (tlc2 > mb && !A.mono) ? 1.f : 0.f;
-        s_pose[13] = (-tlc2 > mb && !A.mono) ? 1.f : 0.f;
+        s_pose[12] = (!A.kf_mode && tlc2 > mb && !A.mono) ? 1.f : 0.f;
+        s_pose[13] = (!A.kf_mode && -tlc2 > mb && !A.mono) ? 1.f : 0.f;
+        s_pose[14] = twc[0]; s_pose[15] = twc[1]; s_pose[16] = twc[2];       // Ow = -Rcw^T tcw (KeyFrame variant, :1480)
     }
     build_frame_grid(A.cam, kps, A.cur_uright + (int64_t)f * A.cur_cap, n, s);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -404,19 +405,33 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
                 const float acc = __fadd_rn(__fadd_rn(__fmul_rn(s_pose[3 * r], X[0]), __fmul_rn(s_pose[3 * r + 1], X[1])), __fmul_rn(s_pose[3 * r + 2], X[2]));
                 xc[r] = (float)__dadd_rn((double)acc, (double)s_pose[9 + r]);
             }
-            const float invz = (float)__ddiv_rn(1.0, (double)xc[2]);                       // :1369
-            if (!(invz < 0.f)) {
+            const float invz = (float)__ddiv_rn(1.0, (double)xc[2]);                       // :1369 / :1506
+            if (A.kf_mode || !(invz < 0.f)) {
                 const float u = __fadd_rn(__fmul_rn(__fmul_rn(A.cam.fx, xc[0]), invz), A.cam.cx);
                 const float v = __fadd_rn(__fmul_rn(__fmul_rn(A.cam.fy, xc[1]), invz), A.cam.cy);
                 if (!(u < A.cam.min_x || u > A.cam.max_x) && !(v < A.cam.min_y || v > A.cam.max_y)) {
-                    const int oct = A.last_octave[lo + i];
-                    const float radius = __fmul_rn(A.th, A.cam.scale[oct]);
-                    int mn, mx;
-                    if (fwd) { mn = oct; mx = -1; } else if (bwd) { mn = 0; mx = oct; } else { mn = oct - 1; mx = oct + 1; }
-                    pp.valid = 1; pp.u = u; pp.v = v; pp.invz = invz; pp.radius = radius; pp.min_level = mn; pp.max_level = mx;
-                    const uint4* dm = reinterpret_cast<const uint4*>(A.last_desc + 32 * (lo + i));
-                    const float ur_pred = __fsub_rn(u, __fmul_rn(A.cam.bf, invz));
-                    t = scan_window(A.cam, s, cur_desc, u, v, radius, mn, mx, __ldg(dm), __ldg(dm + 1), false, ur_pred, radius, &ncand, gl, kGroup);
+                    bool ok = true;
+                    int oct, mn, mx;
+                    if (A.kf_mode) {          // :1517-1531: distance inside the scale-invariance range, level from MapPoint::PredictScale
+                        const float px = __fsub_rn(X[0], s_pose[14]), py = __fsub_rn(X[1], s_pose[15]), pz = __fsub_rn(X[2], s_pose[16]);
+                        const float dist = (float)sqrt(((double)px * px + (double)py * py) + (double)pz * pz);
+                        const float maxd = A.kf_max_dist[lo + i];
+                        ok = !(dist < __fmul_rn(0.8f, A.kf_min_dist[lo + i]) || dist > __fmul_rn(1.2f, maxd));
+                        oct = (int)ceilf(__fdiv_rn((float)log((double)__fdiv_rn(maxd, dist)), A.log_sf));
+                        oct = oct < 0 ? 0 : (oct >= A.cam.nlevels ? A.cam.nlevels - 1 : oct);
+                        mn = oct - 1; mx = oct + 1;
+                    } else {
+                        oct = A.last_octave[lo + i];
+                        if (fwd) { mn = oct; mx = -1; } else if (bwd) { mn = 0; mx = oct; } else { mn = oct - 1; mx = oct + 1; }
+                    }
+                    if (ok) {
+                        const float radius = __fmul_rn(A.th, A.cam.scale[oct]);
+                        pp.valid = 1; pp.u = u; pp.v = v; pp.invz = invz; pp.radius = radius; pp.min_level = mn; pp.max_level = mx;
+                        const uint4* dm = reinterpret_cast<const uint4*>(A.last_desc + 32 * (lo + i));
+                        const float ur_pred = __fsub_rn(u, __fmul_rn(A.cam.bf, invz));
+                        t = scan_window(A.cam, s, cur_desc, u, v, radius, mn, mx, __ldg(dm), __ldg(dm + 1), false, ur_pred,
+                                        A.kf_mode ? __int_as_float(0x7f800000) : radius, &ncand, gl, kGroup);
+                    }
                 }
             }
         }

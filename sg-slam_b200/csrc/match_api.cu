@@ -89,6 +89,26 @@ SGS_API int sgs_match_project_lastframe_batch_device(sgs_matcher* m, const sgs_l
     A.last_angle = a->last_angle; A.last_n = a->last_n; A.last_cap = m->point_cap;
     A.tcw_cur = a->tcw_cur; A.tcw_last = a->tcw_last; A.th = a->th; A.mono = a->mono; A.check_ori = a->check_orientation;
     A.cur_mp = a->cur_mp; A.cur_mp_obs_in = a->cur_mp_obs_in; A.nmatches = a->nmatches; A.ncand = (unsigned long long*)a->ncand;
+    A.kf_mode = 0; A.orb_dist = 100; A.log_sf = 0.f; A.kf_min_dist = A.kf_max_dist = nullptr;      // TH_HIGH, src/ORBmatcher.cc:37
+    A.pre = m->d_pre; A.events = m->d_events;
+    return launch_match_lastframe(A, nframes, (cudaStream_t)stream);
+}
+
+SGS_API int sgs_match_project_keyframe_batch_device(sgs_matcher* m, const sgs_keyframe_batch* a, int nframes, void* stream) {
+    if (!m || !a) { set_error("sgs_match_project_keyframe_batch_device: NULL"); return SGS_ERR_INVALID; }
+    if (nframes < 1 || nframes > m->max_frames) { set_error("nframes outside [1,max_frames]"); return SGS_ERR_INVALID; }
+    if (!a->cur_kps || !a->cur_desc || !a->cur_n || !a->kf_xyz || !a->kf_desc || !a->kf_valid || !a->kf_angle || !a->kf_min_dist || !a->kf_max_dist ||
+        !a->kf_n || !a->tcw_cur || !a->cur_mp || !a->nmatches || !a->ncand || !a->cur_uright) { set_error("sgs_match_project_keyframe_batch_device: NULL array"); return SGS_ERR_INVALID; }
+    if (a->cam.nlevels < 2 || !(a->cam.scale_factors[1] > 1.f)) { set_error("sgs_match_project_keyframe_batch_device: camera scale table missing"); return SGS_ERR_INVALID; }
+    LastFrameArgs A;
+    A.cam = to_cam(a->cam);
+    A.cur_kps = a->cur_kps; A.cur_desc = a->cur_desc; A.cur_uright = a->cur_uright; A.cur_n = a->cur_n;
+    A.cur_cap = m->cur_cap; A.cur_cap_pow2 = pow2_at_least(m->cur_cap);
+    A.last_xyz = a->kf_xyz; A.last_desc = a->kf_desc; A.last_flags = a->kf_valid; A.last_octave = nullptr;
+    A.last_angle = a->kf_angle; A.last_n = a->kf_n; A.last_cap = m->point_cap;
+    A.tcw_cur = a->tcw_cur; A.tcw_last = nullptr; A.th = a->th; A.mono = 1; A.check_ori = a->check_orientation;
+    A.cur_mp = a->cur_mp; A.cur_mp_obs_in = nullptr; A.nmatches = a->nmatches; A.ncand = (unsigned long long*)a->ncand;
+    A.kf_mode = 1; A.orb_dist = a->orb_dist; A.log_sf = logf(a->cam.scale_factors[1]); A.kf_min_dist = a->kf_min_dist; A.kf_max_dist = a->kf_max_dist;
     A.pre = m->d_pre; A.events = m->d_events;
     return launch_match_lastframe(A, nframes, (cudaStream_t)stream);
 }
@@ -145,6 +165,48 @@ SGS_API int sgs_match_project_lastframe(const sgs_frame_view* cur, const float* 
     b.th = th; b.mono = mono; b.check_orientation = check_orientation;
     b.cur_mp = mp.as<int32_t>(); b.cur_mp_obs_in = cur_mp_obs_in ? mpo.as<uint8_t>() : nullptr; b.nmatches = nm.as<int32_t>(); b.ncand = nc.as<uint64_t>();
     rc = sgs_match_project_lastframe_batch_device(m, &b, 1, nullptr);
+    if (rc != SGS_OK) return rc;
+    SGS_CUDA_TRY(cudaDeviceSynchronize());
+    int32_t nm_h = 0;
+    SGS_CUDA_TRY(cudaMemcpy(&nm_h, nm.p, 4, cudaMemcpyDeviceToHost));
+    SGS_CUDA_TRY(cudaMemcpy(cur_mp_inout, mp.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    *nmatches = nm_h;
+    return SGS_OK;
+}
+
+SGS_API int sgs_match_project_keyframe(const sgs_frame_view* cur, const float* tcw_cur, int nkf, const uint8_t* kf_valid, const float* kf_xyz,
+                                       const uint8_t* kf_desc, const float* kf_angle, const float* kf_min_dist, const float* kf_max_dist, float th,
+                                       int orb_dist, int check_orientation, int32_t* cur_mp_inout, int* nmatches, int device) {
+    if (!cur || !tcw_cur || !nmatches || nkf < 0 || cur->n < 0) { set_error("sgs_match_project_keyframe: bad argument"); return SGS_ERR_INVALID; }
+    *nmatches = 0;
+    if (nkf == 0 || cur->n == 0) return SGS_OK;
+    if (!kf_valid || !kf_xyz || !kf_desc || !kf_angle || !kf_min_dist || !kf_max_dist || !cur_mp_inout || !cur->keys_un || !cur->u_right || !cur->desc) {
+        set_error("sgs_match_project_keyframe: NULL array"); return SGS_ERR_INVALID;
+    }
+    sgs_matcher* m = nullptr;
+    int rc = sgs_matcher_create(device, 1, cur->n, nkf, &m);
+    if (rc != SGS_OK) return rc;
+    struct Guard { sgs_matcher* m; ~Guard() { sgs_matcher_destroy(m); } } guard{m};
+    const int n = cur->n;
+    const int32_t n32 = n, nkf32 = nkf;
+    std::vector<uint8_t> flags(nkf);
+    for (int i = 0; i < nkf; ++i) flags[i] = kf_valid[i] ? 1 : 0;
+    DevBuf kps, desc, ur, cn, fl, xyz, kd, ang, mn, mx, kn, tc, mp, nm, nc;
+    SGS_CUDA_TRY(kps.upload(cur->keys_un, sizeof(sgs_keypoint) * n)); SGS_CUDA_TRY(desc.upload(cur->desc, (size_t)32 * n));
+    SGS_CUDA_TRY(ur.upload(cur->u_right, 4 * (size_t)n)); SGS_CUDA_TRY(cn.upload(&n32, 4));
+    SGS_CUDA_TRY(fl.upload(flags.data(), nkf)); SGS_CUDA_TRY(xyz.upload(kf_xyz, 12 * (size_t)nkf)); SGS_CUDA_TRY(kd.upload(kf_desc, 32 * (size_t)nkf));
+    SGS_CUDA_TRY(ang.upload(kf_angle, 4 * (size_t)nkf)); SGS_CUDA_TRY(mn.upload(kf_min_dist, 4 * (size_t)nkf)); SGS_CUDA_TRY(mx.upload(kf_max_dist, 4 * (size_t)nkf));
+    SGS_CUDA_TRY(kn.upload(&nkf32, 4)); SGS_CUDA_TRY(tc.upload(tcw_cur, 64)); SGS_CUDA_TRY(mp.upload(cur_mp_inout, 4 * (size_t)n));
+    SGS_CUDA_TRY(nm.alloc(4)); SGS_CUDA_TRY(nc.alloc(8)); SGS_CUDA_TRY(cudaMemset(nc.p, 0, 8));
+    sgs_keyframe_batch b;
+    std::memset(&b, 0, sizeof b);
+    b.cam = view_cam(cur);
+    b.cur_kps = kps.as<sgs_keypoint>(); b.cur_desc = desc.as<uint8_t>(); b.cur_uright = ur.as<float>(); b.cur_n = cn.as<int32_t>();
+    b.kf_xyz = xyz.as<float>(); b.kf_desc = kd.as<uint8_t>(); b.kf_valid = fl.as<uint8_t>(); b.kf_angle = ang.as<float>();
+    b.kf_min_dist = mn.as<float>(); b.kf_max_dist = mx.as<float>(); b.kf_n = kn.as<int32_t>(); b.tcw_cur = tc.as<float>();
+    b.th = th; b.orb_dist = orb_dist; b.check_orientation = check_orientation;
+    b.cur_mp = mp.as<int32_t>(); b.nmatches = nm.as<int32_t>(); b.ncand = nc.as<uint64_t>();
+    rc = sgs_match_project_keyframe_batch_device(m, &b, 1, nullptr);
     if (rc != SGS_OK) return rc;
     SGS_CUDA_TRY(cudaDeviceSynchronize());
     int32_t nm_h = 0;

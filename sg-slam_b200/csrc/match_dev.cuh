@@ -36,6 +36,9 @@ struct LastFrameArgs {
     const int32_t* last_octave; const float* last_angle; const int32_t* last_n; int32_t last_cap;
     const float* tcw_cur; const float* tcw_last;   // [nframes][16]
     float th; int32_t mono, check_ori;
+    // KeyFrame variant (SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:1474): window from the predicted
+    // scale level, every assigned keypoint blocks, no stereo gate; orb_dist replaces TH_HIGH (100 in the last-frame variant)
+    int32_t kf_mode, orb_dist; float log_sf; const float* kf_min_dist; const float* kf_max_dist;
     // in/out
     int32_t* cur_mp; const uint8_t* cur_mp_obs_in; int32_t* nmatches; unsigned long long* ncand;
     // scratch [nframes][last_cap]

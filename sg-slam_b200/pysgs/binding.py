@@ -82,6 +82,7 @@ ABI_SYMBOLS = [
     'sgs_lk_create', 'sgs_lk_destroy', 'sgs_lk_track', 'sgs_lk_track_batch_device', 'sgs_lk_read_level',
     'sgs_tracker_lk_device', 'sgs_tracker_prev_xy_device', 'sgs_tracker_track_lk', 'sgs_extractor_level0_device', 'sgs_memcpy_d2h',
     'sgs_lk_set_profiling', 'sgs_lk_stage_times', 'sgs_tracker_lk',
+    'sgs_match_project_keyframe_batch_device', 'sgs_match_project_keyframe',
     'sgs_stereo_from_depth_batch_device', 'sgs_frustum_batch_device', 'sgs_frustum', 'sgs_tracker_stereo_device',
     'sgs_fundamental_ransac', 'sgs_fundamental_batch_device', 'sgs_tracker_fundamental_device', 'sgs_tracker_fundamental_device_ptr',
 ]
@@ -261,6 +262,19 @@ def match_project_lastframe(cur, Tcw_cur, Tcw_last, last_has_mp, last_xyz, last_
     nm = C.c_int()
     check(lib().sgs_match_project_lastframe(C.byref(cur.c), _p(Tc), _p(Tl), n, _p(has), _p(xyz), _p(ld), _p(lo), _p(loct), _p(la),
                                             C.c_float(th), int(mono), int(check_ori), _p(mp), _p(mpo), C.byref(nm), device))
+    return nm.value, mp
+
+
+def match_project_keyframe(cur, Tcw_cur, kf_valid, kf_xyz, kf_desc, kf_angle, min_dist, max_dist, th, orb_dist, check_ori=True, cur_mp=None, device=0):
+    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) on the GPU: returns (nmatches, cur_mp)."""
+    n = len(kf_valid)
+    Tc = np.ascontiguousarray(Tcw_cur, np.float32)
+    a = [np.ascontiguousarray(kf_valid, np.uint8), np.ascontiguousarray(kf_xyz, np.float32), np.ascontiguousarray(kf_desc, np.uint8),
+         np.ascontiguousarray(kf_angle, np.float32), np.ascontiguousarray(min_dist, np.float32), np.ascontiguousarray(max_dist, np.float32)]
+    mp = np.full(cur.c.n, -1, np.int32) if cur_mp is None else np.ascontiguousarray(cur_mp, np.int32).copy()
+    nm = C.c_int()
+    check(lib().sgs_match_project_keyframe(C.byref(cur.c), _p(Tc), n, *[_p(x) for x in a], C.c_float(th), int(orb_dist), int(check_ori), _p(mp), C.byref(nm),
+                                           device))
     return nm.value, mp
 
 

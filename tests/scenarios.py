@@ -125,3 +125,22 @@ def dynreject_scenario(seed, n=1000, w=640, h=480, nboxes=2):
     for b in range(nboxes):
         boxes[b] = (rng.uniform(0, w - 200), rng.uniform(0, h - 300), rng.uniform(80, 200), rng.uniform(150, 300))
     return dict(cur=cur, prev=prev.astype(np.float32), F=F, boxes=boxes)
+
+
+def keyframe_scenario(seed, n_cur=1000, n_kf=1000, **kw):
+    """Relocalisation search (src/ORBmatcher.cc:1474): the last-frame scenario re-read as a key frame -- map points with a scale-invariance
+    range around their distance (so that the predicted level spreads over the pyramid, some points fall outside the range), a few current
+    keypoints already holding a map point."""
+    s = random_lastframe_scenario(seed, n_cur=n_cur, n_last=n_kf, **kw)
+    rng = np.random.RandomState(seed + 1000)
+    R = s['Tcw_cur'][:3, :3].astype(np.float64); t = s['Tcw_cur'][:3, 3].astype(np.float64)
+    cen = -R.T @ t
+    d = np.linalg.norm(s['last_xyz'].astype(np.float64) - cen, axis=1)
+    lvl = rng.randint(0, 8, n_kf)
+    maxd = (d * 1.2 ** (lvl - rng.uniform(0.05, 0.95, n_kf))).astype(np.float32)          # ceil(log(maxd/d)/log 1.2) == lvl, away from the boundaries
+    out = rng.rand(n_kf) < 0.05
+    maxd[out] = (d[out] * 0.5).astype(np.float32)                                            # beyond 1.2 maxd: skipped
+    mind = (maxd / np.float32(1.2) ** 8).astype(np.float32)
+    cur_mp = np.where(rng.rand(n_cur) < 0.1, 5000 + np.arange(n_cur), -1).astype(np.int32)
+    s.update(kf_valid=(rng.rand(n_kf) < 0.9).astype(np.uint8), min_dist=mind, max_dist=maxd, cur_mp=cur_mp)
+    return s

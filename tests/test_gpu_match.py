@@ -178,3 +178,20 @@ def test_dynreject_batch_device_compaction():
         assert co[f] == len(sel)
         assert ko[f, :len(sel)].tobytes() == kps[f][sel].tobytes()
         assert np.array_equal(do_[f, :len(sel)], desc[f][sel])
+
+
+@pytest.mark.parametrize('seed,ncur,nkf,orb_dist,th', [(1, 1000, 1000, 100, 10.0), (2, 1500, 800, 64, 3.0), (3, 300, 2000, 100, 10.0), (4, 1000, 1000, 50, 15.0)])
+def test_keyframe_projection_matcher(seed, ncur, nkf, orb_dist, th):
+    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (relocalisation, src/ORBmatcher.cc:1474-1601)."""
+    s = S.keyframe_scenario(seed, n_cur=ncur, n_kf=nkf, conflict=0.4)
+    cam = s['cam']
+    fo = O.FrameArrays(s['kps'], s['uright'], s['desc'], 640, 480, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], s['sf'])
+    fg = B.HostFrame(s['kps'], s['uright'], s['desc'], 640, 480, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], s['sf'])
+    for ori in (True, False):
+        nm_o, mp_o, _ = O.search_by_projection_kf(fo, s['Tcw_cur'], s['kf_valid'], s['last_xyz'], s['last_desc'], s['last_angle'], s['min_dist'], s['max_dist'], th,
+                                                  orb_dist, ori, s['cur_mp'])
+        nm_g, mp_g = B.match_project_keyframe(fg, s['Tcw_cur'], s['kf_valid'], s['last_xyz'], s['last_desc'], s['last_angle'], s['min_dist'], s['max_dist'], th,
+                                              orb_dist, ori, s['cur_mp'])
+        assert nm_g == nm_o and np.array_equal(mp_g, mp_o)
+        assert nm_o > 20
+        assert np.array_equal(mp_g[s['cur_mp'] >= 0], s['cur_mp'][s['cur_mp'] >= 0])        # keypoints that already held a map point are never touched
