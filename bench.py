@@ -469,7 +469,7 @@ def main():
     achieved = dom_bytes / (all_ms[dom] * 1e-3) / 1e9
     traffic = None
     try:        # dram__bytes_read + write of that kernel from the committed ncu --set full capture (profiles/), per launch
-        txt = open(os.path.join(ROOT, 'profiles', 'r01c_ncu_full_summary.txt')).read().split('=== ')
+        txt = open(os.path.join(ROOT, 'profiles', 'r01d_ncu_full_summary.txt')).read().split('=== ')
         blk = [b for b in txt if b.startswith(dom)][0]
         rd = float([l for l in blk.splitlines() if 'dram__bytes_read.sum' in l][0].split()[-1]); wr = float([l for l in blk.splitlines() if 'dram__bytes_write.sum' in l][0].split()[-1])
         traffic = int((rd + wr) * 1e6)          # the summary prints Mbyte for a 512-frame launch
