@@ -43,6 +43,23 @@ TH = 15.0                              # Tracking.cc:919-923 (RGB-D)
 LAUNCHES_PER_STEP = 18 + 12 + 1 + 3 + 1    # extract (7 resize, FAST, quadtree, 8 blur, describe) + LK (3 pyrDown, 4 Scharr, 4 border, track) + RANSAC F + depth lookup/dyn-reject/compact + match
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything libraries print there (e.g. the NCCL version banner) is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + '\n').encode())
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -221,7 +238,7 @@ def run_reference(args):
                        'frames_per_step': per_step, 'note': 'CPU oracle port of the reference path (the reference itself needs OpenCV/ROS: unbuildable here)'},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': '%d frames per step x %d steps' % (per_step, args.steps)},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -235,6 +252,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=48, help='frames of the cpu_baseline sample')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -529,7 +547,7 @@ def main():
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps, 'roofline': roofline, 'cpu_baseline': cpu}
         if bcast_ms is not None:
             line['config']['startup_broadcast_ms'] = bcast_ms
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
