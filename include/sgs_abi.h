@@ -262,6 +262,14 @@ SGS_API int sgs_stereo_from_depth_batch_device(const sgs_keypoint* d_kps, const 
                                                int nframes, const float* d_depth, size_t depth_frame_stride, int depth_pitch, float bf,
                                                float* d_u_right, float* d_depth_out, void* stream);
 SGS_API int sgs_frustum_batch_device(const sgs_frustum_batch* args, int nframes, void* stream);
+/* Frame::UndistortKeyPoints (src/Frame.cc:654-684) = cv::undistortPoints(pts, K, distCoef, Mat(), K), distCoef = (k1, k2, p1, p2, k3);
+ * k1 == 0 copies the keypoints, like the reference.  sgs_image_bounds: Frame::ComputeImageBounds (:686-714) -> min_x, min_y, max_x, max_y. */
+SGS_API int sgs_undistort_batch_device(const sgs_keypoint* d_kps, const int32_t* d_counts, int cap, int nframes, float fx, float fy, float cx,
+                                       float cy, const float* dist_coef5, sgs_keypoint* d_kps_un, void* stream);
+SGS_API int sgs_undistort_points(const float* xy, int n, float fx, float fy, float cx, float cy, const float* dist_coef5, float* out_xy,
+                                 int device);
+SGS_API int sgs_image_bounds(int width, int height, float fx, float fy, float cx, float cy, const float* dist_coef5, float* bounds4,
+                             int device);
 /* host-pointer variant, one frame, n points (arrays of n / 3 n elements) */
 SGS_API int sgs_frustum(const sgs_camera* cam, const float* tcw, int n, const float* xyz, const float* normal, const float* min_dist,
                         const float* max_dist, float viewing_cos_limit, uint8_t* inview, float* proj_x, float* proj_y, float* proj_xr,

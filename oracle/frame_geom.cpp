@@ -66,3 +66,28 @@ SGO_API int sgo_is_in_frustum(const float* Tcw, const float* cam, int nlevels, f
     }
     return cnt;
 }
+
+// cv::undistortPoints(src, dst, K, distCoef(k1,k2,p1,p2,k3), cv::Mat(), K) as called by Frame::UndistortKeyPoints (src/Frame.cc:654-684) and
+// Frame::ComputeImageBounds (:686-714).  Restates calib3d/undistort.cpp cvUndistortPointsInternal: double arithmetic, 5 fixed-point
+// iterations (the default criteria), then re-projection with P = K.  Pinned bit-exactly against cv2.undistortPoints (tests/test_frame_geom.py).
+SGO_API int sgo_undistort_points(const float* xy, int n, float fxf, float fyf, float cxf, float cyf, const float* dist5, float* out_xy) {
+    const double fx = fxf, fy = fyf, cx = cxf, cy = cyf, ifx = 1. / fx, ify = 1. / fy;
+    const double k0 = dist5[0], k1 = dist5[1], p1 = dist5[2], p2 = dist5[3], k2 = dist5[4];     // OpenCV order: k1 k2 p1 p2 k3
+    for (int i = 0; i < n; i++) {
+        double x = xy[2 * i], y = xy[2 * i + 1];
+        const double u = x, v = y;
+        x = (x - cx) * ifx; y = (y - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((0 * r2 + 0) * r2 + 0) * r2) / (1 + ((k2 * r2 + k1) * r2 + k0) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x) + 0 * r2 + 0 * r2 * r2;
+            const double deltaY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y + 0 * r2 + 0 * r2 * r2;
+            x = (x0 - deltaX) * icdist; y = (y0 - deltaY) * icdist;
+        }
+        const double xx = fx * x + 0 * y + cx, yy = 0 * x + fy * y + cy, ww = 1. / (0 * x + 0 * y + 1);
+        out_xy[2 * i] = (float)(xx * ww); out_xy[2 * i + 1] = (float)(yy * ww);
+    }
+    return 0;
+}

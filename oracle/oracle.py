@@ -339,3 +339,11 @@ def is_in_frustum(Tcw, cam, nlevels, log_scale_factor, xyz, normal, min_dist, ma
     lib().sgo_is_in_frustum(_p(T), _p(cm), int(nlevels), C.c_float(log_scale_factor), C.c_float(viewing_cos_limit), n, _p(X), _p(N), _p(mn), _p(mx),
                             _p(out['inview']), _p(out['proj_x']), _p(out['proj_y']), _p(out['proj_xr']), _p(out['level']), _p(out['view_cos']))
     return out
+
+
+def undistort_points(xy, fx, fy, cx, cy, dist5):
+    """cv::undistortPoints(xy, K, dist, R=I, P=K) (Frame::UndistortKeyPoints, src/Frame.cc:654-684)."""
+    a = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); d = np.ascontiguousarray(dist5, np.float32)
+    out = np.zeros_like(a)
+    lib().sgo_undistort_points(_p(a), len(a), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(d), _p(out))
+    return out

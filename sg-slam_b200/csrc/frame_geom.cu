@@ -29,6 +29,44 @@ __global__ void __launch_bounds__(256) stereo_from_depth_kernel(const sgs_keypoi
     if (depth_out) depth_out[o] = dz;
 }
 
+// cv::undistortPoints(pt, K, distCoef, R = I, P = K) for one point: calib3d cvUndistortPointsInternal -- double arithmetic, five fixed-point
+// iterations (the default criteria), re-projection with K; every product and sum individually rounded (no FMA), the zero-coefficient terms of
+// OpenCV's general expressions are kept so that the roundings are the same.  Bit-exact against cv2.undistortPoints.
+__device__ __forceinline__ float2 undistort_point(float xf, float yf, double fx, double fy, double cx, double cy, double k0, double k1, double p1, double p2,
+                                                  double k2) {
+    const double ifx = 1. / fx, ify = 1. / fy;
+    double x = xf, y = yf;
+    const double u = x, v = y;
+    x = (x - cx) * ifx; y = (y - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icdist = 1. / (1 + ((k2 * r2 + k1) * r2 + k0) * r2);       // numerator 1 + ((k7 r2 + k6) r2 + k5) r2 with k5..k7 = 0 is exactly 1
+        if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+        const double deltaX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x), deltaY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+        x = (x0 - deltaX) * icdist; y = (y0 - deltaY) * icdist;
+    }
+    return make_float2((float)(fx * x + cx), (float)(fy * y + cy));          // (xx * ww) with ww = 1/(0 x + 0 y + 1) = 1
+}
+
+__global__ void __launch_bounds__(256) undistort_kernel(const sgs_keypoint* __restrict__ kps, const float2* __restrict__ xy_in, const int32_t* __restrict__ counts,
+                                                        int cap, float fx, float fy, float cx, float cy, float k0, float k1, float p1, float p2, float k2,
+                                                        sgs_keypoint* __restrict__ kps_un, float2* __restrict__ xy_out) {
+    const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    const int n = counts ? min(counts[f], cap) : cap;
+    if (i >= n) return;
+    const int64_t o = (int64_t)f * cap + i;
+    if (kps) {
+        sgs_keypoint k = kps[o];
+        const float2 r = k0 == 0.f ? make_float2(k.x, k.y) : undistort_point(k.x, k.y, fx, fy, cx, cy, k0, k1, p1, p2, k2);       // src/Frame.cc:656-660
+        k.x = r.x; k.y = r.y;
+        kps_un[o] = k;
+    } else {
+        const float2 q = xy_in[o];
+        xy_out[o] = undistort_point(q.x, q.y, fx, fy, cx, cy, k0, k1, p1, p2, k2);
+    }
+}
+
 __global__ void __launch_bounds__(256) frustum_kernel(const sgs_frustum_batch A, int nlevels, float log_sf) {
     const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
     const int n = min(A.mp_n[f], A.point_cap);
@@ -84,6 +122,44 @@ SGS_API int sgs_stereo_from_depth_batch_device(const sgs_keypoint* d_kps, const 
     stereo_from_depth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_kps, d_kps_un, d_counts, cap, d_depth, (int64_t)depth_frame_stride, depth_pitch, bf,
                                                                      d_u_right, d_depth_out);
     SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+
+SGS_API int sgs_undistort_batch_device(const sgs_keypoint* d_kps, const int32_t* d_counts, int cap, int nframes, float fx, float fy, float cx, float cy,
+                                       const float* dist_coef5, sgs_keypoint* d_kps_un, void* stream) {
+    if (!d_kps || !d_counts || !d_kps_un || !dist_coef5 || cap < 1 || nframes < 1) { set_error("sgs_undistort_batch_device: bad argument"); return SGS_ERR_INVALID; }
+    dim3 grid((cap + 255) / 256, nframes);
+    undistort_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_kps, nullptr, d_counts, cap, fx, fy, cx, cy, dist_coef5[0], dist_coef5[1], dist_coef5[2],
+                                                             dist_coef5[3], dist_coef5[4], d_kps_un, nullptr);
+    SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+
+SGS_API int sgs_undistort_points(const float* xy, int n, float fx, float fy, float cx, float cy, const float* dist_coef5, float* out_xy, int device) {
+    if (n < 0 || !dist_coef5 || (n > 0 && (!xy || !out_xy))) { set_error("sgs_undistort_points: bad argument"); return SGS_ERR_INVALID; }
+    if (n == 0) return SGS_OK;
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    float2* d = nullptr;
+    SGS_CUDA_TRY(cudaMalloc(&d, 16 * (size_t)n));
+    cudaMemcpy(d, xy, 8 * (size_t)n, cudaMemcpyHostToDevice);
+    undistort_kernel<<<dim3((n + 255) / 256, 1), 256>>>(nullptr, d, nullptr, n, fx, fy, cx, cy, dist_coef5[0], dist_coef5[1], dist_coef5[2], dist_coef5[3],
+                                                        dist_coef5[4], nullptr, d + n);
+    cudaError_t e = cudaMemcpy(out_xy, d + n, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error("sgs_undistort_points: %s", cudaGetErrorString(e)); return SGS_ERR_CUDA; }
+    return SGS_OK;
+}
+
+// Frame::ComputeImageBounds (src/Frame.cc:686-714): mnMinX, mnMinY, mnMaxX, mnMaxY from the undistorted image corners
+SGS_API int sgs_image_bounds(int width, int height, float fx, float fy, float cx, float cy, const float* dist_coef5, float* bounds4, int device) {
+    if (!dist_coef5 || !bounds4) { set_error("sgs_image_bounds: NULL"); return SGS_ERR_INVALID; }
+    if (dist_coef5[0] == 0.0f) { bounds4[0] = 0.f; bounds4[1] = 0.f; bounds4[2] = (float)width; bounds4[3] = (float)height; return SGS_OK; }
+    const float c[8] = {0.f, 0.f, (float)width, 0.f, 0.f, (float)height, (float)width, (float)height};
+    float u[8];
+    const int rc = sgs_undistort_points(c, 4, fx, fy, cx, cy, dist_coef5, u, device);
+    if (rc != SGS_OK) return rc;
+    bounds4[0] = u[0] < u[4] ? u[0] : u[4]; bounds4[2] = u[2] > u[6] ? u[2] : u[6];
+    bounds4[1] = u[1] < u[3] ? u[1] : u[3]; bounds4[3] = u[5] > u[7] ? u[5] : u[7];
     return SGS_OK;
 }
 

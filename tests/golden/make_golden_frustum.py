@@ -68,5 +68,20 @@ def main():
     print('in view', int(out['inview'].sum()), 'of', n)
 
 
+def make_undistort():
+    """tests/golden/undistort.npz: cv2.undistortPoints(pts, K, D, None, K) with the TUM1 / TUM2 calibrations of the reference's Examples/*.yaml."""
+    rs = np.random.RandomState(3)
+    out = {}
+    for name, (fx, fy, cx, cy, d) in {'TUM1': (517.306408, 516.469215, 318.643040, 255.313989, [0.262383, -0.953104, -0.005358, 0.002628, 1.163314]),
+                                       'TUM2': (520.908620, 521.007327, 325.141442, 249.701764, [0.231222, -0.784899, -0.003257, -0.000105, 0.917205])}.items():
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32); D = np.array(d, np.float32)
+        pts = np.c_[rs.uniform(0, 640, 1500), rs.uniform(0, 480, 1500)].astype(np.float32)
+        pts = np.r_[pts, np.array([[0, 0], [640, 0], [0, 480], [640, 480]], np.float32)]
+        out[name + '_K'] = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], np.float32); out[name + '_D'] = D; out[name + '_pts'] = pts
+        out[name + '_und'] = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+    np.savez_compressed(os.path.join(HERE, 'undistort.npz'), cv2_version=np.array(cv2.__version__), **out)
+
+
 if __name__ == '__main__':
     main()
+    make_undistort()

@@ -30,3 +30,11 @@ def test_stereo_from_rgbd():
     ur, dz = O.stereo_from_rgbd(k, G['depth'], 40.0)
     assert ur.tobytes() == G['u_right'].tobytes() and dz.tobytes() == G['depth_out'].tobytes()
     assert (ur == -1).sum() > 10
+
+
+def test_undistort_points_bit_exact_vs_cv2():
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'undistort.npz'))
+    for name in ('TUM1', 'TUM2'):
+        K = g[name + '_K']
+        got = O.undistort_points(g[name + '_pts'], K[0], K[1], K[2], K[3], g[name + '_D'])
+        assert got.tobytes() == g[name + '_und'].tobytes(), name

@@ -106,3 +106,33 @@ def test_stereo_from_depth():
     torch.cuda.synchronize()
     ru, _ = O.stereo_from_rgbd(kps[1, :counts[1]], depth[0], 40.0)
     assert ur2.cpu().numpy()[1, :counts[1]].tobytes() == ru.tobytes()
+
+
+def test_undistort_and_image_bounds(golden_dir):
+    import torch
+    g = np.load(os.path.join(golden_dir, 'undistort.npz'))
+    v = C.c_void_p
+    for name in ('TUM1', 'TUM2'):
+        K = g[name + '_K']; D = np.ascontiguousarray(g[name + '_D'], np.float32); pts = np.ascontiguousarray(g[name + '_pts'])
+        out = np.zeros_like(pts)
+        B.check(B.lib().sgs_undistort_points(pts.ctypes.data_as(v), len(pts), C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]), C.c_float(K[3]),
+                                             D.ctypes.data_as(v), out.ctypes.data_as(v), 0))
+        assert out.tobytes() == g[name + '_und'].tobytes(), name
+        b = np.zeros(4, np.float32)
+        B.check(B.lib().sgs_image_bounds(640, 480, C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]), C.c_float(K[3]), D.ctypes.data_as(v), b.ctypes.data_as(v), 0))
+        c = g[name + '_und'][-4:]          # corners (0,0) (w,0) (0,h) (w,h)
+        assert b[0] == min(c[0, 0], c[2, 0]) and b[2] == max(c[1, 0], c[3, 0]) and b[1] == min(c[0, 1], c[1, 1]) and b[3] == max(c[2, 1], c[3, 1])
+        # batched keypoint form: two frames, the second shorter; everything but pt is copied
+        cap = len(pts)
+        kps = np.zeros((2, cap), B.KP_DTYPE); kps['x'] = pts[:, 0]; kps['y'] = pts[:, 1]; kps['octave'] = 3; kps['angle'] = 42.0
+        counts = np.array([cap, 100], np.int32)
+        dk = torch.from_numpy(kps.view(np.uint8).reshape(-1)).cuda(); dc = torch.from_numpy(counts).cuda(); du = torch.zeros_like(dk)
+        B.check(B.lib().sgs_undistort_batch_device(v(dk.data_ptr()), v(dc.data_ptr()), cap, 2, C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]), C.c_float(K[3]),
+                                                   D.ctypes.data_as(v), v(du.data_ptr()), v(0)))
+        torch.cuda.synchronize()
+        un = du.cpu().numpy().view(B.KP_DTYPE).reshape(2, cap)
+        assert np.stack([un['x'][0], un['y'][0]], 1).tobytes() == g[name + '_und'].tobytes()
+        assert np.array_equal(un['octave'][1, :100], kps['octave'][1, :100]) and np.array_equal(un['x'][1, :100], un['x'][0, :100])
+    zero = np.zeros(5, np.float32); b = np.zeros(4, np.float32)
+    B.check(B.lib().sgs_image_bounds(640, 480, C.c_float(500), C.c_float(500), C.c_float(320), C.c_float(240), zero.ctypes.data_as(v), b.ctypes.data_as(v), 0))
+    assert list(b) == [0, 0, 640, 480]
