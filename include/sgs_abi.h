@@ -238,6 +238,34 @@ typedef struct sgs_localmap_batch {       /* SearchByProjection(Frame&, vector<M
 SGS_API int sgs_match_project_localmap_batch_device(sgs_matcher* m, const sgs_localmap_batch* args, int nframes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Bag of words (tracking fallback, Tracking::TrackReferenceKeyFrame src/Tracking.cc:858-904):
+ *   sgs_vocabulary_create       : the DBoW2 tree as flat arrays -- parent[i] of node i in node-id order (node 0 = root; DBoW2 appends children
+ *                                 to their parent in that order, TemplatedVocabulary.h:1351-1420 / 1467-1508), node descriptors [nnodes][32],
+ *                                 node weights (leaves: the TF-IDF word weight).  Word ids number the leaves in node-id order.
+ *   sgs_bow_transform_batch_device : TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) per feature
+ *                                 (Frame::ComputeBoW, src/Frame.cc:421-428, levelsup = 4): word id, word weight, node id at level L - levelsup
+ *                                 (0 = root when that level is <= 0).  A feature enters the FeatureVector iff its weight is > 0.
+ *   sgs_match_bow_batch_device  : ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (src/ORBmatcher.cc:159-290) for `nframes`
+ *                                 (key frame, frame) pairs: match_f[j] = key-frame feature whose map point goes to frame feature j, or -1.
+ * ------------------------------------------------------------------------------------ */
+typedef struct sgs_vocabulary sgs_vocabulary;
+SGS_API int sgs_vocabulary_create(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* node_desc,
+                                  const double* node_weight, sgs_vocabulary** out);
+SGS_API void sgs_vocabulary_destroy(sgs_vocabulary* v);
+SGS_API int sgs_bow_transform_batch_device(const sgs_vocabulary* v, const uint8_t* d_desc, const int32_t* d_counts, int cap, int nframes,
+                                           int levelsup, int32_t* d_word, double* d_weight, int32_t* d_node, void* stream);
+typedef struct sgs_bow_batch {
+    const int32_t* kf_node; const double* kf_weight;   /* [F][kf_cap] from sgs_bow_transform_batch_device on the key frame's descriptors */
+    const uint8_t* kf_valid;                             /* map point exists && !isBad() */
+    const uint8_t* kf_desc; const float* kf_angle; const int32_t* kf_n; int32_t kf_cap;
+    const int32_t* f_node; const double* f_weight; const uint8_t* f_desc; const float* f_angle; const int32_t* f_n; int32_t f_cap;
+    float nnratio; int32_t check_orientation;            /* 0.7 / true at src/Tracking.cc:865 */
+    int32_t* match_f;                                    /* out [F][f_cap] */
+    int32_t* nmatches;                                   /* out [F] */
+} sgs_bow_batch;
+SGS_API int sgs_match_bow_batch_device(const sgs_bow_batch* args, int nframes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Frame geometry between the extractor and the matchers (device pointers, `nframes` frames, work enqueued on `stream`):
  *   sgs_stereo_from_depth_batch_device : Frame::ComputeStereoFromRGBD (src/Frame.cc:893-914).  d_depth: float depth images
  *       [F][h][depth_pitch] (elements; depth_frame_stride 0 shares one image); d_kps_un NULL = undistorted keypoints equal the

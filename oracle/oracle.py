@@ -347,3 +347,43 @@ def undistort_points(xy, fx, fy, cx, cy, dist5):
     out = np.zeros_like(a)
     lib().sgo_undistort_points(_p(a), len(a), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(d), _p(out))
     return out
+
+
+class Vocabulary:
+    """DBoW2 vocabulary tree as flat arrays: parent[i] of node i (node 0 = root, parent -1), node descriptors [n,32], leaf weights."""
+
+    def __init__(self, k, L, parent, desc, weight):
+        self.k, self.L = k, L
+        self.parent = np.ascontiguousarray(parent, np.int32); self.desc = np.ascontiguousarray(desc, np.uint8); self.weight = np.ascontiguousarray(weight, np.float64)
+        lib().sgo_voc_create.restype = C.c_void_p
+        self.h = C.c_void_p(lib().sgo_voc_create(k, L, len(self.parent), _p(self.parent), _p(self.desc), _p(self.weight)))
+
+    def __del__(self):
+        try:
+            lib().sgo_voc_free(self.h)
+        except Exception:
+            pass
+
+    def transform(self, desc, levelsup=4):
+        """Per feature: (word id, weight, node id at level L - levelsup) -- TemplatedVocabulary::transform, Frame::ComputeBoW (src/Frame.cc:421-428)."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        word = np.zeros(len(d), np.int32); w = np.zeros(len(d), np.float64); node = np.zeros(len(d), np.int32)
+        lib().sgo_bow_transform(self.h, _p(d), len(d), int(levelsup), _p(word), _p(w), _p(node))
+        return word, w, node
+
+
+def bow_vector(word, weight):
+    n = len(word)
+    ow = np.zeros(n, np.int32); ov = np.zeros(n, np.float64)
+    c = lib().sgo_bow_vector(_p(np.ascontiguousarray(word, np.int32)), _p(np.ascontiguousarray(weight, np.float64)), n, _p(ow), _p(ov))
+    return ow[:c], ov[:c]
+
+
+def search_by_bow(kf_node, kf_weight, kf_valid, kf_desc, kf_angle, f_node, f_weight, f_desc, f_angle, nnratio=0.7, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:159-290): (nmatches, match_f[j] = key-frame feature index or -1)."""
+    a = [np.ascontiguousarray(kf_node, np.int32), np.ascontiguousarray(kf_weight, np.float64), np.ascontiguousarray(kf_valid, np.uint8),
+         np.ascontiguousarray(kf_desc, np.uint8), np.ascontiguousarray(kf_angle, np.float32)]
+    b = [np.ascontiguousarray(f_node, np.int32), np.ascontiguousarray(f_weight, np.float64), np.ascontiguousarray(f_desc, np.uint8), np.ascontiguousarray(f_angle, np.float32)]
+    m = np.zeros(len(b[0]), np.int32)
+    nm = lib().sgo_search_by_bow(len(a[0]), *[_p(x) for x in a], len(b[0]), *[_p(x) for x in b], C.c_float(nnratio), int(check_ori), _p(m))
+    return nm, m

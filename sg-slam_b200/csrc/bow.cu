@@ -1,0 +1,288 @@
+// bow.cu -- bag-of-words pieces of the tracking fallback path (Tracking::TrackReferenceKeyFrame, src/Tracking.cc:858-904):
+//   DBoW2::TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup)   Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1140-1272
+//       (Frame::ComputeBoW, src/Frame.cc:421-428, levelsup = 4): greedy descent of the k-ary tree by Hamming distance, first child wins ties;
+//   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)                           src/ORBmatcher.cc:159-290.
+// The vocabulary lives on the device as flat arrays (the table the multi-GPU bench broadcasts once at start-up).
+//   transform : one warp per descriptor, one lane per child, the arg-min over (distance, child order) by redux.sync.
+//   SearchByBoW: one block per (key frame, frame) pair.  Both feature sets are sorted by (node id, feature index) -- the order of
+//       DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>).  A frame feature belongs to exactly one node, so node buckets are
+//       independent: each bucket is handled by one warp, key-frame features in order (the claims of earlier ones are visible), lanes
+//       over the frame features of the bucket; best / second-best by two warp reductions.  Rotation histogram as in the other matchers.
+// Integer work: bit-exact against the CPU restatement.
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "sgs_common.h"
+
+struct sgs_vocabulary {
+    int device = 0, k = 0, L = 0, nnodes = 0;
+    int32_t* d_first = nullptr; int32_t* d_count = nullptr; int32_t* d_children = nullptr; int32_t* d_word = nullptr;
+    uint8_t* d_desc = nullptr; double* d_weight = nullptr;
+};
+
+namespace sgs {
+
+constexpr int kBowThreads = 256;
+constexpr int kBowThLow = 50, kBowHisto = 30;      // TH_LOW, HISTO_LENGTH (src/ORBmatcher.cc:37-39)
+
+struct VocDev { const int32_t* first; const int32_t* count; const int32_t* children; const int32_t* word; const uint8_t* desc; const double* weight; int L; };
+
+__device__ __forceinline__ int popc256v(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) +
+           __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(256) bow_transform_kernel(const VocDev V, const uint8_t* __restrict__ desc, const int32_t* __restrict__ counts, int cap,
+                                                            int levelsup, int32_t* __restrict__ word, double* __restrict__ weight, int32_t* __restrict__ node) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int n = counts ? min(counts[f], cap) : cap;
+    if (i >= n) return;
+    const int64_t o = (int64_t)f * cap + i;
+    const uint4* d = reinterpret_cast<const uint4*>(desc + 32 * o);
+    const uint4 d0 = __ldg(d), d1 = __ldg(d + 1);
+    const int nid_level = V.L - levelsup;
+    int cur = 0, level = 0, nid = 0;
+    int nch = V.count[0];
+    while (nch > 0) {
+        ++level;
+        const int first = V.first[cur];
+        unsigned best = 0xffffffffu;
+        for (int c0 = 0; c0 < nch; c0 += 32) {          // children in order; (distance << 12 | order) keeps the first of equal distances
+            const int c = c0 + lane;
+            if (c < nch) {
+                const uint4* cd = reinterpret_cast<const uint4*>(V.desc + 32 * (int64_t)__ldg(V.children + first + c));
+                best = min(best, ((unsigned)popc256v(d0, d1, __ldg(cd), __ldg(cd + 1)) << 12) | (unsigned)c);
+            }
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        cur = __ldg(V.children + first + (int)(best & 0xfffu));
+        if (level == nid_level) nid = cur;
+        nch = V.count[cur];
+    }
+    if (lane == 0) { word[o] = V.word[cur]; weight[o] = V.weight[cur]; node[o] = nid; }
+}
+
+struct BowArgs {
+    const int32_t* kf_node; const double* kf_weight; const uint8_t* kf_valid; const uint8_t* kf_desc; const float* kf_angle; const int32_t* kf_n; int kf_cap;
+    const int32_t* f_node; const double* f_weight; const uint8_t* f_desc; const float* f_angle; const int32_t* f_n; int f_cap;
+    float nnratio; int check_ori;
+    int32_t* match_f; int32_t* nmatches;
+    int kf_pow2, f_pow2;
+};
+
+__device__ void bow_bitonic(uint64_t* keys, int n_pow2) {         // ascending, n_pow2 a power of two, padding = all ones
+    for (int k = 2; k <= n_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const uint64_t a = keys[i], b = keys[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// keys: (node id << 32 | feature index)
+__global__ void __launch_bounds__(kBowThreads) bow_search_kernel(const BowArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* kkey = reinterpret_cast<uint64_t*>(smem);            // [kf_pow2]
+    uint64_t* fkey = kkey + A.kf_pow2;                              // [f_pow2]
+    int32_t* run_start = reinterpret_cast<int32_t*>(fkey + A.f_pow2);   // [kf_pow2 + 1]
+    int32_t* events = run_start + A.kf_pow2 + 1;                    // [f_cap] (bin << 16 | frame feature)
+    uint8_t* taken = reinterpret_cast<uint8_t*>(events + A.f_cap);  // [f_cap]
+    __shared__ int hist[kBowHisto];
+    __shared__ int s_nk, s_nf, s_nruns, s_nevent, s_nmatch;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nk_all = min(A.kf_n[f], A.kf_cap), nf_all = min(A.f_n[f], A.f_cap);
+    const int64_t ko = (int64_t)f * A.kf_cap, fo = (int64_t)f * A.f_cap;
+    if (tid == 0) { s_nk = 0; s_nf = 0; s_nruns = 0; s_nevent = 0; s_nmatch = 0; }
+    if (tid < kBowHisto) hist[tid] = 0;
+    for (int i = tid; i < A.kf_pow2; i += blockDim.x) {
+        uint64_t key = ~0ull;
+        if (i < nk_all && A.kf_weight[ko + i] > 0 && A.kf_valid[ko + i]) key = ((uint64_t)(uint32_t)A.kf_node[ko + i] << 32) | (uint32_t)i;      // invalid map points never act
+        kkey[i] = key;
+    }
+    for (int j = tid; j < A.f_pow2; j += blockDim.x) {
+        uint64_t key = ~0ull;
+        if (j < nf_all && A.f_weight[fo + j] > 0) key = ((uint64_t)(uint32_t)A.f_node[fo + j] << 32) | (uint32_t)j;
+        fkey[j] = key;
+    }
+    for (int j = tid; j < A.f_cap; j += blockDim.x) { taken[j] = 0; A.match_f[fo + j] = -1; }
+    __syncthreads();
+    bow_bitonic(kkey, A.kf_pow2);
+    bow_bitonic(fkey, A.f_pow2);
+    // number of live entries and the starts of the key-frame node runs
+    for (int i = tid; i < A.kf_pow2; i += blockDim.x) {
+        if (kkey[i] != ~0ull) {
+            if (i + 1 == A.kf_pow2 || kkey[i + 1] == ~0ull) s_nk = i + 1;
+            if (i == 0 || (kkey[i - 1] >> 32) != (kkey[i] >> 32)) run_start[atomicAdd(&s_nruns, 1)] = i;      // order of the runs does not matter
+        }
+    }
+    for (int j = tid; j < A.f_pow2; j += blockDim.x)
+        if (fkey[j] != ~0ull && (j + 1 == A.f_pow2 || fkey[j + 1] == ~0ull)) s_nf = j + 1;
+    __syncthreads();
+    const int nk = s_nk, nf = s_nf, nruns = s_nruns;
+    const uint4* kdesc = reinterpret_cast<const uint4*>(A.kf_desc + 32 * ko);
+    const uint4* fdesc = reinterpret_cast<const uint4*>(A.f_desc + 32 * fo);
+    int nmatch = 0;
+    for (int r = warp; r < nruns; r += kBowThreads / 32) {
+        const int ks = run_start[r];
+        const uint32_t nodeid = (uint32_t)(kkey[ks] >> 32);
+        // the frame's bucket of this node: [lo, hi) in fkey
+        int lo = 0, hi = nf;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((uint32_t)(fkey[mid] >> 32) < nodeid) lo = mid + 1; else hi = mid; }
+        const int b0 = lo;
+        hi = nf;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((uint32_t)(fkey[mid] >> 32) <= nodeid) lo = mid + 1; else hi = mid; }
+        const int b1 = lo;
+        if (b1 == b0) continue;
+        for (int ki = ks; ki < nk && (uint32_t)(kkey[ki] >> 32) == nodeid; ++ki) {
+            const int realK = (int)(uint32_t)kkey[ki];
+            const uint4 k0 = __ldg(kdesc + 2 * realK), k1 = __ldg(kdesc + 2 * realK + 1);
+            unsigned key1 = 0xffffffffu; int d2 = 256;              // local best (distance << 16 | bucket position), local second-best distance
+            for (int p = b0 + lane; p < b1; p += 32) {
+                const int realF = (int)(uint32_t)fkey[p];
+                if (taken[realF]) continue;                          // :214
+                const int dist = popc256v(k0, k1, __ldg(fdesc + 2 * realF), __ldg(fdesc + 2 * realF + 1));
+                const unsigned key = ((unsigned)dist << 16) | (unsigned)(p - b0);
+                if (key < key1) { d2 = min(d2, (int)(key1 >> 16)); key1 = key; }
+                else d2 = min(d2, dist);
+            }
+            const unsigned K1 = __reduce_min_sync(0xffffffffu, key1);
+            const int c2 = key1 == K1 ? d2 : min((int)(key1 >> 16), 256);
+            const int best2 = __reduce_min_sync(0xffffffffu, c2 > 256 ? 256 : c2);
+            const int best1 = K1 == 0xffffffffu ? 256 : (int)(K1 >> 16);
+            if (best1 <= kBowThLow && (float)best1 < __fmul_rn(A.nnratio, (float)best2)) {        // :237-240
+                const int realF = (int)(uint32_t)fkey[b0 + (int)(K1 & 0xffffu)];
+                if (lane == 0) {
+                    taken[realF] = 1;
+                    A.match_f[fo + realF] = realK;
+                    if (A.check_ori) {
+                        float rot = __fsub_rn(A.kf_angle[ko + realK], A.f_angle[fo + realF]);
+                        if (rot < 0.f) rot = __fadd_rn(rot, 360.f);
+                        int bin = (int)roundf(__fmul_rn(rot, (float)kBowHisto / 360.0f));
+                        if (bin == kBowHisto) bin = 0;
+                        atomicAdd(&hist[bin], 1);
+                        events[atomicAdd(&s_nevent, 1)] = (bin << 16) | realF;
+                    }
+                    ++nmatch;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (lane == 0 && nmatch) atomicAdd(&s_nmatch, nmatch);
+    __syncthreads();
+    if (A.check_ori) {
+        // ComputeThreeMaxima (src/ORBmatcher.cc:1603-1645) on the bin counts, then drop the matches outside the three main bins
+        __shared__ int s_i1, s_i2, s_i3;
+        if (tid == 0) {
+            int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < kBowHisto; ++i) {
+                const int s = hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+                else if (s > max3) { max3 = s; i3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) i3 = -1;
+            s_i1 = i1; s_i2 = i2; s_i3 = i3;
+        }
+        __syncthreads();
+        int removed = 0;
+        for (int e = tid; e < s_nevent; e += blockDim.x) {
+            const int bin = events[e] >> 16, j = events[e] & 0xffff;
+            if (bin != s_i1 && bin != s_i2 && bin != s_i3) { A.match_f[fo + j] = -1; ++removed; }
+        }
+        if (removed) atomicSub(&s_nmatch, removed);
+        __syncthreads();
+    }
+    if (tid == 0) A.nmatches[f] = s_nmatch;
+}
+
+static int pow2_ge(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+}  // namespace sgs
+
+using namespace sgs;
+
+extern "C" {
+
+SGS_API void sgs_vocabulary_destroy(sgs_vocabulary* v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    cudaFree(v->d_first); cudaFree(v->d_count); cudaFree(v->d_children); cudaFree(v->d_word); cudaFree(v->d_desc); cudaFree(v->d_weight);
+    delete v;
+}
+
+SGS_API int sgs_vocabulary_create(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* node_desc, const double* node_weight,
+                                  sgs_vocabulary** out) {
+    if (!out || !parent || !node_desc || !node_weight || nnodes < 2 || k < 2 || L < 1) { set_error("sgs_vocabulary_create: bad argument"); return SGS_ERR_INVALID; }
+    *out = nullptr;
+    std::vector<int32_t> count(nnodes, 0), first(nnodes, 0), children(nnodes - 1), word(nnodes, -1), fill(nnodes, 0);
+    for (int i = 1; i < nnodes; ++i) {
+        if (parent[i] < 0 || parent[i] >= i) { set_error("sgs_vocabulary_create: parent[%d] = %d must name an earlier node", i, parent[i]); return SGS_ERR_INVALID; }
+        count[parent[i]]++;
+    }
+    if (count[0] == 0) { set_error("sgs_vocabulary_create: the root has no children"); return SGS_ERR_INVALID; }
+    int acc = 0;
+    for (int i = 0; i < nnodes; ++i) { first[i] = acc; acc += count[i]; if (count[i] > 4096) { set_error("sgs_vocabulary_create: more than 4096 children"); return SGS_ERR_UNSUPPORTED; } }
+    for (int i = 1; i < nnodes; ++i) children[first[parent[i]] + fill[parent[i]]++] = i;      // children in node-id order, as DBoW2 appends them while loading
+    int w = 0;
+    for (int i = 1; i < nnodes; ++i) if (count[i] == 0) word[i] = w++;
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    sgs_vocabulary* v = new sgs_vocabulary();
+    v->device = device; v->k = k; v->L = L; v->nnodes = nnodes;
+    cudaError_t e = cudaMalloc(&v->d_first, 4 * (size_t)nnodes);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_count, 4 * (size_t)nnodes);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_children, 4 * (size_t)nnodes);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_word, 4 * (size_t)nnodes);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_desc, 32 * (size_t)nnodes);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_weight, 8 * (size_t)nnodes);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_first, first.data(), 4 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_count, count.data(), 4 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_children, children.data(), 4 * (size_t)(nnodes - 1), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_word, word.data(), 4 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_desc, node_desc, 32 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_weight, node_weight, 8 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("sgs_vocabulary_create: %s", cudaGetErrorString(e)); sgs_vocabulary_destroy(v); return SGS_ERR_CUDA; }
+    *out = v;
+    return SGS_OK;
+}
+
+SGS_API int sgs_bow_transform_batch_device(const sgs_vocabulary* v, const uint8_t* d_desc, const int32_t* d_counts, int cap, int nframes, int levelsup,
+                                           int32_t* d_word, double* d_weight, int32_t* d_node, void* stream) {
+    if (!v || !d_desc || !d_word || !d_weight || !d_node || cap < 1 || nframes < 1) { set_error("sgs_bow_transform_batch_device: bad argument"); return SGS_ERR_INVALID; }
+    VocDev V{v->d_first, v->d_count, v->d_children, v->d_word, v->d_desc, v->d_weight, v->L};
+    dim3 grid((cap + 7) / 8, nframes);
+    bow_transform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(V, d_desc, d_counts, cap, levelsup, d_word, d_weight, d_node);
+    SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+
+SGS_API int sgs_match_bow_batch_device(const sgs_bow_batch* a, int nframes, void* stream) {
+    if (!a || !a->kf_node || !a->kf_weight || !a->kf_valid || !a->kf_desc || !a->kf_angle || !a->kf_n || !a->f_node || !a->f_weight || !a->f_desc || !a->f_angle ||
+        !a->f_n || !a->match_f || !a->nmatches || nframes < 1) { set_error("sgs_match_bow_batch_device: bad argument"); return SGS_ERR_INVALID; }
+    if (a->kf_cap < 1 || a->f_cap < 1 || a->kf_cap > 8192 || a->f_cap > 8192) { set_error("sgs_match_bow_batch_device: at most 8192 features per frame"); return SGS_ERR_UNSUPPORTED; }
+    BowArgs A;
+    A.kf_node = a->kf_node; A.kf_weight = a->kf_weight; A.kf_valid = a->kf_valid; A.kf_desc = a->kf_desc; A.kf_angle = a->kf_angle; A.kf_n = a->kf_n; A.kf_cap = a->kf_cap;
+    A.f_node = a->f_node; A.f_weight = a->f_weight; A.f_desc = a->f_desc; A.f_angle = a->f_angle; A.f_n = a->f_n; A.f_cap = a->f_cap;
+    A.nnratio = a->nnratio; A.check_ori = a->check_orientation; A.match_f = a->match_f; A.nmatches = a->nmatches;
+    A.kf_pow2 = pow2_ge(a->kf_cap); A.f_pow2 = pow2_ge(a->f_cap);
+    const size_t smem = 8 * (size_t)A.kf_pow2 + 8 * (size_t)A.f_pow2 + 4 * (size_t)(A.kf_pow2 + 1) + 4 * (size_t)A.f_cap + (size_t)A.f_cap + 16;
+    static size_t configured = 0;
+    if (smem > 40 * 1024 && smem > configured) {
+        SGS_CUDA_TRY(cudaFuncSetAttribute(bow_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    bow_search_kernel<<<nframes, kBowThreads, smem, (cudaStream_t)stream>>>(A);
+    SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+
+}  // extern "C"

@@ -52,6 +52,12 @@ class LastFrameBatch(C.Structure):
                 ('cur_mp', C.c_void_p), ('cur_mp_obs_in', C.c_void_p), ('nmatches', C.c_void_p), ('ncand', C.c_void_p)]
 
 
+class BowBatch(C.Structure):
+    _fields_ = [('kf_node', C.c_void_p), ('kf_weight', C.c_void_p), ('kf_valid', C.c_void_p), ('kf_desc', C.c_void_p), ('kf_angle', C.c_void_p), ('kf_n', C.c_void_p),
+                ('kf_cap', C.c_int32), ('f_node', C.c_void_p), ('f_weight', C.c_void_p), ('f_desc', C.c_void_p), ('f_angle', C.c_void_p), ('f_n', C.c_void_p),
+                ('f_cap', C.c_int32), ('nnratio', C.c_float), ('check_orientation', C.c_int32), ('match_f', C.c_void_p), ('nmatches', C.c_void_p)]
+
+
 class FrustumBatch(C.Structure):
     _fields_ = [('cam', Camera), ('tcw', C.c_void_p), ('mp_xyz', C.c_void_p), ('mp_normal', C.c_void_p), ('mp_min_dist', C.c_void_p), ('mp_max_dist', C.c_void_p),
                 ('mp_n', C.c_void_p), ('point_cap', C.c_int32), ('viewing_cos_limit', C.c_float), ('mp_inview', C.c_void_p), ('proj_x', C.c_void_p),
@@ -83,6 +89,7 @@ ABI_SYMBOLS = [
     'sgs_tracker_lk_device', 'sgs_tracker_prev_xy_device', 'sgs_tracker_track_lk', 'sgs_extractor_level0_device', 'sgs_memcpy_d2h',
     'sgs_lk_set_profiling', 'sgs_lk_stage_times', 'sgs_tracker_lk',
     'sgs_match_project_keyframe_batch_device', 'sgs_match_project_keyframe',
+    'sgs_vocabulary_create', 'sgs_vocabulary_destroy', 'sgs_bow_transform_batch_device', 'sgs_match_bow_batch_device',
     'sgs_stereo_from_depth_batch_device', 'sgs_frustum_batch_device', 'sgs_frustum', 'sgs_undistort_batch_device', 'sgs_undistort_points', 'sgs_image_bounds', 'sgs_tracker_stereo_device',
     'sgs_fundamental_ransac', 'sgs_fundamental_batch_device', 'sgs_tracker_fundamental_device', 'sgs_tracker_fundamental_device_ptr',
 ]

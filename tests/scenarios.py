@@ -144,3 +144,55 @@ def keyframe_scenario(seed, n_cur=1000, n_kf=1000, **kw):
     cur_mp = np.where(rng.rand(n_cur) < 0.1, 5000 + np.arange(n_cur), -1).astype(np.int32)
     s.update(kf_valid=(rng.rand(n_kf) < 0.9).astype(np.uint8), min_dist=mind, max_dist=maxd, cur_mp=cur_mp)
     return s
+
+
+def random_vocabulary(seed, k=10, L=3, stop_frac=0.02):
+    """A DBoW2-shaped vocabulary tree (k children per node, L levels, every leaf at level L) in DEPTH-FIRST node order like ORBvoc.txt:
+    parent[], node descriptors, leaf weights (a few leaves have weight 0 = stopped words).  Children descriptors are noisy copies of the
+    parent's so that the greedy descent is meaningful, with some exact ties between siblings."""
+    rng = np.random.RandomState(seed)
+    parent = [-1]; desc = [np.zeros(32, np.uint8)]; level = [0]
+
+    def grow(pid, lvl):
+        base = np.unpackbits(desc[pid]) if lvl > 0 else rng.randint(0, 2, 256).astype(np.uint8)
+        prev = None
+        for c in range(k):
+            bits = base.copy()
+            nfl = rng.randint(20, 70)
+            bits[rng.choice(256, nfl, replace=False)] ^= 1
+            d = np.packbits(bits)
+            if prev is not None and rng.rand() < 0.05:
+                d = prev.copy()                                  # identical siblings: the first one must win
+            prev = d
+            nid = len(parent)
+            parent.append(pid); desc.append(d); level.append(lvl + 1)
+            if lvl + 1 < L:
+                grow(nid, lvl + 1)
+    grow(0, 0)
+    parent = np.array(parent, np.int32); desc = np.stack(desc); level = np.array(level)
+    weight = np.zeros(len(parent), np.float64)
+    leaves = level == L
+    weight[leaves] = rng.uniform(0.5, 9.0, int(leaves.sum()))
+    weight[leaves & (rng.rand(len(parent)) < stop_frac)] = 0.0
+    return dict(k=k, L=L, parent=parent, desc=desc, weight=weight)
+
+
+def bow_pair_scenario(seed, voc, n_kf=1000, n_f=1000, flips=40):
+    """Key frame and frame descriptors that share structure: each frame feature is a noisy copy of some key-frame feature (several frame
+    features may copy the same one, so claims and ratio tests matter); descriptors sit near vocabulary leaves."""
+    rng = np.random.RandomState(seed)
+    leaves = np.nonzero(voc['weight'] > 0)[0]
+    src = voc['desc'][leaves[rng.randint(0, len(leaves), n_kf)]]
+    bits = np.unpackbits(src, axis=1)
+    for i in range(n_kf):
+        bits[i, rng.choice(256, rng.randint(0, 30), replace=False)] ^= 1
+    kf_desc = np.packbits(bits, axis=1)
+    tgt = rng.randint(0, n_kf, n_f)
+    fb = np.unpackbits(kf_desc[tgt], axis=1)
+    for j in range(n_f):
+        fb[j, rng.choice(256, rng.randint(0, flips + 1), replace=False)] ^= 1
+    f_desc = np.packbits(fb, axis=1)
+    kf_angle = rng.uniform(0, 360, n_kf).astype(np.float32)
+    f_angle = ((kf_angle[tgt] - 25 + rng.normal(0, 6, n_f) + (rng.rand(n_f) < 0.15) * rng.uniform(0, 360, n_f)) % 360).astype(np.float32)
+    kf_valid = (rng.rand(n_kf) < 0.85).astype(np.uint8)
+    return dict(kf_desc=kf_desc, f_desc=f_desc, kf_angle=kf_angle, f_angle=f_angle, kf_valid=kf_valid)
