@@ -305,13 +305,23 @@ def main():
     keys_h = ['ur', 'boxes', 'nb', 'have', 'lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln', 'T', 'pidx']
     hp = {k: torch.from_numpy(np.ascontiguousarray(ti[k])).pin_memory() for k in keys_h}
     dv = {k: t.cuda(non_blocking=True) for k, t in hp.items()}
+    # shared read-only database: an ORBvoc-shaped vocabulary (k = 10, L = 6: 1,111,111 nodes x 32 B = 35.6 MB of node descriptors).
+    # Rank 0 owns it; with more than one rank it reaches the others through ONE ncclBroadcast at start-up (untimed, reported).
+    VOC_K, VOC_L = 10, 6
+    voc_nodes = (VOC_K ** (VOC_L + 1) - 1) // (VOC_K - 1)
+    voc = torch.from_numpy(synth.descriptors_s5(voc_nodes, 5) if rank == 0 else np.zeros((voc_nodes, 32), np.uint8)).cuda()
     bcast_ms = None
     if dist is not None:
-        voc = torch.from_numpy(synth.descriptors_s5(1_081_000, 5)).cuda()   # ORBvoc-sized node-descriptor table (34.6 MB), SURVEY section 5
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record(); dist.broadcast(voc, 0); e1.record(); torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
+    voc_parent = ((np.arange(voc_nodes, dtype=np.int64) - 1) // VOC_K).astype(np.int32); voc_parent[0] = -1        # complete k-ary tree in breadth-first node order
+    voc_weight = np.zeros(voc_nodes, np.float64); voc_weight[(voc_nodes - 1) // VOC_K:] = 1.0 + (np.arange(voc_nodes - (voc_nodes - 1) // VOC_K) % 7)
+    voc_h = v()
+    voc_host = voc.cpu().numpy()
+    B.check(L.sgs_vocabulary_create(local, VOC_K, VOC_L, voc_nodes, voc_parent.ctypes.data_as(v), voc_host.ctypes.data_as(v), voc_weight.ctypes.data_as(v), C.byref(voc_h)))
+    del voc_host
     h_out = dict(kps=pin((NB, cap, 28), torch.uint8), desc=pin((NB, cap, 32), torch.uint8), ur=pin((NB, cap), torch.float32), cnt=pin((NB,), torch.int32),
                  mp=pin((NB, cap), torch.int32), nm=pin((NB,), torch.int32))
     torch.cuda.synchronize()
@@ -397,6 +407,24 @@ def main():
     prev_dev = B.memcpy_d2h(np.zeros((NB, cap, 2), np.float32), pp.value)     # LK output of the last device step
     pF, pI = v(), v()
     B.check(L.sgs_tracker_fundamental_device_ptr(trk.h, C.byref(pF), C.byref(pI)))
+
+    # ---- Frame::ComputeBoW of the same batch (not part of the metric: reported beside it) ------------------------------------------------
+    bow_word = torch.zeros((NB, cap), dtype=torch.int32, device='cuda'); bow_w = torch.zeros((NB, cap), dtype=torch.float64, device='cuda')
+    bow_node = torch.zeros((NB, cap), dtype=torch.int32, device='cuda')
+    dk_, dd_, dc_, _cap = v(), v(), v(), C.c_int()
+    B.check(L.sgs_extractor_results_device(exh, C.byref(dk_), C.byref(dd_), C.byref(dc_), C.byref(_cap)))
+
+    def dev_bow():
+        B.check(L.sgs_bow_transform_batch_device(voc_h, dd_, dc_, cap, NB, 4, v(bow_word.data_ptr()), v(bow_w.data_ptr()), v(bow_node.data_ptr()), v(st.cuda_stream)))
+    with torch.cuda.stream(st):
+        dev_bow()
+        eb0, eb1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        eb0.record(st)
+        for _ in range(5):
+            dev_bow()
+        eb1.record(st)
+    torch.cuda.synchronize()
+    bow_ms = eb0.elapsed_time(eb1) / 5
 
     step_host()   # e2e warm-up; its outputs are also used for the parity spot-check below
     counts_after = h_out['cnt'].numpy().copy(); nmatch = h_out['nm'].numpy().copy()
@@ -540,9 +568,10 @@ def main():
                 'data': 'synthetic',
                 'config': {'workload': 'S2 walking_xyz-shaped synthetic 640x480 stream (BASELINE configs[1]), ORB 1000 features / 8 levels / 1.2: extract + LK(21x21, 4 levels) + findFundamentalMat(RANSAC 1.0/0.99) + dyn-reject(boxes + epipolar) + SearchByProjection(th=15)',
                            'frames_per_gpu_per_step': NB, 'l2_policy': 'inputs larger than L2: %d frames x 307200 B = %.0f MB per step (+ %.0f MB pyramid traffic)' % (NB, NB * 0.3072, NB * 0.95),
-                           'sharding': 'independent streams per rank, no data-path collective; one untimed ncclBroadcast of the map/vocabulary table at start-up',
+                           'sharding': 'independent streams per rank, no data-path collective; one untimed ncclBroadcast of the vocabulary node descriptors (35.6 MB) at start-up',
                            'mean_keypoints': float(n0.mean()), 'mean_after_dynreject': float(counts_after.mean()), 'mean_matches': float(nmatch.mean()),
                            'ransac_iterations_mean': float(F_info[:, 2].mean()), 'ransac_inlier_ratio_mean': float((F_info[:, 1] / np.maximum(1, F_info[:, 0])).mean()),
+                           'bow_transform_ms_per_step': bow_ms, 'bow_note': 'Frame::ComputeBoW (DBoW2 transform, k=10 L=6 vocabulary of %d nodes) of the same %d frames, timed separately, not part of value' % (voc_nodes, NB),
                            'not_in_step': 'the detector (boxes precomputed)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps, 'roofline': roofline, 'cpu_baseline': cpu}
         if bcast_ms is not None:

@@ -264,6 +264,11 @@ typedef struct sgs_bow_batch {
     int32_t* nmatches;                                   /* out [F] */
 } sgs_bow_batch;
 SGS_API int sgs_match_bow_batch_device(const sgs_bow_batch* args, int nframes, void* stream);
+/* host-pointer variants: one descriptor set / one (key frame, frame) pair */
+SGS_API int sgs_bow_transform(const sgs_vocabulary* v, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight, int32_t* node);
+SGS_API int sgs_match_bow(int nkf, const int32_t* kf_node, const double* kf_weight, const uint8_t* kf_valid, const uint8_t* kf_desc,
+                          const float* kf_angle, int nf, const int32_t* f_node, const double* f_weight, const uint8_t* f_desc,
+                          const float* f_angle, float nnratio, int check_orientation, int32_t* match_f, int* nmatches, int device);
 
 /* ------------------------------------------------------------------------------------
  * Frame geometry between the extractor and the matchers (device pointers, `nframes` frames, work enqueued on `stream`):

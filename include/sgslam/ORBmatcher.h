@@ -11,6 +11,7 @@
 //                                              SearchByProjection(Frame&, vector<MapPoint*>&, th)     src/ORBmatcher.cc:45-129
 //                                              DescriptorDistance                                      src/ORBmatcher.cc:1649-1665
 //                                              SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist)  src/ORBmatcher.cc:1474-1601
+//                                              SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)      src/ORBmatcher.cc:159-290
 // The mapping / loop-closing variants (SearchByBoW, Fuse, SearchBySim3, ...) are SURVEY section 8(f) "next" rows.
 #pragma once
 #include <stdexcept>
@@ -127,6 +128,29 @@ public:
                                          mbCheckOrientation ? 1 : 0, cmp.data(), &nmatches, device_));
         for (int j = 0; j < n; ++j)
             if (cmp[j] >= 0 && cmp[j] < nkf) CurrentFrame.mvpMapPoints[j] = vpMPs[cmp[j]];
+        return nmatches;
+    }
+
+    // Search matches between MapPoints in a KeyFrame and ORB in a Frame, brute force constrained to ORB that belong to the same vocabulary
+    // node (Tracking::TrackReferenceKeyFrame src/Tracking.cc:865, Relocalization :1455).  mFeatVec: DBoW2::FeatureVector of both sides.
+    template <class KeyFrameT, class FrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches) {
+        const auto vpMapPointsKF = pKF->GetMapPointMatches();
+        const int nkf = (int)vpMapPointsKF.size(), nf = F.N;
+        vpMapPointMatches = std::vector<MapPointT*>(nf, static_cast<MapPointT*>(NULL));
+        if (nkf == 0 || nf == 0) return 0;
+        std::vector<int32_t> kn(nkf, 0), fn(nf, 0), m(nf, -1);
+        std::vector<double> kw(nkf, 0.0), fw(nf, 0.0);             // weight > 0 <=> the feature is listed in the FeatureVector
+        std::vector<uint8_t> kv(nkf, 0);
+        std::vector<float> ka(nkf, 0.f), fa(nf, 0.f);
+        for (const auto& kvp : pKF->mFeatVec) for (unsigned idx : kvp.second) { kn[idx] = (int32_t)kvp.first; kw[idx] = 1.0; }
+        for (const auto& kvp : F.mFeatVec) for (unsigned idx : kvp.second) { fn[idx] = (int32_t)kvp.first; fw[idx] = 1.0; }
+        for (int i = 0; i < nkf; ++i) { kv[i] = (vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad()) ? 1 : 0; ka[i] = pKF->mvKeysUn[i].angle; }
+        for (int j = 0; j < nf; ++j) fa[j] = F.mvKeysUn[j].angle;
+        int nmatches = 0;
+        check(sgs_match_bow(nkf, kn.data(), kw.data(), kv.data(), pKF->mDescriptors.template ptr<uint8_t>(), ka.data(), nf, fn.data(), fw.data(),
+                            F.mDescriptors.template ptr<uint8_t>(), fa.data(), mfNNratio, mbCheckOrientation ? 1 : 0, m.data(), &nmatches, device_));
+        for (int j = 0; j < nf; ++j) if (m[j] >= 0) vpMapPointMatches[j] = vpMapPointsKF[m[j]];
         return nmatches;
     }
 

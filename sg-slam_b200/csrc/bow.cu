@@ -285,4 +285,70 @@ SGS_API int sgs_match_bow_batch_device(const sgs_bow_batch* a, int nframes, void
     return SGS_OK;
 }
 
+// host-pointer variants for one (key frame, frame) pair / one descriptor set
+SGS_API int sgs_bow_transform(const sgs_vocabulary* v, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight, int32_t* node) {
+    if (!v || n < 0 || (n > 0 && (!desc || !word || !weight || !node))) { set_error("sgs_bow_transform: bad argument"); return SGS_ERR_INVALID; }
+    if (n == 0) return SGS_OK;
+    SGS_CUDA_TRY(cudaSetDevice(v->device));
+    uint8_t* d = nullptr;
+    const size_t N = (size_t)n;
+    SGS_CUDA_TRY(cudaMalloc(&d, 32 * N + 8 * N + 4 * N + 4 * N + 64));
+    double* d_w = reinterpret_cast<double*>(d + 32 * N); int32_t* d_word = reinterpret_cast<int32_t*>(d_w + N); int32_t* d_node = d_word + N;
+    cudaMemcpy(d, desc, 32 * N, cudaMemcpyHostToDevice);
+    int rc = sgs_bow_transform_batch_device(v, d, nullptr, n, 1, levelsup, d_word, d_w, d_node, nullptr);
+    cudaError_t e = cudaSuccess;
+    if (rc == SGS_OK) {
+        e = cudaMemcpy(word, d_word, 4 * N, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(weight, d_w, 8 * N, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(node, d_node, 4 * N, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (rc != SGS_OK) return rc;
+    if (e != cudaSuccess) { set_error("sgs_bow_transform: %s", cudaGetErrorString(e)); return SGS_ERR_CUDA; }
+    return SGS_OK;
+}
+
+SGS_API int sgs_match_bow(int nkf, const int32_t* kf_node, const double* kf_weight, const uint8_t* kf_valid, const uint8_t* kf_desc, const float* kf_angle,
+                          int nf, const int32_t* f_node, const double* f_weight, const uint8_t* f_desc, const float* f_angle, float nnratio,
+                          int check_orientation, int32_t* match_f, int* nmatches, int device) {
+    if (!nmatches || nkf < 0 || nf < 0) { set_error("sgs_match_bow: bad argument"); return SGS_ERR_INVALID; }
+    *nmatches = 0;
+    if (nf > 0 && match_f) for (int j = 0; j < nf; ++j) match_f[j] = -1;
+    if (nkf == 0 || nf == 0) return SGS_OK;
+    if (!kf_node || !kf_weight || !kf_valid || !kf_desc || !kf_angle || !f_node || !f_weight || !f_desc || !f_angle || !match_f) { set_error("sgs_match_bow: NULL array"); return SGS_ERR_INVALID; }
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    const size_t K = (size_t)nkf, F = (size_t)nf;
+    uint8_t* d = nullptr;
+    const size_t bytes = 8 * K + 8 * F + 32 * K + 32 * F + 4 * K + 4 * F + 4 * K + 4 * F + 4 * F + K + 64 + 16;
+    SGS_CUDA_TRY(cudaMalloc(&d, bytes));
+    double* d_kw = reinterpret_cast<double*>(d); double* d_fw = d_kw + K;
+    uint8_t* d_kd = reinterpret_cast<uint8_t*>(d_fw + F); uint8_t* d_fd = d_kd + 32 * K;
+    int32_t* d_kn = reinterpret_cast<int32_t*>(d_fd + 32 * F); int32_t* d_fn = d_kn + K;
+    float* d_ka = reinterpret_cast<float*>(d_fn + F); float* d_fa = d_ka + K;
+    int32_t* d_m = reinterpret_cast<int32_t*>(d_fa + F); int32_t* d_cnt = d_m + F;      // d_cnt: kf_n, f_n, nmatches
+    uint8_t* d_kv = reinterpret_cast<uint8_t*>(d_cnt + 4);
+    const int32_t cnt[3] = {nkf, nf, 0};
+    cudaMemcpy(d_kw, kf_weight, 8 * K, cudaMemcpyHostToDevice); cudaMemcpy(d_fw, f_weight, 8 * F, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_kd, kf_desc, 32 * K, cudaMemcpyHostToDevice); cudaMemcpy(d_fd, f_desc, 32 * F, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_kn, kf_node, 4 * K, cudaMemcpyHostToDevice); cudaMemcpy(d_fn, f_node, 4 * F, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_ka, kf_angle, 4 * K, cudaMemcpyHostToDevice); cudaMemcpy(d_fa, f_angle, 4 * F, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_kv, kf_valid, K, cudaMemcpyHostToDevice); cudaMemcpy(d_cnt, cnt, 12, cudaMemcpyHostToDevice);
+    sgs_bow_batch b;
+    b.kf_node = d_kn; b.kf_weight = d_kw; b.kf_valid = d_kv; b.kf_desc = d_kd; b.kf_angle = d_ka; b.kf_n = d_cnt; b.kf_cap = nkf;
+    b.f_node = d_fn; b.f_weight = d_fw; b.f_desc = d_fd; b.f_angle = d_fa; b.f_n = d_cnt + 1; b.f_cap = nf;
+    b.nnratio = nnratio; b.check_orientation = check_orientation; b.match_f = d_m; b.nmatches = d_cnt + 2;
+    int rc = sgs_match_bow_batch_device(&b, 1, nullptr);
+    cudaError_t e = cudaSuccess;
+    int32_t nm = 0;
+    if (rc == SGS_OK) {
+        e = cudaMemcpy(match_f, d_m, 4 * F, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(&nm, d_cnt + 2, 4, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (rc != SGS_OK) return rc;
+    if (e != cudaSuccess) { set_error("sgs_match_bow: %s", cudaGetErrorString(e)); return SGS_ERR_CUDA; }
+    *nmatches = nm;
+    return SGS_OK;
+}
+
 }  // extern "C"

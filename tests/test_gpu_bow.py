@@ -91,3 +91,28 @@ def test_search_by_bow(seed, nk, nf, flips, nnratio):
                     assert nmg[0] > 50
     finally:
         gv.close()
+
+
+def test_host_variants():
+    voc = S.random_vocabulary(21, k=10, L=3)
+    V = O.Vocabulary(voc['k'], voc['L'], voc['parent'], voc['desc'], voc['weight'])
+    gv = GpuVoc(voc)
+    try:
+        s = S.bow_pair_scenario(5, voc, n_kf=900, n_f=1000)
+        v = C.c_void_p
+        outs = []
+        for d in (s['kf_desc'], s['f_desc']):
+            n = len(d); word = np.zeros(n, np.int32); w = np.zeros(n, np.float64); node = np.zeros(n, np.int32)
+            B.check(B.lib().sgs_bow_transform(gv.h, np.ascontiguousarray(d).ctypes.data_as(v), n, 1, word.ctypes.data_as(v), w.ctypes.data_as(v), node.ctypes.data_as(v)))
+            ow, owt, on = V.transform(d, 1)
+            assert np.array_equal(word, ow) and np.array_equal(node, on) and w.tobytes() == owt.tobytes()
+            outs.append((w, node))
+        (kw, kn), (fw, fn) = outs
+        m = np.zeros(1000, np.int32); nm = C.c_int()
+        P = lambda a: np.ascontiguousarray(a).ctypes.data_as(v)
+        B.check(B.lib().sgs_match_bow(900, P(kn), P(kw), P(s['kf_valid']), P(s['kf_desc']), P(s['kf_angle']), 1000, P(fn), P(fw), P(s['f_desc']), P(s['f_angle']),
+                                      C.c_float(0.7), 1, m.ctypes.data_as(v), C.byref(nm), 0))
+        onm, om = O.search_by_bow(kn, kw, s['kf_valid'], s['kf_desc'], s['kf_angle'], fn, fw, s['f_desc'], s['f_angle'], 0.7, True)
+        assert nm.value == onm and np.array_equal(m, om)
+    finally:
+        gv.close()
