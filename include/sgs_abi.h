@@ -259,8 +259,11 @@ typedef struct sgs_bow_batch {
     const uint8_t* kf_valid;                             /* map point exists && !isBad() */
     const uint8_t* kf_desc; const float* kf_angle; const int32_t* kf_n; int32_t kf_cap;
     const int32_t* f_node; const double* f_weight; const uint8_t* f_desc; const float* f_angle; const int32_t* f_n; int32_t f_cap;
+    const uint8_t* f_valid;                              /* NULL for a Frame; key-frame pair: second key frame's map point exists && !isBad() */
+    int32_t keyframe_pair;                               /* 1: SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:524-657): strict
+                                                            < TH_LOW, match_f is [F][kf_cap], indexed by the FIRST key frame's features */
     float nnratio; int32_t check_orientation;            /* 0.7 / true at src/Tracking.cc:865 */
-    int32_t* match_f;                                    /* out [F][f_cap] */
+    int32_t* match_f;                                    /* out [F][f_cap] (or [F][kf_cap], see keyframe_pair) */
     int32_t* nmatches;                                   /* out [F] */
 } sgs_bow_batch;
 SGS_API int sgs_match_bow_batch_device(const sgs_bow_batch* args, int nframes, void* stream);

@@ -141,3 +141,56 @@ SGO_API int sgo_search_by_bow(int nkf, const int32_t* kf_node, const double* kf_
     }
     return nmatches;
 }
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (src/ORBmatcher.cc:524-657, loop closing): both sides
+// need a good map point, the distance test is strict (< TH_LOW), the result is indexed by the FIRST key frame's features:
+// match_1[i1] = feature of the second key frame whose map point is assigned, or -1.
+SGO_API int sgo_search_by_bow_kfkf(int n1, const int32_t* node1, const double* weight1, const uint8_t* valid1, const uint8_t* desc1, const float* angle1,
+                                   int n2, const int32_t* node2, const double* weight2, const uint8_t* valid2, const uint8_t* desc2, const float* angle2,
+                                   float nnratio, int checkOri, int32_t* match_1) {
+    std::map<int, std::vector<int>> fv1, fv2;
+    for (int i = 0; i < n1; i++) if (weight1[i] > 0) fv1[node1[i]].push_back(i);
+    for (int j = 0; j < n2; j++) if (weight2[j] > 0) fv2[node2[j]].push_back(j);
+    for (int i = 0; i < n1; i++) match_1[i] = -1;
+    std::vector<uint8_t> matched2(n2, 0);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = HISTO_LENGTH / 360.0f;
+    auto A = fv1.begin(); auto B = fv2.begin();
+    while (A != fv1.end() && B != fv2.end()) {
+        if (A->first == B->first) {
+            for (int idx1 : A->second) {
+                if (!valid1[idx1]) continue;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int idx2 : B->second) {
+                    if (matched2[idx2] || !valid2[idx2]) continue;
+                    const int dist = hamming(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW && (float)bestDist1 < nnratio * (float)bestDist2) {
+                    match_1[idx1] = bestIdx2; matched2[bestIdx2] = 1;
+                    if (checkOri) {
+                        float rot = angle1[idx1] - angle2[bestIdx2];
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                    nmatches++;
+                }
+            }
+            ++A; ++B;
+        } else if (A->first < B->first) A = fv1.lower_bound(B->first);
+        else B = fv2.lower_bound(A->first);
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { match_1[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}

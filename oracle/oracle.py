@@ -387,3 +387,14 @@ def search_by_bow(kf_node, kf_weight, kf_valid, kf_desc, kf_angle, f_node, f_wei
     m = np.zeros(len(b[0]), np.int32)
     nm = lib().sgo_search_by_bow(len(a[0]), *[_p(x) for x in a], len(b[0]), *[_p(x) for x in b], C.c_float(nnratio), int(check_ori), _p(m))
     return nm, m
+
+
+def search_by_bow_kfkf(node1, weight1, valid1, desc1, angle1, node2, weight2, valid2, desc2, angle2, nnratio=0.8, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:524-657): (nmatches, match_1[i1] = feature of KF2 or -1)."""
+    a = [np.ascontiguousarray(node1, np.int32), np.ascontiguousarray(weight1, np.float64), np.ascontiguousarray(valid1, np.uint8),
+         np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(angle1, np.float32)]
+    b = [np.ascontiguousarray(node2, np.int32), np.ascontiguousarray(weight2, np.float64), np.ascontiguousarray(valid2, np.uint8),
+         np.ascontiguousarray(desc2, np.uint8), np.ascontiguousarray(angle2, np.float32)]
+    m = np.zeros(len(a[0]), np.int32)
+    nm = lib().sgo_search_by_bow_kfkf(len(a[0]), *[_p(x) for x in a], len(b[0]), *[_p(x) for x in b], C.c_float(nnratio), int(check_ori), _p(m))
+    return nm, m

@@ -66,8 +66,9 @@ __global__ void __launch_bounds__(256) bow_transform_kernel(const VocDev V, cons
 
 struct BowArgs {
     const int32_t* kf_node; const double* kf_weight; const uint8_t* kf_valid; const uint8_t* kf_desc; const float* kf_angle; const int32_t* kf_n; int kf_cap;
-    const int32_t* f_node; const double* f_weight; const uint8_t* f_desc; const float* f_angle; const int32_t* f_n; int f_cap;
+    const int32_t* f_node; const double* f_weight; const uint8_t* f_valid; const uint8_t* f_desc; const float* f_angle; const int32_t* f_n; int f_cap;
     float nnratio; int check_ori;
+    int pair_mode;              // 1: SearchByBoW(KF1, KF2): strict < TH_LOW, second side needs map points, result indexed by the first side
     int32_t* match_f; int32_t* nmatches;
     int kf_pow2, f_pow2;
 };
@@ -93,8 +94,8 @@ __global__ void __launch_bounds__(kBowThreads) bow_search_kernel(const BowArgs A
     uint64_t* kkey = reinterpret_cast<uint64_t*>(smem);            // [kf_pow2]
     uint64_t* fkey = kkey + A.kf_pow2;                              // [f_pow2]
     int32_t* run_start = reinterpret_cast<int32_t*>(fkey + A.f_pow2);   // [kf_pow2 + 1]
-    int32_t* events = run_start + A.kf_pow2 + 1;                    // [f_cap] (bin << 16 | frame feature)
-    uint8_t* taken = reinterpret_cast<uint8_t*>(events + A.f_cap);  // [f_cap]
+    int32_t* events = run_start + A.kf_pow2 + 1;                    // [max(kf_cap, f_cap)] (bin << 16 | index in the result array)
+    uint8_t* taken = reinterpret_cast<uint8_t*>(events + max(A.kf_cap, A.f_cap));  // [f_cap]
     __shared__ int hist[kBowHisto];
     __shared__ int s_nk, s_nf, s_nruns, s_nevent, s_nmatch;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -109,10 +110,12 @@ __global__ void __launch_bounds__(kBowThreads) bow_search_kernel(const BowArgs A
     }
     for (int j = tid; j < A.f_pow2; j += blockDim.x) {
         uint64_t key = ~0ull;
-        if (j < nf_all && A.f_weight[fo + j] > 0) key = ((uint64_t)(uint32_t)A.f_node[fo + j] << 32) | (uint32_t)j;
+        if (j < nf_all && A.f_weight[fo + j] > 0 && (!A.f_valid || A.f_valid[fo + j])) key = ((uint64_t)(uint32_t)A.f_node[fo + j] << 32) | (uint32_t)j;
         fkey[j] = key;
     }
-    for (int j = tid; j < A.f_cap; j += blockDim.x) { taken[j] = 0; A.match_f[fo + j] = -1; }
+    const int64_t oo = A.pair_mode ? ko : fo;                      // the result is indexed by the first side in pair mode
+    for (int j = tid; j < A.f_cap; j += blockDim.x) taken[j] = 0;
+    for (int j = tid; j < (A.pair_mode ? A.kf_cap : A.f_cap); j += blockDim.x) A.match_f[oo + j] = -1;
     __syncthreads();
     bow_bitonic(kkey, A.kf_pow2);
     bow_bitonic(fkey, A.f_pow2);
@@ -157,18 +160,19 @@ __global__ void __launch_bounds__(kBowThreads) bow_search_kernel(const BowArgs A
             const int c2 = key1 == K1 ? d2 : min((int)(key1 >> 16), 256);
             const int best2 = __reduce_min_sync(0xffffffffu, c2 > 256 ? 256 : c2);
             const int best1 = K1 == 0xffffffffu ? 256 : (int)(K1 >> 16);
-            if (best1 <= kBowThLow && (float)best1 < __fmul_rn(A.nnratio, (float)best2)) {        // :237-240
+            if ((A.pair_mode ? best1 < kBowThLow : best1 <= kBowThLow) && (float)best1 < __fmul_rn(A.nnratio, (float)best2)) {        // :237-240 / :599-601
                 const int realF = (int)(uint32_t)fkey[b0 + (int)(K1 & 0xffffu)];
                 if (lane == 0) {
                     taken[realF] = 1;
-                    A.match_f[fo + realF] = realK;
+                    const int slot = A.pair_mode ? realK : realF;
+                    A.match_f[oo + slot] = A.pair_mode ? realF : realK;
                     if (A.check_ori) {
                         float rot = __fsub_rn(A.kf_angle[ko + realK], A.f_angle[fo + realF]);
                         if (rot < 0.f) rot = __fadd_rn(rot, 360.f);
                         int bin = (int)roundf(__fmul_rn(rot, (float)kBowHisto / 360.0f));
                         if (bin == kBowHisto) bin = 0;
                         atomicAdd(&hist[bin], 1);
-                        events[atomicAdd(&s_nevent, 1)] = (bin << 16) | realF;
+                        events[atomicAdd(&s_nevent, 1)] = (bin << 16) | slot;
                     }
                     ++nmatch;
                 }
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(kBowThreads) bow_search_kernel(const BowArgs A
         int removed = 0;
         for (int e = tid; e < s_nevent; e += blockDim.x) {
             const int bin = events[e] >> 16, j = events[e] & 0xffff;
-            if (bin != s_i1 && bin != s_i2 && bin != s_i3) { A.match_f[fo + j] = -1; ++removed; }
+            if (bin != s_i1 && bin != s_i2 && bin != s_i3) { A.match_f[oo + j] = -1; ++removed; }
         }
         if (removed) atomicSub(&s_nmatch, removed);
         __syncthreads();
@@ -271,10 +275,10 @@ SGS_API int sgs_match_bow_batch_device(const sgs_bow_batch* a, int nframes, void
     if (a->kf_cap < 1 || a->f_cap < 1 || a->kf_cap > 8192 || a->f_cap > 8192) { set_error("sgs_match_bow_batch_device: at most 8192 features per frame"); return SGS_ERR_UNSUPPORTED; }
     BowArgs A;
     A.kf_node = a->kf_node; A.kf_weight = a->kf_weight; A.kf_valid = a->kf_valid; A.kf_desc = a->kf_desc; A.kf_angle = a->kf_angle; A.kf_n = a->kf_n; A.kf_cap = a->kf_cap;
-    A.f_node = a->f_node; A.f_weight = a->f_weight; A.f_desc = a->f_desc; A.f_angle = a->f_angle; A.f_n = a->f_n; A.f_cap = a->f_cap;
+    A.f_node = a->f_node; A.f_weight = a->f_weight; A.f_valid = a->f_valid; A.pair_mode = a->keyframe_pair ? 1 : 0; A.f_desc = a->f_desc; A.f_angle = a->f_angle; A.f_n = a->f_n; A.f_cap = a->f_cap;
     A.nnratio = a->nnratio; A.check_ori = a->check_orientation; A.match_f = a->match_f; A.nmatches = a->nmatches;
     A.kf_pow2 = pow2_ge(a->kf_cap); A.f_pow2 = pow2_ge(a->f_cap);
-    const size_t smem = 8 * (size_t)A.kf_pow2 + 8 * (size_t)A.f_pow2 + 4 * (size_t)(A.kf_pow2 + 1) + 4 * (size_t)A.f_cap + (size_t)A.f_cap + 16;
+    const size_t smem = 8 * (size_t)A.kf_pow2 + 8 * (size_t)A.f_pow2 + 4 * (size_t)(A.kf_pow2 + 1) + 4 * (size_t)(a->kf_cap > a->f_cap ? a->kf_cap : a->f_cap) + (size_t)A.f_cap + 16;
     static size_t configured = 0;
     if (smem > 40 * 1024 && smem > configured) {
         SGS_CUDA_TRY(cudaFuncSetAttribute(bow_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -336,6 +340,7 @@ SGS_API int sgs_match_bow(int nkf, const int32_t* kf_node, const double* kf_weig
     sgs_bow_batch b;
     b.kf_node = d_kn; b.kf_weight = d_kw; b.kf_valid = d_kv; b.kf_desc = d_kd; b.kf_angle = d_ka; b.kf_n = d_cnt; b.kf_cap = nkf;
     b.f_node = d_fn; b.f_weight = d_fw; b.f_desc = d_fd; b.f_angle = d_fa; b.f_n = d_cnt + 1; b.f_cap = nf;
+    b.f_valid = nullptr; b.keyframe_pair = 0;
     b.nnratio = nnratio; b.check_orientation = check_orientation; b.match_f = d_m; b.nmatches = d_cnt + 2;
     int rc = sgs_match_bow_batch_device(&b, 1, nullptr);
     cudaError_t e = cudaSuccess;

@@ -55,7 +55,8 @@ class LastFrameBatch(C.Structure):
 class BowBatch(C.Structure):
     _fields_ = [('kf_node', C.c_void_p), ('kf_weight', C.c_void_p), ('kf_valid', C.c_void_p), ('kf_desc', C.c_void_p), ('kf_angle', C.c_void_p), ('kf_n', C.c_void_p),
                 ('kf_cap', C.c_int32), ('f_node', C.c_void_p), ('f_weight', C.c_void_p), ('f_desc', C.c_void_p), ('f_angle', C.c_void_p), ('f_n', C.c_void_p),
-                ('f_cap', C.c_int32), ('nnratio', C.c_float), ('check_orientation', C.c_int32), ('match_f', C.c_void_p), ('nmatches', C.c_void_p)]
+                ('f_cap', C.c_int32), ('f_valid', C.c_void_p), ('keyframe_pair', C.c_int32), ('nnratio', C.c_float), ('check_orientation', C.c_int32),
+                ('match_f', C.c_void_p), ('nmatches', C.c_void_p)]
 
 
 class FrustumBatch(C.Structure):

@@ -116,3 +116,41 @@ def test_host_variants():
         assert nm.value == onm and np.array_equal(m, om)
     finally:
         gv.close()
+
+
+@pytest.mark.parametrize('seed,n1,n2,nnratio', [(1, 1000, 1000, 0.8), (2, 600, 1100, 0.75)])
+def test_search_by_bow_keyframe_pair(seed, n1, n2, nnratio):
+    """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (loop closing, src/ORBmatcher.cc:524-657)."""
+    import torch
+    voc = S.random_vocabulary(13, k=10, L=3)
+    V = O.Vocabulary(voc['k'], voc['L'], voc['parent'], voc['desc'], voc['weight'])
+    gv = GpuVoc(voc)
+    try:
+        cap = 1100
+        s = S.bow_pair_scenario(seed + 40, voc, n_kf=n1, n_f=n2, flips=40)
+        rs = np.random.RandomState(seed)
+        valid2 = (rs.rand(n2) < 0.8).astype(np.uint8)
+        pad = lambda a, n, shape, dt: np.concatenate([a, np.zeros((cap - n,) + shape, dt)])[None]
+        d1 = pad(s['kf_desc'], n1, (32,), np.uint8); d2 = pad(s['f_desc'], n2, (32,), np.uint8)
+        a1 = pad(s['kf_angle'], n1, (), np.float32); a2 = pad(s['f_angle'], n2, (), np.float32)
+        v1 = pad(s['kf_valid'], n1, (), np.uint8); v2 = pad(valid2, n2, (), np.uint8)
+        c1 = np.array([n1], np.int32); c2 = np.array([n2], np.int32)
+        _, w1, nd1 = _transform_gpu(gv, d1, c1, 1); _, w2, nd2 = _transform_gpu(gv, d2, c2, 1)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        t = [dev(x) for x in (v1, d1, a1, c1, d2, a2, c2, v2)]
+        _, ow1, on1 = V.transform(s['kf_desc'], 1); _, ow2, on2 = V.transform(s['f_desc'], 1)
+        for ori in (0, 1):
+            m = torch.zeros((1, cap), dtype=torch.int32, device='cuda'); nm = torch.zeros(1, dtype=torch.int32, device='cuda')
+            a = B.BowBatch()
+            a.kf_node, a.kf_weight, a.kf_valid, a.kf_desc, a.kf_angle, a.kf_n, a.kf_cap = nd1.data_ptr(), w1.data_ptr(), t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), cap
+            a.f_node, a.f_weight, a.f_desc, a.f_angle, a.f_n, a.f_cap = nd2.data_ptr(), w2.data_ptr(), t[4].data_ptr(), t[5].data_ptr(), t[6].data_ptr(), cap
+            a.f_valid, a.keyframe_pair = t[7].data_ptr(), 1
+            a.nnratio, a.check_orientation, a.match_f, a.nmatches = nnratio, ori, m.data_ptr(), nm.data_ptr()
+            B.check(B.lib().sgs_match_bow_batch_device(C.byref(a), 1, C.c_void_p(0)))
+            torch.cuda.synchronize()
+            onm, om = O.search_by_bow_kfkf(on1, ow1, s['kf_valid'], s['kf_desc'], s['kf_angle'], on2, ow2, valid2, s['f_desc'], s['f_angle'], nnratio, bool(ori))
+            assert int(nm.cpu()[0]) == onm and np.array_equal(m.cpu().numpy()[0, :n1], om) and onm > 30
+            sel = om >= 0
+            assert np.all(valid2[om[sel]] == 1) and len(set(om[sel].tolist())) == int(sel.sum())       # only good map points, each used once
+    finally:
+        gv.close()
