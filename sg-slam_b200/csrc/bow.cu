@@ -15,6 +15,9 @@
 
 #include "sgs_common.h"
 
+// host -> device copy of the convenience (host-pointer) entry points: the first failure is kept and reported by the caller
+#define SGS_H2D(err, dst, src, bytes) do { if ((err) == cudaSuccess) (err) = cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice); } while (0)
+
 struct sgs_vocabulary {
     int device = 0, k = 0, L = 0, nnodes = 0;
     int32_t* d_first = nullptr; int32_t* d_count = nullptr; int32_t* d_children = nullptr; int32_t* d_word = nullptr;
@@ -279,11 +282,8 @@ SGS_API int sgs_match_bow_batch_device(const sgs_bow_batch* a, int nframes, void
     A.nnratio = a->nnratio; A.check_ori = a->check_orientation; A.match_f = a->match_f; A.nmatches = a->nmatches;
     A.kf_pow2 = pow2_ge(a->kf_cap); A.f_pow2 = pow2_ge(a->f_cap);
     const size_t smem = 8 * (size_t)A.kf_pow2 + 8 * (size_t)A.f_pow2 + 4 * (size_t)(A.kf_pow2 + 1) + 4 * (size_t)(a->kf_cap > a->f_cap ? a->kf_cap : a->f_cap) + (size_t)A.f_cap + 16;
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {
+    if (smem > 40 * 1024)      // per device and cheap: set whenever the default 48 KB would not do
         SGS_CUDA_TRY(cudaFuncSetAttribute(bow_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     bow_search_kernel<<<nframes, kBowThreads, smem, (cudaStream_t)stream>>>(A);
     SGS_CUDA_TRY(cudaGetLastError());
     return SGS_OK;
@@ -298,7 +298,9 @@ SGS_API int sgs_bow_transform(const sgs_vocabulary* v, const uint8_t* desc, int 
     const size_t N = (size_t)n;
     SGS_CUDA_TRY(cudaMalloc(&d, 32 * N + 8 * N + 4 * N + 4 * N + 64));
     double* d_w = reinterpret_cast<double*>(d + 32 * N); int32_t* d_word = reinterpret_cast<int32_t*>(d_w + N); int32_t* d_node = d_word + N;
-    cudaMemcpy(d, desc, 32 * N, cudaMemcpyHostToDevice);
+    cudaError_t h2d = cudaSuccess;
+    SGS_H2D(h2d, d, desc, 32 * N);
+    if (h2d != cudaSuccess) { cudaFree(d); set_error("sgs_bow_transform: %s", cudaGetErrorString(h2d)); return SGS_ERR_CUDA; }
     int rc = sgs_bow_transform_batch_device(v, d, nullptr, n, 1, levelsup, d_word, d_w, d_node, nullptr);
     cudaError_t e = cudaSuccess;
     if (rc == SGS_OK) {
@@ -332,11 +334,13 @@ SGS_API int sgs_match_bow(int nkf, const int32_t* kf_node, const double* kf_weig
     int32_t* d_m = reinterpret_cast<int32_t*>(d_fa + F); int32_t* d_cnt = d_m + F;      // d_cnt: kf_n, f_n, nmatches
     uint8_t* d_kv = reinterpret_cast<uint8_t*>(d_cnt + 4);
     const int32_t cnt[3] = {nkf, nf, 0};
-    cudaMemcpy(d_kw, kf_weight, 8 * K, cudaMemcpyHostToDevice); cudaMemcpy(d_fw, f_weight, 8 * F, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_kd, kf_desc, 32 * K, cudaMemcpyHostToDevice); cudaMemcpy(d_fd, f_desc, 32 * F, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_kn, kf_node, 4 * K, cudaMemcpyHostToDevice); cudaMemcpy(d_fn, f_node, 4 * F, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_ka, kf_angle, 4 * K, cudaMemcpyHostToDevice); cudaMemcpy(d_fa, f_angle, 4 * F, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_kv, kf_valid, K, cudaMemcpyHostToDevice); cudaMemcpy(d_cnt, cnt, 12, cudaMemcpyHostToDevice);
+    cudaError_t h2d = cudaSuccess;
+    SGS_H2D(h2d, d_kw, kf_weight, 8 * K); SGS_H2D(h2d, d_fw, f_weight, 8 * F);
+    SGS_H2D(h2d, d_kd, kf_desc, 32 * K); SGS_H2D(h2d, d_fd, f_desc, 32 * F);
+    SGS_H2D(h2d, d_kn, kf_node, 4 * K); SGS_H2D(h2d, d_fn, f_node, 4 * F);
+    SGS_H2D(h2d, d_ka, kf_angle, 4 * K); SGS_H2D(h2d, d_fa, f_angle, 4 * F);
+    SGS_H2D(h2d, d_kv, kf_valid, K); SGS_H2D(h2d, d_cnt, cnt, 12);
+    if (h2d != cudaSuccess) { cudaFree(d); set_error("sgs_match_bow: %s", cudaGetErrorString(h2d)); return SGS_ERR_CUDA; }
     sgs_bow_batch b;
     b.kf_node = d_kn; b.kf_weight = d_kw; b.kf_valid = d_kv; b.kf_desc = d_kd; b.kf_angle = d_ka; b.kf_n = d_cnt; b.kf_cap = nkf;
     b.f_node = d_fn; b.f_weight = d_fw; b.f_desc = d_fd; b.f_angle = d_fa; b.f_n = d_cnt + 1; b.f_cap = nf;

@@ -10,6 +10,9 @@
 
 #include "sgs_common.h"
 
+// host -> device copy of the convenience (host-pointer) entry points: the first failure is kept and reported by the caller
+#define SGS_H2D(err, dst, src, bytes) do { if ((err) == cudaSuccess) (err) = cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice); } while (0)
+
 namespace sgs {
 
 __global__ void __launch_bounds__(256) stereo_from_depth_kernel(const sgs_keypoint* __restrict__ kps, const sgs_keypoint* __restrict__ kps_un,
@@ -141,7 +144,9 @@ SGS_API int sgs_undistort_points(const float* xy, int n, float fx, float fy, flo
     SGS_CUDA_TRY(cudaSetDevice(device));
     float2* d = nullptr;
     SGS_CUDA_TRY(cudaMalloc(&d, 16 * (size_t)n));
-    cudaMemcpy(d, xy, 8 * (size_t)n, cudaMemcpyHostToDevice);
+    cudaError_t h2d = cudaSuccess;
+    SGS_H2D(h2d, d, xy, 8 * (size_t)n);
+    if (h2d != cudaSuccess) { cudaFree(d); set_error("sgs_undistort_points: %s", cudaGetErrorString(h2d)); return SGS_ERR_CUDA; }
     undistort_kernel<<<dim3((n + 255) / 256, 1), 256>>>(nullptr, d, nullptr, n, fx, fy, cx, cy, dist_coef5[0], dist_coef5[1], dist_coef5[2], dist_coef5[3],
                                                         dist_coef5[4], nullptr, d + n);
     cudaError_t e = cudaMemcpy(out_xy, d + n, 8 * (size_t)n, cudaMemcpyDeviceToHost);
@@ -193,8 +198,10 @@ SGS_API int sgs_frustum(const sgs_camera* cam, const float* tcw, int n, const fl
     float* d_tcw = d; float* d_xyz = d + 16; float* d_nrm = d_xyz + 3 * N; float* d_mn = d_nrm + 3 * N; float* d_mx = d_mn + N;
     float* d_px = d_mx + N; float* d_py = d_px + N; float* d_pxr = d_py + N; float* d_vc = d_pxr + N;
     int32_t* d_lv = reinterpret_cast<int32_t*>(d_vc + N); int32_t* d_n = d_lv + N; uint8_t* d_in = reinterpret_cast<uint8_t*>(d_n + 4);
-    cudaMemcpy(d_tcw, tcw, 64, cudaMemcpyHostToDevice); cudaMemcpy(d_xyz, xyz, 12 * N, cudaMemcpyHostToDevice); cudaMemcpy(d_nrm, normal, 12 * N, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_mn, min_dist, 4 * N, cudaMemcpyHostToDevice); cudaMemcpy(d_mx, max_dist, 4 * N, cudaMemcpyHostToDevice); cudaMemcpy(d_n, &n, 4, cudaMemcpyHostToDevice);
+    cudaError_t h2d = cudaSuccess;
+    SGS_H2D(h2d, d_tcw, tcw, 64); SGS_H2D(h2d, d_xyz, xyz, 12 * N); SGS_H2D(h2d, d_nrm, normal, 12 * N);
+    SGS_H2D(h2d, d_mn, min_dist, 4 * N); SGS_H2D(h2d, d_mx, max_dist, 4 * N); SGS_H2D(h2d, d_n, &n, 4);
+    if (h2d != cudaSuccess) { cudaFree(d); set_error("sgs_frustum: %s", cudaGetErrorString(h2d)); return SGS_ERR_CUDA; }
     sgs_frustum_batch a;
     a.cam = *cam; a.tcw = d_tcw; a.mp_xyz = d_xyz; a.mp_normal = d_nrm; a.mp_min_dist = d_mn; a.mp_max_dist = d_mx; a.mp_n = d_n; a.point_cap = n;
     a.viewing_cos_limit = viewing_cos_limit; a.mp_inview = d_in; a.proj_x = d_px; a.proj_y = d_py; a.proj_xr = d_pxr; a.level = d_lv; a.view_cos = d_vc;

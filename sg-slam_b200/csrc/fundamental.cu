@@ -19,6 +19,9 @@
 
 #include "sgs_common.h"
 
+// host -> device copy of the convenience (host-pointer) entry points: the first failure is kept and reported by the caller
+#define SGS_H2D(err, dst, src, bytes) do { if ((err) == cudaSuccess) (err) = cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice); } while (0)
+
 namespace sgs {
 
 constexpr int kFmThreads = 256;
@@ -366,11 +369,8 @@ int fm_launch(const sgs_keypoint* d_kps, const float2* d_cur, const float2* d_pr
               double confidence, int max_iters, double* d_F, int32_t* d_info, uint8_t* d_mask, cudaStream_t st) {
     const size_t smem = (size_t)cap * sizeof(float4);
     if (smem > 200 * 1024) { set_error("fundamental: %d pairs per frame do not fit shared memory", cap); return SGS_ERR_UNSUPPORTED; }
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {
+    if (smem > 40 * 1024)      // per device and cheap: set whenever the default 48 KB would not do
         SGS_CUDA_TRY(cudaFuncSetAttribute(fm_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     fm_ransac_kernel<<<nframes, kFmThreads, smem, st>>>(d_kps, d_cur, d_prev, d_counts, cap, d_boxes, d_nboxes, d_have_dyn, max_boxes, d_prev_index,
                                                         thresh, confidence, max_iters, d_F, d_info, d_mask);
     SGS_CUDA_TRY(cudaGetLastError());
@@ -402,8 +402,9 @@ SGS_API int sgs_fundamental_ransac(const float* pts1_xy, const float* pts2_xy, i
     SGS_CUDA_TRY(cudaMalloc(&d_a, 8 * (size_t)n));
     if (cudaMalloc(&d_b, 8 * (size_t)n) != cudaSuccess || cudaMalloc(&d_F, 72) != cudaSuccess || cudaMalloc(&d_info, 16) != cudaSuccess ||
         cudaMalloc(&d_mask, (size_t)n) != cudaSuccess) { set_error("sgs_fundamental_ransac: out of device memory"); return done(SGS_ERR_CUDA); }
-    cudaMemcpy(d_a, pts1_xy, 8 * (size_t)n, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_b, pts2_xy, 8 * (size_t)n, cudaMemcpyHostToDevice);
+    cudaError_t h2d = cudaSuccess;
+    SGS_H2D(h2d, d_a, pts1_xy, 8 * (size_t)n); SGS_H2D(h2d, d_b, pts2_xy, 8 * (size_t)n);
+    if (h2d != cudaSuccess) { set_error("sgs_fundamental_ransac: %s", cudaGetErrorString(h2d)); return done(SGS_ERR_CUDA); }
     rc = fm_launch(nullptr, reinterpret_cast<const float2*>(d_a), reinterpret_cast<const float2*>(d_b), nullptr, n, 1, nullptr, nullptr, nullptr, 0, nullptr,
                    ransac_thresh, confidence, max_iters, d_F, d_info, d_mask, nullptr);
     if (rc != SGS_OK) return done(rc);
