@@ -263,6 +263,16 @@ typedef struct sgs_bow_batch {
     int32_t keyframe_pair;                               /* 1: SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:524-657): strict
                                                             < TH_LOW, match_f is [F][kf_cap], indexed by the FIRST key frame's features */
     float nnratio; int32_t check_orientation;            /* 0.7 / true at src/Tracking.cc:865 */
+    /* keyframe_pair == 2: ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (src/ORBmatcher.cc:659-827):
+     * kf_valid / f_valid mean "the feature has NO map point"; no ratio test; candidates must pass the epipole gate (both sides without
+     * stereo) and CheckDistEpipolarLine (:140-157); match_f is [F][kf_cap] like the key-frame pair mode. */
+    const uint8_t* kf_stereo; const uint8_t* f_stereo;   /* mvuRight >= 0 */
+    const float* kf_xy; const float* f_xy;               /* mvKeysUn[i].pt, [F][cap][2] */
+    const int32_t* f_octave;                             /* mvKeysUn[i].octave of the second key frame */
+    const float* F12;                                    /* [F][9] float, row major */
+    const float* epipole;                                /* [F][2]: (ex, ey) of src/ORBmatcher.cc:667-672 */
+    float level_sigma2[16], scale_factors[16];           /* pKF2->mvLevelSigma2 / mvScaleFactors */
+    int32_t only_stereo;
     int32_t* match_f;                                    /* out [F][f_cap] (or [F][kf_cap], see keyframe_pair) */
     int32_t* nmatches;                                   /* out [F] */
 } sgs_bow_batch;

@@ -194,3 +194,73 @@ SGO_API int sgo_search_by_bow_kfkf(int n1, const int32_t* node1, const double* w
     }
     return nmatches;
 }
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (src/ORBmatcher.cc:659-827, LocalMapping::CreateNewMapPoints)
+// with ORBmatcher::CheckDistEpipolarLine (:140-157).  free1 / free2: the feature has NO map point; stereo1 / stereo2: mvuRight >= 0;
+// xy / octave: mvKeysUn; F12: 3x3 float row major; (ex, ey): epipole of KF1's centre in KF2 (:667-672); sigma2 / scale: per-level tables of KF2.
+// match_1[i1] = matched feature of KF2 or -1.
+SGO_API int sgo_search_for_triangulation(int n1, const int32_t* node1, const double* weight1, const uint8_t* free1, const uint8_t* stereo1, const uint8_t* desc1,
+                                         const float* xy1, const float* angle1, int n2, const int32_t* node2, const double* weight2, const uint8_t* free2,
+                                         const uint8_t* stereo2, const uint8_t* desc2, const float* xy2, const int32_t* octave2, const float* angle2,
+                                         const float* F12, float ex, float ey, const float* sigma2, const float* scale, int only_stereo, int checkOri,
+                                         int32_t* match_1) {
+    std::map<int, std::vector<int>> fv1, fv2;
+    for (int i = 0; i < n1; i++) if (weight1[i] > 0) fv1[node1[i]].push_back(i);
+    for (int j = 0; j < n2; j++) if (weight2[j] > 0) fv2[node2[j]].push_back(j);
+    for (int i = 0; i < n1; i++) match_1[i] = -1;
+    std::vector<uint8_t> matched2(n2, 0);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = HISTO_LENGTH / 360.0f;
+    auto A = fv1.begin(); auto B = fv2.begin();
+    while (A != fv1.end() && B != fv2.end()) {
+        if (A->first == B->first) {
+            for (int idx1 : A->second) {
+                if (!free1[idx1]) continue;
+                const bool bStereo1 = stereo1[idx1] != 0;
+                if (only_stereo && !bStereo1) continue;
+                const float x1 = xy1[2 * idx1], y1 = xy1[2 * idx1 + 1];
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int idx2 : B->second) {
+                    if (matched2[idx2] || !free2[idx2]) continue;
+                    const bool bStereo2 = stereo2[idx2] != 0;
+                    if (only_stereo && !bStereo2) continue;
+                    const int dist = hamming(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const float x2 = xy2[2 * idx2], y2 = xy2[2 * idx2 + 1];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - x2, distey = ey - y2;
+                        if (distex * distex + distey * distey < 100 * scale[octave2[idx2]]) continue;
+                    }
+                    // CheckDistEpipolarLine: l = x1' F12
+                    const float a = x1 * F12[0] + y1 * F12[3] + F12[6], b = x1 * F12[1] + y1 * F12[4] + F12[7], c = x1 * F12[2] + y1 * F12[5] + F12[8];
+                    const float num = a * x2 + b * y2 + c, den = a * a + b * b;
+                    if (den == 0) continue;
+                    const float dsqr = num * num / den;
+                    if (dsqr < 3.84 * sigma2[octave2[idx2]]) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match_1[idx1] = bestIdx2; matched2[bestIdx2] = 1; nmatches++;
+                    if (checkOri) {
+                        float rot = angle1[idx1] - angle2[bestIdx2];
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                }
+            }
+            ++A; ++B;
+        } else if (A->first < B->first) A = fv1.lower_bound(B->first);
+        else B = fv2.lower_bound(A->first);
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { match_1[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}

@@ -398,3 +398,17 @@ def search_by_bow_kfkf(node1, weight1, valid1, desc1, angle1, node2, weight2, va
     m = np.zeros(len(a[0]), np.int32)
     nm = lib().sgo_search_by_bow_kfkf(len(a[0]), *[_p(x) for x in a], len(b[0]), *[_p(x) for x in b], C.c_float(nnratio), int(check_ori), _p(m))
     return nm, m
+
+
+def search_for_triangulation(k1, k2, F12, ex, ey, sigma2, scale, only_stereo=False, check_ori=True):
+    """ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:659-827).  k1 / k2: dicts with node, weight, free, stereo, desc, xy, angle (+ octave for k2)."""
+    f32, u8 = np.float32, np.uint8
+    a = [np.ascontiguousarray(k1['node'], np.int32), np.ascontiguousarray(k1['weight'], np.float64), np.ascontiguousarray(k1['free'], u8), np.ascontiguousarray(k1['stereo'], u8),
+         np.ascontiguousarray(k1['desc'], u8), np.ascontiguousarray(k1['xy'], f32), np.ascontiguousarray(k1['angle'], f32)]
+    b = [np.ascontiguousarray(k2['node'], np.int32), np.ascontiguousarray(k2['weight'], np.float64), np.ascontiguousarray(k2['free'], u8), np.ascontiguousarray(k2['stereo'], u8),
+         np.ascontiguousarray(k2['desc'], u8), np.ascontiguousarray(k2['xy'], f32), np.ascontiguousarray(k2['octave'], np.int32), np.ascontiguousarray(k2['angle'], f32)]
+    Fm = np.ascontiguousarray(F12, f32).reshape(9); s2 = np.ascontiguousarray(sigma2, f32); sc = np.ascontiguousarray(scale, f32)
+    m = np.zeros(len(a[0]), np.int32)
+    nm = lib().sgo_search_for_triangulation(len(a[0]), *[_p(x) for x in a], len(b[0]), *[_p(x) for x in b], _p(Fm), C.c_float(ex), C.c_float(ey), _p(s2), _p(sc),
+                                            int(only_stereo), int(check_ori), _p(m))
+    return nm, m

@@ -11,6 +11,7 @@
 // Integer work: bit-exact against the CPU restatement.
 #include <cuda_runtime.h>
 
+#include <cstring>
 #include <vector>
 
 #include "sgs_common.h"
@@ -72,6 +73,9 @@ struct BowArgs {
     const int32_t* f_node; const double* f_weight; const uint8_t* f_valid; const uint8_t* f_desc; const float* f_angle; const int32_t* f_n; int f_cap;
     float nnratio; int check_ori;
     int pair_mode;              // 1: SearchByBoW(KF1, KF2): strict < TH_LOW, second side needs map points, result indexed by the first side
+                                // 2: SearchForTriangulation: no ratio test, epipole + epipolar-line gates, last of equal distances wins
+    const uint8_t* kf_stereo; const uint8_t* f_stereo; const float* kf_xy; const float* f_xy; const int32_t* f_octave;
+    const float* F12; const float* epipole; float sigma2[16], scale[16]; int only_stereo;
     int32_t* match_f; int32_t* nmatches;
     int kf_pow2, f_pow2;
 };
@@ -108,12 +112,12 @@ __global__ void __launch_bounds__(kBowThreads) bow_search_kernel(const BowArgs A
     if (tid < kBowHisto) hist[tid] = 0;
     for (int i = tid; i < A.kf_pow2; i += blockDim.x) {
         uint64_t key = ~0ull;
-        if (i < nk_all && A.kf_weight[ko + i] > 0 && A.kf_valid[ko + i]) key = ((uint64_t)(uint32_t)A.kf_node[ko + i] << 32) | (uint32_t)i;      // invalid map points never act
+        if (i < nk_all && A.kf_weight[ko + i] > 0 && A.kf_valid[ko + i] && !(A.pair_mode == 2 && A.only_stereo && !A.kf_stereo[ko + i])) key = ((uint64_t)(uint32_t)A.kf_node[ko + i] << 32) | (uint32_t)i;      // invalid map points never act
         kkey[i] = key;
     }
     for (int j = tid; j < A.f_pow2; j += blockDim.x) {
         uint64_t key = ~0ull;
-        if (j < nf_all && A.f_weight[fo + j] > 0 && (!A.f_valid || A.f_valid[fo + j])) key = ((uint64_t)(uint32_t)A.f_node[fo + j] << 32) | (uint32_t)j;
+        if (j < nf_all && A.f_weight[fo + j] > 0 && (!A.f_valid || A.f_valid[fo + j]) && !(A.pair_mode == 2 && A.only_stereo && !A.f_stereo[fo + j])) key = ((uint64_t)(uint32_t)A.f_node[fo + j] << 32) | (uint32_t)j;
         fkey[j] = key;
     }
     const int64_t oo = A.pair_mode ? ko : fo;                      // the result is indexed by the first side in pair mode
@@ -151,6 +155,40 @@ __global__ void __launch_bounds__(kBowThreads) bow_search_kernel(const BowArgs A
             const int realK = (int)(uint32_t)kkey[ki];
             const uint4 k0 = __ldg(kdesc + 2 * realK), k1 = __ldg(kdesc + 2 * realK + 1);
             unsigned key1 = 0xffffffffu; int d2 = 256;              // local best (distance << 16 | bucket position), local second-best distance
+            bool accept;
+            unsigned K1;
+            if (A.pair_mode == 2) {
+                // SearchForTriangulation (:706-740): the best is the smallest distance <= TH_LOW among the candidates that pass the epipole and
+                // epipolar-line gates; a later candidate replaces an earlier one of equal distance (dist > bestDist is the skip test)
+                const float x1 = A.kf_xy[2 * (ko + realK)], y1 = A.kf_xy[2 * (ko + realK) + 1];
+                const float* Fm = A.F12 + 9 * (int64_t)f;
+                const float la = __fadd_rn(__fadd_rn(__fmul_rn(x1, Fm[0]), __fmul_rn(y1, Fm[3])), Fm[6]);        // CheckDistEpipolarLine (:140-157)
+                const float lb = __fadd_rn(__fadd_rn(__fmul_rn(x1, Fm[1]), __fmul_rn(y1, Fm[4])), Fm[7]);
+                const float lc = __fadd_rn(__fadd_rn(__fmul_rn(x1, Fm[2]), __fmul_rn(y1, Fm[5])), Fm[8]);
+                const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+                const bool st1 = A.kf_stereo[ko + realK] != 0;
+                const float ex = A.epipole[2 * f], ey = A.epipole[2 * f + 1];
+                for (int p = b0 + lane; p < b1; p += 32) {
+                    const int realF = (int)(uint32_t)fkey[p];
+                    if (taken[realF]) continue;
+                    const int dist = popc256v(k0, k1, __ldg(fdesc + 2 * realF), __ldg(fdesc + 2 * realF + 1));
+                    if (dist > kBowThLow) continue;
+                    const float x2 = A.f_xy[2 * (fo + realF)], y2 = A.f_xy[2 * (fo + realF) + 1];
+                    const int oc = A.f_octave[fo + realF];
+                    if (!st1 && !A.f_stereo[fo + realF]) {
+                        const float dx = __fsub_rn(ex, x2), dy = __fsub_rn(ey, y2);
+                        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, A.scale[oc])) continue;
+                    }
+                    if (den == 0.f) continue;
+                    const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, x2), __fmul_rn(lb, y2)), lc);
+                    const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                    if (!((double)dsqr < 3.84 * (double)A.sigma2[oc])) continue;
+                    key1 = min(key1, ((unsigned)dist << 16) | (unsigned)(0xffff - (p - b0)));
+                }
+                K1 = __reduce_min_sync(0xffffffffu, key1);
+                accept = K1 != 0xffffffffu;
+                if (accept) K1 = (K1 & 0xffff0000u) | (0xffffu - (K1 & 0xffffu));
+            } else {
             for (int p = b0 + lane; p < b1; p += 32) {
                 const int realF = (int)(uint32_t)fkey[p];
                 if (taken[realF]) continue;                          // :214
@@ -159,11 +197,13 @@ __global__ void __launch_bounds__(kBowThreads) bow_search_kernel(const BowArgs A
                 if (key < key1) { d2 = min(d2, (int)(key1 >> 16)); key1 = key; }
                 else d2 = min(d2, dist);
             }
-            const unsigned K1 = __reduce_min_sync(0xffffffffu, key1);
+            K1 = __reduce_min_sync(0xffffffffu, key1);
             const int c2 = key1 == K1 ? d2 : min((int)(key1 >> 16), 256);
             const int best2 = __reduce_min_sync(0xffffffffu, c2 > 256 ? 256 : c2);
             const int best1 = K1 == 0xffffffffu ? 256 : (int)(K1 >> 16);
-            if ((A.pair_mode ? best1 < kBowThLow : best1 <= kBowThLow) && (float)best1 < __fmul_rn(A.nnratio, (float)best2)) {        // :237-240 / :599-601
+            accept = (A.pair_mode ? best1 < kBowThLow : best1 <= kBowThLow) && (float)best1 < __fmul_rn(A.nnratio, (float)best2);        // :237-240 / :599-601
+            }
+            if (accept) {
                 const int realF = (int)(uint32_t)fkey[b0 + (int)(K1 & 0xffffu)];
                 if (lane == 0) {
                     taken[realF] = 1;
@@ -278,7 +318,14 @@ SGS_API int sgs_match_bow_batch_device(const sgs_bow_batch* a, int nframes, void
     if (a->kf_cap < 1 || a->f_cap < 1 || a->kf_cap > 8192 || a->f_cap > 8192) { set_error("sgs_match_bow_batch_device: at most 8192 features per frame"); return SGS_ERR_UNSUPPORTED; }
     BowArgs A;
     A.kf_node = a->kf_node; A.kf_weight = a->kf_weight; A.kf_valid = a->kf_valid; A.kf_desc = a->kf_desc; A.kf_angle = a->kf_angle; A.kf_n = a->kf_n; A.kf_cap = a->kf_cap;
-    A.f_node = a->f_node; A.f_weight = a->f_weight; A.f_valid = a->f_valid; A.pair_mode = a->keyframe_pair ? 1 : 0; A.f_desc = a->f_desc; A.f_angle = a->f_angle; A.f_n = a->f_n; A.f_cap = a->f_cap;
+    A.f_node = a->f_node; A.f_weight = a->f_weight; A.f_valid = a->f_valid; A.pair_mode = a->keyframe_pair; A.f_desc = a->f_desc;
+    A.kf_stereo = a->kf_stereo; A.f_stereo = a->f_stereo; A.kf_xy = a->kf_xy; A.f_xy = a->f_xy; A.f_octave = a->f_octave; A.F12 = a->F12; A.epipole = a->epipole;
+    A.only_stereo = a->only_stereo;
+    for (int l = 0; l < 16; ++l) { A.sigma2[l] = a->level_sigma2[l]; A.scale[l] = a->scale_factors[l]; }
+    if (a->keyframe_pair < 0 || a->keyframe_pair > 2) { set_error("sgs_match_bow_batch_device: keyframe_pair must be 0, 1 or 2"); return SGS_ERR_INVALID; }
+    if (a->keyframe_pair == 2 && (!a->kf_stereo || !a->f_stereo || !a->kf_xy || !a->f_xy || !a->f_octave || !a->F12 || !a->epipole || !a->f_valid)) {
+        set_error("sgs_match_bow_batch_device: triangulation mode needs positions, octaves, stereo flags, F12 and the epipole"); return SGS_ERR_INVALID;
+    } A.f_angle = a->f_angle; A.f_n = a->f_n; A.f_cap = a->f_cap;
     A.nnratio = a->nnratio; A.check_ori = a->check_orientation; A.match_f = a->match_f; A.nmatches = a->nmatches;
     A.kf_pow2 = pow2_ge(a->kf_cap); A.f_pow2 = pow2_ge(a->f_cap);
     const size_t smem = 8 * (size_t)A.kf_pow2 + 8 * (size_t)A.f_pow2 + 4 * (size_t)(A.kf_pow2 + 1) + 4 * (size_t)(a->kf_cap > a->f_cap ? a->kf_cap : a->f_cap) + (size_t)A.f_cap + 16;
@@ -342,9 +389,9 @@ SGS_API int sgs_match_bow(int nkf, const int32_t* kf_node, const double* kf_weig
     SGS_H2D(h2d, d_kv, kf_valid, K); SGS_H2D(h2d, d_cnt, cnt, 12);
     if (h2d != cudaSuccess) { cudaFree(d); set_error("sgs_match_bow: %s", cudaGetErrorString(h2d)); return SGS_ERR_CUDA; }
     sgs_bow_batch b;
+    std::memset(&b, 0, sizeof b);
     b.kf_node = d_kn; b.kf_weight = d_kw; b.kf_valid = d_kv; b.kf_desc = d_kd; b.kf_angle = d_ka; b.kf_n = d_cnt; b.kf_cap = nkf;
     b.f_node = d_fn; b.f_weight = d_fw; b.f_desc = d_fd; b.f_angle = d_fa; b.f_n = d_cnt + 1; b.f_cap = nf;
-    b.f_valid = nullptr; b.keyframe_pair = 0;
     b.nnratio = nnratio; b.check_orientation = check_orientation; b.match_f = d_m; b.nmatches = d_cnt + 2;
     int rc = sgs_match_bow_batch_device(&b, 1, nullptr);
     cudaError_t e = cudaSuccess;

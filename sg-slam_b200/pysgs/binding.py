@@ -56,6 +56,8 @@ class BowBatch(C.Structure):
     _fields_ = [('kf_node', C.c_void_p), ('kf_weight', C.c_void_p), ('kf_valid', C.c_void_p), ('kf_desc', C.c_void_p), ('kf_angle', C.c_void_p), ('kf_n', C.c_void_p),
                 ('kf_cap', C.c_int32), ('f_node', C.c_void_p), ('f_weight', C.c_void_p), ('f_desc', C.c_void_p), ('f_angle', C.c_void_p), ('f_n', C.c_void_p),
                 ('f_cap', C.c_int32), ('f_valid', C.c_void_p), ('keyframe_pair', C.c_int32), ('nnratio', C.c_float), ('check_orientation', C.c_int32),
+                ('kf_stereo', C.c_void_p), ('f_stereo', C.c_void_p), ('kf_xy', C.c_void_p), ('f_xy', C.c_void_p), ('f_octave', C.c_void_p), ('F12', C.c_void_p),
+                ('epipole', C.c_void_p), ('level_sigma2', C.c_float * 16), ('scale_factors', C.c_float * 16), ('only_stereo', C.c_int32),
                 ('match_f', C.c_void_p), ('nmatches', C.c_void_p)]
 
 

@@ -154,3 +154,61 @@ def test_search_by_bow_keyframe_pair(seed, n1, n2, nnratio):
             assert np.all(valid2[om[sel]] == 1) and len(set(om[sel].tolist())) == int(sel.sum())       # only good map points, each used once
     finally:
         gv.close()
+
+
+@pytest.mark.parametrize('seed,only_stereo', [(1, 0), (2, 1), (3, 0)])
+def test_search_for_triangulation(seed, only_stereo):
+    """ORBmatcher::SearchForTriangulation + CheckDistEpipolarLine (src/ORBmatcher.cc:140-157, 659-827)."""
+    import torch
+    voc = S.random_vocabulary(17, k=10, L=3)
+    V = O.Vocabulary(voc['k'], voc['L'], voc['parent'], voc['desc'], voc['weight'])
+    gv = GpuVoc(voc)
+    try:
+        cap, n1, n2 = 1100, 1000, 1050
+        s = S.bow_pair_scenario(seed + 70, voc, n_kf=n1, n_f=n2, flips=30)
+        rs = np.random.RandomState(seed + 5)
+        tgt_desc = s['f_desc']
+        xy1 = np.c_[rs.uniform(20, 620, n1), rs.uniform(20, 460, n1)].astype(np.float32)
+        # frame-2 features: re-derive which key-frame feature each one copies by nearest descriptor, place it on / near the epipolar line y2 = y1
+        d1b = np.unpackbits(s['kf_desc'], axis=1).astype(np.int16); d2b = np.unpackbits(tgt_desc, axis=1).astype(np.int16)
+        src = np.array([int(np.argmin(np.abs(d1b - d2b[j]).sum(1))) for j in range(n2)])
+        xy2 = np.c_[xy1[src, 0] + rs.uniform(-40, 40, n2), xy1[src, 1] + rs.normal(0, 1.5, n2)].astype(np.float32)
+        oct2 = rs.randint(0, 8, n2).astype(np.int32)
+        free1 = (rs.rand(n1) < 0.8).astype(np.uint8); free2 = (rs.rand(n2) < 0.8).astype(np.uint8)
+        st1 = (rs.rand(n1) < 0.5).astype(np.uint8); st2 = (rs.rand(n2) < 0.5).astype(np.uint8)
+        F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)
+        ex, ey = np.float32(320.5), np.float32(240.25)
+        sf = S.scale_factors().astype(np.float32); sigma2 = (sf * sf).astype(np.float32)
+        _, ow1, on1 = V.transform(s['kf_desc'], 1); _, ow2, on2 = V.transform(tgt_desc, 1)
+        k1 = dict(node=on1, weight=ow1, free=free1, stereo=st1, desc=s['kf_desc'], xy=xy1, angle=s['kf_angle'])
+        k2 = dict(node=on2, weight=ow2, free=free2, stereo=st2, desc=tgt_desc, xy=xy2, octave=oct2, angle=s['f_angle'])
+        pad = lambda a, n, shape, dt: np.concatenate([np.asarray(a, dt), np.zeros((cap - n,) + shape, dt)])[None]
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        D1 = pad(s['kf_desc'], n1, (32,), np.uint8); D2 = pad(tgt_desc, n2, (32,), np.uint8)
+        c1 = np.array([n1], np.int32); c2 = np.array([n2], np.int32)
+        _, w1, nd1 = _transform_gpu(gv, D1, c1, 1); _, w2, nd2 = _transform_gpu(gv, D2, c2, 1)
+        t = dict(free1=dev(pad(free1, n1, (), np.uint8)), d1=dev(D1), a1=dev(pad(s['kf_angle'], n1, (), np.float32)), c1=dev(c1), st1=dev(pad(st1, n1, (), np.uint8)),
+                 xy1=dev(pad(xy1, n1, (2,), np.float32)), free2=dev(pad(free2, n2, (), np.uint8)), d2=dev(D2), a2=dev(pad(s['f_angle'], n2, (), np.float32)), c2=dev(c2),
+                 st2=dev(pad(st2, n2, (), np.uint8)), xy2=dev(pad(xy2, n2, (2,), np.float32)), o2=dev(pad(oct2, n2, (), np.int32)), F=dev(F12.reshape(1, 9)),
+                 ep=dev(np.array([[ex, ey]], np.float32)))
+        for ori in (0, 1):
+            m = torch.zeros((1, cap), dtype=torch.int32, device='cuda'); nm = torch.zeros(1, dtype=torch.int32, device='cuda')
+            a = B.BowBatch()
+            a.kf_node, a.kf_weight, a.kf_valid, a.kf_desc, a.kf_angle, a.kf_n, a.kf_cap = nd1.data_ptr(), w1.data_ptr(), t['free1'].data_ptr(), t['d1'].data_ptr(), t['a1'].data_ptr(), t['c1'].data_ptr(), cap
+            a.f_node, a.f_weight, a.f_desc, a.f_angle, a.f_n, a.f_cap = nd2.data_ptr(), w2.data_ptr(), t['d2'].data_ptr(), t['a2'].data_ptr(), t['c2'].data_ptr(), cap
+            a.f_valid, a.keyframe_pair, a.nnratio, a.check_orientation = t['free2'].data_ptr(), 2, 0.6, ori
+            a.kf_stereo, a.f_stereo, a.kf_xy, a.f_xy, a.f_octave, a.F12, a.epipole = t['st1'].data_ptr(), t['st2'].data_ptr(), t['xy1'].data_ptr(), t['xy2'].data_ptr(), t['o2'].data_ptr(), t['F'].data_ptr(), t['ep'].data_ptr()
+            for l in range(8):
+                a.level_sigma2[l] = float(sigma2[l]); a.scale_factors[l] = float(sf[l])
+            a.only_stereo, a.match_f, a.nmatches = only_stereo, m.data_ptr(), nm.data_ptr()
+            B.check(B.lib().sgs_match_bow_batch_device(C.byref(a), 1, C.c_void_p(0)))
+            torch.cuda.synchronize()
+            onm, om = O.search_for_triangulation(k1, k2, F12, ex, ey, sigma2, sf, bool(only_stereo), bool(ori))
+            assert int(nm.cpu()[0]) == onm and np.array_equal(m.cpu().numpy()[0, :n1], om), (ori, int(nm.cpu()[0]), onm)
+            assert onm > 20
+            sel = om >= 0
+            assert np.all(free1[sel] == 1) and np.all(free2[om[sel]] == 1)
+            if only_stereo:
+                assert np.all(st1[sel] == 1) and np.all(st2[om[sel]] == 1)
+    finally:
+        gv.close()
