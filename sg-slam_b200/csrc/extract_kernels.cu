@@ -273,6 +273,8 @@ struct CudaCtx {
     __device__ __forceinline__ int tid() const { return threadIdx.x; }
     __device__ __forceinline__ int nthreads() const { return blockDim.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ int group() const { return 32; }                     // a warp synchronises by itself
+    __device__ __forceinline__ void group_sync() const { __syncwarp(); }
 };
 
 __host__ __device__ inline size_t qt_node_bytes(int cap) {

@@ -13,6 +13,8 @@ struct HostCtx {
     int tid() const { return 0; }
     int nthreads() const { return 1; }
     void sync() const {}
+    int group() const { return 1; }
+    void group_sync() const {}
 };
 }  // namespace
 

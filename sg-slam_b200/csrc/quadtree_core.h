@@ -86,10 +86,18 @@ enum { QS_LEN = 0, QS_NEXP, QS_NFREE, QS_SEQ, QS_FINISH, QS_FINE, QS_NOUT, QS_NN
 // number of int32-equivalents needed for the node-side arrays given the node capacity
 SGS_HD int qt_pool_cap(int n_target, int n_ini) { return 2 * (n_target > 4 * n_ini ? n_target : 4 * n_ini) + 4 * n_ini + 16; }
 
+// Bitonic sort of n_sort (a power of two) unique keys.  Stages with a partner distance j > 32 run across the whole block (one barrier each);
+// the remaining stages of every merge only touch aligned chunks of 64 keys, which one group of threads (a warp on the device, the single
+// host thread in the check build) finishes chunk by chunk with its own cheap synchronisation.  The keys are unique, so the result does not
+// depend on how the network is scheduled.
 template <class Ctx>
 SGS_HD void qt_bitonic_sort(Ctx& ctx, uint64_t* a, int n_sort) {
+    const int W = ctx.group();
+    const int ngroups = ctx.nthreads() / W, gid = ctx.tid() / W, gl = ctx.tid() % W;
+    const int chunk = n_sort < 64 ? n_sort : 64;
     for (int k = 2; k <= n_sort; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+        int j = k >> 1;
+        for (; j > 32; j >>= 1) {
             for (int t = ctx.tid(); t < (n_sort >> 1); t += ctx.nthreads()) {
                 // t-th compare-exchange of this stage
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
@@ -100,6 +108,19 @@ SGS_HD void qt_bitonic_sort(Ctx& ctx, uint64_t* a, int n_sort) {
             }
             ctx.sync();
         }
+        for (int base = gid * chunk; base < n_sort; base += ngroups * chunk) {
+            for (int jj = j; jj > 0; jj >>= 1) {
+                for (int t = gl; t < (chunk >> 1); t += W) {
+                    const int i = base + (((t & ~(jj - 1)) << 1) | (t & (jj - 1)));
+                    const int p = i | jj;
+                    const bool up = ((i & k) == 0);
+                    const uint64_t x = a[i], y = a[p];
+                    if ((x > y) == up) { a[i] = y; a[p] = x; }
+                }
+                ctx.group_sync();
+            }
+        }
+        ctx.sync();
     }
 }
 
