@@ -426,6 +426,55 @@ def main():
     torch.cuda.synchronize()
     bow_ms = eb0.elapsed_time(eb1) / 5
 
+    # ---- Tracking::SearchLocalPoints of the same batch (not part of the metric): Frame::isInFrustum + SearchByProjection(F, local map, th) ------
+    # local map = 4 jittered copies of the last-frame points (M = 4 x ~1000 per frame), the frame keeps the matches of the step above
+    MCAP = 4 * pcap
+    rs_lm = np.random.RandomState(99 + rank)
+    lm_xyz = np.zeros((NB, MCAP, 3), np.float32); lm_desc = np.zeros((NB, MCAP, 32), np.uint8); lm_n = (4 * ti['ln']).astype(np.int32)
+    for c4 in range(4):
+        lm_xyz[:, c4 * pcap:(c4 + 1) * pcap] = ti['lxyz'] * (1 + rs_lm.normal(0, 0.002, (NB, pcap, 1))).astype(np.float32)
+        lm_desc[:, c4 * pcap:(c4 + 1) * pcap] = ti['ldesc']
+    for f in range(NB):          # compact the 4 copies so that the first lm_n[f] rows are the live points
+        m0 = int(ti['ln'][f])
+        for c4 in range(1, 4):
+            lm_xyz[f, c4 * m0:(c4 + 1) * m0] = lm_xyz[f, c4 * pcap:c4 * pcap + m0]; lm_desc[f, c4 * m0:(c4 + 1) * m0] = lm_desc[f, c4 * pcap:c4 * pcap + m0]
+    lm_dist = np.linalg.norm(lm_xyz, axis=2).astype(np.float32)
+    lm_nrm = (lm_xyz / np.maximum(lm_dist[..., None], 1e-6)).astype(np.float32)
+    lm_max = (lm_dist * 1.2 ** rs_lm.uniform(0.5, 6.5, lm_dist.shape)).astype(np.float32); lm_min = (lm_max / 1.2 ** 8).astype(np.float32)
+    dlm = {k2: torch.from_numpy(a2).cuda() for k2, a2 in dict(xyz=lm_xyz, desc=lm_desc, n=lm_n, nrm=lm_nrm, mx=lm_max, mn=lm_min, obs=np.ones((NB, MCAP), np.uint8)).items()}
+    lm_out = dict(inview=torch.zeros((NB, MCAP), dtype=torch.uint8, device='cuda'), px=torch.zeros((NB, MCAP), device='cuda'), py=torch.zeros((NB, MCAP), device='cuda'),
+                  pxr=torch.zeros((NB, MCAP), device='cuda'), lvl=torch.zeros((NB, MCAP), dtype=torch.int32, device='cuda'), vc=torch.zeros((NB, MCAP), device='cuda'))
+    rk, rd, ru, rc, rmp, rnm, rnc = v(), v(), v(), v(), v(), v(), v()
+    B.check(L.sgs_tracker_results_device(trk.h, C.byref(rk), C.byref(rd), C.byref(ru), C.byref(rc), C.byref(rmp), C.byref(rnm), C.byref(rnc)))
+    lm_fmp = torch.zeros((NB, cap), dtype=torch.int32, device='cuda'); lm_fobs = torch.ones((NB, cap), dtype=torch.uint8, device='cuda')
+    lm_nm = torch.zeros(NB, dtype=torch.int32, device='cuda'); lm_nc = torch.zeros(NB, dtype=torch.int64, device='cuda')
+    lm_fmp0 = torch.from_numpy(B.memcpy_d2h(np.zeros((NB, cap), np.int32), rmp.value)).cuda()
+    lm_matcher = B.Matcher(NB, cap, MCAP, device=local)
+    fa = B.FrustumBatch(); fa.cam = cam
+    fa.tcw, fa.mp_xyz, fa.mp_normal, fa.mp_min_dist, fa.mp_max_dist, fa.mp_n = dv['T'].data_ptr(), dlm['xyz'].data_ptr(), dlm['nrm'].data_ptr(), dlm['mn'].data_ptr(), dlm['mx'].data_ptr(), dlm['n'].data_ptr()
+    fa.point_cap, fa.viewing_cos_limit = MCAP, 0.5
+    fa.mp_inview, fa.proj_x, fa.proj_y, fa.proj_xr, fa.level, fa.view_cos = [lm_out[k2].data_ptr() for k2 in ('inview', 'px', 'py', 'pxr', 'lvl', 'vc')]
+    la = B.LocalMapBatch(); la.cam = cam
+    la.cur_kps, la.cur_desc, la.cur_uright, la.cur_n = rk.value, rd.value, ru.value, rc.value
+    la.mp_inview, la.proj_x, la.proj_y, la.proj_xr, la.level, la.view_cos = fa.mp_inview, fa.proj_x, fa.proj_y, fa.proj_xr, fa.level, fa.view_cos
+    la.mp_desc, la.mp_obs, la.mp_n, la.th, la.nnratio, la.id_base = dlm['desc'].data_ptr(), dlm['obs'].data_ptr(), dlm['n'].data_ptr(), 3.0, 0.8, 100000
+    la.f_mp, la.f_mp_obs, la.nmatches, la.ncand = lm_fmp.data_ptr(), lm_fobs.data_ptr(), lm_nm.data_ptr(), lm_nc.data_ptr()
+
+    def dev_localmap():
+        lm_fmp.copy_(lm_fmp0)          # the frame starts from the matches of SearchByProjection(cur, last)
+        B.check(L.sgs_frustum_batch_device(C.byref(fa), NB, v(st.cuda_stream)))
+        lm_matcher.localmap_batch(la, NB, st.cuda_stream)
+    with torch.cuda.stream(st):
+        dev_localmap()
+        el0, el1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        el0.record(st)
+        for _ in range(5):
+            dev_localmap()
+        el1.record(st)
+    torch.cuda.synchronize()
+    localmap_ms = el0.elapsed_time(el1) / 5
+    lm_stats = (float(lm_out['inview'].float().sum(1).mean().item()), float(lm_nm.float().mean().item()))
+
     step_host()   # e2e warm-up; its outputs are also used for the parity spot-check below
     counts_after = h_out['cnt'].numpy().copy(); nmatch = h_out['nm'].numpy().copy()
     F_dev = B.memcpy_d2h(np.zeros((NB, 9), np.float64), pF.value); F_info = B.memcpy_d2h(np.zeros((NB, 4), np.int32), pI.value)
@@ -571,6 +620,7 @@ def main():
                            'sharding': 'independent streams per rank, no data-path collective; one untimed ncclBroadcast of the vocabulary node descriptors (35.6 MB) at start-up',
                            'mean_keypoints': float(n0.mean()), 'mean_after_dynreject': float(counts_after.mean()), 'mean_matches': float(nmatch.mean()),
                            'ransac_iterations_mean': float(F_info[:, 2].mean()), 'ransac_inlier_ratio_mean': float((F_info[:, 1] / np.maximum(1, F_info[:, 0])).mean()),
+                           'search_local_points_ms_per_step': localmap_ms, 'search_local_points_note': 'Frame::isInFrustum + SearchByProjection(F, local map of %d points/frame, th=3): %.0f points in view, %.0f new matches per frame; timed separately, not part of value' % (int(lm_n.mean()), lm_stats[0], lm_stats[1]),
                            'bow_transform_ms_per_step': bow_ms, 'bow_note': 'Frame::ComputeBoW (DBoW2 transform, k=10 L=6 vocabulary of %d nodes) of the same %d frames, timed separately, not part of value' % (voc_nodes, NB),
                            'not_in_step': 'the detector (boxes precomputed)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps, 'roofline': roofline, 'cpu_baseline': cpu}
