@@ -227,6 +227,21 @@ SGS_API int sgs_match_project_keyframe(const sgs_frame_view* cur, const float* t
                                        const uint8_t* kf_desc, const float* kf_angle, const float* kf_min_dist, const float* kf_max_dist,
                                        float th, int orb_dist, int check_orientation, int32_t* cur_mp_inout, int* nmatches, int device);
 
+typedef struct sgs_fuse_batch {           /* search half of Fuse(KeyFrame*, const vector<MapPoint*>&, th), src/ORBmatcher.cc:829-980 */
+    sgs_camera cam;                       /* the key frame's intrinsics, image bounds and scale factors */
+    const sgs_keypoint* kf_kps; const uint8_t* kf_desc; const float* kf_uright; const int32_t* kf_n; int32_t kf_cap;   /* mvKeysUn, mDescriptors, mvuRight */
+    const float* tcw;                     /* [F][16] key-frame pose */
+    const float* ow;                      /* [F][3]  pKF->GetCameraCenter() */
+    const float* mp_xyz; const float* mp_normal; const float* mp_min_dist; const float* mp_max_dist;      /* [F][mp_cap](x3) */
+    const uint8_t* mp_desc;               /* [F][mp_cap][32] */
+    const uint8_t* mp_valid;              /* exists && !isBad() && !IsInKeyFrame(pKF) */
+    const int32_t* mp_n; int32_t mp_cap;
+    float th; float inv_level_sigma2[16]; /* pKF->mvInvLevelSigma2 */
+    int32_t* best_idx; int32_t* best_dist;/* out [F][mp_cap]: key-frame feature to fuse with (-1 / 256 when no candidate passed the gates); the caller
+                                             applies bestDist <= TH_LOW and the Replace / AddObservation side effects in order */
+} sgs_fuse_batch;
+SGS_API int sgs_fuse_search_batch_device(const sgs_fuse_batch* args, int nframes, void* stream);
+
 typedef struct sgs_localmap_batch {       /* SearchByProjection(Frame&, vector<MapPoint*>&, th), src/ORBmatcher.cc:45 */
     sgs_camera cam;
     const sgs_keypoint* cur_kps; const uint8_t* cur_desc; const float* cur_uright; const int32_t* cur_n;

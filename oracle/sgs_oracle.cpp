@@ -1029,6 +1029,69 @@ SGO_API int sgo_search_by_projection_kf(const SgoFrame* cur, const float* Tcw_cu
     return nmatches;
 }
 
+// The SEARCH half of ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th) (src/ORBmatcher.cc:829-980, called from
+// LocalMapping::SearchInNeighbors): for every candidate map point (mp_valid[i]: exists, !isBad(), !IsInKeyFrame(pKF)) the key-frame
+// feature it would be fused with -- best_idx[i] (-1: nothing passed the gates) and best_dist[i] (256 likewise).  The caller applies
+// "bestDist <= TH_LOW" and the map side effects (Replace / AddObservation) in order, exactly as the reference loop does; they do not
+// influence the search of later points.  kf: the key frame's mvKeysUn / mvuRight / mDescriptors and grid; Ow = pKF->GetCameraCenter().
+SGO_API int sgo_fuse_search(const SgoFrame* kf, const float* Tcw, const float* Ow, int nmp, const uint8_t* mp_valid, const float* mp_xyz, const float* mp_normal,
+                            const float* min_dist, const float* max_dist, const uint8_t* mp_desc, float th, const float* inv_level_sigma2,
+                            float log_scale_factor, int32_t* best_idx, int32_t* best_dist) {
+    FrameView F = to_view(kf); Grid g; build_grid(F, g);
+    float Rcw[9], tcw[3];
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) Rcw[3 * r + c] = Tcw[4 * r + c]; tcw[r] = Tcw[4 * r + 3]; }
+    std::vector<int> cand;
+    int nfound = 0;
+    for (int i = 0; i < nmp; i++) {
+        best_idx[i] = -1; best_dist[i] = 256;
+        if (!mp_valid[i]) continue;
+        const float* Xw = mp_xyz + 3 * i;
+        float p3Dc[3];
+        for (int r = 0; r < 3; r++) {   // gemm(Rcw, p3Dw, 1, tcw, 1): small-matrix path, float accumulation
+            const float acc = Rcw[3 * r] * Xw[0] + Rcw[3 * r + 1] * Xw[1] + Rcw[3 * r + 2] * Xw[2];
+            p3Dc[r] = (float)((double)acc + (double)tcw[r]);
+        }
+        if (p3Dc[2] < 0.0f) continue;
+        const float invz = 1 / p3Dc[2];
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float u = F.fx * x + F.cx, v = F.fy * y + F.cy;
+        if (!(u >= F.minX && u < F.maxX && v >= F.minY && v < F.maxY)) continue;        // KeyFrame::IsInImage
+        const float ur = u - F.bf * invz;
+        const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];
+        const float PO[3] = {Xw[0] - Ow[0], Xw[1] - Ow[1], Xw[2] - Ow[2]};
+        const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const float* Pn = mp_normal + 3 * i;
+        if (((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2]) < 0.5 * dist3D) continue;
+        const float ratio = max_dist[i] / dist3D;
+        int nPredictedLevel = (int)std::ceil(std::log(ratio) / log_scale_factor);
+        if (nPredictedLevel < 0) nPredictedLevel = 0; else if (nPredictedLevel >= F.nlevels) nPredictedLevel = F.nlevels - 1;
+        const float radius = th * F.scaleFactors[nPredictedLevel];
+        features_in_area(F, g, u, v, radius, -1, -1, cand);                             // KeyFrame::GetFeaturesInArea: no level filter
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            const int kpLevel = F.keysUn[idx].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const float kpx = F.keysUn[idx].x, kpy = F.keysUn[idx].y;
+            const float ex = u - kpx, ey = v - kpy;
+            if (F.uRight[idx] >= 0) {
+                const float er = ur - F.uRight[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+            } else {
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+            }
+            const int dist = descriptor_distance(mp_desc + 32 * (size_t)i, F.desc + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        best_idx[i] = bestIdx; best_dist[i] = bestDist;
+        if (bestIdx >= 0) nfound++;
+    }
+    return nfound;
+}
+
 // ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th), src/ORBmatcher.cc:45-129, with the
 // per-point fields that Frame::isInFrustum (src/Frame.cc:296-352) fills given as flat arrays:
 //   mp_inview[i] (mbTrackInView && !isBad()), projx/projy/projxr, level (mnTrackScaleLevel), viewcos, desc.

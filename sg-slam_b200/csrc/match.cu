@@ -588,6 +588,101 @@ int launch_match_lastframe(const LastFrameArgs& A, int nframes, cudaStream_t st)
     return SGS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Search half of ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:829-980, LocalMapping::SearchInNeighbors).  Every map point is
+// independent (the reference's side effects -- Replace / AddObservation -- do not feed back into the search), so the block only shares
+// the key frame's grid: kGroup lanes per map point scan its window, the best (distance, grid position) key is min-reduced over the
+// group, which is the first minimum of the reference's loop over vIndices.
+__global__ void __launch_bounds__(kMatchThreads) fuse_search_kernel(const __grid_constant__ FuseArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    FrameSmem s;
+    carve(smem, A.kf_cap, s);
+    const int f = blockIdx.x;
+    const int n = min(A.kf_n[f], A.kf_cap), nmp = min(A.mp_n[f], A.mp_cap);
+    s.n = n;
+    const sgs_keypoint* kps = A.kf_kps + (int64_t)f * A.kf_cap;
+    const uint4* kf_desc = reinterpret_cast<const uint4*>(A.kf_desc + (int64_t)f * A.kf_cap * 32);
+    build_frame_grid(A.cam, kps, A.kf_uright + (int64_t)f * A.kf_cap, n, s);
+    const float* T = A.tcw + 16 * (int64_t)f; const float* O = A.ow + 3 * (int64_t)f;
+    const int64_t lo = (int64_t)f * A.mp_cap;
+    const float w_inv = __fdiv_rn((float)kGridCols, __fsub_rn(A.cam.max_x, A.cam.min_x));
+    const float h_inv = __fdiv_rn((float)kGridRows, __fsub_rn(A.cam.max_y, A.cam.min_y));
+    const int gl = threadIdx.x & (kGroup - 1), ngroups = blockDim.x / kGroup;
+    for (int i0 = 0; i0 < nmp; i0 += ngroups) {
+        const int i = i0 + threadIdx.x / kGroup;
+        uint32_t best = kNoKey;
+        if (i < nmp && A.mp_valid[lo + i]) {
+            const float* X = A.mp_xyz + 3 * (lo + i);
+            float pc[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {      // Rcw * p3Dw + tcw: small-matrix gemm path (float accumulation)
+                const float acc = __fadd_rn(__fadd_rn(__fmul_rn(T[4 * r], X[0]), __fmul_rn(T[4 * r + 1], X[1])), __fmul_rn(T[4 * r + 2], X[2]));
+                pc[r] = (float)__dadd_rn((double)acc, (double)T[4 * r + 3]);
+            }
+            bool ok = !(pc[2] < 0.0f);
+            const float invz = __fdiv_rn(1.f, pc[2]);
+            const float u = __fadd_rn(__fmul_rn(A.cam.fx, __fmul_rn(pc[0], invz)), A.cam.cx), v = __fadd_rn(__fmul_rn(A.cam.fy, __fmul_rn(pc[1], invz)), A.cam.cy);
+            ok = ok && (u >= A.cam.min_x && u < A.cam.max_x && v >= A.cam.min_y && v < A.cam.max_y);        // KeyFrame::IsInImage
+            const float ur = __fsub_rn(u, __fmul_rn(A.cam.bf, invz));
+            const float maxd = A.mp_max_dist[lo + i];
+            const float px = __fsub_rn(X[0], O[0]), py = __fsub_rn(X[1], O[1]), pz = __fsub_rn(X[2], O[2]);
+            const float dist = (float)sqrt(((double)px * px + (double)py * py) + (double)pz * pz);
+            ok = ok && !(dist < __fmul_rn(0.8f, A.mp_min_dist[lo + i]) || dist > __fmul_rn(1.2f, maxd));
+            const float* N = A.mp_normal + 3 * (lo + i);
+            ok = ok && !((((double)px * N[0] + (double)py * N[1]) + (double)pz * N[2]) < 0.5 * (double)dist);
+            if (ok) {
+                int lvl = (int)ceilf(__fdiv_rn((float)log((double)__fdiv_rn(maxd, dist)), A.log_sf));
+                lvl = lvl < 0 ? 0 : (lvl >= A.cam.nlevels ? A.cam.nlevels - 1 : lvl);
+                const float r = __fmul_rn(A.th, A.cam.scale[lvl]);
+                const int min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, A.cam.min_x), r), w_inv)));
+                const int max_cx = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, A.cam.min_x), r), w_inv)));
+                const int min_cy = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, A.cam.min_y), r), h_inv)));
+                const int max_cy = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, A.cam.min_y), r), h_inv)));
+                if (min_cx < kGridCols && max_cx >= 0 && min_cy < kGridRows && max_cy >= 0) {
+                    const uint4* dm = reinterpret_cast<const uint4*>(A.mp_desc + 32 * (lo + i));
+                    const uint4 d0 = __ldg(dm), d1 = __ldg(dm + 1);
+                    for (int ix = min_cx; ix <= max_cx; ++ix) {
+                        const int beg = s.cell_start[ix * kGridRows + min_cy], end = s.cell_start[ix * kGridRows + max_cy + 1];
+                        for (int j = beg + gl; j < end; j += kGroup) {
+                            const int idx = s.order[j];
+                            const float ex = __fsub_rn(u, s.kx[idx]), ey = __fsub_rn(v, s.ky[idx]);
+                            if (!(fabsf(ex) < r && fabsf(ey) < r)) continue;          // GetFeaturesInArea: |kp - (u, v)| < r (same value as distx = kp - x)
+                            const int o = s.oct[idx];
+                            if (o < lvl - 1 || o > lvl) continue;
+                            const float kr = s.ur[idx];
+                            if (kr >= 0.f) {
+                                const float er = __fsub_rn(ur, kr);
+                                const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+                                if ((double)__fmul_rn(e2, A.inv_sigma2[o]) > 7.8) continue;
+                            } else {
+                                const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                                if ((double)__fmul_rn(e2, A.inv_sigma2[o]) > 5.99) continue;
+                            }
+                            const uint32_t k = ((uint32_t)popc256(d0, d1, __ldg(&kf_desc[2 * idx]), __ldg(&kf_desc[2 * idx + 1])) << 16) | (uint32_t)j;
+                            best = min(best, k);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = kGroup >> 1; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (gl == 0 && i < nmp) {
+            A.best_idx[lo + i] = best == kNoKey ? -1 : (int)s.order[best & 0xFFFFu];
+            A.best_dist[lo + i] = best == kNoKey ? 256 : (int)(best >> 16);
+        }
+    }
+}
+
+int launch_fuse_search(const FuseArgs& A, int nframes, cudaStream_t st) {
+    const size_t smem = frame_smem_bytes(A.kf_cap);
+    if (smem > 200 * 1024 || A.kf_cap > 65535) { set_error("fuse: kf_cap %d too large for shared memory", A.kf_cap); return SGS_ERR_UNSUPPORTED; }
+    SGS_CUDA_TRY(cudaFuncSetAttribute(fuse_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fuse_search_kernel<<<nframes, kMatchThreads, smem, st>>>(A);
+    SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+
 int launch_match_localmap(const LocalMapArgs& A, int nframes, cudaStream_t st) {
     const size_t smem = match_smem_bytes(A.cur_cap);
     if (smem > 200 * 1024 || A.cur_cap > 65535) { set_error("match: cur_cap %d too large for shared memory", A.cur_cap); return SGS_ERR_UNSUPPORTED; }

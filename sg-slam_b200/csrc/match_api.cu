@@ -94,6 +94,22 @@ SGS_API int sgs_match_project_lastframe_batch_device(sgs_matcher* m, const sgs_l
     return launch_match_lastframe(A, nframes, (cudaStream_t)stream);
 }
 
+SGS_API int sgs_fuse_search_batch_device(const sgs_fuse_batch* a, int nframes, void* stream) {
+    if (!a || !a->kf_kps || !a->kf_desc || !a->kf_uright || !a->kf_n || !a->tcw || !a->ow || !a->mp_xyz || !a->mp_normal || !a->mp_min_dist || !a->mp_max_dist ||
+        !a->mp_desc || !a->mp_valid || !a->mp_n || !a->best_idx || !a->best_dist || nframes < 1 || a->kf_cap < 1 || a->mp_cap < 1) {
+        set_error("sgs_fuse_search_batch_device: bad argument"); return SGS_ERR_INVALID;
+    }
+    if (a->cam.nlevels < 2 || a->cam.nlevels > kMaxLevels || !(a->cam.scale_factors[1] > 1.f)) { set_error("sgs_fuse_search_batch_device: camera scale table missing"); return SGS_ERR_INVALID; }
+    FuseArgs A;
+    A.cam = to_cam(a->cam);
+    A.kf_kps = a->kf_kps; A.kf_desc = a->kf_desc; A.kf_uright = a->kf_uright; A.kf_n = a->kf_n; A.kf_cap = a->kf_cap;
+    A.tcw = a->tcw; A.ow = a->ow; A.mp_xyz = a->mp_xyz; A.mp_normal = a->mp_normal; A.mp_min_dist = a->mp_min_dist; A.mp_max_dist = a->mp_max_dist;
+    A.mp_desc = a->mp_desc; A.mp_valid = a->mp_valid; A.mp_n = a->mp_n; A.mp_cap = a->mp_cap; A.th = a->th; A.log_sf = logf(a->cam.scale_factors[1]);
+    for (int l = 0; l < kMaxLevels; ++l) A.inv_sigma2[l] = a->inv_level_sigma2[l];
+    A.best_idx = a->best_idx; A.best_dist = a->best_dist;
+    return launch_fuse_search(A, nframes, (cudaStream_t)stream);
+}
+
 SGS_API int sgs_match_project_keyframe_batch_device(sgs_matcher* m, const sgs_keyframe_batch* a, int nframes, void* stream) {
     if (!m || !a) { set_error("sgs_match_project_keyframe_batch_device: NULL"); return SGS_ERR_INVALID; }
     if (nframes < 1 || nframes > m->max_frames) { set_error("nframes outside [1,max_frames]"); return SGS_ERR_INVALID; }

@@ -56,7 +56,18 @@ struct LocalMapArgs {
     LocalPre* pre;
 };
 
+struct FuseArgs {                 // search half of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th), src/ORBmatcher.cc:829-980
+    MatchCam cam;
+    const sgs_keypoint* kf_kps; const uint8_t* kf_desc; const float* kf_uright; const int32_t* kf_n; int32_t kf_cap;
+    const float* tcw; const float* ow;            // [nframes][16], [nframes][3]
+    const float* mp_xyz; const float* mp_normal; const float* mp_min_dist; const float* mp_max_dist; const uint8_t* mp_desc; const uint8_t* mp_valid;
+    const int32_t* mp_n; int32_t mp_cap;
+    float th, log_sf; float inv_sigma2[kMaxLevels];
+    int32_t* best_idx; int32_t* best_dist;
+};
+
 int launch_match_lastframe(const LastFrameArgs& A, int nframes, cudaStream_t st);
+int launch_fuse_search(const FuseArgs& A, int nframes, cudaStream_t st);
 int launch_match_localmap(const LocalMapArgs& A, int nframes, cudaStream_t st);
 
 }  // namespace sgs

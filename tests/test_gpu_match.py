@@ -195,3 +195,39 @@ def test_keyframe_projection_matcher(seed, ncur, nkf, orb_dist, th):
         assert nm_g == nm_o and np.array_equal(mp_g, mp_o)
         assert nm_o > 20
         assert np.array_equal(mp_g[s['cur_mp'] >= 0], s['cur_mp'][s['cur_mp'] >= 0])        # keypoints that already held a map point are never touched
+
+
+@pytest.mark.parametrize('seed,ncur,nmp,th', [(1, 1000, 1000, 3.0), (2, 1500, 3000, 3.0), (3, 400, 2000, 5.0)])
+def test_fuse_search(seed, ncur, nmp, th):
+    """Search half of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:829-980)."""
+    import ctypes as C
+    import torch
+    s = S.keyframe_scenario(seed, n_cur=ncur, n_kf=nmp, conflict=0.3)
+    cam = s['cam']; sf = s['sf'].astype(np.float32)
+    rs = np.random.RandomState(seed + 7)
+    R = s['Tcw_cur'][:3, :3].astype(np.float64); t = s['Tcw_cur'][:3, 3].astype(np.float64)
+    Ow = (-(R.T @ t)).astype(np.float32)
+    to = s['last_xyz'].astype(np.float64) - Ow.astype(np.float64); d = np.linalg.norm(to, axis=1)
+    nrm = to / np.maximum(d[:, None], 1e-9) + rs.normal(0, 0.6, (nmp, 3)); nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    inv_s2 = (1.0 / (sf * sf)).astype(np.float32)
+    fo = O.FrameArrays(s['kps'], s['uright'], s['desc'], 640, 480, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], s['sf'])
+    bi_o, bd_o = O.fuse_search(fo, s['Tcw_cur'], Ow, s['kf_valid'], s['last_xyz'], nrm, s['min_dist'], s['max_dist'], s['last_desc'], th, inv_s2)
+    assert (bi_o >= 0).sum() > 30 and (bd_o[bi_o >= 0] <= 50).sum() > 10
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    kcap, mcap = ncur + 5, nmp + 3
+    pad = lambda a, cap: np.concatenate([a, np.zeros((cap - len(a),) + a.shape[1:], a.dtype)])[None]
+    t_ = dict(kps=dev(pad(s['kps'], kcap).view(np.uint8).reshape(-1)), kd=dev(pad(s['desc'], kcap)), ur=dev(pad(s['uright'].astype(np.float32), kcap)), kn=dev(np.array([ncur], np.int32)),
+              T=dev(s['Tcw_cur'].astype(np.float32).reshape(1, 16)), ow=dev(Ow.reshape(1, 3)), xyz=dev(pad(s['last_xyz'], mcap)), nrm=dev(pad(nrm, mcap)),
+              mn=dev(pad(s['min_dist'], mcap)), mx=dev(pad(s['max_dist'], mcap)), md=dev(pad(s['last_desc'], mcap)), mv=dev(pad(s['kf_valid'], mcap)), mn_=dev(np.array([nmp], np.int32)))
+    bi = torch.zeros((1, mcap), dtype=torch.int32, device='cuda'); bd = torch.zeros((1, mcap), dtype=torch.int32, device='cuda')
+    a = B.FuseBatch()
+    a.cam = B.make_camera(640, 480, cam, s['sf'])
+    a.kf_kps, a.kf_desc, a.kf_uright, a.kf_n, a.kf_cap = t_['kps'].data_ptr(), t_['kd'].data_ptr(), t_['ur'].data_ptr(), t_['kn'].data_ptr(), kcap
+    a.tcw, a.ow, a.mp_xyz, a.mp_normal, a.mp_min_dist, a.mp_max_dist = t_['T'].data_ptr(), t_['ow'].data_ptr(), t_['xyz'].data_ptr(), t_['nrm'].data_ptr(), t_['mn'].data_ptr(), t_['mx'].data_ptr()
+    a.mp_desc, a.mp_valid, a.mp_n, a.mp_cap, a.th = t_['md'].data_ptr(), t_['mv'].data_ptr(), t_['mn_'].data_ptr(), mcap, th
+    for l in range(8):
+        a.inv_level_sigma2[l] = float(inv_s2[l])
+    a.best_idx, a.best_dist = bi.data_ptr(), bd.data_ptr()
+    B.check(B.lib().sgs_fuse_search_batch_device(C.byref(a), 1, C.c_void_p(0)))
+    torch.cuda.synchronize()
+    assert np.array_equal(bi.cpu().numpy()[0, :nmp], bi_o) and np.array_equal(bd.cpu().numpy()[0, :nmp], bd_o)
