@@ -237,6 +237,8 @@ typedef struct sgs_fuse_batch {           /* search half of Fuse(KeyFrame*, cons
     const uint8_t* mp_valid;              /* exists && !isBad() && !IsInKeyFrame(pKF) */
     const int32_t* mp_n; int32_t mp_cap;
     float th; float inv_level_sigma2[16]; /* pKF->mvInvLevelSigma2 */
+    int32_t sim3_variant;                 /* 1: Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:982-1104): tcw / ow hold the
+                                             Rcw, tcw and Ow the caller decomposed from Scw (:988-992); no chi-square gates */
     int32_t* best_idx; int32_t* best_dist;/* out [F][mp_cap]: key-frame feature to fuse with (-1 / 256 when no candidate passed the gates); the caller
                                              applies bestDist <= TH_LOW and the Replace / AddObservation side effects in order */
 } sgs_fuse_batch;

@@ -1036,7 +1036,9 @@ SGO_API int sgo_search_by_projection_kf(const SgoFrame* cur, const float* Tcw_cu
 // influence the search of later points.  kf: the key frame's mvKeysUn / mvuRight / mDescriptors and grid; Ow = pKF->GetCameraCenter().
 SGO_API int sgo_fuse_search(const SgoFrame* kf, const float* Tcw, const float* Ow, int nmp, const uint8_t* mp_valid, const float* mp_xyz, const float* mp_normal,
                             const float* min_dist, const float* max_dist, const uint8_t* mp_desc, float th, const float* inv_level_sigma2,
-                            float log_scale_factor, int32_t* best_idx, int32_t* best_dist) {
+                            float log_scale_factor, int sim3_variant, int32_t* best_idx, int32_t* best_dist) {
+    // sim3_variant: Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:982-1104, loop closing) with Rcw / tcw / Ow already
+    // decomposed from Scw by the caller (:988-992): invz = 1.0 / z in double, no chi-square gates
     FrameView F = to_view(kf); Grid g; build_grid(F, g);
     float Rcw[9], tcw[3];
     for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) Rcw[3 * r + c] = Tcw[4 * r + c]; tcw[r] = Tcw[4 * r + 3]; }
@@ -1052,7 +1054,7 @@ SGO_API int sgo_fuse_search(const SgoFrame* kf, const float* Tcw, const float* O
             p3Dc[r] = (float)((double)acc + (double)tcw[r]);
         }
         if (p3Dc[2] < 0.0f) continue;
-        const float invz = 1 / p3Dc[2];
+        const float invz = sim3_variant ? (float)(1.0 / p3Dc[2]) : 1 / p3Dc[2];
         const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
         const float u = F.fx * x + F.cx, v = F.fy * y + F.cy;
         if (!(u >= F.minX && u < F.maxX && v >= F.minY && v < F.maxY)) continue;        // KeyFrame::IsInImage
@@ -1075,7 +1077,8 @@ SGO_API int sgo_fuse_search(const SgoFrame* kf, const float* Tcw, const float* O
             if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
             const float kpx = F.keysUn[idx].x, kpy = F.keysUn[idx].y;
             const float ex = u - kpx, ey = v - kpy;
-            if (F.uRight[idx] >= 0) {
+            if (sim3_variant) {
+            } else if (F.uRight[idx] >= 0) {
                 const float er = ur - F.uRight[idx];
                 const float e2 = ex * ex + ey * ey + er * er;
                 if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;

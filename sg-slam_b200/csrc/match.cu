@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(kMatchThreads) fuse_search_kernel(const __grid
                 pc[r] = (float)__dadd_rn((double)acc, (double)T[4 * r + 3]);
             }
             bool ok = !(pc[2] < 0.0f);
-            const float invz = __fdiv_rn(1.f, pc[2]);
+            const float invz = A.sim3_variant ? (float)__ddiv_rn(1.0, (double)pc[2]) : __fdiv_rn(1.f, pc[2]);
             const float u = __fadd_rn(__fmul_rn(A.cam.fx, __fmul_rn(pc[0], invz)), A.cam.cx), v = __fadd_rn(__fmul_rn(A.cam.fy, __fmul_rn(pc[1], invz)), A.cam.cy);
             ok = ok && (u >= A.cam.min_x && u < A.cam.max_x && v >= A.cam.min_y && v < A.cam.max_y);        // KeyFrame::IsInImage
             const float ur = __fsub_rn(u, __fmul_rn(A.cam.bf, invz));
@@ -650,7 +650,8 @@ __global__ void __launch_bounds__(kMatchThreads) fuse_search_kernel(const __grid
                             const int o = s.oct[idx];
                             if (o < lvl - 1 || o > lvl) continue;
                             const float kr = s.ur[idx];
-                            if (kr >= 0.f) {
+                            if (A.sim3_variant) {
+                            } else if (kr >= 0.f) {
                                 const float er = __fsub_rn(ur, kr);
                                 const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
                                 if ((double)__fmul_rn(e2, A.inv_sigma2[o]) > 7.8) continue;
