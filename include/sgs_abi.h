@@ -238,7 +238,11 @@ typedef struct sgs_fuse_batch {           /* search half of Fuse(KeyFrame*, cons
     const int32_t* mp_n; int32_t mp_cap;
     float th; float inv_level_sigma2[16]; /* pKF->mvInvLevelSigma2 */
     int32_t sim3_variant;                 /* 1: Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:982-1104): tcw / ow hold the
-                                             Rcw, tcw and Ow the caller decomposed from Scw (:988-992); no chi-square gates */
+                                             Rcw, tcw and Ow the caller decomposed from Scw (:988-992); no chi-square gates
+                                             2: one direction of SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (:1106-1330): tcw = pose of the key
+                                             frame that OWNS the points, xform2 = [sR21 | t21] (:1122-1124), kf_* = the other key frame; distance |p3Dc2|,
+                                             no viewing-angle test (mp_normal / ow unused); the caller applies <= TH_HIGH and the mutual check (:1314-1327) */
+    const float* xform2;                  /* [F][12] (3x3 row major + 3), variant 2 only */
     int32_t* best_idx; int32_t* best_dist;/* out [F][mp_cap]: key-frame feature to fuse with (-1 / 256 when no candidate passed the gates); the caller
                                              applies bestDist <= TH_LOW and the Replace / AddObservation side effects in order */
 } sgs_fuse_batch;

@@ -414,7 +414,7 @@ def search_for_triangulation(k1, k2, F12, ex, ey, sigma2, scale, only_stereo=Fal
     return nm, m
 
 
-def fuse_search(kf, Tcw, Ow, mp_valid, mp_xyz, mp_normal, min_dist, max_dist, mp_desc, th, inv_level_sigma2, log_scale_factor=None, sim3_variant=False):
+def fuse_search(kf, Tcw, Ow, mp_valid, mp_xyz, mp_normal, min_dist, max_dist, mp_desc, th, inv_level_sigma2, log_scale_factor=None, sim3_variant=0, xform2=None):
     """Search half of ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:829-980): (best_idx, best_dist) per map point."""
     f32 = np.float32
     a = [np.ascontiguousarray(mp_valid, np.uint8), np.ascontiguousarray(mp_xyz, f32), np.ascontiguousarray(mp_normal, f32), np.ascontiguousarray(min_dist, f32),
@@ -424,5 +424,6 @@ def fuse_search(kf, Tcw, Ow, mp_valid, mp_xyz, mp_normal, min_dist, max_dist, mp
     if log_scale_factor is None:
         log_scale_factor = float(f32(np.log(f32(1.2))))
     T = np.ascontiguousarray(Tcw, f32); O_ = np.ascontiguousarray(Ow, f32); s2 = np.ascontiguousarray(inv_level_sigma2, f32)
-    lib().sgo_fuse_search(C.byref(kf.c), _p(T), _p(O_), n, *[_p(x) for x in a], C.c_float(th), _p(s2), C.c_float(log_scale_factor), int(sim3_variant), _p(bi), _p(bd))
+    lib().sgo_fuse_search(C.byref(kf.c), _p(T), _p(O_), n, *[_p(x) for x in a], C.c_float(th), _p(s2), C.c_float(log_scale_factor), int(sim3_variant),
+                          _p(np.ascontiguousarray(xform2, f32)) if xform2 is not None else None, _p(bi), _p(bd))
     return bi, bd

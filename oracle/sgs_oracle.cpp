@@ -1036,7 +1036,10 @@ SGO_API int sgo_search_by_projection_kf(const SgoFrame* cur, const float* Tcw_cu
 // influence the search of later points.  kf: the key frame's mvKeysUn / mvuRight / mDescriptors and grid; Ow = pKF->GetCameraCenter().
 SGO_API int sgo_fuse_search(const SgoFrame* kf, const float* Tcw, const float* Ow, int nmp, const uint8_t* mp_valid, const float* mp_xyz, const float* mp_normal,
                             const float* min_dist, const float* max_dist, const uint8_t* mp_desc, float th, const float* inv_level_sigma2,
-                            float log_scale_factor, int sim3_variant, int32_t* best_idx, int32_t* best_dist) {
+                            float log_scale_factor, int sim3_variant, const float* xform2, int32_t* best_idx, int32_t* best_dist) {
+    // sim3_variant == 2: one direction of ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1106-1330): p3Dc1 = R1w p3Dw + t1w (Tcw), p3Dc2 = sR21 p3Dc1 + t21
+    // (xform2 = 3x3 row major + 3, computed by the caller :1122-1124), distance = |p3Dc2|, no viewing-angle test, no chi-square gates; the caller
+    // applies bestDist <= TH_HIGH and the mutual-agreement check (:1314-1327)
     // sim3_variant: Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:982-1104, loop closing) with Rcw / tcw / Ow already
     // decomposed from Scw by the caller (:988-992): invz = 1.0 / z in double, no chi-square gates
     FrameView F = to_view(kf); Grid g; build_grid(F, g);
@@ -1053,6 +1056,14 @@ SGO_API int sgo_fuse_search(const SgoFrame* kf, const float* Tcw, const float* O
             const float acc = Rcw[3 * r] * Xw[0] + Rcw[3 * r + 1] * Xw[1] + Rcw[3 * r + 2] * Xw[2];
             p3Dc[r] = (float)((double)acc + (double)tcw[r]);
         }
+        if (sim3_variant == 2) {
+            float q[3];
+            for (int r = 0; r < 3; r++) {
+                const float acc = xform2[3 * r] * p3Dc[0] + xform2[3 * r + 1] * p3Dc[1] + xform2[3 * r + 2] * p3Dc[2];
+                q[r] = (float)((double)acc + (double)xform2[9 + r]);
+            }
+            p3Dc[0] = q[0]; p3Dc[1] = q[1]; p3Dc[2] = q[2];
+        }
         if (p3Dc[2] < 0.0f) continue;
         const float invz = sim3_variant ? (float)(1.0 / p3Dc[2]) : 1 / p3Dc[2];
         const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
@@ -1060,11 +1071,12 @@ SGO_API int sgo_fuse_search(const SgoFrame* kf, const float* Tcw, const float* O
         if (!(u >= F.minX && u < F.maxX && v >= F.minY && v < F.maxY)) continue;        // KeyFrame::IsInImage
         const float ur = u - F.bf * invz;
         const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];
-        const float PO[3] = {Xw[0] - Ow[0], Xw[1] - Ow[1], Xw[2] - Ow[2]};
+        float PO[3] = {Xw[0] - Ow[0], Xw[1] - Ow[1], Xw[2] - Ow[2]};
+        if (sim3_variant == 2) { PO[0] = p3Dc[0]; PO[1] = p3Dc[1]; PO[2] = p3Dc[2]; }      // cv::norm(p3Dc2)
         const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
         if (dist3D < minDistance || dist3D > maxDistance) continue;
         const float* Pn = mp_normal + 3 * i;
-        if (((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2]) < 0.5 * dist3D) continue;
+        if (sim3_variant != 2 && ((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2]) < 0.5 * dist3D) continue;
         const float ratio = max_dist[i] / dist3D;
         int nPredictedLevel = (int)std::ceil(std::log(ratio) / log_scale_factor);
         if (nPredictedLevel < 0) nPredictedLevel = 0; else if (nPredictedLevel >= F.nlevels) nPredictedLevel = F.nlevels - 1;

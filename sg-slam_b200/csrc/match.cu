@@ -619,17 +619,28 @@ __global__ void __launch_bounds__(kMatchThreads) fuse_search_kernel(const __grid
                 const float acc = __fadd_rn(__fadd_rn(__fmul_rn(T[4 * r], X[0]), __fmul_rn(T[4 * r + 1], X[1])), __fmul_rn(T[4 * r + 2], X[2]));
                 pc[r] = (float)__dadd_rn((double)acc, (double)T[4 * r + 3]);
             }
+            if (A.sim3_variant == 2) {          // p3Dc2 = sR21 * p3Dc1 + t21
+                const float* S = A.xform2 + 12 * (int64_t)f;
+                float q[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float acc = __fadd_rn(__fadd_rn(__fmul_rn(S[3 * r], pc[0]), __fmul_rn(S[3 * r + 1], pc[1])), __fmul_rn(S[3 * r + 2], pc[2]));
+                    q[r] = (float)__dadd_rn((double)acc, (double)S[9 + r]);
+                }
+                pc[0] = q[0]; pc[1] = q[1]; pc[2] = q[2];
+            }
             bool ok = !(pc[2] < 0.0f);
             const float invz = A.sim3_variant ? (float)__ddiv_rn(1.0, (double)pc[2]) : __fdiv_rn(1.f, pc[2]);
             const float u = __fadd_rn(__fmul_rn(A.cam.fx, __fmul_rn(pc[0], invz)), A.cam.cx), v = __fadd_rn(__fmul_rn(A.cam.fy, __fmul_rn(pc[1], invz)), A.cam.cy);
             ok = ok && (u >= A.cam.min_x && u < A.cam.max_x && v >= A.cam.min_y && v < A.cam.max_y);        // KeyFrame::IsInImage
             const float ur = __fsub_rn(u, __fmul_rn(A.cam.bf, invz));
             const float maxd = A.mp_max_dist[lo + i];
-            const float px = __fsub_rn(X[0], O[0]), py = __fsub_rn(X[1], O[1]), pz = __fsub_rn(X[2], O[2]);
+            const bool cam2 = A.sim3_variant == 2;
+            const float px = cam2 ? pc[0] : __fsub_rn(X[0], O[0]), py = cam2 ? pc[1] : __fsub_rn(X[1], O[1]), pz = cam2 ? pc[2] : __fsub_rn(X[2], O[2]);
             const float dist = (float)sqrt(((double)px * px + (double)py * py) + (double)pz * pz);
             ok = ok && !(dist < __fmul_rn(0.8f, A.mp_min_dist[lo + i]) || dist > __fmul_rn(1.2f, maxd));
             const float* N = A.mp_normal + 3 * (lo + i);
-            ok = ok && !((((double)px * N[0] + (double)py * N[1]) + (double)pz * N[2]) < 0.5 * (double)dist);
+            ok = ok && (cam2 || !((((double)px * N[0] + (double)py * N[1]) + (double)pz * N[2]) < 0.5 * (double)dist));
             if (ok) {
                 int lvl = (int)ceilf(__fdiv_rn((float)log((double)__fdiv_rn(maxd, dist)), A.log_sf));
                 lvl = lvl < 0 ? 0 : (lvl >= A.cam.nlevels ? A.cam.nlevels - 1 : lvl);

@@ -106,7 +106,8 @@ SGS_API int sgs_fuse_search_batch_device(const sgs_fuse_batch* a, int nframes, v
     A.tcw = a->tcw; A.ow = a->ow; A.mp_xyz = a->mp_xyz; A.mp_normal = a->mp_normal; A.mp_min_dist = a->mp_min_dist; A.mp_max_dist = a->mp_max_dist;
     A.mp_desc = a->mp_desc; A.mp_valid = a->mp_valid; A.mp_n = a->mp_n; A.mp_cap = a->mp_cap; A.th = a->th; A.log_sf = logf(a->cam.scale_factors[1]);
     for (int l = 0; l < kMaxLevels; ++l) A.inv_sigma2[l] = a->inv_level_sigma2[l];
-    A.sim3_variant = a->sim3_variant ? 1 : 0;
+    A.sim3_variant = a->sim3_variant; A.xform2 = a->xform2;
+    if (a->sim3_variant < 0 || a->sim3_variant > 2 || (a->sim3_variant == 2 && !a->xform2)) { set_error("sgs_fuse_search_batch_device: bad variant"); return SGS_ERR_INVALID; }
     A.best_idx = a->best_idx; A.best_dist = a->best_dist;
     return launch_fuse_search(A, nframes, (cudaStream_t)stream);
 }

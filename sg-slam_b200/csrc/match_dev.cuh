@@ -63,7 +63,9 @@ struct FuseArgs {                 // search half of ORBmatcher::Fuse(KeyFrame*, 
     const float* mp_xyz; const float* mp_normal; const float* mp_min_dist; const float* mp_max_dist; const uint8_t* mp_desc; const uint8_t* mp_valid;
     const int32_t* mp_n; int32_t mp_cap;
     float th, log_sf; float inv_sigma2[kMaxLevels];
-    int32_t sim3_variant;         // Fuse(KeyFrame*, Scw, ...) (:982-1104): pose already decomposed by the caller, invz = 1.0 / z in double, no chi-square gates
+    const float* xform2;          // [nframes][12]: sR21 (3x3 row major) + t21, variant 2 only
+    int32_t sim3_variant;         // 2: one direction of SearchBySim3 (:1106-1330): second transform xform2, distance |p3Dc2|, no viewing-angle test;
+                                  // 1: Fuse(KeyFrame*, Scw, ...) (:982-1104): pose already decomposed by the caller, invz = 1.0 / z in double, no chi-square gates
     int32_t* best_idx; int32_t* best_dist;
 };
 

@@ -197,7 +197,7 @@ def test_keyframe_projection_matcher(seed, ncur, nkf, orb_dist, th):
         assert np.array_equal(mp_g[s['cur_mp'] >= 0], s['cur_mp'][s['cur_mp'] >= 0])        # keypoints that already held a map point are never touched
 
 
-@pytest.mark.parametrize('seed,ncur,nmp,th,sim3', [(1, 1000, 1000, 3.0, 0), (2, 1500, 3000, 3.0, 0), (3, 400, 2000, 5.0, 0), (4, 1000, 2000, 4.0, 1)])
+@pytest.mark.parametrize('seed,ncur,nmp,th,sim3', [(1, 1000, 1000, 3.0, 0), (2, 1500, 3000, 3.0, 0), (3, 400, 2000, 5.0, 0), (4, 1000, 2000, 4.0, 1), (5, 1000, 2000, 7.5, 2)])
 def test_fuse_search(seed, ncur, nmp, th, sim3):
     """Search half of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:829-980)."""
     import ctypes as C
@@ -210,8 +210,12 @@ def test_fuse_search(seed, ncur, nmp, th, sim3):
     to = s['last_xyz'].astype(np.float64) - Ow.astype(np.float64); d = np.linalg.norm(to, axis=1)
     nrm = to / np.maximum(d[:, None], 1e-9) + rs.normal(0, 0.6, (nmp, 3)); nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
     inv_s2 = (1.0 / (sf * sf)).astype(np.float32)
+    xf = None
+    if sim3 == 2:          # [sR21 | t21]: a small similarity on top of the key-frame pose
+        a_ = 0.004; sc = 1.01
+        xf = np.concatenate([(sc * np.array([[np.cos(a_), -np.sin(a_), 0], [np.sin(a_), np.cos(a_), 0], [0, 0, 1]])).reshape(9), [0.01, -0.005, 0.02]]).astype(np.float32)
     fo = O.FrameArrays(s['kps'], s['uright'], s['desc'], 640, 480, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], s['sf'])
-    bi_o, bd_o = O.fuse_search(fo, s['Tcw_cur'], Ow, s['kf_valid'], s['last_xyz'], nrm, s['min_dist'], s['max_dist'], s['last_desc'], th, inv_s2, sim3_variant=bool(sim3))
+    bi_o, bd_o = O.fuse_search(fo, s['Tcw_cur'], Ow, s['kf_valid'], s['last_xyz'], nrm, s['min_dist'], s['max_dist'], s['last_desc'], th, inv_s2, sim3_variant=sim3, xform2=xf)
     assert (bi_o >= 0).sum() > 30 and (bd_o[bi_o >= 0] <= 50).sum() > 10
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     kcap, mcap = ncur + 5, nmp + 3
@@ -228,6 +232,8 @@ def test_fuse_search(seed, ncur, nmp, th, sim3):
     for l in range(8):
         a.inv_level_sigma2[l] = float(inv_s2[l])
     a.sim3_variant = sim3
+    if xf is not None:
+        t_['xf'] = dev(xf.reshape(1, 12)); a.xform2 = t_['xf'].data_ptr()
     a.best_idx, a.best_dist = bi.data_ptr(), bd.data_ptr()
     B.check(B.lib().sgs_fuse_search_batch_device(C.byref(a), 1, C.c_void_p(0)))
     torch.cuda.synchronize()
