@@ -136,6 +136,10 @@ SGS_API int sgs_hamming_bf(const uint8_t* query, int nq, const uint8_t* train, i
 SGS_API int sgs_hamming_bf_scratch_elems(int nq, int nt, int64_t* elems);
 SGS_API int sgs_hamming_bf_device(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, int32_t* d_best_idx,
                                   int32_t* d_best_dist, int32_t* d_second_dist, int32_t* d_scratch, void* stream);
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307) for `npoints` map points: d_desc [P][max_obs][32] (the descriptors of the
+ * point's observations, max_obs <= 64), d_counts [P]; d_best_idx [P] = index of the descriptor with the smallest median distance to the others. */
+SGS_API int sgs_distinctive_descriptor_batch_device(const uint8_t* d_desc, const int32_t* d_counts, int max_obs, int npoints,
+                                                    int32_t* d_best_idx, void* stream);
 
 /* Flattened read-only view of a Frame as the matchers need it (src/Frame.cc:129-198): undistorted keypoints,
  * mvuRight, descriptors, image bounds (mnMinX..), intrinsics and the extractor's scale factors. */

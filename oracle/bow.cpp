@@ -264,3 +264,18 @@ SGO_API int sgo_search_for_triangulation(int n1, const int32_t* node1, const dou
     }
     return nmatches;
 }
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307): among the n observed descriptors of a map point, the one whose median
+// Hamming distance to all of them (itself included, distance 0) is smallest; vDists[0.5 * (n - 1)] after sorting; the first minimum wins.
+// Returns the index (0 for n == 0).
+SGO_API int sgo_distinctive_descriptor(const uint8_t* desc, int n) {
+    int best_median = 0x7fffffff, best_idx = 0;
+    std::vector<int> d(n);
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) d[j] = i == j ? 0 : hamming(desc + 32 * (size_t)i, desc + 32 * (size_t)j);
+        std::sort(d.begin(), d.end());
+        const int median = d[(int)(0.5 * (n - 1))];
+        if (median < best_median) { best_median = median; best_idx = i; }
+    }
+    return best_idx;
+}

@@ -427,3 +427,9 @@ def fuse_search(kf, Tcw, Ow, mp_valid, mp_xyz, mp_normal, min_dist, max_dist, mp
     lib().sgo_fuse_search(C.byref(kf.c), _p(T), _p(O_), n, *[_p(x) for x in a], C.c_float(th), _p(s2), C.c_float(log_scale_factor), int(sim3_variant),
                           _p(np.ascontiguousarray(xform2, f32)) if xform2 is not None else None, _p(bi), _p(bd))
     return bi, bd
+
+
+def distinctive_descriptor(desc):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307): index of the representative descriptor among desc [n,32]."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    return int(lib().sgo_distinctive_descriptor(_p(d), len(d)))

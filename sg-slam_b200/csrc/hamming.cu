@@ -165,3 +165,49 @@ SGS_API int sgs_hamming_bf(const uint8_t* query, int nq, const uint8_t* train, i
 }
 
 }  // extern "C"
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307) for a batch of map points: one warp per map point, lane i owns row i of
+// the distance matrix (rows i and i + 32 when a point has more than 32 observations, at most 64), finds vDists[0.5 (n - 1)] of its row by
+// counting ranks (distances are integers 0..256) and the warp keeps the first row with the smallest median.
+namespace sgs {
+__global__ void __launch_bounds__(256) distinctive_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ counts, int max_obs, int npoints,
+                                                          int32_t* __restrict__ best_idx) {
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= npoints) return;
+    const int n = min(counts[p], max_obs);
+    const uint4* D = reinterpret_cast<const uint4*>(desc + (int64_t)p * max_obs * 32);
+    const int k = (int)(0.5 * (double)(n - 1));
+    unsigned best = 0xffffffffu;
+    for (int i = lane; i < n; i += 32) {
+        const uint4 a0 = __ldg(D + 2 * i), a1 = __ldg(D + 2 * i + 1);
+        int dist[64];
+        for (int j = 0; j < n; ++j) {
+            const uint4 b0 = __ldg(D + 2 * j), b1 = __ldg(D + 2 * j + 1);
+            dist[j] = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) +
+                      __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+        }
+        // k-th smallest: the value v with  #(dist < v) <= k < #(dist <= v)
+        int median = 0;
+        for (int j = 0; j < n; ++j) {
+            int less = 0, leq = 0;
+            for (int q = 0; q < n; ++q) { less += dist[q] < dist[j]; leq += dist[q] <= dist[j]; }
+            if (less <= k && k < leq) { median = dist[j]; break; }
+        }
+        best = min(best, ((unsigned)median << 8) | (unsigned)i);
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (lane == 0) best_idx[p] = n > 0 ? (int)(best & 0xffu) : 0;
+}
+}  // namespace sgs
+
+extern "C" {
+
+SGS_API int sgs_distinctive_descriptor_batch_device(const uint8_t* d_desc, const int32_t* d_counts, int max_obs, int npoints, int32_t* d_best_idx, void* stream) {
+    if (!d_desc || !d_counts || !d_best_idx || npoints < 1 || max_obs < 1) { sgs::set_error("sgs_distinctive_descriptor_batch_device: bad argument"); return SGS_ERR_INVALID; }
+    if (max_obs > 64) { sgs::set_error("sgs_distinctive_descriptor_batch_device: at most 64 observations per map point"); return SGS_ERR_UNSUPPORTED; }
+    sgs::distinctive_kernel<<<(npoints + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_desc, d_counts, max_obs, npoints, d_best_idx);
+    SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+
+}  // extern "C"

@@ -238,3 +238,27 @@ def test_fuse_search(seed, ncur, nmp, th, sim3):
     B.check(B.lib().sgs_fuse_search_batch_device(C.byref(a), 1, C.c_void_p(0)))
     torch.cuda.synchronize()
     assert np.array_equal(bi.cpu().numpy()[0, :nmp], bi_o) and np.array_equal(bd.cpu().numpy()[0, :nmp], bd_o)
+
+
+def test_distinctive_descriptor_batch():
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307): median-of-distances representative, first minimum wins."""
+    import ctypes as C
+    import torch
+    rs = np.random.RandomState(8)
+    P, cap = 3000, 64
+    counts = rs.randint(0, 65, P).astype(np.int32); counts[:6] = [0, 1, 2, 3, 64, 33]
+    desc = np.zeros((P, cap, 32), np.uint8)
+    for p in range(P):
+        base = rs.randint(0, 2, 256).astype(np.uint8)
+        for i in range(counts[p]):
+            b = base.copy(); b[rs.choice(256, rs.randint(0, 60), replace=False)] ^= 1
+            desc[p, i] = np.packbits(b)
+        if counts[p] >= 4 and p % 5 == 0:
+            desc[p, 2] = desc[p, 1]                                   # exact duplicates: ties between rows
+    dd = torch.from_numpy(desc).cuda(); dc = torch.from_numpy(counts).cuda(); out = torch.full((P,), -3, dtype=torch.int32, device='cuda')
+    v = C.c_void_p
+    B.check(B.lib().sgs_distinctive_descriptor_batch_device(v(dd.data_ptr()), v(dc.data_ptr()), cap, P, v(out.data_ptr()), v(0)))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    for p in range(P):
+        assert got[p] == O.distinctive_descriptor(desc[p, :counts[p]]), (p, counts[p])
