@@ -263,6 +263,24 @@ typedef struct sgs_localmap_batch {       /* SearchByProjection(Frame&, vector<M
 SGS_API int sgs_match_project_localmap_batch_device(sgs_matcher* m, const sgs_localmap_batch* args, int nframes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Optimizer::PoseOptimization(Frame*) (src/Optimizer.cc:239-451): motion-only bundle adjustment after every matcher call, for `nframes`
+ * frames (device pointers).  Map point of keypoint i: points_xyz[mp_index[i]] when mp_index is given (-1 = none; this is the cur_mp array the
+ * projection matchers write), else points_xyz[i] with has_mp[i].  uright < 0 = monocular observation.  Outputs: the optimised pose, the
+ * outlier flags (mvbOutlier) and nInitialCorrespondences - nBad.  Checked against a CPU restatement of the g2o algorithm (g2o itself cannot
+ * be run without Eigen: parity unpinned).  scratch_err: 3 doubles per keypoint, scratch_level: 1 byte per keypoint.
+ * ------------------------------------------------------------------------------------ */
+typedef struct sgs_poseopt_batch {
+    sgs_camera cam;                       /* fx, fy, cx, cy, bf are used */
+    const float* tcw_in;                  /* [F][16] pFrame->mTcw */
+    const sgs_keypoint* kps; const float* uright; const int32_t* n; int32_t cap;       /* mvKeysUn, mvuRight */
+    const uint8_t* has_mp; const int32_t* mp_index; const float* points_xyz; int32_t point_cap;
+    float inv_level_sigma2[16];
+    float* tcw_out; uint8_t* outlier; int32_t* ninliers;
+    double* scratch_err; uint8_t* scratch_level;
+} sgs_poseopt_batch;
+SGS_API int sgs_pose_optimization_batch_device(const sgs_poseopt_batch* args, int nframes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Bag of words (tracking fallback, Tracking::TrackReferenceKeyFrame src/Tracking.cc:858-904):
  *   sgs_vocabulary_create       : the DBoW2 tree as flat arrays -- parent[i] of node i in node-id order (node 0 = root; DBoW2 appends children
  *                                 to their parent in that order, TemplatedVocabulary.h:1351-1420 / 1467-1508), node descriptors [nnodes][32],

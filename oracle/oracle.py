@@ -433,3 +433,17 @@ def distinctive_descriptor(desc):
     """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307): index of the representative descriptor among desc [n,32]."""
     d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
     return int(lib().sgo_distinctive_descriptor(_p(d), len(d)))
+
+
+def pose_optimization(Tcw, has_mp, xyz, kp_xy, octave, uright, inv_level_sigma2, fx, fy, cx, cy, bf):
+    """Optimizer::PoseOptimization (src/Optimizer.cc:239-451): returns (n_inliers, Tcw_out 4x4 float32, outlier uint8 [n])."""
+    f32 = np.float32
+    T = np.ascontiguousarray(Tcw, f32).reshape(16)
+    a = [np.ascontiguousarray(has_mp, np.uint8), np.ascontiguousarray(xyz, f32), np.ascontiguousarray(kp_xy, f32), np.ascontiguousarray(octave, np.int32),
+         np.ascontiguousarray(uright, f32), np.ascontiguousarray(inv_level_sigma2, f32)]
+    n = len(a[0])
+    out = np.zeros(16, f32); outl = np.zeros(n, np.uint8)
+    fn = lib().sgo_pose_optimization
+    fn.restype = C.c_int
+    r = fn(_p(T), n, *[_p(x) for x in a], C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_float(bf), _p(out), _p(outl))
+    return r, out.reshape(4, 4), outl

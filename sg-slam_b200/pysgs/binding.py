@@ -52,6 +52,12 @@ class LastFrameBatch(C.Structure):
                 ('cur_mp', C.c_void_p), ('cur_mp_obs_in', C.c_void_p), ('nmatches', C.c_void_p), ('ncand', C.c_void_p)]
 
 
+class PoseOptBatch(C.Structure):
+    _fields_ = [('cam', Camera), ('tcw_in', C.c_void_p), ('kps', C.c_void_p), ('uright', C.c_void_p), ('n', C.c_void_p), ('cap', C.c_int32),
+                ('has_mp', C.c_void_p), ('mp_index', C.c_void_p), ('points_xyz', C.c_void_p), ('point_cap', C.c_int32), ('inv_level_sigma2', C.c_float * 16),
+                ('tcw_out', C.c_void_p), ('outlier', C.c_void_p), ('ninliers', C.c_void_p), ('scratch_err', C.c_void_p), ('scratch_level', C.c_void_p)]
+
+
 class FuseBatch(C.Structure):
     _fields_ = [('cam', Camera), ('kf_kps', C.c_void_p), ('kf_desc', C.c_void_p), ('kf_uright', C.c_void_p), ('kf_n', C.c_void_p), ('kf_cap', C.c_int32),
                 ('tcw', C.c_void_p), ('ow', C.c_void_p), ('mp_xyz', C.c_void_p), ('mp_normal', C.c_void_p), ('mp_min_dist', C.c_void_p), ('mp_max_dist', C.c_void_p),
@@ -98,7 +104,7 @@ ABI_SYMBOLS = [
     'sgs_lk_create', 'sgs_lk_destroy', 'sgs_lk_track', 'sgs_lk_track_batch_device', 'sgs_lk_read_level',
     'sgs_tracker_lk_device', 'sgs_tracker_prev_xy_device', 'sgs_tracker_track_lk', 'sgs_extractor_level0_device', 'sgs_memcpy_d2h',
     'sgs_lk_set_profiling', 'sgs_lk_stage_times', 'sgs_tracker_lk',
-    'sgs_distinctive_descriptor_batch_device', 'sgs_fuse_search_batch_device', 'sgs_match_project_keyframe_batch_device', 'sgs_match_project_keyframe',
+    'sgs_pose_optimization_batch_device', 'sgs_distinctive_descriptor_batch_device', 'sgs_fuse_search_batch_device', 'sgs_match_project_keyframe_batch_device', 'sgs_match_project_keyframe',
     'sgs_vocabulary_create', 'sgs_vocabulary_destroy', 'sgs_bow_transform_batch_device', 'sgs_match_bow_batch_device', 'sgs_bow_transform', 'sgs_match_bow',
     'sgs_stereo_from_depth_batch_device', 'sgs_frustum_batch_device', 'sgs_frustum', 'sgs_undistort_batch_device', 'sgs_undistort_points', 'sgs_image_bounds', 'sgs_tracker_stereo_device',
     'sgs_fundamental_ransac', 'sgs_fundamental_batch_device', 'sgs_tracker_fundamental_device', 'sgs_tracker_fundamental_device_ptr',
