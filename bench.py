@@ -475,6 +475,29 @@ def main():
     localmap_ms = el0.elapsed_time(el1) / 5
     lm_stats = (float(lm_out['inview'].float().sum(1).mean().item()), float(lm_nm.float().mean().item()))
 
+    # ---- Optimizer::PoseOptimization of the same batch on the matches of the step (not part of the metric) -------------------------------------
+    po = B.PoseOptBatch(); po.cam = cam
+    po_T = torch.zeros((NB, 16), device='cuda'); po_out = torch.zeros((NB, cap), dtype=torch.uint8, device='cuda'); po_nin = torch.zeros(NB, dtype=torch.int32, device='cuda')
+    po_err = torch.zeros((NB, cap, 3), dtype=torch.float64, device='cuda'); po_lvl = torch.zeros((NB, cap), dtype=torch.uint8, device='cuda')
+    po.tcw_in, po.kps, po.uright, po.n, po.cap = dv['T'].data_ptr(), rk.value, ru.value, rc.value, cap
+    po.has_mp, po.mp_index, po.points_xyz, po.point_cap = 0, rmp.value, dv['lxyz'].data_ptr(), pcap
+    for l in range(8):
+        po.inv_level_sigma2[l] = float(1.0 / (sf[l] * sf[l]))
+    po.tcw_out, po.outlier, po.ninliers, po.scratch_err, po.scratch_level = po_T.data_ptr(), po_out.data_ptr(), po_nin.data_ptr(), po_err.data_ptr(), po_lvl.data_ptr()
+
+    def dev_poseopt():
+        B.check(L.sgs_pose_optimization_batch_device(C.byref(po), NB, v(st.cuda_stream)))
+    with torch.cuda.stream(st):
+        dev_poseopt()
+        ep0, ep1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        ep0.record(st)
+        for _ in range(5):
+            dev_poseopt()
+        ep1.record(st)
+    torch.cuda.synchronize()
+    poseopt_ms = ep0.elapsed_time(ep1) / 5
+    poseopt_inl = float(po_nin.float().mean().item()); poseopt_edges = float((lm_fmp0 >= 0).sum(1).float().mean().item())
+
     step_host()   # e2e warm-up; its outputs are also used for the parity spot-check below
     counts_after = h_out['cnt'].numpy().copy(); nmatch = h_out['nm'].numpy().copy()
     F_dev = B.memcpy_d2h(np.zeros((NB, 9), np.float64), pF.value); F_info = B.memcpy_d2h(np.zeros((NB, 4), np.int32), pI.value)
@@ -621,6 +644,7 @@ def main():
                            'mean_keypoints': float(n0.mean()), 'mean_after_dynreject': float(counts_after.mean()), 'mean_matches': float(nmatch.mean()),
                            'ransac_iterations_mean': float(F_info[:, 2].mean()), 'ransac_inlier_ratio_mean': float((F_info[:, 1] / np.maximum(1, F_info[:, 0])).mean()),
                            'search_local_points_ms_per_step': localmap_ms, 'search_local_points_note': 'Frame::isInFrustum + SearchByProjection(F, local map of %d points/frame, th=3): %.0f points in view, %.0f new matches per frame; timed separately, not part of value' % (int(lm_n.mean()), lm_stats[0], lm_stats[1]),
+                           'pose_optimization_ms_per_step': poseopt_ms, 'pose_optimization_note': 'Optimizer::PoseOptimization on the matches of the step (%.0f of %.0f edges kept per frame); timed separately, not part of value' % (poseopt_inl, poseopt_edges),
                            'bow_transform_ms_per_step': bow_ms, 'bow_note': 'Frame::ComputeBoW (DBoW2 transform, k=10 L=6 vocabulary of %d nodes) of the same %d frames, timed separately, not part of value' % (voc_nodes, NB),
                            'not_in_step': 'the detector (boxes precomputed)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps, 'roofline': roofline, 'cpu_baseline': cpu}

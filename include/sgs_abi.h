@@ -279,6 +279,10 @@ typedef struct sgs_poseopt_batch {
     double* scratch_err; uint8_t* scratch_level;
 } sgs_poseopt_batch;
 SGS_API int sgs_pose_optimization_batch_device(const sgs_poseopt_batch* args, int nframes, void* stream);
+/* host-pointer variant, one frame (outlier flags of keypoints without a map point are left untouched = 0) */
+SGS_API int sgs_pose_optimization(const sgs_camera* cam, const float* tcw_in, int n, const sgs_keypoint* kps_un, const float* uright,
+                                  const uint8_t* has_mp, const float* xyz, const float* inv_level_sigma2, float* tcw_out, uint8_t* outlier,
+                                  int* ninliers, int device);
 
 /* ------------------------------------------------------------------------------------
  * Bag of words (tracking fallback, Tracking::TrackReferenceKeyFrame src/Tracking.cc:858-904):

@@ -335,4 +335,48 @@ SGS_API int sgs_pose_optimization_batch_device(const sgs_poseopt_batch* a, int n
     return SGS_OK;
 }
 
+// host-pointer variant, one frame: has_mp [n], xyz [n][3] (GetWorldPos of mvpMapPoints[i]), kps = mvKeysUn, uright = mvuRight
+SGS_API int sgs_pose_optimization(const sgs_camera* cam, const float* tcw_in, int n, const sgs_keypoint* kps_un, const float* uright, const uint8_t* has_mp,
+                                  const float* xyz, const float* inv_level_sigma2, float* tcw_out, uint8_t* outlier, int* ninliers, int device) {
+    if (!cam || !tcw_in || !tcw_out || !ninliers || !inv_level_sigma2 || n < 0 || (n > 0 && (!kps_un || !uright || !has_mp || !xyz || !outlier))) {
+        set_error("sgs_pose_optimization: bad argument"); return SGS_ERR_INVALID;
+    }
+    for (int i = 0; i < 16; ++i) tcw_out[i] = tcw_in[i];
+    *ninliers = 0;
+    if (n == 0) return SGS_OK;
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    const size_t N = (size_t)n;
+    uint8_t* d = nullptr;
+    const size_t bytes = 24 * N + sizeof(sgs_keypoint) * N + 4 * N + 12 * N + 64 + 64 + 16 + N + N + N + 256;
+    SGS_CUDA_TRY(cudaMalloc(&d, bytes));
+    double* d_err = reinterpret_cast<double*>(d);
+    sgs_keypoint* d_k = reinterpret_cast<sgs_keypoint*>(d_err + 3 * N);
+    float* d_ur = reinterpret_cast<float*>(d_k + N); float* d_xyz = d_ur + N; float* d_Tin = d_xyz + 3 * N; float* d_Tout = d_Tin + 16;
+    int32_t* d_n = reinterpret_cast<int32_t*>(d_Tout + 16); int32_t* d_nin = d_n + 1;
+    uint8_t* d_has = reinterpret_cast<uint8_t*>(d_n + 4); uint8_t* d_out = d_has + N; uint8_t* d_lvl = d_out + N;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void* dst, const void* src, size_t b) { if (e == cudaSuccess) e = cudaMemcpy(dst, src, b, cudaMemcpyHostToDevice); };
+    up(d_k, kps_un, sizeof(sgs_keypoint) * N); up(d_ur, uright, 4 * N); up(d_xyz, xyz, 12 * N); up(d_Tin, tcw_in, 64); up(d_n, &n, 4); up(d_has, has_mp, N);
+    if (e == cudaSuccess) e = cudaMemset(d_out, 0, N);
+    int rc = SGS_OK;
+    if (e == cudaSuccess) {
+        sgs_poseopt_batch b;
+        b.cam = *cam; b.tcw_in = d_Tin; b.kps = d_k; b.uright = d_ur; b.n = d_n; b.cap = n; b.has_mp = d_has; b.mp_index = nullptr; b.points_xyz = d_xyz; b.point_cap = n;
+        for (int l = 0; l < 16; ++l) b.inv_level_sigma2[l] = inv_level_sigma2[l];
+        b.tcw_out = d_Tout; b.outlier = d_out; b.ninliers = d_nin; b.scratch_err = d_err; b.scratch_level = d_lvl;
+        rc = sgs_pose_optimization_batch_device(&b, 1, nullptr);
+        if (rc == SGS_OK) {
+            e = cudaMemcpy(tcw_out, d_Tout, 64, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(outlier, d_out, N, cudaMemcpyDeviceToHost);
+            int32_t nin = 0;
+            if (e == cudaSuccess) e = cudaMemcpy(&nin, d_nin, 4, cudaMemcpyDeviceToHost);
+            *ninliers = nin;
+        }
+    }
+    cudaFree(d);
+    if (rc != SGS_OK) return rc;
+    if (e != cudaSuccess) { set_error("sgs_pose_optimization: %s", cudaGetErrorString(e)); return SGS_ERR_CUDA; }
+    return SGS_OK;
+}
+
 }  // extern "C"

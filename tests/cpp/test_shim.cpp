@@ -9,6 +9,7 @@
 
 #include "sgslam/FrameDynamic.h"
 #include "sgslam/FrameGeometry.h"
+#include "sgslam/Optimizer.h"
 #include "sgslam/ORBextractor.h"
 #include "sgslam/ORBmatcher.h"
 
@@ -34,8 +35,9 @@ struct Frame {
     cv::Mat mDescriptors, mTcw;
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<bool> mvbOutlier;
-    std::vector<float> mvScaleFactors;
+    std::vector<float> mvScaleFactors, mvInvLevelSigma2;
     float mbf = 40.f;
+    void SetPose(const cv::Mat& T) { mTcw = T.clone(); }
     static float fx, fy, cx, cy, mnMinX, mnMinY, mnMaxX, mnMaxY;
 };
 float Frame::fx = 535.4f, Frame::fy = 539.2f, Frame::cx = 320.1f, Frame::cy = 247.6f, Frame::mnMinX = 0, Frame::mnMinY = 0, Frame::mnMaxX = 640, Frame::mnMaxY = 480;
@@ -151,6 +153,23 @@ int main(int argc, char** argv) {
         if (store[i].mnTrackScaleLevel != elv[i]) ++lvldiff;
     }
     if (nview != expview || lvldiff > 2) return fail("isInFrustum: count / level");
-    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view\n", nkp, nm, kept, nd, nlk, nview, nfr);
+    // 6. PoseOptimization (expected: the CPU restatement)
+    int32_t npo = 0; f.read(reinterpret_cast<char*>(&npo), 4);
+    std::vector<float> pT0 = rd<float>(f, 16), pxyz = rd<float>(f, (size_t)npo * 3);
+    std::vector<cv::KeyPoint> pk = rd<cv::KeyPoint>(f, npo);
+    std::vector<float> pur = rd<float>(f, npo), pis2 = rd<float>(f, 8);
+    std::vector<uint8_t> phas = rd<uint8_t>(f, npo), pexp_out = rd<uint8_t>(f, npo);
+    std::vector<float> pexpT = rd<float>(f, 16);
+    int32_t pexp_n = 0; f.read(reinterpret_cast<char*>(&pexp_n), 4);
+    Frame pf; pf.N = npo; pf.mvKeysUn = pk; pf.mvuRight = pur; pf.mvScaleFactors = cur.mvScaleFactors; pf.mvInvLevelSigma2 = pis2;
+    pf.mTcw = cv::Mat(4, 4, CV_32F, pT0.data(), 16).clone(); pf.mvbOutlier.assign(npo, false); pf.mvpMapPoints.assign(npo, nullptr);
+    std::vector<MapPoint> pstore(npo);
+    for (int i = 0; i < npo; ++i) if (phas[i]) { pstore[i].pos = cv::Mat(3, 1, CV_32F, &pxyz[3 * (size_t)i], 4).clone(); pf.mvpMapPoints[i] = &pstore[i]; }
+    const int pin = PoseOptimizationGPU(&pf);
+    if (pin != pexp_n) return fail("PoseOptimization: inlier count");
+    for (int i = 0; i < npo; ++i) if (phas[i] && pf.mvbOutlier[i] != (pexp_out[i] != 0)) return fail("PoseOptimization: outlier flags");
+    for (int i = 0; i < 16; ++i) if (std::fabs(pf.mTcw.at<float>(i / 4, i % 4) - pexpT[i]) > 1e-6f) return fail("PoseOptimization: pose");
+    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges\n", nkp, nm, kept, nd, nlk, nview, nfr,
+                pin, npo);
     return 0;
 }

@@ -72,6 +72,14 @@ def test_shim_on_gpu(tmp_path):
         ref = O.is_in_frustum(T, cam9, 8, float(np.float32(np.log(np.float32(1.2)))), xyz, nrm, mn, mx, 0.5)
         np.array([nfr], np.int32).tofile(f); T.tofile(f); xyz.tofile(f); nrm.tofile(f); mn.tofile(f); mx.tofile(f)
         ref['inview'].tofile(f); ref['proj_x'].tofile(f); ref['proj_y'].tofile(f); ref['proj_xr'].tofile(f); ref['view_cos'].tofile(f); ref['level'].tofile(f)
+        # 6. PoseOptimization
+        ps = S.pose_scenario(12, n=700)
+        pc = ps['cam']
+        pn, pT, po = O.pose_optimization(ps['T0'], ps['has'], ps['xyz'], ps['xy'], ps['octave'], ps['uright'], ps['inv_s2'], pc['fx'], pc['fy'], pc['cx'], pc['cy'], pc['bf'])
+        pk = np.zeros(700, O.KP_DTYPE); pk['x'] = ps['xy'][:, 0]; pk['y'] = ps['xy'][:, 1]; pk['octave'] = ps['octave']
+        np.array([700], np.int32).tofile(f); ps['T0'].astype(np.float32).tofile(f); ps['xyz'].astype(np.float32).tofile(f); pk.tofile(f)
+        ps['uright'].astype(np.float32).tofile(f); ps['inv_s2'][:8].astype(np.float32).tofile(f); ps['has'].astype(np.uint8).tofile(f); po.astype(np.uint8).tofile(f)
+        pT.astype(np.float32).tofile(f); np.array([pn], np.int32).tofile(f)
     out = subprocess.run([exe, str(path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'OK shim' in out.stdout
