@@ -521,6 +521,52 @@ SGS_API int sgs_memcpy_d2h(void* dst, const void* d_src, size_t bytes);
 SGS_API int sgs_extractor_set_profiling(sgs_extractor* ex, int enable);
 SGS_API int sgs_extractor_stage_times(sgs_extractor* ex, double* ms_total5, int* ncalls);
 
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Object detector: Detector2D (src/Detector2D.cc:16-89, include/Detector2D.h:29-80) -- ncnn forward of the MobileNetV3-SSDLite graph
+ * Thirdparty/ncnn_model/mobilenetv3_ssdlite_voc.{param,bin} and the reference's post-processing of the "detection_out" rows.
+ * The handle reads the ncnn text graph + weight blob itself (same two files the reference loads at Detector2D.cc:25-26) and runs the
+ * layers as FP32 CUDA kernels on a batch of frames.  ncnn is an unpinned, un-vendored dependency of the reference: the layer semantics
+ * are restated from its published definitions (parity unpinned).
+ * ------------------------------------------------------------------------------------------------------------------------------ */
+typedef struct sgs_detector sgs_detector;
+typedef struct sgs_object2d {   /* Object2D, include/Detector2D.h:29-37 (name = class_names[id]) */
+    int32_t id;
+    float prob;
+    sgs_rect rect;
+} sgs_object2d;
+
+/* Detector2D::Detector2D(detection_confidence_threshold, dynamic_detection_confidence_threshold) + load_param/load_model.
+ * max_frames = largest batch one sgs_detector_detect_device call may carry.  flags: bit 0 = diagnostic mode (every layer its own kernel,
+ * every intermediate blob kept, readable with sgs_detector_blob); bit 1 = plan only (parse, shapes, kernel list and activation pool are
+ * built, no device is touched; the handle serves sgs_detector_info / sgs_detector_describe only). */
+SGS_API int sgs_detector_create(const char* param_path, const char* bin_path, int max_frames, float detection_confidence_threshold,
+                                float dynamic_detection_confidence_threshold, int flags, int device, sgs_detector** out);
+SGS_API void sgs_detector_destroy(sgs_detector* d);
+/* Sizes fixed by the graph: rows_cap = DetectionOutput keep_top_k (rows per frame), input_size = 300 (Detector2D.h:70). */
+SGS_API int sgs_detector_info(const sgs_detector* d, int* rows_cap, int* input_size, int* num_layers, int* num_kernels_per_batch);
+
+/* Detector2D::detect (src/Detector2D.cc:34-89) on nframes interleaved 8-bit 3-channel frames resident in device memory (frame f starts at
+ * d_rgb + f*frame_stride, rows pitch bytes apart; channel order is taken as given, Detector2D.cc:39 passes PIXEL_RGB = no swap).
+ * Outputs (device pointers, any may be NULL):
+ *   d_rows     [F][rows_cap][6]  detection_out rows [label, score, xmin, ymin, xmax, ymax] (normalised);  d_nrows [F]
+ *   d_objects  [F][rows_cap]     every accepted row in detection order (what draw_objects sees, :66);       d_nobjects [F]
+ *   d_dyn_map  [F][max_boxes]    mvPotentialDynamicBorderForMapping (:70);                                  d_ndyn_map [F]
+ *   d_dyn_rm   [F][max_boxes]    mvPotentialDynamicBorderForRmDynamicFeature (:74), d_ndyn_rm [F], d_have_dyn_rm [F] (uint8, :73) --
+ *                                the layout sgs_dynreject_batch_device / sgs_tracker_* take as d_boxes / d_nboxes / d_have_dyn.
+ * Person boxes beyond max_boxes are not written: d_ndyn_* are clamped to max_boxes and d_status[f] (may be NULL) is set to 1. */
+SGS_API int sgs_detector_detect_device(sgs_detector* d, const uint8_t* d_rgb, int64_t frame_stride, int pitch, int width, int height,
+                                       int nframes, float* d_rows, int32_t* d_nrows, sgs_object2d* d_objects, int32_t* d_nobjects,
+                                       sgs_rect* d_dyn_map, int32_t* d_ndyn_map, sgs_rect* d_dyn_rm, int32_t* d_ndyn_rm,
+                                       uint8_t* d_have_dyn_rm, int max_boxes, int32_t* d_status, void* stream);
+/* One frame from host memory: objects[0..*n) = accepted rows in detection order (persons included, id 15).  SGS_ERR_CAPACITY with
+ * *n = required when cap is too small. */
+SGS_API int sgs_detect(sgs_detector* d, const uint8_t* rgb, int width, int height, int pitch, sgs_object2d* objects, int cap, int* n);
+/* Text listing of the kernel list: one line per kernel with its fused element-wise tail and activation-pool buffers.  SGS_ERR_CAPACITY
+ * with *n = bytes required (terminator included) when cap is too small. */
+SGS_API int sgs_detector_describe(const sgs_detector* d, char* out, int64_t cap, int64_t* n);
+/* Diagnostics: copies blob `name` of frame `frame` of the last batch to host floats (ncnn memory order c,h,w).  Needs flags bit 0. */
+SGS_API int sgs_detector_blob(sgs_detector* d, const char* name, int frame, float* out, int64_t cap, int64_t* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,7 @@ ABI_SYMBOLS = [
     'sgs_vocabulary_create', 'sgs_vocabulary_destroy', 'sgs_bow_transform_batch_device', 'sgs_match_bow_batch_device', 'sgs_bow_transform', 'sgs_match_bow',
     'sgs_stereo_from_depth_batch_device', 'sgs_frustum_batch_device', 'sgs_frustum', 'sgs_undistort_batch_device', 'sgs_undistort_points', 'sgs_image_bounds', 'sgs_tracker_stereo_device',
     'sgs_fundamental_ransac', 'sgs_fundamental_batch_device', 'sgs_tracker_fundamental_device', 'sgs_tracker_fundamental_device_ptr',
+    'sgs_detector_create', 'sgs_detector_destroy', 'sgs_detector_info', 'sgs_detector_detect_device', 'sgs_detect', 'sgs_detector_describe', 'sgs_detector_blob',
 ]
 
 
@@ -455,3 +456,63 @@ def fundamental_batch_device(d_kps, d_prev_xy, d_counts, cap, nframes, d_boxes, 
 def memcpy_d2h(dst_array, d_ptr):
     check(lib().sgs_memcpy_d2h(_p(dst_array), C.c_void_p(d_ptr), C.c_size_t(dst_array.nbytes)))
     return dst_array
+
+
+OBJ_DTYPE = np.dtype([('id', '<i4'), ('prob', '<f4'), ('x', '<f4'), ('y', '<f4'), ('w', '<f4'), ('h', '<f4')])   # sgs_object2d
+DET_DIAGNOSTIC, DET_PLAN_ONLY = 1, 2
+
+
+class Detector:
+    """Detector2D (src/Detector2D.cc) on the GPU: sgs_detector_* of include/sgs_abi.h."""
+
+    def __init__(self, param_path, bin_path, max_frames=1, det_thr=0.9, dyn_thr=0.01, flags=0, device=0):
+        self.h = C.c_void_p()
+        self.flags = flags
+        check(lib().sgs_detector_create(os.fsencode(param_path), os.fsencode(bin_path), max_frames, C.c_float(det_thr), C.c_float(dyn_thr), flags, device,
+                                        C.byref(self.h)))
+        r, t, nl, nk = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib().sgs_detector_info(self.h, C.byref(r), C.byref(t), C.byref(nl), C.byref(nk)))
+        self.rows_cap, self.input_size, self.num_layers, self.num_kernels = r.value, t.value, nl.value, nk.value
+
+    def close(self):
+        if self.h:
+            lib().sgs_detector_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def describe(self):
+        n = C.c_int64()
+        rc = lib().sgs_detector_describe(self.h, None, 0, C.byref(n))
+        if rc not in (SGS_OK, SGS_ERR_CAPACITY):
+            check(rc)
+        buf = C.create_string_buffer(n.value)
+        check(lib().sgs_detector_describe(self.h, buf, n.value, C.byref(n)))
+        return buf.value.decode()
+
+    def detect(self, rgb):
+        """One host frame (H x W x 3 uint8): accepted objects in detection order (OBJ_DTYPE)."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        out = np.zeros(self.rows_cap, OBJ_DTYPE); n = C.c_int()
+        check(lib().sgs_detect(self.h, _p(rgb), rgb.shape[1], rgb.shape[0], rgb.strides[0], _p(out), len(out), C.byref(n)))
+        return out[:n.value]
+
+    def detect_device(self, d_rgb, frame_stride, pitch, width, height, nframes, d_rows=0, d_nrows=0, d_objects=0, d_nobjects=0, d_dyn_map=0,
+                      d_ndyn_map=0, d_dyn_rm=0, d_ndyn_rm=0, d_have_dyn_rm=0, max_boxes=0, d_status=0, stream=0):
+        v = C.c_void_p
+        check(lib().sgs_detector_detect_device(self.h, v(d_rgb), C.c_int64(frame_stride), pitch, width, height, nframes, v(d_rows), v(d_nrows), v(d_objects),
+                                               v(d_nobjects), v(d_dyn_map), v(d_ndyn_map), v(d_dyn_rm), v(d_ndyn_rm), v(d_have_dyn_rm), max_boxes, v(d_status),
+                                               v(stream)))
+
+    def blob(self, name, frame=0):
+        n = C.c_int64()
+        rc = lib().sgs_detector_blob(self.h, name.encode(), frame, None, 0, C.byref(n))
+        if rc not in (SGS_OK, SGS_ERR_CAPACITY):
+            check(rc)
+        out = np.zeros(n.value, np.float32)
+        check(lib().sgs_detector_blob(self.h, name.encode(), frame, _p(out), out.size, C.byref(n)))
+        return out
