@@ -498,6 +498,48 @@ def main():
     poseopt_ms = ep0.elapsed_time(ep1) / 5
     poseopt_inl = float(po_nin.float().mean().item()); poseopt_edges = float((lm_fmp0 >= 0).sum(1).float().mean().item())
 
+    # ---- Detector2D::detect of the same batch (not part of the metric: the step takes the boxes as inputs, as the reference's tracking thread does) --
+    # frames = the grey frames replicated to 3 channels; model = the reference's MobileNetV3-SSDLite graph when build() staged it, else the tests' synthetic graph
+    det_info = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        import detector_model as DM
+        real = os.path.join(ROOT, 'oracle', '_ref', 'ncnn_model', 'mobilenetv3_ssdlite_voc')
+        if os.path.exists(real + '.param'):
+            dpp, dbp, dname, gflop = real + '.param', real + '.bin', 'mobilenetv3_ssdlite_voc (9.7 MB FP32 weights)', 1.115
+        else:
+            import tempfile
+            dpp, dbp = DM.write_mini_model(tempfile.mkdtemp(), 0); dname, gflop = 'synthetic graph of tests/detector_model.py (reference model not staged)', None
+        DB = 128                                     # frames per detector call
+        det = B.Detector(dpp, dbp, max_frames=DB, det_thr=0.9, dyn_thr=0.01, device=local)
+        d_rgb = d_frames[:DB].reshape(DB, H, W, 1).expand(DB, H, W, 3).contiguous()
+        det_boxes = torch.zeros((DB, 4, 4), device='cuda'); det_nb = torch.zeros(DB, dtype=torch.int32, device='cuda'); det_have = torch.zeros(DB, dtype=torch.uint8, device='cuda')
+
+        def dev_detect():
+            det.detect_device(d_rgb.data_ptr(), H * W * 3, W * 3, W, H, DB, d_dyn_rm=det_boxes.data_ptr(), d_ndyn_rm=det_nb.data_ptr(), d_have_dyn_rm=det_have.data_ptr(),
+                              max_boxes=4, stream=st.cuda_stream)
+        with torch.cuda.stream(st):
+            for _ in range(2):
+                dev_detect()
+            ed0, ed1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            ed0.record(st)
+            for _ in range(5):
+                dev_detect()
+            ed1.record(st)
+        torch.cuda.synchronize()
+        det_ms = ed0.elapsed_time(ed1) / 5
+        pk, _ = measured_peaks()
+        det_info = {'model': dname, 'frames_per_call': DB, 'ms_per_call': det_ms, 'frames_per_s': DB / det_ms * 1e3, 'kernels_per_call': det.num_kernels,
+                    'note': 'Detector2D::detect (resize + 408-layer ncnn graph + DetectionOutput + box post-processing) on device-resident RGB frames, timed separately, not part of value'}
+        if gflop:
+            tf = DB * gflop / det_ms
+            det_info['roofline'] = {'bound': 'tensor', 'achieved': tf, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': tf / pk['bf16_tflops'],
+                                    'note': '1.115 GFLOP per 300x300 inference (SURVEY 8d); 1x1 convolutions = 3xTF32 mma.sync (FP32-grade accuracy), the rest FP32 CUDA cores; peak = measured dense bf16'}
+        det.close()
+        del d_rgb
+    except Exception as ex:      # the detector is reported, never allowed to take the headline measurement down
+        log('[bench] detector stage skipped: %r' % (ex,))
+
     step_host()   # e2e warm-up; its outputs are also used for the parity spot-check below
     counts_after = h_out['cnt'].numpy().copy(); nmatch = h_out['nm'].numpy().copy()
     F_dev = B.memcpy_d2h(np.zeros((NB, 9), np.float64), pF.value); F_info = B.memcpy_d2h(np.zeros((NB, 4), np.int32), pI.value)
@@ -647,7 +689,8 @@ def main():
                            'search_local_points_ms_per_step': localmap_ms, 'search_local_points_note': 'Frame::isInFrustum + SearchByProjection(F, local map of %d points/frame, th=3): %.0f points in view, %.0f new matches per frame; timed separately, not part of value' % (int(lm_n.mean()), lm_stats[0], lm_stats[1]),
                            'pose_optimization_ms_per_step': poseopt_ms, 'pose_optimization_note': 'Optimizer::PoseOptimization on the matches of the step (%.0f of %.0f edges kept per frame); timed separately, not part of value' % (poseopt_inl, poseopt_edges),
                            'bow_transform_ms_per_step': bow_ms, 'bow_note': 'Frame::ComputeBoW (DBoW2 transform, k=10 L=6 vocabulary of %d nodes) of the same %d frames, timed separately, not part of value' % (voc_nodes, NB),
-                           'not_in_step': 'the detector (boxes precomputed)'},
+                           'detector': det_info,
+                           'not_in_step': 'the detector (boxes are inputs of the step; Detector2D::detect is timed separately under config.detector)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps, 'roofline': roofline, 'cpu_baseline': cpu}
         if bcast_ms is not None:
             line['config']['startup_broadcast_ms'] = bcast_ms

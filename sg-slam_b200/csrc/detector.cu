@@ -13,7 +13,8 @@
 // Element-wise layers (BinaryOp with a constant / a tensor / the chain's own start value, Clip, ReLU) that follow a producer are applied in
 // the producer's epilogue in graph order, one rounding per op, so fused and unfused execution give identical bits.
 // Layout: every blob is [frames][c][h][w] FP32 (ncnn's c,h,w order per frame); activations live in a pool planned by liveness.
-// Arithmetic is FP32 FMA on CUDA cores in this round; the tcgen05 path for the 1x1 convolutions is future work.
+// The 1x1 convolutions run on the tensor cores as error-compensated TF32 (three mma.sync per product, FP32-grade accuracy; flags bit 2 selects a
+// plain FP32 FMA GEMM instead); everything else is FP32 FMA on the CUDA cores.  A tcgen05/TMEM version of the GEMM is future work.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -147,35 +148,187 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const float* __restrict__ 
     }
 }
 
+// 1x1 convolution on the tensor cores with FP32-grade accuracy: every operand is split x = hi + lo (two TF32 values) and each 16x8x8 product
+// is three mma.sync (lo*hi + hi*lo + hi*hi, FP32 accumulate); the dropped lo*lo term is 2^-22 of the product.  Block = 8 warps as WM x WN,
+// each warp MT x NT tiles of m16n8, BK = 16.  Shared tiles are k-major with row strides = 8 (mod 32) floats so that the fragment loads
+// (lane -> 8 rows x 4 k) hit 32 distinct banks.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = __fsub_rn(x, __uint_as_float(hi));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int WM, int WN, int MT, int NT>
+__global__ void __launch_bounds__(256) conv1x1_mma_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+                                                          float* __restrict__ out, int Cin, int Cout, int HW, int ncols, Epi epi) {
+    constexpr int BK = 16, BM = WM * MT * 16, BN = WN * NT * 8, SA = BM + 8, SB = BN + 8, LKS = 256 / BN;
+    static_assert(WM * WN == 8 && (BN == 128 || BN == 256) && BM % 16 == 0, "8 warps; one B column per thread");
+    __shared__ __align__(16) float sA[BK][SA];
+    __shared__ __align__(16) float sB[BK][SB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int wm = warp / WN, wn = warp % WN;
+    const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int lc = tid % BN, lk0 = tid / BN, lj = j0 + lc;
+    const bool lvalid = lj < ncols;
+    int64_t lbase = 0;
+    if (lvalid) { const int f = lj / HW; lbase = (int64_t)f * Cin * HW + (lj - f * HW); }
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    for (int k0 = 0; k0 < Cin; k0 += BK) {
+        for (int e = tid; e < BM * (BK / 4); e += 256) {
+            const int m = e / (BK / 4), kq = (e % (BK / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + m < Cout && k0 + kq < Cin) v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(m0 + m) * Cin + k0 + kq));
+            sA[kq][m] = v.x; sA[kq + 1][m] = v.y; sA[kq + 2][m] = v.z; sA[kq + 3][m] = v.w;
+        }
+#pragma unroll
+        for (int k = lk0; k < BK; k += LKS) sB[k][lc] = (lvalid && k0 + k < Cin) ? __ldg(in + lbase + (int64_t)(k0 + k) * HW) : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < BK; ks += 8) {
+            uint32_t ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const int r = (wm * MT + i) * 16 + g;
+                split_tf32(sA[ks + t][r], ah[i][0], al[i][0]);
+                split_tf32(sA[ks + t][r + 8], ah[i][1], al[i][1]);
+                split_tf32(sA[ks + t + 4][r], ah[i][2], al[i][2]);
+                split_tf32(sA[ks + t + 4][r + 8], ah[i][3], al[i][3]);
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int c = (wn * NT + j) * 8 + g;
+                split_tf32(sB[ks + t][c], bh[j][0], bl[j][0]);
+                split_tf32(sB[ks + t + 4][c], bh[j][1], bl[j][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    mma_tf32(acc[i][j], al[i], bh[j]);
+                    mma_tf32(acc[i][j], ah[i], bl[j]);
+                    mma_tf32(acc[i][j], ah[i], bh[j]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int col = j0 + (wn * NT + j) * 8 + 2 * t + cc;
+            if (col >= ncols) continue;
+            const int f = col / HW, p = col - f * HW;
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int co = m0 + (wm * MT + i) * 16 + g + rr * 8;
+                    if (co >= Cout) continue;
+                    const int64_t idx = ((int64_t)f * Cout + co) * HW + p;
+                    out[idx] = apply_epi(epi, __fadd_rn(acc[i][j][rr * 2 + cc], bias ? __ldg(bias + co) : 0.f), idx);
+                }
+        }
+    }
+}
+
 struct ConvGeom {
     int Cin, Cout, H, W, OH, OW, k, stride, pad, dil;
 };
 
-// depth-wise k x k: one output per thread
-template <int K>
+// depth-wise K x K, stride S: four consecutive outputs of one row per thread; the K + 3S input values of each kernel row are loaded once and
+// shared by the four windows.  Each output accumulates ky-major / kx-minor from zero, then the bias.
+template <int K, int S>
 __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
-                                                     float* __restrict__ out, ConvGeom g, int64_t total, Epi epi) {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int ox = (int)(idx % g.OW);
-    const int oy = (int)((idx / g.OW) % g.OH);
-    const int64_t fc = idx / ((int64_t)g.OW * g.OH);
+                                                     float* __restrict__ out, ConvGeom g, int64_t total /* F*C*OH*ceil(OW/4) */, Epi epi) {
+    constexpr int NX = 3 * S + K;
+    const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (q >= total) return;
+    const int owq = (g.OW + 3) >> 2;
+    const int ox0 = (int)(q % owq) * 4;
+    const int oy = (int)((q / owq) % g.OH);
+    const int64_t fc = q / ((int64_t)owq * g.OH);
     const int c = (int)(fc % g.Cout);
     const float* src = in + fc * (int64_t)g.H * g.W;
-    const float* w = Wt + (int64_t)c * K * K;
-    float acc = 0.f;
+    float w[K * K];
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) w[i] = __ldg(Wt + (int64_t)c * K * K + i);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int ix0 = ox0 * S - g.pad;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
-        const int iy = oy * g.stride - g.pad + ky;
+        const int iy = oy * S - g.pad + ky;
         if (iy < 0 || iy >= g.H) continue;
+        const float* row = src + (int64_t)iy * g.W;
+        float x[NX];
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-            const int ix = ox * g.stride - g.pad + kx;
-            if (ix < 0 || ix >= g.W) continue;
-            acc = fmaf(__ldg(w + ky * K + kx), __ldg(src + (int64_t)iy * g.W + ix), acc);
+        for (int j = 0; j < NX; ++j) { const int ix = ix0 + j; x[j] = (ix >= 0 && ix < g.W) ? __ldg(row + ix) : 0.f; }
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                acc[o] = fmaf(w[ky * K + kx], x[o * S + kx], acc[o]);      // padding taps contribute w * 0
+            }
+    }
+    const float b = bias ? __ldg(bias + c) : 0.f;
+    const int64_t o0 = (fc * g.OH + oy) * (int64_t)g.OW + ox0;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+        if (ox0 + o < g.OW) out[o0 + o] = apply_epi(epi, __fadd_rn(acc[o], b), o0 + o);
+}
+
+// dense k x k convolution with few input channels (the network's first layer 3 -> 16, 3x3 stride 2, and the SE convolutions whose Cin is
+// not a multiple of 4): one output pixel x COT output channels per thread, the weights of the channel block staged in shared memory as
+// [ci][ky][kx][COT] so that every input value is loaded once and used COT times.
+constexpr int kCot = 8;
+__global__ void __launch_bounds__(256) conv_small_kernel(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                         float* __restrict__ out, ConvGeom g, Epi epi) {
+    extern __shared__ __align__(16) float sw[];
+    const int co0 = blockIdx.y * kCot, f = blockIdx.z;
+    const int taps = g.Cin * g.k * g.k;
+    for (int e = threadIdx.x; e < taps * kCot; e += 256) {
+        const int tp = e / kCot, o = e % kCot;
+        sw[e] = co0 + o < g.Cout ? __ldg(Wt + (int64_t)(co0 + o) * taps + tp) : 0.f;
+    }
+    __syncthreads();
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= g.OH * g.OW) return;
+    const int oy = p / g.OW, ox = p - oy * g.OW;
+    float acc[kCot];
+#pragma unroll
+    for (int o = 0; o < kCot; ++o) acc[o] = 0.f;
+    for (int ci = 0; ci < g.Cin; ++ci) {
+        const float* src = in + ((int64_t)f * g.Cin + ci) * g.H * g.W;
+        for (int ky = 0; ky < g.k; ++ky) {
+            const int iy = oy * g.stride - g.pad + ky * g.dil;
+            if (iy < 0 || iy >= g.H) continue;
+            for (int kx = 0; kx < g.k; ++kx) {
+                const int ix = ox * g.stride - g.pad + kx * g.dil;
+                if (ix < 0 || ix >= g.W) continue;
+                const float x = __ldg(src + (int64_t)iy * g.W + ix);
+                const float* wp = sw + ((ci * g.k + ky) * g.k + kx) * kCot;
+#pragma unroll
+                for (int o = 0; o < kCot; ++o) acc[o] = fmaf(wp[o], x, acc[o]);
+            }
         }
     }
-    out[idx] = apply_epi(epi, __fadd_rn(acc, bias ? __ldg(bias + c) : 0.f), idx);
+#pragma unroll
+    for (int o = 0; o < kCot; ++o) {
+        const int co = co0 + o;
+        if (co >= g.Cout) break;
+        const int64_t idx = ((int64_t)f * g.Cout + co) * g.OH * g.OW + p;
+        out[idx] = apply_epi(epi, __fadd_rn(acc[o], bias ? __ldg(bias + co) : 0.f), idx);
+    }
 }
 
 // dense k x k convolution (groups == 1), one output per thread: the network's first layer (3 -> 16, 3x3 stride 2) and any geometry the GEMM
@@ -645,7 +798,7 @@ int build_graph(sgs_detector* D) {
             set3(B[lout[i][0]], cout, oh, ow);
             const bool dw = L.type == "ConvolutionDepthWise";
             const int group = dw ? L.pi(7, 1) : 1;
-            if (dw && !(group == s.c && cout == s.c && dil == 1 && (k == 3 || k == 5))) { set_error("sgs_detector_create: layer %s: grouped convolution other than depth-wise 3x3/5x5 is not supported", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
+            if (dw && !(group == s.c && cout == s.c && dil == 1 && (k == 3 || k == 5) && (st == 1 || st == 2))) { set_error("sgs_detector_create: layer %s: grouped convolution other than depth-wise 3x3/5x5 with stride 1/2 is not supported", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
             const int64_t expect = dw ? (int64_t)cout * k * k : (int64_t)cout * s.c * k * k;
             if ((int64_t)L.weight.size() != expect) { set_error("sgs_detector_create: layer %s: weight size %zu, expected %lld", L.name.c_str(), L.weight.size(), (long long)expect); return SGS_ERR_INVALID; }
         } else if (is_eltwise(L)) {
@@ -934,20 +1087,30 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
         switch (op.kind) {
         case OP_CONV1X1: {
             const int HW = op.g.OH * op.g.OW; const int64_t ncols = (int64_t)F * HW;
-            if (op.g.Cout <= 16) conv1x1_kernel<16, 256><<<dim3((unsigned)((ncols + 255) / 256), (op.g.Cout + 15) / 16), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
+            if (!(D->flags & 4) && ncols < (1ll << 31) - 256) {
+                const int nc = (int)ncols;
+                if (op.g.Cout <= 16) conv1x1_mma_kernel<1, 8, 1, 4><<<dim3((nc + 255) / 256, (op.g.Cout + 15) / 16), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
+                else if (op.g.Cout <= 32) conv1x1_mma_kernel<1, 8, 2, 4><<<dim3((nc + 255) / 256, (op.g.Cout + 31) / 32), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
+                else conv1x1_mma_kernel<2, 4, 2, 4><<<dim3((nc + 127) / 128, (op.g.Cout + 63) / 64), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
+            } else if (op.g.Cout <= 16) conv1x1_kernel<16, 256><<<dim3((unsigned)((ncols + 255) / 256), (op.g.Cout + 15) / 16), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
             else if (op.g.Cout <= 32) conv1x1_kernel<32, 128><<<dim3((unsigned)((ncols + 127) / 128), (op.g.Cout + 31) / 32), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
             else conv1x1_kernel<64, 64><<<dim3((unsigned)((ncols + 63) / 64), (op.g.Cout + 63) / 64), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
             break;
         }
         case OP_CONV_DIRECT: {
             const int64_t total = (int64_t)F * op.g.Cout * op.g.OH * op.g.OW;
-            conv_direct_kernel<<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
+            const size_t wbytes = (size_t)op.g.Cin * op.g.k * op.g.k * kCot * sizeof(float);
+            if (wbytes <= 40 * 1024 && F <= 65535)
+                conv_small_kernel<<<dim3(nblk((int64_t)op.g.OH * op.g.OW), (op.g.Cout + kCot - 1) / kCot, F), 256, wbytes, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
+            else conv_direct_kernel<<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
             break;
         }
         case OP_DWCONV: {
-            const int64_t total = (int64_t)F * op.g.Cout * op.g.OH * op.g.OW;
-            if (op.g.k == 3) dwconv_kernel<3><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
-            else dwconv_kernel<5><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
+            const int64_t total = (int64_t)F * op.g.Cout * op.g.OH * ((op.g.OW + 3) / 4);
+            if (op.g.k == 3 && op.g.stride == 1) dwconv_kernel<3, 1><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
+            else if (op.g.k == 3) dwconv_kernel<3, 2><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
+            else if (op.g.stride == 1) dwconv_kernel<5, 1><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
+            else dwconv_kernel<5, 2><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
             break;
         }
         case OP_ELTWISE: {
