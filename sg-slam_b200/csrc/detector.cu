@@ -6,6 +6,7 @@
 // folds the constant sub-graphs (MemoryData scalars, PriorBox, their Concat) on the host, and turns the rest into a flat list of kernels:
 //   preprocess     : Mat::from_pixels_resize + substract_mean_normalize (Detector2D.cc:39-40), fixed-point bilinear (bit-exact with cv::resize)
 //   conv1x1        : 90 % of the MACs; register-tiled FP32 GEMM  W[Cout x Cin] * X[Cin x (frames*H*W)], bias + fused element-wise tail
+//                    (optional tensor-core variant, see below)
 //   dwconv / conv  : depth-wise 3x3 / 5x5 and the first dense 3x3, one output per thread, fused tail
 //   eltwise        : whatever element-wise chain could not be attached to a producer
 //   permute / copy : CHW -> HWC of the head outputs and their Concat
@@ -13,8 +14,10 @@
 // Element-wise layers (BinaryOp with a constant / a tensor / the chain's own start value, Clip, ReLU) that follow a producer are applied in
 // the producer's epilogue in graph order, one rounding per op, so fused and unfused execution give identical bits.
 // Layout: every blob is [frames][c][h][w] FP32 (ncnn's c,h,w order per frame); activations live in a pool planned by liveness.
-// The 1x1 convolutions run on the tensor cores as error-compensated TF32 (three mma.sync per product, FP32-grade accuracy; flags bit 2 selects a
-// plain FP32 FMA GEMM instead); everything else is FP32 FMA on the CUDA cores.  A tcgen05/TMEM version of the GEMM is future work.
+// Arithmetic is FP32 FMA on the CUDA cores.  flags bit 2 runs the 1x1 convolutions on the tensor cores instead (error-compensated TF32: three
+// mma.sync per product, FP32-grade accuracy); measured on B200 it is 5 % slower than the FMA GEMM on this network (the layers are latency / memory
+// bound at 8-22 % tensor-pipe activity, and the operand split costs ALU issue slots), so it is not the default.  A tcgen05/TMEM GEMM fed by TMA is
+// the next step.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -39,11 +42,24 @@ struct EpiStep {
 };
 constexpr int kMaxEpi = 8;
 struct Epi {
-    int n;
+    int n, kind;
     EpiStep s[kMaxEpi];
 };
 
+enum { EK_GENERIC = 0, EK_NONE, EK_RELU, EK_CLIP, EK_HSWISH, EK_ADD_T, EK_SE_TAIL };   // Epi::kind: recognised tails run as straight-line code
+
 __device__ __forceinline__ float apply_epi(const Epi& e, float v, int64_t idx) {
+    switch (e.kind) {                       // block-uniform
+    case EK_NONE: return v;
+    case EK_RELU: return fmaxf(v, 0.f);
+    case EK_CLIP: return fminf(fmaxf(v, e.s[0].a), e.s[0].b);
+    case EK_HSWISH:                         // v * clip(v + a) / b   (add scalar, clip, mul(rev) start, div scalar)
+        return __fdiv_rn(__fmul_rn(v, fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b)), e.s[3].a);
+    case EK_ADD_T: return __fadd_rn(v, __ldg(e.s[0].t + idx));
+    case EK_SE_TAIL:                        // t1 * (clip(v + a) / b) + t2   (add scalar, clip, div scalar, mul(rev) tensor, add tensor)
+        return __fadd_rn(__fmul_rn(__ldg(e.s[3].t + idx), __fdiv_rn(fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b), e.s[2].a)), __ldg(e.s[4].t + idx));
+    default: break;
+    }
     const float v0 = v;
     for (int i = 0; i < e.n; ++i) {
         const EpiStep& s = e.s[i];
@@ -152,10 +168,98 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const float* __restrict__ 
 // is three mma.sync (lo*hi + hi*lo + hi*hi, FP32 accumulate); the dropped lo*lo term is 2^-22 of the product.  Block = 8 warps as WM x WN,
 // each warp MT x NT tiles of m16n8, BK = 16.  Shared tiles are k-major with row strides = 8 (mod 32) floats so that the fragment loads
 // (lane -> 8 rows x 4 k) hit 32 distinct banks.
+// The same GEMM for the wide layers (Cout >= 96): 128 x 128 tile, BK = 8, 8 x 8 outputs per thread held as 2 x 2 blocks of 4 x 4 (64 floats apart, so
+// that every shared-memory read is a conflict-free / broadcast 16-byte load), next k-tile fetched into registers while the current one is multiplied.
+// Per output the FMA order is k ascending from zero, then the bias: bit-identical to conv1x1_kernel.
+__global__ void __launch_bounds__(256, 2) conv1x1_wide_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+                                                              float* __restrict__ out, int Cin, int Cout, int HW, int64_t ncols, Epi epi) {
+    constexpr int BM = 128, BN = 128, BK = 8;
+    __shared__ __align__(16) float sA[BK][BM + 4];
+    __shared__ __align__(16) float sB[BK][BN];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM;
+    const int64_t j0 = (int64_t)blockIdx.x * BN;
+    const int am = tid >> 1, akq = (tid & 1) * 4;                 // A: one float4 (4 k of one row) per thread
+    const int lc = tid & 127, lk0 = tid >> 7;                      // B: column lc, rows lk0, lk0 + 2, lk0 + 4, lk0 + 6
+    const int64_t lj = j0 + lc;
+    const bool lvalid = lj < ncols, avalid = m0 + am < Cout;
+    int64_t lbase = 0;
+    if (lvalid) { const int64_t f = lj / HW; lbase = f * (int64_t)Cin * HW + (lj - f * HW); }
+    const float* wrow = W + (int64_t)(m0 + am) * Cin;
+    float4 ra;
+    float rb[4];
+    auto gload = [&](int k0) {
+        ra = (avalid && k0 + akq < Cin) ? __ldg(reinterpret_cast<const float4*>(wrow + k0 + akq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const int k = k0 + lk0 + 2 * i; rb[i] = (lvalid && k < Cin) ? __ldg(in + lbase + (int64_t)k * HW) : 0.f; }
+    };
+    auto sstore = [&]() {
+        sA[akq][am] = ra.x; sA[akq + 1][am] = ra.y; sA[akq + 2][am] = ra.z; sA[akq + 3][am] = ra.w;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sB[lk0 + 2 * i][lc] = rb[i];
+    };
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    gload(0);
+    sstore();
+    __syncthreads();
+    for (int k0 = 0; k0 < Cin; k0 += BK) {
+        const bool more = k0 + BK < Cin;
+        if (more) gload(k0 + BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&sA[k][ty * 4]), a1 = *reinterpret_cast<const float4*>(&sA[k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&sB[k][tx * 4]), b1 = *reinterpret_cast<const float4*>(&sB[k][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+        if (more) { sstore(); __syncthreads(); }
+    }
+#pragma unroll
+    for (int jb = 0; jb < 2; ++jb) {
+        const int64_t col0 = j0 + jb * 64 + tx * 4;
+        if (col0 >= ncols) continue;
+        const int64_t f0 = col0 / HW;
+        const int p0 = (int)(col0 - f0 * HW);
+        const bool quad = col0 + 3 < ncols && p0 + 3 < HW;          // the four columns lie in one frame
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int co = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+            if (co >= Cout) continue;
+            const float b = bias ? __ldg(bias + co) : 0.f;
+            if (quad) {
+                const int64_t idx = (f0 * Cout + co) * HW + p0;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = apply_epi(epi, __fadd_rn(acc[i][jb * 4 + j], b), idx + j);
+                if ((idx & 3) == 0) *reinterpret_cast<float4*>(out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+                else { out[idx] = v[0]; out[idx + 1] = v[1]; out[idx + 2] = v[2]; out[idx + 3] = v[3]; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t col = col0 + j;
+                    if (col >= ncols) break;
+                    const int64_t f = col / HW;
+                    const int64_t idx = (f * Cout + co) * HW + (col - f * HW);
+                    out[idx] = apply_epi(epi, __fadd_rn(acc[i][jb * 4 + j], b), idx);
+                }
+            }
+        }
+    }
+}
+
+// x = hi + lo with hi, lo representable in TF32 (10 mantissa bits), both rounded to nearest / ties away like cvt.rna.tf32.f32 -- done with integer
+// adds and masks: the cvt instruction issues at a fraction of the ALU rate and would bound the whole GEMM.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = __fsub_rn(x, __uint_as_float(hi));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = (__float_as_uint(__fsub_rn(x, __uint_as_float(hi))) + 0x1000u) & 0xffffe000u;
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -164,12 +268,13 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 template <int WM, int WN, int MT, int NT>
-__global__ void __launch_bounds__(256) conv1x1_mma_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+__global__ void __launch_bounds__(256, 2) conv1x1_mma_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
                                                           float* __restrict__ out, int Cin, int Cout, int HW, int ncols, Epi epi) {
-    constexpr int BK = 16, BM = WM * MT * 16, BN = WN * NT * 8, SA = BM + 8, SB = BN + 8, LKS = 256 / BN;
+    constexpr int BK = 32, BM = WM * MT * 16, BN = WN * NT * 8, SA = BK + 4, SB = BN + 8, LKS = 256 / BN;
+    constexpr int NA = (BM * BK / 4 + 255) / 256, NBR = BK / LKS;           // float4 of A / floats of B each thread stages per k-tile
     static_assert(WM * WN == 8 && (BN == 128 || BN == 256) && BM % 16 == 0, "8 warps; one B column per thread");
-    __shared__ __align__(16) float sA[BK][SA];
-    __shared__ __align__(16) float sB[BK][SB];
+    __shared__ __align__(16) float sA[BM][SA];      // m-major: fragment loads (8 rows x 4 k per warp) hit banks 4g + t
+    __shared__ __align__(16) float sB[BK][SB];      // k-major, row stride = 8 (mod 32): banks 8t + g
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int wm = warp / WN, wn = warp % WN;
     const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
@@ -177,6 +282,30 @@ __global__ void __launch_bounds__(256) conv1x1_mma_kernel(const float* __restric
     const bool lvalid = lj < ncols;
     int64_t lbase = 0;
     if (lvalid) { const int f = lj / HW; lbase = (int64_t)f * Cin * HW + (lj - f * HW); }
+    float4 ra[NA];
+    float rb[NBR];
+    auto gload = [&](int k0) {                       // global -> registers (next k-tile, overlapped with the mma of the current one)
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int e = tid + i * 256, m = e / (BK / 4), kq = (e % (BK / 4)) * 4;
+            ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < BM * BK / 4 && m0 + m < Cout && k0 + kq < Cin) ra[i] = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(m0 + m) * Cin + k0 + kq));
+        }
+#pragma unroll
+        for (int i = 0; i < NBR; ++i) {
+            const int k = k0 + lk0 + i * LKS;
+            rb[i] = (lvalid && k < Cin) ? __ldg(in + lbase + (int64_t)k * HW) : 0.f;
+        }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int e = tid + i * 256, m = e / (BK / 4), kq = (e % (BK / 4)) * 4;
+            if (e < BM * BK / 4) *reinterpret_cast<float4*>(&sA[m][kq]) = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NBR; ++i) sB[lk0 + i * LKS][lc] = rb[i];
+    };
     float acc[MT][NT][4];
 #pragma unroll
     for (int i = 0; i < MT; ++i)
@@ -184,26 +313,23 @@ __global__ void __launch_bounds__(256) conv1x1_mma_kernel(const float* __restric
         for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    gload(0);
+    sstore();
+    __syncthreads();
     for (int k0 = 0; k0 < Cin; k0 += BK) {
-        for (int e = tid; e < BM * (BK / 4); e += 256) {
-            const int m = e / (BK / 4), kq = (e % (BK / 4)) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + m < Cout && k0 + kq < Cin) v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(m0 + m) * Cin + k0 + kq));
-            sA[kq][m] = v.x; sA[kq + 1][m] = v.y; sA[kq + 2][m] = v.z; sA[kq + 3][m] = v.w;
-        }
-#pragma unroll
-        for (int k = lk0; k < BK; k += LKS) sB[k][lc] = (lvalid && k0 + k < Cin) ? __ldg(in + lbase + (int64_t)(k0 + k) * HW) : 0.f;
-        __syncthreads();
+        const bool more = k0 + BK < Cin;
+        if (more) gload(k0 + BK);
 #pragma unroll
         for (int ks = 0; ks < BK; ks += 8) {
+            if (k0 + ks >= Cin) break;                      // block-uniform: the zero-filled tail of the last k-tile
             uint32_t ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
                 const int r = (wm * MT + i) * 16 + g;
-                split_tf32(sA[ks + t][r], ah[i][0], al[i][0]);
-                split_tf32(sA[ks + t][r + 8], ah[i][1], al[i][1]);
-                split_tf32(sA[ks + t + 4][r], ah[i][2], al[i][2]);
-                split_tf32(sA[ks + t + 4][r + 8], ah[i][3], al[i][3]);
+                split_tf32(sA[r][ks + t], ah[i][0], al[i][0]);
+                split_tf32(sA[r + 8][ks + t], ah[i][1], al[i][1]);
+                split_tf32(sA[r][ks + t + 4], ah[i][2], al[i][2]);
+                split_tf32(sA[r + 8][ks + t + 4], ah[i][3], al[i][3]);
             }
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
@@ -211,34 +337,52 @@ __global__ void __launch_bounds__(256) conv1x1_mma_kernel(const float* __restric
                 split_tf32(sB[ks + t][c], bh[j][0], bl[j][0]);
                 split_tf32(sB[ks + t + 4][c], bh[j][1], bl[j][1]);
             }
+            // term-major: the MT*NT accumulators are independent, so consecutive HMMAs never wait on each other's result
 #pragma unroll
             for (int i = 0; i < MT; ++i)
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    mma_tf32(acc[i][j], al[i], bh[j]);
-                    mma_tf32(acc[i][j], ah[i], bl[j]);
-                    mma_tf32(acc[i][j], ah[i], bh[j]);
-                }
+                for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], al[i], bh[j]);
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], ah[i], bl[j]);
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], ah[i], bh[j]);
         }
         __syncthreads();
+        if (more) { sstore(); __syncthreads(); }
     }
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
+        const int col = j0 + (wn * NT + j) * 8 + 2 * t;          // this thread's two adjacent columns of the n8 tile
+        if (col >= ncols) continue;
+        const int f = col / HW, p = col - f * HW;
+        const bool pair = col + 1 < ncols && p + 1 < HW;          // the second column belongs to the same frame
+        int f1 = f, p1 = p + 1;
+        if (!pair && col + 1 < ncols) { f1 = f + 1; p1 = 0; }
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int col = j0 + (wn * NT + j) * 8 + 2 * t + cc;
-            if (col >= ncols) continue;
-            const int f = col / HW, p = col - f * HW;
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int i = 0; i < MT; ++i)
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int co = m0 + (wm * MT + i) * 16 + g + rr * 8;
-                    if (co >= Cout) continue;
-                    const int64_t idx = ((int64_t)f * Cout + co) * HW + p;
-                    out[idx] = apply_epi(epi, __fadd_rn(acc[i][j][rr * 2 + cc], bias ? __ldg(bias + co) : 0.f), idx);
+            for (int rr = 0; rr < 2; ++rr) {
+                const int co = m0 + (wm * MT + i) * 16 + g + rr * 8;
+                if (co >= Cout) continue;
+                const float b = bias ? __ldg(bias + co) : 0.f;
+                const int64_t idx = ((int64_t)f * Cout + co) * HW + p;
+                const float v0 = apply_epi(epi, __fadd_rn(acc[i][j][rr * 2], b), idx);
+                if (pair) {
+                    const float v1 = apply_epi(epi, __fadd_rn(acc[i][j][rr * 2 + 1], b), idx + 1);
+                    if ((idx & 1) == 0) *reinterpret_cast<float2*>(out + idx) = make_float2(v0, v1);
+                    else { out[idx] = v0; out[idx + 1] = v1; }
+                } else {
+                    out[idx] = v0;
+                    if (col + 1 < ncols) {
+                        const int64_t idx1 = ((int64_t)f1 * Cout + co) * HW + p1;
+                        out[idx1] = apply_epi(epi, __fadd_rn(acc[i][j][rr * 2 + 1], b), idx1);
+                    }
                 }
-        }
+            }
     }
 }
 
@@ -1012,11 +1156,20 @@ int build_graph(sgs_detector* D) {
 }
 
 Epi make_epi(const sgs_detector* D, const std::vector<EpiStepH>& h) {
-    Epi e; e.n = (int)h.size();
+    Epi e; e.n = (int)h.size(); e.kind = EK_GENERIC;
     for (int i = 0; i < e.n; ++i) {
         e.s[i].op = h[i].op; e.s[i].src = h[i].src; e.s[i].rev = h[i].rev; e.s[i].a = h[i].a; e.s[i].b = h[i].b;
         e.s[i].t = h[i].src == SRC_TENSOR ? D->blobs[h[i].tblob].dev : nullptr;
     }
+    auto is = [&](int i, int op, int src) { return h[i].op == op && (op >= E_CLIP || h[i].src == src); };
+    // the fast paths reproduce the generic loop operation for operation (same operand order, one rounding each)
+    if (e.n == 0) e.kind = EK_NONE;
+    else if (e.n == 1 && h[0].op == E_RELU) e.kind = EK_RELU;
+    else if (e.n == 1 && h[0].op == E_CLIP) e.kind = EK_CLIP;
+    else if (e.n == 1 && is(0, E_ADD, SRC_TENSOR)) e.kind = EK_ADD_T;          // addition commutes: rev is irrelevant
+    else if (e.n == 4 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_MUL, SRC_START) && is(3, E_DIV, SRC_SCALAR) && !h[3].rev) e.kind = EK_HSWISH;
+    else if (e.n == 5 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_DIV, SRC_SCALAR) && !h[2].rev && is(3, E_MUL, SRC_TENSOR) && is(4, E_ADD, SRC_TENSOR))
+        e.kind = EK_SE_TAIL;
     return e;
 }
 
@@ -1087,12 +1240,16 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
         switch (op.kind) {
         case OP_CONV1X1: {
             const int HW = op.g.OH * op.g.OW; const int64_t ncols = (int64_t)F * HW;
-            if (!(D->flags & 4) && ncols < (1ll << 31) - 256) {
+            if ((D->flags & 4) && ncols < (1ll << 31) - 256) {
                 const int nc = (int)ncols;
-                if (op.g.Cout <= 16) conv1x1_mma_kernel<1, 8, 1, 4><<<dim3((nc + 255) / 256, (op.g.Cout + 15) / 16), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
-                else if (op.g.Cout <= 32) conv1x1_mma_kernel<1, 8, 2, 4><<<dim3((nc + 255) / 256, (op.g.Cout + 31) / 32), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
-                else conv1x1_mma_kernel<2, 4, 2, 4><<<dim3((nc + 127) / 128, (op.g.Cout + 63) / 64), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
-            } else if (op.g.Cout <= 16) conv1x1_kernel<16, 256><<<dim3((unsigned)((ncols + 255) / 256), (op.g.Cout + 15) / 16), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
+                const dim3 g16((nc + 255) / 256, (op.g.Cout + 15) / 16), g32((nc + 255) / 256, (op.g.Cout + 31) / 32), g64((nc + 127) / 128, (op.g.Cout + 63) / 64);
+#define SGS_MMA_ARGS bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi
+                if (op.g.Cout <= 16) conv1x1_mma_kernel<1, 8, 1, 4><<<g16, 256, 0, st>>>(SGS_MMA_ARGS);
+                else if (op.g.Cout <= 32) conv1x1_mma_kernel<1, 8, 2, 4><<<g32, 256, 0, st>>>(SGS_MMA_ARGS);
+                else conv1x1_mma_kernel<2, 4, 2, 4><<<g64, 256, 0, st>>>(SGS_MMA_ARGS);
+#undef SGS_MMA_ARGS
+            } else if (op.g.Cout >= 96 && !(D->flags & 8)) conv1x1_wide_kernel<<<dim3((unsigned)((ncols + 127) / 128), (op.g.Cout + 127) / 128), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
+            else if (op.g.Cout <= 16) conv1x1_kernel<16, 256><<<dim3((unsigned)((ncols + 255) / 256), (op.g.Cout + 15) / 16), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
             else if (op.g.Cout <= 32) conv1x1_kernel<32, 128><<<dim3((unsigned)((ncols + 127) / 128), (op.g.Cout + 31) / 32), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
             else conv1x1_kernel<64, 64><<<dim3((unsigned)((ncols + 63) / 64), (op.g.Cout + 63) / 64), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
             break;

@@ -10,6 +10,7 @@
 #include "sgslam/FrameDynamic.h"
 #include "sgslam/FrameGeometry.h"
 #include "sgslam/Optimizer.h"
+#include "sgslam/Detector2D.h"
 #include "sgslam/ORBextractor.h"
 #include "sgslam/ORBmatcher.h"
 
@@ -169,7 +170,33 @@ int main(int argc, char** argv) {
     if (pin != pexp_n) return fail("PoseOptimization: inlier count");
     for (int i = 0; i < npo; ++i) if (phas[i] && pf.mvbOutlier[i] != (pexp_out[i] != 0)) return fail("PoseOptimization: outlier flags");
     for (int i = 0; i < 16; ++i) if (std::fabs(pf.mTcw.at<float>(i / 4, i % 4) - pexpT[i]) > 1e-6f) return fail("PoseOptimization: pose");
-    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges\n", nkp, nm, kept, nd, nlk, nview, nfr,
-                pin, npo);
+    // 7. Detector2D::detect through the class mirror (model paths on the command line)
+    int ndet = -1, npers = 0;
+    if (argc >= 4) {
+        int32_t dh[3]; f.read(reinterpret_cast<char*>(dh), sizeof dh);
+        const int dW = dh[0], dH = dh[1], dn = dh[2];
+        std::vector<uint8_t> rgb = rd<uint8_t>(f, (size_t)dW * dH * 3);
+        std::vector<int32_t> eid = rd<int32_t>(f, dn);
+        std::vector<float> erect = rd<float>(f, (size_t)dn * 5);          // prob, x, y, w, h
+        struct Img { const uint8_t* data; int cols, rows; size_t step; } im3{rgb.data(), dW, dH, (size_t)dW * 3};
+        DetectorGPU det(0.9f, 0.01f, argv[2], argv[3]);
+        det.detect(im3);
+        ndet = (int)det.mvObjects2D_to_View.size();
+        if (ndet != dn) return fail("Detector2D: object count");
+        size_t others = 0;
+        for (int i = 0; i < dn; ++i) {
+            const Object2D& o = det.mvObjects2D_to_View[i];
+            if (o.id != eid[i] || o.name != DetectorGPU::class_name(eid[i])) return fail("Detector2D: labels");
+            const float got[5] = {o.prob, o.rect.x, o.rect.y, o.rect.width, o.rect.height};
+            for (int k = 0; k < 5; ++k) if (std::fabs(got[k] - erect[(size_t)i * 5 + k]) > 0.03f) return fail("Detector2D: boxes");
+            if (o.id == 15) ++npers; else ++others;
+        }
+        if ((int)det.mvPotentialDynamicBorderForMapping.size() != npers || det.mvObjects2D.size() != others || det.mbHaveDynamicObjectForMapping != (npers > 0))
+            return fail("Detector2D: person / object split");
+        det.detect(im3);                                                    // the view list accumulates until draw_objects clears it
+        if ((int)det.mvObjects2D_to_View.size() != 2 * dn || (int)det.mvPotentialDynamicBorderForMapping.size() != npers) return fail("Detector2D: second call");
+    }
+    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges, %d detections (%d persons)\n", nkp, nm, kept,
+                nd, nlk, nview, nfr, pin, npo, ndet, npers);
     return 0;
 }

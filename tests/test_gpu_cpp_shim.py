@@ -80,6 +80,15 @@ def test_shim_on_gpu(tmp_path):
         np.array([700], np.int32).tofile(f); ps['T0'].astype(np.float32).tofile(f); ps['xyz'].astype(np.float32).tofile(f); pk.tofile(f)
         ps['uright'].astype(np.float32).tofile(f); ps['inv_s2'][:8].astype(np.float32).tofile(f); ps['has'].astype(np.uint8).tofile(f); po.astype(np.uint8).tofile(f)
         pT.astype(np.float32).tofile(f); np.array([pn], np.int32).tofile(f)
-    out = subprocess.run([exe, str(path)], capture_output=True, text=True)
+        # 7. Detector2D::detect on the synthetic SSD graph of tests/detector_model.py
+        import detector_model as DM
+        import detector_oracle as DO
+        import ncnn_model as NM
+        dpp, dbp = DM.write_mini_model(str(tmp_path / 'model'), 0)
+        layers = NM.parse_param(dpp); NM.load_weights(layers, dbp)
+        rgb = DM.synthetic_rgb(480, 640, 1)
+        _, (objs, _, _) = DO.detect(layers, rgb, 0.9, 0.01)
+        np.array([640, 480, len(objs)], np.int32).tofile(f); rgb.tofile(f); objs[:, 0].astype(np.int32).tofile(f); objs[:, 1:].astype(np.float32).tofile(f)
+    out = subprocess.run([exe, str(path), dpp, dbp], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'OK shim' in out.stdout

@@ -18,6 +18,7 @@ REAL = os.path.join(ROOT, 'oracle', '_ref', 'ncnn_model', 'mobilenetv3_ssdlite_v
 
 
 def main():
+    flags = int(os.environ.get('SGS_DET_FLAGS', '0'))
     batches = [int(a) for a in sys.argv[1:]] or [1, 8, 64, 256]
     if os.path.exists(REAL + '.param'):
         pp, bp, name = REAL + '.param', REAL + '.bin', 'mobilenetv3_ssdlite_voc'
@@ -26,7 +27,7 @@ def main():
     H, W = 480, 640
     base = np.stack([DM.synthetic_rgb(H, W, s) for s in range(8)])
     for F in batches:
-        det = B.Detector(pp, bp, max_frames=F)
+        det = B.Detector(pp, bp, max_frames=F, flags=flags)
         d = torch.from_numpy(base[np.arange(F) % 8]).cuda()
         nd = torch.zeros(F, dtype=torch.int32, device='cuda'); boxes = torch.zeros((F, 4, 4), device='cuda'); have = torch.zeros(F, dtype=torch.uint8, device='cuda')
         run = lambda: det.detect_device(d.data_ptr(), H * W * 3, W * 3, W, H, F, d_dyn_rm=boxes.data_ptr(), d_ndyn_rm=nd.data_ptr(), d_have_dyn_rm=have.data_ptr(), max_boxes=4)
