@@ -48,28 +48,43 @@ struct Epi {
 
 enum { EK_GENERIC = 0, EK_NONE, EK_RELU, EK_CLIP, EK_HSWISH, EK_ADD_T, EK_SE_TAIL };   // Epi::kind: recognised tails run as straight-line code
 
+template <int KIND>
 __device__ __forceinline__ float apply_epi(const Epi& e, float v, int64_t idx) {
-    switch (e.kind) {                       // block-uniform
-    case EK_NONE: return v;
-    case EK_RELU: return fmaxf(v, 0.f);
-    case EK_CLIP: return fminf(fmaxf(v, e.s[0].a), e.s[0].b);
-    case EK_HSWISH:                         // v * clip(v + a) / b   (add scalar, clip, mul(rev) start, div scalar)
+    if constexpr (KIND == EK_NONE) return v;
+    else if constexpr (KIND == EK_RELU) return fmaxf(v, 0.f);
+    else if constexpr (KIND == EK_CLIP) return fminf(fmaxf(v, e.s[0].a), e.s[0].b);
+    else if constexpr (KIND == EK_HSWISH)                // v * clip(v + a) / b   (add scalar, clip, mul(rev) start, div scalar)
         return __fdiv_rn(__fmul_rn(v, fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b)), e.s[3].a);
-    case EK_ADD_T: return __fadd_rn(v, __ldg(e.s[0].t + idx));
-    case EK_SE_TAIL:                        // t1 * (clip(v + a) / b) + t2   (add scalar, clip, div scalar, mul(rev) tensor, add tensor)
+    else if constexpr (KIND == EK_ADD_T) return __fadd_rn(v, __ldg(e.s[0].t + idx));
+    else if constexpr (KIND == EK_SE_TAIL)               // t1 * (clip(v + a) / b) + t2   (add scalar, clip, div scalar, mul(rev) tensor, add tensor)
         return __fadd_rn(__fmul_rn(__ldg(e.s[3].t + idx), __fdiv_rn(fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b), e.s[2].a)), __ldg(e.s[4].t + idx));
-    default: break;
+    else {
+        const float v0 = v;
+        for (int i = 0; i < e.n; ++i) {
+            const EpiStep& s = e.s[i];
+            if (s.op == E_CLIP) { v = fminf(fmaxf(v, s.a), s.b); continue; }
+            if (s.op == E_RELU) { v = fmaxf(v, 0.f); continue; }
+            const float o = s.src == SRC_SCALAR ? s.a : (s.src == SRC_START ? v0 : __ldg(s.t + idx));
+            const float x = s.rev ? o : v, y = s.rev ? v : o;
+            v = s.op == E_ADD ? __fadd_rn(x, y) : s.op == E_SUB ? __fsub_rn(x, y) : s.op == E_MUL ? __fmul_rn(x, y) : __fdiv_rn(x, y);
+        }
+        return v;
     }
-    const float v0 = v;
-    for (int i = 0; i < e.n; ++i) {
-        const EpiStep& s = e.s[i];
-        if (s.op == E_CLIP) { v = fminf(fmaxf(v, s.a), s.b); continue; }
-        if (s.op == E_RELU) { v = fmaxf(v, 0.f); continue; }
-        const float o = s.src == SRC_SCALAR ? s.a : (s.src == SRC_START ? v0 : __ldg(s.t + idx));
-        const float x = s.rev ? o : v, y = s.rev ? v : o;
-        v = s.op == E_ADD ? __fadd_rn(x, y) : s.op == E_SUB ? __fsub_rn(x, y) : s.op == E_MUL ? __fmul_rn(x, y) : __fdiv_rn(x, y);
+}
+
+// Runs `body` with the tail kind as a compile-time constant: the (block-uniform) switch is taken once per thread, not once per output.
+template <int KIND> struct EpiKind { static constexpr int value = KIND; };
+template <class F>
+__device__ __forceinline__ void epi_dispatch(int kind, F&& body) {
+    switch (kind) {
+    case EK_NONE: body(EpiKind<EK_NONE>{}); break;
+    case EK_RELU: body(EpiKind<EK_RELU>{}); break;
+    case EK_CLIP: body(EpiKind<EK_CLIP>{}); break;
+    case EK_HSWISH: body(EpiKind<EK_HSWISH>{}); break;
+    case EK_ADD_T: body(EpiKind<EK_ADD_T>{}); break;
+    case EK_SE_TAIL: body(EpiKind<EK_SE_TAIL>{}); break;
+    default: body(EpiKind<EK_GENERIC>{}); break;
     }
-    return v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------- kernels
@@ -108,19 +123,17 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
 // 1x1 convolution as a GEMM over all frames: out[f][co][p] = bias[co] + sum_ci W[co][ci] * in[f][ci][p].  Columns j = f*HW + p.
 template <int BM, int BN>
 __global__ void __launch_bounds__(256) conv1x1_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
-                                                      float* __restrict__ out, int Cin, int Cout, int HW, int64_t ncols, Epi epi) {
+                                                      float* __restrict__ out, int Cin, int Cout, int HW, int ncols, Epi epi) {
     constexpr int BK = 16, TX = BN / 4, LKS = 256 / BN;
     static_assert(BM * BN == 4096, "256 threads x 4x4 outputs");
     __shared__ __align__(16) float sA[BK][BM + 4];
     __shared__ __align__(16) float sB[BK][BN];
     const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
-    const int m0 = blockIdx.y * BM;
-    const int64_t j0 = (int64_t)blockIdx.x * BN;
-    const int lc = tid % BN, lk0 = tid / BN;
-    const int64_t lj = j0 + lc;
+    const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int lc = tid % BN, lk0 = tid / BN, lj = j0 + lc;
     const bool lvalid = lj < ncols;
     int64_t lbase = 0;
-    if (lvalid) { const int64_t f = lj / HW; lbase = f * (int64_t)Cin * HW + (lj - f * HW); }
+    if (lvalid) { const int f = lj / HW; lbase = (int64_t)f * Cin * HW + (lj - f * HW); }
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -148,111 +161,28 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const float* __restrict__ 
         }
         __syncthreads();
     }
+    // this thread's four adjacent columns: frame / pixel of the first by one division, the others by carry
+    const int col0 = j0 + tx * 4;
+    if (col0 >= ncols) return;
+    int fj[4], pj[4];
+    fj[0] = col0 / HW; pj[0] = col0 - fj[0] * HW;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int64_t col = j0 + tx * 4 + j;
-        if (col >= ncols) continue;
-        const int64_t f = col / HW;
-        const int p = (int)(col - f * HW);
+    for (int j = 1; j < 4; ++j) { fj[j] = fj[j - 1]; pj[j] = pj[j - 1] + 1; if (pj[j] >= HW) { pj[j] = 0; ++fj[j]; } }
+    epi_dispatch(epi.kind, [&](auto kind) {
+        constexpr int EK = decltype(kind)::value;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int co = m0 + ty * 4 + i;
-            if (co >= Cout) continue;
-            const int64_t idx = (f * Cout + co) * HW + p;
-            out[idx] = apply_epi(epi, __fadd_rn(acc[i][j], bias ? __ldg(bias + co) : 0.f), idx);
-        }
-    }
-}
-
-// 1x1 convolution on the tensor cores with FP32-grade accuracy: every operand is split x = hi + lo (two TF32 values) and each 16x8x8 product
-// is three mma.sync (lo*hi + hi*lo + hi*hi, FP32 accumulate); the dropped lo*lo term is 2^-22 of the product.  Block = 8 warps as WM x WN,
-// each warp MT x NT tiles of m16n8, BK = 16.  Shared tiles are k-major with row strides = 8 (mod 32) floats so that the fragment loads
-// (lane -> 8 rows x 4 k) hit 32 distinct banks.
-// The same GEMM for the wide layers (Cout >= 96): 128 x 128 tile, BK = 8, 8 x 8 outputs per thread held as 2 x 2 blocks of 4 x 4 (64 floats apart, so
-// that every shared-memory read is a conflict-free / broadcast 16-byte load), next k-tile fetched into registers while the current one is multiplied.
-// Per output the FMA order is k ascending from zero, then the bias: bit-identical to conv1x1_kernel.
-__global__ void __launch_bounds__(256, 2) conv1x1_wide_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
-                                                              float* __restrict__ out, int Cin, int Cout, int HW, int64_t ncols, Epi epi) {
-    constexpr int BM = 128, BN = 128, BK = 8;
-    __shared__ __align__(16) float sA[BK][BM + 4];
-    __shared__ __align__(16) float sB[BK][BN];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * BM;
-    const int64_t j0 = (int64_t)blockIdx.x * BN;
-    const int am = tid >> 1, akq = (tid & 1) * 4;                 // A: one float4 (4 k of one row) per thread
-    const int lc = tid & 127, lk0 = tid >> 7;                      // B: column lc, rows lk0, lk0 + 2, lk0 + 4, lk0 + 6
-    const int64_t lj = j0 + lc;
-    const bool lvalid = lj < ncols, avalid = m0 + am < Cout;
-    int64_t lbase = 0;
-    if (lvalid) { const int64_t f = lj / HW; lbase = f * (int64_t)Cin * HW + (lj - f * HW); }
-    const float* wrow = W + (int64_t)(m0 + am) * Cin;
-    float4 ra;
-    float rb[4];
-    auto gload = [&](int k0) {
-        ra = (avalid && k0 + akq < Cin) ? __ldg(reinterpret_cast<const float4*>(wrow + k0 + akq)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const int k = k0 + lk0 + 2 * i; rb[i] = (lvalid && k < Cin) ? __ldg(in + lbase + (int64_t)k * HW) : 0.f; }
-    };
-    auto sstore = [&]() {
-        sA[akq][am] = ra.x; sA[akq + 1][am] = ra.y; sA[akq + 2][am] = ra.z; sA[akq + 3][am] = ra.w;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sB[lk0 + 2 * i][lc] = rb[i];
-    };
-    float acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    gload(0);
-    sstore();
-    __syncthreads();
-    for (int k0 = 0; k0 < Cin; k0 += BK) {
-        const bool more = k0 + BK < Cin;
-        if (more) gload(k0 + BK);
-#pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&sA[k][ty * 4]), a1 = *reinterpret_cast<const float4*>(&sA[k][64 + ty * 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&sB[k][tx * 4]), b1 = *reinterpret_cast<const float4*>(&sB[k][64 + tx * 4]);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-        __syncthreads();
-        if (more) { sstore(); __syncthreads(); }
-    }
-#pragma unroll
-    for (int jb = 0; jb < 2; ++jb) {
-        const int64_t col0 = j0 + jb * 64 + tx * 4;
-        if (col0 >= ncols) continue;
-        const int64_t f0 = col0 / HW;
-        const int p0 = (int)(col0 - f0 * HW);
-        const bool quad = col0 + 3 < ncols && p0 + 3 < HW;          // the four columns lie in one frame
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int co = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
-            if (co >= Cout) continue;
+            if (co >= Cout) break;
             const float b = bias ? __ldg(bias + co) : 0.f;
-            if (quad) {
-                const int64_t idx = (f0 * Cout + co) * HW + p0;
-                float v[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = apply_epi(epi, __fadd_rn(acc[i][jb * 4 + j], b), idx + j);
-                if ((idx & 3) == 0) *reinterpret_cast<float4*>(out + idx) = make_float4(v[0], v[1], v[2], v[3]);
-                else { out[idx] = v[0]; out[idx + 1] = v[1]; out[idx + 2] = v[2]; out[idx + 3] = v[3]; }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t col = col0 + j;
-                    if (col >= ncols) break;
-                    const int64_t f = col / HW;
-                    const int64_t idx = (f * Cout + co) * HW + (col - f * HW);
-                    out[idx] = apply_epi(epi, __fadd_rn(acc[i][jb * 4 + j], b), idx);
-                }
+            for (int j = 0; j < 4; ++j) {
+                if (col0 + j >= ncols) break;
+                const int64_t idx = ((int64_t)fj[j] * Cout + co) * HW + pj[j];
+                out[idx] = apply_epi<EK>(epi, __fadd_rn(acc[i][j], b), idx);
             }
         }
-    }
+    });
 }
 
 // x = hi + lo with hi, lo representable in TF32 (10 mantissa bits), both rounded to nearest / ties away like cvt.rna.tf32.f32 -- done with integer
@@ -354,36 +284,39 @@ __global__ void __launch_bounds__(256, 2) conv1x1_mma_kernel(const float* __rest
         __syncthreads();
         if (more) { sstore(); __syncthreads(); }
     }
+    epi_dispatch(epi.kind, [&](auto kind) {
+        constexpr int EK = decltype(kind)::value;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        const int col = j0 + (wn * NT + j) * 8 + 2 * t;          // this thread's two adjacent columns of the n8 tile
-        if (col >= ncols) continue;
-        const int f = col / HW, p = col - f * HW;
-        const bool pair = col + 1 < ncols && p + 1 < HW;          // the second column belongs to the same frame
-        int f1 = f, p1 = p + 1;
-        if (!pair && col + 1 < ncols) { f1 = f + 1; p1 = 0; }
+        for (int j = 0; j < NT; ++j) {
+            const int col = j0 + (wn * NT + j) * 8 + 2 * t;          // this thread's two adjacent columns of the n8 tile
+            if (col >= ncols) continue;
+            const int f = col / HW, p = col - f * HW;
+            const bool pair = col + 1 < ncols && p + 1 < HW;          // the second column belongs to the same frame
+            int f1 = f, p1 = p + 1;
+            if (!pair && col + 1 < ncols) { f1 = f + 1; p1 = 0; }
 #pragma unroll
-        for (int i = 0; i < MT; ++i)
+            for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int co = m0 + (wm * MT + i) * 16 + g + rr * 8;
-                if (co >= Cout) continue;
-                const float b = bias ? __ldg(bias + co) : 0.f;
-                const int64_t idx = ((int64_t)f * Cout + co) * HW + p;
-                const float v0 = apply_epi(epi, __fadd_rn(acc[i][j][rr * 2], b), idx);
-                if (pair) {
-                    const float v1 = apply_epi(epi, __fadd_rn(acc[i][j][rr * 2 + 1], b), idx + 1);
-                    if ((idx & 1) == 0) *reinterpret_cast<float2*>(out + idx) = make_float2(v0, v1);
-                    else { out[idx] = v0; out[idx + 1] = v1; }
-                } else {
-                    out[idx] = v0;
-                    if (col + 1 < ncols) {
-                        const int64_t idx1 = ((int64_t)f1 * Cout + co) * HW + p1;
-                        out[idx1] = apply_epi(epi, __fadd_rn(acc[i][j][rr * 2 + 1], b), idx1);
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int co = m0 + (wm * MT + i) * 16 + g + rr * 8;
+                    if (co >= Cout) continue;
+                    const float b = bias ? __ldg(bias + co) : 0.f;
+                    const int64_t idx = ((int64_t)f * Cout + co) * HW + p;
+                    const float v0 = apply_epi<EK>(epi, __fadd_rn(acc[i][j][rr * 2], b), idx);
+                    if (pair) {
+                        const float v1 = apply_epi<EK>(epi, __fadd_rn(acc[i][j][rr * 2 + 1], b), idx + 1);
+                        if ((idx & 1) == 0) *reinterpret_cast<float2*>(out + idx) = make_float2(v0, v1);
+                        else { out[idx] = v0; out[idx + 1] = v1; }
+                    } else {
+                        out[idx] = v0;
+                        if (col + 1 < ncols) {
+                            const int64_t idx1 = ((int64_t)f1 * Cout + co) * HW + p1;
+                            out[idx1] = apply_epi<EK>(epi, __fadd_rn(acc[i][j][rr * 2 + 1], b), idx1);
+                        }
                     }
                 }
-            }
-    }
+        }
+    });
 }
 
 struct ConvGeom {
@@ -394,41 +327,41 @@ struct ConvGeom {
 // shared by the four windows.  Each output accumulates ky-major / kx-minor from zero, then the bias.
 template <int K, int S>
 __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
-                                                     float* __restrict__ out, ConvGeom g, int64_t total /* F*C*OH*ceil(OW/4) */, Epi epi) {
+                                                     float* __restrict__ out, ConvGeom g, Epi epi) {
     constexpr int NX = 3 * S + K;
-    const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (q >= total) return;
     const int owq = (g.OW + 3) >> 2;
-    const int ox0 = (int)(q % owq) * 4;
-    const int oy = (int)((q / owq) % g.OH);
-    const int64_t fc = q / ((int64_t)owq * g.OH);
-    const int c = (int)(fc % g.Cout);
+    const int q = blockIdx.x * 256 + threadIdx.x;                  // (row, quad of outputs) inside one channel plane
+    if (q >= g.OH * owq) return;
+    const int oy = q / owq, ox0 = (q - oy * owq) * 4;
+    const int c = blockIdx.y;
+    const int64_t fc = (int64_t)blockIdx.z * g.Cout + c;
     const float* src = in + fc * (int64_t)g.H * g.W;
     float w[K * K];
 #pragma unroll
-    for (int i = 0; i < K * K; ++i) w[i] = __ldg(Wt + (int64_t)c * K * K + i);
+    for (int i = 0; i < K * K; ++i) w[i] = __ldg(Wt + c * K * K + i);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const int ix0 = ox0 * S - g.pad;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
         const int iy = oy * S - g.pad + ky;
         if (iy < 0 || iy >= g.H) continue;
-        const float* row = src + (int64_t)iy * g.W;
+        const float* row = src + iy * g.W;
         float x[NX];
 #pragma unroll
         for (int j = 0; j < NX; ++j) { const int ix = ix0 + j; x[j] = (ix >= 0 && ix < g.W) ? __ldg(row + ix) : 0.f; }
 #pragma unroll
         for (int kx = 0; kx < K; ++kx)
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                acc[o] = fmaf(w[ky * K + kx], x[o * S + kx], acc[o]);      // padding taps contribute w * 0
-            }
+            for (int o = 0; o < 4; ++o) acc[o] = fmaf(w[ky * K + kx], x[o * S + kx], acc[o]);      // padding taps contribute w * 0
     }
     const float b = bias ? __ldg(bias + c) : 0.f;
     const int64_t o0 = (fc * g.OH + oy) * (int64_t)g.OW + ox0;
+    epi_dispatch(epi.kind, [&](auto kind) {
+        constexpr int EK = decltype(kind)::value;
 #pragma unroll
-    for (int o = 0; o < 4; ++o)
-        if (ox0 + o < g.OW) out[o0 + o] = apply_epi(epi, __fadd_rn(acc[o], b), o0 + o);
+        for (int o = 0; o < 4; ++o)
+            if (ox0 + o < g.OW) out[o0 + o] = apply_epi<EK>(epi, __fadd_rn(acc[o], b), o0 + o);
+    });
 }
 
 // dense k x k convolution with few input channels (the network's first layer 3 -> 16, 3x3 stride 2, and the SE convolutions whose Cin is
@@ -466,13 +399,17 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const float* __restrict
             }
         }
     }
+    epi_dispatch(epi.kind, [&](auto kind) {
+        constexpr int EK = decltype(kind)::value;
 #pragma unroll
-    for (int o = 0; o < kCot; ++o) {
-        const int co = co0 + o;
-        if (co >= g.Cout) break;
-        const int64_t idx = ((int64_t)f * g.Cout + co) * g.OH * g.OW + p;
-        out[idx] = apply_epi(epi, __fadd_rn(acc[o], bias ? __ldg(bias + co) : 0.f), idx);
-    }
+        for (int o = 0; o < kCot; ++o) {
+            const int co = co0 + o;
+            if (co < g.Cout) {
+                const int64_t idx = ((int64_t)f * g.Cout + co) * g.OH * g.OW + p;
+                out[idx] = apply_epi<EK>(epi, __fadd_rn(acc[o], bias ? __ldg(bias + co) : 0.f), idx);
+            }
+        }
+    });
 }
 
 // dense k x k convolution (groups == 1), one output per thread: the network's first layer (3 -> 16, 3x3 stride 2) and any geometry the GEMM
@@ -500,12 +437,13 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const float* __restric
             }
         }
     }
-    out[idx] = apply_epi(epi, __fadd_rn(acc, bias ? __ldg(bias + co) : 0.f), idx);
+    out[idx] = apply_epi<EK_GENERIC>(epi, __fadd_rn(acc, bias ? __ldg(bias + co) : 0.f), idx);
 }
 
 __global__ void __launch_bounds__(256) eltwise_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total, Epi epi) {
     const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx < total) out[idx] = apply_epi(epi, __ldg(in + idx), idx);
+    if (idx >= total) return;
+    epi_dispatch(epi.kind, [&](auto kind) { out[idx] = apply_epi<decltype(kind)::value>(epi, __ldg(in + idx), idx); });
 }
 
 // Permute order_type 3 on a 3-D blob: (c,h,w) -> (h,w,c)
@@ -942,7 +880,7 @@ int build_graph(sgs_detector* D) {
             set3(B[lout[i][0]], cout, oh, ow);
             const bool dw = L.type == "ConvolutionDepthWise";
             const int group = dw ? L.pi(7, 1) : 1;
-            if (dw && !(group == s.c && cout == s.c && dil == 1 && (k == 3 || k == 5) && (st == 1 || st == 2))) { set_error("sgs_detector_create: layer %s: grouped convolution other than depth-wise 3x3/5x5 with stride 1/2 is not supported", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
+            if (dw && !(group == s.c && cout == s.c && cout <= 65535 && dil == 1 && (k == 3 || k == 5) && (st == 1 || st == 2))) { set_error("sgs_detector_create: layer %s: grouped convolution other than depth-wise 3x3/5x5 with stride 1/2 is not supported", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
             const int64_t expect = dw ? (int64_t)cout * k * k : (int64_t)cout * s.c * k * k;
             if ((int64_t)L.weight.size() != expect) { set_error("sgs_detector_create: layer %s: weight size %zu, expected %lld", L.name.c_str(), L.weight.size(), (long long)expect); return SGS_ERR_INVALID; }
         } else if (is_eltwise(L)) {
@@ -1223,7 +1161,7 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
                                int32_t* d_ndyn_map, sgs_rect* d_dyn_rm, int32_t* d_ndyn_rm, uint8_t* d_have_dyn_rm, int max_boxes,
                                int32_t* d_status, void* stream) {
     if (D && (D->flags & 2)) { set_error("sgs_detector_detect_device: the handle is plan-only (flags bit 1)"); return SGS_ERR_UNSUPPORTED; }
-    if (!D || !d_rgb || nframes < 1 || nframes > D->max_frames || width < 2 || height < 2 || pitch < width * 3 || max_boxes < 0 ||
+    if (!D || !d_rgb || nframes < 1 || nframes > D->max_frames || nframes > 65535 || width < 2 || height < 2 || pitch < width * 3 || max_boxes < 0 ||
         ((d_dyn_map || d_dyn_rm) && max_boxes < 1)) {
         set_error("sgs_detector_detect_device: bad argument (nframes %d of max %d, %dx%d pitch %d)", nframes, D ? D->max_frames : 0, width, height, pitch);
         return SGS_ERR_INVALID;
@@ -1248,26 +1186,28 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
                 else if (op.g.Cout <= 32) conv1x1_mma_kernel<1, 8, 2, 4><<<g32, 256, 0, st>>>(SGS_MMA_ARGS);
                 else conv1x1_mma_kernel<2, 4, 2, 4><<<g64, 256, 0, st>>>(SGS_MMA_ARGS);
 #undef SGS_MMA_ARGS
-            } else if (op.g.Cout >= 96 && !(D->flags & 8)) conv1x1_wide_kernel<<<dim3((unsigned)((ncols + 127) / 128), (op.g.Cout + 127) / 128), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
-            else if (op.g.Cout <= 16) conv1x1_kernel<16, 256><<<dim3((unsigned)((ncols + 255) / 256), (op.g.Cout + 15) / 16), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
-            else if (op.g.Cout <= 32) conv1x1_kernel<32, 128><<<dim3((unsigned)((ncols + 127) / 128), (op.g.Cout + 31) / 32), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
-            else conv1x1_kernel<64, 64><<<dim3((unsigned)((ncols + 63) / 64), (op.g.Cout + 63) / 64), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, ncols, epi);
+            } else if (ncols < (1ll << 31) - 256) {
+                const int nc = (int)ncols;
+                if (op.g.Cout <= 16) conv1x1_kernel<16, 256><<<dim3((nc + 255) / 256, (op.g.Cout + 15) / 16), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
+                else if (op.g.Cout <= 32) conv1x1_kernel<32, 128><<<dim3((nc + 127) / 128, (op.g.Cout + 31) / 32), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
+                else conv1x1_kernel<64, 64><<<dim3((nc + 63) / 64, (op.g.Cout + 63) / 64), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
+            } else { set_error("sgs_detector_detect_device: batch too large for 32-bit column indices"); return SGS_ERR_UNSUPPORTED; }
             break;
         }
         case OP_CONV_DIRECT: {
             const int64_t total = (int64_t)F * op.g.Cout * op.g.OH * op.g.OW;
             const size_t wbytes = (size_t)op.g.Cin * op.g.k * op.g.k * kCot * sizeof(float);
-            if (wbytes <= 40 * 1024 && F <= 65535)
+            if (wbytes <= 40 * 1024)
                 conv_small_kernel<<<dim3(nblk((int64_t)op.g.OH * op.g.OW), (op.g.Cout + kCot - 1) / kCot, F), 256, wbytes, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
             else conv_direct_kernel<<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
             break;
         }
         case OP_DWCONV: {
-            const int64_t total = (int64_t)F * op.g.Cout * op.g.OH * ((op.g.OW + 3) / 4);
-            if (op.g.k == 3 && op.g.stride == 1) dwconv_kernel<3, 1><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
-            else if (op.g.k == 3) dwconv_kernel<3, 2><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
-            else if (op.g.stride == 1) dwconv_kernel<5, 1><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
-            else dwconv_kernel<5, 2><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
+            const dim3 grid(nblk((int64_t)op.g.OH * ((op.g.OW + 3) / 4)), op.g.Cout, F);      // Cout, F <= 65535 (checked at create / entry)
+            if (op.g.k == 3 && op.g.stride == 1) dwconv_kernel<3, 1><<<grid, 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
+            else if (op.g.k == 3) dwconv_kernel<3, 2><<<grid, 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
+            else if (op.g.stride == 1) dwconv_kernel<5, 1><<<grid, 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
+            else dwconv_kernel<5, 2><<<grid, 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
             break;
         }
         case OP_ELTWISE: {
