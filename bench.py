@@ -534,7 +534,7 @@ def main():
         if gflop:
             tf = DB * gflop / det_ms
             det_info['roofline'] = {'bound': 'tensor', 'achieved': tf, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': tf / pk['bf16_tflops'],
-                                    'note': '1.115 GFLOP per 300x300 inference (SURVEY 8d); all layers FP32 FMA on the CUDA cores (the 3xTF32 tensor-core GEMM behind flags bit 2 measured slower on this network); peak = measured dense bf16'}
+                                    'note': '1.115 GFLOP per 300x300 inference (SURVEY 8d); 1x1 convolutions = error-compensated TF32 on the tensor cores (three mma.sync per product, FP32-grade accuracy), the rest FP32 FMA on the CUDA cores; peak = measured dense bf16'}
         det.close()
         del d_rgb
     except Exception as ex:      # the detector is reported, never allowed to take the headline measurement down

@@ -538,9 +538,9 @@ typedef struct sgs_object2d {   /* Object2D, include/Detector2D.h:29-37 (name = 
 /* Detector2D::Detector2D(detection_confidence_threshold, dynamic_detection_confidence_threshold) + load_param/load_model.
  * max_frames = largest batch one sgs_detector_detect_device call may carry.  flags: bit 0 = diagnostic mode (every layer its own kernel,
  * every intermediate blob kept, readable with sgs_detector_blob); bit 1 = plan only (parse, shapes, kernel list and activation pool are
- * built, no device is touched; the handle serves sgs_detector_info / sgs_detector_describe only); bit 2 = run the 1x1 convolutions on the
- * tensor cores (error-compensated TF32, three mma.sync per product) instead of the FP32 FMA GEMM: same results to ~1e-6 relative, measured
- * slightly slower on B200 for this network. */
+ * built, no device is touched; the handle serves sgs_detector_info / sgs_detector_describe only); bit 2 = run the 1x1 convolutions as a plain
+ * FP32 FMA GEMM instead of the error-compensated TF32 tensor-core GEMM (three mma.sync per product; same results to ~1e-6 relative, the FMA path
+ * is ~8 % slower on B200). */
 SGS_API int sgs_detector_create(const char* param_path, const char* bin_path, int max_frames, float detection_confidence_threshold,
                                 float dynamic_detection_confidence_threshold, int flags, int device, sgs_detector** out);
 SGS_API void sgs_detector_destroy(sgs_detector* d);

@@ -5,8 +5,7 @@
 // The handle parses the ncnn text graph and weight blob itself, infers every blob shape for the fixed 3x300x300 input (Detector2D.h:70),
 // folds the constant sub-graphs (MemoryData scalars, PriorBox, their Concat) on the host, and turns the rest into a flat list of kernels:
 //   preprocess     : Mat::from_pixels_resize + substract_mean_normalize (Detector2D.cc:39-40), fixed-point bilinear (bit-exact with cv::resize)
-//   conv1x1        : 90 % of the MACs; register-tiled FP32 GEMM  W[Cout x Cin] * X[Cin x (frames*H*W)], bias + fused element-wise tail
-//                    (optional tensor-core variant, see below)
+//   conv1x1        : 90 % of the MACs; GEMM  W[Cout x Cin] * X[Cin x (frames*H*W)], bias + fused element-wise tail (tensor cores, see below)
 //   dwconv / conv  : depth-wise 3x3 / 5x5 and the first dense 3x3, one output per thread, fused tail
 //   eltwise        : whatever element-wise chain could not be attached to a producer
 //   permute / copy : CHW -> HWC of the head outputs and their Concat
@@ -14,10 +13,9 @@
 // Element-wise layers (BinaryOp with a constant / a tensor / the chain's own start value, Clip, ReLU) that follow a producer are applied in
 // the producer's epilogue in graph order, one rounding per op, so fused and unfused execution give identical bits.
 // Layout: every blob is [frames][c][h][w] FP32 (ncnn's c,h,w order per frame); activations live in a pool planned by liveness.
-// Arithmetic is FP32 FMA on the CUDA cores.  flags bit 2 runs the 1x1 convolutions on the tensor cores instead (error-compensated TF32: three
-// mma.sync per product, FP32-grade accuracy); measured on B200 it is 5 % slower than the FMA GEMM on this network (the layers are latency / memory
-// bound at 8-22 % tensor-pipe activity, and the operand split costs ALU issue slots), so it is not the default.  A tcgen05/TMEM GEMM fed by TMA is
-// the next step.
+// The 1x1 convolutions (90 % of the MACs) run on the tensor cores with FP32-grade accuracy: every operand is split into two TF32 values and each
+// product is three mma.sync (error-compensated TF32); flags bit 2 selects a plain FP32 FMA GEMM instead (8 % slower on B200 at batch 64, results equal
+// to ~1e-6 relative).  Everything else is FP32 FMA on the CUDA cores.  A tcgen05/TMEM GEMM fed by TMA is the next step.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -1178,7 +1176,7 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
         switch (op.kind) {
         case OP_CONV1X1: {
             const int HW = op.g.OH * op.g.OW; const int64_t ncols = (int64_t)F * HW;
-            if ((D->flags & 4) && ncols < (1ll << 31) - 256) {
+            if (!(D->flags & 4) && ncols < (1ll << 31) - 256) {
                 const int nc = (int)ncols;
                 const dim3 g16((nc + 255) / 256, (op.g.Cout + 15) / 16), g32((nc + 255) / 256, (op.g.Cout + 31) / 32), g64((nc + 127) / 128, (op.g.Cout + 63) / 64);
 #define SGS_MMA_ARGS bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi

@@ -459,7 +459,7 @@ def memcpy_d2h(dst_array, d_ptr):
 
 
 OBJ_DTYPE = np.dtype([('id', '<i4'), ('prob', '<f4'), ('x', '<f4'), ('y', '<f4'), ('w', '<f4'), ('h', '<f4')])   # sgs_object2d
-DET_DIAGNOSTIC, DET_PLAN_ONLY, DET_TENSOR_CORE_GEMM = 1, 2, 4
+DET_DIAGNOSTIC, DET_PLAN_ONLY, DET_FMA_GEMM = 1, 2, 4
 
 
 class Detector:

@@ -114,8 +114,8 @@ def test_detections_of_the_synthetic_graph(mini):
     rows_ref, post = DO.detect(layers, frames[0], 0.9, 0.01)
     assert len(post[1]) > 2
     _check_rows(small, 0, rows_ref, post, max_boxes=2)
-    # error-compensated TF32 tensor-core GEMM (flags bit 2) against the default FP32 FMA GEMM: same detections, values within FP32 noise
-    fma = B.Detector(pp, bp, max_frames=4, flags=B.DET_TENSOR_CORE_GEMM)
+    # plain FP32 FMA GEMM (flags bit 2) against the default error-compensated TF32 tensor-core GEMM: same detections, values within FP32 noise
+    fma = B.Detector(pp, bp, max_frames=4, flags=B.DET_FMA_GEMM)
     c = _run(fma, frames)
     assert np.array_equal(c['nrows'], a['nrows']) and np.array_equal(c['rows'][..., 0], a['rows'][..., 0])
     assert np.abs(c['rows'] - a['rows']).max() <= TOL
