@@ -245,10 +245,17 @@ typedef struct sgs_fuse_batch {           /* search half of Fuse(KeyFrame*, cons
                                              Rcw, tcw and Ow the caller decomposed from Scw (:988-992); no chi-square gates
                                              2: one direction of SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (:1106-1330): tcw = pose of the key
                                              frame that OWNS the points, xform2 = [sR21 | t21] (:1122-1124), kf_* = the other key frame; distance |p3Dc2|,
-                                             no viewing-angle test (mp_normal / ow unused); the caller applies <= TH_HIGH and the mutual check (:1314-1327) */
+                                             no viewing-angle test (mp_normal / ow unused); the caller applies <= TH_HIGH and the mutual check (:1314-1327)
+                                             3: SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (:292-405, loop closing): tcw / ow as in 1
+                                             (decomposed from Scw by the caller, :301-305), mp_valid = !isBad() && not in spAlreadyFound; the points are
+                                             matched IN ORDER -- a feature taken by an earlier point is skipped by later ones (:374) -- and bestDist <=
+                                             TH_LOW is applied here; best_idx[i] = the feature point i claimed (-1: none), results in kf_matched */
     const float* xform2;                  /* [F][12] (3x3 row major + 3), variant 2 only */
     int32_t* best_idx; int32_t* best_dist;/* out [F][mp_cap]: key-frame feature to fuse with (-1 / 256 when no candidate passed the gates); the caller
                                              applies bestDist <= TH_LOW and the Replace / AddObservation side effects in order */
+    int32_t* kf_matched;                  /* variant 3 only, in/out [F][kf_cap]: vpMatched -- >= 0 = occupied on entry; a feature matched by this call
+                                             receives the index of the map point that claimed it */
+    int32_t* nmatches;                    /* variant 3 only, out [F] (may be NULL): the function's return value */
 } sgs_fuse_batch;
 SGS_API int sgs_fuse_search_batch_device(const sgs_fuse_batch* args, int nframes, void* stream);
 

@@ -429,6 +429,20 @@ def fuse_search(kf, Tcw, Ow, mp_valid, mp_xyz, mp_normal, min_dist, max_dist, mp
     return bi, bd
 
 
+def search_by_projection_sim3(kf, Tcw, Ow, mp_valid, mp_xyz, mp_normal, min_dist, max_dist, mp_desc, th, kf_matched, log_scale_factor=None):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (src/ORBmatcher.cc:292-405) with Scw already decomposed into Tcw rows / Ow.
+    kf_matched: int32 per key-frame feature, >= 0 = occupied; returns (nmatches, updated copy: claimed features hold the claiming point's index)."""
+    f32 = np.float32
+    a = [np.ascontiguousarray(mp_valid, np.uint8), np.ascontiguousarray(mp_xyz, f32), np.ascontiguousarray(mp_normal, f32), np.ascontiguousarray(min_dist, f32),
+         np.ascontiguousarray(max_dist, f32), np.ascontiguousarray(mp_desc, np.uint8)]
+    if log_scale_factor is None:
+        log_scale_factor = float(f32(np.log(f32(1.2))))
+    T = np.ascontiguousarray(Tcw, f32); O_ = np.ascontiguousarray(Ow, f32)
+    m = np.ascontiguousarray(kf_matched, np.int32).copy()
+    nm = lib().sgo_search_by_projection_sim3(C.byref(kf.c), _p(T), _p(O_), len(a[0]), *[_p(x) for x in a], C.c_float(th), C.c_float(log_scale_factor), _p(m))
+    return nm, m
+
+
 def distinctive_descriptor(desc):
     """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307): index of the representative descriptor among desc [n,32]."""
     d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)

@@ -664,7 +664,7 @@ void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, in
     else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
 }
 
-constexpr int TH_HIGH = 100, HISTO_LENGTH = 30;  // src/ORBmatcher.cc:37-39
+constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;  // src/ORBmatcher.cc:37-39
 
 }  // namespace
 
@@ -1105,6 +1105,56 @@ SGO_API int sgo_fuse_search(const SgoFrame* kf, const float* Tcw, const float* O
         if (bestIdx >= 0) nfound++;
     }
     return nfound;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th),
+// src/ORBmatcher.cc:292-405 (loop closing, LoopClosing.cc:239 / :589).  Rcw, tcw (Tcw rows) and Ow are the values the caller decomposed from Scw
+// (:301-305) with the reference's own cv::Mat expressions.  mp_valid[i] = !isBad() && not in spAlreadyFound (:308-320).  kf_matched[idx] is
+// vpMatched: >= 0 means occupied on entry (any id); a feature claimed here receives the index i of the claiming point.  Points are visited in
+// order and a feature taken by an earlier point is skipped by later ones (:374-375), so the result depends on the order.
+SGO_API int sgo_search_by_projection_sim3(const SgoFrame* kf, const float* Tcw, const float* Ow, int nmp, const uint8_t* mp_valid, const float* mp_xyz,
+                                          const float* mp_normal, const float* min_dist, const float* max_dist, const uint8_t* mp_desc, float th,
+                                          float log_scale_factor, int32_t* kf_matched) {
+    FrameView F = to_view(kf); Grid g; build_grid(F, g);
+    float Rcw[9], tcw[3];
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) Rcw[3 * r + c] = Tcw[4 * r + c]; tcw[r] = Tcw[4 * r + 3]; }
+    std::vector<int> cand;
+    int nmatches = 0;
+    for (int i = 0; i < nmp; i++) {
+        if (!mp_valid[i]) continue;
+        const float* Xw = mp_xyz + 3 * i;
+        float p3Dc[3];
+        for (int r = 0; r < 3; r++) {   // Rcw*p3Dw+tcw: small-matrix gemm path, float accumulation (:329)
+            const float acc = Rcw[3 * r] * Xw[0] + Rcw[3 * r + 1] * Xw[1] + Rcw[3 * r + 2] * Xw[2];
+            p3Dc[r] = (float)((double)acc + (double)tcw[r]);
+        }
+        if (p3Dc[2] < 0.0f) continue;                                                     // :332
+        const float invz = 1 / p3Dc[2];                                                   // :336, float division
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float u = F.fx * x + F.cx, v = F.fy * y + F.cy;
+        if (!(u >= F.minX && u < F.maxX && v >= F.minY && v < F.maxY)) continue;          // KeyFrame::IsInImage (:344)
+        const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];   // Get{Max,Min}DistanceInvariance
+        const float PO[3] = {Xw[0] - Ow[0], Xw[1] - Ow[1], Xw[2] - Ow[2]};
+        const float dist = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+        if (dist < minDistance || dist > maxDistance) continue;                            // :353
+        const float* Pn = mp_normal + 3 * i;
+        if (((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2]) < 0.5 * dist) continue;   // :359
+        int nPredictedLevel = (int)std::ceil(std::log(max_dist[i] / dist) / log_scale_factor);               // MapPoint::PredictScale(dist, pKF)
+        if (nPredictedLevel < 0) nPredictedLevel = 0; else if (nPredictedLevel >= F.nlevels) nPredictedLevel = F.nlevels - 1;
+        const float radius = th * F.scaleFactors[nPredictedLevel];
+        features_in_area(F, g, u, v, radius, -1, -1, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            if (kf_matched[idx] >= 0) continue;                                             // :374
+            const int kpLevel = F.keysUn[idx].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const int d = descriptor_distance(mp_desc + 32 * (size_t)i, F.desc + 32 * (size_t)idx);
+            if (d < bestDist) { bestDist = d; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) { kf_matched[bestIdx] = i; nmatches++; }                   // :393-397
+    }
+    return nmatches;
 }
 
 // ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th), src/ORBmatcher.cc:45-129, with the

@@ -27,7 +27,7 @@ namespace sgs {
 constexpr int kMatchThreads = 256;
 constexpr int kGridCols = 64, kGridRows = 48;         // FRAME_GRID_COLS / ROWS, include/Frame.h:39-40
 constexpr int kGridCells = kGridCols * kGridRows;
-constexpr int kThHigh = 100, kHistoLen = 30;          // src/ORBmatcher.cc:37-39
+constexpr int kThHigh = 100, kThLow = 50, kHistoLen = 30;   // src/ORBmatcher.cc:37-39
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 
 struct FrameSmem {
@@ -608,10 +608,21 @@ __global__ void __launch_bounds__(kMatchThreads) fuse_search_kernel(const __grid
     const float w_inv = __fdiv_rn((float)kGridCols, __fsub_rn(A.cam.max_x, A.cam.min_x));
     const float h_inv = __fdiv_rn((float)kGridRows, __fsub_rn(A.cam.max_y, A.cam.min_y));
     const int gl = threadIdx.x & (kGroup - 1), ngroups = blockDim.x / kGroup;
+    // variant 3 (SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)): the reference visits the points in order and a feature claimed by an
+    // earlier point is invisible to later ones.  A wave of ngroups points searches in parallel against the claims made so far; one thread then walks
+    // the wave in order and accepts picks until it meets a pick that an earlier point of the same wave has just taken -- that point (and the ones
+    // behind it) search again.  A pick that is still free after the earlier claims is the same pick the sequential loop would make.
+    const bool claim = A.sim3_variant == 3;
+    int32_t* matched = claim ? A.kf_matched + (int64_t)f * A.kf_cap : nullptr;
+    __shared__ int s_pick[kMatchThreads / kGroup], s_pick_dist[kMatchThreads / kGroup], s_first, s_nm;
+    if (threadIdx.x == 0) s_nm = 0;
     for (int i0 = 0; i0 < nmp; i0 += ngroups) {
-        const int i = i0 + threadIdx.x / kGroup;
+      const int grp = threadIdx.x / kGroup, cnt = min(ngroups, nmp - i0);
+      int first = 0;
+      do {
+        const int i = i0 + grp;
         uint32_t best = kNoKey;
-        if (i < nmp && A.mp_valid[lo + i]) {
+        if (i < nmp && grp >= first && A.mp_valid[lo + i]) {
             const float* X = A.mp_xyz + 3 * (lo + i);
             float pc[3];
 #pragma unroll
@@ -630,7 +641,7 @@ __global__ void __launch_bounds__(kMatchThreads) fuse_search_kernel(const __grid
                 pc[0] = q[0]; pc[1] = q[1]; pc[2] = q[2];
             }
             bool ok = !(pc[2] < 0.0f);
-            const float invz = A.sim3_variant ? (float)__ddiv_rn(1.0, (double)pc[2]) : __fdiv_rn(1.f, pc[2]);
+            const float invz = (A.sim3_variant == 1 || A.sim3_variant == 2) ? (float)__ddiv_rn(1.0, (double)pc[2]) : __fdiv_rn(1.f, pc[2]);
             const float u = __fadd_rn(__fmul_rn(A.cam.fx, __fmul_rn(pc[0], invz)), A.cam.cx), v = __fadd_rn(__fmul_rn(A.cam.fy, __fmul_rn(pc[1], invz)), A.cam.cy);
             ok = ok && (u >= A.cam.min_x && u < A.cam.max_x && v >= A.cam.min_y && v < A.cam.max_y);        // KeyFrame::IsInImage
             const float ur = __fsub_rn(u, __fmul_rn(A.cam.bf, invz));
@@ -660,6 +671,7 @@ __global__ void __launch_bounds__(kMatchThreads) fuse_search_kernel(const __grid
                             if (!(fabsf(ex) < r && fabsf(ey) < r)) continue;          // GetFeaturesInArea: |kp - (u, v)| < r (same value as distx = kp - x)
                             const int o = s.oct[idx];
                             if (o < lvl - 1 || o > lvl) continue;
+                            if (claim && matched[idx] >= 0) continue;                  // if(vpMatched[idx]) continue;  (:374)
                             const float kr = s.ur[idx];
                             if (A.sim3_variant) {
                             } else if (kr >= 0.f) {
@@ -679,10 +691,37 @@ __global__ void __launch_bounds__(kMatchThreads) fuse_search_kernel(const __grid
         }
 #pragma unroll
         for (int o = kGroup >> 1; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-        if (gl == 0 && i < nmp) {
-            A.best_idx[lo + i] = best == kNoKey ? -1 : (int)s.order[best & 0xFFFFu];
-            A.best_dist[lo + i] = best == kNoKey ? 256 : (int)(best >> 16);
+        if (!claim) {
+            if (gl == 0 && i < nmp) {
+                A.best_idx[lo + i] = best == kNoKey ? -1 : (int)s.order[best & 0xFFFFu];
+                A.best_dist[lo + i] = best == kNoKey ? 256 : (int)(best >> 16);
+            }
+            break;
         }
+        if (gl == 0 && grp >= first && grp < cnt) {
+            s_pick[grp] = best == kNoKey ? -1 : (int)s.order[best & 0xFFFFu];
+            s_pick_dist[grp] = best == kNoKey ? 256 : (int)(best >> 16);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int k = first;
+            for (; k < cnt; ++k) {
+                const int idx = s_pick[k], d = s_pick_dist[k];
+                const bool take = idx >= 0 && d <= kThLow;                             // if(bestDist<=TH_LOW)  (:393)
+                if (take && matched[idx] >= 0) break;                                  // taken by an earlier point of this wave: search again
+                if (take) { matched[idx] = i0 + k; s_nm = s_nm + 1; }
+                A.best_idx[lo + i0 + k] = take ? idx : -1;
+                A.best_dist[lo + i0 + k] = d;
+            }
+            s_first = k;
+        }
+        __syncthreads();
+        first = s_first;
+      } while (first < cnt);
+    }
+    if (claim) {
+        __syncthreads();
+        if (threadIdx.x == 0 && A.nmatches) A.nmatches[f] = s_nm;
     }
 }
 

@@ -107,8 +107,10 @@ SGS_API int sgs_fuse_search_batch_device(const sgs_fuse_batch* a, int nframes, v
     A.mp_desc = a->mp_desc; A.mp_valid = a->mp_valid; A.mp_n = a->mp_n; A.mp_cap = a->mp_cap; A.th = a->th; A.log_sf = logf(a->cam.scale_factors[1]);
     for (int l = 0; l < kMaxLevels; ++l) A.inv_sigma2[l] = a->inv_level_sigma2[l];
     A.sim3_variant = a->sim3_variant; A.xform2 = a->xform2;
-    if (a->sim3_variant < 0 || a->sim3_variant > 2 || (a->sim3_variant == 2 && !a->xform2)) { set_error("sgs_fuse_search_batch_device: bad variant"); return SGS_ERR_INVALID; }
+    if (a->sim3_variant < 0 || a->sim3_variant > 3 || (a->sim3_variant == 2 && !a->xform2) || (a->sim3_variant == 3 && !a->kf_matched)) {
+        set_error("sgs_fuse_search_batch_device: bad variant"); return SGS_ERR_INVALID; }
     A.best_idx = a->best_idx; A.best_dist = a->best_dist;
+    A.kf_matched = a->kf_matched; A.nmatches = a->nmatches;
     return launch_fuse_search(A, nframes, (cudaStream_t)stream);
 }
 

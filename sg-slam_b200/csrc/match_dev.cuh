@@ -66,7 +66,9 @@ struct FuseArgs {                 // search half of ORBmatcher::Fuse(KeyFrame*, 
     const float* xform2;          // [nframes][12]: sR21 (3x3 row major) + t21, variant 2 only
     int32_t sim3_variant;         // 2: one direction of SearchBySim3 (:1106-1330): second transform xform2, distance |p3Dc2|, no viewing-angle test;
                                   // 1: Fuse(KeyFrame*, Scw, ...) (:982-1104): pose already decomposed by the caller, invz = 1.0 / z in double, no chi-square gates
+                                  // 3: SearchByProjection(KeyFrame*, Scw, ...) (:292-405): as 1 with invz = 1 / z in float; occupied features are skipped and claimed in point order
     int32_t* best_idx; int32_t* best_dist;
+    int32_t* kf_matched; int32_t* nmatches;   // variant 3 (SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th), :292-405): vpMatched in/out [nframes][kf_cap], matches per frame
 };
 
 int launch_match_lastframe(const LastFrameArgs& A, int nframes, cudaStream_t st);

@@ -62,7 +62,7 @@ class FuseBatch(C.Structure):
     _fields_ = [('cam', Camera), ('kf_kps', C.c_void_p), ('kf_desc', C.c_void_p), ('kf_uright', C.c_void_p), ('kf_n', C.c_void_p), ('kf_cap', C.c_int32),
                 ('tcw', C.c_void_p), ('ow', C.c_void_p), ('mp_xyz', C.c_void_p), ('mp_normal', C.c_void_p), ('mp_min_dist', C.c_void_p), ('mp_max_dist', C.c_void_p),
                 ('mp_desc', C.c_void_p), ('mp_valid', C.c_void_p), ('mp_n', C.c_void_p), ('mp_cap', C.c_int32), ('th', C.c_float), ('inv_level_sigma2', C.c_float * 16),
-                ('sim3_variant', C.c_int32), ('xform2', C.c_void_p), ('best_idx', C.c_void_p), ('best_dist', C.c_void_p)]
+                ('sim3_variant', C.c_int32), ('xform2', C.c_void_p), ('best_idx', C.c_void_p), ('best_dist', C.c_void_p), ('kf_matched', C.c_void_p), ('nmatches', C.c_void_p)]
 
 
 class BowBatch(C.Structure):

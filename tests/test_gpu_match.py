@@ -240,6 +240,53 @@ def test_fuse_search(seed, ncur, nmp, th, sim3):
     assert np.array_equal(bi.cpu().numpy()[0, :nmp], bi_o) and np.array_equal(bd.cpu().numpy()[0, :nmp], bd_o)
 
 
+@pytest.mark.parametrize('seed,ncur,nmp,th', [(11, 600, 900, 10), (12, 300, 1500, 10), (13, 800, 800, 4), (14, 1000, 3000, 10)])
+def test_search_by_projection_sim3(seed, ncur, nmp, th):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (src/ORBmatcher.cc:292-405): ordered claims, two key frames per call."""
+    import ctypes as C
+    import torch
+    from test_match_sim3 import sim3_inputs
+    inv_s2 = None
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    kcap, mcap = ncur + 5, nmp + 3
+    pad = lambda a, cap: np.concatenate([a, np.zeros((cap - len(a),) + a.shape[1:], a.dtype)])
+    per = []
+    for k in range(2):
+        s, Ow, nrm, matched = sim3_inputs(seed + 100 * k, ncur, nmp)
+        cam = s['cam']
+        fo = O.FrameArrays(s['kps'], s['uright'], s['desc'], 640, 480, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], s['sf'])
+        nm_o, m_o = O.search_by_projection_sim3(fo, s['Tcw_cur'], Ow, s['kf_valid'], s['last_xyz'], nrm, s['min_dist'], s['max_dist'], s['last_desc'], float(th), matched)
+        assert nm_o > 30
+        per.append((s, Ow, nrm, matched, nm_o, m_o))
+    st = lambda f: np.stack([f(p) for p in per])
+    t_ = dict(kps=dev(st(lambda p: pad(p[0]['kps'], kcap)).view(np.uint8).reshape(-1)), kd=dev(st(lambda p: pad(p[0]['desc'], kcap))),
+              ur=dev(st(lambda p: pad(p[0]['uright'].astype(np.float32), kcap))), kn=dev(np.array([ncur, ncur], np.int32)),
+              T=dev(st(lambda p: p[0]['Tcw_cur'].astype(np.float32).reshape(16))), ow=dev(st(lambda p: p[1])), xyz=dev(st(lambda p: pad(p[0]['last_xyz'], mcap))),
+              nrm=dev(st(lambda p: pad(p[2], mcap))), mn=dev(st(lambda p: pad(p[0]['min_dist'], mcap))), mx=dev(st(lambda p: pad(p[0]['max_dist'], mcap))),
+              md=dev(st(lambda p: pad(p[0]['last_desc'], mcap))), mv=dev(st(lambda p: pad(p[0]['kf_valid'], mcap))), mn_=dev(np.array([nmp, nmp], np.int32)),
+              matched=dev(st(lambda p: np.concatenate([p[3], np.full(kcap - ncur, -1, np.int32)]))))
+    bi = torch.zeros((2, mcap), dtype=torch.int32, device='cuda'); bd = torch.zeros((2, mcap), dtype=torch.int32, device='cuda'); nm = torch.zeros(2, dtype=torch.int32, device='cuda')
+    a = B.FuseBatch()
+    a.cam = B.make_camera(640, 480, per[0][0]['cam'], per[0][0]['sf'])
+    a.kf_kps, a.kf_desc, a.kf_uright, a.kf_n, a.kf_cap = t_['kps'].data_ptr(), t_['kd'].data_ptr(), t_['ur'].data_ptr(), t_['kn'].data_ptr(), kcap
+    a.tcw, a.ow, a.mp_xyz, a.mp_normal, a.mp_min_dist, a.mp_max_dist = t_['T'].data_ptr(), t_['ow'].data_ptr(), t_['xyz'].data_ptr(), t_['nrm'].data_ptr(), t_['mn'].data_ptr(), t_['mx'].data_ptr()
+    a.mp_desc, a.mp_valid, a.mp_n, a.mp_cap, a.th = t_['md'].data_ptr(), t_['mv'].data_ptr(), t_['mn_'].data_ptr(), mcap, float(th)
+    a.sim3_variant = 3
+    a.best_idx, a.best_dist, a.kf_matched, a.nmatches = bi.data_ptr(), bd.data_ptr(), t_['matched'].data_ptr(), nm.data_ptr()
+    B.check(B.lib().sgs_fuse_search_batch_device(C.byref(a), 2, C.c_void_p(0)))
+    torch.cuda.synchronize()
+    got = t_['matched'].cpu().numpy(); bi_h = bi.cpu().numpy()
+    for k, (s, Ow, nrm, matched, nm_o, m_o) in enumerate(per):
+        assert int(nm[k].item()) == nm_o
+        assert np.array_equal(got[k, :ncur], m_o) and (got[k, ncur:] == -1).all()
+        claimed = np.nonzero((matched < 0) & (m_o >= 0))[0]
+        assert np.array_equal(np.sort(bi_h[k, m_o[claimed]]), np.sort(claimed))             # best_idx[i] = the feature point i claimed
+        assert (bi_h[k, :nmp] >= 0).sum() == nm_o
+    a.kf_matched = None
+    with pytest.raises(B.SgsError):
+        B.check(B.lib().sgs_fuse_search_batch_device(C.byref(a), 2, C.c_void_p(0)))
+
+
 def test_distinctive_descriptor_batch():
     """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307): median-of-distances representative, first minimum wins."""
     import ctypes as C
