@@ -1,5 +1,5 @@
 """Times the detector (sgs_detector_detect_device) on synthetic RGB frames resident in HBM: frames/s per batch size, CUDA events on the launching
-stream.  Usage: python tools/bench_detector.py [batch ...]   (model: oracle/_ref/ncnn_model when staged, else the synthetic graph of the tests)"""
+stream.  Usage: python tools/bench_detector.py [--size WxH] [batch ...]   (model: oracle/_ref/ncnn_model when staged, else the synthetic graph of the tests)"""
 import os
 import sys
 import tempfile
@@ -19,12 +19,15 @@ REAL = os.path.join(ROOT, 'oracle', '_ref', 'ncnn_model', 'mobilenetv3_ssdlite_v
 
 def main():
     flags = int(os.environ.get('SGS_DET_FLAGS', '0'))
-    batches = [int(a) for a in sys.argv[1:]] or [1, 8, 64, 256]
+    argv = sys.argv[1:]
+    W, H = 640, 480
+    if argv and argv[0] == '--size':
+        W, H = [int(x) for x in argv[1].split('x')]; argv = argv[2:]
+    batches = [int(a) for a in argv] or [1, 8, 64, 256]
     if os.path.exists(REAL + '.param'):
         pp, bp, name = REAL + '.param', REAL + '.bin', 'mobilenetv3_ssdlite_voc'
     else:
         pp, bp = DM.write_mini_model(tempfile.mkdtemp(), 0); name = 'synthetic-mini'
-    H, W = 480, 640
     base = np.stack([DM.synthetic_rgb(H, W, s) for s in range(8)])
     for F in batches:
         det = B.Detector(pp, bp, max_frames=F, flags=flags)
@@ -41,7 +44,7 @@ def main():
             run()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print('%s batch %4d: %8.3f ms/batch  %9.1f frames/s  %6.2f TFLOP/s (1.115 GFLOP/frame)  kernels/batch %d' % (name, F, ms, F / ms * 1e3, F * 1.115 / ms, det.num_kernels), flush=True)
+        print('%s %dx%d batch %4d: %8.3f ms/batch  %9.1f frames/s  %6.2f TFLOP/s (1.115 GFLOP/frame)  kernels/batch %d' % (name, W, H, F, ms, F / ms * 1e3, F * 1.115 / ms, det.num_kernels), flush=True)
         det.close()
 
 
