@@ -258,6 +258,12 @@ typedef struct sgs_fuse_batch {           /* search half of Fuse(KeyFrame*, cons
     int32_t* nmatches;                    /* variant 3 only, out [F] (may be NULL): the function's return value */
 } sgs_fuse_batch;
 SGS_API int sgs_fuse_search_batch_device(const sgs_fuse_batch* args, int nframes, void* stream);
+/* One key frame from host memory (same fields and variants as sgs_fuse_batch; kf = the key frame's mvKeysUn / mvuRight / mDescriptors view).
+ * kf_matched_inout [kf->n] and nmatches are used by variant 3 only; xform2 [12] by variant 2 only; inv_level_sigma2 [nlevels] by variant 0 only. */
+SGS_API int sgs_fuse_search(const sgs_frame_view* kf, const float* tcw, const float* ow, int nmp, const uint8_t* mp_valid, const float* mp_xyz,
+                            const float* mp_normal, const float* mp_min_dist, const float* mp_max_dist, const uint8_t* mp_desc, float th,
+                            const float* inv_level_sigma2, int sim3_variant, const float* xform2, int32_t* best_idx, int32_t* best_dist,
+                            int32_t* kf_matched_inout, int* nmatches, int device);
 
 typedef struct sgs_localmap_batch {       /* SearchByProjection(Frame&, vector<MapPoint*>&, th), src/ORBmatcher.cc:45 */
     sgs_camera cam;

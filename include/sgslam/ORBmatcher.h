@@ -12,8 +12,13 @@
 //                                              DescriptorDistance                                      src/ORBmatcher.cc:1649-1665
 //                                              SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist)  src/ORBmatcher.cc:1474-1601
 //                                              SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)      src/ORBmatcher.cc:159-290
-// The mapping / loop-closing variants (SearchByBoW, Fuse, SearchBySim3, ...) are SURVEY section 8(f) "next" rows.
+// Mapping / loop closing:                      Fuse(KeyFrame*, vpMapPoints, th)                       src/ORBmatcher.cc:829-980
+//                                              Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)     src/ORBmatcher.cc:982-1104
+//                                              SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)  src/ORBmatcher.cc:292-405
+// SearchByBoW(KF, KF), SearchForTriangulation and SearchBySim3 have device entry points (sgs_match_bow_batch_device, sgs_fuse_search_batch_device) but no mirror yet.
 #pragma once
+#include <cmath>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -155,6 +160,88 @@ public:
     }
 
     static const int TH_LOW = 50;      // src/ORBmatcher.cc:37-39
+    // ---- mapping / loop-closing variants.  The search runs on the GPU; the reference's map side effects (Replace, AddObservation, AddMapPoint,
+    // vpReplacePoint / vpMatched writes) are applied afterwards on the host, in the reference's order and with its own checks re-evaluated at that
+    // moment (the search of one point reads only immutable key-frame data and that point's own fields, so it does not depend on them).
+    // MapPoint keeps mfMinDistance / mfMaxDistance private: they are recovered from Get{Min,Max}DistanceInvariance() (0.8 f / 1.2 f factors).
+
+    // Project MapPoints into KeyFrame and search for duplicated MapPoints (LocalMapping::SearchInNeighbors, src/LocalMapping.cc:215).  src/ORBmatcher.cc:829-980
+    template <class KeyFrameT, class MapPointT>
+    int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, const float th = 3.0) {
+        const cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation(), Ow = pKF->GetCameraCenter();
+        float T[16] = {0}, O[3];
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T[4 * r + c] = Rcw.template at<float>(r, c); T[4 * r + 3] = tcw.template at<float>(r, 0); O[r] = Ow.template at<float>(r, 0); }
+        T[15] = 1.f;
+        std::vector<int32_t> bi, bd;
+        search_kf(pKF, T, O, vpMapPoints, [&](MapPointT* p) { return p && !p->isBad() && !p->IsInKeyFrame(pKF); }, th, 0, bi, bd, nullptr);
+        int nFused = 0;
+        for (size_t i = 0; i < vpMapPoints.size(); ++i) {
+            MapPointT* pMP = vpMapPoints[i];
+            if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF) || bd[i] > TH_LOW) continue;        // :848-853 re-evaluated in order, :963
+            MapPointT* pMPinKF = pKF->GetMapPoint(bi[i]);
+            if (pMPinKF) {
+                if (!pMPinKF->isBad()) {
+                    if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                    else pMPinKF->Replace(pMP);
+                }
+            } else {
+                pMP->AddObservation(pKF, bi[i]);
+                pKF->AddMapPoint(pMP, bi[i]);
+            }
+            nFused++;
+        }
+        return nFused;
+    }
+
+    // Project MapPoints into KeyFrame using a given Sim3 and search for duplicated MapPoints (LoopClosing::SearchAndFuse, src/LoopClosing.cc:589).  :982-1104
+    // Rcw / tcw / Ow are decomposed from Scw with the expressions of :988-992 evaluated by the caller's own cv::Mat (decompose_scw below).
+    template <class KeyFrameT, class MapPointT>
+    int Fuse(KeyFrameT* pKF, const cv::Mat& Scw, const std::vector<MapPointT*>& vpPoints, float th, std::vector<MapPointT*>& vpReplacePoint) {
+        float T[16], O[3];
+        decompose_scw(Scw, T, O);
+        return Fuse(pKF, T, O, vpPoints, th, vpReplacePoint);
+    }
+    template <class KeyFrameT, class MapPointT>
+    int Fuse(KeyFrameT* pKF, const float T[16], const float O[3], const std::vector<MapPointT*>& vpPoints, float th, std::vector<MapPointT*>& vpReplacePoint) {
+        const auto spAlreadyFound = pKF->GetMapPoints();
+        std::vector<int32_t> bi, bd;
+        search_kf(pKF, T, O, vpPoints, [&](MapPointT* p) { return !p->isBad() && !spAlreadyFound.count(p); }, th, 1, bi, bd, nullptr);
+        int nFused = 0;
+        for (size_t i = 0; i < vpPoints.size(); ++i) {
+            MapPointT* pMP = vpPoints[i];
+            if (pMP->isBad() || spAlreadyFound.count(pMP) || bd[i] > TH_LOW) continue;
+            MapPointT* pMPinKF = pKF->GetMapPoint(bi[i]);
+            if (pMPinKF) {
+                if (!pMPinKF->isBad()) vpReplacePoint[i] = pMPinKF;
+            } else {
+                pMP->AddObservation(pKF, bi[i]);
+                pKF->AddMapPoint(pMP, bi[i]);
+            }
+            nFused++;
+        }
+        return nFused;
+    }
+
+    // Project MapPoints using a Similarity Transformation and search matches (LoopClosing::ComputeSim3 / DetectLoop, src/LoopClosing.cc:239,:589).  :292-405
+    // The points are matched in order: a key-frame feature taken by an earlier point is not offered to later ones.
+    template <class KeyFrameT, class MapPointT>
+    int SearchByProjection(KeyFrameT* pKF, const cv::Mat& Scw, const std::vector<MapPointT*>& vpPoints, std::vector<MapPointT*>& vpMatched, int th) {
+        float T[16], O[3];
+        decompose_scw(Scw, T, O);
+        return SearchByProjection(pKF, T, O, vpPoints, vpMatched, th);
+    }
+    template <class KeyFrameT, class MapPointT>
+    int SearchByProjection(KeyFrameT* pKF, const float T[16], const float O[3], const std::vector<MapPointT*>& vpPoints, std::vector<MapPointT*>& vpMatched, int th) {
+        std::vector<int32_t> occupied(vpMatched.size(), -1);
+        for (size_t j = 0; j < vpMatched.size(); ++j) if (vpMatched[j]) occupied[j] = (int32_t)vpPoints.size();       // any id >= 0: taken on entry
+        auto found = [&](MapPointT* p) { for (MapPointT* q : vpMatched) if (q == p) return true; return false; };     // spAlreadyFound (:308-309)
+        std::vector<int32_t> bi, bd;
+        const int nmatches = search_kf(pKF, T, O, vpPoints, [&](MapPointT* p) { return !p->isBad() && !found(p); }, (float)th, 3, bi, bd, &occupied);
+        for (size_t j = 0; j < vpMatched.size(); ++j)
+            if (occupied[j] >= 0 && occupied[j] < (int32_t)vpPoints.size()) vpMatched[j] = vpPoints[occupied[j]];
+        return nmatches;
+    }
+
     static const int TH_HIGH = 100;
     static const int HISTO_LENGTH = 30;
 
@@ -171,6 +258,57 @@ protected:
         v.nlevels = (int)scale.size(); v.scale_factors = scale.data();
         return v;
     }
+    // sRcw = Scw(0:3,0:3); scw = sqrt(sRcw.row(0).dot(sRcw.row(0))); Rcw = sRcw/scw; tcw = Scw(0:3,3)/scw; Ow = -Rcw.t()*tcw   (src/ORBmatcher.cc:301-305, :988-992)
+    // with scalar float operations in OpenCV's evaluation order: Mat::dot accumulates in double; Mat/scalar is convertTo(alpha = 1/s), which for CV_32F
+    // multiplies by the FLOAT value of the reciprocal; the transposed product accumulates in double (pinned with cv2.gemm).  The
+    // Mat/scalar rule is restated from OpenCV's sources and could not be checked here (cv2 has no MatExpr): inside the reference tree prefer the
+    // overloads below that take Rcw|tcw (4x4 row major) and Ow computed by the reference's own three lines.
+    static void decompose_scw(const cv::Mat& Scw, float T[16], float O[3]) {
+        double dot = 0;
+        for (int c = 0; c < 3; ++c) dot += (double)Scw.at<float>(0, c) * (double)Scw.at<float>(0, c);
+        const float scw = std::sqrt((float)dot);
+        const float inv = (float)(1.0 / (double)scw);
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T[4 * r + c] = Scw.at<float>(r, c) * inv; T[4 * r + 3] = Scw.at<float>(r, 3) * inv; }
+        T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
+        for (int r = 0; r < 3; ++r) {
+            double acc = 0;
+            for (int k = 0; k < 3; ++k) acc += (double)T[4 * k + r] * (double)T[4 * k + 3];
+            O[r] = (float)(-acc);
+        }
+    }
+
+    // Flattens the key frame and the candidate points and runs sgs_fuse_search.  valid(p) = the reference's per-point skip test.
+    template <class KeyFrameT, class MapPointT, class ValidF>
+    int search_kf(KeyFrameT* pKF, const float T[16], const float O[3], const std::vector<MapPointT*>& pts, ValidF valid, float th, int variant,
+                  std::vector<int32_t>& bi, std::vector<int32_t>& bd, std::vector<int32_t>* kf_matched) {
+        const int nmp = (int)pts.size();
+        std::vector<float> scale(pKF->mvScaleFactors.begin(), pKF->mvScaleFactors.end()), inv_s2(pKF->mvInvLevelSigma2.begin(), pKF->mvInvLevelSigma2.end());
+        sgs_frame_view v;
+        v.n = pKF->N;
+        v.keys_un = reinterpret_cast<const sgs_keypoint*>(pKF->mvKeysUn.data());
+        v.u_right = pKF->mvuRight.data();
+        v.desc = pKF->mDescriptors.template ptr<uint8_t>();
+        v.min_x = pKF->mnMinX; v.min_y = pKF->mnMinY; v.max_x = pKF->mnMaxX; v.max_y = pKF->mnMaxY;
+        v.fx = pKF->fx; v.fy = pKF->fy; v.cx = pKF->cx; v.cy = pKF->cy; v.bf = pKF->mbf;
+        v.nlevels = (int)scale.size(); v.scale_factors = scale.data();
+        std::vector<uint8_t> ok(nmp, 0), desc((size_t)nmp * 32, 0);
+        std::vector<float> xyz((size_t)nmp * 3, 0.f), nrm((size_t)nmp * 3, 0.f), mn(nmp, 0.f), mx(nmp, 0.f);
+        for (int i = 0; i < nmp; ++i) {
+            MapPointT* p = pts[i];
+            if (!valid(p)) continue;
+            ok[i] = 1;
+            const cv::Mat P = p->GetWorldPos(), Nn = p->GetNormal(), d = p->GetDescriptor();
+            for (int k = 0; k < 3; ++k) { xyz[3 * (size_t)i + k] = P.template at<float>(k, 0); nrm[3 * (size_t)i + k] = Nn.template at<float>(k, 0); }
+            std::memcpy(&desc[(size_t)i * 32], d.template ptr<uint8_t>(), 32);
+            mn[i] = p->GetMinDistanceInvariance() / 0.8f; mx[i] = p->GetMaxDistanceInvariance() / 1.2f;
+        }
+        bi.assign(nmp, -1); bd.assign(nmp, 256);
+        int nmatches = 0;
+        check(sgs_fuse_search(&v, T, O, nmp, ok.data(), xyz.data(), nrm.data(), mn.data(), mx.data(), desc.data(), th, inv_s2.data(), variant, nullptr, bi.data(),
+                              bd.data(), kf_matched ? kf_matched->data() : nullptr, &nmatches, device_));
+        return nmatches;
+    }
+
     static void check(int status) {
         if (status != SGS_OK) throw std::runtime_error(std::string("sgs: ") + sgs_last_error());
     }

@@ -236,6 +236,50 @@ SGS_API int sgs_match_project_keyframe(const sgs_frame_view* cur, const float* t
     return SGS_OK;
 }
 
+SGS_API int sgs_fuse_search(const sgs_frame_view* kf, const float* tcw, const float* ow, int nmp, const uint8_t* mp_valid, const float* mp_xyz,
+                            const float* mp_normal, const float* mp_min_dist, const float* mp_max_dist, const uint8_t* mp_desc, float th,
+                            const float* inv_level_sigma2, int sim3_variant, const float* xform2, int32_t* best_idx, int32_t* best_dist,
+                            int32_t* kf_matched_inout, int* nmatches, int device) {
+    if (!kf || !tcw || !ow || nmp < 0 || kf->n < 0 || !best_idx || !best_dist) { set_error("sgs_fuse_search: bad argument"); return SGS_ERR_INVALID; }
+    if (nmatches) *nmatches = 0;
+    for (int i = 0; i < nmp; ++i) { best_idx[i] = -1; best_dist[i] = 256; }
+    if (nmp == 0 || kf->n == 0) return SGS_OK;
+    if (!mp_valid || !mp_xyz || !mp_normal || !mp_min_dist || !mp_max_dist || !mp_desc || !kf->keys_un || !kf->u_right || !kf->desc ||
+        (sim3_variant == 0 && !inv_level_sigma2) || (sim3_variant == 3 && !kf_matched_inout)) { set_error("sgs_fuse_search: NULL array"); return SGS_ERR_INVALID; }
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    const int n = kf->n;
+    const int32_t n32 = n, nmp32 = nmp;
+    DevBuf kps, desc, ur, kn, tc, o, xyz, nrm, mn, mx, md, mv, mpn, xf, bi, bd, km, nm;
+    SGS_CUDA_TRY(kps.upload(kf->keys_un, sizeof(sgs_keypoint) * n)); SGS_CUDA_TRY(desc.upload(kf->desc, (size_t)32 * n)); SGS_CUDA_TRY(ur.upload(kf->u_right, 4 * (size_t)n));
+    SGS_CUDA_TRY(kn.upload(&n32, 4)); SGS_CUDA_TRY(tc.upload(tcw, 64)); SGS_CUDA_TRY(o.upload(ow, 12));
+    SGS_CUDA_TRY(xyz.upload(mp_xyz, 12 * (size_t)nmp)); SGS_CUDA_TRY(nrm.upload(mp_normal, 12 * (size_t)nmp)); SGS_CUDA_TRY(mn.upload(mp_min_dist, 4 * (size_t)nmp));
+    SGS_CUDA_TRY(mx.upload(mp_max_dist, 4 * (size_t)nmp)); SGS_CUDA_TRY(md.upload(mp_desc, 32 * (size_t)nmp)); SGS_CUDA_TRY(mv.upload(mp_valid, (size_t)nmp));
+    SGS_CUDA_TRY(mpn.upload(&nmp32, 4)); SGS_CUDA_TRY(bi.alloc(4 * (size_t)nmp)); SGS_CUDA_TRY(bd.alloc(4 * (size_t)nmp)); SGS_CUDA_TRY(nm.alloc(4));
+    if (xform2) SGS_CUDA_TRY(xf.upload(xform2, 48));
+    if (kf_matched_inout) SGS_CUDA_TRY(km.upload(kf_matched_inout, 4 * (size_t)n));
+    sgs_fuse_batch b;
+    std::memset(&b, 0, sizeof b);
+    b.cam = view_cam(kf);
+    b.kf_kps = kps.as<sgs_keypoint>(); b.kf_desc = desc.as<uint8_t>(); b.kf_uright = ur.as<float>(); b.kf_n = kn.as<int32_t>(); b.kf_cap = n;
+    b.tcw = tc.as<float>(); b.ow = o.as<float>(); b.mp_xyz = xyz.as<float>(); b.mp_normal = nrm.as<float>(); b.mp_min_dist = mn.as<float>(); b.mp_max_dist = mx.as<float>();
+    b.mp_desc = md.as<uint8_t>(); b.mp_valid = mv.as<uint8_t>(); b.mp_n = mpn.as<int32_t>(); b.mp_cap = nmp; b.th = th;
+    for (int l = 0; l < 16; ++l) b.inv_level_sigma2[l] = inv_level_sigma2 && l < kf->nlevels ? inv_level_sigma2[l] : 0.f;
+    b.sim3_variant = sim3_variant; b.xform2 = xform2 ? xf.as<float>() : nullptr;
+    b.best_idx = bi.as<int32_t>(); b.best_dist = bd.as<int32_t>(); b.kf_matched = kf_matched_inout ? km.as<int32_t>() : nullptr; b.nmatches = nm.as<int32_t>();
+    const int rc = sgs_fuse_search_batch_device(&b, 1, nullptr);
+    if (rc != SGS_OK) return rc;
+    SGS_CUDA_TRY(cudaDeviceSynchronize());
+    SGS_CUDA_TRY(cudaMemcpy(best_idx, bi.p, 4 * (size_t)nmp, cudaMemcpyDeviceToHost));
+    SGS_CUDA_TRY(cudaMemcpy(best_dist, bd.p, 4 * (size_t)nmp, cudaMemcpyDeviceToHost));
+    if (sim3_variant == 3) {
+        SGS_CUDA_TRY(cudaMemcpy(kf_matched_inout, km.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+        int32_t nm_h = 0;
+        SGS_CUDA_TRY(cudaMemcpy(&nm_h, nm.p, 4, cudaMemcpyDeviceToHost));
+        if (nmatches) *nmatches = nm_h;
+    }
+    return SGS_OK;
+}
+
 SGS_API int sgs_match_project_localmap(const sgs_frame_view* f, int nmp, const uint8_t* mp_inview, const float* proj_x, const float* proj_y,
                                        const float* proj_xr, const int32_t* level, const float* view_cos, const uint8_t* mp_desc,
                                        const uint8_t* mp_obs, float th, float nnratio, int32_t id_base, int32_t* f_mp_inout,

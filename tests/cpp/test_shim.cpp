@@ -11,6 +11,8 @@
 #include "sgslam/FrameGeometry.h"
 #include "sgslam/Optimizer.h"
 #include "sgslam/Detector2D.h"
+#include <set>
+
 #include "sgslam/ORBextractor.h"
 #include "sgslam/ORBmatcher.h"
 
@@ -28,6 +30,25 @@ struct MapPoint {
     float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
     int Observations() { return nobs; }
     bool isBad() { return bad; }
+    // mapping-side surface used by Fuse / SearchByProjection(KeyFrame*, Scw, ...): observations as an opaque key-frame set, Replace marks the point bad
+    std::set<const void*> obs; MapPoint* replaced_by = nullptr;
+    template <class KF> bool IsInKeyFrame(KF* kf) { return obs.count(kf) != 0; }
+    template <class KF> void AddObservation(KF* kf, size_t) { if (obs.insert(kf).second) ++nobs; }
+    void Replace(MapPoint* other) { bad = true; replaced_by = other; }
+};
+struct KeyFrame {
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<float> mvuRight, mvScaleFactors, mvInvLevelSigma2;
+    cv::Mat mDescriptors, R, t, O;
+    float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mnMinX = 0, mnMinY = 0, mnMaxX = 640, mnMaxY = 480;
+    std::vector<MapPoint*> mps;
+    cv::Mat GetRotation() { return R; }
+    cv::Mat GetTranslation() { return t; }
+    cv::Mat GetCameraCenter() { return O; }
+    MapPoint* GetMapPoint(size_t idx) { return mps[idx]; }
+    void AddMapPoint(MapPoint* p, size_t idx) { mps[idx] = p; }
+    std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> r; for (MapPoint* p : mps) if (p && !p->isBad()) r.insert(p); return r; }
 };
 struct Frame {
     int N = 0;
@@ -196,7 +217,68 @@ int main(int argc, char** argv) {
         det.detect(im3);                                                    // the view list accumulates until draw_objects clears it
         if ((int)det.mvObjects2D_to_View.size() != 2 * dn || (int)det.mvPotentialDynamicBorderForMapping.size() != npers) return fail("Detector2D: second call");
     }
-    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges, %d detections (%d persons)\n", nkp, nm, kept,
-                nd, nlk, nview, nfr, pin, npo, ndet, npers);
+    // 8. SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) and 9. Fuse(KeyFrame*, vpMapPoints, th) on one key frame / candidate list
+    int nsim3 = -1, nfused = -1;
+    if (argc >= 4) {
+        int32_t kh[3]; f.read(reinterpret_cast<char*>(kh), sizeof kh);
+        const int nk = kh[0], nmp = kh[1], ith = kh[2];
+        KeyFrame kf; kf.N = nk;
+        kf.mvKeysUn = rd<cv::KeyPoint>(f, nk); kf.mvuRight = rd<float>(f, nk);
+        std::vector<uint8_t> kd = rd<uint8_t>(f, (size_t)nk * 32);
+        kf.mDescriptors = cv::Mat(nk, 32, CV_8U, kd.data(), 32);
+        kf.mvScaleFactors = rd<float>(f, 8); kf.mvInvLevelSigma2 = rd<float>(f, 8);
+        std::vector<float> cam5 = rd<float>(f, 5), T = rd<float>(f, 16), Ow = rd<float>(f, 3);
+        kf.fx = cam5[0]; kf.fy = cam5[1]; kf.cx = cam5[2]; kf.cy = cam5[3]; kf.mbf = cam5[4];
+        kf.R = cv::Mat(3, 3, CV_32F); kf.t = cv::Mat(3, 1, CV_32F); kf.O = cv::Mat(3, 1, CV_32F);
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) kf.R.at<float>(r, c) = T[4 * r + c]; kf.t.at<float>(r, 0) = T[4 * r + 3]; kf.O.at<float>(r, 0) = Ow[r]; }
+        std::vector<uint8_t> pvalid = rd<uint8_t>(f, nmp);
+        std::vector<float> pxyz = rd<float>(f, (size_t)nmp * 3), pnrm = rd<float>(f, (size_t)nmp * 3), pmin = rd<float>(f, nmp), pmax = rd<float>(f, nmp);
+        std::vector<uint8_t> pdesc = rd<uint8_t>(f, (size_t)nmp * 32);
+        std::vector<int32_t> m_in = rd<int32_t>(f, nk), m_exp = rd<int32_t>(f, nk);
+        int32_t nm_exp = 0; f.read(reinterpret_cast<char*>(&nm_exp), 4);
+        std::vector<int32_t> kf_has = rd<int32_t>(f, nk), pobs = rd<int32_t>(f, nmp);
+        std::vector<uint8_t> pinkf = rd<uint8_t>(f, nmp);
+        float fth = 0; f.read(reinterpret_cast<char*>(&fth), 4);
+        int32_t nf_exp = 0; f.read(reinterpret_cast<char*>(&nf_exp), 4);
+        std::vector<int32_t> kf_final = rd<int32_t>(f, nk);
+        std::vector<uint8_t> pbad_exp = rd<uint8_t>(f, nmp), ebad_exp = rd<uint8_t>(f, nk);
+        auto make_points = [&](std::vector<MapPoint>& store, std::vector<MapPoint*>& ptrs) {
+            store.assign(nmp, MapPoint()); ptrs.resize(nmp);
+            for (int i = 0; i < nmp; ++i) {
+                MapPoint& p = store[i];
+                p.pos = cv::Mat(3, 1, CV_32F, &pxyz[3 * (size_t)i], 4).clone(); p.normal = cv::Mat(3, 1, CV_32F, &pnrm[3 * (size_t)i], 4).clone();
+                p.desc = cv::Mat(1, 32, CV_8U, &pdesc[(size_t)i * 32], 32).clone(); p.mfMinDistance = pmin[i]; p.mfMaxDistance = pmax[i]; p.bad = !pvalid[i];
+                ptrs[i] = &p;
+            }
+        };
+        ORBmatcher lm(0.8f, true);
+        {   // 8.
+            std::vector<MapPoint> store; std::vector<MapPoint*> pts; make_points(store, pts);
+            std::vector<MapPoint> dummy(nk); std::vector<MapPoint*> vpMatched(nk, nullptr);
+            for (int j = 0; j < nk; ++j) if (m_in[j] >= 0) vpMatched[j] = &dummy[j];
+            nsim3 = lm.SearchByProjection(&kf, T.data(), Ow.data(), pts, vpMatched, ith);
+            if (nsim3 != nm_exp) return fail("SearchByProjection(KF,Scw): match count");
+            for (int j = 0; j < nk; ++j) {
+                MapPoint* e = m_in[j] >= 0 ? &dummy[j] : (m_exp[j] >= 0 ? pts[m_exp[j]] : nullptr);
+                if (vpMatched[j] != e) return fail("SearchByProjection(KF,Scw): vpMatched");
+            }
+        }
+        {   // 9.
+            std::vector<MapPoint> store; std::vector<MapPoint*> pts; make_points(store, pts);
+            std::vector<MapPoint> exist(nk); kf.mps.assign(nk, nullptr);
+            for (int j = 0; j < nk; ++j) if (kf_has[j] >= 0) { exist[j].nobs = kf_has[j]; exist[j].obs.insert(&kf); kf.mps[j] = &exist[j]; }
+            for (int i = 0; i < nmp; ++i) { store[i].nobs = pobs[i]; if (pinkf[i]) store[i].obs.insert(&kf); }
+            nfused = lm.Fuse(&kf, pts, fth);
+            if (nfused != nf_exp) return fail("Fuse: count");
+            for (int j = 0; j < nk; ++j) {
+                MapPoint* e = kf_final[j] >= 0 ? pts[kf_final[j]] : (kf_final[j] == -2 ? &exist[j] : nullptr);
+                if (kf.mps[j] != e) return fail("Fuse: key-frame map points");
+                if (kf_has[j] >= 0 && exist[j].bad != (ebad_exp[j] != 0)) return fail("Fuse: replaced key-frame points");
+            }
+            for (int i = 0; i < nmp; ++i) if (store[i].bad != (pbad_exp[i] != 0)) return fail("Fuse: replaced candidates");
+        }
+    }
+    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges, %d detections (%d persons), %d sim3 matches, %d fused\n",
+                nkp, nm, kept, nd, nlk, nview, nfr, pin, npo, ndet, npers, nsim3, nfused);
     return 0;
 }

@@ -89,6 +89,51 @@ def test_shim_on_gpu(tmp_path):
         rgb = DM.synthetic_rgb(480, 640, 1)
         _, (objs, _, _) = DO.detect(layers, rgb, 0.9, 0.01)
         np.array([640, 480, len(objs)], np.int32).tofile(f); rgb.tofile(f); objs[:, 0].astype(np.int32).tofile(f); objs[:, 1:].astype(np.float32).tofile(f)
+        # 8./9. SearchByProjection(KeyFrame*, Scw, ...) and Fuse(KeyFrame*, vpMapPoints, th) through the class mirror: one key frame, one candidate list
+        from test_match_sim3 import sim3_inputs
+        ks, kOw, knrm, kmatched = sim3_inputs(31, 700, 1200)
+        f32 = np.float32
+        # the mirror recovers mfMin/MaxDistance from the *Invariance getters: use values that survive the 0.8 / 1.2 round trip
+        kmin = ((f32(0.8) * ks['min_dist'].astype(f32)) / f32(0.8)).astype(f32); kmax = ((f32(1.2) * ks['max_dist'].astype(f32)) / f32(1.2)).astype(f32)
+        kmin = ((f32(0.8) * kmin) / f32(0.8)).astype(f32); kmax = ((f32(1.2) * kmax) / f32(1.2)).astype(f32)
+        kc = ks['cam']; sf8 = ks['sf'].astype(f32); inv8 = (1.0 / (sf8 * sf8)).astype(f32)
+        kfo = O.FrameArrays(ks['kps'], ks['uright'], ks['desc'], 640, 480, kc['fx'], kc['fy'], kc['cx'], kc['cy'], kc['bf'], ks['sf'])
+        nm3, m3 = O.search_by_projection_sim3(kfo, ks['Tcw_cur'], kOw, ks['kf_valid'], ks['last_xyz'], knrm, kmin, kmax, ks['last_desc'], 10.0, kmatched)
+        assert nm3 > 30
+        nk_, nmp_ = len(ks['kps']), len(ks['last_xyz'])
+        rs9 = np.random.RandomState(99)
+        kf_has = np.where(rs9.rand(nk_) < 0.3, rs9.randint(1, 6, nk_), -1).astype(np.int32)      # Observations() of the point the key frame already holds there
+        pobs = rs9.randint(1, 6, nmp_).astype(np.int32); pinkf = (rs9.rand(nmp_) < 0.1).astype(np.uint8)
+        fth = 3.0
+        valid9 = (ks['kf_valid'].astype(bool) & ~pinkf.astype(bool)).astype(np.uint8)
+        bi9, bd9 = O.fuse_search(kfo, ks['Tcw_cur'], kOw, valid9, ks['last_xyz'], knrm, kmin, kmax, ks['last_desc'], fth, inv8)
+        # the reference's side-effect loop (src/ORBmatcher.cc:962-977) on the mock objects of test_shim.cpp
+        kf_final = np.where(kf_has >= 0, -2, -1).astype(np.int32); ebad = np.zeros(nk_, np.uint8); pbad = (1 - ks['kf_valid']).astype(np.uint8); inkf = pinkf.copy(); nfused = 0
+        pobs_run = pobs.copy()
+        for i in range(nmp_):
+            if pbad[i] or inkf[i] or bd9[i] > 50:
+                continue
+            j = bi9[i]
+            if kf_final[j] != -1:                       # a point is already there (an original one, or a candidate added earlier in this call)
+                holder_bad = ebad[j] if kf_final[j] == -2 else pbad[kf_final[j]]
+                holder_obs = kf_has[j] if kf_final[j] == -2 else pobs_run[kf_final[j]]
+                if not holder_bad:
+                    if holder_obs > pobs_run[i]:
+                        pbad[i] = 1
+                    elif kf_final[j] == -2:
+                        ebad[j] = 1
+                    else:
+                        pbad[kf_final[j]] = 1
+            else:
+                kf_final[j] = i; inkf[i] = 1; pobs_run[i] += 1
+            nfused += 1
+        assert nfused > 20 and ebad.sum() > 0
+        np.array([nk_, nmp_, 10], np.int32).tofile(f); ks['kps'].tofile(f); ks['uright'].astype(f32).tofile(f); ks['desc'].tofile(f); sf8.tofile(f); inv8.tofile(f)
+        np.array([kc['fx'], kc['fy'], kc['cx'], kc['cy'], kc['bf']], f32).tofile(f); ks['Tcw_cur'].astype(f32).tofile(f); kOw.astype(f32).tofile(f)
+        ks['kf_valid'].astype(np.uint8).tofile(f); ks['last_xyz'].astype(f32).tofile(f); knrm.astype(f32).tofile(f); kmin.tofile(f); kmax.tofile(f); ks['last_desc'].tofile(f)
+        kmatched.astype(np.int32).tofile(f); m3.astype(np.int32).tofile(f); np.array([nm3], np.int32).tofile(f)
+        kf_has.tofile(f); pobs.tofile(f); pinkf.tofile(f); np.array([fth], f32).tofile(f); np.array([nfused], np.int32).tofile(f)
+        kf_final.tofile(f); pbad.astype(np.uint8).tofile(f); ebad.tofile(f)
     out = subprocess.run([exe, str(path), dpp, dbp], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'OK shim' in out.stdout
