@@ -242,6 +242,64 @@ public:
         return nmatches;
     }
 
+    // Search matches between MapPoints seen in KF1 and KF2 transforming by a Sim3 [s12*R12|t12] (LoopClosing::ComputeSim3, src/LoopClosing.cc:313).  :1106-1330
+    // Both projection searches run on the GPU; vbAlreadyMatched, the <= TH_HIGH decision and the agreement check are the reference's, on the host.
+    // sR12 = s12*R12, sR21 = (1.0/s12)*R12.t(), t21 = -sR21*t12 (:1122-1124) in scalar float arithmetic (Mat*scalar = multiply by the float value of the
+    // factor -- restated, see decompose_scw; the small-matrix product sums float products left to right).
+    template <class KeyFrameT, class MapPointT>
+    int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const float& s12, const cv::Mat& R12, const cv::Mat& t12, const float th) {
+        float x21[12], x12[12];                                   // [sR21 | t21], [sR12 | t12]
+        const float inv = (float)(1.0 / (double)s12);
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) { x12[3 * r + c] = R12.at<float>(r, c) * s12; x21[3 * r + c] = R12.at<float>(c, r) * inv; }
+            x12[9 + r] = t12.at<float>(r, 0);
+        }
+        for (int r = 0; r < 3; ++r) {
+            volatile float acc = x21[3 * r] * x12[9];
+            acc = acc + x21[3 * r + 1] * x12[10];
+            acc = acc + x21[3 * r + 2] * x12[11];
+            x21[9 + r] = -acc;
+        }
+        const std::vector<MapPointT*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+        const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+        std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+        for (int i = 0; i < N1; ++i) {
+            MapPointT* pMP = vpMatches12[i];
+            if (pMP) {
+                vbAlreadyMatched1[i] = true;
+                const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+                if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+            }
+        }
+        auto pose = [](KeyFrameT* kf, float T[16]) {
+            const cv::Mat R = kf->GetRotation(), t = kf->GetTranslation();
+            for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T[4 * r + c] = R.template at<float>(r, c); T[4 * r + 3] = t.template at<float>(r, 0); }
+            T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
+        };
+        float T1[16], T2[16];
+        pose(pKF1, T1); pose(pKF2, T2);
+        const float zero[3] = {0.f, 0.f, 0.f};
+        std::vector<int32_t> bi1, bd1, bi2, bd2;
+        // the skip test depends on the feature index, not only on the point: flatten with explicit masks
+        auto masked = [&](const std::vector<MapPointT*>& pts, const std::vector<bool>& already) {
+            std::vector<MapPointT*> v(pts.size(), nullptr);
+            for (size_t i = 0; i < pts.size(); ++i) if (pts[i] && !already[i] && !pts[i]->isBad()) v[i] = pts[i];
+            return v;
+        };
+        const std::vector<MapPointT*> c1 = masked(vpMapPoints1, vbAlreadyMatched1), c2 = masked(vpMapPoints2, vbAlreadyMatched2);
+        search_kf(pKF2, T1, zero, c1, [](MapPointT* p) { return p != nullptr; }, th, 2, bi1, bd1, nullptr, x21);      // KF1's points into KF2 (:1148-1225)
+        search_kf(pKF1, T2, zero, c2, [](MapPointT* p) { return p != nullptr; }, th, 2, bi2, bd2, nullptr, x12);      // KF2's points into KF1 (:1227-1307)
+        int nFound = 0;
+        for (int i1 = 0; i1 < N1; ++i1) {
+            const int idx2 = bd1[i1] <= TH_HIGH ? bi1[i1] : -1;
+            if (idx2 >= 0) {
+                const int idx1 = bd2[idx2] <= TH_HIGH ? bi2[idx2] : -1;
+                if (idx1 == i1) { vpMatches12[i1] = vpMapPoints2[idx2]; nFound++; }
+            }
+        }
+        return nFound;
+    }
+
     static const int TH_HIGH = 100;
     static const int HISTO_LENGTH = 30;
 
@@ -280,7 +338,7 @@ protected:
     // Flattens the key frame and the candidate points and runs sgs_fuse_search.  valid(p) = the reference's per-point skip test.
     template <class KeyFrameT, class MapPointT, class ValidF>
     int search_kf(KeyFrameT* pKF, const float T[16], const float O[3], const std::vector<MapPointT*>& pts, ValidF valid, float th, int variant,
-                  std::vector<int32_t>& bi, std::vector<int32_t>& bd, std::vector<int32_t>* kf_matched) {
+                  std::vector<int32_t>& bi, std::vector<int32_t>& bd, std::vector<int32_t>* kf_matched, const float* xform2 = nullptr) {
         const int nmp = (int)pts.size();
         std::vector<float> scale(pKF->mvScaleFactors.begin(), pKF->mvScaleFactors.end()), inv_s2(pKF->mvInvLevelSigma2.begin(), pKF->mvInvLevelSigma2.end());
         sgs_frame_view v;
@@ -297,14 +355,15 @@ protected:
             MapPointT* p = pts[i];
             if (!valid(p)) continue;
             ok[i] = 1;
-            const cv::Mat P = p->GetWorldPos(), Nn = p->GetNormal(), d = p->GetDescriptor();
-            for (int k = 0; k < 3; ++k) { xyz[3 * (size_t)i + k] = P.template at<float>(k, 0); nrm[3 * (size_t)i + k] = Nn.template at<float>(k, 0); }
+            const cv::Mat P = p->GetWorldPos(), d = p->GetDescriptor();
+            for (int k = 0; k < 3; ++k) xyz[3 * (size_t)i + k] = P.template at<float>(k, 0);
+            if (variant != 2) { const cv::Mat Nn = p->GetNormal(); for (int k = 0; k < 3; ++k) nrm[3 * (size_t)i + k] = Nn.template at<float>(k, 0); }
             std::memcpy(&desc[(size_t)i * 32], d.template ptr<uint8_t>(), 32);
             mn[i] = p->GetMinDistanceInvariance() / 0.8f; mx[i] = p->GetMaxDistanceInvariance() / 1.2f;
         }
         bi.assign(nmp, -1); bd.assign(nmp, 256);
         int nmatches = 0;
-        check(sgs_fuse_search(&v, T, O, nmp, ok.data(), xyz.data(), nrm.data(), mn.data(), mx.data(), desc.data(), th, inv_s2.data(), variant, nullptr, bi.data(),
+        check(sgs_fuse_search(&v, T, O, nmp, ok.data(), xyz.data(), nrm.data(), mn.data(), mx.data(), desc.data(), th, inv_s2.data(), variant, xform2, bi.data(),
                               bd.data(), kf_matched ? kf_matched->data() : nullptr, &nmatches, device_));
         return nmatches;
     }

@@ -11,6 +11,7 @@
 #include "sgslam/FrameGeometry.h"
 #include "sgslam/Optimizer.h"
 #include "sgslam/Detector2D.h"
+#include <map>
 #include <set>
 
 #include "sgslam/ORBextractor.h"
@@ -35,6 +36,8 @@ struct MapPoint {
     template <class KF> bool IsInKeyFrame(KF* kf) { return obs.count(kf) != 0; }
     template <class KF> void AddObservation(KF* kf, size_t) { if (obs.insert(kf).second) ++nobs; }
     void Replace(MapPoint* other) { bad = true; replaced_by = other; }
+    std::map<const void*, int> index_in_kf;
+    template <class KF> int GetIndexInKeyFrame(KF* kf) { auto it = index_in_kf.find(kf); return it == index_in_kf.end() ? -1 : it->second; }
 };
 struct KeyFrame {
     int N = 0;
@@ -47,6 +50,7 @@ struct KeyFrame {
     cv::Mat GetTranslation() { return t; }
     cv::Mat GetCameraCenter() { return O; }
     MapPoint* GetMapPoint(size_t idx) { return mps[idx]; }
+    std::vector<MapPoint*> GetMapPointMatches() { return mps; }
     void AddMapPoint(MapPoint* p, size_t idx) { mps[idx] = p; }
     std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> r; for (MapPoint* p : mps) if (p && !p->isBad()) r.insert(p); return r; }
 };
@@ -218,7 +222,7 @@ int main(int argc, char** argv) {
         if ((int)det.mvObjects2D_to_View.size() != 2 * dn || (int)det.mvPotentialDynamicBorderForMapping.size() != npers) return fail("Detector2D: second call");
     }
     // 8. SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) and 9. Fuse(KeyFrame*, vpMapPoints, th) on one key frame / candidate list
-    int nsim3 = -1, nfused = -1;
+    int nsim3 = -1, nfused = -1, nsim3b = -1;
     if (argc >= 4) {
         int32_t kh[3]; f.read(reinterpret_cast<char*>(kh), sizeof kh);
         const int nk = kh[0], nmp = kh[1], ith = kh[2];
@@ -277,8 +281,33 @@ int main(int argc, char** argv) {
             }
             for (int i = 0; i < nmp; ++i) if (store[i].bad != (pbad_exp[i] != 0)) return fail("Fuse: replaced candidates");
         }
+        {   // 10. SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th): two key frames with the same features and pose, different map points
+            int32_t sh[2]; f.read(reinterpret_cast<char*>(sh), sizeof sh);
+            const int npts = sh[0];
+            float s12 = 0, th3 = 0; f.read(reinterpret_cast<char*>(&s12), 4); f.read(reinterpret_cast<char*>(&th3), 4);
+            std::vector<float> R12 = rd<float>(f, 9), t12 = rd<float>(f, 3);
+            std::vector<int32_t> mp1 = rd<int32_t>(f, nk), mp2 = rd<int32_t>(f, nk), pre = rd<int32_t>(f, nk), exp12 = rd<int32_t>(f, nk);
+            int32_t nfound_exp = 0; f.read(reinterpret_cast<char*>(&nfound_exp), 4);
+            std::vector<MapPoint> store; std::vector<MapPoint*> pts; make_points(store, pts);
+            (void)npts;
+            KeyFrame kf2 = kf;
+            kf.mps.assign(nk, nullptr); kf2.mps.assign(nk, nullptr);
+            for (int j = 0; j < nk; ++j) {
+                if (mp1[j] >= 0) kf.mps[j] = pts[mp1[j]];
+                if (mp2[j] >= 0) { kf2.mps[j] = pts[mp2[j]]; pts[mp2[j]]->index_in_kf[&kf2] = j; }
+            }
+            std::vector<MapPoint*> vpMatches12(nk, nullptr);
+            for (int j = 0; j < nk; ++j) if (pre[j] >= 0) vpMatches12[j] = pts[pre[j]];
+            cv::Mat R(3, 3, CV_32F, R12.data(), 12), t(3, 1, CV_32F, t12.data(), 4);
+            nsim3b = lm.SearchBySim3(&kf, &kf2, vpMatches12, s12, R, t, th3);
+            if (nsim3b != nfound_exp) return fail("SearchBySim3: count");
+            for (int j = 0; j < nk; ++j) {
+                MapPoint* e = exp12[j] >= 0 ? pts[exp12[j]] : nullptr;
+                if (vpMatches12[j] != e) return fail("SearchBySim3: vpMatches12");
+            }
+        }
     }
-    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges, %d detections (%d persons), %d sim3 matches, %d fused\n",
-                nkp, nm, kept, nd, nlk, nview, nfr, pin, npo, ndet, npers, nsim3, nfused);
+    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges, %d detections (%d persons), %d sim3 matches, %d fused, %d Sim3 pairs\n",
+                nkp, nm, kept, nd, nlk, nview, nfr, pin, npo, ndet, npers, nsim3, nfused, nsim3b);
     return 0;
 }

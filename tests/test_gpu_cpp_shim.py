@@ -134,6 +134,47 @@ def test_shim_on_gpu(tmp_path):
         kmatched.astype(np.int32).tofile(f); m3.astype(np.int32).tofile(f); np.array([nm3], np.int32).tofile(f)
         kf_has.tofile(f); pobs.tofile(f); pinkf.tofile(f); np.array([fth], f32).tofile(f); np.array([nfused], np.int32).tofile(f)
         kf_final.tofile(f); pbad.astype(np.uint8).tofile(f); ebad.tofile(f)
+        # 10. SearchBySim3: both key frames share the features and the pose; each holds some of the candidate points at the features they resemble
+        bi0, bd0 = O.fuse_search(kfo, ks['Tcw_cur'], kOw, np.ones(nmp_, np.uint8), ks['last_xyz'], knrm, kmin, kmax, ks['last_desc'], 3.0, inv8, sim3_variant=1)
+        mp1 = np.full(nk_, -1, np.int32); mp2 = np.full(nk_, -1, np.int32)
+        for i in np.argsort(bd0, kind='stable'):
+            j = bi0[i]
+            if j < 0 or bd0[i] > 70:
+                continue
+            if mp1[j] < 0 and rs9.rand() < 0.6:
+                mp1[j] = i
+            elif mp2[j] < 0:
+                mp2[j] = i
+        both = np.nonzero((mp1 >= 0) & (mp2 >= 0))[0]
+        assert len(both) > 15
+        pre = np.full(nk_, -1, np.int32); pre[both[:4]] = mp2[both[:4]]                       # vpMatches12 entries that are already set
+        s12 = f32(1.02); a12 = 0.003
+        R12 = np.array([[np.cos(a12), -np.sin(a12), 0], [np.sin(a12), np.cos(a12), 0], [0, 0, 1]], f32); t12 = np.array([0.01, -0.005, 0.008], f32)
+        inv12 = f32(1.0 / np.float64(s12))
+        sR12 = (R12 * s12).astype(f32); sR21 = (R12.T * inv12).astype(f32)
+        t21 = np.array([-f32(f32(f32(sR21[r, 0] * t12[0]) + f32(sR21[r, 1] * t12[1])) + f32(sR21[r, 2] * t12[2])) for r in range(3)], f32)
+        x21 = np.concatenate([sR21.reshape(9), t21]).astype(f32); x12 = np.concatenate([sR12.reshape(9), t12]).astype(f32)
+        already1 = pre >= 0
+        already2 = np.zeros(nk_, bool)
+        for j in np.nonzero(already1)[0]:
+            already2[np.nonzero(mp2 == pre[j])[0]] = True                                       # GetIndexInKeyFrame(pKF2)
+        ok_pt = ks['kf_valid'].astype(bool)
+
+        def direction(mp, already, xf):
+            has = (mp >= 0) & ~already
+            has &= np.where(mp >= 0, ok_pt[np.maximum(mp, 0)], False)
+            g = np.maximum(mp, 0)
+            bi_, bd_ = O.fuse_search(kfo, ks['Tcw_cur'], np.zeros(3, f32), has.astype(np.uint8), ks['last_xyz'][g], knrm[g], kmin[g], kmax[g], ks['last_desc'][g], 7.5, inv8,
+                                     sim3_variant=2, xform2=xf)
+            return np.where(bd_ <= 100, bi_, -1)
+        vn1 = direction(mp1, already1, x21); vn2 = direction(mp2, already2, x12)
+        exp12 = pre.copy(); nfound = 0
+        for i1 in range(nk_):
+            if vn1[i1] >= 0 and vn2[vn1[i1]] == i1:
+                exp12[i1] = mp2[vn1[i1]]; nfound += 1
+        assert nfound > 5
+        np.array([nmp_, 0], np.int32).tofile(f); np.array([s12, 7.5], f32).tofile(f); R12.tofile(f); t12.tofile(f); mp1.tofile(f); mp2.tofile(f); pre.tofile(f); exp12.tofile(f)
+        np.array([nfound], np.int32).tofile(f)
     out = subprocess.run([exe, str(path), dpp, dbp], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'OK shim' in out.stdout
