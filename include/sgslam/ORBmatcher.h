@@ -15,7 +15,8 @@
 // Mapping / loop closing:                      Fuse(KeyFrame*, vpMapPoints, th)                       src/ORBmatcher.cc:829-980
 //                                              Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)     src/ORBmatcher.cc:982-1104
 //                                              SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)  src/ORBmatcher.cc:292-405
-// SearchByBoW(KF, KF), SearchForTriangulation and SearchBySim3 have device entry points (sgs_match_bow_batch_device, sgs_fuse_search_batch_device) but no mirror yet.
+//                                              SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)  src/ORBmatcher.cc:1106-1330
+// SearchByBoW(KF, KF) and SearchForTriangulation have device entry points (sgs_match_bow_batch_device) but no mirror yet.
 #pragma once
 #include <cmath>
 #include <cstring>
