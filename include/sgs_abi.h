@@ -342,6 +342,14 @@ SGS_API int sgs_bow_transform(const sgs_vocabulary* v, const uint8_t* desc, int 
 SGS_API int sgs_match_bow(int nkf, const int32_t* kf_node, const double* kf_weight, const uint8_t* kf_valid, const uint8_t* kf_desc,
                           const float* kf_angle, int nf, const int32_t* f_node, const double* f_weight, const uint8_t* f_desc,
                           const float* f_angle, float nnratio, int check_orientation, int32_t* match_f, int* nmatches, int device);
+/* Two key frames from host memory.  mode 1: SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (valid = map point exists && !isBad()); mode 2:
+ * SearchForTriangulation (valid = the feature has NO map point; the stereo flags, positions, second frame's octaves, F12 [9], epipole [2], the
+ * second key frame's mvLevelSigma2 / mvScaleFactors [nlevels] and only_stereo are needed).  match12[i1] = feature of the second key frame or -1. */
+SGS_API int sgs_match_bow_keyframes(int mode, int n1, const int32_t* node1, const double* weight1, const uint8_t* valid1, const uint8_t* desc1, const float* angle1,
+                                    int n2, const int32_t* node2, const double* weight2, const uint8_t* valid2, const uint8_t* desc2, const float* angle2,
+                                    float nnratio, int check_orientation, const uint8_t* stereo1, const uint8_t* stereo2, const float* xy1, const float* xy2,
+                                    const int32_t* octave2, const float* F12, const float* epipole, const float* level_sigma2, const float* scale_factors, int nlevels,
+                                    int only_stereo, int32_t* match12, int* nmatches, int device);
 
 /* ------------------------------------------------------------------------------------
  * Frame geometry between the extractor and the matchers (device pointers, `nframes` frames, work enqueued on `stream`):

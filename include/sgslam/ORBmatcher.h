@@ -16,12 +16,15 @@
 //                                              Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)     src/ORBmatcher.cc:982-1104
 //                                              SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)  src/ORBmatcher.cc:292-405
 //                                              SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)  src/ORBmatcher.cc:1106-1330
-// SearchByBoW(KF, KF) and SearchForTriangulation have device entry points (sgs_match_bow_batch_device) but no mirror yet.
+//                                              SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12)         src/ORBmatcher.cc:524-657
+//                                              SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)  src/ORBmatcher.cc:659-827
+// Not mirrored: SearchForInitialization (monocular initialisation, never reached by the RGB-D system).
 #pragma once
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../sgs_abi.h"
@@ -157,6 +160,63 @@ public:
         check(sgs_match_bow(nkf, kn.data(), kw.data(), kv.data(), pKF->mDescriptors.template ptr<uint8_t>(), ka.data(), nf, fn.data(), fw.data(),
                             F.mDescriptors.template ptr<uint8_t>(), fa.data(), mfNNratio, mbCheckOrientation ? 1 : 0, m.data(), &nmatches, device_));
         for (int j = 0; j < nf; ++j) if (m[j] >= 0) vpMapPointMatches[j] = vpMapPointsKF[m[j]];
+        return nmatches;
+    }
+
+    // Matching between two key frames' map points through the vocabulary tree (LoopClosing::ComputeSim3, src/LoopClosing.cc:272).  src/ORBmatcher.cc:524-657
+    template <class KeyFrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12) {
+        const std::vector<MapPointT*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+        const int n1 = (int)vpMapPoints1.size(), n2 = (int)vpMapPoints2.size();
+        vpMatches12 = std::vector<MapPointT*>(n1, static_cast<MapPointT*>(NULL));
+        if (n1 == 0 || n2 == 0) return 0;
+        KfBow a = flatten_bow(pKF1, n1), b = flatten_bow(pKF2, n2);
+        for (int i = 0; i < n1; ++i) a.valid[i] = (vpMapPoints1[i] && !vpMapPoints1[i]->isBad()) ? 1 : 0;
+        for (int i = 0; i < n2; ++i) b.valid[i] = (vpMapPoints2[i] && !vpMapPoints2[i]->isBad()) ? 1 : 0;
+        std::vector<int32_t> m(n1, -1);
+        int nmatches = 0;
+        check(sgs_match_bow_keyframes(1, n1, a.node.data(), a.weight.data(), a.valid.data(), pKF1->mDescriptors.template ptr<uint8_t>(), a.angle.data(), n2, b.node.data(),
+                                      b.weight.data(), b.valid.data(), pKF2->mDescriptors.template ptr<uint8_t>(), b.angle.data(), mfNNratio, mbCheckOrientation ? 1 : 0, nullptr,
+                                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, m.data(), &nmatches, device_));
+        for (int i = 0; i < n1; ++i) if (m[i] >= 0) vpMatches12[i] = vpMapPoints2[m[i]];
+        return nmatches;
+    }
+
+    // Matching to triangulate new MapPoints, checking the epipolar constraint (LocalMapping::CreateNewMapPoints, src/LocalMapping.cc:298).  src/ORBmatcher.cc:659-827
+    template <class KeyFrameT>
+    int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, const cv::Mat& F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo) {
+        const int n1 = pKF1->N, n2 = pKF2->N;
+        vMatchedPairs.clear();
+        if (n1 == 0 || n2 == 0) return 0;
+        // epipole of camera 1 in image 2 (:667-672): C2 = R2w*Cw + t2w (small-matrix product: float sum, the addition in double), invz = 1.0f / z
+        const cv::Mat Cw = pKF1->GetCameraCenter(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+        float C2[3];
+        for (int r = 0; r < 3; ++r) {
+            volatile float acc = R2w.template at<float>(r, 0) * Cw.template at<float>(0, 0);
+            acc = acc + R2w.template at<float>(r, 1) * Cw.template at<float>(1, 0);
+            acc = acc + R2w.template at<float>(r, 2) * Cw.template at<float>(2, 0);
+            C2[r] = (float)((double)acc + (double)t2w.template at<float>(r, 0));
+        }
+        const float invz = 1.0f / C2[2];
+        volatile float exv = pKF2->fx * C2[0]; exv = exv * invz; exv = exv + pKF2->cx;
+        volatile float eyv = pKF2->fy * C2[1]; eyv = eyv * invz; eyv = eyv + pKF2->cy;
+        const float epi[2] = {exv, eyv};
+        KfBow a = flatten_bow(pKF1, n1), b = flatten_bow(pKF2, n2);
+        std::vector<uint8_t> st1(n1), st2(n2);
+        std::vector<float> xy1(2 * (size_t)n1), xy2(2 * (size_t)n2), F(9);
+        std::vector<int32_t> oct2(n2);
+        for (int i = 0; i < n1; ++i) { a.valid[i] = pKF1->GetMapPoint(i) ? 0 : 1; st1[i] = pKF1->mvuRight[i] >= 0 ? 1 : 0; xy1[2 * (size_t)i] = pKF1->mvKeysUn[i].pt.x; xy1[2 * (size_t)i + 1] = pKF1->mvKeysUn[i].pt.y; }
+        for (int i = 0; i < n2; ++i) { b.valid[i] = pKF2->GetMapPoint(i) ? 0 : 1; st2[i] = pKF2->mvuRight[i] >= 0 ? 1 : 0; xy2[2 * (size_t)i] = pKF2->mvKeysUn[i].pt.x; xy2[2 * (size_t)i + 1] = pKF2->mvKeysUn[i].pt.y; oct2[i] = pKF2->mvKeysUn[i].octave; }
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F[3 * r + c] = F12.template at<float>(r, c);
+        std::vector<float> s2(pKF2->mvLevelSigma2.begin(), pKF2->mvLevelSigma2.end()), sf(pKF2->mvScaleFactors.begin(), pKF2->mvScaleFactors.end());
+        std::vector<int32_t> m(n1, -1);
+        int nmatches = 0;
+        check(sgs_match_bow_keyframes(2, n1, a.node.data(), a.weight.data(), a.valid.data(), pKF1->mDescriptors.template ptr<uint8_t>(), a.angle.data(), n2, b.node.data(),
+                                      b.weight.data(), b.valid.data(), pKF2->mDescriptors.template ptr<uint8_t>(), b.angle.data(), mfNNratio, mbCheckOrientation ? 1 : 0, st1.data(),
+                                      st2.data(), xy1.data(), xy2.data(), oct2.data(), F.data(), epi, s2.data(), sf.data(), (int)sf.size(), bOnlyStereo ? 1 : 0, m.data(), &nmatches,
+                                      device_));
+        vMatchedPairs.reserve(nmatches);
+        for (int i = 0; i < n1; ++i) if (m[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m[i]));
         return nmatches;
     }
 
@@ -317,6 +377,17 @@ protected:
         v.nlevels = (int)scale.size(); v.scale_factors = scale.data();
         return v;
     }
+    struct KfBow { std::vector<int32_t> node; std::vector<double> weight; std::vector<uint8_t> valid; std::vector<float> angle; };
+    // per-feature view of a key frame's DBoW2::FeatureVector: node id of the feature, weight 1 = the feature is listed (0 = not in mFeatVec)
+    template <class KeyFrameT>
+    static KfBow flatten_bow(KeyFrameT* pKF, int n) {
+        KfBow b;
+        b.node.assign(n, 0); b.weight.assign(n, 0.0); b.valid.assign(n, 0); b.angle.assign(n, 0.f);
+        for (const auto& kvp : pKF->mFeatVec) for (unsigned idx : kvp.second) { b.node[idx] = (int32_t)kvp.first; b.weight[idx] = 1.0; }
+        for (int i = 0; i < n; ++i) b.angle[i] = pKF->mvKeysUn[i].angle;
+        return b;
+    }
+
     // sRcw = Scw(0:3,0:3); scw = sqrt(sRcw.row(0).dot(sRcw.row(0))); Rcw = sRcw/scw; tcw = Scw(0:3,3)/scw; Ow = -Rcw.t()*tcw   (src/ORBmatcher.cc:301-305, :988-992)
     // with scalar float operations in OpenCV's evaluation order: Mat::dot accumulates in double; Mat/scalar is convertTo(alpha = 1/s), which for CV_32F
     // multiplies by the FLOAT value of the reciprocal; the transposed product accumulates in double (pinned with cv2.gemm).  The

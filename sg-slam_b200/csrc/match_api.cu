@@ -280,6 +280,47 @@ SGS_API int sgs_fuse_search(const sgs_frame_view* kf, const float* tcw, const fl
     return SGS_OK;
 }
 
+SGS_API int sgs_match_bow_keyframes(int mode, int n1, const int32_t* node1, const double* weight1, const uint8_t* valid1, const uint8_t* desc1, const float* angle1,
+                                    int n2, const int32_t* node2, const double* weight2, const uint8_t* valid2, const uint8_t* desc2, const float* angle2,
+                                    float nnratio, int check_orientation, const uint8_t* stereo1, const uint8_t* stereo2, const float* xy1, const float* xy2,
+                                    const int32_t* octave2, const float* F12, const float* epipole, const float* level_sigma2, const float* scale_factors, int nlevels,
+                                    int only_stereo, int32_t* match12, int* nmatches, int device) {
+    if (!nmatches || n1 < 0 || n2 < 0 || (mode != 1 && mode != 2)) { set_error("sgs_match_bow_keyframes: bad argument"); return SGS_ERR_INVALID; }
+    *nmatches = 0;
+    if (n1 > 0 && match12) for (int i = 0; i < n1; ++i) match12[i] = -1;
+    if (n1 == 0 || n2 == 0) return SGS_OK;
+    if (!node1 || !weight1 || !valid1 || !desc1 || !angle1 || !node2 || !weight2 || !valid2 || !desc2 || !angle2 || !match12) { set_error("sgs_match_bow_keyframes: NULL array"); return SGS_ERR_INVALID; }
+    if (mode == 2 && (!stereo1 || !stereo2 || !xy1 || !xy2 || !octave2 || !F12 || !epipole || !level_sigma2 || !scale_factors || nlevels < 1 || nlevels > 16)) {
+        set_error("sgs_match_bow_keyframes: triangulation mode needs stereo flags, positions, octaves, F12, the epipole and the level tables"); return SGS_ERR_INVALID; }
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    const size_t A = (size_t)n1, Bn = (size_t)n2;
+    const int32_t cnt[3] = {n1, n2, 0};
+    DevBuf nd1, w1, v1, d1, a1, nd2, w2, v2, d2, a2, c, m, s1, s2, p1, p2, o2, f, ep;
+    SGS_CUDA_TRY(nd1.upload(node1, 4 * A)); SGS_CUDA_TRY(w1.upload(weight1, 8 * A)); SGS_CUDA_TRY(v1.upload(valid1, A)); SGS_CUDA_TRY(d1.upload(desc1, 32 * A)); SGS_CUDA_TRY(a1.upload(angle1, 4 * A));
+    SGS_CUDA_TRY(nd2.upload(node2, 4 * Bn)); SGS_CUDA_TRY(w2.upload(weight2, 8 * Bn)); SGS_CUDA_TRY(v2.upload(valid2, Bn)); SGS_CUDA_TRY(d2.upload(desc2, 32 * Bn)); SGS_CUDA_TRY(a2.upload(angle2, 4 * Bn));
+    SGS_CUDA_TRY(c.upload(cnt, 12)); SGS_CUDA_TRY(m.alloc(4 * A));
+    sgs_bow_batch b;
+    std::memset(&b, 0, sizeof b);
+    b.kf_node = nd1.as<int32_t>(); b.kf_weight = w1.as<double>(); b.kf_valid = v1.as<uint8_t>(); b.kf_desc = d1.as<uint8_t>(); b.kf_angle = a1.as<float>(); b.kf_n = c.as<int32_t>(); b.kf_cap = n1;
+    b.f_node = nd2.as<int32_t>(); b.f_weight = w2.as<double>(); b.f_valid = v2.as<uint8_t>(); b.f_desc = d2.as<uint8_t>(); b.f_angle = a2.as<float>(); b.f_n = c.as<int32_t>() + 1; b.f_cap = n2;
+    b.keyframe_pair = mode; b.nnratio = nnratio; b.check_orientation = check_orientation; b.match_f = m.as<int32_t>(); b.nmatches = c.as<int32_t>() + 2;
+    if (mode == 2) {
+        SGS_CUDA_TRY(s1.upload(stereo1, A)); SGS_CUDA_TRY(s2.upload(stereo2, Bn)); SGS_CUDA_TRY(p1.upload(xy1, 8 * A)); SGS_CUDA_TRY(p2.upload(xy2, 8 * Bn));
+        SGS_CUDA_TRY(o2.upload(octave2, 4 * Bn)); SGS_CUDA_TRY(f.upload(F12, 36)); SGS_CUDA_TRY(ep.upload(epipole, 8));
+        b.kf_stereo = s1.as<uint8_t>(); b.f_stereo = s2.as<uint8_t>(); b.kf_xy = p1.as<float>(); b.f_xy = p2.as<float>(); b.f_octave = o2.as<int32_t>();
+        b.F12 = f.as<float>(); b.epipole = ep.as<float>(); b.only_stereo = only_stereo;
+        for (int l = 0; l < nlevels; ++l) { b.level_sigma2[l] = level_sigma2[l]; b.scale_factors[l] = scale_factors[l]; }
+    }
+    const int rc = sgs_match_bow_batch_device(&b, 1, nullptr);
+    if (rc != SGS_OK) return rc;
+    SGS_CUDA_TRY(cudaDeviceSynchronize());
+    SGS_CUDA_TRY(cudaMemcpy(match12, m.p, 4 * A, cudaMemcpyDeviceToHost));
+    int32_t nm = 0;
+    SGS_CUDA_TRY(cudaMemcpy(&nm, c.as<int32_t>() + 2, 4, cudaMemcpyDeviceToHost));
+    *nmatches = nm;
+    return SGS_OK;
+}
+
 SGS_API int sgs_match_project_localmap(const sgs_frame_view* f, int nmp, const uint8_t* mp_inview, const float* proj_x, const float* proj_y,
                                        const float* proj_xr, const int32_t* level, const float* view_cos, const uint8_t* mp_desc,
                                        const uint8_t* mp_obs, float th, float nnratio, int32_t id_base, int32_t* f_mp_inout,

@@ -42,7 +42,8 @@ struct MapPoint {
 struct KeyFrame {
     int N = 0;
     std::vector<cv::KeyPoint> mvKeysUn;
-    std::vector<float> mvuRight, mvScaleFactors, mvInvLevelSigma2;
+    std::vector<float> mvuRight, mvScaleFactors, mvInvLevelSigma2, mvLevelSigma2;
+    std::map<unsigned, std::vector<unsigned> > mFeatVec;          // DBoW2::FeatureVector
     cv::Mat mDescriptors, R, t, O;
     float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mnMinX = 0, mnMinY = 0, mnMaxX = 640, mnMaxY = 480;
     std::vector<MapPoint*> mps;
@@ -307,7 +308,41 @@ int main(int argc, char** argv) {
             }
         }
     }
-    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges, %d detections (%d persons), %d sim3 matches, %d fused, %d Sim3 pairs\n",
-                nkp, nm, kept, nd, nlk, nview, nfr, pin, npo, ndet, npers, nsim3, nfused, nsim3b);
+    // 11. SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) and 12. SearchForTriangulation on a pair of key frames with a flattened FeatureVector
+    int nbow2 = -1, ntri = -1;
+    if (argc >= 4) {
+        int32_t ph[3]; f.read(reinterpret_cast<char*>(ph), sizeof ph);
+        const int nn[2] = {ph[0], ph[1]}, only_stereo = ph[2];
+        KeyFrame K[2]; std::vector<uint8_t> dd[2]; std::vector<MapPoint> pstore[2];
+        for (int q = 0; q < 2; ++q) {
+            const int n = nn[q];
+            K[q].N = n; K[q].mvKeysUn = rd<cv::KeyPoint>(f, n); K[q].mvuRight = rd<float>(f, n); dd[q] = rd<uint8_t>(f, (size_t)n * 32);
+            K[q].mDescriptors = cv::Mat(n, 32, CV_8U, dd[q].data(), 32);
+            std::vector<int32_t> node = rd<int32_t>(f, n); std::vector<uint8_t> listed = rd<uint8_t>(f, n), state = rd<uint8_t>(f, n);
+            for (int i = 0; i < n; ++i) if (listed[i]) K[q].mFeatVec[(unsigned)node[i]].push_back((unsigned)i);
+            pstore[q].assign(n, MapPoint()); K[q].mps.assign(n, nullptr);
+            for (int i = 0; i < n; ++i) if (state[i]) { pstore[q][i].bad = state[i] == 2; K[q].mps[i] = &pstore[q][i]; }
+        }
+        std::vector<float> R2 = rd<float>(f, 9), t2 = rd<float>(f, 3), Cw = rd<float>(f, 3), cam4 = rd<float>(f, 4), F12v = rd<float>(f, 9), sig = rd<float>(f, 8), sfv = rd<float>(f, 8);
+        K[1].R = cv::Mat(3, 3, CV_32F, R2.data(), 12).clone(); K[1].t = cv::Mat(3, 1, CV_32F, t2.data(), 4).clone(); K[0].O = cv::Mat(3, 1, CV_32F, Cw.data(), 4).clone();
+        K[1].fx = cam4[0]; K[1].fy = cam4[1]; K[1].cx = cam4[2]; K[1].cy = cam4[3];
+        K[1].mvLevelSigma2 = sig; K[1].mvScaleFactors = sfv;
+        int32_t nm11 = 0, nm12 = 0;
+        f.read(reinterpret_cast<char*>(&nm11), 4); std::vector<int32_t> e11 = rd<int32_t>(f, nn[0]);
+        f.read(reinterpret_cast<char*>(&nm12), 4); std::vector<int32_t> e12 = rd<int32_t>(f, nn[0]);
+        ORBmatcher bm(0.8f, true);
+        std::vector<MapPoint*> v12;
+        nbow2 = bm.SearchByBoW(&K[0], &K[1], v12);
+        if (nbow2 != nm11 || (int)v12.size() != nn[0]) return fail("SearchByBoW(KF,KF): count");
+        for (int i = 0; i < nn[0]; ++i) if (v12[i] != (e11[i] >= 0 ? K[1].mps[e11[i]] : nullptr)) return fail("SearchByBoW(KF,KF): vpMatches12");
+        std::vector<std::pair<size_t, size_t> > pairs;
+        cv::Mat F12m(3, 3, CV_32F, F12v.data(), 12);
+        ntri = bm.SearchForTriangulation(&K[0], &K[1], F12m, pairs, only_stereo != 0);
+        if (ntri != nm12 || (int)pairs.size() != nm12) return fail("SearchForTriangulation: count");
+        size_t k = 0;
+        for (int i = 0; i < nn[0]; ++i) if (e12[i] >= 0) { if (pairs[k].first != (size_t)i || pairs[k].second != (size_t)e12[i]) return fail("SearchForTriangulation: pairs"); ++k; }
+    }
+    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges, %d detections (%d persons), %d sim3 matches, %d fused, %d Sim3 pairs, %d BoW pairs, %d triangulation pairs\n",
+                nkp, nm, kept, nd, nlk, nview, nfr, pin, npo, ndet, npers, nsim3, nfused, nsim3b, nbow2, ntri);
     return 0;
 }

@@ -175,6 +175,38 @@ def test_shim_on_gpu(tmp_path):
         assert nfound > 5
         np.array([nmp_, 0], np.int32).tofile(f); np.array([s12, 7.5], f32).tofile(f); R12.tofile(f); t12.tofile(f); mp1.tofile(f); mp2.tofile(f); pre.tofile(f); exp12.tofile(f)
         np.array([nfound], np.int32).tofile(f)
+        # 11./12. SearchByBoW(KF, KF) and SearchForTriangulation through the class mirror (flattened FeatureVectors from the oracle's vocabulary transform)
+        voc = S.random_vocabulary(17, k=10, L=3)
+        V = O.Vocabulary(voc['k'], voc['L'], voc['parent'], voc['desc'], voc['weight'])
+        n1_, n2_ = 900, 950
+        bs = S.bow_pair_scenario(77, voc, n_kf=n1_, n_f=n2_, flips=30)
+        rsb = np.random.RandomState(78)
+        xy1 = np.c_[rsb.uniform(20, 620, n1_), rsb.uniform(20, 460, n1_)].astype(f32)
+        d1b = np.unpackbits(bs['kf_desc'], axis=1).astype(np.int16); d2b = np.unpackbits(bs['f_desc'], axis=1).astype(np.int16)
+        src_ = np.array([int(np.argmin(np.abs(d1b - d2b[j]).sum(1))) for j in range(n2_)])
+        xy2 = np.c_[xy1[src_, 0] + rsb.uniform(-40, 40, n2_), xy1[src_, 1] + rsb.normal(0, 1.5, n2_)].astype(f32)
+        oct2 = rsb.randint(0, 8, n2_).astype(np.int32)
+        st = [rsb.choice([0, 1, 2], n1_, p=[0.5, 0.42, 0.08]).astype(np.uint8), rsb.choice([0, 1, 2], n2_, p=[0.5, 0.42, 0.08]).astype(np.uint8)]   # 0 no point, 1 point, 2 bad point
+        ur = [np.where(rsb.rand(n1_) < 0.5, 100.0, -1.0).astype(f32), np.where(rsb.rand(n2_) < 0.5, 100.0, -1.0).astype(f32)]
+        _, ow1, on1 = V.transform(bs['kf_desc'], 1); _, ow2, on2 = V.transform(bs['f_desc'], 1)
+        F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], f32)
+        R2 = S.pose(0.01, -0.02, 0.015, (0, 0, 0))[:3, :3].astype(f32); t2 = np.array([0.3, -0.1, 0.2], f32); Cw = np.array([0.5, 0.2, -1.5], f32)
+        camv = np.array([535.4, 539.2, 320.1, 247.6], f32)
+        C2 = [f32(np.float64(f32(f32(f32(R2[r, 0] * Cw[0]) + f32(R2[r, 1] * Cw[1])) + f32(R2[r, 2] * Cw[2]))) + np.float64(t2[r])) for r in range(3)]
+        invz2 = f32(1.0) / C2[2]
+        ex = f32(f32(f32(camv[0] * C2[0]) * invz2) + camv[2]); ey = f32(f32(f32(camv[1] * C2[1]) * invz2) + camv[3])
+        sig8 = (sf8 * sf8).astype(f32)
+        nm11, m11 = O.search_by_bow_kfkf(on1, ow1, (st[0] == 1), bs['kf_desc'], bs['kf_angle'], on2, ow2, (st[1] == 1), bs['f_desc'], bs['f_angle'], nnratio=0.8, check_ori=True)
+        k1 = dict(node=on1, weight=ow1, free=(st[0] == 0), stereo=(ur[0] >= 0), desc=bs['kf_desc'], xy=xy1, angle=bs['kf_angle'])
+        k2 = dict(node=on2, weight=ow2, free=(st[1] == 0), stereo=(ur[1] >= 0), desc=bs['f_desc'], xy=xy2, octave=oct2, angle=bs['f_angle'])
+        nm12, m12 = O.search_for_triangulation(k1, k2, F12, float(ex), float(ey), sig8, sf8, False, True)
+        assert nm11 > 20 and nm12 > 20
+        np.array([n1_, n2_, 0], np.int32).tofile(f)
+        for q, (dsc, ang, xy, octv, onode, oweight) in enumerate([(bs['kf_desc'], bs['kf_angle'], xy1, np.zeros(n1_, np.int32), on1, ow1), (bs['f_desc'], bs['f_angle'], xy2, oct2, on2, ow2)]):
+            kk = np.zeros(len(dsc), O.KP_DTYPE); kk['x'] = xy[:, 0]; kk['y'] = xy[:, 1]; kk['angle'] = ang; kk['octave'] = octv
+            kk.tofile(f); ur[q].tofile(f); dsc.tofile(f); np.asarray(onode, np.int32).tofile(f); (np.asarray(oweight) > 0).astype(np.uint8).tofile(f); st[q].tofile(f)
+        R2.tofile(f); t2.tofile(f); Cw.tofile(f); camv.tofile(f); F12.tofile(f); sig8.tofile(f); sf8.tofile(f)
+        np.array([nm11], np.int32).tofile(f); m11.astype(np.int32).tofile(f); np.array([nm12], np.int32).tofile(f); m12.astype(np.int32).tofile(f)
     out = subprocess.run([exe, str(path), dpp, dbp], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'OK shim' in out.stdout
