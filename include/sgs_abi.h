@@ -265,6 +265,20 @@ SGS_API int sgs_fuse_search(const sgs_frame_view* kf, const float* tcw, const fl
                             const float* inv_level_sigma2, int sim3_variant, const float* xform2, int32_t* best_idx, int32_t* best_dist,
                             int32_t* kf_matched_inout, int* nmatches, int device);
 
+typedef struct sgs_init_batch {           /* SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:407-522 */
+    sgs_camera cam;                       /* image bounds of F2 (its feature grid); intrinsics unused */
+    const sgs_keypoint* f1_kps; const uint8_t* f1_desc; const int32_t* f1_n; int32_t f1_cap;   /* reference frame: mvKeysUn, mDescriptors */
+    const sgs_keypoint* f2_kps; const uint8_t* f2_desc; const int32_t* f2_n; int32_t f2_cap;   /* current frame */
+    float* prev_xy;                       /* in/out [F][f1_cap][2]: vbPrevMatched (matched entries receive the matched keypoint's position) */
+    int32_t window_size; float nnratio; int32_t check_orientation;                             /* 100 / 0.9 / true at src/Tracking.cc:660-661 */
+    int32_t* match12;                     /* out [F][f1_cap]: vnMatches12 */
+    int32_t* nmatches;                    /* out [F] */
+} sgs_init_batch;
+SGS_API int sgs_search_for_initialization_batch_device(const sgs_init_batch* args, int nframes, void* stream);
+/* One pair from host memory (only n, keys_un, desc and the image bounds of the views are read). */
+SGS_API int sgs_search_for_initialization(const sgs_frame_view* f1, const sgs_frame_view* f2, float* prev_xy_inout, int window_size, float nnratio,
+                                          int check_orientation, int32_t* match12, int* nmatches, int device);
+
 typedef struct sgs_localmap_batch {       /* SearchByProjection(Frame&, vector<MapPoint*>&, th), src/ORBmatcher.cc:45 */
     sgs_camera cam;
     const sgs_keypoint* cur_kps; const uint8_t* cur_desc; const float* cur_uright; const int32_t* cur_n;

@@ -18,7 +18,7 @@
 //                                              SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)  src/ORBmatcher.cc:1106-1330
 //                                              SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12)         src/ORBmatcher.cc:524-657
 //                                              SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)  src/ORBmatcher.cc:659-827
-// Not mirrored: SearchForInitialization (monocular initialisation, never reached by the RGB-D system).
+//                                              SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)  src/ORBmatcher.cc:407-522
 #pragma once
 #include <cmath>
 #include <cstring>
@@ -160,6 +160,26 @@ public:
         check(sgs_match_bow(nkf, kn.data(), kw.data(), kv.data(), pKF->mDescriptors.template ptr<uint8_t>(), ka.data(), nf, fn.data(), fw.data(),
                             F.mDescriptors.template ptr<uint8_t>(), fa.data(), mfNNratio, mbCheckOrientation ? 1 : 0, m.data(), &nmatches, device_));
         for (int j = 0; j < nf; ++j) if (m[j] >= 0) vpMapPointMatches[j] = vpMapPointsKF[m[j]];
+        return nmatches;
+    }
+
+    // Matching for the Map Initialization (only used in the monocular case, Tracking::MonocularInitialization src/Tracking.cc:660-661).  src/ORBmatcher.cc:407-522
+    template <class FrameT, class PointT>
+    int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<PointT>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10) {
+        const int n1 = (int)F1.mvKeysUn.size();
+        vnMatches12 = std::vector<int>(n1, -1);
+        std::vector<float> scale(F2.mvScaleFactors.begin(), F2.mvScaleFactors.end());
+        sgs_frame_view v1 = view(F1, scale), v2 = view(F2, scale);
+        v1.n = n1; v2.n = (int)F2.mvKeysUn.size();
+        std::vector<float> prev(2 * (size_t)n1);
+        for (int i = 0; i < n1; ++i) { prev[2 * (size_t)i] = vbPrevMatched[i].x; prev[2 * (size_t)i + 1] = vbPrevMatched[i].y; }
+        std::vector<int32_t> m(n1, -1);
+        int nmatches = 0;
+        check(sgs_search_for_initialization(&v1, &v2, prev.data(), windowSize, mfNNratio, mbCheckOrientation ? 1 : 0, m.data(), &nmatches, device_));
+        for (int i = 0; i < n1; ++i) {
+            vnMatches12[i] = m[i];
+            if (m[i] >= 0) { vbPrevMatched[i].x = prev[2 * (size_t)i]; vbPrevMatched[i].y = prev[2 * (size_t)i + 1]; }
+        }
         return nmatches;
     }
 

@@ -443,6 +443,14 @@ def search_by_projection_sim3(kf, Tcw, Ow, mp_valid, mp_xyz, mp_normal, min_dist
     return nm, m
 
 
+def search_for_initialization(f1, f2, prev_xy, window_size=100, nnratio=0.9, check_ori=True):
+    """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:407-522): (nmatches, match12, updated vbPrevMatched)."""
+    p = np.ascontiguousarray(prev_xy, np.float32).reshape(-1, 2).copy()
+    m = np.zeros(f1.c.N, np.int32)
+    nm = lib().sgo_search_for_initialization(C.byref(f1.c), C.byref(f2.c), _p(p), int(window_size), C.c_float(nnratio), int(check_ori), _p(m))
+    return nm, m, p
+
+
 def distinctive_descriptor(desc):
     """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307): index of the representative descriptor among desc [n,32]."""
     d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)

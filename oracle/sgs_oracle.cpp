@@ -19,6 +19,7 @@
 // -ffp-contract=off so no FMA contraction can occur.
 // =====================================================================================
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -1105,6 +1106,59 @@ SGO_API int sgo_fuse_search(const SgoFrame* kf, const float* Tcw, const float* O
         if (bestIdx >= 0) nfound++;
     }
     return nfound;
+}
+
+// ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:407-522 (monocular
+// initialisation, Tracking::MonocularInitialization).  f1: mvKeysUn / mDescriptors of the reference frame; f2: the current frame with its grid.
+// prev_xy [n1][2] = vbPrevMatched (in/out: matched entries receive the matched keypoint's position, :517-519); match12 [n1] out.
+// The loop is order dependent: a feature of F2 keeps the best distance seen so far (vMatchedDistance) and a better later match steals it (:466-471).
+SGO_API int sgo_search_for_initialization(const SgoFrame* f1, const SgoFrame* f2, float* prev_xy, int window_size, float nnratio, int check_ori,
+                                          int32_t* match12) {
+    FrameView F1 = to_view(f1), F2 = to_view(f2); Grid g; build_grid(F2, g);
+    int nmatches = 0;
+    for (int i = 0; i < F1.N; i++) match12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = HISTO_LENGTH / 360.0f;
+    std::vector<int> vMatchedDistance(F2.N, INT_MAX), vnMatches21(F2.N, -1);
+    std::vector<int> cand;
+    for (int i1 = 0; i1 < F1.N; i1++) {
+        const int level1 = F1.keysUn[i1].octave;
+        if (level1 > 0) continue;
+        features_in_area(F2, g, prev_xy[2 * i1], prev_xy[2 * i1 + 1], (float)window_size, level1, level1, cand);
+        if (cand.empty()) continue;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int i2 : cand) {
+            const int dist = descriptor_distance(F1.desc + 32 * (size_t)i1, F2.desc + 32 * (size_t)i2);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { match12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                match12[i1] = bestIdx2; vnMatches21[bestIdx2] = i1; vMatchedDistance[bestIdx2] = bestDist; nmatches++;
+                if (check_ori) {
+                    float rot = F1.keysUn[i1].angle - F2.keysUn[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i])
+                if (match12[idx1] >= 0) { match12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < F1.N; i1++)
+        if (match12[i1] >= 0) { prev_xy[2 * i1] = F2.keysUn[match12[i1]].x; prev_xy[2 * i1 + 1] = F2.keysUn[match12[i1]].y; }
+    return nmatches;
 }
 
 // ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th),

@@ -73,7 +73,7 @@ __device__ void build_frame_grid(const MatchCam& cam, const sgs_keypoint* __rest
     // histogram (cell id kept in `order` temporarily is not needed: recomputed in the scatter pass)
     for (int i = tid; i < n; i += kMatchThreads) {
         const sgs_keypoint kp = kps[i];
-        s.kx[i] = kp.x; s.ky[i] = kp.y; s.oct[i] = (uint8_t)kp.octave; s.ur[i] = uright[i];
+        s.kx[i] = kp.x; s.ky[i] = kp.y; s.oct[i] = (uint8_t)kp.octave; s.ur[i] = uright ? uright[i] : -1.f;
         const int px = grid_round(__fmul_rn(__fsub_rn(kp.x, cam.min_x), w_inv));
         const int py = grid_round(__fmul_rn(__fsub_rn(kp.y, cam.min_y), h_inv));
         if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) atomicAdd(&s.cell_start[px * kGridRows + py + 1], 1);
@@ -730,6 +730,127 @@ int launch_fuse_search(const FuseArgs& A, int nframes, cudaStream_t st) {
     if (smem > 200 * 1024 || A.kf_cap > 65535) { set_error("fuse: kf_cap %d too large for shared memory", A.kf_cap); return SGS_ERR_UNSUPPORTED; }
     SGS_CUDA_TRY(cudaFuncSetAttribute(fuse_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fuse_search_kernel<<<nframes, kMatchThreads, smem, st>>>(A);
+    SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:407-522), one block per (F1, F2) pair.  The reference loop is order dependent (a feature of
+// F2 remembers the best distance that claimed it, a better later keypoint steals it), so the keypoints of F1 are visited one after the other; the
+// block shares the candidate scan of each: every thread folds its candidates into (best key, second-best distance), the pairs are merged with the
+// rule of the sequential update (strict <, first candidate in grid order wins ties), thread 0 applies :462-489.
+struct BestTwo { uint32_t best; uint32_t second; };      // best = dist << 16 | position in the grid order (kNoKey = none); second = distance (0xFFFFFFFF = none)
+__device__ __forceinline__ BestTwo merge_two(BestTwo a, BestTwo b) {
+    BestTwo r;
+    const uint32_t lo = min(a.best, b.best), hi = max(a.best, b.best);
+    r.best = lo;
+    r.second = min(min(a.second, b.second), hi == kNoKey ? 0xFFFFFFFFu : (hi >> 16));
+    return r;
+}
+
+__global__ void __launch_bounds__(kMatchThreads) search_init_kernel(const __grid_constant__ InitArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    FrameSmem s;
+    carve(smem, A.f2_cap, s);
+    int32_t* mdist = reinterpret_cast<int32_t*>(smem + frame_smem_bytes(A.f2_cap));      // vMatchedDistance
+    int32_t* m21 = mdist + A.f2_cap;                                                        // vnMatches21
+    int8_t* bin_of = reinterpret_cast<int8_t*>(m21 + A.f2_cap);                             // rotation bin a keypoint of F1 was pushed to, or -1
+    __shared__ int hist[kHistoLen];
+    __shared__ BestTwo s_part[kMatchThreads / 32];
+    __shared__ int s_nm;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n1 = min(A.f1_n[f], A.f1_cap), n2 = min(A.f2_n[f], A.f2_cap);
+    s.n = n2;
+    const sgs_keypoint* k1 = A.f1_kps + (int64_t)f * A.f1_cap;
+    const sgs_keypoint* k2 = A.f2_kps + (int64_t)f * A.f2_cap;
+    const uint4* d1 = reinterpret_cast<const uint4*>(A.f1_desc + (int64_t)f * A.f1_cap * 32);
+    const uint4* d2 = reinterpret_cast<const uint4*>(A.f2_desc + (int64_t)f * A.f2_cap * 32);
+    float* prev = A.prev_xy + (int64_t)f * A.f1_cap * 2;
+    int32_t* m12 = A.match12 + (int64_t)f * A.f1_cap;
+    build_frame_grid(A.cam, k2, nullptr, n2, s);
+    for (int i = tid; i < n2; i += kMatchThreads) { mdist[i] = 0x7fffffff; m21[i] = -1; }
+    for (int i = tid; i < A.f1_cap; i += kMatchThreads) { bin_of[i] = -1; m12[i] = -1; }
+    if (tid < kHistoLen) hist[tid] = 0;
+    if (tid == 0) s_nm = 0;
+    __syncthreads();
+    const float w_inv = __fdiv_rn((float)kGridCols, __fsub_rn(A.cam.max_x, A.cam.min_x));
+    const float h_inv = __fdiv_rn((float)kGridRows, __fsub_rn(A.cam.max_y, A.cam.min_y));
+    const float r = (float)A.window;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        if (k1[i1].octave > 0) continue;                                                    // level1 > 0 (:424-426), block-uniform
+        const float x = prev[2 * i1], y = prev[2 * i1 + 1];
+        // Frame::GetFeaturesInArea(x, y, windowSize, 0, 0) (src/Frame.cc:354-407)
+        const int min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, A.cam.min_x), r), w_inv)));
+        const int max_cx = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, A.cam.min_x), r), w_inv)));
+        const int min_cy = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, A.cam.min_y), r), h_inv)));
+        const int max_cy = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, A.cam.min_y), r), h_inv)));
+        if (min_cx >= kGridCols || max_cx < 0 || min_cy >= kGridRows || max_cy < 0) continue;
+        const uint4 a0 = __ldg(&d1[2 * i1]), a1 = __ldg(&d1[2 * i1 + 1]);
+        BestTwo t;
+        t.best = kNoKey; t.second = 0xFFFFFFFFu;
+        for (int ix = min_cx; ix <= max_cx; ++ix) {
+            const int beg = s.cell_start[ix * kGridRows + min_cy], end = s.cell_start[ix * kGridRows + max_cy + 1];
+            for (int j = beg + tid; j < end; j += kMatchThreads) {
+                const int idx = s.order[j];
+                if (s.oct[idx] > 0) continue;                                               // maxLevel = 0
+                if (!(fabsf(__fsub_rn(s.kx[idx], x)) < r && fabsf(__fsub_rn(s.ky[idx], y)) < r)) continue;
+                const uint32_t d = (uint32_t)popc256(a0, a1, __ldg(&d2[2 * idx]), __ldg(&d2[2 * idx + 1]));
+                if (mdist[idx] <= (int)d) continue;                                         // if(vMatchedDistance[i2]<=dist) continue;  (:447)
+                const uint32_t key = (d << 16) | (uint32_t)j;
+                if (key < t.best) { if (t.best != kNoKey) t.second = min(t.second, t.best >> 16); t.best = key; }
+                else t.second = min(t.second, d);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            BestTwo u;
+            u.best = __shfl_xor_sync(0xffffffffu, t.best, o); u.second = __shfl_xor_sync(0xffffffffu, t.second, o);
+            t = merge_two(t, u);
+        }
+        if ((tid & 31) == 0) s_part[tid >> 5] = t;
+        __syncthreads();
+        if (tid == 0) {
+            BestTwo b = s_part[0];
+            for (int w = 1; w < kMatchThreads / 32; ++w) b = merge_two(b, s_part[w]);
+            if (b.best != kNoKey) {
+                const int best_d = (int)(b.best >> 16), idx2 = s.order[b.best & 0xFFFFu];
+                const float second_f = b.second == 0xFFFFFFFFu ? 2147483648.f : (float)(int)b.second;     // (float)INT_MAX
+                if (best_d <= kThLow && (float)best_d < __fmul_rn(second_f, A.nnratio)) {
+                    if (m21[idx2] >= 0) { m12[m21[idx2]] = -1; s_nm = s_nm - 1; }
+                    m12[i1] = idx2; m21[idx2] = i1; mdist[idx2] = best_d; s_nm = s_nm + 1;
+                    if (A.check_ori) {
+                        float rot = __fsub_rn(k1[i1].angle, k2[idx2].angle);
+                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                        int bin = (int)roundf(__fmul_rn(rot, (float)kHistoLen / 360.0f));
+                        if (bin == kHistoLen) bin = 0;
+                        hist[bin] = hist[bin] + 1; bin_of[i1] = (int8_t)bin;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (A.check_ori) {
+        __shared__ int keep[3];
+        if (tid == 0) three_maxima(hist, keep[0], keep[1], keep[2]);
+        __syncthreads();
+        int removed = 0;
+        for (int i = tid; i < n1; i += kMatchThreads) {
+            const int b = bin_of[i];
+            if (b >= 0 && b != keep[0] && b != keep[1] && b != keep[2] && m12[i] >= 0) { m12[i] = -1; ++removed; }
+        }
+        if (removed) atomicSub(&s_nm, removed);
+        __syncthreads();
+    }
+    for (int i = tid; i < n1; i += kMatchThreads)
+        if (m12[i] >= 0) { prev[2 * i] = s.kx[m12[i]]; prev[2 * i + 1] = s.ky[m12[i]]; }     // :517-519
+    if (tid == 0 && A.nmatches) A.nmatches[f] = s_nm;
+}
+
+int launch_search_init(const InitArgs& A, int nframes, cudaStream_t st) {
+    const size_t smem = frame_smem_bytes(A.f2_cap) + (size_t)A.f2_cap * 8 + (size_t)((A.f1_cap + 15) & ~15);
+    if (smem > 200 * 1024 || A.f2_cap > 65535 || A.f1_cap > 65535) { set_error("search for initialisation: capacities %d / %d too large for shared memory", A.f1_cap, A.f2_cap); return SGS_ERR_UNSUPPORTED; }
+    SGS_CUDA_TRY(cudaFuncSetAttribute(search_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    search_init_kernel<<<nframes, kMatchThreads, smem, st>>>(A);
     SGS_CUDA_TRY(cudaGetLastError());
     return SGS_OK;
 }

@@ -280,6 +280,49 @@ SGS_API int sgs_fuse_search(const sgs_frame_view* kf, const float* tcw, const fl
     return SGS_OK;
 }
 
+SGS_API int sgs_search_for_initialization_batch_device(const sgs_init_batch* a, int nframes, void* stream) {
+    if (!a || !a->f1_kps || !a->f1_desc || !a->f1_n || !a->f2_kps || !a->f2_desc || !a->f2_n || !a->prev_xy || !a->match12 || nframes < 1 || a->f1_cap < 1 || a->f2_cap < 1 ||
+        a->window_size < 0 || !(a->cam.max_x > a->cam.min_x) || !(a->cam.max_y > a->cam.min_y)) { set_error("sgs_search_for_initialization_batch_device: bad argument"); return SGS_ERR_INVALID; }
+    InitArgs A;
+    A.cam = to_cam(a->cam);
+    A.f1_kps = a->f1_kps; A.f1_desc = a->f1_desc; A.f1_n = a->f1_n; A.f1_cap = a->f1_cap;
+    A.f2_kps = a->f2_kps; A.f2_desc = a->f2_desc; A.f2_n = a->f2_n; A.f2_cap = a->f2_cap;
+    A.prev_xy = a->prev_xy; A.window = a->window_size; A.nnratio = a->nnratio; A.check_ori = a->check_orientation; A.match12 = a->match12; A.nmatches = a->nmatches;
+    return launch_search_init(A, nframes, (cudaStream_t)stream);
+}
+
+SGS_API int sgs_search_for_initialization(const sgs_frame_view* f1, const sgs_frame_view* f2, float* prev_xy, int window_size, float nnratio, int check_orientation,
+                                          int32_t* match12, int* nmatches, int device) {
+    if (!f1 || !f2 || !nmatches || f1->n < 0 || f2->n < 0) { set_error("sgs_search_for_initialization: bad argument"); return SGS_ERR_INVALID; }
+    *nmatches = 0;
+    if (f1->n > 0 && match12) for (int i = 0; i < f1->n; ++i) match12[i] = -1;
+    if (f1->n == 0 || f2->n == 0) return SGS_OK;
+    if (!prev_xy || !match12 || !f1->keys_un || !f1->desc || !f2->keys_un || !f2->desc) { set_error("sgs_search_for_initialization: NULL array"); return SGS_ERR_INVALID; }
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    const size_t A1 = (size_t)f1->n, A2 = (size_t)f2->n;
+    const int32_t cnt[3] = {f1->n, f2->n, 0};
+    DevBuf k1, d1, k2, d2, c, pv, m;
+    SGS_CUDA_TRY(k1.upload(f1->keys_un, sizeof(sgs_keypoint) * A1)); SGS_CUDA_TRY(d1.upload(f1->desc, 32 * A1));
+    SGS_CUDA_TRY(k2.upload(f2->keys_un, sizeof(sgs_keypoint) * A2)); SGS_CUDA_TRY(d2.upload(f2->desc, 32 * A2));
+    SGS_CUDA_TRY(c.upload(cnt, 12)); SGS_CUDA_TRY(pv.upload(prev_xy, 8 * A1)); SGS_CUDA_TRY(m.alloc(4 * A1));
+    sgs_init_batch b;
+    std::memset(&b, 0, sizeof b);
+    b.cam = view_cam(f2);
+    b.f1_kps = k1.as<sgs_keypoint>(); b.f1_desc = d1.as<uint8_t>(); b.f1_n = c.as<int32_t>(); b.f1_cap = f1->n;
+    b.f2_kps = k2.as<sgs_keypoint>(); b.f2_desc = d2.as<uint8_t>(); b.f2_n = c.as<int32_t>() + 1; b.f2_cap = f2->n;
+    b.prev_xy = pv.as<float>(); b.window_size = window_size; b.nnratio = nnratio; b.check_orientation = check_orientation;
+    b.match12 = m.as<int32_t>(); b.nmatches = c.as<int32_t>() + 2;
+    const int rc = sgs_search_for_initialization_batch_device(&b, 1, nullptr);
+    if (rc != SGS_OK) return rc;
+    SGS_CUDA_TRY(cudaDeviceSynchronize());
+    SGS_CUDA_TRY(cudaMemcpy(match12, m.p, 4 * A1, cudaMemcpyDeviceToHost));
+    SGS_CUDA_TRY(cudaMemcpy(prev_xy, pv.p, 8 * A1, cudaMemcpyDeviceToHost));
+    int32_t nm = 0;
+    SGS_CUDA_TRY(cudaMemcpy(&nm, c.as<int32_t>() + 2, 4, cudaMemcpyDeviceToHost));
+    *nmatches = nm;
+    return SGS_OK;
+}
+
 SGS_API int sgs_match_bow_keyframes(int mode, int n1, const int32_t* node1, const double* weight1, const uint8_t* valid1, const uint8_t* desc1, const float* angle1,
                                     int n2, const int32_t* node2, const double* weight2, const uint8_t* valid2, const uint8_t* desc2, const float* angle2,
                                     float nnratio, int check_orientation, const uint8_t* stereo1, const uint8_t* stereo2, const float* xy1, const float* xy2,

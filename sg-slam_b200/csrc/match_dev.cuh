@@ -71,7 +71,17 @@ struct FuseArgs {                 // search half of ORBmatcher::Fuse(KeyFrame*, 
     int32_t* kf_matched; int32_t* nmatches;   // variant 3 (SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th), :292-405): vpMatched in/out [nframes][kf_cap], matches per frame
 };
 
+struct InitArgs {                 // ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:407-522
+    MatchCam cam;                 // image bounds of F2 (its feature grid)
+    const sgs_keypoint* f1_kps; const uint8_t* f1_desc; const int32_t* f1_n; int32_t f1_cap;
+    const sgs_keypoint* f2_kps; const uint8_t* f2_desc; const int32_t* f2_n; int32_t f2_cap;
+    float* prev_xy;               // in/out [nframes][f1_cap][2]
+    int32_t window; float nnratio; int32_t check_ori;
+    int32_t* match12; int32_t* nmatches;
+};
+
 int launch_match_lastframe(const LastFrameArgs& A, int nframes, cudaStream_t st);
+int launch_search_init(const InitArgs& A, int nframes, cudaStream_t st);
 int launch_fuse_search(const FuseArgs& A, int nframes, cudaStream_t st);
 int launch_match_localmap(const LocalMapArgs& A, int nframes, cudaStream_t st);
 

@@ -342,7 +342,34 @@ int main(int argc, char** argv) {
         size_t k = 0;
         for (int i = 0; i < nn[0]; ++i) if (e12[i] >= 0) { if (pairs[k].first != (size_t)i || pairs[k].second != (size_t)e12[i]) return fail("SearchForTriangulation: pairs"); ++k; }
     }
-    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges, %d detections (%d persons), %d sim3 matches, %d fused, %d Sim3 pairs, %d BoW pairs, %d triangulation pairs\n",
-                nkp, nm, kept, nd, nlk, nview, nfr, pin, npo, ndet, npers, nsim3, nfused, nsim3b, nbow2, ntri);
+    // 13. SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+    int ninit = -1;
+    if (argc >= 4) {
+        int32_t ih[3]; f.read(reinterpret_cast<char*>(ih), sizeof ih);
+        const int a1 = ih[0], a2 = ih[1], win = ih[2];
+        Frame I1, I2;
+        I1.N = a1; I1.mvKeysUn = rd<cv::KeyPoint>(f, a1); I1.mvuRight.assign(a1, -1.f);
+        std::vector<uint8_t> e1 = rd<uint8_t>(f, (size_t)a1 * 32);
+        I1.mDescriptors = cv::Mat(a1, 32, CV_8U, e1.data(), 32);
+        I2.N = a2; I2.mvKeysUn = rd<cv::KeyPoint>(f, a2); I2.mvuRight.assign(a2, -1.f);
+        std::vector<uint8_t> e2 = rd<uint8_t>(f, (size_t)a2 * 32);
+        I2.mDescriptors = cv::Mat(a2, 32, CV_8U, e2.data(), 32);
+        I1.mvScaleFactors = cur.mvScaleFactors; I2.mvScaleFactors = cur.mvScaleFactors;
+        std::vector<float> pin_ = rd<float>(f, (size_t)a1 * 2), pout = rd<float>(f, (size_t)a1 * 2);
+        int32_t nmi = 0; f.read(reinterpret_cast<char*>(&nmi), 4);
+        std::vector<int32_t> em = rd<int32_t>(f, a1);
+        std::vector<cv::Point2f> prevm(a1);
+        for (int i = 0; i < a1; ++i) { prevm[i].x = pin_[2 * (size_t)i]; prevm[i].y = pin_[2 * (size_t)i + 1]; }
+        std::vector<int> m12v;
+        ORBmatcher im(0.9f, true);
+        ninit = im.SearchForInitialization(I1, I2, prevm, m12v, win);
+        if (ninit != nmi || (int)m12v.size() != a1) return fail("SearchForInitialization: count");
+        for (int i = 0; i < a1; ++i) {
+            if (m12v[i] != em[i]) return fail("SearchForInitialization: vnMatches12");
+            if (prevm[i].x != pout[2 * (size_t)i] || prevm[i].y != pout[2 * (size_t)i + 1]) return fail("SearchForInitialization: vbPrevMatched");
+        }
+    }
+    std::printf("OK shim: %d keypoints, %d matches, %d/%d kept, %d LK tracks, F ok, %d/%d map points in view, pose optimised on %d/%d edges, %d detections (%d persons), %d sim3 matches, %d fused, %d Sim3 pairs, %d BoW pairs, %d triangulation pairs, %d initialisation matches\n",
+                nkp, nm, kept, nd, nlk, nview, nfr, pin, npo, ndet, npers, nsim3, nfused, nsim3b, nbow2, ntri, ninit);
     return 0;
 }

@@ -207,6 +207,13 @@ def test_shim_on_gpu(tmp_path):
             kk.tofile(f); ur[q].tofile(f); dsc.tofile(f); np.asarray(onode, np.int32).tofile(f); (np.asarray(oweight) > 0).astype(np.uint8).tofile(f); st[q].tofile(f)
         R2.tofile(f); t2.tofile(f); Cw.tofile(f); camv.tofile(f); F12.tofile(f); sig8.tofile(f); sf8.tofile(f)
         np.array([nm11], np.int32).tofile(f); m11.astype(np.int32).tofile(f); np.array([nm12], np.int32).tofile(f); m12.astype(np.int32).tofile(f)
+        # 13. SearchForInitialization through the class mirror
+        from test_match_init import init_scenario
+        isc = init_scenario(5)
+        inm, im12, iprev = O.search_for_initialization(isc['f1'], isc['f2'], isc['prev'], 100, 0.9, True)
+        assert inm > 40
+        np.array([len(isc['k1']), len(isc['k2']), 100], np.int32).tofile(f); isc['k1'].tofile(f); isc['d1'].tofile(f); isc['k2'].tofile(f); isc['d2'].tofile(f)
+        isc['prev'].astype(f32).tofile(f); iprev.astype(f32).tofile(f); np.array([inm], np.int32).tofile(f); im12.astype(np.int32).tofile(f)
     out = subprocess.run([exe, str(path), dpp, dbp], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'OK shim' in out.stdout

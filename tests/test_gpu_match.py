@@ -287,6 +287,49 @@ def test_search_by_projection_sim3(seed, ncur, nmp, th):
         B.check(B.lib().sgs_fuse_search_batch_device(C.byref(a), 2, C.c_void_p(0)))
 
 
+@pytest.mark.parametrize('window,ori', [(100, True), (100, False), (40, True)])
+def test_search_for_initialization(window, ori):
+    """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:407-522): order-dependent distance book-keeping, two pairs per call + the host entry point."""
+    import ctypes as C
+    import torch
+    from test_match_init import init_scenario
+    sc = [init_scenario(seed) for seed in (1, 2)]
+    ref = [O.search_for_initialization(s['f1'], s['f2'], s['prev'], window, 0.9, ori) for s in sc]
+    assert all(r[0] > 40 for r in ref)
+    n1, n2 = len(sc[0]['k1']), len(sc[0]['k2'])
+    c1, c2 = n1 + 7, n2 + 5
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    pad = lambda a, cap: np.concatenate([a, np.zeros((cap - len(a),) + a.shape[1:], a.dtype)])
+    t_ = dict(k1=dev(np.stack([pad(s['k1'], c1) for s in sc]).view(np.uint8).reshape(-1)), d1=dev(np.stack([pad(s['d1'], c1) for s in sc])),
+              k2=dev(np.stack([pad(s['k2'], c2) for s in sc]).view(np.uint8).reshape(-1)), d2=dev(np.stack([pad(s['d2'], c2) for s in sc])),
+              n1=dev(np.array([n1, n1], np.int32)), n2=dev(np.array([n2, n2], np.int32)), prev=dev(np.stack([pad(s['prev'], c1) for s in sc])))
+    m = torch.zeros((2, c1), dtype=torch.int32, device='cuda'); nm = torch.zeros(2, dtype=torch.int32, device='cuda')
+    a = B.InitBatch()
+    a.cam = B.make_camera(640, 480, sc[0]['cam'], sc[0]['sf'])
+    a.f1_kps, a.f1_desc, a.f1_n, a.f1_cap = t_['k1'].data_ptr(), t_['d1'].data_ptr(), t_['n1'].data_ptr(), c1
+    a.f2_kps, a.f2_desc, a.f2_n, a.f2_cap = t_['k2'].data_ptr(), t_['d2'].data_ptr(), t_['n2'].data_ptr(), c2
+    a.prev_xy, a.window_size, a.nnratio, a.check_orientation, a.match12, a.nmatches = t_['prev'].data_ptr(), window, 0.9, int(ori), m.data_ptr(), nm.data_ptr()
+    B.check(B.lib().sgs_search_for_initialization_batch_device(C.byref(a), 2, C.c_void_p(0)))
+    torch.cuda.synchronize()
+    mh = m.cpu().numpy(); ph = t_['prev'].cpu().numpy()
+    for k, (nm_o, m_o, p_o) in enumerate(ref):
+        assert int(nm[k].item()) == nm_o and np.array_equal(mh[k, :n1], m_o) and (mh[k, n1:] == -1).all()
+        assert np.array_equal(ph[k, :n1], p_o)
+    # host entry point on the first pair
+    s = sc[0]
+    sf = np.ascontiguousarray(s['sf'], np.float32)
+    def view(k, d):
+        v = B.FrameView(); v.n = len(k); v.keys_un = k.ctypes.data; v.u_right = None; v.desc = d.ctypes.data
+        v.min_x, v.min_y, v.max_x, v.max_y = 0.0, 0.0, 640.0, 480.0
+        v.nlevels = 8; v.scale_factors = sf.ctypes.data
+        return v
+    k1 = np.ascontiguousarray(s['k1']); k2 = np.ascontiguousarray(s['k2']); d1 = np.ascontiguousarray(s['d1']); d2 = np.ascontiguousarray(s['d2'])
+    v1, v2 = view(k1, d1), view(k2, d2)
+    prev = s['prev'].copy(); mo = np.zeros(n1, np.int32); nmo = C.c_int()
+    B.check(B.lib().sgs_search_for_initialization(C.byref(v1), C.byref(v2), prev.ctypes.data_as(C.c_void_p), window, C.c_float(0.9), int(ori), mo.ctypes.data_as(C.c_void_p), C.byref(nmo), 0))
+    assert nmo.value == ref[0][0] and np.array_equal(mo, ref[0][1]) and np.array_equal(prev, ref[0][2])
+
+
 def test_distinctive_descriptor_batch():
     """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307): median-of-distances representative, first minimum wins."""
     import ctypes as C
