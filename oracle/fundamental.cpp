@@ -211,6 +211,17 @@ bool have_collinear(const float* m, int count) {      // fundam.cpp haveCollinea
     return false;
 }
 
+void compute_errors(const float* m1, const float* m2, int n, const double* F, float* err) {      // FMEstimatorCallback::computeError
+    for (int i = 0; i < n; i++) {
+        const double x1 = m1[2 * i], y1 = m1[2 * i + 1], x2 = m2[2 * i], y2 = m2[2 * i + 1];
+        double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+        const double s2 = 1. / (a * a + b * b), d2 = x2 * a + y2 * b + c;
+        a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8];
+        const double s1 = 1. / (a * a + b * b), d1 = x1 * a + y1 * b + c;
+        err[i] = (float)std::max(d1 * d1 * s1, d2 * d2 * s2);
+    }
+}
+
 int find_inliers(const float* m1, const float* m2, int n, const double* F, float t, uint8_t* mask) {
     int nz = 0;
     for (int i = 0; i < n; i++) {
@@ -242,9 +253,52 @@ SGO_API int sgo_run7point(const float* m1, const float* m2, double* F27) { retur
 SGO_API int sgo_find_fundamental_ransac(const float* m1, const float* m2, int n, double thresh, double confidence, int max_iters, double* F,
                                         uint8_t* mask_out, int32_t* info) {
     if (info) info[0] = info[1] = info[2] = 0;
-    if (n < 15) return 0;
     if (thresh <= 0) thresh = 3;
     if (confidence < DBL_EPSILON || confidence > 1 - DBL_EPSILON) confidence = 0.99;
+    if (n < 15) {
+        // fundam.cpp cv::findFundamentalMat: fewer than 15 pairs never reach RANSAC.  < 7: empty; == 7: the 7-point solver directly (up to three
+        // stacked solutions -- not provided here: 0 is returned); 8..14: LMeDSPointSetRegistrator(cb, 7, confidence).run (ptsetreg.cpp), maxIters = 1000:
+        // a fixed number of samples (outlier ratio 0.45), the model with the smallest median error (element count/2 of the sorted errors), inliers
+        // within sigma = 2.5 * 1.4826 * (1 + 5 / (count - 7)) * sqrt(median); the result is dropped when fewer than 7 pairs are inliers.
+        if (n <= 7) return 0;
+        CvRng rng((uint64_t)-1);
+        const int niters = std::max(update_num_iters(confidence, 0.45, 7, 1000), 3);
+        double min_median = DBL_MAX, best[9], models[27];
+        float ms1[14], ms2[14];
+        std::vector<float> err(n);
+        int iter = 0;
+        for (iter = 0; iter < niters; iter++) {
+            bool found = false;
+            for (int attempt = 0; attempt < 10000 && !found; attempt++) {
+                int idx[7];
+                for (int i = 0; i < 7; i++) {
+                    int v;
+                    for (v = rng.uniform(0, n); std::find(idx, idx + i, v) != idx + i; v = rng.uniform(0, n)) {}
+                    idx[i] = v;
+                    ms1[2 * i] = m1[2 * v]; ms1[2 * i + 1] = m1[2 * v + 1]; ms2[2 * i] = m2[2 * v]; ms2[2 * i + 1] = m2[2 * v + 1];
+                }
+                found = !have_collinear(ms1, 7) && !have_collinear(ms2, 7);
+            }
+            if (!found) { if (iter == 0) return 0; break; }
+            const int nmodels = run7point(ms1, ms2, models);
+            for (int k = 0; k < nmodels; k++) {
+                compute_errors(m1, m2, n, models + 9 * k, err.data());
+                std::nth_element(err.begin(), err.begin() + n / 2, err.end());
+                const double median = err[n / 2];
+                if (median < min_median) { min_median = median; std::memcpy(best, models + 9 * k, sizeof(best)); }
+            }
+        }
+        if (!(min_median < DBL_MAX)) return 0;
+        double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 7)) * std::sqrt(min_median);
+        sigma = std::max(sigma, 0.001);
+        std::vector<uint8_t> mask(n);
+        const int good = find_inliers(m1, m2, n, best, (float)(sigma * sigma), mask.data());
+        if (info) { info[0] = iter; info[1] = good; info[2] = niters; }
+        if (good < 7) return 0;
+        std::memcpy(F, best, sizeof(best));
+        if (mask_out) std::memcpy(mask_out, mask.data(), n);
+        return 1;
+    }
     CvRng rng((uint64_t)-1);
     int niters = std::max(max_iters, 1), max_good = 0, iter = 0;
     const float t = (float)(thresh * thresh);

@@ -296,11 +296,15 @@ def run7point(m1, m2):
     return [F[9 * k:9 * k + 9].reshape(3, 3).copy() for k in range(max(n, 0))]
 
 
-def find_fundamental_ransac(pts1, pts2, thresh=1.0, confidence=0.99, max_iters=1000):
+def find_fundamental_ransac(pts1, pts2, thresh=1.0, confidence=0.99, max_iters=1000, small_sample=False):
     """cv::findFundamentalMat(pts1, pts2, FM_RANSAC, thresh, confidence) (src/Frame.cc:469-472).
-    Returns (F 3x3 float64 or None, mask uint8 [n], info int32 [3] = iterations run, inliers, final niters)."""
+    Returns (F 3x3 float64 or None, mask uint8 [n], info int32 [3] = iterations run, inliers, final niters).
+    With fewer than 15 pairs OpenCV does not run RANSAC: by default None is returned (what the product's kernel reports as "empty F");
+    small_sample=True evaluates OpenCV's LMedS branch for 8..14 pairs (pinned for 14, numerically arbitrary below -- see tests/test_fundamental.py)."""
     a = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2); b = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
     F = np.zeros(9, np.float64); mask = np.zeros(len(a), np.uint8); info = np.zeros(3, np.int32)
+    if len(a) < 15 and not small_sample:
+        return None, mask, info
     fn = lib().sgo_find_fundamental_ransac
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
