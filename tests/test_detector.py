@@ -89,6 +89,25 @@ def test_plan_fuses_elementwise_tails(tmp_path):
     assert sum(l.startswith('eltwise') for l in txt2.splitlines()) >= 20
 
 
+def test_folded_prior_boxes_match_the_oracle_bitwise(tmp_path):
+    """The product folds PriorBox + Concat on the host at create time; in plan-only diagnostic mode the constant is readable without a device."""
+    pp, bp = DM.write_mini_model(str(tmp_path), 0)
+    layers = NM.parse_param(pp); NM.load_weights(layers, bp)
+    ref = DO.forward(layers, DO.preprocess(DM.synthetic_rgb(480, 640, 1)), want='mbox_priorbox')['mbox_priorbox']
+    d = B.Detector(pp, bp, max_frames=1, flags=B.DET_DIAGNOSTIC | B.DET_PLAN_ONLY)
+    got = d.blob('mbox_priorbox')
+    d.close()
+    assert got.tobytes() == np.ascontiguousarray(ref, np.float32).tobytes()
+    if os.path.exists(REAL + '.param'):
+        layers = NM.parse_param(REAL + '.param'); NM.load_weights(layers, REAL + '.bin')
+        pri = [DO.prior_boxes(L, fw, fw, 300, 300) for L, fw in zip([l for l in layers if l.type == 'PriorBox'], (19, 10, 5, 3, 2, 1))]
+        ref = np.concatenate(pri, axis=1)
+        d = B.Detector(REAL + '.param', REAL + '.bin', max_frames=1, flags=B.DET_DIAGNOSTIC | B.DET_PLAN_ONLY)
+        got = d.blob('mbox_priorbox')
+        d.close()
+        assert got.size == 2 * 9072 and got.tobytes() == np.ascontiguousarray(ref, np.float32).tobytes()
+
+
 def test_create_reports_bad_files(tmp_path):
     pp, bp = DM.write_mini_model(str(tmp_path), 0)
     with pytest.raises(B.SgsError) as e:

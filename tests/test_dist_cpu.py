@@ -43,3 +43,19 @@ def test_two_rank_gloo_sharding_and_broadcast():
     import bench
     f0, _, _ = bench.make_frames(6, seed=2, unique=3)
     assert int(f0.astype(np.uint64).sum()) == s0[0]
+
+
+def test_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference: the CPU port of the path on the host cores, ONE JSON line on stdout with the contract's keys (no GPU involved)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'frames/s' and d['value'] > 0 and d['n_gpus'] == 1 and d['higher_is_better'] is True
+    assert d['cpu_baseline']['kind'] in ('port', 'reference') and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
