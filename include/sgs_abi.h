@@ -326,6 +326,13 @@ typedef struct sgs_vocabulary sgs_vocabulary;
 SGS_API int sgs_vocabulary_create(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* node_desc,
                                   const double* node_weight, sgs_vocabulary** out);
 SGS_API void sgs_vocabulary_destroy(sgs_vocabulary* v);
+/* Vocabulary files of the reference: ORBVocabulary::loadFromTextFile / loadFromBinaryFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1351-1420,
+ * :1467-1508); like src/System.cc:69-73 a ".txt" suffix selects the text reader.  sgs_vocabulary_parse_file fills the flat arrays sgs_vocabulary_create
+ * takes (nnodes counts the implicit root = node 0; all arrays NULL = size query; SGS_ERR_CAPACITY when cap < nnodes) -- what rank 0 broadcasts in a
+ * multi-GPU job; sgs_vocabulary_load = parse + create. */
+SGS_API int sgs_vocabulary_parse_file(const char* path, int* k, int* L, int* nnodes, int32_t* parent, uint8_t* node_desc, double* node_weight,
+                                      uint8_t* is_leaf, int cap);
+SGS_API int sgs_vocabulary_load(const char* path, int device, sgs_vocabulary** out);
 SGS_API int sgs_bow_transform_batch_device(const sgs_vocabulary* v, const uint8_t* d_desc, const int32_t* d_counts, int cap, int nframes,
                                            int levelsup, int32_t* d_word, double* d_weight, int32_t* d_node, void* stream);
 typedef struct sgs_bow_batch {

@@ -10,6 +10,9 @@
 //       over the frame features of the bucket; best / second-best by two warp reductions.  Rotation histogram as in the other matchers.
 // Integer work: bit-exact against the CPU restatement.
 #include <cuda_runtime.h>
+#include <string>
+#include <cstdlib>
+#include <cstdio>
 
 #include <cstring>
 #include <vector>
@@ -300,6 +303,94 @@ SGS_API int sgs_vocabulary_create(int device, int k, int L, int nnodes, const in
     if (e != cudaSuccess) { set_error("sgs_vocabulary_create: %s", cudaGetErrorString(e)); sgs_vocabulary_destroy(v); return SGS_ERR_CUDA; }
     *out = v;
     return SGS_OK;
+}
+
+// ---- vocabulary files: ORBVocabulary::loadFromTextFile / loadFromBinaryFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1351-1420, :1467-1508).
+// Text: first line "k L scoring weighting", then one line per node in node-id order (the root is implicit): "parent isLeaf d0 ... d31 weight".
+// Binary: uint32 nb_nodes, uint32 size_node (= 41), int k, int L, int scoring, int weighting, then nb_nodes records
+// { int32 parent; uint8 descriptor[32]; float weight; uint8 is_leaf }.  src/System.cc:69-73 picks the text reader for a ".txt" suffix.
+// Blank lines of a text file are skipped (the reference's eof() loop turns a trailing newline into one undefined extra node).
+namespace {
+struct VocFile { int k = 0, L = 0; std::vector<int32_t> parent; std::vector<uint8_t> desc, leaf; std::vector<double> weight; };
+
+int parse_vocabulary_file(const char* path, VocFile& V) {
+    const std::string p(path);
+    const bool text = p.size() >= 4 && p.compare(p.size() - 4, 4, ".txt") == 0;
+    FILE* f = std::fopen(path, text ? "r" : "rb");
+    if (!f) { set_error("vocabulary: cannot open %s", path); return SGS_ERR_INVALID; }
+    struct Closer { FILE* f; ~Closer() { std::fclose(f); } } closer{f};
+    V.parent.assign(1, -1); V.desc.assign(32, 0); V.leaf.assign(1, 0); V.weight.assign(1, 0.0);       // node 0 = root
+    if (text) {
+        int n1 = 0, n2 = 0;
+        if (std::fscanf(f, "%d %d %d %d", &V.k, &V.L, &n1, &n2) != 4 || V.k < 0 || V.k > 20 || V.L < 1 || V.L > 10 || n1 < 0 || n1 > 5 || n2 < 0 || n2 > 3) {
+            set_error("vocabulary: %s is not a DBoW2 text vocabulary", path); return SGS_ERR_INVALID; }
+        std::vector<char> line(1 << 12);
+        if (!std::fgets(line.data(), (int)line.size(), f)) return SGS_OK;            // rest of the header line
+        while (std::fgets(line.data(), (int)line.size(), f)) {
+            char* c = line.data();
+            while (*c == ' ' || *c == '\t') ++c;
+            if (*c == '\n' || *c == '\r' || *c == 0) continue;
+            char* e = nullptr;
+            const long pid = std::strtol(c, &e, 10); c = e;
+            const long isleaf = std::strtol(c, &e, 10); c = e;
+            const size_t nid = V.parent.size();
+            if (pid < 0 || (size_t)pid >= nid) { set_error("vocabulary: %s: node %zu names parent %ld", path, nid, pid); return SGS_ERR_INVALID; }
+            V.parent.push_back((int32_t)pid); V.leaf.push_back(isleaf > 0 ? 1 : 0);
+            for (int i = 0; i < 32; ++i) { const long v = std::strtol(c, &e, 10); if (e == c) { set_error("vocabulary: %s: node %zu has a short descriptor", path, nid); return SGS_ERR_INVALID; } c = e; V.desc.push_back((uint8_t)v); }
+            V.weight.push_back(std::strtod(c, &e));
+        }
+    } else {
+        uint32_t nb = 0, sz = 0; int32_t hdr[4];
+        if (std::fread(&nb, 4, 1, f) != 1 || std::fread(&sz, 4, 1, f) != 1 || std::fread(hdr, 4, 4, f) != 4 || sz != 41 || hdr[0] < 2 || hdr[0] > 20 || hdr[1] < 1 || hdr[1] > 10) {
+            set_error("vocabulary: %s is not a DBoW2 binary vocabulary (41-byte nodes)", path); return SGS_ERR_INVALID; }
+        V.k = hdr[0]; V.L = hdr[1];
+        std::vector<uint8_t> buf((size_t)nb * 41);
+        if (std::fread(buf.data(), 41, nb, f) != nb) { set_error("vocabulary: %s is truncated", path); return SGS_ERR_INVALID; }
+        V.parent.reserve(nb + 1); V.desc.reserve(32 * ((size_t)nb + 1)); V.leaf.reserve(nb + 1); V.weight.reserve(nb + 1);
+        for (uint32_t i = 0; i < nb; ++i) {
+            const uint8_t* r = buf.data() + (size_t)i * 41;
+            int32_t pid; float w;
+            std::memcpy(&pid, r, 4); std::memcpy(&w, r + 36, 4);
+            if (pid < 0 || (uint32_t)pid > i) { set_error("vocabulary: %s: node %u names parent %d", path, i + 1, pid); return SGS_ERR_INVALID; }
+            V.parent.push_back(pid); V.desc.insert(V.desc.end(), r + 4, r + 36); V.weight.push_back((double)w); V.leaf.push_back(r[40] ? 1 : 0);
+        }
+    }
+    if (V.parent.size() < 2) { set_error("vocabulary: %s holds no nodes", path); return SGS_ERR_INVALID; }
+    return SGS_OK;
+}
+}  // namespace
+
+SGS_API int sgs_vocabulary_parse_file(const char* path, int* k, int* L, int* nnodes, int32_t* parent, uint8_t* node_desc, double* node_weight, uint8_t* is_leaf,
+                                      int cap) {
+    if (!path || !nnodes) { set_error("sgs_vocabulary_parse_file: bad argument"); return SGS_ERR_INVALID; }
+    VocFile V;
+    const int rc = parse_vocabulary_file(path, V);
+    if (rc != SGS_OK) return rc;
+    const int n = (int)V.parent.size();
+    if (k) *k = V.k;
+    if (L) *L = V.L;
+    *nnodes = n;
+    if (!parent && !node_desc && !node_weight && !is_leaf) return SGS_OK;                     // size query
+    if (cap < n) { set_error("sgs_vocabulary_parse_file: %d nodes, capacity %d", n, cap); return SGS_ERR_CAPACITY; }
+    if (parent) std::memcpy(parent, V.parent.data(), 4 * (size_t)n);
+    if (node_desc) std::memcpy(node_desc, V.desc.data(), 32 * (size_t)n);
+    if (node_weight) std::memcpy(node_weight, V.weight.data(), 8 * (size_t)n);
+    if (is_leaf) std::memcpy(is_leaf, V.leaf.data(), (size_t)n);
+    return SGS_OK;
+}
+
+SGS_API int sgs_vocabulary_load(const char* path, int device, sgs_vocabulary** out) {
+    if (!path || !out) { set_error("sgs_vocabulary_load: bad argument"); return SGS_ERR_INVALID; }
+    *out = nullptr;
+    VocFile V;
+    const int rc = parse_vocabulary_file(path, V);
+    if (rc != SGS_OK) return rc;
+    const int n = (int)V.parent.size();
+    std::vector<int> nchild(n, 0);
+    for (int i = 1; i < n; ++i) nchild[V.parent[i]]++;
+    for (int i = 1; i < n; ++i)
+        if ((nchild[i] == 0) != (V.leaf[i] != 0)) { set_error("sgs_vocabulary_load: %s: node %d is flagged %s but has %d children", path, i, V.leaf[i] ? "leaf" : "inner", nchild[i]); return SGS_ERR_UNSUPPORTED; }
+    return sgs_vocabulary_create(device, V.k, V.L, n, V.parent.data(), V.desc.data(), V.weight.data(), out);
 }
 
 SGS_API int sgs_bow_transform_batch_device(const sgs_vocabulary* v, const uint8_t* d_desc, const int32_t* d_counts, int cap, int nframes, int levelsup,

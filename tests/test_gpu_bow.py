@@ -212,3 +212,28 @@ def test_search_for_triangulation(seed, only_stereo):
                 assert np.all(st1[sel] == 1) and np.all(st2[om[sel]] == 1)
     finally:
         gv.close()
+
+
+def test_vocabulary_loaded_from_files(tmp_path):
+    """sgs_vocabulary_load (text and binary files of the reference's formats) gives the same transform as the tree built from arrays and as the oracle."""
+    from test_vocabulary_files import write_binary, write_text
+    voc = S.random_vocabulary(23, k=7, L=3)
+    voc['weight'] = voc['weight'].astype(np.float32).astype(np.float64)          # representable in the binary format, so that both files hold the same tree
+    V = O.Vocabulary(voc['k'], voc['L'], voc['parent'], voc['desc'], voc['weight'])
+    write_text(tmp_path / 'v.txt', voc); write_binary(tmp_path / 'v.bin', voc)
+    rs = np.random.RandomState(4)
+    leaves = np.nonzero(voc['weight'] > 0)[0]
+    d = voc['desc'][leaves[rs.randint(0, len(leaves), 500)]].copy()
+    d[rs.rand(500) < 0.5, rs.randint(0, 32)] ^= 0x15
+    ow, oweight, onode = V.transform(d, 1)
+    v = C.c_void_p
+    for name in ('v.txt', 'v.bin'):
+        h = C.c_void_p()
+        B.check(B.lib().sgs_vocabulary_load(str(tmp_path / name).encode(), 0, C.byref(h)))
+        word = np.zeros(500, np.int32); w = np.zeros(500, np.float64); node = np.zeros(500, np.int32)
+        B.check(B.lib().sgs_bow_transform(h, np.ascontiguousarray(d).ctypes.data_as(v), 500, 1, word.ctypes.data_as(v), w.ctypes.data_as(v), node.ctypes.data_as(v)))
+        B.lib().sgs_vocabulary_destroy(h)
+        assert np.array_equal(word, ow) and np.array_equal(w, oweight) and np.array_equal(node, onode), name
+    with pytest.raises(B.SgsError):
+        h = C.c_void_p()
+        B.check(B.lib().sgs_vocabulary_load(str(tmp_path / 'missing.txt').encode(), 0, C.byref(h)))
