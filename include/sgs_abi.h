@@ -312,6 +312,21 @@ SGS_API int sgs_pose_optimization(const sgs_camera* cam, const float* tcw_in, in
                                   int* ninliers, int device);
 
 /* ------------------------------------------------------------------------------------
+ * Settings file of the reference (Examples/TUM*.yaml, OpenCV FileStorage "%YAML:1.0" with flat `key: value` lines): the keys the hot path reads
+ * at src/Tracking.cc:53-147 (camera, ORB extractor, depth) and src/System.cc:160-162 (detector thresholds).  A missing key reads as 0, like an
+ * empty cv::FileNode converted to a number.  Host code, no device involved.
+ * ------------------------------------------------------------------------------------ */
+typedef struct sgs_settings {
+    float fx, fy, cx, cy, k1, k2, p1, p2, k3, bf, fps;   /* Camera.* (Tracking.cc:54-81) */
+    int32_t width, height, rgb;                            /* Camera.width / height / RGB */
+    float th_depth;                                        /* mThDepth = bf * ThDepth / fx (Tracking.cc:136) */
+    float depth_map_factor;                                /* mDepthMapFactor = 1 / DepthMapFactor, or 1 when |DepthMapFactor| < 1e-5 (:142-146) */
+    sgs_orb_params orb;                                    /* ORBextractor.* (:113-117) */
+    float detection_confidence_threshold, dynamic_detection_confidence_threshold;   /* Detector2D.* (System.cc:160-162) */
+} sgs_settings;
+SGS_API int sgs_settings_load(const char* path, sgs_settings* out);
+
+/* ------------------------------------------------------------------------------------
  * Bag of words (tracking fallback, Tracking::TrackReferenceKeyFrame src/Tracking.cc:858-904):
  *   sgs_vocabulary_create       : the DBoW2 tree as flat arrays -- parent[i] of node i in node-id order (node 0 = root; DBoW2 appends children
  *                                 to their parent in that order, TemplatedVocabulary.h:1351-1420 / 1467-1508), node descriptors [nnodes][32],

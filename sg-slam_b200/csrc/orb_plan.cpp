@@ -2,6 +2,10 @@
 // circular-patch row extents, level geometry, the FAST cell table and the fixed-point bilinear tables.
 // Semantics follow ORBextractor::ORBextractor (src/ORBextractor.cc:411-471), ComputePyramid (:1108-1133) and the
 // cell loop of ComputeKeyPointsOctTree (:766-830); arithmetic types are reproduced exactly (float vs double).
+#include <cstdio>
+#include <string>
+#include <cstdlib>
+#include <map>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -153,3 +157,49 @@ int make_plan(const sgs_orb_params& p, int width, int height, OrbPlan* plan) {
 }
 
 }  // namespace sgs
+
+// ---- settings file (Examples/TUM*.yaml): flat "key: value" lines of an OpenCV FileStorage YAML document
+extern "C" SGS_API int sgs_settings_load(const char* path, sgs_settings* out) {
+    using sgs::set_error;
+    if (!path || !out) { set_error("sgs_settings_load: bad argument"); return SGS_ERR_INVALID; }
+    FILE* f = std::fopen(path, "r");
+    if (!f) { set_error("sgs_settings_load: cannot open %s", path); return SGS_ERR_INVALID; }
+    std::map<std::string, double> kv;
+    char line[1024];
+    bool first = true, yaml = false;
+    while (std::fgets(line, sizeof line, f)) {
+        std::string s(line);
+        if (first) { first = false; if (s.compare(0, 5, "%YAML") == 0) { yaml = true; continue; } }
+        const size_t hash = s.find('#');
+        if (hash != std::string::npos) s.erase(hash);
+        const size_t colon = s.find(':');
+        if (colon == std::string::npos) continue;
+        std::string key = s.substr(0, colon), val = s.substr(colon + 1);
+        auto trim = [](std::string& t) { const char* ws = " \t\r\n\""; t.erase(0, t.find_first_not_of(ws)); const size_t e = t.find_last_not_of(ws); t.erase(e == std::string::npos ? 0 : e + 1); };
+        trim(key); trim(val);
+        if (key.empty() || val.empty()) continue;
+        char* end = nullptr;
+        const double v = std::strtod(val.c_str(), &end);
+        if (end != val.c_str()) kv[key] = v;
+    }
+    std::fclose(f);
+    if (!yaml) { set_error("sgs_settings_load: %s does not start with %%YAML", path); return SGS_ERR_INVALID; }
+    auto get = [&](const char* k) -> double { auto it = kv.find(k); return it == kv.end() ? 0.0 : it->second; };
+    sgs_settings S;
+    std::memset(&S, 0, sizeof S);
+    S.fx = (float)get("Camera.fx"); S.fy = (float)get("Camera.fy"); S.cx = (float)get("Camera.cx"); S.cy = (float)get("Camera.cy");
+    S.k1 = (float)get("Camera.k1"); S.k2 = (float)get("Camera.k2"); S.p1 = (float)get("Camera.p1"); S.p2 = (float)get("Camera.p2"); S.k3 = (float)get("Camera.k3");
+    S.bf = (float)get("Camera.bf"); S.fps = (float)get("Camera.fps");
+    S.width = (int32_t)get("Camera.width"); S.height = (int32_t)get("Camera.height"); S.rgb = (int32_t)get("Camera.RGB");
+    if (!(S.fx != 0.f)) { set_error("sgs_settings_load: %s has no Camera.fx", path); return SGS_ERR_INVALID; }
+    S.th_depth = S.bf * (float)get("ThDepth") / S.fx;
+    const float dmf = (float)get("DepthMapFactor");
+    S.depth_map_factor = std::fabs(dmf) < 1e-5 ? 1.f : 1.0f / dmf;
+    S.orb.nfeatures = (int32_t)get("ORBextractor.nFeatures"); S.orb.scale_factor = (float)get("ORBextractor.scaleFactor"); S.orb.nlevels = (int32_t)get("ORBextractor.nLevels");
+    S.orb.ini_th_fast = (int32_t)get("ORBextractor.iniThFAST"); S.orb.min_th_fast = (int32_t)get("ORBextractor.minThFAST");
+    S.detection_confidence_threshold = (float)get("Detector2D.detection_confidence_threshold");
+    S.dynamic_detection_confidence_threshold = (float)get("Detector2D.dynamic_detection_confidence_threshold");
+    *out = S;
+    return SGS_OK;
+}
+

@@ -30,6 +30,12 @@ class OrbParams(C.Structure):
                 ('ini_th_fast', C.c_int32), ('min_th_fast', C.c_int32)]
 
 
+class Settings(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ('fx', 'fy', 'cx', 'cy', 'k1', 'k2', 'p1', 'p2', 'k3', 'bf', 'fps')] + [('width', C.c_int32), ('height', C.c_int32), ('rgb', C.c_int32),
+                ('th_depth', C.c_float), ('depth_map_factor', C.c_float), ('orb', OrbParams), ('detection_confidence_threshold', C.c_float),
+                ('dynamic_detection_confidence_threshold', C.c_float)]
+
+
 class FrameView(C.Structure):
     _fields_ = [('n', C.c_int32), ('keys_un', C.c_void_p), ('u_right', C.c_void_p), ('desc', C.c_void_p),
                 ('min_x', C.c_float), ('min_y', C.c_float), ('max_x', C.c_float), ('max_y', C.c_float),
@@ -96,7 +102,7 @@ class LocalMapBatch(C.Structure):
 
 
 ABI_SYMBOLS = [
-    'sgs_abi_version', 'sgs_last_error', 'sgs_device_count',
+    'sgs_abi_version', 'sgs_last_error', 'sgs_device_count', 'sgs_settings_load',
     'sgs_extractor_create', 'sgs_extractor_destroy', 'sgs_extractor_tables', 'sgs_extractor_max_keypoints', 'sgs_extractor_level_info',
     'sgs_extract', 'sgs_extract_batch', 'sgs_extract_batch_device', 'sgs_extractor_results_device', 'sgs_extractor_fetch', 'sgs_extractor_read_level',
     'sgs_extractor_read_candidates',
