@@ -934,9 +934,9 @@ int build_graph(sgs_detector* D) {
             D->dp.nprior = pr.w / 4;
             D->loc_blob = lin[i][0]; D->conf_blob = lin[i][1];
             if (B[D->loc_blob].n != (int64_t)D->dp.nprior * 4 || B[D->conf_blob].n != (int64_t)D->dp.nprior * D->dp.ncls || D->dp.ncls < 2 || D->dp.ncls > 256 ||
-                D->dp.nprior > 65535 || D->dp.nms_topk < 1 || D->dp.nms_topk > 1024 || D->dp.keep_topk < 1 || D->dp.keep_topk > 1024 ||
+                D->dp.nprior > kDetSortCap || D->dp.nms_topk < 1 || D->dp.nms_topk > 1024 || D->dp.keep_topk < 1 || D->dp.keep_topk > 1024 ||
                 (int64_t)(D->dp.ncls - 1) * D->dp.nms_topk > kMergeCap) {
-                set_error("sgs_detector_create: DetectionOutput %s: sizes outside what the kernels take (priors %d, classes %d)", L.name.c_str(), D->dp.nprior, D->dp.ncls); return SGS_ERR_UNSUPPORTED; }
+                set_error("sgs_detector_create: DetectionOutput %s: sizes outside what the kernels take (priors %d of at most %d, classes %d)", L.name.c_str(), D->dp.nprior, kDetSortCap, D->dp.ncls); return SGS_ERR_UNSUPPORTED; }
             std::vector<float> pb(pr.cval.begin(), pr.cval.begin() + pr.w), vr(pr.cval.begin() + pr.w, pr.cval.end());
             int rc = upload(D, pb, &D->d_prior); if (rc) return rc;
             rc = upload(D, vr, &D->d_var); if (rc) return rc;

@@ -85,7 +85,7 @@ class Graph:
                     f.write(np.ascontiguousarray(a).tobytes())
 
 
-def write_mini_model(dirpath, seed=0, conf_gain=1.0, person_bias=2.0):
+def write_mini_model(dirpath, seed=0, conf_gain=1.0, person_bias=2.0, many_priors=False):
     g = Graph(seed)
     data = g.add('Input', [], name='input')
     x = g.hswish(g.conv(data, 3, 8, 3, 2, 1))                                     # 8 x 150 x 150
@@ -103,7 +103,7 @@ def write_mini_model(dirpath, seed=0, conf_gain=1.0, person_bias=2.0):
     f2 = g.clip(g.conv(g.clip(g.conv(g.clip(g.conv(f1, 32, 16)), 16, 16, 3, 2, 1, dw=True)), 16, 32))   # 10
     ncls = 21
     locs, confs, priors = [], [], []
-    specs = [(f1, 32, '-23300=1,60.000000 -23301=1,105.0 -23302=1,2.000000', 4), (f2, 32, '-23300=1,105.000000 -23301=1,150.0 -23302=2,2.000000,3.0', 6)]
+    specs = [(x if many_priors else f1, 32, '-23300=1,60.000000 -23301=1,105.0 -23302=1,2.000000', 4), (f2, 32, '-23300=1,105.000000 -23301=1,150.0 -23302=2,2.000000,3.0', 6)]
     for k, (f, c, pb, npr) in enumerate(specs):
         cf = g.conv(g.clip(g.conv(f, c, c, 3, 1, 1, dw=True)), c, npr * ncls, gain=conf_gain)
         g.layers[-1][5][2][15::ncls] += np.float32(person_bias)            # make the person class (id 15) show up among the detections

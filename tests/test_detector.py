@@ -118,6 +118,10 @@ def test_create_reports_bad_files(tmp_path):
     with pytest.raises(B.SgsError) as e:
         B.Detector(pp, str(short), flags=B.DET_PLAN_ONLY)
     assert e.value.code == B.SGS_ERR_INVALID
+    big_pp, big_bp = DM.write_mini_model(str(tmp_path / 'big'), 0, many_priors=True)          # 38x38x4 + 10x10x6 priors: more than one sort pass holds
+    with pytest.raises(B.SgsError) as e:
+        B.Detector(big_pp, big_bp, flags=B.DET_PLAN_ONLY)
+    assert e.value.code == B.SGS_ERR_UNSUPPORTED and 'priors 6376' in str(e.value)
     bad = tmp_path / 'bad.param'
     bad.write_text(open(pp).read().replace('Softmax', 'LSTM'))
     with pytest.raises(B.SgsError) as e:
