@@ -207,6 +207,19 @@ def cpu_frames_per_s(frames, ti, nframes, cores):
     return nframes / (time.perf_counter() - t0), res
 
 
+def detector_cpu_baseline(param_path, bin_path, frames_rgb):
+    """CPU baseline of Detector2D::detect on a bounded sample: the FP32 restatement (PyTorch conv stack + numpy glue, oracle/detector_oracle.py) -- NOT ncnn,
+    which is not installable here.  Returns frames/s over the sample (serial; PyTorch uses the host threads inside the convolutions)."""
+    import detector_oracle as DO
+    import ncnn_model as NM
+    layers = NM.parse_param(param_path); NM.load_weights(layers, bin_path)
+    DO.detect(layers, frames_rgb[0])                      # warm-up
+    t0 = time.perf_counter()
+    for f in frames_rgb:
+        DO.detect(layers, f)
+    return len(frames_rgb) / (time.perf_counter() - t0)
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path.  The reference cannot be compiled here (needs OpenCV/Eigen/ncnn/ROS,
     DESIGN.md), so this times the CPU oracle port with all host threads, on the same workload/config."""
@@ -501,6 +514,7 @@ def main():
     # ---- Detector2D::detect of the same batch (not part of the metric: the step takes the boxes as inputs, as the reference's tracking thread does) --
     # frames = the grey frames replicated to 3 channels; model = the reference's MobileNetV3-SSDLite graph when build() staged it, else the tests' synthetic graph
     det_info = None
+    det_model = None
     try:
         sys.path.insert(0, os.path.join(ROOT, 'tests'))
         import detector_model as DM
@@ -510,6 +524,7 @@ def main():
         else:
             import tempfile
             dpp, dbp = DM.write_mini_model(tempfile.mkdtemp(), 0); dname, gflop = 'synthetic graph of tests/detector_model.py (reference model not staged)', None
+        det_model = (dpp, dbp)
         DB = 128                                     # frames per detector call
         det = B.Detector(dpp, dbp, max_frames=DB, det_thr=0.9, dyn_thr=0.01, device=local)
         d_rgb = d_frames[:DB].reshape(DB, H, W, 1).expand(DB, H, W, 3).contiguous()
@@ -676,6 +691,13 @@ def main():
                'F_rel_err_max': (max(f_err) if f_err else None)}
         if not ok:
             log('[bench] WARNING: GPU results differ from the oracle on the CPU sample')
+        if det_info is not None and det_model is not None:
+            try:
+                sample = [np.repeat(frames[f][:, :, None], 3, axis=2) for f in range(3)]
+                det_info['cpu_baseline'] = {'value': detector_cpu_baseline(det_model[0], det_model[1], sample), 'unit': 'frames/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+                                            'sample': '3 frames, serial; PyTorch-CPU FP32 convolutions + numpy glue (the restatement used as the test oracle, not ncnn)'}
+            except Exception as ex:
+                log('[bench] detector CPU baseline skipped: %r' % (ex,))
 
     if rank == 0:
         line = {'metric': 'frames/sec ORB extract+match+dyn-reject 640x480', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
