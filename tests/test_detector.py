@@ -61,6 +61,35 @@ def test_oracle_detection_invariants(tmp_path):
     assert np.all(objs[:, 2] >= 0) and np.all(objs[:, 2] + objs[:, 4] <= 640)
 
 
+def test_oracle_convolutions_against_a_direct_sum(tmp_path):
+    """The oracle evaluates Convolution / ConvolutionDepthWise with torch.conv2d; here the same outputs are recomputed at random positions as explicit
+    float64 sums over the ncnn weight layout [out][in/group][kh][kw] with ncnn's stride / symmetric zero padding, for every convolution of the graph."""
+    pp, bp = DM.write_mini_model(str(tmp_path), 0)
+    layers = NM.parse_param(pp); NM.load_weights(layers, bp)
+    blobs = DO.forward(layers, DO.preprocess(DM.synthetic_rgb(480, 640, 3)))
+    rs = np.random.RandomState(0)
+    checked = 0
+    for L in layers:
+        if L.type not in ('Convolution', 'ConvolutionDepthWise'):
+            continue
+        x = blobs[L.inputs[0]].astype(np.float64); y = blobs[L.outputs[0]]
+        k, s, p = L.p(1), L.p(3, 1), L.p(4, 0)
+        cout, oh, ow = y.shape
+        assert oh == (x.shape[1] + 2 * p - k) // s + 1 and ow == (x.shape[2] + 2 * p - k) // s + 1
+        xp = np.pad(x, ((0, 0), (p, p), (p, p)))
+        for _ in range(12):
+            co, oy, ox = rs.randint(cout), rs.randint(oh), rs.randint(ow)
+            win = xp[:, oy * s:oy * s + k, ox * s:ox * s + k]
+            if L.type == 'ConvolutionDepthWise':
+                v = (win[co] * L.weight[co, 0].astype(np.float64)).sum()
+            else:
+                v = (win * L.weight[co].astype(np.float64)).sum()
+            v += float(L.bias[co]) if L.bias is not None else 0.0
+            assert abs(v - float(y[co, oy, ox])) <= 1e-4 * max(1.0, abs(v)), (L.name, co, oy, ox)
+            checked += 1
+    assert checked >= 200
+
+
 def _describe(pp, bp, flags):
     d = B.Detector(pp, bp, max_frames=4, flags=flags | B.DET_PLAN_ONLY)
     txt = d.describe(); info = (d.num_layers, d.num_kernels)
