@@ -307,7 +307,7 @@ SGS_API int sgs_vocabulary_create(int device, int k, int L, int nnodes, const in
 
 // ---- vocabulary files: ORBVocabulary::loadFromTextFile / loadFromBinaryFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1351-1420, :1467-1508).
 // Text: first line "k L scoring weighting", then one line per node in node-id order (the root is implicit): "parent isLeaf d0 ... d31 weight".
-// Binary: uint32 nb_nodes, uint32 size_node (= 41), int k, int L, int scoring, int weighting, then nb_nodes records
+// Binary: uint32 nb_nodes (root included), uint32 size_node (= 41), int k, int L, int scoring, int weighting, then nb_nodes - 1 records
 // { int32 parent; uint8 descriptor[32]; float weight; uint8 is_leaf }.  src/System.cc:69-73 picks the text reader for a ".txt" suffix.
 // Blank lines of a text file are skipped (the reference's eof() loop turns a trailing newline into one undefined extra node).
 namespace {
@@ -344,6 +344,14 @@ int parse_vocabulary_file(const char* path, VocFile& V) {
         if (std::fread(&nb, 4, 1, f) != 1 || std::fread(&sz, 4, 1, f) != 1 || std::fread(hdr, 4, 4, f) != 4 || sz != 41 || hdr[0] < 2 || hdr[0] > 20 || hdr[1] < 1 || hdr[1] > 10) {
             set_error("vocabulary: %s is not a DBoW2 binary vocabulary (41-byte nodes)", path); return SGS_ERR_INVALID; }
         V.k = hdr[0]; V.L = hdr[1];
+        // saveToBinaryFile (:1514-1535) writes nb_nodes = m_nodes.size() -- the root INCLUDED -- and then records for nodes 1 .. nb_nodes-1.
+        // (loadFromBinaryFile's eof() loop additionally re-reads the last record into a phantom node nb_nodes; it duplicates the last child of its
+        // parent, which a strict '<' descent can never select, so it is not materialised here.)
+        if (nb < 2) { set_error("vocabulary: %s holds no nodes", path); return SGS_ERR_INVALID; }
+        nb -= 1;
+        long here = std::ftell(f), end = -1;
+        if (here >= 0 && std::fseek(f, 0, SEEK_END) == 0) { end = std::ftell(f); std::fseek(f, here, SEEK_SET); }
+        if (here < 0 || end < 0 || (uint64_t)(end - here) < (uint64_t)nb * 41) { set_error("vocabulary: %s is truncated", path); return SGS_ERR_INVALID; }   // before allocating
         std::vector<uint8_t> buf((size_t)nb * 41);
         if (std::fread(buf.data(), 41, nb, f) != nb) { set_error("vocabulary: %s is truncated", path); return SGS_ERR_INVALID; }
         V.parent.reserve(nb + 1); V.desc.reserve(32 * ((size_t)nb + 1)); V.leaf.reserve(nb + 1); V.weight.reserve(nb + 1);

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "sgs_common.h"
+#include "sgs_logf.h"
 
 // host -> device copy of the convenience (host-pointer) entry points: the first failure is kept and reported by the caller
 #define SGS_H2D(err, dst, src, bytes) do { if ((err) == cudaSuccess) (err) = cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice); } while (0)
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256) frustum_kernel(const sgs_frustum_batch A,
         ok = ok && !(vc < A.viewing_cos_limit);
         if (ok) {
             const float ratio = __fdiv_rn(A.mp_max_dist[o], dist);
-            int ns = (int)ceilf(__fdiv_rn((float)log((double)ratio), log_sf));
+            int ns = (int)ceilf(__fdiv_rn(glibc_logf(ratio), log_sf));          // MapPoint.cc:402-418, libm logf restated (sgs_logf.h)
             ns = ns < 0 ? 0 : (ns >= nlevels ? nlevels - 1 : ns);
             in = 1; pu = u; pv = v; pxr = __fsub_rn(u, __fmul_rn(A.cam.bf, invz)); lvl = ns; vcos = vc;
         }

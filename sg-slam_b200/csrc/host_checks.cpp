@@ -70,3 +70,21 @@ int sgs_hostcheck_quadtree(const sgs_orb_params* p, int w, int h, int level, con
     for (int i = 0; i < nout; ++i) { out[3 * i] = sgs::qt_x(sel[i]); out[3 * i + 1] = sgs::qt_y(sel[i]); out[3 * i + 2] = sgs::qt_score(sel[i]); }
     return nout;
 }
+
+// glibc_logf (sgs_logf.h, the product's restatement of libm's logf used by PredictScale) against the running libm: number of floats whose
+// results differ in any bit among the `count` bit patterns first, first + stride, ...
+#include <cmath>
+#include "sgs_logf.h"
+extern "C" __attribute__((visibility("default")))
+long long sgs_hostcheck_logf_mismatches(uint32_t first, uint32_t stride, long long count) {
+    long long bad = 0;
+    uint32_t b = first;
+    for (long long i = 0; i < count; ++i, b += stride) {
+        float x; std::memcpy(&x, &b, 4);
+        const float r = ::logf(x), p = sgs::glibc_logf(x);
+        if (std::memcmp(&r, &p, 4) != 0 && !(r != r && p != p)) ++bad;
+    }
+    return bad;
+}
+extern "C" __attribute__((visibility("default")))
+float sgs_hostcheck_logf(float x) { return sgs::glibc_logf(x); }

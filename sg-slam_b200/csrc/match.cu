@@ -21,6 +21,7 @@
 
 #include "match_dev.cuh"
 #include "sgs_common.h"
+#include "sgs_logf.h"
 
 namespace sgs {
 
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
                         const float dist = (float)sqrt(((double)px * px + (double)py * py) + (double)pz * pz);
                         const float maxd = A.kf_max_dist[lo + i];
                         ok = !(dist < __fmul_rn(0.8f, A.kf_min_dist[lo + i]) || dist > __fmul_rn(1.2f, maxd));
-                        oct = (int)ceilf(__fdiv_rn((float)log((double)__fdiv_rn(maxd, dist)), A.log_sf));
+                        oct = (int)ceilf(__fdiv_rn(glibc_logf(__fdiv_rn(maxd, dist)), A.log_sf));
                         oct = oct < 0 ? 0 : (oct >= A.cam.nlevels ? A.cam.nlevels - 1 : oct);
                         mn = oct - 1; mx = oct + 1;
                     } else {
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(kMatchThreads) fuse_search_kernel(const __grid
             const float* N = A.mp_normal + 3 * (lo + i);
             ok = ok && (cam2 || !((((double)px * N[0] + (double)py * N[1]) + (double)pz * N[2]) < 0.5 * (double)dist));
             if (ok) {
-                int lvl = (int)ceilf(__fdiv_rn((float)log((double)__fdiv_rn(maxd, dist)), A.log_sf));
+                int lvl = (int)ceilf(__fdiv_rn(glibc_logf(__fdiv_rn(maxd, dist)), A.log_sf));
                 lvl = lvl < 0 ? 0 : (lvl >= A.cam.nlevels ? A.cam.nlevels - 1 : lvl);
                 const float r = __fmul_rn(A.th, A.cam.scale[lvl]);
                 const int min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, A.cam.min_x), r), w_inv)));

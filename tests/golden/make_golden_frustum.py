@@ -2,6 +2,8 @@
 """Golden vectors for Frame::isInFrustum (src/Frame.cc:296-352) and Frame::ComputeStereoFromRGBD (:893-914), evaluated with the REAL OpenCV
 matrix primitives the reference calls (cv2.gemm for Rcw*P+tcw and -Rcw.t()*tcw, cv2.norm, float32 scalar arithmetic), so that the double
 accumulation / single rounding conventions of the oracle are pinned.  Run in the build container:  python tests/golden/make_golden_frustum.py"""
+import ctypes
+import ctypes.util
 import math
 import os
 
@@ -10,6 +12,14 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 f32 = np.float32
+_libm = ctypes.CDLL(ctypes.util.find_library('m'))
+_libm.logf.restype = ctypes.c_float
+_libm.logf.argtypes = [ctypes.c_float]
+
+
+def logf(x):
+    """libm's float logarithm -- what `log(float)` in Frame.cc:1017 / MapPoint.cc:411 calls (glibc 2.39 here)."""
+    return f32(_libm.logf(float(x)))
 
 
 def main():
@@ -29,7 +39,7 @@ def main():
     nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(f32)
     maxd = (dist0 * rs.uniform(0.6, 4.0, n)).astype(f32); mind = (maxd / f32(1.2) ** rs.randint(3, 9, n)).astype(f32)
     Ow = cv2.gemm(R, t, -1, None, 0, flags=cv2.GEMM_1_T)            # mOw = -mRcw.t()*mtcw: the MatExpr folds transpose and sign into one gemm call
-    logsf = f32(math.log(f32(1.2)))                                # what logf(1.2f) rounds to
+    logsf = logf(f32(1.2))                                         # mfLogScaleFactor = log(mfScaleFactor), float overload
     out = dict(inview=np.zeros(n, np.uint8), proj_x=np.zeros(n, f32), proj_y=np.zeros(n, f32), proj_xr=np.zeros(n, f32), level=np.zeros(n, np.int32),
                view_cos=np.zeros(n, f32), level_arg=np.zeros(n, np.float64))
     fx, fy, cx, cy, bf = cam[:5]
@@ -51,8 +61,8 @@ def main():
         if vc < f32(0.5):
             continue
         ratio = maxd[i] / dist
-        arg = float(f32(math.log(float(ratio)))) / float(logsf)          # ~ logf(ratio) / mfLogScaleFactor (float division below)
-        lv = int(math.ceil(f32(f32(math.log(float(ratio))) / logsf)))
+        arg = float(logf(ratio)) / float(logsf)                          # logf(ratio) / mfLogScaleFactor in double, for diagnostics only
+        lv = int(math.ceil(f32(logf(ratio) / logsf)))                    # MapPoint::PredictScale: float log, float division, ceil
         lv = 0 if lv < 0 else (7 if lv >= 8 else lv)
         out['inview'][i] = 1; out['proj_x'][i] = u; out['proj_y'][i] = v; out['proj_xr'][i] = u - bf * invz; out['level'][i] = lv; out['view_cos'][i] = vc
         out['level_arg'][i] = arg

@@ -99,3 +99,17 @@ def test_quadtree_core_random(hc, seed):
         got = _run_qt(hc, p, w, h, 0, c, N)
         ref = _oracle_qt(p, w, h, 0, c, N)
         assert np.array_equal(got, ref), (seed, N, len(c))
+
+
+def test_logf_restatement_equals_libm(hc):
+    """sgs_logf.h (the device's logf for MapPoint::PredictScale, src/MapPoint.cc:402-418) against the running libm, bit for bit: a stride-61
+    sweep over every positive finite float (35 M values), every float in [0.25, 16] (the range of mfMaxDistance / dist), the special cases."""
+    hc.sgs_hostcheck_logf_mismatches.restype = C.c_longlong
+    hc.sgs_hostcheck_logf.restype = C.c_float
+    assert hc.sgs_hostcheck_logf_mismatches(C.c_uint32(1), C.c_uint32(61), C.c_longlong(0x7f800000 // 61)) == 0
+    lo = int(np.float32(0.25).view(np.uint32)); hi = int(np.float32(16.0).view(np.uint32))
+    assert hc.sgs_hostcheck_logf_mismatches(C.c_uint32(lo), C.c_uint32(1), C.c_longlong(hi - lo + 1)) == 0
+    assert hc.sgs_hostcheck_logf(C.c_float(1.0)) == 0.0
+    assert hc.sgs_hostcheck_logf(C.c_float(0.0)) == -np.inf and hc.sgs_hostcheck_logf(C.c_float(np.inf)) == np.inf
+    assert np.isnan(hc.sgs_hostcheck_logf(C.c_float(-1.0))) and np.isnan(hc.sgs_hostcheck_logf(C.c_float(np.nan)))
+    assert hc.sgs_hostcheck_logf_mismatches(C.c_uint32(1), C.c_uint32(1), C.c_longlong(0x00800000)) == 0       # all subnormals

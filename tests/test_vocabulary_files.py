@@ -30,7 +30,7 @@ def write_binary(path, voc):
     for i in range(1, n):
         child[voc['parent'][i]] += 1
     with open(path, 'wb') as f:
-        f.write(struct.pack('<IIiiii', n - 1, 41, voc['k'], voc['L'], 0, 0))
+        f.write(struct.pack('<IIiiii', n, 41, voc['k'], voc['L'], 0, 0))      # nb_nodes counts the root (saveToBinaryFile, TemplatedVocabulary.h:1517)
         for i in range(1, n):
             f.write(struct.pack('<i', int(voc['parent'][i])) + bytes(voc['desc'][i]) + struct.pack('<f', float(voc['weight'][i])) + bytes([1 if child[i] == 0 else 0]))
     return child

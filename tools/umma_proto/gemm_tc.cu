@@ -1,0 +1,114 @@
+// Prototype / unit harness of the tcgen05 1x1-convolution GEMM (see sg-slam_b200/csrc/conv1x1_tc.cuh for the product kernel).
+// out[p][co] = bias[co] + sum_ci X[p][ci] * W[co][ci]   X: [npix][Cin] (NHWC activations), W: [Cout][Cin]
+// FP32-grade accuracy on the TF32 tensor pipe: x = hi + lo (both TF32), three tcgen05.mma per k-step (lo*hi + hi*lo + hi*hi), FP32 accumulate in TMEM.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include "../../sg-slam_b200/csrc/conv1x1_tc.cuh"
+
+using namespace sgs::tc;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+static float frand(uint32_t& s) { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xffff) / 32768.0f - 1.0f; }
+
+static int run_case(int npix, int Cin, int Cout, int out_pitch, int tail, bool timing) {
+    const int in_pitch = (Cin + 3) & ~3;
+    uint32_t seed = 1234u + npix + Cin * 7 + Cout * 13;
+    std::vector<float> X((size_t)npix * in_pitch, 0.f), W((size_t)Cout * Cin), Bs(Cout), R((size_t)npix * out_pitch, 0.f);
+    for (int p = 0; p < npix; ++p) for (int c = 0; c < Cin; ++c) X[(size_t)p * in_pitch + c] = frand(seed) * 3.f;
+    for (auto& v : W) v = frand(seed) * 0.5f;
+    for (auto& v : Bs) v = frand(seed);
+    for (auto& v : R) v = frand(seed);
+    float *dX, *dB, *dO, *dR;
+    CK(cudaMalloc(&dX, X.size() * 4)); CK(cudaMalloc(&dB, Bs.size() * 4)); CK(cudaMalloc(&dO, (size_t)npix * out_pitch * 4)); CK(cudaMalloc(&dR, R.size() * 4));
+    CK(cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, Bs.data(), Bs.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dR, R.data(), R.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dO, 0xff, (size_t)npix * out_pitch * 4));
+    GemmPlan plan;
+    if (!plan_weights(W.data(), Cin, Cout, &plan)) { printf("plan_weights failed\n"); return 1; }
+    GemmTail T{}; T.kind = tail; T.a = 3.f; T.lo = 0.f; T.hi = 6.f; T.b = 6.f; T.t1 = dR; T.t2 = dR;
+    if (!launch_conv1x1_tc(plan, dX, in_pitch, npix, dB, dO, out_pitch, T, 0)) { printf("launch failed\n"); return 1; }
+    CK(cudaDeviceSynchronize());
+    std::vector<float> O((size_t)npix * out_pitch);
+    CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0; int bad = 0;
+    const int step = npix > 20000 ? 97 : 1;
+    for (int p = 0; p < npix; p += step)
+        for (int co = 0; co < Cout; ++co) {
+            double acc = 0, mag = 0;
+            for (int c = 0; c < Cin; ++c) { const double t = (double)X[(size_t)p * in_pitch + c] * W[(size_t)co * Cin + c]; acc += t; mag += fabs(t); }
+            acc += Bs[co]; mag += fabs(Bs[co]);
+            double ref = acc;
+            if (tail == TK_RELU) ref = acc > 0 ? acc : 0;
+            else if (tail == TK_CLIP) ref = fmin(fmax(acc, 0.), 6.);
+            else if (tail == TK_HSWISH) ref = acc * fmin(fmax(acc + 3., 0.), 6.) / 6.;
+            else if (tail == TK_ADD_T) ref = acc + R[(size_t)p * out_pitch + co];
+            else if (tail == TK_SE_TAIL) ref = R[(size_t)p * out_pitch + co] * (fmin(fmax(acc + 3., 0.), 6.) / 6.) + R[(size_t)p * out_pitch + co];
+            const double got = O[(size_t)p * out_pitch + co];
+            const double err = fabs(got - ref) / (mag + 1.0);
+            if (!(err < 2e-6)) { if (bad < 5) printf("  mismatch p=%d co=%d got=%.8g ref=%.8g\n", p, co, got, ref); ++bad; }
+            if (err > maxerr) maxerr = err;
+            if (fabs(ref) > maxref) maxref = fabs(ref);
+        }
+    // padding columns must be untouched
+    int touched = 0;
+    if (out_pitch > Cout) for (int p = 0; p < npix; p += step) for (int c = Cout; c < out_pitch; ++c) { uint32_t b; memcpy(&b, &O[(size_t)p * out_pitch + c], 4); if (b != 0xffffffffu) ++touched; }
+    printf("case npix=%d Cin=%d Cout=%d pitch=%d tail=%d: NT=%d ntiles=%d KB=%d stages=%d smem=%d  max rel err %.3g (max |ref| %.3g) bad=%d touched_pad=%d\n", npix, Cin, Cout, out_pitch, tail,
+           plan.NT, plan.n_tiles, plan.KB, plan.stages, plan.smem_bytes, maxerr, maxref, bad, touched);
+    if (timing) {
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        for (int i = 0; i < 3; ++i) launch_conv1x1_tc(plan, dX, in_pitch, npix, dB, dO, out_pitch, T, 0);
+        CK(cudaEventRecord(e0));
+        const int it = 20;
+        for (int i = 0; i < it; ++i) launch_conv1x1_tc(plan, dX, in_pitch, npix, dB, dO, out_pitch, T, 0);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= it;
+        const double bytes = (double)npix * (in_pitch + out_pitch) * 4, flop = 2.0 * npix * Cin * Cout;
+        printf("   time %.3f ms  %.1f GB/s  %.2f TFLOP/s (fp32-equivalent)\n", ms, bytes / ms * 1e-6, flop / ms * 1e-9);
+    }
+    free_plan(&plan);
+    cudaFree(dX); cudaFree(dB); cudaFree(dO); cudaFree(dR);
+    return bad || touched;
+}
+
+int main(int argc, char** argv) {
+    int fails = 0;
+    if (argc > 1 && !strcmp(argv[1], "profile")) {          // two launches per case for ncu
+        run_case(22500 * 128, 16, 64, 64, TK_RELU, false);
+        run_case(361 * 128, 112, 672, 672, TK_HSWISH, false);
+        run_case(1444 * 128, 40, 240, 240, TK_HSWISH, false);
+        return 0;
+    }
+    fails += run_case(128, 32, 16, 16, TK_NONE, false);
+    fails += run_case(128, 32, 64, 64, TK_NONE, false);
+    fails += run_case(256, 64, 128, 128, TK_RELU, false);
+    fails += run_case(300, 16, 64, 64, TK_RELU, false);
+    fails += run_case(1000, 24, 72, 72, TK_HSWISH, false);
+    fails += run_case(361, 112, 672, 672, TK_HSWISH, false);
+    fails += run_case(361, 672, 84, 84, TK_NONE, false);
+    fails += run_case(100, 960, 126, 126, TK_NONE, false);
+    fails += run_case(1444, 40, 10, 12, TK_RELU, false);
+    fails += run_case(361, 28, 112, 112, TK_SE_TAIL, false);
+    fails += run_case(361, 184, 80, 80, TK_ADD_T, false);
+    fails += run_case(25, 512, 126, 126, TK_CLIP, false);
+    fails += run_case(1, 64, 128, 128, TK_CLIP, false);
+    if (argc > 1) {
+        fails += run_case(22500 * 128, 16, 64, 64, TK_RELU, true);
+        fails += run_case(22500 * 128, 16, 16, 16, TK_RELU, true);
+        fails += run_case(5625 * 128, 64, 24, 24, TK_NONE, true);
+        fails += run_case(5625 * 128, 24, 72, 72, TK_RELU, true);
+        fails += run_case(1444 * 128, 40, 240, 240, TK_HSWISH, true);
+        fails += run_case(361 * 128, 112, 672, 672, TK_HSWISH, true);
+        fails += run_case(361 * 128, 672, 160, 160, TK_NONE, true);
+        fails += run_case(100 * 128, 160, 960, 960, TK_HSWISH, true);
+        fails += run_case(100 * 128, 960, 160, 160, TK_NONE, true);
+    }
+    printf(fails ? "FAILED (%d)\n" : "ALL OK\n", fails);
+    return fails ? 1 : 0;
+}
