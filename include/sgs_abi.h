@@ -99,6 +99,9 @@ SGS_API int sgs_extract(sgs_extractor* ex, const uint8_t* gray, int width, int h
  * buffers (input, and outputs with cap == sgs_extractor_max_keypoints) are used directly, without staging. */
 SGS_API int sgs_extract_batch(sgs_extractor* ex, const uint8_t* gray, int nframes, size_t frame_stride, int pitch,
                               sgs_keypoint* kps, uint8_t* desc, int cap, int* n);
+/* kps == desc == n == NULL: upload + kernels only, no copy back and no synchronisation -- the results stay on the device
+ * (sgs_extractor_results_device); sgs_extractor_stream is the stream that work was enqueued on (for event ordering). */
+SGS_API void* sgs_extractor_stream(const sgs_extractor* ex);
 
 /* Device-resident batch: d_gray is a DEVICE pointer ([nframes] images, frame_stride/pitch bytes); results stay on the
  * device inside the handle (see sgs_extractor_results_device).  Asynchronous on `stream`. */
@@ -340,6 +343,9 @@ SGS_API int sgs_settings_load(const char* path, sgs_settings* out);
 typedef struct sgs_vocabulary sgs_vocabulary;
 SGS_API int sgs_vocabulary_create(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* node_desc,
                                   const double* node_weight, sgs_vocabulary** out);
+/* the same with the node descriptors in DEVICE memory (e.g. the buffer an ncclBroadcast just filled): copied device to device, no host bounce */
+SGS_API int sgs_vocabulary_create_device(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* d_node_desc,
+                                         const double* node_weight, sgs_vocabulary** out);
 SGS_API void sgs_vocabulary_destroy(sgs_vocabulary* v);
 /* Vocabulary files of the reference: ORBVocabulary::loadFromTextFile / loadFromBinaryFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1351-1420,
  * :1467-1508); like src/System.cc:69-73 a ".txt" suffix selects the text reader.  sgs_vocabulary_parse_file fills the flat arrays sgs_vocabulary_create
@@ -457,8 +463,10 @@ SGS_API int sgs_dynreject_batch_device(const sgs_keypoint* d_kps, const uint8_t*
  * keypoints, points2 = their LK-tracked positions in the previous frame), including the selection in front of it
  * (src/Frame.cc:454-468: when the previous frame had dynamic boxes and more than 20 pairs have their PREVIOUS point outside
  * them, only those pairs are used).  F: 3x3 row-major double scaled to F33 = 1; a NaN in F[0] == empty matrix.
- *   info (4 x int32, may be NULL): pairs used, inliers of F, iterations run, status (0 ok, 1 fewer than 15 pairs -- OpenCV
- *   would run LMedS / plain 7-point, not provided --, 2 no model found, 3 no previous frame).
+ *   All three branches of OpenCV's function are on the device: >= 15 pairs RANSAC, 8..14 pairs LMedS (300 fixed samples, smallest median
+ *   error), exactly 7 pairs the 7-point solver itself (first of its stacked solutions = what the reference reads), fewer: empty matrix.
+ *   info (4 x int32, may be NULL): pairs used, inliers of F, iterations run, status (0 ok, 1 fewer than 7 pairs, 2 no model found,
+ *   3 no previous frame).
  *   sgs_fundamental_ransac       : host pointers, one point set, no box selection; mask [n] may be NULL.
  *   sgs_fundamental_batch_device : device pointers, `nframes` frames: d_kps [F][cap], d_prev_xy [F][cap][2], d_counts [F],
  *                                  previous-frame boxes d_prev_boxes [F][max_boxes] / d_prev_nboxes [F] / d_prev_have_dyn [F]
@@ -595,9 +603,9 @@ typedef struct sgs_object2d {   /* Object2D, include/Detector2D.h:29-37 (name = 
 /* Detector2D::Detector2D(detection_confidence_threshold, dynamic_detection_confidence_threshold) + load_param/load_model.
  * max_frames = largest batch one sgs_detector_detect_device call may carry.  flags: bit 0 = diagnostic mode (every layer its own kernel,
  * every intermediate blob kept, readable with sgs_detector_blob); bit 1 = plan only (parse, shapes, kernel list and activation pool are
- * built, no device is touched; the handle serves sgs_detector_info / sgs_detector_describe only); bit 2 = run the 1x1 convolutions as a plain
- * FP32 FMA GEMM instead of the error-compensated TF32 tensor-core GEMM (three mma.sync per product; same results to ~1e-6 relative, the FMA path
- * is ~8 % slower on B200). */
+ * built, no device is touched; the handle serves sgs_detector_info / sgs_detector_describe only).
+ * The 1x1 convolutions (90 % of the MACs) run as a TMA-fed tcgen05 / TMEM GEMM on [frame][h][w][c] activations with error-compensated TF32 operands
+ * (three tcgen05.mma per 8-wide k-step, FP32 accumulate: ~1e-6 relative); there is no other GEMM path. */
 SGS_API int sgs_detector_create(const char* param_path, const char* bin_path, int max_frames, float detection_confidence_threshold,
                                 float dynamic_detection_confidence_threshold, int flags, int device, sgs_detector** out);
 SGS_API void sgs_detector_destroy(sgs_detector* d);
@@ -610,8 +618,11 @@ SGS_API int sgs_detector_info(const sgs_detector* d, int* rows_cap, int* input_s
  *   d_rows     [F][rows_cap][6]  detection_out rows [label, score, xmin, ymin, xmax, ymax] (normalised);  d_nrows [F]
  *   d_objects  [F][rows_cap]     every accepted row in detection order (what draw_objects sees, :66);       d_nobjects [F]
  *   d_dyn_map  [F][max_boxes]    mvPotentialDynamicBorderForMapping (:70);                                  d_ndyn_map [F]
- *   d_dyn_rm   [F][max_boxes]    mvPotentialDynamicBorderForRmDynamicFeature (:74), d_ndyn_rm [F], d_have_dyn_rm [F] (uint8, :73) --
- *                                the layout sgs_dynreject_batch_device / sgs_tracker_* take as d_boxes / d_nboxes / d_have_dyn.
+ *   d_dyn_rm   [F][max_boxes]    mvPotentialDynamicBorderForRmDynamicFeature (:74), d_ndyn_rm [F] -- the layout sgs_dynreject_batch_device /
+ *                                sgs_tracker_* take as d_boxes / d_nboxes;  d_have_dyn_rm [F] (uint8) = the flag the FRAME ends up with
+ *                                (src/Frame.cc:482-491): Detector2D's mbHaveDynamicObjectForRmDynamicFeature (:73) is copied only when mvObjects2D
+ *                                -- the NON-person objects -- is not empty; otherwise the Frame member is never written (include/Frame.h:112,
+ *                                uninitialised in the reference; defined as false here, quirk Q12) and the previous-frame flag is false.
  * Person boxes beyond max_boxes are not written: d_ndyn_* are clamped to max_boxes and d_status[f] (may be NULL) is set to 1. */
 SGS_API int sgs_detector_detect_device(sgs_detector* d, const uint8_t* d_rgb, int64_t frame_stride, int pitch, int width, int height,
                                        int nframes, float* d_rows, int32_t* d_nrows, sgs_object2d* d_objects, int32_t* d_nobjects,
@@ -620,6 +631,23 @@ SGS_API int sgs_detector_detect_device(sgs_detector* d, const uint8_t* d_rgb, in
 /* One frame from host memory: objects[0..*n) = accepted rows in detection order (persons included, id 15).  SGS_ERR_CAPACITY with
  * *n = required when cap is too small. */
 SGS_API int sgs_detect(sgs_detector* d, const uint8_t* rgb, int width, int height, int pitch, sgs_object2d* objects, int cap, int* n);
+/* Detector inside the tracking step (src/Tracking.cc:288-307 hands the colour image to the detector thread, src/Frame.cc:478-500 joins it before the
+ * rejection).  sgs_tracker_detect_device runs Detector2D::detect on device frames and leaves the person boxes in the tracker's own box arrays
+ * (sgs_tracker_boxes_device), which sgs_tracker_fundamental_device / sgs_tracker_track_device use when called with boxes / nboxes / have_dyn == NULL.
+ * stream == NULL: the tracker's detector stream.
+ * sgs_tracker_step is the whole front end with HOST buffers: colour frames -> detector on its own stream; gray frames -> ORB extract -> LK ->
+ * (join) findFundamentalMat -> dyn-reject + compaction -> SearchByProjection(cur, last); uploads overlap the kernels, one synchronisation at the end.
+ * Shapes as for sgs_tracker_track_lk; rgb: interleaved 8-bit frames (rgb_pitch bytes per row); boxes_out [F][max_boxes] / nboxes_out [F] / have_out [F]
+ * (may be NULL) return the boxes the rejection used. */
+SGS_API int sgs_tracker_detect_device(sgs_tracker* t, sgs_detector* det, const uint8_t* d_rgb, int64_t frame_stride, int pitch, int width, int height,
+                                      int nframes, void* stream);
+SGS_API int sgs_tracker_boxes_device(const sgs_tracker* t, const sgs_rect** d_boxes, const int32_t** d_nboxes, const uint8_t** d_have_dyn);
+SGS_API int sgs_tracker_step(sgs_tracker* t, sgs_detector* det, const uint8_t* gray, size_t gray_stride, int gray_pitch, const uint8_t* rgb,
+                             size_t rgb_stride, int rgb_pitch, int nframes, const int32_t* prev_index, const float* u_right, const float* last_xyz,
+                             const uint8_t* last_desc, const uint8_t* last_flags, const int32_t* last_octave, const float* last_angle,
+                             const int32_t* last_n, const float* tcw_cur, const float* tcw_last, float th, int mono, int check_orientation,
+                             sgs_keypoint* kps_out, uint8_t* desc_out, float* u_right_out, int32_t* counts_out, int32_t* cur_mp_out,
+                             int32_t* nmatches_out, sgs_rect* boxes_out, int32_t* nboxes_out, uint8_t* have_out);
 /* Text listing of the kernel list: one line per kernel with its fused element-wise tail and activation-pool buffers.  SGS_ERR_CAPACITY
  * with *n = bytes required (terminator included) when cap is too small. */
 SGS_API int sgs_detector_describe(const sgs_detector* d, char* out, int64_t cap, int64_t* n);

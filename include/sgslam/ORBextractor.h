@@ -8,6 +8,7 @@
 //     src/Frame.cc:813,830); the 19-px reflect-101 border of the reference is not materialised (never read for RGB-D/mono);
 //   * failures of the GPU path (no device, CUDA error) throw std::runtime_error -- there is no CPU fallback.
 #pragma once
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -43,17 +44,19 @@ public:
     // Compute the ORB features and descriptors on an image.  The mask is ignored, as in the reference (src/ORBextractor.cc:1045).
     void operator()(cv::InputArray image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray descriptors) {
         if (image.empty()) return;                                                  // :1048
-        if (image.type() != CV_8UC1) throw std::runtime_error("ORBextractor: image must be CV_8UC1");   // assert at :1051
-        ensure(image.cols, image.rows);
+        const cv::Mat im = image.getMat();                                          // :1050 (only member functions of _InputArray / _OutputArray are used: real OpenCV compiles this)
+        if (im.type() != CV_8UC1) throw std::runtime_error("ORBextractor: image must be CV_8UC1");   // assert at :1051
+        ensure(im.cols, im.rows);
         kps_.resize(cap_);
         desc_.resize((size_t)cap_ * 32);
         int n = 0;
-        check(sgs_extract(h_, image.data, image.cols, image.rows, (int)image.step, reinterpret_cast<sgs_keypoint*>(kps_.data()), desc_.data(), cap_, &n));
+        check(sgs_extract(h_, im.data, im.cols, im.rows, (int)im.step, reinterpret_cast<sgs_keypoint*>(kps_.data()), desc_.data(), cap_, &n));
         keypoints.assign(kps_.begin(), kps_.begin() + n);
         if (n == 0) { descriptors.release(); }                                      // :1066-1067
         else {
-            descriptors.create(n, 32, CV_8U);
-            for (int i = 0; i < n; ++i) std::memcpy(descriptors.ptr<uint8_t>(i), desc_.data() + (size_t)i * 32, 32);
+            descriptors.create(n, 32, CV_8U);                                       // :1069-1070
+            cv::Mat d = descriptors.getMat();
+            for (int i = 0; i < n; ++i) std::memcpy(d.ptr<uint8_t>(i), desc_.data() + (size_t)i * 32, 32);
         }
         if (keep_pyramid_)
             for (int l = 0; l < nlevels; ++l) {

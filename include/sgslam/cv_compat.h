@@ -71,8 +71,30 @@ private:
     std::shared_ptr<std::vector<uint8_t>> owner_;
 };
 
-typedef const Mat& InputArray;
-typedef Mat& OutputArray;
+// cv::InputArray / cv::OutputArray: proxy classes with the member-FUNCTION surface of OpenCV's _InputArray / _OutputArray (getMat(), empty(), type(),
+// create(), release()), so that code written against them compiles unchanged against the real headers (where `image.cols` or `image.data` do not exist).
+class _InputArray {
+public:
+    _InputArray() : m_(nullptr) {}
+    _InputArray(const Mat& m) : m_(const_cast<Mat*>(&m)) {}
+    Mat getMat() const { return m_ ? *m_ : Mat(); }
+    bool empty() const { return !m_ || m_->empty(); }
+    int type() const { return m_ ? m_->type() : 0; }
+    int rows() const { return m_ ? m_->rows : 0; }
+    int cols() const { return m_ ? m_->cols : 0; }
+protected:
+    Mat* m_;
+};
+class _OutputArray : public _InputArray {
+public:
+    _OutputArray() {}
+    _OutputArray(Mat& m) : _InputArray(m) {}
+    void create(int r, int c, int type) const { m_->create(r, c, type); }
+    void release() const { if (m_) m_->release(); }
+};
+typedef const _InputArray& InputArray;
+typedef const _OutputArray& OutputArray;
+inline InputArray noArray() { static _InputArray none; return none; }
 
 }  // namespace cv
 #endif

@@ -13,7 +13,7 @@
 //     space), solves det(l f1 + (1 - l) f2) = 0 with cv::solveCubic, and scales each F to F33 = 1
 //   * error = (float)max(d1^2/(a1^2+b1^2), d2^2/(a2^2+b2^2)) in double, inlier iff <= (float)(thr*thr)
 //   * a model replaces the best one iff inliers > max(best, 6); niters = RANSACUpdateNumIters(...) after every improvement
-//   * no refit on the inliers; fewer than 15 points would go to LMedS in OpenCV -- not restated (returns 0, "empty matrix")
+//   * no refit on the inliers; fewer than 15 pairs never reach RANSAC: 8..14 -> LMedS, exactly 7 -> the 7-point solver itself, fewer -> empty (all restated below)
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -257,10 +257,19 @@ SGO_API int sgo_find_fundamental_ransac(const float* m1, const float* m2, int n,
     if (confidence < DBL_EPSILON || confidence > 1 - DBL_EPSILON) confidence = 0.99;
     if (n < 15) {
         // fundam.cpp cv::findFundamentalMat: fewer than 15 pairs never reach RANSAC.  < 7: empty; == 7: the 7-point solver directly (up to three
-        // stacked solutions -- not provided here: 0 is returned); 8..14: LMeDSPointSetRegistrator(cb, 7, confidence).run (ptsetreg.cpp), maxIters = 1000:
+        // stacked solutions; the first is returned); 8..14: LMeDSPointSetRegistrator(cb, 7, confidence).run (ptsetreg.cpp), maxIters = 1000:
         // a fixed number of samples (outlier ratio 0.45), the model with the smallest median error (element count/2 of the sorted errors), inliers
         // within sigma = 2.5 * 1.4826 * (1 + 5 / (count - 7)) * sqrt(median); the result is dropped when fewer than 7 pairs are inliers.
-        if (n <= 7) return 0;
+        if (n < 7) return 0;
+        if (n == 7) {             // runKernel directly: the stacked solutions; callers read rows 0..2 = the first one (src/Frame.cc:617-619)
+            double models7[27];
+            const int nm = run7point(m1, m2, models7);
+            if (nm <= 0) return 0;
+            std::memcpy(F, models7, 9 * sizeof(double));
+            if (mask_out) std::memset(mask_out, 1, n);
+            if (info) { info[0] = 1; info[1] = 7; info[2] = 1; }
+            return 1;
+        }
         CvRng rng((uint64_t)-1);
         const int niters = std::max(update_num_iters(confidence, 0.45, 7, 1000), 3);
         double min_median = DBL_MAX, best[9], models[27];

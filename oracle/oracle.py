@@ -47,6 +47,20 @@ def lib():
     return _LIB
 
 
+_libm = None
+
+
+def logf(x):
+    """libm's float logarithm: what `log(float)` calls in the reference (mfLogScaleFactor = log(mfScaleFactor), src/Frame.cc:139; PredictScale,
+    src/MapPoint.cc:402-418).  numpy's float32 log is a different implementation (1 ulp apart at 1.2f)."""
+    global _libm
+    if _libm is None:
+        import ctypes.util
+        _libm = C.CDLL(ctypes.util.find_library('m'))
+        _libm.logf.restype = C.c_float; _libm.logf.argtypes = [C.c_float]
+    return np.float32(_libm.logf(float(np.float32(x))))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -201,7 +215,7 @@ class FrameArrays:
         self.scaleFactors = np.ascontiguousarray(scaleFactors, np.float32)
         self.c = SgoFrame(len(self.keysUn), self.keysUn.ctypes.data, self.uRight.ctypes.data, self.desc.ctypes.data,
                           0.0, 0.0, float(w), float(h), fx, fy, cx, cy, bf, len(self.scaleFactors),
-                          self.scaleFactors.ctypes.data, float(np.log(np.float32(self.scaleFactors[1]))) if len(self.scaleFactors) > 1 else 0.0)
+                          self.scaleFactors.ctypes.data, float(logf(self.scaleFactors[1])) if len(self.scaleFactors) > 1 else 0.0)
 
 
 def features_in_area(fr, x, y, r, minLevel=-1, maxLevel=-1):
@@ -236,7 +250,7 @@ def search_by_projection_kf(cur, Tcw_cur, kf_valid, kf_xyz, kf_desc, kf_angle, m
          np.ascontiguousarray(kf_angle, np.float32), np.ascontiguousarray(min_dist, np.float32), np.ascontiguousarray(max_dist, np.float32)]
     mp = np.full(cur.c.N, -1, np.int32) if cur_mp is None else np.ascontiguousarray(cur_mp, np.int32).copy()
     if log_scale_factor is None:
-        log_scale_factor = float(np.float32(np.log(np.float32(1.2))))
+        log_scale_factor = float(logf(1.2))
     ncand = C.c_int64()
     fn = lib().sgo_search_by_projection_kf
     fn.restype = C.c_int
@@ -296,14 +310,14 @@ def run7point(m1, m2):
     return [F[9 * k:9 * k + 9].reshape(3, 3).copy() for k in range(max(n, 0))]
 
 
-def find_fundamental_ransac(pts1, pts2, thresh=1.0, confidence=0.99, max_iters=1000, small_sample=False):
+def find_fundamental_ransac(pts1, pts2, thresh=1.0, confidence=0.99, max_iters=1000, small_sample=True):
     """cv::findFundamentalMat(pts1, pts2, FM_RANSAC, thresh, confidence) (src/Frame.cc:469-472).
     Returns (F 3x3 float64 or None, mask uint8 [n], info int32 [3] = iterations run, inliers, final niters).
-    With fewer than 15 pairs OpenCV does not run RANSAC: by default None is returned (what the product's kernel reports as "empty F");
-    small_sample=True evaluates OpenCV's LMedS branch for 8..14 pairs (pinned for 14, numerically arbitrary below -- see tests/test_fundamental.py)."""
+    Like OpenCV: 15 pairs and more -> RANSAC; 8..14 -> LMedS (pinned for 14 pairs, numerically arbitrary below -- see tests/test_fundamental.py);
+    exactly 7 -> the first solution of the 7-point solver; fewer -> None.  (`small_sample` is kept for old call sites and ignored.)"""
     a = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2); b = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
     F = np.zeros(9, np.float64); mask = np.zeros(len(a), np.uint8); info = np.zeros(3, np.int32)
-    if len(a) < 15 and not small_sample:
+    if len(a) < 7:
         return None, mask, info
     fn = lib().sgo_find_fundamental_ransac
     fn.restype = C.c_int
@@ -426,7 +440,7 @@ def fuse_search(kf, Tcw, Ow, mp_valid, mp_xyz, mp_normal, min_dist, max_dist, mp
     n = len(a[0])
     bi = np.zeros(n, np.int32); bd = np.zeros(n, np.int32)
     if log_scale_factor is None:
-        log_scale_factor = float(f32(np.log(f32(1.2))))
+        log_scale_factor = float(logf(1.2))
     T = np.ascontiguousarray(Tcw, f32); O_ = np.ascontiguousarray(Ow, f32); s2 = np.ascontiguousarray(inv_level_sigma2, f32)
     lib().sgo_fuse_search(C.byref(kf.c), _p(T), _p(O_), n, *[_p(x) for x in a], C.c_float(th), _p(s2), C.c_float(log_scale_factor), int(sim3_variant),
                           _p(np.ascontiguousarray(xform2, f32)) if xform2 is not None else None, _p(bi), _p(bd))
@@ -440,7 +454,7 @@ def search_by_projection_sim3(kf, Tcw, Ow, mp_valid, mp_xyz, mp_normal, min_dist
     a = [np.ascontiguousarray(mp_valid, np.uint8), np.ascontiguousarray(mp_xyz, f32), np.ascontiguousarray(mp_normal, f32), np.ascontiguousarray(min_dist, f32),
          np.ascontiguousarray(max_dist, f32), np.ascontiguousarray(mp_desc, np.uint8)]
     if log_scale_factor is None:
-        log_scale_factor = float(f32(np.log(f32(1.2))))
+        log_scale_factor = float(logf(1.2))
     T = np.ascontiguousarray(Tcw, f32); O_ = np.ascontiguousarray(Ow, f32)
     m = np.ascontiguousarray(kf_matched, np.int32).copy()
     nm = lib().sgo_search_by_projection_sim3(C.byref(kf.c), _p(T), _p(O_), len(a[0]), *[_p(x) for x in a], C.c_float(th), C.c_float(log_scale_factor), _p(m))
@@ -473,3 +487,54 @@ def pose_optimization(Tcw, has_mp, xyz, kp_xy, octave, uright, inv_level_sigma2,
     fn.restype = C.c_int
     r = fn(_p(T), n, *[_p(x) for x in a], C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_float(bf), _p(out), _p(outl))
     return r, out.reshape(4, 4), outl
+
+
+class SgoChainArgs(C.Structure):
+    _fields_ = [('params', C.c_void_p), ('frames', C.c_void_p), ('nframes', C.c_int32), ('w', C.c_int32), ('h', C.c_int32), ('prev_index', C.c_void_p),
+                ('boxes', C.c_void_p), ('nboxes', C.c_void_p), ('have_dyn', C.c_void_p), ('max_boxes', C.c_int32), ('depth', C.c_void_p), ('u_right_in', C.c_void_p),
+                ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float), ('bf', C.c_float), ('scale_factors', C.c_void_p),
+                ('log_scale_factor', C.c_float), ('point_cap', C.c_int32), ('last_xyz', C.c_void_p), ('last_desc', C.c_void_p), ('last_flags', C.c_void_p),
+                ('last_octave', C.c_void_p), ('last_angle', C.c_void_p), ('last_n', C.c_void_p), ('tcw', C.c_void_p), ('th', C.c_float), ('cap', C.c_int32),
+                ('kps', C.c_void_p), ('desc', C.c_void_p), ('counts', C.c_void_p), ('prev_xy', C.c_void_p), ('F', C.c_void_p), ('f_ok', C.c_void_p),
+                ('keep', C.c_void_p), ('nkeep', C.c_void_p), ('restored', C.c_void_p), ('match', C.c_void_p), ('nmatch', C.c_void_p)]
+
+
+def online_cpus():
+    return int(lib().sgo_online_cpus())
+
+
+class Chain:
+    """The reference's per-frame tracking chain (extract -> LK -> findFundamentalMat -> dyn-reject -> SearchByProjection(cur, last)) for a batch of
+    frames inside the C++ oracle (oracle/chain.cpp): one frame per task, `nthreads` pinned worker threads.  Inputs as bench.py builds them
+    (make_track_inputs); `want_outputs` allocates the per-frame results for parity checks, otherwise only the counts come back."""
+
+    def __init__(self, frames, pidx, ti, cam, cap, nfeatures=1000, th=15.0, want_outputs=True, p=None):
+        self.p = p or params(nfeatures)
+        self.a = {}
+        keep = self.a
+        keep['frames'] = np.ascontiguousarray(frames, np.uint8)
+        B, h, w = keep['frames'].shape
+        keep['pidx'] = np.ascontiguousarray(pidx, np.int32)
+        keep['boxes'] = np.ascontiguousarray(ti['boxes'], np.float32); keep['nb'] = np.ascontiguousarray(ti['nb'], np.int32); keep['have'] = np.ascontiguousarray(ti['have'], np.uint8)
+        keep['ur'] = np.ascontiguousarray(ti['ur'], np.float32)
+        assert keep['ur'].shape[1] == cap
+        keep['sf'] = np.ascontiguousarray(ti['sf'], np.float32)
+        for k in ('lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln', 'T'):
+            keep[k] = np.ascontiguousarray(ti[k])
+        pc = keep['lflags'].shape[1]
+        o = self.out = {}
+        o['counts'] = np.zeros(B, np.int32); o['nkeep'] = np.zeros(B, np.int32); o['restored'] = np.zeros(B, np.int32); o['nmatch'] = np.zeros(B, np.int32); o['f_ok'] = np.zeros(B, np.int32)
+        if want_outputs:
+            o['kps'] = np.zeros((B, cap), KP_DTYPE); o['desc'] = np.zeros((B, cap, 32), np.uint8); o['prev_xy'] = np.zeros((B, cap, 2), np.float32)
+            o['F'] = np.zeros((B, 9), np.float64); o['keep'] = np.zeros((B, cap), np.uint8); o['match'] = np.full((B, cap), -1, np.int32)
+        g = lambda k: o[k].ctypes.data if k in o else None
+        self.args = SgoChainArgs(C.addressof(self.p), keep['frames'].ctypes.data, B, w, h, keep['pidx'].ctypes.data, keep['boxes'].ctypes.data, keep['nb'].ctypes.data,
+                                 keep['have'].ctypes.data, keep['boxes'].shape[1], None, keep['ur'].ctypes.data, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'],
+                                 keep['sf'].ctypes.data, float(logf(keep['sf'][1])), pc, keep['lxyz'].ctypes.data, keep['ldesc'].ctypes.data, keep['lflags'].ctypes.data,
+                                 keep['loct'].ctypes.data, keep['lang'].ctypes.data, keep['ln'].ctypes.data, keep['T'].ctypes.data, th, cap,
+                                 g('kps'), g('desc'), g('counts'), g('prev_xy'), g('F'), g('f_ok'), g('keep'), g('nkeep'), g('restored'), g('match'), g('nmatch'))
+        self.nframes = B
+
+    def run(self, first=0, count=None, nthreads=1, pin=True):
+        count = self.nframes - first if count is None else count
+        return int(lib().sgo_chain_batch(C.byref(self.args), int(first), int(count), int(nthreads), 1 if pin else 0))

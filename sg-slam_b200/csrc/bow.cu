@@ -10,6 +10,8 @@
 //       over the frame features of the bucket; best / second-best by two warp reductions.  Rotation histogram as in the other matchers.
 // Integer work: bit-exact against the CPU restatement.
 #include <cuda_runtime.h>
+
+#include <stdexcept>
 #include <string>
 #include <cstdlib>
 #include <cstdio>
@@ -270,8 +272,8 @@ SGS_API void sgs_vocabulary_destroy(sgs_vocabulary* v) {
     delete v;
 }
 
-SGS_API int sgs_vocabulary_create(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* node_desc, const double* node_weight,
-                                  sgs_vocabulary** out) {
+static int vocabulary_create_impl(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* node_desc, bool desc_on_device,
+                                  const double* node_weight, sgs_vocabulary** out) {
     if (!out || !parent || !node_desc || !node_weight || nnodes < 2 || k < 2 || L < 1) { set_error("sgs_vocabulary_create: bad argument"); return SGS_ERR_INVALID; }
     *out = nullptr;
     std::vector<int32_t> count(nnodes, 0), first(nnodes, 0), children(nnodes - 1), word(nnodes, -1), fill(nnodes, 0);
@@ -298,11 +300,21 @@ SGS_API int sgs_vocabulary_create(int device, int k, int L, int nnodes, const in
     if (e == cudaSuccess) e = cudaMemcpy(v->d_count, count.data(), 4 * (size_t)nnodes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(v->d_children, children.data(), 4 * (size_t)(nnodes - 1), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(v->d_word, word.data(), 4 * (size_t)nnodes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(v->d_desc, node_desc, 32 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_desc, node_desc, 32 * (size_t)nnodes, desc_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(v->d_weight, node_weight, 8 * (size_t)nnodes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error("sgs_vocabulary_create: %s", cudaGetErrorString(e)); sgs_vocabulary_destroy(v); return SGS_ERR_CUDA; }
     *out = v;
     return SGS_OK;
+}
+
+SGS_API int sgs_vocabulary_create(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* node_desc, const double* node_weight,
+                                  sgs_vocabulary** out) {
+    return vocabulary_create_impl(device, k, L, nnodes, parent, node_desc, false, node_weight, out);
+}
+// node descriptors already on the device (the buffer an ncclBroadcast just filled): consumed in place, no bounce through the host
+SGS_API int sgs_vocabulary_create_device(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* d_node_desc, const double* node_weight,
+                                         sgs_vocabulary** out) {
+    return vocabulary_create_impl(device, k, L, nnodes, parent, d_node_desc, true, node_weight, out);
 }
 
 // ---- vocabulary files: ORBVocabulary::loadFromTextFile / loadFromBinaryFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1351-1420, :1467-1508).
@@ -372,7 +384,8 @@ SGS_API int sgs_vocabulary_parse_file(const char* path, int* k, int* L, int* nno
                                       int cap) {
     if (!path || !nnodes) { set_error("sgs_vocabulary_parse_file: bad argument"); return SGS_ERR_INVALID; }
     VocFile V;
-    const int rc = parse_vocabulary_file(path, V);
+    int rc = SGS_OK;
+    try { rc = parse_vocabulary_file(path, V); } catch (const std::exception& ex) { set_error("sgs_vocabulary_parse_file: %s while reading %s", ex.what(), path); return SGS_ERR_INVALID; }
     if (rc != SGS_OK) return rc;
     const int n = (int)V.parent.size();
     if (k) *k = V.k;
@@ -391,7 +404,8 @@ SGS_API int sgs_vocabulary_load(const char* path, int device, sgs_vocabulary** o
     if (!path || !out) { set_error("sgs_vocabulary_load: bad argument"); return SGS_ERR_INVALID; }
     *out = nullptr;
     VocFile V;
-    const int rc = parse_vocabulary_file(path, V);
+    int rc = SGS_OK;
+    try { rc = parse_vocabulary_file(path, V); } catch (const std::exception& ex) { set_error("sgs_vocabulary_load: %s while reading %s", ex.what(), path); return SGS_ERR_INVALID; }
     if (rc != SGS_OK) return rc;
     const int n = (int)V.parent.size();
     std::vector<int> nchild(n, 0);

@@ -22,8 +22,8 @@ namespace sgs {
 namespace tc {
 
 constexpr int kBM = 128;        // pixels per tile = UMMA M = TMEM lanes
-constexpr int kBK = 32;         // floats per k-block = one 128-byte swizzle row
-constexpr int kMaxStages = 4;
+constexpr int kBK = 32;         // floats per k-block = one 128-byte swizzle row (16 = one 64-byte row for layers with at most 16 input channels)
+constexpr int kMaxStages = 8;
 constexpr int kMaxNT = 128;      // output channels per tile (TMEM columns per CTA)
 
 // ---------------------------------------------------------------------------------------------------------------- PTX wrappers
@@ -32,6 +32,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm vo
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -63,10 +64,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes (one swizzle row) and whose 8-row groups are 1024 bytes apart
-// (cute::UMMA::SmemDescriptor: start >> 4 | LBO << 16 | SBO << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61).
-__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// Shared-memory matrix descriptor of a K-major tile whose rows are one swizzle row (ROWB = 128 or 64 bytes) and whose 8-row groups are 8 * ROWB
+// bytes apart (cute::UMMA::SmemDescriptor: start >> 4 | LBO << 16 | SBO << 32 | version 1 << 46 | layout << 61; SWIZZLE_128B = 2, SWIZZLE_64B = 4).
+template <int ROWB>
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t saddr) {
+    static_assert(ROWB == 128 || ROWB == 64, "one swizzle row per tile row");
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)((8 * ROWB) >> 4) << 32) | (1ull << 46) | ((uint64_t)(ROWB == 128 ? 2 : 4) << 61);
 }
 // cute::UMMA::InstrDescriptor for kind::tf32: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
 __host__ __device__ inline uint32_t tf32_idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24); }
@@ -79,8 +82,10 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
 
 struct TcGeom {
     int npix, Cin, Cout;          // rows of X, channels in / out
-    int NT, KB, stages;           // output channels per tile (multiple of 16), k-blocks, pipeline depth
-    uint32_t tmem_cols;           // power of two >= max(32, NT)
+    int NT, KB, stages;           // output channels per tile (multiple of 16), k-blocks, pipeline depth of the operand ring
+    int m_tiles;                  // 128-pixel tiles
+    int b_resident;               // the CTA's weight tile (all k-blocks, hi + lo) is loaded once and stays in shared memory
+    uint32_t tmem_cols;           // power of two >= 2 * NT: two accumulators (the epilogue of tile i overlaps the MMAs of tile i + 1)
     int HW;                       // pixels per frame (output addressing)
     int64_t frame_stride;         // floats between consecutive frames of the output
     int64_t base_off;             // float offset of frame 0 of the output inside `out`
@@ -88,31 +93,44 @@ struct TcGeom {
     int vec_ok;                   // 16-byte aligned rows: float4 stores
 };
 
+// warp 0: TMA producer, warp 1: MMA issuer (+ TMEM owner), warps 2 .. 2+EPW-1: epilogue (EPW = 4 or 8), the last four warps: operand split
+constexpr int tc_threads(int epw) { return (2 + epw + 4) * 32; }
+
+// Persistent, warp-specialised.  CTA (x, y) owns output-channel tile y and walks the pixel tiles x, x + gridDim.x, ...
+//   producer  : TMA loads of the activation k-blocks (and of the weight k-blocks unless resident) into a ring of `stages` slots
+//   split     : 128 threads turn each landed FP32 activation block into TF32 hi (in place) + lo
+//   MMA       : one thread issues 3 tcgen05.mma per 8-wide k-step into one of two TMEM accumulators, commits to the ring / to the epilogue
+//   epilogue  : 128 threads (one TMEM lane = one pixel each) read the accumulator, add bias, apply the tail, store NHWC
+// mbarriers: full[s] (TMA -> split), ready[s] (split -> MMA), empty[s] (MMA -> producer), bfull (resident weights), acc_full[a] / acc_empty[a].
 // EpiFn: struct with  template <int N> __device__ void run(float (&v)[N], int64_t idx0) const   applied to N consecutive channels of one pixel;
 // idx0 = pixel * Cout + channel (the NHWC index of same-shape operand tensors).
-template <class EpiFn>
-__global__ void __launch_bounds__(kBM) conv1x1_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
-                                                         const __grid_constant__ CUtensorMap mapBl, const float* __restrict__ bias, float* __restrict__ out,
-                                                         const TcGeom G, const EpiFn epi) {
+template <class EpiFn, int BKT, int EPW>
+__global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+                                                                   const __grid_constant__ CUtensorMap mapBl, const float* __restrict__ bias,
+                                                                   float* __restrict__ out, const TcGeom G, const EpiFn epi) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_accum;
+    __shared__ __align__(8) uint64_t s_full[kMaxStages], s_ready[kMaxStages], s_empty[kMaxStages], s_bfull, s_acc_full[2], s_acc_empty[2];
     __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * G.NT;
-    // stage layout: A (hi in place of the landed FP32 tile) | A lo | B hi | B lo, every part a multiple of 1024 bytes
-    const uint32_t a_bytes = kBM * kBK * 4, b_bytes = (uint32_t)G.NT * kBK * 4, stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.y * G.NT;
+    constexpr int ROWB = BKT * 4;                                             // bytes per operand row = one swizzle row
+    const uint32_t a_bytes = kBM * ROWB, b_bytes = (uint32_t)G.NT * ROWB;
+    const uint32_t stage_bytes = 2 * a_bytes + (G.b_resident ? 0u : 2 * b_bytes);
     const uint32_t sbase = (smem_addr(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - smem_addr(smem_raw));
+    const uint32_t bres = sbase + (uint32_t)G.stages * stage_bytes;          // resident weights: [kb][hi | lo]
+    const int my_tiles = (G.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
-        for (int s = 0; s < G.stages; ++s) { mbar_init(smem_addr(&s_full[s]), 1); mbar_init(smem_addr(&s_empty[s]), 1); }
-        mbar_init(smem_addr(&s_accum), 1);
+        for (int s = 0; s < G.stages; ++s) { mbar_init(smem_addr(&s_full[s]), 1); mbar_init(smem_addr(&s_ready[s]), 4); mbar_init(smem_addr(&s_empty[s]), 1); }
+        mbar_init(smem_addr(&s_bfull), 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_addr(&s_acc_full[a]), 1); mbar_init(smem_addr(&s_acc_empty[a]), EPW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
     }
-    if (warp == 0) {
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "r"(G.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -121,118 +139,159 @@ __global__ void __launch_bounds__(kBM) conv1x1_tc_kernel(const __grid_constant__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
-    auto issue_loads = [&](int kb) {
-        const int s = kb % G.stages;
-        const uint32_t st = sbase + (uint32_t)s * stage_bytes, bar = smem_addr(&s_full[s]);
-        mbar_expect_tx(bar, a_bytes + 2 * b_bytes);
-        tma_load_2d(st, &mapA, kb * kBK, m0, bar);
-        tma_load_2d(st + 2 * a_bytes, &mapBh, kb * kBK, n0, bar);
-        tma_load_2d(st + 2 * a_bytes + b_bytes, &mapBl, kb * kBK, n0, bar);
-    };
-    if (tid == 0)
-        for (int kb = 0; kb < G.KB && kb < G.stages; ++kb) issue_loads(kb);
-
-    const uint32_t idesc = tf32_idesc(G.NT);
-    for (int kb = 0; kb < G.KB; ++kb) {
-        const int s = kb % G.stages;
-        const uint32_t ph = (uint32_t)(kb / G.stages) & 1u;
-        mbar_wait(smem_addr(&s_full[s]), ph);
-        // split the activation tile: hi in place, lo next to it (same swizzled position)
-        uint4* ahi = reinterpret_cast<uint4*>(gbase + (size_t)s * stage_bytes);
-        uint4* alo = reinterpret_cast<uint4*>(gbase + (size_t)s * stage_bytes + a_bytes);
-#pragma unroll
-        for (int j = 0; j < (kBM * kBK / 4) / kBM; ++j) {
-            const int i = tid + j * kBM;
-            const uint4 x = ahi[i];
-            uint4 h, l;
-            split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-            ahi[i] = h; alo[i] = l;
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            if (G.b_resident) {
+                mbar_expect_tx(smem_addr(&s_bfull), (uint32_t)G.KB * 2 * b_bytes);
+                for (int kb = 0; kb < G.KB; ++kb) {
+                    tma_load_2d(bres + (uint32_t)kb * 2 * b_bytes, &mapBh, kb * BKT, n0, smem_addr(&s_bfull));
+                    tma_load_2d(bres + (uint32_t)kb * 2 * b_bytes + b_bytes, &mapBl, kb * BKT, n0, smem_addr(&s_bfull));
+                }
+            }
+            uint32_t g = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * kBM;
+                for (int kb = 0; kb < G.KB; ++kb, ++g) {
+                    const uint32_t s = g % (uint32_t)G.stages, ph = (g / (uint32_t)G.stages) & 1u;
+                    mbar_wait(smem_addr(&s_empty[s]), ph ^ 1u);
+                    const uint32_t st = sbase + s * stage_bytes, bar = smem_addr(&s_full[s]);
+                    mbar_expect_tx(bar, a_bytes + (G.b_resident ? 0u : 2 * b_bytes));
+                    tma_load_2d(st, &mapA, kb * BKT, m0, bar);
+                    if (!G.b_resident) {
+                        tma_load_2d(st + 2 * a_bytes, &mapBh, kb * BKT, n0, bar);
+                        tma_load_2d(st + 2 * a_bytes + b_bytes, &mapBl, kb * BKT, n0, bar);
+                    }
+                }
+            }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        __syncthreads();
-        if (tid == 0) {
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = tf32_idesc(G.NT);
+            if (G.b_resident) mbar_wait(smem_addr(&s_bfull), 0);
+            uint32_t g = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
+                mbar_wait(smem_addr(&s_acc_empty[ab]), aph ^ 1u);                   // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem + ab * (uint32_t)G.NT;
+                for (int kb = 0; kb < G.KB; ++kb, ++g) {
+                    const uint32_t s = g % (uint32_t)G.stages, ph = (g / (uint32_t)G.stages) & 1u;
+                    mbar_wait(smem_addr(&s_ready[s]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = sbase + s * stage_bytes;
+                    const uint32_t bh0 = G.b_resident ? bres + (uint32_t)kb * 2 * b_bytes : st + 2 * a_bytes;
+                    const int ksteps = min(BKT, G.Cin - kb * BKT + 7) >> 3;         // 8-wide k-steps that hold real channels (the rest is zero fill)
+                    for (int j = 0; j < ksteps; ++j) {
+                        const uint64_t ah = kmajor_desc<ROWB>(st + j * 32), al = kmajor_desc<ROWB>(st + a_bytes + j * 32);
+                        const uint64_t bh = kmajor_desc<ROWB>(bh0 + j * 32), bl = kmajor_desc<ROWB>(bh0 + b_bytes + j * 32);
+                        umma_tf32(acc, al, bh, idesc, (kb | j) != 0);
+                        umma_tf32(acc, ah, bl, idesc, 1);
+                        umma_tf32(acc, ah, bh, idesc, 1);
+                    }
+                    umma_commit(smem_addr(&s_empty[s]));                            // slot free once these MMAs have read it
+                }
+                umma_commit(smem_addr(&s_acc_full[ab]));                            // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 2 + EPW) {
+        // ------------------------------------------------------------------------------------------------ operand split (128 threads)
+        const int t = tid - (2 + EPW) * 32;
+        uint32_t g = 0;
+        for (int it = 0; it < my_tiles; ++it)
+            for (int kb = 0; kb < G.KB; ++kb, ++g) {
+                const uint32_t s = g % (uint32_t)G.stages, ph = (g / (uint32_t)G.stages) & 1u;
+                mbar_wait(smem_addr(&s_full[s]), ph);
+                uint4* ahi = reinterpret_cast<uint4*>(gbase + (size_t)s * stage_bytes);
+                uint4* alo = reinterpret_cast<uint4*>(gbase + (size_t)s * stage_bytes + a_bytes);
+#pragma unroll
+                for (int j = 0; j < (kBM * BKT / 4) / 128; ++j) {
+                    const int i = t + j * 128;
+                    const uint4 x = ahi[i];
+                    uint4 h, l;
+                    split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+                    ahi[i] = h; alo[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_addr(&s_ready[s]));
+            }
+    } else {
+        // ------------------------------------------------------------------------------------------------ epilogue: warp w reads TMEM lane quadrant w % 4;
+        // with eight epilogue warps the two warps of a quadrant take alternate 32-channel chunks
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+        for (int it = 0; it < my_tiles; ++it) {
+            const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
+            const int p = ((int)blockIdx.x + it * (int)gridDim.x) * kBM + quad * 32 + lane;
+            const bool live = p < G.npix;
+            float* orow = nullptr;
+            int64_t idx_row = 0;
+            if (live) {
+                const int f = p / G.HW, pl = p - f * G.HW;
+                orow = out + G.base_off + (int64_t)f * G.frame_stride + (int64_t)pl * G.pitch;
+                idx_row = (int64_t)p * G.Cout;
+            }
+            mbar_wait(smem_addr(&s_acc_full[ab]), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t st = sbase + (uint32_t)s * stage_bytes;
-            const int ksteps = min(kBK, G.Cin - kb * kBK + 7) >> 3;          // 8-wide k-steps that hold real channels (the rest of the block is zero fill)
-            for (int j = 0; j < ksteps; ++j) {
-                const uint64_t ah = kmajor_sw128_desc(st + j * 32), al = kmajor_sw128_desc(st + a_bytes + j * 32);
-                const uint64_t bh = kmajor_sw128_desc(st + 2 * a_bytes + j * 32), bl = kmajor_sw128_desc(st + 2 * a_bytes + b_bytes + j * 32);
-                umma_tf32(tmem, al, bh, idesc, (kb | j) != 0);
-                umma_tf32(tmem, ah, bl, idesc, 1);
-                umma_tf32(tmem, ah, bh, idesc, 1);
-            }
-            umma_commit(smem_addr(&s_empty[s]));
-            if (kb + G.stages < G.KB) {               // refill this stage once its MMAs have read it
-                mbar_wait(smem_addr(&s_empty[s]), ph);
-                issue_loads(kb + G.stages);
-            } else if (kb == G.KB - 1) {
-                umma_commit(smem_addr(&s_accum));
-            }
-        }
-    }
-    mbar_wait(smem_addr(&s_accum), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // epilogue: this thread owns TMEM lane 32*warp + lane = pixel m0 + tid
-    const int p = m0 + tid;
-    const bool live = p < G.npix;
-    float* orow = nullptr;
-    int64_t idx_row = 0;
-    if (live) {
-        const int f = p / G.HW, pl = p - f * G.HW;
-        orow = out + G.base_off + (int64_t)f * G.frame_stride + (int64_t)pl * G.pitch;
-        idx_row = (int64_t)p * G.Cout;
-    }
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < G.NT; c0 += 32) {
-        if (n0 + c0 >= G.Cout) break;                                   // uniform: padding columns of the last tile
-        uint32_t r[2][16];
-        const bool two = c0 + 16 < G.NT && n0 + c0 + 16 < G.Cout;       // uniform
-        tmem_ld16(trow + (uint32_t)c0, r[0]);
-        if (two) tmem_ld16(trow + (uint32_t)c0 + 16u, r[1]);
-        tmem_ld_wait();
-        if (!live) continue;
+            const uint32_t tacc = trow + ab * (uint32_t)G.NT;
+            for (int c0 = 32 * half; c0 < G.NT; c0 += 32 * (EPW / 4)) {
+                if (n0 + c0 >= G.Cout) break;                                   // uniform: padding columns of the last tile
+                uint32_t r[2][16];
+                const bool two = c0 + 16 < G.NT && n0 + c0 + 16 < G.Cout;       // uniform
+                tmem_ld16(tacc + (uint32_t)c0, r[0]);
+                if (two) tmem_ld16(tacc + (uint32_t)c0 + 16u, r[1]);
+                const bool full0 = G.Cout - (n0 + c0) >= 16, full1 = two && G.Cout - (n0 + c0 + 16) >= 16;
+                float4 bq[2][4];                                                // the bias of the chunk travels while the TMEM load completes
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (h == 1 && !two) break;
-            const int co = n0 + c0 + 16 * h;
-            const int nv = min(16, G.Cout - co);
-            float v[16];
-            if (nv == 16) {
-                if (bias) {
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int q = 0; q < 16; q += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + co + q));
-                        v[q] = __fadd_rn(__uint_as_float(r[h][q]), b.x); v[q + 1] = __fadd_rn(__uint_as_float(r[h][q + 1]), b.y);
-                        v[q + 2] = __fadd_rn(__uint_as_float(r[h][q + 2]), b.z); v[q + 3] = __fadd_rn(__uint_as_float(r[h][q + 3]), b.w);
-                    }
-                } else {
+                    for (int q = 0; q < 4; ++q)
+                        bq[h][q] = (bias && (h == 0 ? full0 : full1)) ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + 16 * h) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                tmem_ld_wait();
+                if (!live) continue;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[h][q]);
-                }
-                epi.template run<16>(v, idx_row + co);
-                if (G.vec_ok) {
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && !two) break;
+                    const int co = n0 + c0 + 16 * h;
+                    const int nv = min(16, G.Cout - co);
+                    float v[16];
+                    if (nv == 16) {
 #pragma unroll
-                    for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(orow + co + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-                } else {
+                        for (int q = 0; q < 4; ++q) {
+                            v[4 * q] = __fadd_rn(__uint_as_float(r[h][4 * q]), bq[h][q].x); v[4 * q + 1] = __fadd_rn(__uint_as_float(r[h][4 * q + 1]), bq[h][q].y);
+                            v[4 * q + 2] = __fadd_rn(__uint_as_float(r[h][4 * q + 2]), bq[h][q].z); v[4 * q + 3] = __fadd_rn(__uint_as_float(r[h][4 * q + 3]), bq[h][q].w);
+                        }
+                        epi.template run<16>(v, idx_row + co);
+                        if (G.vec_ok) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) orow[co + q] = v[q];
-                }
-            } else {
+                            for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(orow + co + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                        } else {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    if (q < nv) {
-                        float one[1] = {__fadd_rn(__uint_as_float(r[h][q]), bias ? __ldg(bias + co + q) : 0.f)};
-                        epi.template run<1>(one, idx_row + co + q);
-                        orow[co + q] = one[0];
+                            for (int q = 0; q < 16; ++q) orow[co + q] = v[q];
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            if (q < nv) {
+                                float one[1] = {__fadd_rn(__uint_as_float(r[h][q]), bias ? __ldg(bias + co + q) : 0.f)};
+                                epi.template run<1>(one, idx_row + co + q);
+                                orow[co + q] = one[0];
+                            }
+                        }
                     }
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_addr(&s_acc_empty[ab]));                // this warp's quadrant of the accumulator is drained
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(G.tmem_cols) : "memory");
+    __syncwarp();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(G.tmem_cols) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------- host side
@@ -250,20 +309,20 @@ inline PFN_tmap_encode tmap_encoder() {
     }
     return fn;
 }
-// 2-D FP32 tensor [rows][cols] with `pitch` floats between rows; box = 32 floats x box_rows, 128-byte swizzle, zero fill outside
-inline bool encode_kmajor_map(CUtensorMap* m, const float* base, int64_t rows, int cols, int64_t pitch, int box_rows) {
+// 2-D FP32 tensor [rows][cols] with `pitch` floats between rows; box = bk floats (one 128- or 64-byte swizzle row) x box_rows, zero fill outside
+inline bool encode_kmajor_map(CUtensorMap* m, const float* base, int64_t rows, int cols, int64_t pitch, int box_rows, int bk) {
     PFN_tmap_encode fn = tmap_encoder();
-    if (!fn || ((uintptr_t)base & 15) || (pitch & 3) || box_rows < 1 || box_rows > 256) return false;
+    if (!fn || ((uintptr_t)base & 15) || (pitch & 3) || box_rows < 1 || box_rows > 256 || (bk != 32 && bk != 16)) return false;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)pitch * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t est[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct GemmPlan {
-    int Cin = 0, Cout = 0, NT = 0, n_tiles = 0, KB = 0, stages = 0, smem_bytes = 0, Kp = 0, Np = 0;
+    int Cin = 0, Cout = 0, NT = 0, n_tiles = 0, KB = 0, BK = kBK, epw = 4, stages = 0, smem_bytes = 0, Kp = 0, Np = 0, b_resident = 0, ctas_per_sm = 1;
     uint32_t tmem_cols = 0;
     float* d_whi = nullptr; float* d_wlo = nullptr;
     CUtensorMap map_hi, map_lo;
@@ -279,22 +338,36 @@ inline void split_tf32_host(float x, float& hi, float& lo) {
     memcpy(&lo, &l, 4);
 }
 
-// Splits and uploads W [Cout][Cin], picks the tiling.  Returns false when TMA is unavailable or an allocation fails.
-inline bool plan_weights(const float* W, int Cin, int Cout, GemmPlan* P) {
+// Tiling of one layer (no device access): output-channel tiles of at most kMaxNT, weights resident when all their k-blocks fit in 96 KB,
+// ring depth from what is left of the shared memory; small weight tiles leave room for two CTAs per SM (more loads in flight, two MMA issuers).
+inline void plan_tiling(int Cin, int Cout, GemmPlan* P) {
     P->Cin = Cin; P->Cout = Cout;
-    const int nt = (Cout + kMaxNT - 1) / kMaxNT;                         // output-channel tiles of at most kMaxNT (several CTAs stay resident per SM)
+    const int nt = (Cout + kMaxNT - 1) / kMaxNT;
     P->NT = ((Cout + nt - 1) / nt + 15) & ~15;
     P->n_tiles = (Cout + P->NT - 1) / P->NT;
-    P->KB = (Cin + kBK - 1) / kBK;
-    P->Kp = P->KB * kBK; P->Np = P->n_tiles * P->NT;
-    const int stage_bytes = 2 * kBM * kBK * 4 + 2 * P->NT * kBK * 4;
-    int st = P->KB >= 3 ? 2 : 1;                                         // short contractions: all loads are in flight at once anyway
-    if (st > P->KB) st = P->KB;
+    P->BK = Cin <= 16 ? 16 : kBK;                                        // at most 16 input channels: 64-byte operand rows, half the ring slot
+    P->KB = (Cin + P->BK - 1) / P->BK;
+    P->Kp = P->KB * P->BK; P->Np = P->n_tiles * P->NT;
+    const int a_stage = 2 * kBM * P->BK * 4, b_block = 2 * P->NT * P->BK * 4;
+    const int b_all = P->KB * b_block;
+    P->b_resident = b_all <= 96 * 1024 ? 1 : 0;
+    P->ctas_per_sm = (P->b_resident && b_all + 2 * a_stage + 1024 <= 110 * 1024) ? 2 : 1;      // resident weights + two ring slots fit twice: two CTAs per SM
+    P->epw = P->ctas_per_sm == 2 ? 4 : 8;                                // one CTA per SM: eight epilogue warps keep up with wide output tiles
+    const int budget = (P->ctas_per_sm == 2 ? 110 : 220) * 1024 - 1024 - (P->b_resident ? b_all : 0);
+    const int stage_bytes = a_stage + (P->b_resident ? 0 : b_block);
+    int st = budget / stage_bytes;
+    if (st > kMaxStages) st = kMaxStages;
+    if (st < 2) st = 2;
     P->stages = st;
-    P->smem_bytes = st * stage_bytes + 1024;
+    P->smem_bytes = st * stage_bytes + (P->b_resident ? b_all : 0) + 1024;
     uint32_t tc = 32;
-    while ((int)tc < P->NT) tc <<= 1;
+    while ((int)tc < 2 * P->NT) tc <<= 1;
     P->tmem_cols = tc;
+}
+
+// Splits and uploads W [Cout][Cin], picks the tiling.  Returns false when TMA is unavailable or an allocation fails.
+inline bool plan_weights(const float* W, int Cin, int Cout, GemmPlan* P) {
+    plan_tiling(Cin, Cout, P);
     std::vector<float> hi((size_t)P->Np * P->Kp, 0.f), lo((size_t)P->Np * P->Kp, 0.f);
     for (int co = 0; co < Cout; ++co)
         for (int c = 0; c < Cin; ++c) split_tf32_host(W[(size_t)co * Cin + c], hi[(size_t)co * P->Kp + c], lo[(size_t)co * P->Kp + c]);
@@ -302,55 +375,93 @@ inline bool plan_weights(const float* W, int Cin, int Cout, GemmPlan* P) {
     if (cudaMalloc((void**)&P->d_wlo, lo.size() * 4) != cudaSuccess) return false;
     if (cudaMemcpy(P->d_whi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return false;
     if (cudaMemcpy(P->d_wlo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return false;
-    return encode_kmajor_map(&P->map_hi, P->d_whi, P->Np, P->Kp, P->Kp, P->NT) && encode_kmajor_map(&P->map_lo, P->d_wlo, P->Np, P->Kp, P->Kp, P->NT);
+    return encode_kmajor_map(&P->map_hi, P->d_whi, P->Np, P->Kp, P->Kp, P->NT, P->BK) && encode_kmajor_map(&P->map_lo, P->d_wlo, P->Np, P->Kp, P->Kp, P->NT, P->BK);
 }
 inline void free_plan(GemmPlan* P) { cudaFree(P->d_whi); cudaFree(P->d_wlo); P->d_whi = P->d_wlo = nullptr; }
 
 // ---- stand-alone tails of the unit harness (the detector passes its own functor built from the ncnn element-wise chain)
 enum { TK_NONE = 0, TK_RELU, TK_CLIP, TK_HSWISH, TK_ADD_T, TK_SE_TAIL };
+// x / c.  For c == 6 (the hard-swish / hard-sigmoid divisor of the model) the quotient comes from the reciprocal and one FMA correction:
+// q = RN(x * r), q' = RN(q + RN(x - 6q) * r), which equals the correctly rounded RN(x / 6) for every float with |x| >= 2^-100 and for zeros up to the
+// sign of zero (verified exhaustively on the host over all 2^32 bit patterns); below 2^-100 it may differ from the IEEE quotient in the last bit of a
+// denormal.  Both the fused and the layer-by-layer execution use this function.  (The generic IEEE division takes its slow path whenever the dividend is
+// zero -- half of all hard-swish outputs.)
+__device__ __forceinline__ float div_scalar(float x, float c) {
+    if (c == 6.0f) {
+        const float r = 0x1.555556p-3f;                 // RN(1/6)
+        const float q = __fmul_rn(x, r);
+        return __fmaf_rn(__fmaf_rn(-6.0f, q, x), r, q);
+    }
+    return __fdiv_rn(x, c);
+}
+
 struct GemmTail {
     int kind;
     float a, lo, hi, b;
     const float* t1; const float* t2;
     template <int N>
     __device__ __forceinline__ void run(float (&v)[N], int64_t idx0) const {
+        switch (kind) {
+        case TK_RELU:
 #pragma unroll
-        for (int q = 0; q < N; ++q) {
-            float x = v[q];
-            switch (kind) {
-            case TK_RELU: x = fmaxf(x, 0.f); break;
-            case TK_CLIP: x = fminf(fmaxf(x, lo), hi); break;
-            case TK_HSWISH: x = __fdiv_rn(__fmul_rn(x, fminf(fmaxf(__fadd_rn(x, a), lo), hi)), b); break;
-            case TK_ADD_T: x = __fadd_rn(x, __ldg(t1 + idx0 + q)); break;
-            case TK_SE_TAIL: x = __fadd_rn(__fmul_rn(__ldg(t1 + idx0 + q), __fdiv_rn(fminf(fmaxf(__fadd_rn(x, a), lo), hi), b)), __ldg(t2 + idx0 + q)); break;
-            default: break;
-            }
-            v[q] = x;
+            for (int q = 0; q < N; ++q) v[q] = fmaxf(v[q], 0.f);
+            break;
+        case TK_CLIP:
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[q] = fminf(fmaxf(v[q], lo), hi);
+            break;
+        case TK_HSWISH:
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[q] = div_scalar(__fmul_rn(v[q], fminf(fmaxf(__fadd_rn(v[q], a), lo), hi)), b);
+            break;
+        case TK_ADD_T:
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[q] = __fadd_rn(v[q], __ldg(t1 + idx0 + q));
+            break;
+        case TK_SE_TAIL:
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[q] = __fadd_rn(__fmul_rn(__ldg(t1 + idx0 + q), div_scalar(fminf(fmaxf(__fadd_rn(v[q], a), lo), hi), b)), __ldg(t2 + idx0 + q));
+            break;
+        default: break;
         }
     }
 };
 
+inline int sm_count() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148; }
+    return n;
+}
+
+// mapA: encode_kmajor_map over the input activations (any number of rows >= npix; box kBM rows, P.BK columns)
 template <class EpiFn>
-inline bool launch_conv1x1_tc_geom(const GemmPlan& P, const float* x, int64_t in_pitch, int npix, const float* bias, float* out, int HW, int64_t frame_stride,
-                                   int64_t base_off, int pitch, const EpiFn& epi, cudaStream_t st) {
-    CUtensorMap mapA;
-    if (!encode_kmajor_map(&mapA, x, npix, P.Cin, in_pitch, kBM)) return false;
+inline bool launch_conv1x1_tc_map(const GemmPlan& P, const CUtensorMap& mapA, int npix, const float* bias, float* out, int HW, int64_t frame_stride, int64_t base_off,
+                                  int pitch, const EpiFn& epi, cudaStream_t st) {
     TcGeom G;
     G.npix = npix; G.Cin = P.Cin; G.Cout = P.Cout; G.NT = P.NT; G.KB = P.KB; G.stages = P.stages; G.tmem_cols = P.tmem_cols;
+    G.m_tiles = (npix + kBM - 1) / kBM; G.b_resident = P.b_resident;
     G.HW = HW; G.frame_stride = frame_stride; G.base_off = base_off; G.pitch = pitch;
     G.vec_ok = ((pitch & 3) == 0 && (frame_stride & 3) == 0 && (base_off & 3) == 0 && (((uintptr_t)out) & 15) == 0) ? 1 : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(conv1x1_tc_kernel<EpiFn>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return false;
-        attr_set = true;
-    }
-    const dim3 grid((npix + kBM - 1) / kBM, P.n_tiles);
-    conv1x1_tc_kernel<EpiFn><<<grid, kBM, P.smem_bytes, st>>>(mapA, P.map_hi, P.map_lo, bias, out, G, epi);
+    int gx = (sm_count() * P.ctas_per_sm) / P.n_tiles;                  // one wave of persistent CTAs
+    if (gx < 1) gx = 1;
+    if (gx > G.m_tiles) gx = G.m_tiles;
+    const dim3 grid(gx, P.n_tiles);
+    auto go = [&](auto kern, int threads) -> bool {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return false;   // cheap; per device
+        kern<<<grid, threads, P.smem_bytes, st>>>(mapA, P.map_hi, P.map_lo, bias, out, G, epi);
+        return true;
+    };
+    bool ok;
+    if (P.BK == 16) ok = P.epw == 4 ? go(conv1x1_tc_kernel<EpiFn, 16, 4>, tc_threads(4)) : go(conv1x1_tc_kernel<EpiFn, 16, 8>, tc_threads(8));
+    else ok = P.epw == 4 ? go(conv1x1_tc_kernel<EpiFn, 32, 4>, tc_threads(4)) : go(conv1x1_tc_kernel<EpiFn, 32, 8>, tc_threads(8));
+    if (!ok) return false;
     return cudaGetLastError() == cudaSuccess;
 }
 
 inline bool launch_conv1x1_tc(const GemmPlan& P, const float* x, int in_pitch, int npix, const float* bias, float* out, int out_pitch, const GemmTail& T, cudaStream_t st) {
-    return launch_conv1x1_tc_geom(P, x, in_pitch, npix, bias, out, npix > 0 ? npix : 1, 0, 0, out_pitch, T, st);
+    CUtensorMap mapA;
+    if (!encode_kmajor_map(&mapA, x, npix, P.Cin, in_pitch, kBM, P.BK)) return false;
+    return launch_conv1x1_tc_map(P, mapA, npix, bias, out, npix > 0 ? npix : 1, 0, 0, out_pitch, T, st);
 }
 
 }  // namespace tc

@@ -5,17 +5,17 @@
 // The handle parses the ncnn text graph and weight blob itself, infers every blob shape for the fixed 3x300x300 input (Detector2D.h:70),
 // folds the constant sub-graphs (MemoryData scalars, PriorBox, their Concat) on the host, and turns the rest into a flat list of kernels:
 //   preprocess     : Mat::from_pixels_resize + substract_mean_normalize (Detector2D.cc:39-40), fixed-point bilinear (bit-exact with cv::resize)
-//   conv1x1        : 90 % of the MACs; GEMM  W[Cout x Cin] * X[Cin x (frames*H*W)], bias + fused element-wise tail (tensor cores, see below)
-//   dwconv / conv  : depth-wise 3x3 / 5x5 and the first dense 3x3, one output per thread, fused tail
+//   conv1x1        : 90 % of the MACs; out[p][co] = bias[co] + sum_ci X[p][ci] * W[co][ci] over the pixels of all frames, as a TMA-fed tcgen05 / TMEM
+//                    GEMM with error-compensated TF32 operands (conv1x1_tc.cuh), bias + fused element-wise tail in its epilogue
+//   dwconv / conv  : depth-wise 3x3 / 5x5 (channel-vectorised) and the few dense convolutions the GEMM does not take (first layer, Cin not a multiple of 4)
 //   eltwise        : whatever element-wise chain could not be attached to a producer
-//   permute / copy : CHW -> HWC of the head outputs and their Concat
 //   softmax, detection-output (per class: threshold, sort, top-k, greedy NMS; per frame: merge, top-k, Detector2D.cc:52-88)
 // Element-wise layers (BinaryOp with a constant / a tensor / the chain's own start value, Clip, ReLU) that follow a producer are applied in
 // the producer's epilogue in graph order, one rounding per op, so fused and unfused execution give identical bits.
-// Layout: every blob is [frames][c][h][w] FP32 (ncnn's c,h,w order per frame); activations live in a pool planned by liveness.
-// The 1x1 convolutions (90 % of the MACs) run on the tensor cores with FP32-grade accuracy: every operand is split into two TF32 values and each
-// product is three mma.sync (error-compensated TF32); flags bit 2 selects a plain FP32 FMA GEMM instead (8 % slower on B200 at batch 64, results equal
-// to ~1e-6 relative).  Everything else is FP32 FMA on the CUDA cores.  A tcgen05/TMEM GEMM fed by TMA is the next step.
+// Layout: every 3-D blob is [frames][h][w][c] FP32 (channels innermost): both GEMM operands are K-major for tcgen05.mma and TMA-addressable, the
+// depth-wise kernels read channel vectors, and ncnn's Permute(order 3: c,h,w -> h,w,c) in front of the SSD heads becomes an alias -- the head
+// convolutions write straight into the concatenated mbox_loc / mbox_conf buffers.  sgs_detector_blob transposes back to ncnn's c,h,w on read-out.
+// Activations live in a pool planned by liveness.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -24,11 +24,15 @@
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <stdexcept>
 
+#include "conv1x1_tc.cuh"
 #include "sgs_common.h"
 
 namespace sgs {
 namespace det {
+
+using tc::div_scalar;
 
 // ---------------------------------------------------------------------------------------------------------------- element-wise tail
 enum { E_ADD = 0, E_SUB = 1, E_MUL = 2, E_DIV = 3, E_CLIP = 4, E_RELU = 5 };   // 0..3 = ncnn BinaryOp op_type
@@ -44,7 +48,7 @@ struct Epi {
     EpiStep s[kMaxEpi];
 };
 
-enum { EK_GENERIC = 0, EK_NONE, EK_RELU, EK_CLIP, EK_HSWISH, EK_ADD_T, EK_SE_TAIL };   // Epi::kind: recognised tails run as straight-line code
+enum { EK_GENERIC = 0, EK_NONE, EK_RELU, EK_CLIP, EK_HSWISH, EK_ADD_T, EK_SE_TAIL, EK_SE_MUL };   // Epi::kind: recognised tails run as straight-line code
 
 template <int KIND>
 __device__ __forceinline__ float apply_epi(const Epi& e, float v, int64_t idx) {
@@ -52,10 +56,12 @@ __device__ __forceinline__ float apply_epi(const Epi& e, float v, int64_t idx) {
     else if constexpr (KIND == EK_RELU) return fmaxf(v, 0.f);
     else if constexpr (KIND == EK_CLIP) return fminf(fmaxf(v, e.s[0].a), e.s[0].b);
     else if constexpr (KIND == EK_HSWISH)                // v * clip(v + a) / b   (add scalar, clip, mul(rev) start, div scalar)
-        return __fdiv_rn(__fmul_rn(v, fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b)), e.s[3].a);
+        return div_scalar(__fmul_rn(v, fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b)), e.s[3].a);
     else if constexpr (KIND == EK_ADD_T) return __fadd_rn(v, __ldg(e.s[0].t + idx));
     else if constexpr (KIND == EK_SE_TAIL)               // t1 * (clip(v + a) / b) + t2   (add scalar, clip, div scalar, mul(rev) tensor, add tensor)
-        return __fadd_rn(__fmul_rn(__ldg(e.s[3].t + idx), __fdiv_rn(fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b), e.s[2].a)), __ldg(e.s[4].t + idx));
+        return __fadd_rn(__fmul_rn(__ldg(e.s[3].t + idx), div_scalar(fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b), e.s[2].a)), __ldg(e.s[4].t + idx));
+    else if constexpr (KIND == EK_SE_MUL)                // t1 * (clip(v + a) / b)   (add scalar, clip, div scalar, mul(rev) tensor): hard-sigmoid gate
+        return __fmul_rn(__ldg(e.s[3].t + idx), div_scalar(fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b), e.s[2].a));
     else {
         const float v0 = v;
         for (int i = 0; i < e.n; ++i) {
@@ -64,7 +70,7 @@ __device__ __forceinline__ float apply_epi(const Epi& e, float v, int64_t idx) {
             if (s.op == E_RELU) { v = fmaxf(v, 0.f); continue; }
             const float o = s.src == SRC_SCALAR ? s.a : (s.src == SRC_START ? v0 : __ldg(s.t + idx));
             const float x = s.rev ? o : v, y = s.rev ? v : o;
-            v = s.op == E_ADD ? __fadd_rn(x, y) : s.op == E_SUB ? __fsub_rn(x, y) : s.op == E_MUL ? __fmul_rn(x, y) : __fdiv_rn(x, y);
+            v = s.op == E_ADD ? __fadd_rn(x, y) : s.op == E_SUB ? __fsub_rn(x, y) : s.op == E_MUL ? __fmul_rn(x, y) : div_scalar(x, y);
         }
         return v;
     }
@@ -81,6 +87,7 @@ __device__ __forceinline__ void epi_dispatch(int kind, F&& body) {
     case EK_HSWISH: body(EpiKind<EK_HSWISH>{}); break;
     case EK_ADD_T: body(EpiKind<EK_ADD_T>{}); break;
     case EK_SE_TAIL: body(EpiKind<EK_SE_TAIL>{}); break;
+    case EK_SE_MUL: body(EpiKind<EK_SE_MUL>{}); break;
     default: body(EpiKind<EK_GENERIC>{}); break;
     }
 }
@@ -114,266 +121,109 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
         const int h0 = r0[c] * a0 + r0[c + 3] * a1, h1 = r1[c] * a0 + r1[c + 3] * a1;
         int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
         v = max(0, min(255, v));
-        out[((int64_t)f * 3 + c) * T * T + i] = __fsub_rn((float)v, mean[c]);
+        out[((int64_t)f * T * T + i) * 3 + c] = __fsub_rn((float)v, mean[c]);
     }
-}
-
-// 1x1 convolution as a GEMM over all frames: out[f][co][p] = bias[co] + sum_ci W[co][ci] * in[f][ci][p].  Columns j = f*HW + p.
-template <int BM, int BN>
-__global__ void __launch_bounds__(256) conv1x1_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
-                                                      float* __restrict__ out, int Cin, int Cout, int HW, int ncols, Epi epi) {
-    constexpr int BK = 16, TX = BN / 4, LKS = 256 / BN;
-    static_assert(BM * BN == 4096, "256 threads x 4x4 outputs");
-    __shared__ __align__(16) float sA[BK][BM + 4];
-    __shared__ __align__(16) float sB[BK][BN];
-    const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
-    const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
-    const int lc = tid % BN, lk0 = tid / BN, lj = j0 + lc;
-    const bool lvalid = lj < ncols;
-    int64_t lbase = 0;
-    if (lvalid) { const int f = lj / HW; lbase = (int64_t)f * Cin * HW + (lj - f * HW); }
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < Cin; k0 += BK) {
-        for (int e = tid; e < BM * (BK / 4); e += 256) {
-            const int m = e / (BK / 4), kq = (e % (BK / 4)) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + m < Cout && k0 + kq < Cin) v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(m0 + m) * Cin + k0 + kq));
-            sA[kq][m] = v.x; sA[kq + 1][m] = v.y; sA[kq + 2][m] = v.z; sA[kq + 3][m] = v.w;
-        }
-#pragma unroll
-        for (int k = lk0; k < BK; k += LKS) sB[k][lc] = (lvalid && k0 + k < Cin) ? __ldg(in + lbase + (int64_t)(k0 + k) * HW) : 0.f;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&sB[k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-    // this thread's four adjacent columns: frame / pixel of the first by one division, the others by carry
-    const int col0 = j0 + tx * 4;
-    if (col0 >= ncols) return;
-    int fj[4], pj[4];
-    fj[0] = col0 / HW; pj[0] = col0 - fj[0] * HW;
-#pragma unroll
-    for (int j = 1; j < 4; ++j) { fj[j] = fj[j - 1]; pj[j] = pj[j - 1] + 1; if (pj[j] >= HW) { pj[j] = 0; ++fj[j]; } }
-    epi_dispatch(epi.kind, [&](auto kind) {
-        constexpr int EK = decltype(kind)::value;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int co = m0 + ty * 4 + i;
-            if (co >= Cout) break;
-            const float b = bias ? __ldg(bias + co) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (col0 + j >= ncols) break;
-                const int64_t idx = ((int64_t)fj[j] * Cout + co) * HW + pj[j];
-                out[idx] = apply_epi<EK>(epi, __fadd_rn(acc[i][j], b), idx);
-            }
-        }
-    });
-}
-
-// x = hi + lo with hi, lo representable in TF32 (10 mantissa bits), both rounded to nearest / ties away like cvt.rna.tf32.f32 -- done with integer
-// adds and masks: the cvt instruction issues at a fraction of the ALU rate and would bound the whole GEMM.
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-    lo = (__float_as_uint(__fsub_rn(x, __uint_as_float(hi))) + 0x1000u) & 0xffffe000u;
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
-template <int WM, int WN, int MT, int NT>
-__global__ void __launch_bounds__(256, 2) conv1x1_mma_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
-                                                          float* __restrict__ out, int Cin, int Cout, int HW, int ncols, Epi epi) {
-    constexpr int BK = 32, BM = WM * MT * 16, BN = WN * NT * 8, SA = BK + 4, SB = BN + 8, LKS = 256 / BN;
-    constexpr int NA = (BM * BK / 4 + 255) / 256, NBR = BK / LKS;           // float4 of A / floats of B each thread stages per k-tile
-    static_assert(WM * WN == 8 && (BN == 128 || BN == 256) && BM % 16 == 0, "8 warps; one B column per thread");
-    __shared__ __align__(16) float sA[BM][SA];      // m-major: fragment loads (8 rows x 4 k per warp) hit banks 4g + t
-    __shared__ __align__(16) float sB[BK][SB];      // k-major, row stride = 8 (mod 32): banks 8t + g
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int wm = warp / WN, wn = warp % WN;
-    const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
-    const int lc = tid % BN, lk0 = tid / BN, lj = j0 + lc;
-    const bool lvalid = lj < ncols;
-    int64_t lbase = 0;
-    if (lvalid) { const int f = lj / HW; lbase = (int64_t)f * Cin * HW + (lj - f * HW); }
-    float4 ra[NA];
-    float rb[NBR];
-    auto gload = [&](int k0) {                       // global -> registers (next k-tile, overlapped with the mma of the current one)
-#pragma unroll
-        for (int i = 0; i < NA; ++i) {
-            const int e = tid + i * 256, m = e / (BK / 4), kq = (e % (BK / 4)) * 4;
-            ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < BM * BK / 4 && m0 + m < Cout && k0 + kq < Cin) ra[i] = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(m0 + m) * Cin + k0 + kq));
-        }
-#pragma unroll
-        for (int i = 0; i < NBR; ++i) {
-            const int k = k0 + lk0 + i * LKS;
-            rb[i] = (lvalid && k < Cin) ? __ldg(in + lbase + (int64_t)k * HW) : 0.f;
-        }
-    };
-    auto sstore = [&]() {
-#pragma unroll
-        for (int i = 0; i < NA; ++i) {
-            const int e = tid + i * 256, m = e / (BK / 4), kq = (e % (BK / 4)) * 4;
-            if (e < BM * BK / 4) *reinterpret_cast<float4*>(&sA[m][kq]) = ra[i];
-        }
-#pragma unroll
-        for (int i = 0; i < NBR; ++i) sB[lk0 + i * LKS][lc] = rb[i];
-    };
-    float acc[MT][NT][4];
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-    gload(0);
-    sstore();
-    __syncthreads();
-    for (int k0 = 0; k0 < Cin; k0 += BK) {
-        const bool more = k0 + BK < Cin;
-        if (more) gload(k0 + BK);
-#pragma unroll
-        for (int ks = 0; ks < BK; ks += 8) {
-            if (k0 + ks >= Cin) break;                      // block-uniform: the zero-filled tail of the last k-tile
-            uint32_t ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
-#pragma unroll
-            for (int i = 0; i < MT; ++i) {
-                const int r = (wm * MT + i) * 16 + g;
-                split_tf32(sA[r][ks + t], ah[i][0], al[i][0]);
-                split_tf32(sA[r + 8][ks + t], ah[i][1], al[i][1]);
-                split_tf32(sA[r][ks + t + 4], ah[i][2], al[i][2]);
-                split_tf32(sA[r + 8][ks + t + 4], ah[i][3], al[i][3]);
-            }
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const int c = (wn * NT + j) * 8 + g;
-                split_tf32(sB[ks + t][c], bh[j][0], bl[j][0]);
-                split_tf32(sB[ks + t + 4][c], bh[j][1], bl[j][1]);
-            }
-            // term-major: the MT*NT accumulators are independent, so consecutive HMMAs never wait on each other's result
-#pragma unroll
-            for (int i = 0; i < MT; ++i)
-#pragma unroll
-                for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], al[i], bh[j]);
-#pragma unroll
-            for (int i = 0; i < MT; ++i)
-#pragma unroll
-                for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], ah[i], bl[j]);
-#pragma unroll
-            for (int i = 0; i < MT; ++i)
-#pragma unroll
-                for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], ah[i], bh[j]);
-        }
-        __syncthreads();
-        if (more) { sstore(); __syncthreads(); }
-    }
-    epi_dispatch(epi.kind, [&](auto kind) {
-        constexpr int EK = decltype(kind)::value;
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            const int col = j0 + (wn * NT + j) * 8 + 2 * t;          // this thread's two adjacent columns of the n8 tile
-            if (col >= ncols) continue;
-            const int f = col / HW, p = col - f * HW;
-            const bool pair = col + 1 < ncols && p + 1 < HW;          // the second column belongs to the same frame
-            int f1 = f, p1 = p + 1;
-            if (!pair && col + 1 < ncols) { f1 = f + 1; p1 = 0; }
-#pragma unroll
-            for (int i = 0; i < MT; ++i)
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int co = m0 + (wm * MT + i) * 16 + g + rr * 8;
-                    if (co >= Cout) continue;
-                    const float b = bias ? __ldg(bias + co) : 0.f;
-                    const int64_t idx = ((int64_t)f * Cout + co) * HW + p;
-                    const float v0 = apply_epi<EK>(epi, __fadd_rn(acc[i][j][rr * 2], b), idx);
-                    if (pair) {
-                        const float v1 = apply_epi<EK>(epi, __fadd_rn(acc[i][j][rr * 2 + 1], b), idx + 1);
-                        if ((idx & 1) == 0) *reinterpret_cast<float2*>(out + idx) = make_float2(v0, v1);
-                        else { out[idx] = v0; out[idx + 1] = v1; }
-                    } else {
-                        out[idx] = v0;
-                        if (col + 1 < ncols) {
-                            const int64_t idx1 = ((int64_t)f1 * Cout + co) * HW + p1;
-                            out[idx1] = apply_epi<EK>(epi, __fadd_rn(acc[i][j][rr * 2 + 1], b), idx1);
-                        }
-                    }
-                }
-        }
-    });
 }
 
 struct ConvGeom {
     int Cin, Cout, H, W, OH, OW, k, stride, pad, dil;
 };
 
-// depth-wise K x K, stride S: four consecutive outputs of one row per thread; the K + 3S input values of each kernel row are loaded once and
-// shared by the four windows.  Each output accumulates ky-major / kx-minor from zero, then the bias.
-template <int K, int S>
-__global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
-                                                     float* __restrict__ out, ConvGeom g, Epi epi) {
-    constexpr int NX = 3 * S + K;
-    const int owq = (g.OW + 3) >> 2;
-    const int q = blockIdx.x * 256 + threadIdx.x;                  // (row, quad of outputs) inside one channel plane
-    if (q >= g.OH * owq) return;
-    const int oy = q / owq, ox0 = (q - oy * owq) * 4;
-    const int c = blockIdx.y;
-    const int64_t fc = (int64_t)blockIdx.z * g.Cout + c;
-    const float* src = in + fc * (int64_t)g.H * g.W;
-    float w[K * K];
+// The tail of a kernel's epilogue as the functor conv1x1_tc_kernel takes: the (block-uniform) switch on the tail kind is taken once per group of
+// N consecutive channels, the recognised kinds run as straight-line code.
+struct EpiFn {
+    Epi e;
+    template <int N>
+    __device__ __forceinline__ void run(float (&v)[N], int64_t idx0) const {
+        epi_dispatch(e.kind, [&](auto kind) {
 #pragma unroll
-    for (int i = 0; i < K * K; ++i) w[i] = __ldg(Wt + c * K * K + i);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int q = 0; q < N; ++q) v[q] = apply_epi<decltype(kind)::value>(e, v[q], idx0 + q);
+        });
+    }
+};
+
+// depth-wise K x K, stride S on [frame][h][w][c]: V channels (float4 when C % 4 == 0) x XT consecutive outputs of one row per thread; the
+// K + (XT-1)S input vectors of each kernel row are loaded once and shared by the XT windows.  Weights transposed to [ky][kx][c] at load time.
+// Each output accumulates ky-major / kx-minor from zero, then the bias.
+template <int K, int S, int V>
+__global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                     float* __restrict__ out, ConvGeom g, int64_t total, Epi epi) {
+    constexpr int XT = 4, NX = (XT - 1) * S + K;
+    const int64_t t0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t0 >= total) return;
+    const int cv = g.Cout / V, owq = (g.OW + XT - 1) / XT;
+    const int c = (int)(t0 % cv) * V;
+    int64_t t = t0 / cv;
+    const int ox0 = (int)(t % owq) * XT; t /= owq;
+    const int oy = (int)(t % g.OH);
+    const int64_t f = t / g.OH;
+    float acc[XT][V];
+#pragma unroll
+    for (int o = 0; o < XT; ++o)
+#pragma unroll
+        for (int q = 0; q < V; ++q) acc[o][q] = 0.f;
     const int ix0 = ox0 * S - g.pad;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
         const int iy = oy * S - g.pad + ky;
         if (iy < 0 || iy >= g.H) continue;
-        const float* row = src + iy * g.W;
-        float x[NX];
+        const float* row = in + ((f * g.H + iy) * (int64_t)g.W) * g.Cout + c;
+        float x[NX][V];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) { const int ix = ix0 + j; x[j] = (ix >= 0 && ix < g.W) ? __ldg(row + ix) : 0.f; }
+        for (int j = 0; j < NX; ++j) {
+            const int ix = ix0 + j;
+            if (ix >= 0 && ix < g.W) {
+                if constexpr (V == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(row + (int64_t)ix * g.Cout)); x[j][0] = q.x; x[j][1] = q.y; x[j][2] = q.z; x[j][3] = q.w; }
+                else x[j][0] = __ldg(row + (int64_t)ix * g.Cout);
+            } else {
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx)
+                for (int q = 0; q < V; ++q) x[j][q] = 0.f;
+            }
+        }
 #pragma unroll
-            for (int o = 0; o < 4; ++o) acc[o] = fmaf(w[ky * K + kx], x[o * S + kx], acc[o]);      // padding taps contribute w * 0
+        for (int kx = 0; kx < K; ++kx) {
+            float w[V];
+            if constexpr (V == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(Wt + (ky * K + kx) * g.Cout + c)); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+            else w[0] = __ldg(Wt + (ky * K + kx) * g.Cout + c);
+#pragma unroll
+            for (int o = 0; o < XT; ++o)
+#pragma unroll
+                for (int q = 0; q < V; ++q) acc[o][q] = fmaf(w[q], x[o * S + kx][q], acc[o][q]);      // padding taps contribute w * 0
+        }
     }
-    const float b = bias ? __ldg(bias + c) : 0.f;
-    const int64_t o0 = (fc * g.OH + oy) * (int64_t)g.OW + ox0;
+    float b[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) b[q] = bias ? __ldg(bias + c + q) : 0.f;
+    const int64_t o0 = ((f * g.OH + oy) * (int64_t)g.OW + ox0) * g.Cout + c;
     epi_dispatch(epi.kind, [&](auto kind) {
         constexpr int EK = decltype(kind)::value;
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
-            if (ox0 + o < g.OW) out[o0 + o] = apply_epi<EK>(epi, __fadd_rn(acc[o], b), o0 + o);
+        for (int o = 0; o < XT; ++o) {
+            if (ox0 + o >= g.OW) break;
+            const int64_t oi = o0 + (int64_t)o * g.Cout;
+            float r[V];
+#pragma unroll
+            for (int q = 0; q < V; ++q) r[q] = apply_epi<EK>(epi, __fadd_rn(acc[o][q], b[q]), oi + q);
+            if constexpr (V == 4) *reinterpret_cast<float4*>(out + oi) = make_float4(r[0], r[1], r[2], r[3]);
+            else out[oi] = r[0];
+        }
     });
 }
 
-// dense k x k convolution with few input channels (the network's first layer 3 -> 16, 3x3 stride 2, and the SE convolutions whose Cin is
-// not a multiple of 4): one output pixel x COT output channels per thread, the weights of the channel block staged in shared memory as
-// [ci][ky][kx][COT] so that every input value is loaded once and used COT times.
+// dense k x k convolution on [frame][h][w][c] for the layers the GEMM does not take (the network's first layer 3 -> 16, 3x3 stride 2, and the 1x1
+// convolutions whose Cin is not a multiple of 4): one output pixel x kCot output channels per thread, the weights of the channel block staged
+// in shared memory as [ky][kx][ci][kCot] so that every input value is loaded once and used kCot times.  Output addressing as in the GEMM
+// (frame stride / base offset / pitch), so that a head convolution of this kind could write into a concatenated buffer as well.
 constexpr int kCot = 8;
 __global__ void __launch_bounds__(256) conv_small_kernel(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
-                                                         float* __restrict__ out, ConvGeom g, Epi epi) {
+                                                         float* __restrict__ out, ConvGeom g, int64_t out_frame_stride, int64_t out_base, Epi epi) {
     extern __shared__ __align__(16) float sw[];
     const int co0 = blockIdx.y * kCot, f = blockIdx.z;
     const int taps = g.Cin * g.k * g.k;
     for (int e = threadIdx.x; e < taps * kCot; e += 256) {
-        const int tp = e / kCot, o = e % kCot;
-        sw[e] = co0 + o < g.Cout ? __ldg(Wt + (int64_t)(co0 + o) * taps + tp) : 0.f;
+        const int tp = e / kCot, o = e % kCot;                 // tp = (ky * k + kx) * Cin + ci
+        const int ci = tp % g.Cin, kk = tp / g.Cin;
+        sw[e] = co0 + o < g.Cout ? __ldg(Wt + ((int64_t)(co0 + o) * g.Cin + ci) * g.k * g.k + kk) : 0.f;
     }
     __syncthreads();
     const int p = blockIdx.x * 256 + threadIdx.x;
@@ -382,77 +232,46 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const float* __restrict
     float acc[kCot];
 #pragma unroll
     for (int o = 0; o < kCot; ++o) acc[o] = 0.f;
-    for (int ci = 0; ci < g.Cin; ++ci) {
-        const float* src = in + ((int64_t)f * g.Cin + ci) * g.H * g.W;
-        for (int ky = 0; ky < g.k; ++ky) {
-            const int iy = oy * g.stride - g.pad + ky * g.dil;
-            if (iy < 0 || iy >= g.H) continue;
-            for (int kx = 0; kx < g.k; ++kx) {
-                const int ix = ox * g.stride - g.pad + kx * g.dil;
-                if (ix < 0 || ix >= g.W) continue;
-                const float x = __ldg(src + (int64_t)iy * g.W + ix);
-                const float* wp = sw + ((ci * g.k + ky) * g.k + kx) * kCot;
+    for (int ky = 0; ky < g.k; ++ky) {
+        const int iy = oy * g.stride - g.pad + ky * g.dil;
+        if (iy < 0 || iy >= g.H) continue;
+        for (int kx = 0; kx < g.k; ++kx) {
+            const int ix = ox * g.stride - g.pad + kx * g.dil;
+            if (ix < 0 || ix >= g.W) continue;
+            const float* src = in + (((int64_t)f * g.H + iy) * g.W + ix) * g.Cin;
+            const float* wp = sw + (ky * g.k + kx) * g.Cin * kCot;
+            for (int ci = 0; ci < g.Cin; ++ci) {
+                const float x = __ldg(src + ci);
 #pragma unroll
-                for (int o = 0; o < kCot; ++o) acc[o] = fmaf(wp[o], x, acc[o]);
+                for (int o = 0; o < kCot; ++o) acc[o] = fmaf(wp[ci * kCot + o], x, acc[o]);
             }
         }
     }
+    float* orow = out + out_base + (int64_t)f * out_frame_stride + (int64_t)p * g.Cout;
+    const int64_t idx0 = ((int64_t)f * g.OH * g.OW + p) * g.Cout;
+    const bool vec = co0 + kCot <= g.Cout && (g.Cout & 3) == 0 && ((out_base | out_frame_stride) & 3) == 0;
     epi_dispatch(epi.kind, [&](auto kind) {
         constexpr int EK = decltype(kind)::value;
+        float r[kCot];
 #pragma unroll
         for (int o = 0; o < kCot; ++o) {
             const int co = co0 + o;
-            if (co < g.Cout) {
-                const int64_t idx = ((int64_t)f * g.Cout + co) * g.OH * g.OW + p;
-                out[idx] = apply_epi<EK>(epi, __fadd_rn(acc[o], bias ? __ldg(bias + co) : 0.f), idx);
-            }
+            r[o] = co < g.Cout ? apply_epi<EK>(epi, __fadd_rn(acc[o], bias ? __ldg(bias + co) : 0.f), idx0 + co) : 0.f;
+        }
+        if (vec) {
+#pragma unroll
+            for (int o = 0; o < kCot; o += 4) *reinterpret_cast<float4*>(orow + co0 + o) = make_float4(r[o], r[o + 1], r[o + 2], r[o + 3]);
+        } else {
+#pragma unroll
+            for (int o = 0; o < kCot; ++o) if (co0 + o < g.Cout) orow[co0 + o] = r[o];
         }
     });
-}
-
-// dense k x k convolution (groups == 1), one output per thread: the network's first layer (3 -> 16, 3x3 stride 2) and any geometry the GEMM
-// kernel does not take
-__global__ void __launch_bounds__(256) conv_direct_kernel(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
-                                                          float* __restrict__ out, ConvGeom g, int64_t total, Epi epi) {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int ox = (int)(idx % g.OW);
-    const int oy = (int)((idx / g.OW) % g.OH);
-    const int64_t fc = idx / ((int64_t)g.OW * g.OH);
-    const int co = (int)(fc % g.Cout);
-    const int64_t f = fc / g.Cout;
-    float acc = 0.f;
-    for (int ci = 0; ci < g.Cin; ++ci) {
-        const float* src = in + (f * g.Cin + ci) * (int64_t)g.H * g.W;
-        const float* w = Wt + ((int64_t)co * g.Cin + ci) * g.k * g.k;
-        for (int ky = 0; ky < g.k; ++ky) {
-            const int iy = oy * g.stride - g.pad + ky * g.dil;
-            if (iy < 0 || iy >= g.H) continue;
-            for (int kx = 0; kx < g.k; ++kx) {
-                const int ix = ox * g.stride - g.pad + kx * g.dil;
-                if (ix < 0 || ix >= g.W) continue;
-                acc = fmaf(__ldg(w + ky * g.k + kx), __ldg(src + (int64_t)iy * g.W + ix), acc);
-            }
-        }
-    }
-    out[idx] = apply_epi<EK_GENERIC>(epi, __fadd_rn(acc, bias ? __ldg(bias + co) : 0.f), idx);
 }
 
 __global__ void __launch_bounds__(256) eltwise_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total, Epi epi) {
     const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (idx >= total) return;
     epi_dispatch(epi.kind, [&](auto kind) { out[idx] = apply_epi<decltype(kind)::value>(epi, __ldg(in + idx), idx); });
-}
-
-// Permute order_type 3 on a 3-D blob: (c,h,w) -> (h,w,c)
-__global__ void __launch_bounds__(256) permute_hwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW, int64_t total) {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % C);
-    const int64_t fp = idx / C;
-    const int p = (int)(fp % HW);
-    const int64_t f = fp / HW;
-    out[idx] = __ldg(in + (f * C + c) * HW + p);
 }
 
 // Concat piece: per frame n floats from src (frame stride n) to dst + off (frame stride dst_n)
@@ -464,12 +283,27 @@ __global__ void __launch_bounds__(256) concat_copy_kernel(const float* __restric
     dst[f * dst_n + off + i] = __ldg(src + idx);
 }
 
-// Softmax over the innermost axis (w = classes) of a 2-D blob: max-subtract, exp, sum, divide
+// Softmax over the innermost axis (w = classes) of a 2-D blob: max-subtract, exp, sum, divide.  One row per thread; rows of at most 32 classes
+// stay in registers (one read and one write of the row), longer rows take the three-pass form.  Same operations in the same order either way.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int ncls, int64_t rows) {
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (r >= rows) return;
     const float* x = in + r * ncls;
     float* y = out + r * ncls;
+    if (ncls <= 32) {
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = c < ncls ? __ldg(x + c) : 0.f;
+        float m = v[0];
+#pragma unroll
+        for (int c = 1; c < 32; ++c) if (c < ncls) m = fmaxf(m, v[c]);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) if (c < ncls) { v[c] = expf(__fsub_rn(v[c], m)); s = __fadd_rn(s, v[c]); }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) if (c < ncls) y[c] = __fdiv_rn(v[c], s);
+        return;
+    }
     float m = x[0];
     for (int c = 1; c < ncls; ++c) m = fmaxf(m, x[c]);
     float s = 0.f;
@@ -622,7 +456,7 @@ __global__ void __launch_bounds__(256) detout_merge_kernel(const float* __restri
         for (int i = threadIdx.x; i < m * 6; i += blockDim.x) rows[(int64_t)f * Q.rows_cap * 6 + i] = srow[i];
     if (threadIdx.x != 0) return;
     if (nrows) nrows[f] = m;
-    int no = 0, nm = 0, nr = 0, over = 0;
+    int no = 0, nm = 0, nr = 0, nnp = 0, over = 0;                  // objects, person boxes (mapping / rejection), non-person objects
     for (int i = 0; i < m; ++i) {
         const float* v = srow + i * 6;
         const int lab = (int)v[0];
@@ -637,15 +471,17 @@ __global__ void __launch_bounds__(256) detout_merge_kernel(const float* __restri
         ++no;
         if (lab == Q.person) {
             if (nm < Q.max_boxes) { if (dyn_map) dyn_map[(int64_t)f * Q.max_boxes + nm] = r; ++nm; } else over = 1;
-            if (v[1] > 0.2f) {
+            if ((double)v[1] > 0.2) {                                  // `object2d.prob > 0.2`: float against a double literal (Detector2D.cc:78)
                 if (nr < Q.max_boxes) { if (dyn_rm) dyn_rm[(int64_t)f * Q.max_boxes + nr] = r; ++nr; } else over = 1;
             }
-        }
+        } else ++nnp;
     }
     if (nobjects) nobjects[f] = no;
     if (ndyn_map) ndyn_map[f] = nm;
     if (ndyn_rm) ndyn_rm[f] = nr;
-    if (have_dyn_rm) have_dyn_rm[f] = nr > 0 ? 1 : 0;
+    // Frame.cc:482-491 copies the detector's flag only when mvObjects2D (the NON-person objects, Detector2D.cc:84-85) is not empty; otherwise the Frame
+    // member stays uninitialised (include/Frame.h:112) -- defined here as false -- and bPreFrameHavePotentialDynamicObj = false.
+    if (have_dyn_rm) have_dyn_rm[f] = (nr > 0 && nnp > 0) ? 1 : 0;
     if (status) status[f] = over;
 }
 
@@ -667,12 +503,13 @@ struct Blob {
     int producer = -1;
     int root = -1;                 // blob whose storage this one aliases (Split / Flatten / Reshape outputs)
     bool is_const = false;
+    bool hwc = false;              // 3-D blob stored [h][w][c] (every activation); Permute(3) outputs alias their input and are "native" again
     std::vector<float> cval;       // constant-folded value
     int buf = -1;                  // pool buffer of the root
     float* dev = nullptr;
 };
 
-enum OpKind { OP_CONV1X1, OP_CONV_DIRECT, OP_DWCONV, OP_ELTWISE, OP_PERMUTE, OP_CONCAT_COPY, OP_SOFTMAX };
+enum OpKind { OP_CONV1X1, OP_CONV_DIRECT, OP_DWCONV, OP_ELTWISE, OP_CONCAT_COPY, OP_SOFTMAX };
 struct EpiStepH { int op, src, rev; float a, b; int tblob; };
 struct Op {
     OpKind kind;
@@ -681,7 +518,10 @@ struct Op {
     std::vector<EpiStepH> epi;
     ConvGeom g{};
     float* d_w = nullptr; float* d_b = nullptr;
-    int64_t off = 0;               // concat offset
+    int64_t off = 0;               // concat offset (copy pieces, and convolutions that write straight into a concatenated buffer: `cat`)
+    bool cat = false;
+    tc::GemmPlan gp;               // OP_CONV1X1: split weights, tiling, weight tensor maps
+    CUtensorMap map_in;            // OP_CONV1X1: the input activations [max_frames * H * W][Cin]
 };
 
 }  // namespace det
@@ -727,6 +567,7 @@ int parse_param(const char* path, std::vector<Layer>& layers) {
         std::istringstream ss(line);
         Layer L; int nin = 0, nout = 0;
         if (!(ss >> L.type >> L.name >> nin >> nout)) continue;
+        if (nin < 0 || nout < 0 || nin > 64 || nout > 64) { set_error("sgs_detector_create: layer %s declares %d inputs / %d outputs", L.name.c_str(), nin, nout); return SGS_ERR_INVALID; }
         L.in.resize(nin); L.out.resize(nout);
         for (auto& s : L.in) ss >> s;
         for (auto& s : L.out) ss >> s;
@@ -740,7 +581,7 @@ int parse_param(const char* path, std::vector<Layer>& layers) {
             if (key <= -23300) {                                  // array: -23300-id=count,v0,v1,...
                 key = -(key + 23300);
                 std::istringstream vs(val); std::string tok; bool first = true; size_t cnt = 0;
-                while (std::getline(vs, tok, ',')) { if (first) { cnt = (size_t)atoi(tok.c_str()); first = false; } else v.push_back(atof(tok.c_str())); }
+                while (std::getline(vs, tok, ',')) { if (first) { const int c = atoi(tok.c_str()); if (c < 0 || c > 4096) { set_error("sgs_detector_create: array of %d values in layer %s", c, L.name.c_str()); return SGS_ERR_INVALID; } cnt = (size_t)c; first = false; } else v.push_back(atof(tok.c_str())); }
                 v.resize(cnt);
             } else v.push_back(atof(val.c_str()));
             L.prm[key] = v;
@@ -766,7 +607,7 @@ int load_bin(const char* path, std::vector<Layer>& layers) {
             if (off + 4 <= buf.size()) memcpy(&tag, buf.data() + off, 4);
             off += 4;
             if (tag != 0) { set_error("sgs_detector_create: layer %s: only raw float32 weights are supported (storage tag %#x)", L.name.c_str(), tag); return SGS_ERR_UNSUPPORTED; }
-            if (!take(L.weight, (size_t)L.pi(6, 0))) { set_error("sgs_detector_create: %s truncated at layer %s", path, L.name.c_str()); return SGS_ERR_INVALID; }
+            if (L.pi(6, 0) < 0 || L.pi(0, 0) < 0 || !take(L.weight, (size_t)L.pi(6, 0))) { set_error("sgs_detector_create: %s truncated at layer %s", path, L.name.c_str()); return SGS_ERR_INVALID; }
             if (L.pi(5, 0) && !take(L.bias, (size_t)L.pi(0, 0))) { set_error("sgs_detector_create: %s truncated at layer %s", path, L.name.c_str()); return SGS_ERR_INVALID; }
         } else if (L.type == "MemoryData") {
             const size_t n = (size_t)std::max(1, L.pi(0, 0)) * std::max(1, L.pi(1, 0)) * std::max(1, L.pi(2, 0));
@@ -862,13 +703,13 @@ int build_graph(sgs_detector* D) {
     for (size_t i = 0; i < Ls.size(); ++i) {
         const Layer& L = Ls[i];
         auto in0 = [&]() -> Blob& { return B[lin[i][0]]; };
-        if (L.type == "Input") { set3(B[lout[i][0]], 3, D->T, D->T); D->input_blob = lout[i][0]; }
+        if (L.type == "Input") { set3(B[lout[i][0]], 3, D->T, D->T); B[lout[i][0]].hwc = true; D->input_blob = lout[i][0]; }
         else if (L.type == "MemoryData") {
             Blob& o = B[lout[i][0]];
             o.dims = 1; o.w = (int)L.data.size(); o.n = o.w; o.is_const = true; o.cval = L.data;
             if (L.pi(1, 0) > 0 || L.pi(2, 0) > 0 || o.n != 1) { set_error("sgs_detector_create: MemoryData %s: only scalar constants are supported", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
         } else if (L.type == "Split") {
-            for (int o : lout[i]) { Blob& ob = B[o]; const Blob& s = in0(); ob.dims = s.dims; ob.c = s.c; ob.h = s.h; ob.w = s.w; ob.n = s.n; ob.root = lin[i][0]; ob.is_const = s.is_const; ob.cval = s.cval; }
+            for (int o : lout[i]) { Blob& ob = B[o]; const Blob& s = in0(); ob.dims = s.dims; ob.c = s.c; ob.h = s.h; ob.w = s.w; ob.n = s.n; ob.root = lin[i][0]; ob.is_const = s.is_const; ob.cval = s.cval; ob.hwc = s.hwc; }
         } else if (L.type == "Convolution" || L.type == "ConvolutionDepthWise") {
             const Blob& s = in0();
             const int k = L.pi(1, 1), dil = L.pi(2, 1), st = L.pi(3, 1), pad = L.pi(4, 0), cout = L.pi(0, 0);
@@ -876,6 +717,8 @@ int build_graph(sgs_detector* D) {
                 set_error("sgs_detector_create: layer %s: only square kernels with symmetric explicit padding are supported", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
             const int oh = (s.h + 2 * pad - dil * (k - 1) - 1) / st + 1, ow = (s.w + 2 * pad - dil * (k - 1) - 1) / st + 1;
             set3(B[lout[i][0]], cout, oh, ow);
+            B[lout[i][0]].hwc = true;
+            if (!s.hwc) { set_error("sgs_detector_create: layer %s convolves a blob that is not an activation map", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
             const bool dw = L.type == "ConvolutionDepthWise";
             const int group = dw ? L.pi(7, 1) : 1;
             if (dw && !(group == s.c && cout == s.c && cout <= 65535 && dil == 1 && (k == 3 || k == 5) && (st == 1 || st == 2))) { set_error("sgs_detector_create: layer %s: grouped convolution other than depth-wise 3x3/5x5 with stride 1/2 is not supported", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
@@ -883,7 +726,7 @@ int build_graph(sgs_detector* D) {
             if ((int64_t)L.weight.size() != expect) { set_error("sgs_detector_create: layer %s: weight size %zu, expected %lld", L.name.c_str(), L.weight.size(), (long long)expect); return SGS_ERR_INVALID; }
         } else if (is_eltwise(L)) {
             const Blob& s = in0(); Blob& o = B[lout[i][0]];
-            o.dims = s.dims; o.c = s.c; o.h = s.h; o.w = s.w; o.n = s.n;
+            o.dims = s.dims; o.c = s.c; o.h = s.h; o.w = s.w; o.n = s.n; o.hwc = s.hwc;
             if (L.type == "BinaryOp") {
                 const Blob& t = B[lin[i][1]];
                 if (s.is_const || !(t.is_const ? t.n == 1 : t.n == s.n)) { set_error("sgs_detector_create: BinaryOp %s: unsupported operand shapes", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
@@ -891,15 +734,17 @@ int build_graph(sgs_detector* D) {
             }
         } else if (L.type == "Permute") {
             const Blob& s = in0();
-            if (s.dims != 3 || L.pi(0, 0) != 3) { set_error("sgs_detector_create: Permute %s: only order_type 3 on 3-D blobs is supported", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
+            if (s.dims != 3 || L.pi(0, 0) != 3 || !s.hwc) { set_error("sgs_detector_create: Permute %s: only order_type 3 on 3-D activation maps is supported", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
             set3(B[lout[i][0]], s.h, s.w, s.c);
+            B[lout[i][0]].root = lin[i][0];                   // (c,h,w) -> (h,w,c) is how the activation is stored already: an alias, in ncnn's "native" order from here on
         } else if (L.type == "Flatten") {
             const Blob& s = in0(); Blob& o = B[lout[i][0]];
+            if (s.hwc && s.c > 1 && s.h * s.w > 1) { set_error("sgs_detector_create: Flatten %s of an un-permuted activation map is not supported", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
             o.dims = 1; o.w = (int)s.n; o.n = s.n; o.root = lin[i][0]; o.is_const = s.is_const; o.cval = s.cval;
         } else if (L.type == "Reshape") {
             const Blob& s = in0(); Blob& o = B[lout[i][0]];
             const int w = L.pi(0, -233), h = L.pi(1, -233);
-            if (w <= 0 || L.pi(2, -233) != -233) { set_error("sgs_detector_create: Reshape %s: unsupported target", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
+            if (w <= 0 || L.pi(2, -233) != -233 || (s.hwc && s.c > 1 && s.h * s.w > 1)) { set_error("sgs_detector_create: Reshape %s: unsupported target", L.name.c_str()); return SGS_ERR_UNSUPPORTED; }
             if (h == -233) { o.dims = 1; o.w = w; } else { o.dims = 2; o.w = w; o.h = h == -1 ? (int)(s.n / w) : h; }
             o.n = s.n; o.root = lin[i][0];
             if ((int64_t)o.w * o.h != s.n) { set_error("sgs_detector_create: Reshape %s: element count mismatch", L.name.c_str()); return SGS_ERR_INVALID; }
@@ -948,7 +793,7 @@ int build_graph(sgs_detector* D) {
     // ---- pass 2: kernel list.  absorbed[i] = layer i was folded into an earlier kernel's element-wise tail.
     auto consumers_of_root = [&](int b) {      // layers reading b or any alias of it (aliases never chain through compute layers)
         std::vector<int> r; const int rb = root_of(*D, b);
-        for (size_t q = 0; q < B.size(); ++q) if (!B[q].is_const && root_of(*D, (int)q) == rb) for (int l : cons[q]) if (Ls[l].type != "Split" && Ls[l].type != "Flatten" && Ls[l].type != "Reshape") r.push_back(l);
+        for (size_t q = 0; q < B.size(); ++q) if (!B[q].is_const && root_of(*D, (int)q) == rb) for (int l : cons[q]) if (Ls[l].type != "Split" && Ls[l].type != "Flatten" && Ls[l].type != "Reshape" && Ls[l].type != "Permute") r.push_back(l);
         std::sort(r.begin(), r.end());
         return r;
     };
@@ -1006,7 +851,17 @@ int build_graph(sgs_detector* D) {
             op.g = ConvGeom{s.c, o.c, s.h, s.w, o.h, o.w, L.pi(1, 1), L.pi(3, 1), L.pi(4, 0), L.pi(2, 1)};
             if (L.type == "ConvolutionDepthWise") op.kind = OP_DWCONV;
             else op.kind = (op.g.k == 1 && op.g.stride == 1 && op.g.pad == 0 && s.c % 4 == 0) ? OP_CONV1X1 : OP_CONV_DIRECT;
-            int rc = upload(D, L.weight, &op.d_w); if (rc) return rc;
+            int rc = SGS_OK;
+            if (op.kind == OP_CONV1X1) {
+                if (D->flags & 2) tc::plan_tiling(op.g.Cin, op.g.Cout, &op.gp);
+                else if (!tc::plan_weights(L.weight.data(), op.g.Cin, op.g.Cout, &op.gp)) { set_error("sgs_detector_create: layer %s: the tcgen05 GEMM could not be set up (TMA tensor maps need a CUDA 12 driver; %s)", L.name.c_str(), cudaGetErrorString(cudaGetLastError())); return SGS_ERR_CUDA; }
+            } else if (op.kind == OP_DWCONV) {                    // [c][ky][kx] -> [ky][kx][c]: channel vectors
+                std::vector<float> wt(L.weight.size());
+                const int kk = op.g.k * op.g.k;
+                for (int c = 0; c < op.g.Cout; ++c) for (int t = 0; t < kk; ++t) wt[(size_t)t * op.g.Cout + c] = L.weight[(size_t)c * kk + t];
+                rc = upload(D, wt, &op.d_w);
+            } else rc = upload(D, L.weight, &op.d_w);
+            if (rc) return rc;
             rc = upload(D, L.bias, &op.d_b); if (rc) return rc;
             int fin = lout[i][0];
             if (!diag) build_tail((int)i, lout[i][0], op.epi, fin);
@@ -1034,12 +889,28 @@ int build_graph(sgs_detector* D) {
             }
             op.out = fin;
             D->ops.push_back(op);
-        } else if (L.type == "Permute") {
-            Op op; op.kind = OP_PERMUTE; op.layer = (int)i; op.in = lin[i][0]; op.out = lout[i][0];
-            D->ops.push_back(op);
         } else if (L.type == "Concat" && !B[lout[i][0]].is_const) {
+            // SSD head outputs: when every piece is the (permuted, flattened) output of a convolution that nothing else reads, those convolutions
+            // write their [h][w][c] rows straight into the concatenated buffer; otherwise (and in diagnostic mode) the pieces are copied
+            std::vector<int> prod;
+            bool direct = !diag;
+            for (int b : lin[i]) {
+                const int r = root_of(*D, b);
+                int q = -1;
+                for (size_t o = 0; o < D->ops.size(); ++o) if (root_of(*D, D->ops[o].out) == r && !D->ops[o].cat) q = (int)o;
+                const auto cs = consumers_of_root(r);
+                bool ok = q >= 0 && (D->ops[q].kind == OP_CONV1X1 || D->ops[q].kind == OP_CONV_DIRECT) && cs.size() == 1 && cs[0] == (int)i && B[r].hwc;
+                if (ok) for (auto& st : D->ops[q].epi) if (st.src == SRC_TENSOR) ok = false;
+                direct = direct && ok;
+                prod.push_back(q);
+            }
             int64_t off = 0;
-            for (int b : lin[i]) { Op op; op.kind = OP_CONCAT_COPY; op.layer = (int)i; op.in = b; op.out = lout[i][0]; op.off = off; off += B[b].n; D->ops.push_back(op); }
+            for (size_t j = 0; j < lin[i].size(); ++j) {
+                const int b = lin[i][j];
+                if (direct) { Op& po = D->ops[prod[j]]; po.out = lout[i][0]; po.cat = true; po.off = off; }
+                else { Op op; op.kind = OP_CONCAT_COPY; op.layer = (int)i; op.in = b; op.out = lout[i][0]; op.off = off; D->ops.push_back(op); }
+                off += B[b].n;
+            }
         } else if (L.type == "Softmax") {
             Op op; op.kind = OP_SOFTMAX; op.layer = (int)i; op.in = lin[i][0]; op.out = lout[i][0];
             D->ops.push_back(op);
@@ -1084,6 +955,9 @@ int build_graph(sgs_detector* D) {
     if (D->flags & 2) return SGS_OK;                     // plan only
     for (size_t q = 0; q < D->pool_size.size(); ++q) SGS_CUDA_TRY(cudaMalloc((void**)&D->pool[q], (size_t)D->pool_size[q] * D->max_frames * sizeof(float)));
     for (auto& b : B) { const int r = root_of(*D, (int)(&b - &B[0])); if (B[r].buf >= 0) b.dev = D->pool[B[r].buf]; }
+    for (auto& op : D->ops)                                   // the GEMMs' activation operand: [max_frames * H * W][Cin], rows past the batch are never stored
+        if (op.kind == OP_CONV1X1 && !tc::encode_kmajor_map(&op.map_in, B[op.in].dev, (int64_t)D->max_frames * op.g.H * op.g.W, op.g.Cin, op.g.Cin, tc::kBM, op.gp.BK)) {
+            set_error("sgs_detector_create: layer %s: cuTensorMapEncodeTiled failed", D->layers[op.layer].name.c_str()); return SGS_ERR_CUDA; }
     SGS_CUDA_TRY(cudaMalloc((void**)&D->d_picked, (size_t)D->max_frames * (D->dp.ncls - 1) * D->dp.nms_topk * sizeof(unsigned long long)));
     SGS_CUDA_TRY(cudaMalloc((void**)&D->d_picked_n, (size_t)D->max_frames * (D->dp.ncls - 1) * sizeof(int32_t)));
     SGS_CUDA_TRY(cudaMalloc((void**)&D->d_obj, (size_t)D->dp.keep_topk * sizeof(sgs_object2d)));
@@ -1106,6 +980,7 @@ Epi make_epi(const sgs_detector* D, const std::vector<EpiStepH>& h) {
     else if (e.n == 4 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_MUL, SRC_START) && is(3, E_DIV, SRC_SCALAR) && !h[3].rev) e.kind = EK_HSWISH;
     else if (e.n == 5 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_DIV, SRC_SCALAR) && !h[2].rev && is(3, E_MUL, SRC_TENSOR) && is(4, E_ADD, SRC_TENSOR))
         e.kind = EK_SE_TAIL;
+    else if (e.n == 4 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_DIV, SRC_SCALAR) && !h[2].rev && is(3, E_MUL, SRC_TENSOR)) e.kind = EK_SE_MUL;
     return e;
 }
 
@@ -1122,12 +997,19 @@ int sgs_detector_create(const char* param_path, const char* bin_path, int max_fr
     if (!(flags & 2)) SGS_CUDA_TRY(cudaSetDevice(device));
     sgs_detector* D = new sgs_detector();
     D->device = device; D->max_frames = max_frames; D->flags = flags; D->det_thr = det_thr; D->dyn_thr = dyn_thr;
-    int rc = parse_param(param_path, D->layers);
-    if (rc == SGS_OK) rc = load_bin(bin_path, D->layers);
-    if (rc == SGS_OK) rc = build_graph(D);
+    int rc = SGS_OK;
+    try {                                              // malformed files must come back as a status, never as an exception through the C ABI
+        rc = parse_param(param_path, D->layers);
+        if (rc == SGS_OK) rc = load_bin(bin_path, D->layers);
+        if (rc == SGS_OK) rc = build_graph(D);
+    } catch (const std::exception& ex) {
+        set_error("sgs_detector_create: %s while reading %s / %s", ex.what(), param_path, bin_path);
+        rc = SGS_ERR_INVALID;
+    }
     if (rc == SGS_OK && !(flags & 2)) {
         cudaError_t e = cudaFuncSetAttribute(detout_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeCap * 8 + D->dp.keep_topk * 24);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(detout_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDetSortCap * 8 + D->dp.nms_topk * 20);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         if (e != cudaSuccess) { set_error("sgs_detector_create: cudaFuncSetAttribute -> %s", cudaGetErrorString(e)); rc = SGS_ERR_CUDA; }
     }
     if (rc != SGS_OK) { sgs_detector_destroy(D); return rc; }
@@ -1141,6 +1023,7 @@ void sgs_detector_destroy(sgs_detector* D) {
     cudaSetDevice(D->device);
     for (float* p : D->pool) cudaFree(p);
     for (float* p : D->weights) cudaFree(p);
+    for (auto& op : D->ops) if (op.kind == OP_CONV1X1) tc::free_plan(&op.gp);
     cudaFree(D->d_picked); cudaFree(D->d_picked_n); cudaFree(D->d_img); cudaFree(D->d_obj); cudaFree(D->d_cnt);
     delete D;
 }
@@ -1175,47 +1058,36 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
         const Epi epi = make_epi(D, op.epi);
         switch (op.kind) {
         case OP_CONV1X1: {
-            const int HW = op.g.OH * op.g.OW; const int64_t ncols = (int64_t)F * HW;
-            if (!(D->flags & 4) && ncols < (1ll << 31) - 256) {
-                const int nc = (int)ncols;
-                const dim3 g16((nc + 255) / 256, (op.g.Cout + 15) / 16), g32((nc + 255) / 256, (op.g.Cout + 31) / 32), g64((nc + 127) / 128, (op.g.Cout + 63) / 64);
-#define SGS_MMA_ARGS bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi
-                if (op.g.Cout <= 16) conv1x1_mma_kernel<1, 8, 1, 4><<<g16, 256, 0, st>>>(SGS_MMA_ARGS);
-                else if (op.g.Cout <= 32) conv1x1_mma_kernel<1, 8, 2, 4><<<g32, 256, 0, st>>>(SGS_MMA_ARGS);
-                else conv1x1_mma_kernel<2, 4, 2, 4><<<g64, 256, 0, st>>>(SGS_MMA_ARGS);
-#undef SGS_MMA_ARGS
-            } else if (ncols < (1ll << 31) - 256) {
-                const int nc = (int)ncols;
-                if (op.g.Cout <= 16) conv1x1_kernel<16, 256><<<dim3((nc + 255) / 256, (op.g.Cout + 15) / 16), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
-                else if (op.g.Cout <= 32) conv1x1_kernel<32, 128><<<dim3((nc + 127) / 128, (op.g.Cout + 31) / 32), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
-                else conv1x1_kernel<64, 64><<<dim3((nc + 63) / 64, (op.g.Cout + 63) / 64), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g.Cin, op.g.Cout, HW, nc, epi);
-            } else { set_error("sgs_detector_detect_device: batch too large for 32-bit column indices"); return SGS_ERR_UNSUPPORTED; }
+            const int HW = op.g.OH * op.g.OW; const int64_t npix = (int64_t)F * HW;
+            if (npix >= (1ll << 31) - 256) { set_error("sgs_detector_detect_device: batch too large for 32-bit pixel indices"); return SGS_ERR_UNSUPPORTED; }
+            const int64_t fstride = op.cat ? bo.n : (int64_t)HW * op.g.Cout;
+            if (!tc::launch_conv1x1_tc_map(op.gp, op.map_in, (int)npix, op.d_b, bo.dev, HW, fstride, op.cat ? op.off : 0, op.g.Cout, EpiFn{epi}, st)) {
+                set_error("sgs_detector_detect_device: layer %s: GEMM launch failed (%s)", D->layers[op.layer].name.c_str(), cudaGetErrorString(cudaGetLastError())); return SGS_ERR_CUDA; }
             break;
         }
         case OP_CONV_DIRECT: {
-            const int64_t total = (int64_t)F * op.g.Cout * op.g.OH * op.g.OW;
             const size_t wbytes = (size_t)op.g.Cin * op.g.k * op.g.k * kCot * sizeof(float);
-            if (wbytes <= 40 * 1024)
-                conv_small_kernel<<<dim3(nblk((int64_t)op.g.OH * op.g.OW), (op.g.Cout + kCot - 1) / kCot, F), 256, wbytes, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
-            else conv_direct_kernel<<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi);
+            if (wbytes > 96 * 1024) { set_error("sgs_detector_detect_device: layer %s: %zu bytes of weights per channel block do not fit shared memory", D->layers[op.layer].name.c_str(), wbytes); return SGS_ERR_UNSUPPORTED; }
+            const int64_t fstride = op.cat ? bo.n : (int64_t)op.g.OH * op.g.OW * op.g.Cout;
+            conv_small_kernel<<<dim3(nblk((int64_t)op.g.OH * op.g.OW), (op.g.Cout + kCot - 1) / kCot, F), 256, wbytes, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, fstride,
+                                                                                                                        op.cat ? op.off : 0, epi);
             break;
         }
         case OP_DWCONV: {
-            const dim3 grid(nblk((int64_t)op.g.OH * ((op.g.OW + 3) / 4)), op.g.Cout, F);      // Cout, F <= 65535 (checked at create / entry)
-            if (op.g.k == 3 && op.g.stride == 1) dwconv_kernel<3, 1><<<grid, 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
-            else if (op.g.k == 3) dwconv_kernel<3, 2><<<grid, 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
-            else if (op.g.stride == 1) dwconv_kernel<5, 1><<<grid, 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
-            else dwconv_kernel<5, 2><<<grid, 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
+            const int V = op.g.Cout % 4 == 0 ? 4 : 1;
+            const int64_t total = (int64_t)F * op.g.OH * ((op.g.OW + 3) / 4) * (op.g.Cout / V);
+#define SGS_DW(K, S) do { if (V == 4) dwconv_kernel<K, S, 4><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi); \
+                          else dwconv_kernel<K, S, 1><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi); } while (0)
+            if (op.g.k == 3 && op.g.stride == 1) SGS_DW(3, 1);
+            else if (op.g.k == 3) SGS_DW(3, 2);
+            else if (op.g.stride == 1) SGS_DW(5, 1);
+            else SGS_DW(5, 2);
+#undef SGS_DW
             break;
         }
         case OP_ELTWISE: {
             const int64_t total = (int64_t)F * bo.n;
             eltwise_kernel<<<nblk(total), 256, 0, st>>>(bi.dev, bo.dev, total, epi);
-            break;
-        }
-        case OP_PERMUTE: {
-            const int64_t total = (int64_t)F * bo.n;
-            permute_hwc_kernel<<<nblk(total), 256, 0, st>>>(bi.dev, bo.dev, bi.c, bi.h * bi.w, total);
             break;
         }
         case OP_CONCAT_COPY: {
@@ -1261,7 +1133,7 @@ int sgs_detect(sgs_detector* D, const uint8_t* rgb, int width, int height, int p
 
 int sgs_detector_describe(const sgs_detector* D, char* out, int64_t cap, int64_t* n) {
     if (!D || !n) { set_error("sgs_detector_describe: bad argument"); return SGS_ERR_INVALID; }
-    static const char* kind[] = {"conv1x1", "conv", "dwconv", "eltwise", "permute", "concat", "softmax"};
+    static const char* kind[] = {"conv1x1", "conv", "dwconv", "eltwise", "concat", "softmax"};
     static const char* opn[] = {"add", "sub", "mul", "div", "clip", "relu"};
     std::ostringstream ss;
     int64_t pool_floats = 0;
@@ -1272,7 +1144,8 @@ int sgs_detector_describe(const sgs_detector* D, char* out, int64_t cap, int64_t
         ss << kind[op.kind] << ' ' << D->layers[op.layer].name << " in " << bi.name << " buf " << D->blobs[root_of(*D, op.in)].buf << " out " << bo.name << " buf "
            << D->blobs[root_of(*D, op.out)].buf << " n " << bo.n;
         if (op.kind <= OP_DWCONV) ss << " geom " << op.g.Cin << 'x' << op.g.H << 'x' << op.g.W << "->" << op.g.Cout << 'x' << op.g.OH << 'x' << op.g.OW << " k" << op.g.k << " s" << op.g.stride << " p" << op.g.pad;
-        if (op.kind == OP_CONCAT_COPY) ss << " off " << op.off;
+        if (op.kind == OP_CONCAT_COPY || op.cat) ss << " off " << op.off;
+        if (op.kind == OP_CONV1X1) ss << " tile " << op.gp.NT << "x" << op.gp.n_tiles << " kb " << op.gp.KB << "x" << op.gp.BK << " stages " << op.gp.stages << (op.gp.b_resident ? " wres" : "") << " cps " << op.gp.ctas_per_sm;
         for (const auto& s : op.epi) {
             ss << " | " << opn[s.op] << (s.rev ? "(rev)" : "");
             if (s.op <= E_DIV) { if (s.src == SRC_SCALAR) ss << ' ' << s.a; else if (s.src == SRC_START) ss << " start"; else ss << ' ' << D->blobs[s.tblob].name << " buf " << D->blobs[root_of(*D, s.tblob)].buf; }
@@ -1304,6 +1177,13 @@ int sgs_detector_blob(sgs_detector* D, const char* name, int frame, float* out, 
     if (b.n > cap) { set_error("sgs_detector_blob: %lld floats, capacity %lld", (long long)b.n, (long long)cap); return SGS_ERR_CAPACITY; }
     SGS_CUDA_TRY(cudaSetDevice(D->device));
     SGS_CUDA_TRY(cudaDeviceSynchronize());
+    if (b.hwc && b.dims == 3 && b.c > 1 && b.h * b.w > 1) {        // stored [h][w][c]; ncnn's order is [c][h][w]
+        std::vector<float> tmp((size_t)b.n);
+        SGS_CUDA_TRY(cudaMemcpy(tmp.data(), b.dev + (int64_t)frame * b.n, (size_t)b.n * sizeof(float), cudaMemcpyDeviceToHost));
+        const int hw = b.h * b.w;
+        for (int p = 0; p < hw; ++p) for (int c = 0; c < b.c; ++c) out[(size_t)c * hw + p] = tmp[(size_t)p * b.c + c];
+        return SGS_OK;
+    }
     SGS_CUDA_TRY(cudaMemcpy(out, b.dev + (int64_t)frame * b.n, (size_t)b.n * sizeof(float), cudaMemcpyDeviceToHost));
     return SGS_OK;
 }

@@ -385,11 +385,12 @@ SGS_API int sgs_extractor_fetch(sgs_extractor* ex, int nframes, sgs_keypoint* kp
 
 SGS_API int sgs_extract_batch(sgs_extractor* ex, const uint8_t* gray, int nframes, size_t frame_stride, int pitch, sgs_keypoint* kps,
                               uint8_t* desc, int cap, int* n) {
-    if (!ex || !n) return fail_invalid("sgs_extract_batch: NULL argument");
+    const bool no_fetch = ex && !kps && !desc && !n && gray;      // upload + kernels only: the results stay on the device (sgs_extractor_results_device)
+    if (!ex || (!n && !no_fetch)) return fail_invalid("sgs_extract_batch: NULL argument");
     if (nframes < 0 || nframes > ex->max_batch) return fail_invalid("sgs_extract_batch: nframes outside [0,max_batch]");
     if (nframes == 0) return SGS_OK;
     if (!gray) { for (int f = 0; f < nframes; ++f) n[f] = 0; return SGS_OK; }  // empty image: ORBextractor.cc:1048
-    if (!kps) return fail_invalid("sgs_extract_batch: NULL output");                  // desc == NULL: keypoints only
+    if (!kps && !no_fetch) return fail_invalid("sgs_extract_batch: NULL output");    // desc == NULL: keypoints only
     const OrbPlan& PL = ex->plan;
     if (pitch < PL.width || frame_stride < (size_t)pitch * PL.height) return fail_invalid("sgs_extract_batch: pitch/frame_stride too small");
     SGS_CUDA_TRY(cudaSetDevice(ex->device));
@@ -421,7 +422,7 @@ SGS_API int sgs_extract_batch(sgs_extractor* ex, const uint8_t* gray, int nframe
             if (rc != SGS_OK) return rc;
         }
         ex->last_level0_external = false;
-        return sgs_extractor_fetch(ex, nframes, kps, desc, cap, n, st);
+        return no_fetch ? SGS_OK : sgs_extractor_fetch(ex, nframes, kps, desc, cap, n, st);
     }
     if (pinned) {
         if (frame_stride == (size_t)pitch * PL.height) {
@@ -439,8 +440,10 @@ SGS_API int sgs_extract_batch(sgs_extractor* ex, const uint8_t* gray, int nframe
     ex->last_level0_external = false;
     int rc = enqueue(ex, ex->d_pyr, g0.pitch, g0.frame_stride, nframes, st);
     if (rc != SGS_OK) return rc;
-    return sgs_extractor_fetch(ex, nframes, kps, desc, cap, n, st);
+    return no_fetch ? SGS_OK : sgs_extractor_fetch(ex, nframes, kps, desc, cap, n, st);
 }
+
+SGS_API void* sgs_extractor_stream(const sgs_extractor* ex) { return ex ? (void*)ex->stream : nullptr; }
 
 SGS_API int sgs_extract(sgs_extractor* ex, const uint8_t* gray, int width, int height, int pitch, sgs_keypoint* kps, uint8_t* desc, int cap, int* n) {
     if (!ex || !n) return fail_invalid("sgs_extract: NULL argument");

@@ -11,7 +11,7 @@
 //     sign vectors projected off the row space.  The row space comes from a twice-applied modified Gram-Schmidt instead of the
 //     Jacobi sweeps (same subspace, ~1e-15 relative difference in F).
 // All arithmetic is FP64 with individually rounded products and sums (-fmad=false), errors are rounded to float before the
-// threshold test like OpenCV's.  Fewer than 15 pairs (OpenCV: LMedS / plain 7-point) are not handled on the device: F = NaN.
+// threshold test like OpenCV's.  Fewer than 15 pairs take OpenCV's other branches in the same kernel: LMedS (8..14), plain 7-point (7), empty (< 7).
 #include <cuda_runtime.h>
 
 #include <cfloat>
@@ -192,6 +192,43 @@ __device__ __forceinline__ bool fm_inlier(const float4 p, const double* F, float
     const float err = (float)fmax(d1 * d1 * s1, d2 * d2 * s2);
     return err <= t;
 }
+__device__ __forceinline__ float fm_error(const float4 p, const double* F) {                  // FMEstimatorCallback::computeError, one pair
+    const double x1 = p.x, y1 = p.y, x2 = p.z, y2 = p.w;
+    double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+    const double s2 = 1. / (a * a + b * b), d2 = x2 * a + y2 * b + c;
+    a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8];
+    const double s1 = 1. / (a * a + b * b), d1 = x1 * a + y1 * b + c;
+    return (float)fmax(d1 * d1 * s1, d2 * d2 * s2);
+}
+
+// RANSACPointSetRegistrator / LMeDSPointSetRegistrator::getSubset for `want` consecutive iterations (sequential RNG state: one thread).
+// Returns the number of samples drawn; *ok = 0 when a draw failed (10000 attempts without a non-collinear sample): the estimator's loop ends there.
+__device__ int fm_draw_samples(FmRng& rng, const float4* pts, int n, int want, int (*idx_out)[7], int* ok) {
+    int got = 0;
+    *ok = 1;
+    for (; got < want; ++got) {
+        bool found = false;
+        for (int attempt = 0; attempt < 10000 && !found; ++attempt) {
+            float2 a[7], b[7];
+            int* idx = idx_out[got];
+            for (int i = 0; i < 7; ++i) {
+                int v;
+                for (;;) {
+                    v = rng.uniform(0, n);
+                    bool dup = false;
+                    for (int j = 0; j < i; ++j) dup |= idx[j] == v;
+                    if (!dup) break;
+                }
+                idx[i] = v;
+                const float4 p = pts[v];
+                a[i] = make_float2(p.x, p.y); b[i] = make_float2(p.z, p.w);
+            }
+            found = !fm_collinear(a) && !fm_collinear(b);
+        }
+        if (!found) { *ok = 0; break; }
+    }
+    return got;
+}
 
 __device__ int fm_update_iters(double p, double ep, int max_iters) {     // RANSACUpdateNumIters, modelPoints = 7
     p = fmin(fmax(p, 0.), 1.); ep = fmin(fmax(ep, 0.), 1.);
@@ -202,7 +239,8 @@ __device__ int fm_update_iters(double p, double ep, int max_iters) {     // RANS
 }
 
 // cur points come from keypoints (kps != nullptr) or a float2 array; prev from a float2 array.
-// info[f] = {pairs used, inliers of the returned model, iterations run, status (0 ok, 1 fewer than 15 pairs, 2 no model, 3 no previous frame)}
+// info[f] = {pairs used, inliers of the returned model, iterations run, status (0 ok, 1 fewer than 7 pairs, 2 no model, 3 no previous frame)}
+// 7 pairs: the 7-point solver directly; 8..14 pairs: LMedS; 15 and more: RANSAC -- the three branches of cv::findFundamentalMat(FM_RANSAC).
 __global__ void __launch_bounds__(kFmThreads) fm_ransac_kernel(const sgs_keypoint* __restrict__ kps, const float2* __restrict__ cur_xy,
                                                                const float2* __restrict__ prev_xy, const int32_t* __restrict__ counts, int cap,
                                                                const sgs_rect* __restrict__ prev_boxes, const int32_t* __restrict__ prev_nboxes,
@@ -266,10 +304,93 @@ __global__ void __launch_bounds__(kFmThreads) fm_ransac_kernel(const sgs_keypoin
     __syncthreads();
     double* Fo = F_out + (int64_t)f * 9;
     int32_t* inf = info ? info + (int64_t)f * 4 : nullptr;
-    if (n < 15 || no_prev) {          // OpenCV: empty (< 7), plain 7-point (== 7) or LMedS (< 15); not on the device
-        if (tid < 9) Fo[tid] = __longlong_as_double(0x7ff8000000000000LL);
+    if (thresh <= 0) thresh = 3;
+    if (confidence < DBL_EPSILON || confidence > 1 - DBL_EPSILON) confidence = 0.99;
+    const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+    if (n < 7 || no_prev) {           // cv::findFundamentalMat returns an empty matrix below 7 pairs (fundam.cpp): "empty F" = NaN here
+        if (tid < 9) Fo[tid] = kNaN;
         if (tid == 0 && inf) { inf[0] = n; inf[1] = 0; inf[2] = 0; inf[3] = no_prev ? 3 : 1; }
         if (mask_out) for (int i = tid; i < n_all; i += kFmThreads) mask_out[(int64_t)f * cap + i] = 0;
+        return;
+    }
+    if (n == 7) {                     // exactly 7 pairs: the 7-point solver itself, up to three stacked solutions; the reference reads rows 0..2 = the first
+        if (tid == 0) {
+            float2 a[7], b[7];
+            for (int i = 0; i < 7; ++i) { const float4 p = s_pts[i]; a[i] = make_float2(p.x, p.y); b[i] = make_float2(p.z, p.w); }
+            double Fm[27];
+            const int nm = fm_run7point(a, b, Fm);
+            for (int i = 0; i < 9; ++i) Fo[i] = nm > 0 ? Fm[i] : kNaN;
+            if (inf) { inf[0] = n; inf[1] = nm > 0 ? 7 : 0; inf[2] = 1; inf[3] = nm > 0 ? 0 : 2; }
+        }
+        if (mask_out) for (int i = tid; i < n_all; i += kFmThreads) mask_out[(int64_t)f * cap + i] = i < n ? 1 : 0;      // OpenCV sets the whole mask
+        return;
+    }
+    if (n < 15) {
+        // 8..14 pairs: cv::findFundamentalMat switches to LMeDSPointSetRegistrator(cb, 7, confidence) (fundam.cpp; ptsetreg.cpp): a FIXED number of
+        // samples (outlier ratio 0.45, at most 1000), the model with the smallest median error (element n/2 of the sorted errors, strict '<'),
+        // inliers within sigma = 2.5 * 1.4826 * (1 + 5 / (n - 7)) * sqrt(median) (at least 0.001); fewer than 7 inliers -> empty matrix.
+        __shared__ float s_med[kFmRound * 3];
+        __shared__ double s_minmed;
+        __shared__ int s_lm_good;
+        const int niters = max(fm_update_iters(confidence, 0.45, 1000), 3);
+        if (tid == 0) { s_done = 0; s_rng = 0xffffffffffffffffULL; s_minmed = DBL_MAX; s_drawn_ok = 1; s_lm_good = 0; }
+        __syncthreads();
+        while (true) {
+            if (tid == 0) {
+                FmRng rng; rng.state = s_rng;
+                int okd = 1;
+                s_round = fm_draw_samples(rng, s_pts, n, min(kFmRound, niters - s_done), s_idx, &okd);
+                if (!okd) s_drawn_ok = 0;
+                s_rng = rng.state;
+            }
+            __syncthreads();
+            const int round = s_round;
+            if (tid < round) {
+                float2 a[7], b[7];
+                for (int i = 0; i < 7; ++i) { const float4 p = s_pts[s_idx[tid][i]]; a[i] = make_float2(p.x, p.y); b[i] = make_float2(p.z, p.w); }
+                double Fm[27];
+                const int nm = fm_run7point(a, b, Fm);
+                s_nmodels[tid] = nm;
+                for (int k = 0; k < nm; ++k) {
+                    float e[14];
+                    for (int i = 0; i < n; ++i) {                              // insertion sort of the n <= 14 errors
+                        const float v = fm_error(s_pts[i], Fm + 9 * k);
+                        int j = i;
+                        for (; j > 0 && e[j - 1] > v; --j) e[j] = e[j - 1];
+                        e[j] = v;
+                    }
+                    s_med[tid * 3 + k] = e[n / 2];
+                    for (int i = 0; i < 9; ++i) s_models[tid * 3 + k][i] = Fm[9 * k + i];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {                                                    // sequential replay: strict improvement, iteration order, model order
+                double mm = s_minmed;
+                for (int it = 0; it < round; ++it)
+                    for (int k = 0; k < s_nmodels[it]; ++k) {
+                        const double med = (double)s_med[it * 3 + k];
+                        if (med < mm) { mm = med; for (int i = 0; i < 9; ++i) s_best[i] = s_models[it * 3 + k][i]; }
+                    }
+                s_minmed = mm; s_done += round;
+            }
+            __syncthreads();
+            if (s_done >= niters || !s_drawn_ok) break;
+            __syncthreads();
+        }
+        bool ok = s_minmed < DBL_MAX;
+        float tl = 0.f;
+        if (ok) {
+            double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 7)) * sqrt(s_minmed);
+            sigma = fmax(sigma, 0.001);
+            tl = (float)(sigma * sigma);
+            if (tid < n && fm_inlier(s_pts[tid], s_best, tl)) atomicAdd(&s_lm_good, 1);
+        }
+        __syncthreads();
+        const int good = s_lm_good;
+        ok = ok && good >= 7;
+        if (tid < 9) Fo[tid] = ok ? s_best[tid] : kNaN;
+        if (tid == 0 && inf) { inf[0] = n; inf[1] = good; inf[2] = s_done; inf[3] = ok ? 0 : 2; }
+        if (mask_out) for (int i = tid; i < n_all; i += kFmThreads) mask_out[(int64_t)f * cap + i] = (ok && i < n && fm_inlier(s_pts[i], s_best, tl)) ? 1 : 0;
         return;
     }
     if (thresh <= 0) thresh = 3;
@@ -283,28 +404,9 @@ __global__ void __launch_bounds__(kFmThreads) fm_ransac_kernel(const sgs_keypoin
         if (tid == 0) {
             FmRng rng; rng.state = s_rng;
             const int want = min(first ? kFmFirstRound : kFmRound, s_niters - s_done);
-            int got = 0;
-            for (; got < want; ++got) {
-                bool found = false;
-                for (int attempt = 0; attempt < 10000 && !found; ++attempt) {
-                    float2 a[7], b[7];
-                    int* idx = s_idx[got];
-                    for (int i = 0; i < 7; ++i) {
-                        int v;
-                        for (;;) {
-                            v = rng.uniform(0, n);
-                            bool dup = false;
-                            for (int j = 0; j < i; ++j) dup |= idx[j] == v;
-                            if (!dup) break;
-                        }
-                        idx[i] = v;
-                        const float4 p = s_pts[v];
-                        a[i] = make_float2(p.x, p.y); b[i] = make_float2(p.z, p.w);
-                    }
-                    found = !fm_collinear(a) && !fm_collinear(b);
-                }
-                if (!found) { s_drawn_ok = 0; break; }     // getSubset failed: the loop ends here (or fails when it is the first iteration)
-            }
+            int okd = 1;
+            const int got = fm_draw_samples(rng, s_pts, n, want, s_idx, &okd);      // a failed draw ends the loop (or fails it when it is the first iteration)
+            if (!okd) s_drawn_ok = 0;
             s_round = got;
             s_rng = rng.state;
         }

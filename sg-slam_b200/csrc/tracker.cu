@@ -32,6 +32,9 @@ struct sgs_tracker {
     sgs_keypoint* d_kps2 = nullptr; uint8_t* d_desc2 = nullptr; int32_t* d_cnt2 = nullptr; uint8_t* d_keep = nullptr; float* d_uright2 = nullptr;
     int32_t* d_mp = nullptr; int32_t* d_nm = nullptr; unsigned long long* d_ncand = nullptr;
     int last_nframes = 0;
+    // detector inside the step (sgs_tracker_step / sgs_tracker_detect_device): RGB staging, its own stream, the join events
+    uint8_t* d_rgb = nullptr; size_t d_rgb_cap = 0; int32_t* d_det_status = nullptr;
+    cudaStream_t det_st = nullptr; cudaEvent_t det_ev = nullptr; cudaEvent_t ex_ev = nullptr;
 };
 
 namespace sgs {
@@ -86,6 +89,11 @@ SGS_API void sgs_tracker_destroy(sgs_tracker* t) {
     if (t->st) cudaStreamDestroy(t->st);
     if (t->copy_st) cudaStreamDestroy(t->copy_st);
     if (t->copy_ev) cudaEventDestroy(t->copy_ev);
+    if (t->d_rgb) cudaFree(t->d_rgb);
+    if (t->d_det_status) cudaFree(t->d_det_status);
+    if (t->det_st) cudaStreamDestroy(t->det_st);
+    if (t->det_ev) cudaEventDestroy(t->det_ev);
+    if (t->ex_ev) cudaEventDestroy(t->ex_ev);
     delete t;
 }
 
@@ -109,13 +117,16 @@ SGS_API int sgs_tracker_create(const sgs_orb_params* params, int width, int heig
     cudaError_t e = cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->copy_st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->copy_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->det_st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->det_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ex_ev, cudaEventDisableTiming);
 #define A(call) if (e == cudaSuccess) e = (call)
     A(dalloc(&t->d_prev, B * K * 2)); A(dalloc(&t->d_uright_in, B * K)); A(dalloc(&t->d_F, B * 9)); A(dalloc(&t->d_boxes, B * t->max_boxes));
     A(dalloc(&t->d_nboxes, B)); A(dalloc(&t->d_have, B)); A(dalloc(&t->d_lxyz, B * M * 3)); A(dalloc(&t->d_ldesc, B * M * 32));
     A(dalloc(&t->d_lflags, B * M)); A(dalloc(&t->d_loct, B * M)); A(dalloc(&t->d_lang, B * M)); A(dalloc(&t->d_ln, B));
     A(dalloc(&t->d_tc, B * 16)); A(dalloc(&t->d_tl, B * 16)); A(dalloc(&t->d_kps2, B * K)); A(dalloc(&t->d_desc2, B * K * 32));
     A(dalloc(&t->d_cnt2, B)); A(dalloc(&t->d_keep, B * K)); A(dalloc(&t->d_uright2, B * K)); A(dalloc(&t->d_mp, B * K)); A(dalloc(&t->d_nm, B));
-    A(dalloc(&t->d_ncand, B)); A(dalloc(&t->d_Fgpu, B * 9)); A(dalloc(&t->d_finfo, B * 4));
+    A(dalloc(&t->d_ncand, B)); A(dalloc(&t->d_Fgpu, B * 9)); A(dalloc(&t->d_finfo, B * 4)); A(dalloc(&t->d_det_status, B));
 #undef A
     if (e != cudaSuccess) { set_error("sgs_tracker_create: %s", cudaGetErrorString(e)); sgs_tracker_destroy(t); return SGS_ERR_CUDA; }
     *out = t;
@@ -148,8 +159,10 @@ SGS_API int sgs_tracker_track_device(sgs_tracker* t, int nframes, const float* p
                                      const int32_t* nboxes, const uint8_t* have_dyn, const float* last_xyz, const uint8_t* last_desc,
                                      const uint8_t* last_flags, const int32_t* last_octave, const float* last_angle, const int32_t* last_n,
                                      const float* tcw_cur, const float* tcw_last, float th, int mono, int check_orientation, void* stream) {
-    if (!t || !nboxes || !have_dyn || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle ||
+    if (!t || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle ||
         !last_n || !tcw_cur || !tcw_last) return bad("sgs_tracker_track_device: NULL argument");
+    if (!nboxes) nboxes = t->d_nboxes;           // boxes / nboxes / have_dyn == NULL: the tracker's own arrays, filled by sgs_tracker_detect_device
+    if (!have_dyn) have_dyn = t->d_have;
     if (!u_right) u_right = t->d_uright_in;      // filled by sgs_tracker_stereo_device
     if (!F) F = t->d_Fgpu;                  // filled by sgs_tracker_fundamental_device
     if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_track_device: nframes exceeds the last extract call");
@@ -233,7 +246,9 @@ SGS_API int sgs_tracker_lk_device(sgs_tracker* t, const uint8_t* d_frames, int n
 
 SGS_API int sgs_tracker_fundamental_device(sgs_tracker* t, int nframes, const sgs_rect* d_boxes, const int32_t* d_nboxes, const uint8_t* d_have_dyn,
                                            const int32_t* d_prev_index, void* stream) {
-    if (!t || !d_nboxes || !d_have_dyn || !d_prev_index) return bad("sgs_tracker_fundamental_device: NULL argument");
+    if (!t || !d_prev_index) return bad("sgs_tracker_fundamental_device: NULL argument");
+    if (!d_nboxes) d_nboxes = t->d_nboxes;       // NULL: the tracker's own arrays, filled by sgs_tracker_detect_device
+    if (!d_have_dyn) d_have_dyn = t->d_have;
     if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_fundamental_device: nframes exceeds the last extract call");
     const sgs_keypoint* d_kps; const uint8_t* d_desc; const int32_t* d_cnt; int cap = 0;
     sgs_extractor_results_device(t->ex, &d_kps, &d_desc, &d_cnt, &cap);
@@ -307,6 +322,98 @@ SGS_API int sgs_tracker_track_lk(sgs_tracker* t, int nframes, const int32_t* pre
     D2H(kps_out, t->d_kps2, B * K * sizeof(sgs_keypoint)); D2H(desc_out, t->d_desc2, B * K * 32); D2H(counts_out, t->d_cnt2, B * 4);
     if (u_right_out) D2H(u_right_out, t->d_uright2, B * K * 4);
     D2H(cur_mp_out, t->d_mp, B * K * 4); D2H(nmatches_out, t->d_nm, B * 4);
+#undef D2H
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    return SGS_OK;
+}
+
+// Detector2D::detect for the frames of the batch (src/Tracking.cc:288-307 hands the colour image to the detector thread; src/Frame.cc:478-500
+// joins it before the rejection): the person boxes land in the tracker's own box arrays, in the layout the F estimate and the rejection take
+// when called with boxes == NULL.  d_rgb: device frames (interleaved 8-bit RGB).  Enqueued on `stream` (NULL: the tracker's detector stream, which
+// the next sgs_tracker_fundamental_device / _track_device call on the tracker's stream is NOT ordered after -- use sgs_tracker_step for that).
+SGS_API int sgs_tracker_detect_device(sgs_tracker* t, sgs_detector* det, const uint8_t* d_rgb, int64_t frame_stride, int pitch, int width, int height, int nframes,
+                                      void* stream) {
+    if (!t || !det || !d_rgb) return bad("sgs_tracker_detect_device: NULL argument");
+    if (nframes < 1 || nframes > t->max_batch) return bad("sgs_tracker_detect_device: nframes outside [1,max_batch]");
+    return sgs_detector_detect_device(det, d_rgb, frame_stride, pitch, width, height, nframes, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, t->d_boxes, t->d_nboxes,
+                                      t->d_have, t->max_boxes, t->d_det_status, stream ? stream : (void*)t->det_st);
+}
+SGS_API int sgs_tracker_boxes_device(const sgs_tracker* t, const sgs_rect** d_boxes, const int32_t** d_nboxes, const uint8_t** d_have_dyn) {
+    if (!t) return bad("sgs_tracker_boxes_device: NULL");
+    if (d_boxes) *d_boxes = t->d_boxes;
+    if (d_nboxes) *d_nboxes = t->d_nboxes;
+    if (d_have_dyn) *d_have_dyn = t->d_have;
+    return SGS_OK;
+}
+
+// The whole per-frame front end of the tracking thread for a batch of frames, HOST buffers in and out (src/Tracking.cc:203-307 + the Frame
+// constructor src/Frame.cc:129-198 + TrackWithMotionModel's matcher call :906-924):
+//   colour frames -> detector (own stream)            ------------------\
+//   gray frames   -> ORB extract -> LK to the previous frame -> join -> findFundamentalMat -> dyn-reject + compaction -> SearchByProjection(cur, last)
+// Uploads run on copy streams beside the kernels; one synchronisation at the end.  boxes_out / nboxes_out / have_out (may be NULL): the
+// detector's person boxes for the rejection, as the Frame would hold them.
+SGS_API int sgs_tracker_step(sgs_tracker* t, sgs_detector* det, const uint8_t* gray, size_t gray_stride, int gray_pitch, const uint8_t* rgb, size_t rgb_stride,
+                             int rgb_pitch, int nframes, const int32_t* prev_index, const float* u_right, const float* last_xyz, const uint8_t* last_desc,
+                             const uint8_t* last_flags, const int32_t* last_octave, const float* last_angle, const int32_t* last_n, const float* tcw_cur,
+                             const float* tcw_last, float th, int mono, int check_orientation, sgs_keypoint* kps_out, uint8_t* desc_out, float* u_right_out,
+                             int32_t* counts_out, int32_t* cur_mp_out, int32_t* nmatches_out, sgs_rect* boxes_out, int32_t* nboxes_out, uint8_t* have_out) {
+    if (!t || !det || !gray || !rgb || !prev_index || !u_right || !last_xyz || !last_desc || !last_flags || !last_octave || !last_angle || !last_n || !tcw_cur ||
+        !tcw_last || !kps_out || !desc_out || !counts_out || !cur_mp_out || !nmatches_out) return bad("sgs_tracker_step: NULL argument");
+    if (nframes < 1 || nframes > t->max_batch) return bad("sgs_tracker_step: nframes outside [1,max_batch]");
+    if (rgb_pitch < t->width * 3 || rgb_stride < (size_t)rgb_pitch * t->height) return bad("sgs_tracker_step: rgb pitch / stride too small");
+    for (int f = 0; f < nframes; ++f) if (prev_index[f] < 0 || prev_index[f] >= nframes) return bad("sgs_tracker_step: prev_index out of range");
+    SGS_CUDA_TRY(cudaSetDevice(t->device));
+    const size_t B = nframes, K = t->cap, M = t->point_cap;
+    // ---- detector branch: colour frames up, network, boxes into the tracker's arrays
+    const size_t rgb_bytes = (size_t)t->width * 3 * t->height;
+    if (t->d_rgb_cap < rgb_bytes * (size_t)t->max_batch) {
+        if (t->d_rgb) cudaFree(t->d_rgb);
+        t->d_rgb = nullptr; t->d_rgb_cap = 0;
+        SGS_CUDA_TRY(cudaMalloc((void**)&t->d_rgb, rgb_bytes * (size_t)t->max_batch));
+        t->d_rgb_cap = rgb_bytes * (size_t)t->max_batch;
+    }
+    if (rgb_stride == (size_t)rgb_pitch * t->height) {
+        SGS_CUDA_TRY(cudaMemcpy2DAsync(t->d_rgb, (size_t)t->width * 3, rgb, rgb_pitch, (size_t)t->width * 3, (size_t)t->height * B, cudaMemcpyHostToDevice, t->det_st));
+    } else {
+        for (size_t f = 0; f < B; ++f)
+            SGS_CUDA_TRY(cudaMemcpy2DAsync(t->d_rgb + f * rgb_bytes, (size_t)t->width * 3, rgb + f * rgb_stride, rgb_pitch, (size_t)t->width * 3, t->height, cudaMemcpyHostToDevice, t->det_st));
+    }
+    int rc = sgs_tracker_detect_device(t, det, t->d_rgb, (int64_t)rgb_bytes, t->width * 3, t->width, t->height, nframes, t->det_st);
+    if (rc != SGS_OK) return rc;
+    SGS_CUDA_TRY(cudaEventRecord(t->det_ev, t->det_st));
+    // ---- tracking branch: gray frames up + ORB extraction (the extractor's streams), then LK on the tracker's stream
+    rc = sgs_extract_batch(t->ex, gray, nframes, gray_stride, gray_pitch, nullptr, nullptr, 0, nullptr);
+    if (rc != SGS_OK) return rc;
+    t->last_nframes = nframes;
+    cudaStream_t st = t->st, cs = t->copy_st;
+    SGS_CUDA_TRY(cudaEventRecord(t->ex_ev, (cudaStream_t)sgs_extractor_stream(t->ex)));
+    SGS_CUDA_TRY(cudaStreamWaitEvent(st, t->ex_ev, 0));
+#define H2D(dst, src, bytes, s) SGS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s))
+    H2D(t->d_pidx, prev_index, sizeof(int32_t) * B, st);
+    H2D(t->d_uright_in, u_right, B * K * 4, cs);
+    H2D(t->d_lxyz, last_xyz, B * M * 12, cs); H2D(t->d_ldesc, last_desc, B * M * 32, cs); H2D(t->d_lflags, last_flags, B * M, cs);
+    H2D(t->d_loct, last_octave, B * M * 4, cs); H2D(t->d_lang, last_angle, B * M * 4, cs); H2D(t->d_ln, last_n, B * 4, cs);
+    H2D(t->d_tc, tcw_cur, B * 64, cs); H2D(t->d_tl, tcw_last, B * 64, cs);
+#undef H2D
+    SGS_CUDA_TRY(cudaEventRecord(t->copy_ev, cs));
+    const uint8_t* d_frames; int pitch; size_t fstride;
+    sgs_extractor_level0_device(t->ex, &d_frames, &pitch, &fstride);
+    rc = sgs_tracker_lk_device(t, d_frames, nframes, fstride, pitch, t->d_pidx, st);
+    if (rc != SGS_OK) return rc;
+    SGS_CUDA_TRY(cudaStreamWaitEvent(st, t->det_ev, 0));                  // the join of src/Frame.cc:478-481: boxes of every frame of the batch are there
+    rc = sgs_tracker_fundamental_device(t, nframes, nullptr, nullptr, nullptr, t->d_pidx, st);
+    if (rc != SGS_OK) return rc;
+    SGS_CUDA_TRY(cudaStreamWaitEvent(st, t->copy_ev, 0));
+    rc = sgs_tracker_track_device(t, nframes, nullptr, t->d_uright_in, nullptr, nullptr, nullptr, nullptr, t->d_lxyz, t->d_ldesc, t->d_lflags, t->d_loct, t->d_lang, t->d_ln,
+                                  t->d_tc, t->d_tl, th, mono, check_orientation, st);
+    if (rc != SGS_OK) return rc;
+#define D2H(dst, src, bytes) SGS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st))
+    D2H(kps_out, t->d_kps2, B * K * sizeof(sgs_keypoint)); D2H(desc_out, t->d_desc2, B * K * 32); D2H(counts_out, t->d_cnt2, B * 4);
+    if (u_right_out) D2H(u_right_out, t->d_uright2, B * K * 4);
+    D2H(cur_mp_out, t->d_mp, B * K * 4); D2H(nmatches_out, t->d_nm, B * 4);
+    if (boxes_out) D2H(boxes_out, t->d_boxes, B * t->max_boxes * sizeof(sgs_rect));
+    if (nboxes_out) D2H(nboxes_out, t->d_nboxes, B * 4);
+    if (have_out) D2H(have_out, t->d_have, B);
 #undef D2H
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
     return SGS_OK;

@@ -117,7 +117,7 @@ ABI_SYMBOLS = [
     'sgs_tracker_lk_device', 'sgs_tracker_prev_xy_device', 'sgs_tracker_track_lk', 'sgs_extractor_level0_device', 'sgs_memcpy_d2h',
     'sgs_lk_set_profiling', 'sgs_lk_stage_times', 'sgs_tracker_lk',
     'sgs_pose_optimization_batch_device', 'sgs_pose_optimization', 'sgs_distinctive_descriptor_batch_device', 'sgs_fuse_search_batch_device', 'sgs_fuse_search', 'sgs_match_project_keyframe_batch_device', 'sgs_match_project_keyframe',
-    'sgs_vocabulary_create', 'sgs_vocabulary_destroy', 'sgs_vocabulary_parse_file', 'sgs_vocabulary_load', 'sgs_bow_transform_batch_device', 'sgs_match_bow_batch_device', 'sgs_bow_transform', 'sgs_match_bow', 'sgs_match_bow_keyframes', 'sgs_search_for_initialization_batch_device', 'sgs_search_for_initialization',
+    'sgs_tracker_detect_device', 'sgs_tracker_boxes_device', 'sgs_tracker_step', 'sgs_extractor_stream', 'sgs_vocabulary_create', 'sgs_vocabulary_create_device', 'sgs_vocabulary_destroy', 'sgs_vocabulary_parse_file', 'sgs_vocabulary_load', 'sgs_bow_transform_batch_device', 'sgs_match_bow_batch_device', 'sgs_bow_transform', 'sgs_match_bow', 'sgs_match_bow_keyframes', 'sgs_search_for_initialization_batch_device', 'sgs_search_for_initialization',
     'sgs_stereo_from_depth_batch_device', 'sgs_frustum_batch_device', 'sgs_frustum', 'sgs_undistort_batch_device', 'sgs_undistort_points', 'sgs_image_bounds', 'sgs_tracker_stereo_device',
     'sgs_fundamental_ransac', 'sgs_fundamental_batch_device', 'sgs_tracker_fundamental_device', 'sgs_tracker_fundamental_device_ptr',
     'sgs_detector_create', 'sgs_detector_destroy', 'sgs_detector_info', 'sgs_detector_detect_device', 'sgs_detect', 'sgs_detector_describe', 'sgs_detector_blob',
@@ -471,7 +471,7 @@ def memcpy_d2h(dst_array, d_ptr):
 
 
 OBJ_DTYPE = np.dtype([('id', '<i4'), ('prob', '<f4'), ('x', '<f4'), ('y', '<f4'), ('w', '<f4'), ('h', '<f4')])   # sgs_object2d
-DET_DIAGNOSTIC, DET_PLAN_ONLY, DET_FMA_GEMM = 1, 2, 4
+DET_DIAGNOSTIC, DET_PLAN_ONLY = 1, 2
 
 
 class Detector:

@@ -106,3 +106,16 @@ def descriptors_near(train, seed=6, maxflips=40):
         idx = rng.choice(256, nf, replace=False)
         bits[i, idx] ^= 1
     return np.packbits(bits, axis=1)
+
+
+def scale_factors(nlevels=8, sf=1.2):
+    """mvScaleFactor of ORBextractor (src/ORBextractor.cc:416-421): float32 chain 1, 1.2, 1.44, ..."""
+    s = [np.float32(1.0)]
+    for _ in range(1, nlevels):
+        s.append(np.float32(np.float64(s[-1]) * np.float64(np.float32(sf))))
+    return np.array(s, np.float32)
+
+
+def gray_to_rgb(frames):
+    """Colour frames for the detector: the gray frame in all three channels ([n,h,w] -> [n,h,w,3] uint8)."""
+    return np.ascontiguousarray(np.repeat(frames[..., None], 3, axis=-1))

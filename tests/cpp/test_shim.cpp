@@ -155,8 +155,11 @@ int main(int argc, char** argv) {
     double fmax = 1.0;
     for (int i = 0; i < 9; ++i) fmax = std::max(fmax, std::fabs(expF[i]));
     for (int i = 0; i < 9; ++i) if (std::fabs(Fg.at<double>(i / 3, i % 3) - expF[i]) > 1e-9 * fmax) return fail("findFundamentalMat: F");
-    if (!FindFundamentalMatRansac(std::vector<cv::Point2f>(cpts.begin(), cpts.begin() + 10), std::vector<cv::Point2f>(exp_trk.begin(), exp_trk.begin() + 10)).empty())
-        return fail("findFundamentalMat: fewer than 15 pairs must come back empty");
+    // below 15 pairs OpenCV's function takes its LMedS branch (8..14 pairs), below 7 it returns an empty matrix: both through the same entry point
+    if (FindFundamentalMatRansac(std::vector<cv::Point2f>(cpts.begin(), cpts.begin() + 10), std::vector<cv::Point2f>(exp_trk.begin(), exp_trk.begin() + 10)).empty())
+        return fail("findFundamentalMat: 10 pairs must take the LMedS branch and return a model");
+    if (!FindFundamentalMatRansac(std::vector<cv::Point2f>(cpts.begin(), cpts.begin() + 6), std::vector<cv::Point2f>(exp_trk.begin(), exp_trk.begin() + 6)).empty())
+        return fail("findFundamentalMat: fewer than 7 pairs must come back empty");
     // 5. isInFrustum for a batch of map points (expected values: CPU oracle)
     int32_t nfr = 0; f.read(reinterpret_cast<char*>(&nfr), 4);
     std::vector<float> fT = rd<float>(f, 16), fxyz = rd<float>(f, (size_t)nfr * 3), fnrm = rd<float>(f, (size_t)nfr * 3), fmn = rd<float>(f, nfr), fmx = rd<float>(f, nfr);

@@ -25,6 +25,17 @@ def main():
         out[f'l{i}_F'] = np.zeros((0, 3)) if F is None else F
         out[f'l{i}_mask'] = np.zeros(0, np.uint8) if mask is None else mask.ravel().astype(np.uint8)
         print(n, noise, of, None if F is None else int(mask.sum()))
+    # exactly 7 pairs: cv::findFundamentalMat runs the 7-point solver itself and returns its 1..3 solutions STACKED (3k x 3); the reference reads
+    # F.at<double>(0..2, 0..2) = the first (src/Frame.cc:613-627).  Fewer than 7: empty.
+    for j in range(4):
+        m1, m2 = g.two_view(rs, 7, 0.3, 0.0)
+        F, mask = cv2.findFundamentalMat(m1, m2, cv2.FM_RANSAC, 1.0, 0.99)
+        out[f's{j}_m1'] = m1; out[f's{j}_m2'] = m2; out[f's{j}_F'] = np.zeros((0, 3)) if F is None else F
+        print(7, None if F is None else F.shape)
+    m1, m2 = g.two_view(rs, 6, 0.3, 0.0)
+    F, mask = cv2.findFundamentalMat(m1, m2, cv2.FM_RANSAC, 1.0, 0.99)
+    assert F is None
+    out['n_seven'] = np.array(4)
     out['n_cases'] = np.array(len(cases)); out['cv2_version'] = np.array(cv2.__version__)
     np.savez_compressed(os.path.join(HERE, 'fm_lmeds.npz'), **out)
 

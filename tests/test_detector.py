@@ -162,7 +162,14 @@ def test_create_reports_bad_files(tmp_path):
 def test_plan_of_the_reference_model():
     txt, (nl, nk) = _describe(REAL + '.param', REAL + '.bin', 0)
     lines = txt.splitlines()
-    assert nl == 408 and nk == 129 and not any(l.startswith('eltwise') for l in lines)
+    assert nl == 408 and nk == 105 and not any(l.startswith(('eltwise', 'permute', 'concat')) for l in lines)
+    # [h][w][c] activations: the 12 Permute layers are aliases and the 12 SSD head convolutions write straight into mbox_loc / mbox_conf
+    heads = [l for l in lines if ' out mbox_loc ' in l or ' out mbox_conf ' in l]
+    assert len(heads) == 12 and all(l.startswith('conv1x1 ') and ' off ' in l for l in heads)
+    offs = sorted(int(l.split(' off ')[1].split()[0]) for l in heads if ' out mbox_conf ' in l)
+    assert offs == [0, 30324, 42924, 46074, 47208, 47544]
+    # every 1x1 convolution of the model with Cin % 4 == 0 is planned for the tcgen05 GEMM: 66 of the 70 convolutions
+    assert sum(l.startswith('conv1x1 ') for l in lines) == 66 and sum(l.startswith('conv ') for l in lines) == 4
     layers = NM.parse_param(REAL + '.param')
     used, total = NM.load_weights(layers, REAL + '.bin')
     assert used == total == 9693828

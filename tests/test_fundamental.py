@@ -31,9 +31,10 @@ def test_ransac_matches_cv2():
 
 
 def test_fewer_than_15_points_is_not_ransac():
+    """Below 15 pairs the oracle follows OpenCV's other branches (next test): LMedS runs its fixed 300 samples."""
     m1, m2 = G['r1_m1'][:14], G['r1_m2'][:14]
-    F, _, _ = O.find_fundamental_ransac(m1, m2)
-    assert F is None        # OpenCV switches to LMedS below 15 points: reported as "no F" unless small_sample=True (next test)
+    F, _, info = O.find_fundamental_ransac(m1, m2)
+    assert F is not None and info[0] == 300
 
 
 def test_select_static_pairs():
@@ -71,5 +72,10 @@ def test_small_sample_branch_is_lmeds(golden_dir):
                 l2 = x1 @ Fx.T; l1 = x2 @ Fx
                 d2 = (np.sum(l2 * x2, 1) ** 2) / (l2[:, 0] ** 2 + l2[:, 1] ** 2); d1 = (np.sum(l1 * x1, 1) ** 2) / (l1[:, 0] ** 2 + l1[:, 1] ** 2)
                 assert np.sort(np.maximum(d1, d2))[len(m1) // 2] < 1e-18
-    assert O.find_fundamental_ransac(g['l0_m1'][:7], g['l0_m2'][:7], 1.0, 0.99, small_sample=True)[0] is None        # == 7 pairs: the stacked 7-point solutions are not provided
+    # exactly 7 pairs: the 7-point solver itself; cv2 stacks its 1..3 solutions, the reference reads the first (rows 0..2)
+    for j in range(int(g['n_seven'])):
+        F, mask, info = O.find_fundamental_ransac(g[f's{j}_m1'], g[f's{j}_m2'])
+        Fg = g[f's{j}_F']
+        assert F is not None and len(Fg) in (3, 9) and np.abs(F - Fg[:3]).max() <= 1e-9 and mask.all()
+    assert O.find_fundamental_ransac(g['l0_m1'][:6], g['l0_m2'][:6])[0] is None                                      # fewer than 7: empty
 

@@ -69,7 +69,7 @@ def test_shim_on_gpu(tmp_path):
         mx = (d0 * rs.choice([0.5, 1.7, 3.1], nfr)).astype(np.float32); mn = (mx / 5).astype(np.float32)
         mn = (np.float32(0.8) * mn / np.float32(0.8)).astype(np.float32); mx = (np.float32(1.2) * mx / np.float32(1.2)).astype(np.float32)   # fixed points of the round trip
         cam9 = np.array([535.4, 539.2, 320.1, 247.6, 40.0, 0, 0, 640, 480], np.float32)
-        ref = O.is_in_frustum(T, cam9, 8, float(np.float32(np.log(np.float32(1.2)))), xyz, nrm, mn, mx, 0.5)
+        ref = O.is_in_frustum(T, cam9, 8, float(O.logf(1.2)), xyz, nrm, mn, mx, 0.5)
         np.array([nfr], np.int32).tofile(f); T.tofile(f); xyz.tofile(f); nrm.tofile(f); mn.tofile(f); mx.tofile(f)
         ref['inview'].tofile(f); ref['proj_x'].tofile(f); ref['proj_y'].tofile(f); ref['proj_xr'].tofile(f); ref['view_cos'].tofile(f); ref['level'].tofile(f)
         # 6. PoseOptimization

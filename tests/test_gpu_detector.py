@@ -58,7 +58,8 @@ def _check_rows(out, f, rows_ref, post_ref, max_boxes=32):
         k = out['n' + key][f]
         assert k == min(len(ref), max_boxes)
         assert np.abs(out[key][f, :k] - ref[:k]).max(initial=0) <= TOL * 1280
-    assert out['have'][f] == (1 if len(dyn_rm) else 0)
+    # the flag the Frame ends up with (src/Frame.cc:482-491): person boxes for rejection AND at least one non-person object (quirk Q12)
+    assert out['have'][f] == (1 if len(dyn_rm) and (objs[:, 0] != 15).any() else 0)
     assert out['status'][f] == (1 if max(len(dyn_map), len(dyn_rm)) > max_boxes else 0)
 
 
@@ -114,12 +115,6 @@ def test_detections_of_the_synthetic_graph(mini):
     rows_ref, post = DO.detect(layers, frames[0], 0.9, 0.01)
     assert len(post[1]) > 2
     _check_rows(small, 0, rows_ref, post, max_boxes=2)
-    # plain FP32 FMA GEMM (flags bit 2) against the default error-compensated TF32 tensor-core GEMM: same detections, values within FP32 noise
-    fma = B.Detector(pp, bp, max_frames=4, flags=B.DET_FMA_GEMM)
-    c = _run(fma, frames)
-    assert np.array_equal(c['nrows'], a['nrows']) and np.array_equal(c['rows'][..., 0], a['rows'][..., 0])
-    assert np.abs(c['rows'] - a['rows']).max() <= TOL
-    fma.close()
     # host entry point == device entry point
     objs = fused.detect(frames[0])
     assert objs.tobytes() == a['objects'][0, :a['nobjects'][0]].tobytes()

@@ -70,7 +70,7 @@ def test_frustum_batch_against_oracle():
         nn = tc / d0[:, None] + rs.normal(0, 0.5, (cap, 3)); nrm[f] = (nn / np.linalg.norm(nn, axis=1, keepdims=True)).astype(np.float32)
         mx[f] = (d0 * rs.uniform(0.5, 5, cap)).astype(np.float32); mn[f] = (mx[f] / 1.2 ** rs.randint(2, 9, cap)).astype(np.float32)
     out = _frustum_gpu(Tcw, cam9, xyz, nrm, mn, mx, counts, cap)
-    logsf = float(np.float32(np.log(np.float32(1.2))))
+    logsf = float(O.logf(1.2))
     for f in range(F):
         n = counts[f]
         ref = O.is_in_frustum(Tcw[f], cam9, 8, logsf, xyz[f, :n], nrm[f, :n], mn[f, :n], mx[f, :n], 0.5)
@@ -97,7 +97,7 @@ def test_predict_scale_at_ceil_boundaries():
     mx = (target.view(np.int32) + off).view(np.float32).reshape(1, cap)
     mn = (mx / np.float32(60.0)).astype(np.float32)
     out = _frustum_gpu(T, cam9, xyz, nrm, mn, mx, [cap], cap)
-    logsf = float(np.float32(np.log(np.float32(1.2))))
+    logsf = float(O.logf(1.2))
     ref = O.is_in_frustum(T[0], cam9, 8, logsf, xyz[0], nrm[0], mn[0], mx[0], 0.5)
     assert ref['inview'].sum() > cap // 2
     _same({k_: v[0] for k_, v in out.items()}, ref)

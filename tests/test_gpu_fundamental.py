@@ -58,11 +58,58 @@ def test_random_scenes_against_oracle():
             assert info[1] == io[1] and info[2] == io[0], (trial, info, io)      # inliers, iterations run
 
 
+def _sym_epipolar(F, m1, m2):
+    x1 = np.c_[m1.astype(np.float64), np.ones(len(m1))]; x2 = np.c_[m2.astype(np.float64), np.ones(len(m2))]
+    l2 = x1 @ F.T; l1 = x2 @ F
+    d2 = (np.sum(l2 * x2, 1) ** 2) / (l2[:, 0] ** 2 + l2[:, 1] ** 2); d1 = (np.sum(l1 * x1, 1) ** 2) / (l1[:, 0] ** 2 + l1[:, 1] ** 2)
+    return np.maximum(d1, d2)
+
+
+def test_small_sample_branches_golden(golden_dir):
+    """cv::findFundamentalMat(FM_RANSAC) below 15 pairs (src/Frame.cc:469-472 calls it unconditionally): 8..14 pairs -> LMedS, 7 -> the 7-point
+    solver itself (first of the stacked solutions), fewer -> empty.  cv2 golden vectors: 14 pairs (median = 8th smallest error, well defined) must
+    match exactly; with 8..13 pairs the median is one of the seven sample errors (~1e-27), the winner among equally perfect minimal models is
+    rounding noise in OpenCV itself, so only the defining properties are checked (300 samples, a model fitting >= 7 pairs, vanishing median)."""
+    g = np.load(os.path.join(golden_dir, 'fm_lmeds.npz'))
+    for i in range(int(g['n_cases'])):
+        m1, m2, Fg, maskg = g[f'l{i}_m1'], g[f'l{i}_m2'], g[f'l{i}_F'], g[f'l{i}_mask']
+        F, mask, info = B.fundamental_ransac(m1, m2)
+        assert F is not None and info[0] == len(m1) and info[2] == 300 and info[3] == 0, i
+        if len(m1) == 14:
+            assert _same(F, Fg) and np.array_equal(mask, maskg), i
+            assert info[1] == int(maskg.sum())
+        else:
+            assert mask.sum() >= 7 and np.sort(_sym_epipolar(F, m1, m2))[len(m1) // 2] < 1e-18, i
+    for j in range(int(g['n_seven'])):
+        F, mask, info = B.fundamental_ransac(g[f's{j}_m1'], g[f's{j}_m2'])
+        assert F is not None and _same(F, g[f's{j}_F'][:3]) and mask.all() and info[3] == 0, j
+
+
+def test_small_sample_random_against_oracle():
+    """14 pairs on random scenes: GPU == oracle (F, mask, inliers, 300 iterations); 8..13: same structural properties on both sides."""
+    rs = np.random.RandomState(123)
+    for trial in range(16):
+        n = 14 if trial < 8 else int(rs.randint(8, 14))
+        m1, m2 = _scene(rs, n, rs.choice([0.1, 0.5]), rs.choice([0.0, 0.2]))
+        Fo, mo, io = O.find_fundamental_ransac(m1, m2)
+        F, mask, info = B.fundamental_ransac(m1, m2)
+        assert (F is None) == (Fo is None), (trial, n)
+        if Fo is None:
+            continue
+        assert info[2] == io[0] == 300
+        if n == 14:
+            assert _same(F, Fo) and np.array_equal(mask, mo) and info[1] == io[1], (trial, np.abs(F - Fo).max())
+        else:
+            for Fx in (F, Fo):
+                assert np.sort(_sym_epipolar(Fx, m1, m2))[n // 2] < 1e-16, (trial, n)
+            assert mask.sum() >= 7 and mo.sum() >= 7
+
+
 def test_degenerate_inputs():
     rs = np.random.RandomState(3)
-    m1, m2 = _scene(rs, 14, 0.2, 0.0)
+    m1, m2 = _scene(rs, 6, 0.2, 0.0)
     F, mask, info = B.fundamental_ransac(m1, m2)
-    assert F is None and info[3] == 1                   # fewer than 15 pairs: not RANSAC in OpenCV, not provided here
+    assert F is None and info[3] == 1 and not mask.any()          # fewer than 7 pairs: OpenCV returns an empty matrix
     pts = np.tile(np.array([[100.0, 100.0]], np.float32), (40, 1))      # all points identical: every sample is collinear
     F, mask, info = B.fundamental_ransac(pts, pts)
     Fo, _, _ = O.find_fundamental_ransac(pts, pts)
@@ -107,3 +154,4 @@ def test_batch_device_with_previous_boxes():
         else:
             assert _same(F[f], Fo), f
             assert info[f, 1] == io[1] and info[f, 2] == io[0]
+    assert info[3, 0] == 14 and info[3, 2] == 300          # the 14-pair frame took the LMedS branch on the device as well

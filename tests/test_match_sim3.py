@@ -27,7 +27,7 @@ def transcription(s, Ow, nrm, matched, th):
     fo = O.FrameArrays(s['kps'], s['uright'], s['desc'], 640, 480, cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf'], s['sf'])
     T = s['Tcw_cur'].astype(f32); R = T[:3, :3]; t = T[:3, 3]
     fx, fy, cx, cy = [f32(cam[k]) for k in ('fx', 'fy', 'cx', 'cy')]
-    logsf = f32(np.log(f32(1.2)))
+    logsf = O.logf(1.2)
     m = matched.copy(); n = 0
     for i in range(len(s['last_xyz'])):
         if not s['kf_valid'][i]:
@@ -46,7 +46,7 @@ def transcription(s, Ow, nrm, matched, th):
             continue
         if (np.float64(PO[0]) * nrm[i, 0] + np.float64(PO[1]) * nrm[i, 1]) + np.float64(PO[2]) * nrm[i, 2] < 0.5 * np.float64(dist):
             continue
-        lvl = int(np.ceil(f32(np.log(f32(s['max_dist'][i] / dist))) / logsf))
+        lvl = int(np.ceil(f32(O.logf(f32(s['max_dist'][i] / dist)) / logsf)))
         lvl = min(max(lvl, 0), 7)
         cand = O.features_in_area(fo, float(u), float(v), float(f32(th) * sf[lvl]))
         best, bi = 256, -1

@@ -18,9 +18,12 @@ REAL = os.path.join(ROOT, 'oracle', '_ref', 'ncnn_model', 'mobilenetv3_ssdlite_v
 
 
 def main():
-    flags = int(os.environ.get('SGS_DET_FLAGS', '0'))
+    flags = 0
     argv = sys.argv[1:]
     W, H = 640, 480
+    once = False
+    if argv and argv[0] == '--once':       # one warm-up call + one call (for an ncu launch list)
+        once = True; argv = argv[1:]
     if argv and argv[0] == '--size':
         W, H = [int(x) for x in argv[1].split('x')]; argv = argv[2:]
     batches = [int(a) for a in argv] or [1, 8, 64, 256]
@@ -34,10 +37,10 @@ def main():
         d = torch.from_numpy(base[np.arange(F) % 8]).cuda()
         nd = torch.zeros(F, dtype=torch.int32, device='cuda'); boxes = torch.zeros((F, 4, 4), device='cuda'); have = torch.zeros(F, dtype=torch.uint8, device='cuda')
         run = lambda: det.detect_device(d.data_ptr(), H * W * 3, W * 3, W, H, F, d_dyn_rm=boxes.data_ptr(), d_ndyn_rm=nd.data_ptr(), d_have_dyn_rm=have.data_ptr(), max_boxes=4)
-        for _ in range(3):
+        for _ in range(1 if once else 3):
             run()
         torch.cuda.synchronize()
-        reps = max(3, min(50, 2000 // F))
+        reps = 1 if once else max(3, min(50, 2000 // F))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):

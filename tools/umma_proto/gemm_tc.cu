@@ -59,8 +59,8 @@ static int run_case(int npix, int Cin, int Cout, int out_pitch, int tail, bool t
     // padding columns must be untouched
     int touched = 0;
     if (out_pitch > Cout) for (int p = 0; p < npix; p += step) for (int c = Cout; c < out_pitch; ++c) { uint32_t b; memcpy(&b, &O[(size_t)p * out_pitch + c], 4); if (b != 0xffffffffu) ++touched; }
-    printf("case npix=%d Cin=%d Cout=%d pitch=%d tail=%d: NT=%d ntiles=%d KB=%d stages=%d smem=%d  max rel err %.3g (max |ref| %.3g) bad=%d touched_pad=%d\n", npix, Cin, Cout, out_pitch, tail,
-           plan.NT, plan.n_tiles, plan.KB, plan.stages, plan.smem_bytes, maxerr, maxref, bad, touched);
+    printf("case npix=%d Cin=%d Cout=%d pitch=%d tail=%d: NT=%d ntiles=%d KB=%d stages=%d bres=%d cps=%d smem=%d  max rel err %.3g (max |ref| %.3g) bad=%d touched_pad=%d\n", npix, Cin, Cout, out_pitch, tail,
+           plan.NT, plan.n_tiles, plan.KB, plan.stages, plan.b_resident, plan.ctas_per_sm, plan.smem_bytes, maxerr, maxref, bad, touched);
     if (timing) {
         cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         for (int i = 0; i < 3; ++i) launch_conv1x1_tc(plan, dX, in_pitch, npix, dB, dO, out_pitch, T, 0);
