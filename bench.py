@@ -211,6 +211,9 @@ def detector_cpu_rate(rgb_frames):
     NOT ncnn, which is not installable here.  frames/s over the sample."""
     import detector_oracle as DO
     import ncnn_model as NM
+    import oracle as O
+    import torch
+    torch.set_num_threads(O.online_cpus())                # the CPUs this process may really use (affinity mask capped by the cgroup quota)
     layers = NM.parse_param(MODEL + '.param'); NM.load_weights(layers, MODEL + '.bin')
     DO.detect(layers, rgb_frames[0])                      # warm-up
     t0 = time.perf_counter()

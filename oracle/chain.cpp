@@ -6,6 +6,8 @@
 // `cpu_baseline`) and the pure-oracle side of the full-chain parity check.  TEST / BENCH INFRASTRUCTURE, never linked into the product.
 #include <atomic>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -148,8 +150,20 @@ SGO_API int sgo_chain_batch(const SgoChainArgs* a, int first, int count, int nth
     return nthreads;
 }
 
+// CPUs this process may really use: the affinity mask, capped by the cgroup CPU quota when there is one (cpu.max "quota period": containers on
+// shared hosts often see every core of the machine but are throttled to a few cores' worth of time; running more busy threads than that only
+// adds throttling stalls).
 SGO_API int sgo_online_cpus(void) {
     cpu_set_t mask;
-    if (sched_getaffinity(0, sizeof(mask), &mask) != 0) return (int)std::thread::hardware_concurrency();
-    return CPU_COUNT(&mask);
+    int n = sched_getaffinity(0, sizeof(mask), &mask) == 0 ? CPU_COUNT(&mask) : (int)std::thread::hardware_concurrency();
+    if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[64] = {0}; long period = 0;
+        if (std::fscanf(f, "%63s %ld", q, &period) == 2 && q[0] != 'm' && period > 0) {
+            const long quota = std::atol(q);
+            const int cap = (int)((quota + period - 1) / period);
+            if (cap >= 1 && cap < n) n = cap;
+        }
+        std::fclose(f);
+    }
+    return n > 0 ? n : 1;
 }

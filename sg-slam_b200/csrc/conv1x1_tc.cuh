@@ -91,6 +91,7 @@ struct TcGeom {
     int64_t base_off;             // float offset of frame 0 of the output inside `out`
     int pitch;                    // floats between consecutive pixels of the output
     int vec_ok;                   // 16-byte aligned rows: float4 stores
+    int coalesce;                 // contiguous [pixel][channel] output: full 32-channel chunks are transposed through shared memory and stored row by row
 };
 
 // warp 0: TMA producer, warp 1: MMA issuer (+ TMEM owner), warps 2 .. 2+EPW-1: epilogue (EPW = 4 or 8), the last four warps: operand split
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_
     const uint32_t sbase = (smem_addr(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - smem_addr(smem_raw));
     const uint32_t bres = sbase + (uint32_t)G.stages * stage_bytes;          // resident weights: [kb][hi | lo]
+    const uint32_t epi_off = (uint32_t)G.stages * stage_bytes + (G.b_resident ? (uint32_t)G.KB * 2 * b_bytes : 0u);      // per epilogue warp: 32 rows x 128 B
     const int my_tiles = (G.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
@@ -250,6 +252,32 @@ __global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_
                     for (int q = 0; q < 4; ++q)
                         bq[h][q] = (bias && (h == 0 ? full0 : full1)) ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + 16 * h) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                 tmem_ld_wait();
+                if (EPW == 8 && G.coalesce && full0 && full1) {
+                    // whole 32-channel chunk: bias + tail in registers (one pixel per lane), transpose through this warp's 4 KB of shared memory
+                    // (16-byte pieces XOR-swizzled by the row: conflict-free both ways), then every store instruction writes 4 rows x 128 contiguous bytes
+                    float4* stg = reinterpret_cast<float4*>(gbase + epi_off + (size_t)(warp - 2) * 4096);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            stg[lane * 8 + ((4 * h + q) ^ (lane & 7))] = make_float4(__fadd_rn(__uint_as_float(r[h][4 * q]), bq[h][q].x), __fadd_rn(__uint_as_float(r[h][4 * q + 1]), bq[h][q].y),
+                                                                                     __fadd_rn(__uint_as_float(r[h][4 * q + 2]), bq[h][q].z), __fadd_rn(__uint_as_float(r[h][4 * q + 3]), bq[h][q].w));
+                    __syncwarp();
+                    // the tail runs on the row-major side: its tensor operands are read as coalesced float4 rows, like the stores
+                    const int p0 = ((int)blockIdx.x + it * (int)gridDim.x) * kBM + quad * 32;
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const int row = i4 * 4 + (lane >> 3), c = lane & 7;
+                        if (p0 + row < G.npix) {
+                            const float4 x = stg[row * 8 + (c ^ (row & 7))];
+                            float v[4] = {x.x, x.y, x.z, x.w};
+                            epi.template run<4>(v, (int64_t)(p0 + row) * G.Cout + n0 + c0 + 4 * c);
+                            *reinterpret_cast<float4*>(out + G.base_off + (int64_t)(p0 + row) * G.pitch + n0 + c0 + 4 * c) = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 if (!live) continue;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -340,7 +368,7 @@ inline void split_tf32_host(float x, float& hi, float& lo) {
 
 // Tiling of one layer (no device access): output-channel tiles of at most kMaxNT, weights resident when all their k-blocks fit in 96 KB,
 // ring depth from what is left of the shared memory; small weight tiles leave room for two CTAs per SM (more loads in flight, two MMA issuers).
-inline void plan_tiling(int Cin, int Cout, GemmPlan* P) {
+inline void plan_tiling(int Cin, int Cout, GemmPlan* P, bool tensor_tail = false) {
     P->Cin = Cin; P->Cout = Cout;
     const int nt = (Cout + kMaxNT - 1) / kMaxNT;
     P->NT = ((Cout + nt - 1) / nt + 15) & ~15;
@@ -351,23 +379,25 @@ inline void plan_tiling(int Cin, int Cout, GemmPlan* P) {
     const int a_stage = 2 * kBM * P->BK * 4, b_block = 2 * P->NT * P->BK * 4;
     const int b_all = P->KB * b_block;
     P->b_resident = b_all <= 96 * 1024 ? 1 : 0;
-    P->ctas_per_sm = (P->b_resident && b_all + 2 * a_stage + 1024 <= 110 * 1024) ? 2 : 1;      // resident weights + two ring slots fit twice: two CTAs per SM
+    // resident weights + two ring slots fit twice: two CTAs per SM -- unless the tail reads other tensors, which only the eight-warp epilogue fetches row-wise
+    P->ctas_per_sm = (!tensor_tail && P->b_resident && b_all + 2 * a_stage + 1024 <= 110 * 1024) ? 2 : 1;
     P->epw = P->ctas_per_sm == 2 ? 4 : 8;                                // one CTA per SM: eight epilogue warps keep up with wide output tiles
-    const int budget = (P->ctas_per_sm == 2 ? 110 : 220) * 1024 - 1024 - (P->b_resident ? b_all : 0);
+    const int epi_stage = P->epw == 8 ? 8 * 4096 : 0;                    // the eight epilogue warps' transpose buffers (the two-CTA variant stores directly)
+    const int budget = (P->ctas_per_sm == 2 ? 110 : 220) * 1024 - 1024 - epi_stage - (P->b_resident ? b_all : 0);
     const int stage_bytes = a_stage + (P->b_resident ? 0 : b_block);
     int st = budget / stage_bytes;
     if (st > kMaxStages) st = kMaxStages;
     if (st < 2) st = 2;
     P->stages = st;
-    P->smem_bytes = st * stage_bytes + (P->b_resident ? b_all : 0) + 1024;
+    P->smem_bytes = st * stage_bytes + (P->b_resident ? b_all : 0) + epi_stage + 1024;
     uint32_t tc = 32;
     while ((int)tc < 2 * P->NT) tc <<= 1;
     P->tmem_cols = tc;
 }
 
 // Splits and uploads W [Cout][Cin], picks the tiling.  Returns false when TMA is unavailable or an allocation fails.
-inline bool plan_weights(const float* W, int Cin, int Cout, GemmPlan* P) {
-    plan_tiling(Cin, Cout, P);
+inline bool plan_weights(const float* W, int Cin, int Cout, GemmPlan* P, bool tensor_tail = false) {
+    plan_tiling(Cin, Cout, P, tensor_tail);
     std::vector<float> hi((size_t)P->Np * P->Kp, 0.f), lo((size_t)P->Np * P->Kp, 0.f);
     for (int co = 0; co < Cout; ++co)
         for (int c = 0; c < Cin; ++c) split_tf32_host(W[(size_t)co * Cin + c], hi[(size_t)co * P->Kp + c], lo[(size_t)co * P->Kp + c]);
@@ -442,6 +472,7 @@ inline bool launch_conv1x1_tc_map(const GemmPlan& P, const CUtensorMap& mapA, in
     G.m_tiles = (npix + kBM - 1) / kBM; G.b_resident = P.b_resident;
     G.HW = HW; G.frame_stride = frame_stride; G.base_off = base_off; G.pitch = pitch;
     G.vec_ok = ((pitch & 3) == 0 && (frame_stride & 3) == 0 && (base_off & 3) == 0 && (((uintptr_t)out) & 15) == 0) ? 1 : 0;
+    G.coalesce = (G.vec_ok && (frame_stride == 0 || frame_stride == (int64_t)HW * pitch)) ? 1 : 0;
     int gx = (sm_count() * P.ctas_per_sm) / P.n_tiles;                  // one wave of persistent CTAs
     if (gx < 1) gx = 1;
     if (gx > G.m_tiles) gx = G.m_tiles;

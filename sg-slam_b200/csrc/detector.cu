@@ -92,6 +92,29 @@ __device__ __forceinline__ void epi_dispatch(int kind, F&& body) {
     }
 }
 
+// Four consecutive channels of one pixel (idx % 4 == 0, 16-byte aligned operand tensors): the tensor operands of the recognised tails are fetched
+// as one float4 each instead of four scalar loads (the element order and roundings are those of apply_epi).
+template <int KIND>
+__device__ __forceinline__ void apply_epi4(const Epi& e, float (&v)[4], int64_t idx) {
+    if constexpr (KIND == EK_ADD_T) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(e.s[0].t + idx));
+        v[0] = __fadd_rn(v[0], t.x); v[1] = __fadd_rn(v[1], t.y); v[2] = __fadd_rn(v[2], t.z); v[3] = __fadd_rn(v[3], t.w);
+    } else if constexpr (KIND == EK_SE_TAIL || KIND == EK_SE_MUL) {
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(e.s[3].t + idx));
+        float4 t2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (KIND == EK_SE_TAIL) t2 = __ldg(reinterpret_cast<const float4*>(e.s[4].t + idx));
+        const float a[4] = {t1.x, t1.y, t1.z, t1.w}, b[4] = {t2.x, t2.y, t2.z, t2.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float g = __fmul_rn(a[q], div_scalar(fminf(fmaxf(__fadd_rn(v[q], e.s[0].a), e.s[1].a), e.s[1].b), e.s[2].a));
+            v[q] = KIND == EK_SE_TAIL ? __fadd_rn(g, b[q]) : g;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = apply_epi<KIND>(e, v[q], idx + q);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------- kernels
 // Mat::from_pixels_resize(..., PIXEL_RGB, w, h, 300, 300) + substract_mean_normalize (norm = 1).  11-bit fixed-point bilinear, the arithmetic
 // of cv::resize INTER_LINEAR on 8-bit data: horizontal pass keeps value*2048, vertical pass ((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.
@@ -136,10 +159,23 @@ struct EpiFn {
     template <int N>
     __device__ __forceinline__ void run(float (&v)[N], int64_t idx0) const {
         epi_dispatch(e.kind, [&](auto kind) {
+            constexpr int EK = decltype(kind)::value;
+            if constexpr (N % 4 == 0) {
+                if ((idx0 & 3) == 0) {
 #pragma unroll
-            for (int q = 0; q < N; ++q) v[q] = apply_epi<decltype(kind)::value>(e, v[q], idx0 + q);
+                    for (int q = 0; q < N; q += 4) {
+                        float w[4] = {v[q], v[q + 1], v[q + 2], v[q + 3]};
+                        apply_epi4<EK>(e, w, idx0 + q);
+                        v[q] = w[0]; v[q + 1] = w[1]; v[q + 2] = w[2]; v[q + 3] = w[3];
+                    }
+                    return;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[q] = apply_epi<EK>(e, v[q], idx0 + q);
         });
     }
+    __host__ __device__ bool reads_tensors() const { return e.kind == EK_ADD_T || e.kind == EK_SE_TAIL || e.kind == EK_SE_MUL || e.kind == EK_GENERIC; }
 };
 
 // depth-wise K x K, stride S on [frame][h][w][c]: V channels (float4 when C % 4 == 0) x XT consecutive outputs of one row per thread; the
@@ -201,11 +237,11 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ i
         for (int o = 0; o < XT; ++o) {
             if (ox0 + o >= g.OW) break;
             const int64_t oi = o0 + (int64_t)o * g.Cout;
-            float r[V];
-#pragma unroll
-            for (int q = 0; q < V; ++q) r[q] = apply_epi<EK>(epi, __fadd_rn(acc[o][q], b[q]), oi + q);
-            if constexpr (V == 4) *reinterpret_cast<float4*>(out + oi) = make_float4(r[0], r[1], r[2], r[3]);
-            else out[oi] = r[0];
+            if constexpr (V == 4) {
+                float r[4] = {__fadd_rn(acc[o][0], b[0]), __fadd_rn(acc[o][1], b[1]), __fadd_rn(acc[o][2], b[2]), __fadd_rn(acc[o][3], b[3])};
+                apply_epi4<EK>(epi, r, oi);
+                *reinterpret_cast<float4*>(out + oi) = make_float4(r[0], r[1], r[2], r[3]);
+            } else out[oi] = apply_epi<EK>(epi, __fadd_rn(acc[o][0], b[0]), oi);
         }
     });
 }
@@ -253,15 +289,21 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const float* __restrict
     epi_dispatch(epi.kind, [&](auto kind) {
         constexpr int EK = decltype(kind)::value;
         float r[kCot];
-#pragma unroll
-        for (int o = 0; o < kCot; ++o) {
-            const int co = co0 + o;
-            r[o] = co < g.Cout ? apply_epi<EK>(epi, __fadd_rn(acc[o], bias ? __ldg(bias + co) : 0.f), idx0 + co) : 0.f;
-        }
         if (vec) {
 #pragma unroll
-            for (int o = 0; o < kCot; o += 4) *reinterpret_cast<float4*>(orow + co0 + o) = make_float4(r[o], r[o + 1], r[o + 2], r[o + 3]);
+            for (int o = 0; o < kCot; o += 4) {
+                float w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) w[q] = __fadd_rn(acc[o + q], bias ? __ldg(bias + co0 + o + q) : 0.f);
+                apply_epi4<EK>(epi, w, idx0 + co0 + o);
+                *reinterpret_cast<float4*>(orow + co0 + o) = make_float4(w[0], w[1], w[2], w[3]);
+            }
         } else {
+#pragma unroll
+            for (int o = 0; o < kCot; ++o) {
+                const int co = co0 + o;
+                r[o] = co < g.Cout ? apply_epi<EK>(epi, __fadd_rn(acc[o], bias ? __ldg(bias + co) : 0.f), idx0 + co) : 0.f;
+            }
 #pragma unroll
             for (int o = 0; o < kCot; ++o) if (co0 + o < g.Cout) orow[co0 + o] = r[o];
         }
@@ -852,9 +894,13 @@ int build_graph(sgs_detector* D) {
             if (L.type == "ConvolutionDepthWise") op.kind = OP_DWCONV;
             else op.kind = (op.g.k == 1 && op.g.stride == 1 && op.g.pad == 0 && s.c % 4 == 0) ? OP_CONV1X1 : OP_CONV_DIRECT;
             int rc = SGS_OK;
+            int fin = lout[i][0];
+            if (!diag) build_tail((int)i, lout[i][0], op.epi, fin);
             if (op.kind == OP_CONV1X1) {
-                if (D->flags & 2) tc::plan_tiling(op.g.Cin, op.g.Cout, &op.gp);
-                else if (!tc::plan_weights(L.weight.data(), op.g.Cin, op.g.Cout, &op.gp)) { set_error("sgs_detector_create: layer %s: the tcgen05 GEMM could not be set up (TMA tensor maps need a CUDA 12 driver; %s)", L.name.c_str(), cudaGetErrorString(cudaGetLastError())); return SGS_ERR_CUDA; }
+                bool tensor_tail = false;
+                for (auto& st : op.epi) tensor_tail = tensor_tail || st.src == SRC_TENSOR;
+                if (D->flags & 2) tc::plan_tiling(op.g.Cin, op.g.Cout, &op.gp, tensor_tail);
+                else if (!tc::plan_weights(L.weight.data(), op.g.Cin, op.g.Cout, &op.gp, tensor_tail)) { set_error("sgs_detector_create: layer %s: the tcgen05 GEMM could not be set up (TMA tensor maps need a CUDA 12 driver; %s)", L.name.c_str(), cudaGetErrorString(cudaGetLastError())); return SGS_ERR_CUDA; }
             } else if (op.kind == OP_DWCONV) {                    // [c][ky][kx] -> [ky][kx][c]: channel vectors
                 std::vector<float> wt(L.weight.size());
                 const int kk = op.g.k * op.g.k;
@@ -863,8 +909,6 @@ int build_graph(sgs_detector* D) {
             } else rc = upload(D, L.weight, &op.d_w);
             if (rc) return rc;
             rc = upload(D, L.bias, &op.d_b); if (rc) return rc;
-            int fin = lout[i][0];
-            if (!diag) build_tail((int)i, lout[i][0], op.epi, fin);
             op.out = fin;
             D->ops.push_back(op);
         } else if (is_eltwise(L)) {

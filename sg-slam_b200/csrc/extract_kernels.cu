@@ -2,7 +2,7 @@
 //
 // Stage            reference (src/ORBextractor.cc)                kernel
 //   pyramid        ComputePyramid :1108-1133 (cv::resize)          resize_level_kernel   (1 launch per level >= 1, all frames)
-//   FAST + NMS     ComputeKeyPointsOctTree :766-830 (cv::FAST)     fast_cells_kernel     (1 launch: all levels, all frames)
+//   FAST + NMS     ComputeKeyPointsOctTree :766-830 (cv::FAST)     fast_warp_cells_kernel (fast_kernel.cu; 1 launch: all levels, all frames)
 //   distribution   DistributeOctTree :540-764                      quadtree_kernel       (1 launch: block per (level, frame))
 //   blur           GaussianBlur :1086-1087                         blur_tile_kernel      (blur_kernel.cu, 1 launch per level)
 //   orient + BRIEF IC_Angle :78-105, computeOrbDescriptor :109-148 describe_kernel       (1 launch: warp per keypoint)
@@ -61,205 +61,6 @@ void launch_resize(const DevPlan& P, int level, cudaStream_t st) {
     const DevLevel& d = P.lv[level];
     dim3 block(32, 8), grid((d.w + 127) / 128, (d.h + 7) / 8, P.nframes);
     resize_level_kernel<<<grid, block, 0, st>>>(s.img, s.w, s.h, s.pitch, s.fstride, d.img_w, d.w, d.h, d.pitch, d.fstride, d.xtab, d.ytab);
-}
-
-// --------------------------------------------------------------------------------------------------------------------
-// FAST-9-16 + cell-local 3x3 NMS + per-cell threshold fallback.  One block per (cell, frame); a cell is one cv::FAST call
-// of the reference.  Facts used (proved against cv2 in tests/test_oracle_golden.py):
-//   * score(p) = max over the 16 contiguous 9-arcs of max(min d, -max d) - 1 with d_k = I(p) - I(ring_k);  p is a corner
-//     at threshold t  <=>  score(p) >= t; the reported response is that score whatever t was;
-//   * NMS keeps p iff score(p) > score(q) for its 8 neighbours q, pixels outside the cell interior counting as 0 -- the
-//     predicate is the same for both thresholds because neighbours below the threshold are below score(p) anyway;
-//   * the cell uses iniTh when that leaves at least one keypoint, otherwise minTh (:813-817).
-// Phases: (A) 4-point compass reject -> survivor list, (B) full 16-bit segment test -> corner list, (C) exact score,
-// (D) NMS + threshold choice + emission of packed candidates through one global atomic per cell.
-// --------------------------------------------------------------------------------------------------------------------
-constexpr int kFastThreads = 256;
-constexpr int kTileMax = 66;     // w_cell <= 60 (n_cols = floor(width/30)) plus the 6-px overlap
-constexpr int kTilePitch = 72;
-
-// Exact FAST score from the 16 ring values: max over the 16 contiguous 9-arcs of max(min d, -max d) - 1, d_k = v - r_k.
-// Both halves are evaluated at once as packed signed 16-bit lanes (lo = d, hi = -d; |d| <= 255) with a sliding
-// min: windows of 2, 4, 8 then 9 ring positions (VIMNMX.S16x2).
-// NOTE (toolchain finding): with CUDA 12.9 ptxas -O3 for sm_100a the straightforward 32-bit formulation
-// `max(best, max(mn9, -mx9))` is MISCOMPILED (the negation is folded into a 3-input VIMNMX3 incorrectly; -Xptxas -O0
-// gives the right answer).  tools/ptxas_minmax_repro.cu reproduces it.  This formulation never negates a max result.
-__device__ __forceinline__ int fast_score_from_ring(int v, const int (&r)[16]) {
-    unsigned p[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int d = v - r[k];
-        p[k] = ((unsigned)d & 0xFFFFu) | ((unsigned)(-d) << 16);
-    }
-    unsigned w2[16], w4[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) w2[k] = __vmins2(p[k], p[(k + 1) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) w4[k] = __vmins2(w2[k], w2[(k + 2) & 15]);
-    unsigned best = 0x80008000u;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) best = __vmaxs2(best, __vmins2(__vmins2(w4[k], w4[(k + 4) & 15]), p[(k + 8) & 15]));
-    const int lo = (int)(short)(best & 0xFFFFu), hi = (int)(short)(best >> 16);
-    return (lo > hi ? lo : hi) - 1;
-}
-
-__device__ __forceinline__ bool has_arc9(uint32_t m) {
-    m |= m << 16;
-    uint32_t r = m & (m >> 1);
-    r &= r >> 2;   // runs of 4
-    r &= r >> 4;   // runs of 8
-    r &= m >> 8;   // runs of 9
-    return (r & 0xFFFFu) != 0;
-}
-
-__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ DevPlan P, const FastCell* __restrict__ cells) {
-    __shared__ __align__(16) uint8_t tile[kTileMax * kTilePitch];
-    __shared__ __align__(16) uint8_t score[(kTileMax + 2) * kTilePitch];  // +1 row above/below; columns x-1/x+1 stay inside the pitch
-    __shared__ uint16_t list_a[kTileMax * kTileMax];
-    __shared__ uint16_t list_b[kTileMax * kTileMax];
-    __shared__ int s_na, s_nb, s_nk, s_any_ini, s_base;
-
-    const FastCell c = cells[blockIdx.x];
-    const DevLevel& L = P.lv[c.level];
-    const int f = blockIdx.y;
-    const int w = c.x1 - c.x0, h = c.y1 - c.y0;
-    const uint8_t* img = L.img + (int64_t)f * L.fstride + (int64_t)c.y0 * L.pitch + c.x0;
-    const int tid = threadIdx.x;
-    if (tid == 0) { s_na = 0; s_nb = 0; s_nk = 0; s_any_ini = 0; }
-    for (int i = tid; i < (kTileMax + 2) * kTilePitch / 4; i += kFastThreads) reinterpret_cast<uint32_t*>(score)[i] = 0u;
-    for (int i = tid; i < w * h; i += kFastThreads) {
-        const int y = i / w, x = i - y * w;
-        tile[y * kTilePitch + x] = __ldg(img + (int64_t)y * L.pitch + x);
-    }
-    __syncthreads();
-    const int t_lo = min(P.ini_th, P.min_th);
-    const int iw = w - 6, ih = h - 6;
-    // (A) compass test: any 9-arc contains at least 2 of the ring pixels 0,4,8,12
-    for (int i0 = 0; i0 < iw * ih; i0 += kFastThreads) {
-        const int i = i0 + tid;
-        bool surv = false;
-        int pos = 0;
-        if (i < iw * ih) {
-            const int y = i / iw + 3, x = i - (i / iw) * iw + 3;
-            pos = y * kTilePitch + x;
-            const int v = tile[pos];
-            const int p0 = tile[pos + 3 * kTilePitch], p4 = tile[pos + 3], p8 = tile[pos - 3 * kTilePitch], p12 = tile[pos - 3];
-            const int hi = v + t_lo, lo = v - t_lo;
-            const int nb = (p0 > hi) + (p4 > hi) + (p8 > hi) + (p12 > hi);
-            const int nd = (p0 < lo) + (p4 < lo) + (p8 < lo) + (p12 < lo);
-            surv = (nb >= 2) | (nd >= 2);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, surv);
-        if (m) {
-            const int lane = tid & 31;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_na, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (surv) list_a[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;
-        }
-    }
-    __syncthreads();
-    // (B) full segment test at the lower threshold
-    const int na = s_na;
-    for (int i0 = 0; i0 < na; i0 += kFastThreads) {
-        const int i = i0 + tid;
-        bool corner = false;
-        int pos = 0;
-        if (i < na) {
-            pos = list_a[i];
-            const uint8_t* p = tile + pos;
-            const int v = p[0];
-            const int hi = v + t_lo, lo = v - t_lo;
-            uint32_t mb = 0, md = 0;
-#define SGS_RING(k, dx, dy) { const int r = p[(dy) * kTilePitch + (dx)]; mb |= (uint32_t)(r > hi) << (k); md |= (uint32_t)(r < lo) << (k); }
-            SGS_RING(0, 0, 3) SGS_RING(1, 1, 3) SGS_RING(2, 2, 2) SGS_RING(3, 3, 1) SGS_RING(4, 3, 0) SGS_RING(5, 3, -1) SGS_RING(6, 2, -2) SGS_RING(7, 1, -3)
-            SGS_RING(8, 0, -3) SGS_RING(9, -1, -3) SGS_RING(10, -2, -2) SGS_RING(11, -3, -1) SGS_RING(12, -3, 0) SGS_RING(13, -3, 1) SGS_RING(14, -2, 2) SGS_RING(15, -1, 3)
-#undef SGS_RING
-            corner = has_arc9(mb) || has_arc9(md);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, corner);
-        if (m) {
-            const int lane = tid & 31;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_nb, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (corner) list_b[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;
-        }
-    }
-    __syncthreads();
-    // (C) exact score of every corner
-    const int nb = s_nb;
-    for (int i = tid; i < nb; i += kFastThreads) {
-        const int pos = list_b[i];
-        const uint8_t* p = tile + pos;
-        int r[16];
-        r[0] = p[3 * kTilePitch]; r[1] = p[3 * kTilePitch + 1]; r[2] = p[2 * kTilePitch + 2]; r[3] = p[kTilePitch + 3];
-        r[4] = p[3]; r[5] = p[-kTilePitch + 3]; r[6] = p[-2 * kTilePitch + 2]; r[7] = p[-3 * kTilePitch + 1];
-        r[8] = p[-3 * kTilePitch]; r[9] = p[-3 * kTilePitch - 1]; r[10] = p[-2 * kTilePitch - 2]; r[11] = p[-kTilePitch - 3];
-        r[12] = p[-3]; r[13] = p[kTilePitch - 3]; r[14] = p[2 * kTilePitch - 2]; r[15] = p[3 * kTilePitch - 1];
-        score[pos + kTilePitch] = (uint8_t)fast_score_from_ring(p[0], r);  // score map is shifted one row down
-    }
-    __syncthreads();
-    // (D) NMS (cell-local: the score map is zero outside the interior) and threshold choice
-    bool keep = false;  // valid for at most ceil(nb / threads) == handled in a loop below
-    for (int i0 = 0; i0 < nb; i0 += kFastThreads) {
-        const int i = i0 + tid;
-        keep = false;
-        int pos = 0, s = 0;
-        if (i < nb) {
-            pos = list_b[i];
-            const uint8_t* q = score + pos + kTilePitch;
-            s = q[0];
-            keep = s > q[-1] && s > q[1] && s > q[-kTilePitch - 1] && s > q[-kTilePitch] && s > q[-kTilePitch + 1] &&
-                   s > q[kTilePitch - 1] && s > q[kTilePitch] && s > q[kTilePitch + 1];
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
-            const int lane = tid & 31;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_nk, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) {
-                list_a[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;  // list_a is free again: reuse for kept
-                if (s >= P.ini_th) s_any_ini = 1;
-            }
-        }
-    }
-    __syncthreads();
-    const int nk = s_nk;
-    const int thr = s_any_ini ? P.ini_th : P.min_th;
-    // count the emitted ones, reserve, write
-    int cnt = 0;
-    for (int i = tid; i < nk; i += kFastThreads) cnt += (score[list_a[i] + kTilePitch] >= thr) ? 1 : 0;
-    // block-wide sum via shared atomics (tiny)
-    if (tid == 0) s_na = 0;
-    __syncthreads();
-    if (cnt) atomicAdd(&s_na, cnt);
-    __syncthreads();
-    const int total = s_na;
-    if (total == 0) return;
-    if (tid == 0) {
-        s_base = atomicAdd(&P.cand_count[f * P.nlevels + c.level], total);
-        s_nb = 0;
-    }
-    __syncthreads();
-    const int base = s_base;
-    if (base + total > L.cand_cap) { if (tid == 0) atomicExch(P.error_flag, 1); return; }
-    uint32_t* out = L.cand + (int64_t)f * P.cand_fstride;
-    for (int i = tid; i < nk; i += kFastThreads) {
-        const int pos = list_a[i];
-        const int s = score[pos + kTilePitch];
-        if (s >= thr) {
-            const int y = pos / kTilePitch, x = pos - y * kTilePitch;
-            const int slot = atomicAdd(&s_nb, 1);
-            out[base + slot] = qt_pack(c.x0 + x - kMinBorder, c.y0 + y - kMinBorder, s);
-        }
-    }
-}
-
-void launch_fast(const DevPlan& P, const FastCell* d_cells, int ncells, cudaStream_t st) {
-    dim3 grid(ncells, P.nframes);
-    fast_cells_kernel<<<grid, kFastThreads, 0, st>>>(P, d_cells);
 }
 
 // --------------------------------------------------------------------------------------------------------------------

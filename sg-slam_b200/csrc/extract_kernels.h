@@ -9,7 +9,6 @@ namespace sgs {
 void launch_resize(const DevPlan& P, int level, cudaStream_t st);        // direct kernel (any scale factor)
 bool resize_tile_supported(const DevPlan& P, int level);
 void launch_resize_tile(const DevPlan& P, int level, cudaStream_t st);   // shared-memory tiled kernel (pyramid_kernel.cu)
-void launch_fast(const DevPlan& P, const FastCell* d_cells, int ncells, cudaStream_t st);   // block-per-cell reference kernel (kept for A/B)
 
 // warp-per-cell FAST with TMA-staged tiles (fast_kernel.cu)
 struct FastTmaMaps { CUtensorMap m[kMaxLevels]; };

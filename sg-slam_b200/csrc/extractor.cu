@@ -45,7 +45,6 @@ struct sgs_extractor {
     FastTmaMaps fast_maps{};
     bool maps_ok = false;            // levels >= 1 (own buffers) encoded
     const void* map0_ptr = nullptr; int map0_pitch = 0; int64_t map0_fstride = 0; int map0_frames = 0; bool map0_ok = false;
-    int fast_variant = 2;            // 2: warp-per-cell + TMA, 1: warp-per-cell plain loads, 0: block-per-cell reference kernel
     // pinned staging for the host API
     uint8_t* h_in = nullptr; size_t h_in_bytes = 0;
     sgs_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_count = nullptr; int32_t* h_error = nullptr;
@@ -120,10 +119,8 @@ int enqueue(sgs_extractor* ex, const uint8_t* d_l0, int pitch, int64_t fstride, 
         if (resize_tile_supported(P, l)) launch_resize_tile(P, l, st); else launch_resize(P, l, st);
     }
     if (prof) cudaEventRecord(ex->ev[1], st);
-    if (ex->fast_variant == 0) {
-        launch_fast(P, ex->d_cells, (int)ex->plan.cells.size(), st);
-    } else {
-        bool tma = ex->fast_variant == 2 && ex->maps_ok;
+    {   // tiles by TMA when every level could be described by a tensor map (16-byte aligned base / pitch); the same kernel with plain loads otherwise
+        bool tma = ex->maps_ok;
         if (tma && !(ex->map0_ok && ex->map0_ptr == d_l0 && ex->map0_pitch == pitch && ex->map0_fstride == fstride && ex->map0_frames >= map_frames)) {
             ex->map0_ok = encode_level_map(&ex->fast_maps.m[0], d_l0, P.lv[0].w, P.lv[0].h, pitch, fstride, map_frames, ex->fast_plan.tp, ex->fast_plan.th);
             ex->map0_ptr = d_l0; ex->map0_pitch = pitch; ex->map0_fstride = fstride; ex->map0_frames = map_frames;
@@ -265,9 +262,8 @@ SGS_API int sgs_extractor_create(const sgs_orb_params* params, int width, int he
     }
     // warp-per-cell FAST: tile geometry, shared-memory opt-in, TMA tensor maps of the own pyramid levels
     ex->fast_plan = make_fast_launch_plan(PL);
-    if (ex->fast_plan.smem_bytes > 200 * 1024) ex->fast_variant = 0;
-    else TRY_OR_FREE(configure_fast_smem(ex->fast_plan.smem_bytes));
-    if (const char* v = getenv("SGS_FAST_VARIANT")) ex->fast_variant = atoi(v);
+    if (ex->fast_plan.smem_bytes > 200 * 1024) { set_error("sgs_extractor_create: FAST cells of this geometry need %d bytes of shared memory per block", ex->fast_plan.smem_bytes); free_all(ex); return SGS_ERR_UNSUPPORTED; }
+    TRY_OR_FREE(configure_fast_smem(ex->fast_plan.smem_bytes));
     ex->maps_ok = true;
     for (int l = 1; l < L && ex->maps_ok; ++l)
         ex->maps_ok = encode_level_map(&ex->fast_maps.m[l], D.lv[l].img, D.lv[l].w, D.lv[l].h, D.lv[l].pitch, D.lv[l].fstride, max_batch, ex->fast_plan.tp, ex->fast_plan.th);

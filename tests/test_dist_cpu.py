@@ -17,7 +17,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     import bench
     from pysgs import synth
-    frames, boxes, unique = bench.make_frames(6, seed=2 + rank, unique=3)
+    frames, boxes, unique = bench.make_frames(6, 2 + rank, 640, 480, unique=3)
     table = torch.from_numpy(synth.descriptors_s5(4096, 5)) if rank == 0 else torch.zeros(4096, 32, dtype=torch.uint8)
     dist.broadcast(table, 0)
     t = torch.tensor([1.0 + rank], dtype=torch.float64)
@@ -41,7 +41,7 @@ def test_two_rank_gloo_sharding_and_broadcast():
     # determinism: the same rank seed gives the same shard
     sys.path[:0] = [ROOT, os.path.join(ROOT, 'sg-slam_b200'), os.path.join(ROOT, 'tests')]
     import bench
-    f0, _, _ = bench.make_frames(6, seed=2, unique=3)
+    f0, _, _ = bench.make_frames(6, 2, 640, 480, unique=3)
     assert int(f0.astype(np.uint64).sum()) == s0[0]
 
 

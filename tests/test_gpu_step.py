@@ -17,9 +17,9 @@ from pysgs import synth  # noqa: E402
 W, H, NF, TH = 640, 480, 1000, 15.0
 
 
-def _inputs(frames, boxes_gt, kps, desc, counts, cap, pidx):
+def _inputs(frames, boxes_gt, kps, desc, counts, cap, pcap, pidx):
     import bench
-    return bench.make_track_inputs(kps, desc, counts, boxes_gt, cap, cap, pidx, W, H, dict(synth.TUM3))
+    return bench.make_track_inputs(kps, desc, counts, boxes_gt, cap, pcap, pidx, W, H, dict(synth.TUM3))
 
 
 def test_step_equals_the_stages_called_one_by_one(tmp_path):
@@ -40,7 +40,7 @@ def test_step_equals_the_stages_called_one_by_one(tmp_path):
     # 1. stage by stage: extract (host), detector (host frames one by one -> boxes by hand), track_lk with those boxes
     kps = np.zeros((nb, cap), B.KP_DTYPE); desc = np.zeros((nb, cap, 32), np.uint8); n = np.zeros(nb, np.int32)
     B.check(L.sgs_tracker_extract(trk.h, P(frames), nb, C.c_size_t(W * H), W, P(kps), P(desc), cap, P(n)))
-    ti = _inputs(frames, gt, kps, desc, n, cap, pidx)
+    ti = _inputs(frames, gt, kps, desc, n, cap, trk.point_cap, pidx)
     import torch
     d_rgb = torch.from_numpy(rgb).cuda()
     d_bx = torch.zeros((nb, 4, 4), device='cuda'); d_nb = torch.zeros(nb, dtype=torch.int32, device='cuda'); d_hv = torch.zeros(nb, dtype=torch.uint8, device='cuda')

@@ -31,7 +31,7 @@ static int run_case(int npix, int Cin, int Cout, int out_pitch, int tail, bool t
     CK(cudaMemcpy(dR, R.data(), R.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(dO, 0xff, (size_t)npix * out_pitch * 4));
     GemmPlan plan;
-    if (!plan_weights(W.data(), Cin, Cout, &plan)) { printf("plan_weights failed\n"); return 1; }
+    if (!plan_weights(W.data(), Cin, Cout, &plan, tail == TK_ADD_T || tail == TK_SE_TAIL)) { printf("plan_weights failed\n"); return 1; }
     GemmTail T{}; T.kind = tail; T.a = 3.f; T.lo = 0.f; T.hi = 6.f; T.b = 6.f; T.t1 = dR; T.t2 = dR;
     if (!launch_conv1x1_tc(plan, dX, in_pitch, npix, dB, dO, out_pitch, T, 0)) { printf("launch failed\n"); return 1; }
     CK(cudaDeviceSynchronize());
@@ -96,6 +96,8 @@ int main(int argc, char** argv) {
     fails += run_case(1444, 40, 10, 12, TK_RELU, false);
     fails += run_case(361, 28, 112, 112, TK_SE_TAIL, false);
     fails += run_case(361, 184, 80, 80, TK_ADD_T, false);
+    fails += run_case(1000, 16, 16, 16, TK_ADD_T, false);
+    fails += run_case(700, 40, 160, 160, TK_SE_TAIL, false);
     fails += run_case(25, 512, 126, 126, TK_CLIP, false);
     fails += run_case(1, 64, 128, 128, TK_CLIP, false);
     if (argc > 1) {
@@ -108,6 +110,8 @@ int main(int argc, char** argv) {
         fails += run_case(361 * 128, 672, 160, 160, TK_NONE, true);
         fails += run_case(100 * 128, 160, 960, 960, TK_HSWISH, true);
         fails += run_case(100 * 128, 960, 160, 160, TK_NONE, true);
+        fails += run_case(22500 * 128, 16, 16, 16, TK_ADD_T, true);
+        fails += run_case(361 * 128, 28, 112, 112, TK_SE_TAIL, true);
     }
     printf(fails ? "FAILED (%d)\n" : "ALL OK\n", fails);
     return fails ? 1 : 0;
