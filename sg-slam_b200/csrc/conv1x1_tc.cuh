@@ -37,7 +37,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
+#ifdef TC_DBG_SUSPEND
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
@@ -80,6 +84,14 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
     lo = (__float_as_uint(__fsub_rn(__uint_as_float(x), __uint_as_float(hi))) + 0x1000u) & 0xffffe000u;
 }
 
+#ifdef SGS_TC_TRACE
+// pipeline trace of CTA (0, 0) (tools/umma_proto only): SM clock at the hand-over points of the four roles
+__device__ long long g_tc_trace[4][1024];
+#define TC_TRACE(role, slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 1024) g_tc_trace[role][slot] = clock64(); } while (0)
+#else
+#define TC_TRACE(role, slot) do { } while (0)
+#endif
+
 struct TcGeom {
     int npix, Cin, Cout;          // rows of X, channels in / out
     int NT, KB, stages;           // output channels per tile (multiple of 16), k-blocks, pipeline depth of the operand ring
@@ -91,7 +103,7 @@ struct TcGeom {
     int64_t base_off;             // float offset of frame 0 of the output inside `out`
     int pitch;                    // floats between consecutive pixels of the output
     int vec_ok;                   // 16-byte aligned rows: float4 stores
-    int coalesce;                 // contiguous [pixel][channel] output: full 32-channel chunks are transposed through shared memory and stored row by row
+    int coalesce;                 // contiguous [pixel][channel] output (frame_stride == HW * pitch): a pixel's row address needs no division by HW
 };
 
 // warp 0: TMA producer, warp 1: MMA issuer (+ TMEM owner), warps 2 .. 2+EPW-1: epilogue (EPW = 4 or 8), the last four warps: operand split
@@ -164,6 +176,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_
                         tma_load_2d(st + 2 * a_bytes, &mapBh, kb * BKT, n0, bar);
                         tma_load_2d(st + 2 * a_bytes + b_bytes, &mapBl, kb * BKT, n0, bar);
                     }
+                    TC_TRACE(0, g);
                 }
             }
         }
@@ -182,6 +195,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_
                     const uint32_t s = g % (uint32_t)G.stages, ph = (g / (uint32_t)G.stages) & 1u;
                     mbar_wait(smem_addr(&s_ready[s]), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    TC_TRACE(2, 2 * g);
                     const uint32_t st = sbase + s * stage_bytes;
                     const uint32_t bh0 = G.b_resident ? bres + (uint32_t)kb * 2 * b_bytes : st + 2 * a_bytes;
                     const int ksteps = min(BKT, G.Cin - kb * BKT + 7) >> 3;         // 8-wide k-steps that hold real channels (the rest is zero fill)
@@ -193,6 +207,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_
                         umma_tf32(acc, ah, bh, idesc, 1);
                     }
                     umma_commit(smem_addr(&s_empty[s]));                            // slot free once these MMAs have read it
+                    TC_TRACE(2, 2 * g + 1);
                 }
                 umma_commit(smem_addr(&s_acc_full[ab]));                            // accumulator complete -> epilogue
             }
@@ -205,6 +220,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_
             for (int kb = 0; kb < G.KB; ++kb, ++g) {
                 const uint32_t s = g % (uint32_t)G.stages, ph = (g / (uint32_t)G.stages) & 1u;
                 mbar_wait(smem_addr(&s_full[s]), ph);
+                if (t == 0) TC_TRACE(1, 2 * g);
                 uint4* ahi = reinterpret_cast<uint4*>(gbase + (size_t)s * stage_bytes);
                 uint4* alo = reinterpret_cast<uint4*>(gbase + (size_t)s * stage_bytes + a_bytes);
 #pragma unroll
@@ -218,6 +234,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_addr(&s_ready[s]));
+                if (t == 0) TC_TRACE(1, 2 * g + 1);
             }
     } else {
         // ------------------------------------------------------------------------------------------------ epilogue: warp w reads TMEM lane quadrant w % 4;
@@ -226,94 +243,122 @@ __global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_
         const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
         for (int it = 0; it < my_tiles; ++it) {
             const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
-            const int p = ((int)blockIdx.x + it * (int)gridDim.x) * kBM + quad * 32 + lane;
-            const bool live = p < G.npix;
-            float* orow = nullptr;
-            int64_t idx_row = 0;
-            if (live) {
-                const int f = p / G.HW, pl = p - f * G.HW;
-                orow = out + G.base_off + (int64_t)f * G.frame_stride + (int64_t)pl * G.pitch;
-                idx_row = (int64_t)p * G.Cout;
-            }
             mbar_wait(smem_addr(&s_acc_full[ab]), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 64) TC_TRACE(3, 2 * it);
             const uint32_t tacc = trow + ab * (uint32_t)G.NT;
-            for (int c0 = 32 * half; c0 < G.NT; c0 += 32 * (EPW / 4)) {
-                if (n0 + c0 >= G.Cout) break;                                   // uniform: padding columns of the last tile
+#ifdef SGS_TC_TRACE
+            int tk = 0;
+#define TC_TRACE_EPI() do { if (tid == 64 && tk < 16) { TC_TRACE(3, 64 + 16 * it + tk); ++tk; } } while (0)
+#else
+#define TC_TRACE_EPI() do { } while (0)
+#endif
+            const int ncol = min(G.NT, G.Cout - n0);                            // real output channels of this tile (uniform)
+            const int cstep = 32 * (EPW / 4);
+            for (int c0 = 32 * half; c0 < ncol; c0 += cstep) {
+                const int nch = min(32, ncol - c0);                             // channels of this chunk (uniform)
+                const bool last = c0 + cstep >= ncol;
                 uint32_t r[2][16];
-                const bool two = c0 + 16 < G.NT && n0 + c0 + 16 < G.Cout;       // uniform
                 tmem_ld16(tacc + (uint32_t)c0, r[0]);
-                if (two) tmem_ld16(tacc + (uint32_t)c0 + 16u, r[1]);
-                const bool full0 = G.Cout - (n0 + c0) >= 16, full1 = two && G.Cout - (n0 + c0 + 16) >= 16;
-                float4 bq[2][4];                                                // the bias of the chunk travels while the TMEM load completes
+                if (nch <= 16) {
+                    // At most 16 channels (narrow layers, the left-over chunk of a tile): one pixel per lane, 64 contiguous bytes each -- the short
+                    // dependency chain matters more here than the shape of the stores (tiles of narrow layers are small and come in quick succession).
+                    tmem_ld_wait();
+                    if (last) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_addr(&s_acc_empty[ab]));
+                    }
+                    const int p = ((int)blockIdx.x + it * (int)gridDim.x) * kBM + quad * 32 + lane;
+                    if (p < G.npix) {
+                        int64_t off = (int64_t)p * G.pitch;
+                        if (!G.coalesce) { const int f = p / G.HW; off = (int64_t)f * G.frame_stride + (int64_t)(p - f * G.HW) * G.pitch; }
+                        float* o = out + G.base_off + off + n0 + c0;
+                        const int64_t idx = (int64_t)p * G.Cout + n0 + c0;
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        bq[h][q] = (bias && (h == 0 ? full0 : full1)) ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + 16 * h) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                tmem_ld_wait();
-                if (EPW == 8 && G.coalesce && full0 && full1) {
-                    // whole 32-channel chunk: bias + tail in registers (one pixel per lane), transpose through this warp's 4 KB of shared memory
-                    // (16-byte pieces XOR-swizzled by the row: conflict-free both ways), then every store instruction writes 4 rows x 128 contiguous bytes
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const int nq = min(4, nch - 4 * q4);
+                            if (nq <= 0) break;
+                            float v[4] = {__uint_as_float(r[0][4 * q4]), __uint_as_float(r[0][4 * q4 + 1]), __uint_as_float(r[0][4 * q4 + 2]), __uint_as_float(r[0][4 * q4 + 3])};
+                            if (nq == 4 && G.vec_ok) {
+                                const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + 4 * q4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                v[0] = __fadd_rn(v[0], bv.x); v[1] = __fadd_rn(v[1], bv.y); v[2] = __fadd_rn(v[2], bv.z); v[3] = __fadd_rn(v[3], bv.w);
+                                epi.template run<4>(v, idx + 4 * q4);
+                                *reinterpret_cast<float4*>(o + 4 * q4) = make_float4(v[0], v[1], v[2], v[3]);
+                            } else {
+#pragma unroll 1
+                                for (int q = 0; q < nq; ++q) {
+                                    float one[1] = {__fadd_rn(q == 0 ? v[0] : q == 1 ? v[1] : q == 2 ? v[2] : v[3], bias ? __ldg(bias + n0 + c0 + 4 * q4 + q) : 0.f)};
+                                    epi.template run<1>(one, idx + 4 * q4 + q);
+                                    o[4 * q4 + q] = one[0];
+                                }
+                            }
+                        }
+                    }
+                    continue;
+                }
+                tmem_ld16(tacc + (uint32_t)c0 + 16u, r[1]);
+                {
+                    // The raw accumulators (one pixel per lane) are transposed through this warp's 4 KB of shared memory (16-byte pieces XOR-swizzled by the
+                    // row: conflict-free both ways); on the row-major side a lane owns ONE channel quad of eight rows: its bias is fetched once, the tensor
+                    // operands of the tail are read as coalesced rows, and every store instruction writes 4 rows x 128 contiguous bytes (4 memory wavefronts
+                    // instead of the 32 of a one-pixel-per-lane store).
+                    const int c = lane & 7, cq = 4 * c;
+                    const int nq = min(4, nch - cq);                            // channels this lane owns on the row-major side: 4 = a whole quad, <= 0 = none
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias) {
+                        if (nq == 4) bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + cq));
+                        else if (nq > 0) { bv.x = __ldg(bias + n0 + c0 + cq); if (nq > 1) bv.y = __ldg(bias + n0 + c0 + cq + 1); if (nq > 2) bv.z = __ldg(bias + n0 + c0 + cq + 2); }
+                    }
                     float4* stg = reinterpret_cast<float4*>(gbase + epi_off + (size_t)(warp - 2) * 4096);
+                    tmem_ld_wait();
+                    TC_TRACE_EPI();
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            stg[lane * 8 + ((4 * h + q) ^ (lane & 7))] = make_float4(__fadd_rn(__uint_as_float(r[h][4 * q]), bq[h][q].x), __fadd_rn(__uint_as_float(r[h][4 * q + 1]), bq[h][q].y),
-                                                                                     __fadd_rn(__uint_as_float(r[h][4 * q + 2]), bq[h][q].z), __fadd_rn(__uint_as_float(r[h][4 * q + 3]), bq[h][q].w));
+                            stg[lane * 8 + ((4 * h + q) ^ (lane & 7))] = make_float4(__uint_as_float(r[h][4 * q]), __uint_as_float(r[h][4 * q + 1]), __uint_as_float(r[h][4 * q + 2]), __uint_as_float(r[h][4 * q + 3]));
+                    if (last) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    // the tail runs on the row-major side: its tensor operands are read as coalesced float4 rows, like the stores
+                    if (last && lane == 0) mbar_arrive(smem_addr(&s_acc_empty[ab]));          // every TMEM read of this warp's quadrant has completed: the MMAs of tile it + 2 may start
+                    TC_TRACE_EPI();
                     const int p0 = ((int)blockIdx.x + it * (int)gridDim.x) * kBM + quad * 32;
+                    if (nq > 0) {
+                        const bool vec = nq == 4 && G.vec_ok;
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        const int row = i4 * 4 + (lane >> 3), c = lane & 7;
-                        if (p0 + row < G.npix) {
-                            const float4 x = stg[row * 8 + (c ^ (row & 7))];
-                            float v[4] = {x.x, x.y, x.z, x.w};
-                            epi.template run<4>(v, (int64_t)(p0 + row) * G.Cout + n0 + c0 + 4 * c);
-                            *reinterpret_cast<float4*>(out + G.base_off + (int64_t)(p0 + row) * G.pitch + n0 + c0 + 4 * c) = make_float4(v[0], v[1], v[2], v[3]);
-                        }
-                    }
-                    __syncwarp();
-                    continue;
-                }
-                if (!live) continue;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h == 1 && !two) break;
-                    const int co = n0 + c0 + 16 * h;
-                    const int nv = min(16, G.Cout - co);
-                    float v[16];
-                    if (nv == 16) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            v[4 * q] = __fadd_rn(__uint_as_float(r[h][4 * q]), bq[h][q].x); v[4 * q + 1] = __fadd_rn(__uint_as_float(r[h][4 * q + 1]), bq[h][q].y);
-                            v[4 * q + 2] = __fadd_rn(__uint_as_float(r[h][4 * q + 2]), bq[h][q].z); v[4 * q + 3] = __fadd_rn(__uint_as_float(r[h][4 * q + 3]), bq[h][q].w);
-                        }
-                        epi.template run<16>(v, idx_row + co);
-                        if (G.vec_ok) {
-#pragma unroll
-                            for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(orow + co + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) orow[co + q] = v[q];
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            if (q < nv) {
-                                float one[1] = {__fadd_rn(__uint_as_float(r[h][q]), bias ? __ldg(bias + co + q) : 0.f)};
-                                epi.template run<1>(one, idx_row + co + q);
-                                orow[co + q] = one[0];
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const int row = i4 * 4 + (lane >> 3), p = p0 + row;
+                            if (p < G.npix) {
+                                const float4 x = stg[row * 8 + (c ^ (row & 7))];
+                                float v[4] = {__fadd_rn(x.x, bv.x), __fadd_rn(x.y, bv.y), __fadd_rn(x.z, bv.z), __fadd_rn(x.w, bv.w)};
+                                const int64_t idx = (int64_t)p * G.Cout + n0 + c0 + cq;
+                                int64_t off = (int64_t)p * G.pitch;                 // contiguous [pixel][channel] output
+                                if (!G.coalesce) { const int f = p / G.HW; off = (int64_t)f * G.frame_stride + (int64_t)(p - f * G.HW) * G.pitch; }      // slice of a concatenation buffer
+                                float* o = out + G.base_off + off + n0 + c0 + cq;
+                                if (vec) {
+                                    epi.template run<4>(v, idx);
+                                    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                                } else {                                        // unaligned rows, or the last channels of a layer whose Cout is not a multiple of 4
+#pragma unroll 1
+                                    for (int q = 0; q < nq; ++q) {
+                                        float one[1] = {q == 0 ? v[0] : q == 1 ? v[1] : q == 2 ? v[2] : v[3]};
+                                        epi.template run<1>(one, idx + q);
+                                        o[q] = one[0];
+                                    }
+                                }
                             }
                         }
                     }
+                    __syncwarp();
+                    TC_TRACE_EPI();
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_addr(&s_acc_empty[ab]));                // this warp's quadrant of the accumulator is drained
+            if (half == 1 && 32 >= ncol) {                                       // this warp had no chunk: nothing of the accumulator to wait for
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_addr(&s_acc_empty[ab]));
+            }
+            if (tid == 64) TC_TRACE(3, 2 * it + 1);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -379,10 +424,11 @@ inline void plan_tiling(int Cin, int Cout, GemmPlan* P, bool tensor_tail = false
     const int a_stage = 2 * kBM * P->BK * 4, b_block = 2 * P->NT * P->BK * 4;
     const int b_all = P->KB * b_block;
     P->b_resident = b_all <= 96 * 1024 ? 1 : 0;
-    // resident weights + two ring slots fit twice: two CTAs per SM -- unless the tail reads other tensors, which only the eight-warp epilogue fetches row-wise
-    P->ctas_per_sm = (!tensor_tail && P->b_resident && b_all + 2 * a_stage + 1024 <= 110 * 1024) ? 2 : 1;
+    // resident weights + two ring slots + the four transpose buffers fit twice: two CTAs per SM
+    (void)tensor_tail;
+    P->ctas_per_sm = (P->b_resident && b_all + 2 * a_stage + 4 * 4096 + 1024 <= 110 * 1024) ? 2 : 1;
     P->epw = P->ctas_per_sm == 2 ? 4 : 8;                                // one CTA per SM: eight epilogue warps keep up with wide output tiles
-    const int epi_stage = P->epw == 8 ? 8 * 4096 : 0;                    // the eight epilogue warps' transpose buffers (the two-CTA variant stores directly)
+    const int epi_stage = P->epw * 4096;                                 // the epilogue warps' transpose buffers
     const int budget = (P->ctas_per_sm == 2 ? 110 : 220) * 1024 - 1024 - epi_stage - (P->b_resident ? b_all : 0);
     const int stage_bytes = a_stage + (P->b_resident ? 0 : b_block);
     int st = budget / stage_bytes;
@@ -416,43 +462,30 @@ enum { TK_NONE = 0, TK_RELU, TK_CLIP, TK_HSWISH, TK_ADD_T, TK_SE_TAIL };
 // sign of zero (verified exhaustively on the host over all 2^32 bit patterns); below 2^-100 it may differ from the IEEE quotient in the last bit of a
 // denormal.  Both the fused and the layer-by-layer execution use this function.  (The generic IEEE division takes its slow path whenever the dividend is
 // zero -- half of all hard-swish outputs.)
-__device__ __forceinline__ float div_scalar(float x, float c) {
-    if (c == 6.0f) {
-        const float r = 0x1.555556p-3f;                 // RN(1/6)
-        const float q = __fmul_rn(x, r);
-        return __fmaf_rn(__fmaf_rn(-6.0f, q, x), r, q);
-    }
-    return __fdiv_rn(x, c);
+__device__ __forceinline__ float div6(float x) {         // correctly rounded x / 6 without the division subroutine
+    const float r = 0x1.555556p-3f;                     // RN(1/6)
+    const float q = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-6.0f, q, x), r, q);
 }
+__device__ __forceinline__ float div_scalar(float x, float c) { return c == 6.0f ? div6(x) : __fdiv_rn(x, c); }
 
-struct GemmTail {
+struct GemmTail {                  // the unit harness' description of a tail (tools/umma_proto); the detector has its own functor (detector.cu: EpiFnK)
     int kind;
     float a, lo, hi, b;
     const float* t1; const float* t2;
+};
+template <int KIND>
+struct GemmTailK {                 // tail kind fixed at compile time: the epilogue carries the code of one tail only
+    GemmTail t;
     template <int N>
     __device__ __forceinline__ void run(float (&v)[N], int64_t idx0) const {
-        switch (kind) {
-        case TK_RELU:
 #pragma unroll
-            for (int q = 0; q < N; ++q) v[q] = fmaxf(v[q], 0.f);
-            break;
-        case TK_CLIP:
-#pragma unroll
-            for (int q = 0; q < N; ++q) v[q] = fminf(fmaxf(v[q], lo), hi);
-            break;
-        case TK_HSWISH:
-#pragma unroll
-            for (int q = 0; q < N; ++q) v[q] = div_scalar(__fmul_rn(v[q], fminf(fmaxf(__fadd_rn(v[q], a), lo), hi)), b);
-            break;
-        case TK_ADD_T:
-#pragma unroll
-            for (int q = 0; q < N; ++q) v[q] = __fadd_rn(v[q], __ldg(t1 + idx0 + q));
-            break;
-        case TK_SE_TAIL:
-#pragma unroll
-            for (int q = 0; q < N; ++q) v[q] = __fadd_rn(__fmul_rn(__ldg(t1 + idx0 + q), div_scalar(fminf(fmaxf(__fadd_rn(v[q], a), lo), hi), b)), __ldg(t2 + idx0 + q));
-            break;
-        default: break;
+        for (int q = 0; q < N; ++q) {
+            if constexpr (KIND == TK_RELU) v[q] = fmaxf(v[q], 0.f);
+            else if constexpr (KIND == TK_CLIP) v[q] = fminf(fmaxf(v[q], t.lo), t.hi);
+            else if constexpr (KIND == TK_HSWISH) v[q] = div6(__fmul_rn(v[q], fminf(fmaxf(__fadd_rn(v[q], t.a), t.lo), t.hi)));
+            else if constexpr (KIND == TK_ADD_T) v[q] = __fadd_rn(v[q], __ldg(t.t1 + idx0 + q));
+            else if constexpr (KIND == TK_SE_TAIL) v[q] = __fadd_rn(__fmul_rn(__ldg(t.t1 + idx0 + q), div6(fminf(fmaxf(__fadd_rn(v[q], t.a), t.lo), t.hi))), __ldg(t.t2 + idx0 + q));
         }
     }
 };
@@ -472,7 +505,7 @@ inline bool launch_conv1x1_tc_map(const GemmPlan& P, const CUtensorMap& mapA, in
     G.m_tiles = (npix + kBM - 1) / kBM; G.b_resident = P.b_resident;
     G.HW = HW; G.frame_stride = frame_stride; G.base_off = base_off; G.pitch = pitch;
     G.vec_ok = ((pitch & 3) == 0 && (frame_stride & 3) == 0 && (base_off & 3) == 0 && (((uintptr_t)out) & 15) == 0) ? 1 : 0;
-    G.coalesce = (G.vec_ok && (frame_stride == 0 || frame_stride == (int64_t)HW * pitch)) ? 1 : 0;
+    G.coalesce = (frame_stride == 0 || frame_stride == (int64_t)HW * pitch) ? 1 : 0;
     int gx = (sm_count() * P.ctas_per_sm) / P.n_tiles;                  // one wave of persistent CTAs
     if (gx < 1) gx = 1;
     if (gx > G.m_tiles) gx = G.m_tiles;
@@ -492,7 +525,15 @@ inline bool launch_conv1x1_tc_map(const GemmPlan& P, const CUtensorMap& mapA, in
 inline bool launch_conv1x1_tc(const GemmPlan& P, const float* x, int in_pitch, int npix, const float* bias, float* out, int out_pitch, const GemmTail& T, cudaStream_t st) {
     CUtensorMap mapA;
     if (!encode_kmajor_map(&mapA, x, npix, P.Cin, in_pitch, kBM, P.BK)) return false;
-    return launch_conv1x1_tc_map(P, mapA, npix, bias, out, npix > 0 ? npix : 1, 0, 0, out_pitch, T, st);
+    const int HW = npix > 0 ? npix : 1;
+    switch (T.kind) {
+    case TK_RELU: return launch_conv1x1_tc_map(P, mapA, npix, bias, out, HW, 0, 0, out_pitch, GemmTailK<TK_RELU>{T}, st);
+    case TK_CLIP: return launch_conv1x1_tc_map(P, mapA, npix, bias, out, HW, 0, 0, out_pitch, GemmTailK<TK_CLIP>{T}, st);
+    case TK_HSWISH: return launch_conv1x1_tc_map(P, mapA, npix, bias, out, HW, 0, 0, out_pitch, GemmTailK<TK_HSWISH>{T}, st);
+    case TK_ADD_T: return launch_conv1x1_tc_map(P, mapA, npix, bias, out, HW, 0, 0, out_pitch, GemmTailK<TK_ADD_T>{T}, st);
+    case TK_SE_TAIL: return launch_conv1x1_tc_map(P, mapA, npix, bias, out, HW, 0, 0, out_pitch, GemmTailK<TK_SE_TAIL>{T}, st);
+    default: return launch_conv1x1_tc_map(P, mapA, npix, bias, out, HW, 0, 0, out_pitch, GemmTailK<TK_NONE>{T}, st);
+    }
 }
 
 }  // namespace tc

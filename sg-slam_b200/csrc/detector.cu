@@ -33,6 +33,7 @@ namespace sgs {
 namespace det {
 
 using tc::div_scalar;
+using tc::div6;
 
 // ---------------------------------------------------------------------------------------------------------------- element-wise tail
 enum { E_ADD = 0, E_SUB = 1, E_MUL = 2, E_DIV = 3, E_CLIP = 4, E_RELU = 5 };   // 0..3 = ncnn BinaryOp op_type
@@ -48,7 +49,8 @@ struct Epi {
     EpiStep s[kMaxEpi];
 };
 
-enum { EK_GENERIC = 0, EK_NONE, EK_RELU, EK_CLIP, EK_HSWISH, EK_ADD_T, EK_SE_TAIL, EK_SE_MUL };   // Epi::kind: recognised tails run as straight-line code
+enum { EK_GENERIC = 0, EK_NONE, EK_RELU, EK_CLIP, EK_HSWISH, EK_ADD_T, EK_SE_TAIL, EK_SE_MUL };   // Epi::kind: recognised tails run as straight-line code;
+// the divisor of the three hard-swish / hard-sigmoid kinds is exactly 6 (checked at classification: other divisors take the generic tail)
 
 template <int KIND>
 __device__ __forceinline__ float apply_epi(const Epi& e, float v, int64_t idx) {
@@ -56,12 +58,12 @@ __device__ __forceinline__ float apply_epi(const Epi& e, float v, int64_t idx) {
     else if constexpr (KIND == EK_RELU) return fmaxf(v, 0.f);
     else if constexpr (KIND == EK_CLIP) return fminf(fmaxf(v, e.s[0].a), e.s[0].b);
     else if constexpr (KIND == EK_HSWISH)                // v * clip(v + a) / b   (add scalar, clip, mul(rev) start, div scalar)
-        return div_scalar(__fmul_rn(v, fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b)), e.s[3].a);
+        return div6(__fmul_rn(v, fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b)));
     else if constexpr (KIND == EK_ADD_T) return __fadd_rn(v, __ldg(e.s[0].t + idx));
     else if constexpr (KIND == EK_SE_TAIL)               // t1 * (clip(v + a) / b) + t2   (add scalar, clip, div scalar, mul(rev) tensor, add tensor)
-        return __fadd_rn(__fmul_rn(__ldg(e.s[3].t + idx), div_scalar(fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b), e.s[2].a)), __ldg(e.s[4].t + idx));
+        return __fadd_rn(__fmul_rn(__ldg(e.s[3].t + idx), div6(fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b))), __ldg(e.s[4].t + idx));
     else if constexpr (KIND == EK_SE_MUL)                // t1 * (clip(v + a) / b)   (add scalar, clip, div scalar, mul(rev) tensor): hard-sigmoid gate
-        return __fmul_rn(__ldg(e.s[3].t + idx), div_scalar(fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b), e.s[2].a));
+        return __fmul_rn(__ldg(e.s[3].t + idx), div6(fminf(fmaxf(__fadd_rn(v, e.s[0].a), e.s[1].a), e.s[1].b)));
     else {
         const float v0 = v;
         for (int i = 0; i < e.n; ++i) {
@@ -92,6 +94,20 @@ __device__ __forceinline__ void epi_dispatch(int kind, F&& body) {
     }
 }
 
+template <class F>
+inline void epi_dispatch_host(int kind, F&& body) {
+    switch (kind) {
+    case EK_NONE: body(EpiKind<EK_NONE>{}); break;
+    case EK_RELU: body(EpiKind<EK_RELU>{}); break;
+    case EK_CLIP: body(EpiKind<EK_CLIP>{}); break;
+    case EK_HSWISH: body(EpiKind<EK_HSWISH>{}); break;
+    case EK_ADD_T: body(EpiKind<EK_ADD_T>{}); break;
+    case EK_SE_TAIL: body(EpiKind<EK_SE_TAIL>{}); break;
+    case EK_SE_MUL: body(EpiKind<EK_SE_MUL>{}); break;
+    default: body(EpiKind<EK_GENERIC>{}); break;
+    }
+}
+
 // Four consecutive channels of one pixel (idx % 4 == 0, 16-byte aligned operand tensors): the tensor operands of the recognised tails are fetched
 // as one float4 each instead of four scalar loads (the element order and roundings are those of apply_epi).
 template <int KIND>
@@ -106,7 +122,7 @@ __device__ __forceinline__ void apply_epi4(const Epi& e, float (&v)[4], int64_t 
         const float a[4] = {t1.x, t1.y, t1.z, t1.w}, b[4] = {t2.x, t2.y, t2.z, t2.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float g = __fmul_rn(a[q], div_scalar(fminf(fmaxf(__fadd_rn(v[q], e.s[0].a), e.s[1].a), e.s[1].b), e.s[2].a));
+            const float g = __fmul_rn(a[q], div6(fminf(fmaxf(__fadd_rn(v[q], e.s[0].a), e.s[1].a), e.s[1].b)));
             v[q] = KIND == EK_SE_TAIL ? __fadd_rn(g, b[q]) : g;
         }
     } else {
@@ -176,6 +192,30 @@ struct EpiFn {
         });
     }
     __host__ __device__ bool reads_tensors() const { return e.kind == EK_ADD_T || e.kind == EK_SE_TAIL || e.kind == EK_SE_MUL || e.kind == EK_GENERIC; }
+};
+
+// The same with the tail kind fixed at compile time: one instantiation of the tcgen05 GEMM per kind, so that the epilogue warps carry the code of one
+// tail only (with the run-time switch every tail was inlined at every call site and the five warp roles of the kernel thrashed the instruction cache:
+// ncu stall_no_instruction 4.6 per issue, in-network times 1.5 - 1.8x those of the single-tail unit harness).
+template <int KIND>
+struct EpiFnK {
+    Epi e;
+    template <int N>
+    __device__ __forceinline__ void run(float (&v)[N], int64_t idx0) const {
+        if constexpr (N % 4 == 0) {
+            if ((idx0 & 3) == 0) {
+#pragma unroll
+                for (int q = 0; q < N; q += 4) {
+                    float w[4] = {v[q], v[q + 1], v[q + 2], v[q + 3]};
+                    apply_epi4<KIND>(e, w, idx0 + q);
+                    v[q] = w[0]; v[q + 1] = w[1]; v[q + 2] = w[2]; v[q + 3] = w[3];
+                }
+                return;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < N; ++q) v[q] = apply_epi<KIND>(e, v[q], idx0 + q);
+    }
 };
 
 // depth-wise K x K, stride S on [frame][h][w][c]: V channels (float4 when C % 4 == 0) x XT consecutive outputs of one row per thread; the
@@ -1021,10 +1061,10 @@ Epi make_epi(const sgs_detector* D, const std::vector<EpiStepH>& h) {
     else if (e.n == 1 && h[0].op == E_RELU) e.kind = EK_RELU;
     else if (e.n == 1 && h[0].op == E_CLIP) e.kind = EK_CLIP;
     else if (e.n == 1 && is(0, E_ADD, SRC_TENSOR)) e.kind = EK_ADD_T;          // addition commutes: rev is irrelevant
-    else if (e.n == 4 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_MUL, SRC_START) && is(3, E_DIV, SRC_SCALAR) && !h[3].rev) e.kind = EK_HSWISH;
-    else if (e.n == 5 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_DIV, SRC_SCALAR) && !h[2].rev && is(3, E_MUL, SRC_TENSOR) && is(4, E_ADD, SRC_TENSOR))
+    else if (e.n == 4 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_MUL, SRC_START) && is(3, E_DIV, SRC_SCALAR) && !h[3].rev && h[3].a == 6.0f) e.kind = EK_HSWISH;
+    else if (e.n == 5 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_DIV, SRC_SCALAR) && !h[2].rev && h[2].a == 6.0f && is(3, E_MUL, SRC_TENSOR) && is(4, E_ADD, SRC_TENSOR))
         e.kind = EK_SE_TAIL;
-    else if (e.n == 4 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_DIV, SRC_SCALAR) && !h[2].rev && is(3, E_MUL, SRC_TENSOR)) e.kind = EK_SE_MUL;
+    else if (e.n == 4 && is(0, E_ADD, SRC_SCALAR) && h[1].op == E_CLIP && is(2, E_DIV, SRC_SCALAR) && !h[2].rev && h[2].a == 6.0f && is(3, E_MUL, SRC_TENSOR)) e.kind = EK_SE_MUL;
     return e;
 }
 
@@ -1105,7 +1145,11 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
             const int HW = op.g.OH * op.g.OW; const int64_t npix = (int64_t)F * HW;
             if (npix >= (1ll << 31) - 256) { set_error("sgs_detector_detect_device: batch too large for 32-bit pixel indices"); return SGS_ERR_UNSUPPORTED; }
             const int64_t fstride = op.cat ? bo.n : (int64_t)HW * op.g.Cout;
-            if (!tc::launch_conv1x1_tc_map(op.gp, op.map_in, (int)npix, op.d_b, bo.dev, HW, fstride, op.cat ? op.off : 0, op.g.Cout, EpiFn{epi}, st)) {
+            bool launched = false;
+            epi_dispatch_host(epi.kind, [&](auto kind) {
+                launched = tc::launch_conv1x1_tc_map(op.gp, op.map_in, (int)npix, op.d_b, bo.dev, HW, fstride, op.cat ? op.off : 0, op.g.Cout, EpiFnK<decltype(kind)::value>{epi}, st);
+            });
+            if (!launched) {
                 set_error("sgs_detector_detect_device: layer %s: GEMM launch failed (%s)", D->layers[op.layer].name.c_str(), cudaGetErrorString(cudaGetLastError())); return SGS_ERR_CUDA; }
             break;
         }

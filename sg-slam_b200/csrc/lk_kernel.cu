@@ -137,6 +137,15 @@ __device__ __forceinline__ long long warp_sum_exact(int v) {
 
 __device__ __forceinline__ int lk_descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
+// Three neighbouring pixels of one image row as the bytes (p0, p1, p1, p2): the low half feeds the bilinear taps of column 0, the high half those of
+// column 1 (IDP.2A: two 16-bit weights x two bytes + accumulator in one instruction, same issue rate as one IMAD).
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (lo) / ... byte2, byte3 (hi): SIGNED 16-bit halves (w11 = 16384 - w00 - w01 - w10 can be -1) x unsigned bytes
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t lk_pack_weights(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+
+__device__ __forceinline__ uint32_t lk_pack_row(uint32_t p0, uint32_t p1, uint32_t p2) { return p0 | (p1 * 0x00010100u) | (p2 << 24); }
+
 __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
     w00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), 16384.f));
     w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), 16384.f));
@@ -153,27 +162,29 @@ __device__ __forceinline__ void lk_setup_tiles(const uint8_t* __restrict__ img, 
                                                int k2, int g7, int erow, int lane, int w00, int w01, int w10, int w11,
                                                int (&C)[14], int (&GX)[14], int (&GY)[14], int& Ce, int& GXe, int& GYe,
                                                int& s11, int& s12, int& s22) {
-    int R[8][3], Dx[8][3], Dy[8][3];
+    uint32_t Rw[8];                  // row r of the 8x3 tile of I as bytes (p0, p1, p1, p2): the two horizontal pixel pairs of the lane's two columns
+    int Dx[8][3], Dy[8][3];
     {
         const int64_t o = (int64_t)(ipy + g7) * pitch + (ipx + k2);
         const uint8_t* p = img + o; const uint32_t* q = der + o;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
+            Rw[r] = lk_pack_row(__ldg(p), __ldg(p + 1), __ldg(p + 2));
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
-                R[r][x] = __ldg(p + x);
                 const uint32_t d = __ldg(q + x);
                 Dx[r][x] = (int)(short)(d & 0xffffu); Dy[r][x] = (int)d >> 16;
             }
             p += pitch; q += pitch;
         }
     }
+    const uint32_t wt = lk_pack_weights(w00, w01), wb = lk_pack_weights(w10, w11);
     int a11 = 0, a12 = 0, a22 = 0;
 #pragma unroll
     for (int r = 0; r < 7; ++r)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int ival = (R[r][c] * w00 + R[r][c + 1] * w01 + R[r + 1][c] * w10 + R[r + 1][c + 1] * w11 + 256) >> 9;
+            const int ival = (c == 0 ? dp2a_lo_su(wt, Rw[r], dp2a_lo_su(wb, Rw[r + 1], 256)) : dp2a_hi_su(wt, Rw[r], dp2a_hi_su(wb, Rw[r + 1], 256))) >> 9;
             const int ixv = (Dx[r][c] * w00 + Dx[r][c + 1] * w01 + Dx[r + 1][c] * w10 + Dx[r + 1][c + 1] * w11 + 8192) >> 14;
             const int iyv = (Dy[r][c] * w00 + Dy[r][c + 1] * w01 + Dy[r + 1][c] * w10 + Dy[r + 1][c + 1] * w11 + 8192) >> 14;
             C[2 * r + c] = 256 - 512 * ival; GX[2 * r + c] = ixv; GY[2 * r + c] = iyv;
@@ -197,29 +208,31 @@ __device__ __forceinline__ void lk_setup_tiles(const uint8_t* __restrict__ img, 
 // template into the first multiply-add), and lanes 0..20 each own one pixel of the left-over column 20.  Lanes 30, 31 repeat the
 // work of lane 29 and are masked out.  Every lane loads its own 8x3 (+2x2) bytes of J from the padded plane and keeps them while the
 // iterations stay on the same integer position (the usual case: steps are sub-pixel); the sums per lane are < 15 * 2^25: exact in int32.
-__device__ __forceinline__ void lk_load_j_tile(const uint8_t* __restrict__ img, int pitch, int inx, int iny, int k2, int g7, int erow, int (&v)[8][3], int (&e)[4]) {
+__device__ __forceinline__ void lk_load_j_tile(const uint8_t* __restrict__ img, int pitch, int inx, int iny, int k2, int g7, int erow, uint32_t (&v)[8], uint32_t& e) {
     const uint8_t* p = img + (int64_t)(iny + g7) * pitch + (inx + k2);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        v[r][0] = __ldg(p); v[r][1] = __ldg(p + 1); v[r][2] = __ldg(p + 2);
+        v[r] = lk_pack_row(__ldg(p), __ldg(p + 1), __ldg(p + 2));
         p += pitch;
     }
     const uint8_t* q = img + (int64_t)(iny + erow) * pitch + (inx + 20);
-    e[0] = __ldg(q); e[1] = __ldg(q + 1); e[2] = __ldg(q + pitch); e[3] = __ldg(q + pitch + 1);
+    e = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + pitch) << 16) | ((uint32_t)__ldg(q + pitch + 1) << 24);
 }
 
-__device__ __forceinline__ void lk_mismatch_tiles(const int (&v)[8][3], const int (&e)[4], bool lane30, int w00, int w01, int w10, int w11,
+// v[r] = packed row r of the lane's 8x3 tile of J (lk_pack_row), e = the 2x2 pixels under its pixel of column 20 (top pair | bottom pair << 16);
+// wt = w00 | w01 << 16, wb = w10 | w11 << 16.  
+__device__ __forceinline__ void lk_mismatch_tiles(const uint32_t (&v)[8], uint32_t e, bool lane30, uint32_t wt, uint32_t wb,
                                                   const int (&C)[14], const int (&GX)[14], const int (&GY)[14], int Ce, int GXe, int GYe, int& s1, int& s2) {
     int a1 = 0, a2 = 0, b1 = 0, b2 = 0;
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
-        const int da = (v[r][0] * w00 + v[r][1] * w01 + v[r + 1][0] * w10 + v[r + 1][1] * w11 + C[2 * r]) >> 9;
-        const int db = (v[r][1] * w00 + v[r][2] * w01 + v[r + 1][1] * w10 + v[r + 1][2] * w11 + C[2 * r + 1]) >> 9;
+        const int da = dp2a_lo_su(wt, v[r], dp2a_lo_su(wb, v[r + 1], C[2 * r])) >> 9;
+        const int db = dp2a_hi_su(wt, v[r], dp2a_hi_su(wb, v[r + 1], C[2 * r + 1])) >> 9;
         a1 += da * GX[2 * r]; a2 += da * GY[2 * r];
         b1 += db * GX[2 * r + 1]; b2 += db * GY[2 * r + 1];
     }
     if (lane30) { a1 = 0; a2 = 0; b1 = 0; b2 = 0; }
-    const int de = (e[0] * w00 + e[1] * w01 + e[2] * w10 + e[3] * w11 + Ce) >> 9;
+    const int de = dp2a_lo_su(wt, e, dp2a_hi_su(wb, e, Ce)) >> 9;
     s1 = a1 + b1 + de * GXe; s2 = a2 + b2 + de * GYe;
 }
 
@@ -271,14 +284,15 @@ __global__ void __launch_bounds__(kLkWarps * 32) lk_track_kernel(const __grid_co
         D = __fdiv_rn(1.f, D);
         qx = __fsub_rn(qx, half_win); qy = __fsub_rn(qy, half_win);
         float pdx = 0.f, pdy = 0.f;
-        int jv[8][3], je[4], tile_x = 0x7fffffff, tile_y = 0x7fffffff;
+        uint32_t jv[8], je = 0;
+        int tile_x = 0x7fffffff, tile_y = 0x7fffffff;
         for (int j = 0; j < kLkMaxCount; ++j) {
             const int inx = (int)floorf(qx), iny = (int)floorf(qy);
             if (inx < -kWin || inx >= lw || iny < -kWin || iny >= lh) break;
             lk_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
             if (inx != tile_x || iny != tile_y) { lk_load_j_tile(Jimg, pitch, inx, iny, k2, g7, erow, jv, je); tile_x = inx; tile_y = iny; }
             int s1, s2;
-            lk_mismatch_tiles(jv, je, lane >= 30, w00, w01, w10, w11, C, GX, GY, Ce, GXe, GYe, s1, s2);
+            lk_mismatch_tiles(jv, je, lane >= 30, lk_pack_weights(w00, w01), lk_pack_weights(w10, w11), C, GX, GY, Ce, GXe, GYe, s1, s2);
             const float B1 = __fmul_rn((float)warp_sum_exact(s1), flt_scale), B2 = __fmul_rn((float)warp_sum_exact(s2), flt_scale);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, B2), __fmul_rn(A22, B1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, B1), __fmul_rn(A11, B2)), D);

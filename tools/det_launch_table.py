@@ -23,6 +23,8 @@ for i, r in enumerate(rows):
     if 'Kernel Name' in r:
         hdr = r; data = rows[i + 1:]; break
 mv = hdr.index('Metric Value'); gi = hdr.index('Grid Size'); kn = hdr.index('Kernel Name')
+first = next(i for i, r in enumerate(data) if 'preprocess_kernel' in r[kn])          # one call = preprocess ... detout_merge; the window may start mid-call
+data = data[first:] + data[:first]
 ts = [float(r[mv].replace(',', '')) / 1000 for r in data]
 agg = collections.OrderedDict()
 for r, t in zip(data, ts):

@@ -17,6 +17,25 @@ using namespace sgs::tc;
 
 static float frand(uint32_t& s) { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xffff) / 32768.0f - 1.0f; }
 
+#ifdef SGS_TC_TRACE
+static void dump_trace(int KB, int tiles) {
+    static long long h[4][1024];
+    CK(cudaMemcpyFromSymbol(h, g_tc_trace, sizeof(h)));
+    const long long t0 = h[0][0];
+    printf("   trace of CTA (0,0), SM clocks since the first TMA issue; per k-block: tma-issue | full-seen split-done | ready-seen mma-committed\n");
+    for (int g = 0; g < KB * tiles && g < 512; ++g) {
+        printf("   t%2d kb%2d  tma %7lld | split %7lld %7lld | mma %7lld %7lld", g / KB, g % KB, h[0][g] - t0, h[1][2 * g] - t0, h[1][2 * g + 1] - t0, h[2][2 * g] - t0, h[2][2 * g + 1] - t0);
+        if (g % KB == KB - 1) printf("  || epi acc-full %7lld drained %7lld", h[3][2 * (g / KB)] - t0, h[3][2 * (g / KB) + 1] - t0);
+        printf("\n");
+    }
+    for (int it = 0; it < tiles && it < 4; ++it) {
+        printf("   epilogue warp 2, tile %d (after tmem wait | staged | stored, per chunk):", it);
+        for (int k = 0; k < 12; ++k) if (h[3][64 + 16 * it + k]) printf(" %lld", h[3][64 + 16 * it + k] - t0);
+        printf("\n");
+    }
+}
+#endif
+
 static int run_case(int npix, int Cin, int Cout, int out_pitch, int tail, bool timing) {
     const int in_pitch = (Cin + 3) & ~3;
     uint32_t seed = 1234u + npix + Cin * 7 + Cout * 13;
@@ -35,6 +54,11 @@ static int run_case(int npix, int Cin, int Cout, int out_pitch, int tail, bool t
     GemmTail T{}; T.kind = tail; T.a = 3.f; T.lo = 0.f; T.hi = 6.f; T.b = 6.f; T.t1 = dR; T.t2 = dR;
     if (!launch_conv1x1_tc(plan, dX, in_pitch, npix, dB, dO, out_pitch, T, 0)) { printf("launch failed\n"); return 1; }
     CK(cudaDeviceSynchronize());
+#ifdef SGS_TC_TRACE
+    launch_conv1x1_tc(plan, dX, in_pitch, npix, dB, dO, out_pitch, T, 0); CK(cudaDeviceSynchronize());      // warm second launch is the one traced
+    printf("case npix=%d Cin=%d Cout=%d: NT=%d ntiles=%d KB=%d stages=%d bres=%d cps=%d\n", npix, Cin, Cout, plan.NT, plan.n_tiles, plan.KB, plan.stages, plan.b_resident, plan.ctas_per_sm);
+    dump_trace(plan.KB, 5);
+#endif
     std::vector<float> O((size_t)npix * out_pitch);
     CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
     double maxerr = 0, maxref = 0; int bad = 0;
@@ -83,6 +107,9 @@ int main(int argc, char** argv) {
         run_case(22500 * 128, 16, 64, 64, TK_RELU, false);
         run_case(361 * 128, 112, 672, 672, TK_HSWISH, false);
         run_case(1444 * 128, 40, 240, 240, TK_HSWISH, false);
+        run_case(361 * 128, 80, 184, 184, TK_HSWISH, false);
+        run_case(5625 * 128, 72, 24, 24, TK_ADD_T, false);
+        run_case(361 * 128, 28, 112, 112, TK_SE_TAIL, false);
         return 0;
     }
     fails += run_case(128, 32, 16, 16, TK_NONE, false);
