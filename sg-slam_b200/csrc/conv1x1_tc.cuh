@@ -270,28 +270,30 @@ __global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_
                         if (lane == 0) mbar_arrive(smem_addr(&s_acc_empty[ab]));
                     }
                     const int p = ((int)blockIdx.x + it * (int)gridDim.x) * kBM + quad * 32 + lane;
-                    if (p < G.npix) {
+                    if (G.coalesce && G.vec_ok && nch == 16 && p - lane + 32 <= G.npix) {          // the usual case as straight-line code
+                        float* o = out + G.base_off + (int64_t)p * G.pitch + n0 + c0;
+                        const int64_t idx = (int64_t)p * G.Cout + n0 + c0;
+                        float4 bv[4];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) bv[q4] = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            float v[4] = {__fadd_rn(__uint_as_float(r[0][4 * q4]), bv[q4].x), __fadd_rn(__uint_as_float(r[0][4 * q4 + 1]), bv[q4].y),
+                                          __fadd_rn(__uint_as_float(r[0][4 * q4 + 2]), bv[q4].z), __fadd_rn(__uint_as_float(r[0][4 * q4 + 3]), bv[q4].w)};
+                            epi.template run<4>(v, idx + 4 * q4);
+                            *reinterpret_cast<float4*>(o + 4 * q4) = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                    } else if (p < G.npix) {
                         int64_t off = (int64_t)p * G.pitch;
                         if (!G.coalesce) { const int f = p / G.HW; off = (int64_t)f * G.frame_stride + (int64_t)(p - f * G.HW) * G.pitch; }
                         float* o = out + G.base_off + off + n0 + c0;
                         const int64_t idx = (int64_t)p * G.Cout + n0 + c0;
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const int nq = min(4, nch - 4 * q4);
-                            if (nq <= 0) break;
-                            float v[4] = {__uint_as_float(r[0][4 * q4]), __uint_as_float(r[0][4 * q4 + 1]), __uint_as_float(r[0][4 * q4 + 2]), __uint_as_float(r[0][4 * q4 + 3])};
-                            if (nq == 4 && G.vec_ok) {
-                                const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + 4 * q4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                v[0] = __fadd_rn(v[0], bv.x); v[1] = __fadd_rn(v[1], bv.y); v[2] = __fadd_rn(v[2], bv.z); v[3] = __fadd_rn(v[3], bv.w);
-                                epi.template run<4>(v, idx + 4 * q4);
-                                *reinterpret_cast<float4*>(o + 4 * q4) = make_float4(v[0], v[1], v[2], v[3]);
-                            } else {
-#pragma unroll 1
-                                for (int q = 0; q < nq; ++q) {
-                                    float one[1] = {__fadd_rn(q == 0 ? v[0] : q == 1 ? v[1] : q == 2 ? v[2] : v[3], bias ? __ldg(bias + n0 + c0 + 4 * q4 + q) : 0.f)};
-                                    epi.template run<1>(one, idx + 4 * q4 + q);
-                                    o[4 * q4 + q] = one[0];
-                                }
+                        for (int q = 0; q < 16; ++q) {
+                            if (q < nch) {
+                                float one[1] = {__fadd_rn(__uint_as_float(r[0][q]), bias ? __ldg(bias + n0 + c0 + q) : 0.f)};
+                                epi.template run<1>(one, idx + q);
+                                o[q] = one[0];
                             }
                         }
                     }
@@ -323,22 +325,41 @@ __global__ void __launch_bounds__(tc_threads(EPW), EPW == 4 ? 2 : 1) conv1x1_tc_
                     if (last && lane == 0) mbar_arrive(smem_addr(&s_acc_empty[ab]));          // every TMEM read of this warp's quadrant has completed: the MMAs of tile it + 2 may start
                     TC_TRACE_EPI();
                     const int p0 = ((int)blockIdx.x + it * (int)gridDim.x) * kBM + quad * 32;
-                    if (nq > 0) {
-                        const bool vec = nq == 4 && G.vec_ok;
+                    if (G.coalesce && G.vec_ok && (nch & 3) == 0 && p0 + 32 <= G.npix) {
+                        // the usual case as straight-line code: whole quads, all 32 rows inside the layer, contiguous rows -- one pointer per lane, constant strides,
+                        // the eight shared-memory reads in flight together
+                        if (nq == 4) {
+                            const int r0 = lane >> 3;
+                            float* o = out + G.base_off + (int64_t)(p0 + r0) * G.pitch + n0 + c0 + cq;
+                            const int64_t idx = (int64_t)(p0 + r0) * G.Cout + n0 + c0 + cq;
+                            const int64_t ostep = 4 * (int64_t)G.pitch, istep = 4 * (int64_t)G.Cout;
+                            float4 x[8];
 #pragma unroll
+                            for (int i4 = 0; i4 < 8; ++i4) x[i4] = stg[(i4 * 4 + r0) * 8 + (c ^ ((i4 * 4 + r0) & 7))];
+#pragma unroll
+                            for (int i4 = 0; i4 < 8; ++i4) {
+                                float v[4] = {__fadd_rn(x[i4].x, bv.x), __fadd_rn(x[i4].y, bv.y), __fadd_rn(x[i4].z, bv.z), __fadd_rn(x[i4].w, bv.w)};
+                                epi.template run<4>(v, idx + i4 * istep);
+                                *reinterpret_cast<float4*>(o + i4 * ostep) = make_float4(v[0], v[1], v[2], v[3]);
+                            }
+                        }
+                    } else if (nq > 0) {
+                        // the last rows of a layer, slices of a concatenation buffer, unaligned rows, channel counts that are not multiples of 4
+                        const bool vec = nq == 4 && G.vec_ok;
+#pragma unroll 1
                         for (int i4 = 0; i4 < 8; ++i4) {
                             const int row = i4 * 4 + (lane >> 3), p = p0 + row;
                             if (p < G.npix) {
                                 const float4 x = stg[row * 8 + (c ^ (row & 7))];
                                 float v[4] = {__fadd_rn(x.x, bv.x), __fadd_rn(x.y, bv.y), __fadd_rn(x.z, bv.z), __fadd_rn(x.w, bv.w)};
                                 const int64_t idx = (int64_t)p * G.Cout + n0 + c0 + cq;
-                                int64_t off = (int64_t)p * G.pitch;                 // contiguous [pixel][channel] output
-                                if (!G.coalesce) { const int f = p / G.HW; off = (int64_t)f * G.frame_stride + (int64_t)(p - f * G.HW) * G.pitch; }      // slice of a concatenation buffer
+                                int64_t off = (int64_t)p * G.pitch;
+                                if (!G.coalesce) { const int f = p / G.HW; off = (int64_t)f * G.frame_stride + (int64_t)(p - f * G.HW) * G.pitch; }
                                 float* o = out + G.base_off + off + n0 + c0 + cq;
                                 if (vec) {
                                     epi.template run<4>(v, idx);
                                     *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                                } else {                                        // unaligned rows, or the last channels of a layer whose Cout is not a multiple of 4
+                                } else {
 #pragma unroll 1
                                     for (int q = 0; q < nq; ++q) {
                                         float one[1] = {q == 0 ? v[0] : q == 1 ? v[1] : q == 2 ? v[2] : v[3]};
@@ -413,10 +434,10 @@ inline void split_tf32_host(float x, float& hi, float& lo) {
 
 // Tiling of one layer (no device access): output-channel tiles of at most kMaxNT, weights resident when all their k-blocks fit in 96 KB,
 // ring depth from what is left of the shared memory; small weight tiles leave room for two CTAs per SM (more loads in flight, two MMA issuers).
-inline void plan_tiling(int Cin, int Cout, GemmPlan* P, bool tensor_tail = false) {
+inline void plan_tiling(int Cin, int Cout, GemmPlan* P, int force_nt = 0) {
     P->Cin = Cin; P->Cout = Cout;
     const int nt = (Cout + kMaxNT - 1) / kMaxNT;
-    P->NT = ((Cout + nt - 1) / nt + 15) & ~15;
+    P->NT = force_nt > 0 ? force_nt : ((Cout + nt - 1) / nt + 15) & ~15;
     P->n_tiles = (Cout + P->NT - 1) / P->NT;
     P->BK = Cin <= 16 ? 16 : kBK;                                        // at most 16 input channels: 64-byte operand rows, half the ring slot
     P->KB = (Cin + P->BK - 1) / P->BK;
@@ -425,7 +446,6 @@ inline void plan_tiling(int Cin, int Cout, GemmPlan* P, bool tensor_tail = false
     const int b_all = P->KB * b_block;
     P->b_resident = b_all <= 96 * 1024 ? 1 : 0;
     // resident weights + two ring slots + the four transpose buffers fit twice: two CTAs per SM
-    (void)tensor_tail;
     P->ctas_per_sm = (P->b_resident && b_all + 2 * a_stage + 4 * 4096 + 1024 <= 110 * 1024) ? 2 : 1;
     P->epw = P->ctas_per_sm == 2 ? 4 : 8;                                // one CTA per SM: eight epilogue warps keep up with wide output tiles
     const int epi_stage = P->epw * 4096;                                 // the epilogue warps' transpose buffers
@@ -442,8 +462,8 @@ inline void plan_tiling(int Cin, int Cout, GemmPlan* P, bool tensor_tail = false
 }
 
 // Splits and uploads W [Cout][Cin], picks the tiling.  Returns false when TMA is unavailable or an allocation fails.
-inline bool plan_weights(const float* W, int Cin, int Cout, GemmPlan* P, bool tensor_tail = false) {
-    plan_tiling(Cin, Cout, P, tensor_tail);
+inline bool plan_weights(const float* W, int Cin, int Cout, GemmPlan* P, int force_nt = 0) {
+    plan_tiling(Cin, Cout, P, force_nt);
     std::vector<float> hi((size_t)P->Np * P->Kp, 0.f), lo((size_t)P->Np * P->Kp, 0.f);
     for (int co = 0; co < Cout; ++co)
         for (int c = 0; c < Cin; ++c) split_tf32_host(W[(size_t)co * Cin + c], hi[(size_t)co * P->Kp + c], lo[(size_t)co * P->Kp + c]);

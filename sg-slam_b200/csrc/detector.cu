@@ -937,10 +937,8 @@ int build_graph(sgs_detector* D) {
             int fin = lout[i][0];
             if (!diag) build_tail((int)i, lout[i][0], op.epi, fin);
             if (op.kind == OP_CONV1X1) {
-                bool tensor_tail = false;
-                for (auto& st : op.epi) tensor_tail = tensor_tail || st.src == SRC_TENSOR;
-                if (D->flags & 2) tc::plan_tiling(op.g.Cin, op.g.Cout, &op.gp, tensor_tail);
-                else if (!tc::plan_weights(L.weight.data(), op.g.Cin, op.g.Cout, &op.gp, tensor_tail)) { set_error("sgs_detector_create: layer %s: the tcgen05 GEMM could not be set up (TMA tensor maps need a CUDA 12 driver; %s)", L.name.c_str(), cudaGetErrorString(cudaGetLastError())); return SGS_ERR_CUDA; }
+                if (D->flags & 2) tc::plan_tiling(op.g.Cin, op.g.Cout, &op.gp);
+                else if (!tc::plan_weights(L.weight.data(), op.g.Cin, op.g.Cout, &op.gp)) { set_error("sgs_detector_create: layer %s: the tcgen05 GEMM could not be set up (TMA tensor maps need a CUDA 12 driver; %s)", L.name.c_str(), cudaGetErrorString(cudaGetLastError())); return SGS_ERR_CUDA; }
             } else if (op.kind == OP_DWCONV) {                    // [c][ky][kx] -> [ky][kx][c]: channel vectors
                 std::vector<float> wt(L.weight.size());
                 const int kk = op.g.k * op.g.k;

@@ -50,7 +50,7 @@ static int run_case(int npix, int Cin, int Cout, int out_pitch, int tail, bool t
     CK(cudaMemcpy(dR, R.data(), R.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(dO, 0xff, (size_t)npix * out_pitch * 4));
     GemmPlan plan;
-    if (!plan_weights(W.data(), Cin, Cout, &plan, tail == TK_ADD_T || tail == TK_SE_TAIL)) { printf("plan_weights failed\n"); return 1; }
+    if (!plan_weights(W.data(), Cin, Cout, &plan, getenv("SGS_TC_NT") ? atoi(getenv("SGS_TC_NT")) : 0)) { printf("plan_weights failed\n"); return 1; }
     GemmTail T{}; T.kind = tail; T.a = 3.f; T.lo = 0.f; T.hi = 6.f; T.b = 6.f; T.t1 = dR; T.t2 = dR;
     if (!launch_conv1x1_tc(plan, dX, in_pitch, npix, dB, dO, out_pitch, T, 0)) { printf("launch failed\n"); return 1; }
     CK(cudaDeviceSynchronize());
