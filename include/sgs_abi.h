@@ -212,6 +212,7 @@ typedef struct sgs_lastframe_batch {      /* SearchByProjection(Frame&, const Fr
     const uint8_t* cur_mp_obs_in; /* may be NULL */
     int32_t* nmatches;            /* out [F] */
     uint64_t* ncand;              /* out [F] (accumulated): candidates examined, for the roofline byte count */
+    const uint8_t* frame_enable;  /* may be NULL; [F]: 0 = leave this frame untouched (the wide-window retry of src/Tracking.cc:927-931 only runs on the frames that need it) */
 } sgs_lastframe_batch;
 SGS_API int sgs_match_project_lastframe_batch_device(sgs_matcher* m, const sgs_lastframe_batch* args, int nframes, void* stream);
 
@@ -307,6 +308,7 @@ typedef struct sgs_poseopt_batch {
     float inv_level_sigma2[16];
     float* tcw_out; uint8_t* outlier; int32_t* ninliers;
     double* scratch_err; uint8_t* scratch_level;
+    const float* points2_xyz; int32_t id_base2, point2_cap;   /* may be NULL: mp_index values >= id_base2 address points2_xyz[f][id - id_base2] (the ids sgs_match_project_localmap* writes with id_base) */
 } sgs_poseopt_batch;
 SGS_API int sgs_pose_optimization_batch_device(const sgs_poseopt_batch* args, int nframes, void* stream);
 /* host-pointer variant, one frame (outlier flags of keypoints without a map point are left untouched = 0) */
@@ -585,6 +587,39 @@ SGS_API int sgs_memcpy_d2h(void* dst, const void* d_src, size_t bytes);
  * stream.  Stages: 0 pyramid, 1 FAST, 2 quadtree, 3 blur, 4 orientation+BRIEF.  ms_total5 accumulates over `ncalls`. */
 SGS_API int sgs_extractor_set_profiling(sgs_extractor* ex, int enable);
 SGS_API int sgs_extractor_stage_times(sgs_extractor* ex, double* ms_total5, int* ncalls);
+
+/* ------------------------------------------------------------------------------------
+ * The rest of the tracking thread's per-frame chain on the device, after sgs_tracker_track_device / sgs_tracker_track_lk / sgs_tracker_step
+ * (whose SearchByProjection(cur, last, th) matches are still on the device):
+ *   Tracking::TrackWithMotionModel, src/Tracking.cc:926-967 : < 20 matches -> the search again with 2 th on cleared matches (:927-931);
+ *       Optimizer::PoseOptimization (:937); outliers lose their map point (:940-957); nmatches / nmatchesMap;
+ *   Tracking::TrackLocalMap, :969-1000 with SearchLocalPoints, :1262-1312 : map points already matched in the frame (the discarded outliers
+ *       included, their mnLastFrameSeen is the frame's id) are left out; Frame::isInFrustum(pMP, 0.5) + MapPoint::PredictScale for the rest;
+ *       ORBmatcher(0.8).SearchByProjection(F, mvpLocalMapPoints, th_local); Optimizer::PoseOptimization again; mnMatchesInliers.
+ * UpdateLocalMap (which key frames / points form the local map) stays with the caller: the local map arrives as arrays, one list per frame.
+ * Ids written to f_mp: 0 .. point_cap-1 = the last-frame point (as after sgs_tracker_track_*), point_cap + j = local-map point j.
+ * stats [F][8]: 0 nmatches of the first search, 1 retried with 2 th (0/1), 2 nmatches after the retry, 3 nmatches after discarding outliers,
+ *   4 nmatchesMap, 5 nToMatch (local-map points in the frustum), 6 matches added by the local search, 7 mnMatchesInliers.
+ * ------------------------------------------------------------------------------------ */
+typedef struct sgs_posechain_batch {
+    /* the arguments sgs_tracker_track_device took (needed for the retry and as the points of the first PoseOptimization) */
+    const float* last_xyz; const uint8_t* last_desc; const uint8_t* last_flags; const int32_t* last_octave; const float* last_angle; const int32_t* last_n;
+    const float* tcw_cur; const float* tcw_last; float th; int32_t mono, check_orientation;
+    const int32_t* last_local_id;     /* [F][point_cap]: index of last-frame point i in this frame's local-map list, -1 = not in it (may be NULL = none is) */
+    /* local map of every frame: [F][mp_cap] */
+    const float* mp_xyz; const float* mp_normal; const float* mp_min_dist; const float* mp_max_dist; const uint8_t* mp_desc;
+    const uint8_t* mp_valid;          /* !isBad() */
+    const uint8_t* mp_obs;            /* Observations() > 0 */
+    const int32_t* mp_n; int32_t mp_cap;
+    float th_local, nnratio_local;    /* 3 (RGB-D; 1 otherwise; 5 after a relocalisation) and 0.8, src/Tracking.cc:1303-1310 */
+    float inv_level_sigma2[16];       /* Frame::mvInvLevelSigma2 */
+    /* outputs (device) */
+    float* tcw_motion; float* tcw_final;      /* [F][16] pose after TrackWithMotionModel / after TrackLocalMap */
+    int32_t* f_mp;                    /* [F][cap] final mvpMapPoints as ids (see above) */
+    uint8_t* outlier;                 /* [F][cap] mvbOutlier after the second PoseOptimization */
+    int32_t* stats;                   /* [F][8] */
+} sgs_posechain_batch;
+SGS_API int sgs_tracker_pose_chain_device(sgs_tracker* t, const sgs_posechain_batch* args, int nframes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------------------
  * Object detector: Detector2D (src/Detector2D.cc:16-89, include/Detector2D.h:29-80) -- ncnn forward of the MobileNetV3-SSDLite graph

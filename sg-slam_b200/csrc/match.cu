@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_lastframe_kernel(const __
     __shared__ int s_nmatch, s_nevent;
     __shared__ float s_pose[20];     // Rcw (9), tcw (3), forward/backward flags, Ow (3)
     const int f = blockIdx.x;
+    if (A.frame_enable && !A.frame_enable[f]) return;      // block-uniform
     const int n = min(A.cur_n[f], A.cur_cap);
     const int nlast = min(A.last_n[f], A.last_cap);
     FrameSmem s;

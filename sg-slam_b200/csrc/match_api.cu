@@ -90,6 +90,7 @@ SGS_API int sgs_match_project_lastframe_batch_device(sgs_matcher* m, const sgs_l
     A.tcw_cur = a->tcw_cur; A.tcw_last = a->tcw_last; A.th = a->th; A.mono = a->mono; A.check_ori = a->check_orientation;
     A.cur_mp = a->cur_mp; A.cur_mp_obs_in = a->cur_mp_obs_in; A.nmatches = a->nmatches; A.ncand = (unsigned long long*)a->ncand;
     A.kf_mode = 0; A.orb_dist = 100; A.log_sf = 0.f; A.kf_min_dist = A.kf_max_dist = nullptr;      // TH_HIGH, src/ORBmatcher.cc:37
+    A.frame_enable = a->frame_enable;
     A.pre = m->d_pre; A.events = m->d_events;
     return launch_match_lastframe(A, nframes, (cudaStream_t)stream);
 }
@@ -129,6 +130,7 @@ SGS_API int sgs_match_project_keyframe_batch_device(sgs_matcher* m, const sgs_ke
     A.tcw_cur = a->tcw_cur; A.tcw_last = nullptr; A.th = a->th; A.mono = 1; A.check_ori = a->check_orientation;
     A.cur_mp = a->cur_mp; A.cur_mp_obs_in = nullptr; A.nmatches = a->nmatches; A.ncand = (unsigned long long*)a->ncand;
     A.kf_mode = 1; A.orb_dist = a->orb_dist; A.log_sf = logf(a->cam.scale_factors[1]); A.kf_min_dist = a->kf_min_dist; A.kf_max_dist = a->kf_max_dist;
+    A.frame_enable = nullptr;
     A.pre = m->d_pre; A.events = m->d_events;
     return launch_match_lastframe(A, nframes, (cudaStream_t)stream);
 }

@@ -41,6 +41,7 @@ struct LastFrameArgs {
     int32_t kf_mode, orb_dist; float log_sf; const float* kf_min_dist; const float* kf_max_dist;
     // in/out
     int32_t* cur_mp; const uint8_t* cur_mp_obs_in; int32_t* nmatches; unsigned long long* ncand;
+    const uint8_t* frame_enable;   // optional [nframes]: frames with 0 are left untouched (the wide-window retry of Tracking.cc:927-931 runs on the frames that need it)
     // scratch [nframes][last_cap]
     PointPre* pre; int32_t* events;
 };

@@ -109,6 +109,7 @@ struct PoArgs {
     float fx, fy, cx, cy, bf;
     const float* tcw_in; const sgs_keypoint* kps; const float* uright; const int32_t* n; int cap;
     const uint8_t* has_mp; const int32_t* mp_index; const float* points_xyz; int point_cap;
+    const float* points2_xyz; int id_base2, point2_cap;      // optional second point array (local-map points of the chained call)
     float inv_sigma2[16];
     float* tcw_out; uint8_t* outlier; int32_t* ninliers;
     double* err;          // scratch [F][cap][3]: the error vector each edge carries between evaluations
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(const PoArgs A) {
 
     auto has = [&](int i) -> bool { return A.mp_index ? A.mp_index[ko + i] >= 0 : A.has_mp[ko + i] != 0; };
     auto world = [&](int i, double* X) {
-        const float* p = A.points_xyz + 3 * ((int64_t)f * A.point_cap + (A.mp_index ? A.mp_index[ko + i] : i));
+        const int id = A.mp_index ? A.mp_index[ko + i] : i;
+        const float* p = (A.points2_xyz && id >= A.id_base2) ? A.points2_xyz + 3 * ((int64_t)f * A.point2_cap + (id - A.id_base2)) : A.points_xyz + 3 * ((int64_t)f * A.point_cap + id);
         X[0] = p[0]; X[1] = p[1]; X[2] = p[2];
     };
     // edge error at the current estimate (EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose::computeError)
@@ -328,6 +330,7 @@ SGS_API int sgs_pose_optimization_batch_device(const sgs_poseopt_batch* a, int n
     A.fx = a->cam.fx; A.fy = a->cam.fy; A.cx = a->cam.cx; A.cy = a->cam.cy; A.bf = a->cam.bf;
     A.tcw_in = a->tcw_in; A.kps = a->kps; A.uright = a->uright; A.n = a->n; A.cap = a->cap;
     A.has_mp = a->has_mp; A.mp_index = a->mp_index; A.points_xyz = a->points_xyz; A.point_cap = a->mp_index ? a->point_cap : a->cap;
+    A.points2_xyz = a->mp_index ? a->points2_xyz : nullptr; A.id_base2 = a->id_base2; A.point2_cap = a->point2_cap;
     for (int l = 0; l < 16; ++l) A.inv_sigma2[l] = a->inv_level_sigma2[l];
     A.tcw_out = a->tcw_out; A.outlier = a->outlier; A.ninliers = a->ninliers; A.err = a->scratch_err; A.level = a->scratch_level;
     pose_opt_kernel<<<nframes, kPoThreads, 0, (cudaStream_t)stream>>>(A);
@@ -364,6 +367,7 @@ SGS_API int sgs_pose_optimization(const sgs_camera* cam, const float* tcw_in, in
         b.cam = *cam; b.tcw_in = d_Tin; b.kps = d_k; b.uright = d_ur; b.n = d_n; b.cap = n; b.has_mp = d_has; b.mp_index = nullptr; b.points_xyz = d_xyz; b.point_cap = n;
         for (int l = 0; l < 16; ++l) b.inv_level_sigma2[l] = inv_level_sigma2[l];
         b.tcw_out = d_Tout; b.outlier = d_out; b.ninliers = d_nin; b.scratch_err = d_err; b.scratch_level = d_lvl;
+        b.points2_xyz = nullptr; b.id_base2 = 0; b.point2_cap = 0;
         rc = sgs_pose_optimization_batch_device(&b, 1, nullptr);
         if (rc == SGS_OK) {
             e = cudaMemcpy(tcw_out, d_Tout, 64, cudaMemcpyDeviceToHost);

@@ -35,6 +35,13 @@ struct sgs_tracker {
     // detector inside the step (sgs_tracker_step / sgs_tracker_detect_device): RGB staging, its own stream, the join events
     uint8_t* d_rgb = nullptr; size_t d_rgb_cap = 0; int32_t* d_det_status = nullptr;
     cudaStream_t det_st = nullptr; cudaEvent_t det_ev = nullptr; cudaEvent_t ex_ev = nullptr;
+    // sgs_tracker_pose_chain_device: scratch sized on first use for (max_batch, mp_cap)
+    int chain_mp_cap = 0;
+    sgs_matcher* mt_local = nullptr;
+    uint8_t* d_enable = nullptr; int32_t* d_nm2 = nullptr; uint8_t* d_obs = nullptr; uint8_t* d_seen = nullptr; int32_t* d_ninl = nullptr; int32_t* d_nml = nullptr;
+    double* d_po_err = nullptr; uint8_t* d_po_level = nullptr;
+    uint8_t* d_inview = nullptr; float* d_projx = nullptr; float* d_projy = nullptr; float* d_projxr = nullptr; int32_t* d_level = nullptr; float* d_viewcos = nullptr;
+    unsigned long long* d_ncand2 = nullptr;
 };
 
 namespace sgs {
@@ -65,6 +72,90 @@ __global__ void compact_uright_kernel(const float* __restrict__ ur_in, const uin
     }
     for (int i = threadIdx.x; i < cap; i += 256) mp[base + i] = -1;   // Tracking.cc:916 clears mvpMapPoints before the search
 }
+// ---- glue of sgs_tracker_pose_chain_device (Tracking::TrackWithMotionModel / TrackLocalMap between the matcher and optimiser calls) ----------
+// src/Tracking.cc:927-931: fewer than 20 matches -> clear the frame's matches and search again with 2 th
+__global__ void chain_retry_kernel(const int32_t* __restrict__ nm, int cap, int32_t* __restrict__ mp, uint8_t* __restrict__ enable, int32_t* __restrict__ stats) {
+    const int f = blockIdx.x;
+    const bool retry = nm[f] < 20;
+    if (threadIdx.x == 0) { enable[f] = retry ? 1 : 0; stats[8 * f] = nm[f]; stats[8 * f + 1] = retry ? 1 : 0; }
+    if (retry) for (int i = threadIdx.x; i < cap; i += blockDim.x) mp[(int64_t)f * cap + i] = -1;
+}
+__global__ void chain_merge_counts_kernel(const uint8_t* __restrict__ enable, const int32_t* __restrict__ nm2, int32_t* __restrict__ nm, int32_t* __restrict__ stats, int nframes) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    if (enable[f]) nm[f] = nm2[f];
+    stats[8 * f + 2] = nm[f];
+}
+// :940-957 discard the outliers of the first PoseOptimization; SearchLocalPoints' first loop (:1265-1281): every map point matched in the frame --
+// the discarded ones too, their mnLastFrameSeen was set at :951 -- is marked as seen, bad ones lose their slot (last_flags bit 2 = isBad()).
+__global__ void __launch_bounds__(256) chain_discard_kernel(const int32_t* __restrict__ n_cur, int cap, int point_cap, const uint8_t* __restrict__ last_flags,
+                                                            const int32_t* __restrict__ last_local_id, int mp_cap, int32_t* __restrict__ mp, uint8_t* __restrict__ outlier,
+                                                            uint8_t* __restrict__ obs, uint8_t* __restrict__ seen, const int32_t* __restrict__ nm, int32_t* __restrict__ stats) {
+    __shared__ int s_drop, s_map;
+    const int f = blockIdx.x;
+    const int n = min(n_cur[f], cap);
+    if (threadIdx.x == 0) { s_drop = 0; s_map = 0; }
+    __syncthreads();
+    int drop = 0, nmap = 0;
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+        const int64_t k = (int64_t)f * cap + i;
+        int id = i < n ? mp[k] : -1;
+        uint8_t ob = 0;
+        if (id >= 0) {
+            const uint8_t fl = last_flags[(int64_t)f * point_cap + id];
+            const int lid = last_local_id ? last_local_id[(int64_t)f * point_cap + id] : -1;
+            if (lid >= 0 && lid < mp_cap) seen[(int64_t)f * mp_cap + lid] = 1;
+            if (outlier[k]) { id = -1; outlier[k] = 0; ++drop; }
+            else {
+                if (fl & 2) ++nmap;
+                if (fl & 4) id = -1;                       // isBad(): removed by SearchLocalPoints, after the counts of TrackWithMotionModel
+                else ob = (fl >> 1) & 1;
+            }
+        }
+        if (i < n) mp[k] = id;
+        obs[k] = ob;
+    }
+    atomicAdd(&s_drop, drop); atomicAdd(&s_map, nmap);
+    __syncthreads();
+    if (threadIdx.x == 0) { stats[8 * f + 3] = nm[f] - s_drop; stats[8 * f + 4] = s_map; }
+}
+// SearchLocalPoints' second loop (:1286-1300): points seen in this frame or bad are skipped before isInFrustum; nToMatch
+__global__ void __launch_bounds__(256) chain_mask_kernel(const int32_t* __restrict__ mp_n, int mp_cap, const uint8_t* __restrict__ mp_valid, const uint8_t* __restrict__ seen,
+                                                         uint8_t* __restrict__ inview, int32_t* __restrict__ stats) {
+    __shared__ int s_cnt;
+    const int f = blockIdx.x;
+    const int n = min(mp_n[f], mp_cap);
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int j = threadIdx.x; j < mp_cap; j += blockDim.x) {
+        const int64_t k = (int64_t)f * mp_cap + j;
+        const uint8_t v = (j < n && inview[k] && mp_valid[k] && !seen[k]) ? 1 : 0;
+        inview[k] = v; c += v;
+    }
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) stats[8 * f + 5] = s_cnt;
+}
+// :982-996 mnMatchesInliers (mbOnlyTracking == false): map point && !outlier && Observations() > 0
+__global__ void __launch_bounds__(256) chain_final_kernel(const int32_t* __restrict__ n_cur, int cap, const int32_t* __restrict__ mp, const uint8_t* __restrict__ outlier,
+                                                          const uint8_t* __restrict__ obs, const int32_t* __restrict__ nml, int32_t* __restrict__ f_mp, int32_t* __restrict__ stats) {
+    __shared__ int s_cnt;
+    const int f = blockIdx.x;
+    const int n = min(n_cur[f], cap);
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+        const int64_t k = (int64_t)f * cap + i;
+        const int id = i < n ? mp[k] : -1;
+        f_mp[k] = id;
+        if (id >= 0 && !outlier[k] && obs[k]) ++c;
+    }
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) { stats[8 * f + 6] = nml[f]; stats[8 * f + 7] = s_cnt; }
+}
 }  // namespace sgs
 
 using namespace sgs;
@@ -94,6 +185,10 @@ SGS_API void sgs_tracker_destroy(sgs_tracker* t) {
     if (t->det_st) cudaStreamDestroy(t->det_st);
     if (t->det_ev) cudaEventDestroy(t->det_ev);
     if (t->ex_ev) cudaEventDestroy(t->ex_ev);
+    if (t->mt_local) sgs_matcher_destroy(t->mt_local);
+    void* cptrs[] = {t->d_enable, t->d_nm2, t->d_obs, t->d_seen, t->d_ninl, t->d_nml, t->d_po_err, t->d_po_level, t->d_inview, t->d_projx, t->d_projy, t->d_projxr,
+                     t->d_level, t->d_viewcos, t->d_ncand2};
+    for (void* p : cptrs) if (p) cudaFree(p);
     delete t;
 }
 
@@ -331,6 +426,88 @@ SGS_API int sgs_tracker_track_lk(sgs_tracker* t, int nframes, const int32_t* pre
 // joins it before the rejection): the person boxes land in the tracker's own box arrays, in the layout the F estimate and the rejection take
 // when called with boxes == NULL.  d_rgb: device frames (interleaved 8-bit RGB).  Enqueued on `stream` (NULL: the tracker's detector stream, which
 // the next sgs_tracker_fundamental_device / _track_device call on the tracker's stream is NOT ordered after -- use sgs_tracker_step for that).
+SGS_API int sgs_tracker_pose_chain_device(sgs_tracker* t, const sgs_posechain_batch* a, int nframes, void* stream) {
+    if (!t || !a) return bad("sgs_tracker_pose_chain_device: NULL");
+    if (!a->last_xyz || !a->last_desc || !a->last_flags || !a->last_octave || !a->last_angle || !a->last_n || !a->tcw_cur || !a->tcw_last || !a->mp_xyz || !a->mp_normal ||
+        !a->mp_min_dist || !a->mp_max_dist || !a->mp_desc || !a->mp_valid || !a->mp_obs || !a->mp_n || !a->tcw_motion || !a->tcw_final || !a->f_mp || !a->outlier || !a->stats)
+        return bad("sgs_tracker_pose_chain_device: NULL array");
+    if (nframes < 1 || nframes > t->last_nframes) return bad("sgs_tracker_pose_chain_device: nframes exceeds the last track call");
+    if (a->mp_cap < 1) return bad("sgs_tracker_pose_chain_device: mp_cap < 1");
+    SGS_CUDA_TRY(cudaSetDevice(t->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : t->st;
+    const size_t B = t->max_batch, K = t->cap, M = a->mp_cap;
+    if (t->chain_mp_cap < a->mp_cap) {                       // scratch for this local-map capacity (first call, or a larger map)
+        if (t->mt_local) { sgs_matcher_destroy(t->mt_local); t->mt_local = nullptr; }
+        void** ps[] = {(void**)&t->d_enable, (void**)&t->d_nm2, (void**)&t->d_obs, (void**)&t->d_seen, (void**)&t->d_ninl, (void**)&t->d_nml, (void**)&t->d_po_err,
+                       (void**)&t->d_po_level, (void**)&t->d_inview, (void**)&t->d_projx, (void**)&t->d_projy, (void**)&t->d_projxr, (void**)&t->d_level, (void**)&t->d_viewcos,
+                       (void**)&t->d_ncand2};
+        for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
+        t->chain_mp_cap = 0;
+        int rc = sgs_matcher_create(t->device, t->max_batch, t->cap, a->mp_cap, &t->mt_local);
+        if (rc != SGS_OK) return rc;
+        cudaError_t e = cudaSuccess;
+#define A(call) if (e == cudaSuccess) e = (call)
+        A(dalloc(&t->d_enable, B)); A(dalloc(&t->d_nm2, B)); A(dalloc(&t->d_obs, B * K)); A(dalloc(&t->d_seen, B * M)); A(dalloc(&t->d_ninl, B)); A(dalloc(&t->d_nml, B));
+        A(dalloc(&t->d_po_err, B * K * 3)); A(dalloc(&t->d_po_level, B * K)); A(dalloc(&t->d_inview, B * M)); A(dalloc(&t->d_projx, B * M)); A(dalloc(&t->d_projy, B * M));
+        A(dalloc(&t->d_projxr, B * M)); A(dalloc(&t->d_level, B * M)); A(dalloc(&t->d_viewcos, B * M)); A(dalloc(&t->d_ncand2, B));
+#undef A
+        if (e != cudaSuccess) { set_error("sgs_tracker_pose_chain_device: %s", cudaGetErrorString(e)); return SGS_ERR_CUDA; }
+        t->chain_mp_cap = a->mp_cap;
+    }
+    const int F = nframes, cap = t->cap;
+    // 1. the wide-window retry of the frames with fewer than 20 matches
+    chain_retry_kernel<<<F, 256, 0, st>>>(t->d_nm, cap, t->d_mp, t->d_enable, a->stats);
+    sgs_lastframe_batch lf;
+    std::memset(&lf, 0, sizeof lf);
+    lf.cam = t->cam;
+    lf.cur_kps = t->d_kps2; lf.cur_desc = t->d_desc2; lf.cur_uright = t->d_uright2; lf.cur_n = t->d_cnt2;
+    lf.last_xyz = a->last_xyz; lf.last_desc = a->last_desc; lf.last_flags = a->last_flags; lf.last_octave = a->last_octave; lf.last_angle = a->last_angle; lf.last_n = a->last_n;
+    lf.tcw_cur = a->tcw_cur; lf.tcw_last = a->tcw_last; lf.th = 2.f * a->th; lf.mono = a->mono; lf.check_orientation = a->check_orientation;
+    lf.cur_mp = t->d_mp; lf.nmatches = t->d_nm2; lf.ncand = (uint64_t*)t->d_ncand2; lf.frame_enable = t->d_enable;
+    SGS_CUDA_TRY(cudaMemsetAsync(t->d_ncand2, 0, (size_t)F * 8, st));
+    SGS_CUDA_TRY(cudaMemsetAsync(t->d_nm2, 0, (size_t)F * 4, st));
+    int rc = sgs_match_project_lastframe_batch_device(t->mt, &lf, F, st);
+    if (rc != SGS_OK) return rc;
+    chain_merge_counts_kernel<<<(F + 127) / 128, 128, 0, st>>>(t->d_enable, t->d_nm2, t->d_nm, a->stats, F);
+    // 2. PoseOptimization on the last-frame matches
+    SGS_CUDA_TRY(cudaMemsetAsync(a->outlier, 0, (size_t)F * cap, st));
+    sgs_poseopt_batch po;
+    std::memset(&po, 0, sizeof po);
+    po.cam = t->cam; po.tcw_in = a->tcw_cur; po.kps = t->d_kps2; po.uright = t->d_uright2; po.n = t->d_cnt2; po.cap = cap;
+    po.mp_index = t->d_mp; po.points_xyz = a->last_xyz; po.point_cap = t->point_cap;
+    for (int l = 0; l < 16; ++l) po.inv_level_sigma2[l] = a->inv_level_sigma2[l];
+    po.tcw_out = a->tcw_motion; po.outlier = a->outlier; po.ninliers = t->d_ninl; po.scratch_err = t->d_po_err; po.scratch_level = t->d_po_level;
+    rc = sgs_pose_optimization_batch_device(&po, F, st);
+    if (rc != SGS_OK) return rc;
+    // 3. discard outliers, mark the map points seen in the frame
+    SGS_CUDA_TRY(cudaMemsetAsync(t->d_seen, 0, (size_t)F * M, st));
+    chain_discard_kernel<<<F, 256, 0, st>>>(t->d_cnt2, cap, t->point_cap, a->last_flags, a->last_local_id, a->mp_cap, t->d_mp, a->outlier, t->d_obs, t->d_seen, t->d_nm, a->stats);
+    // 4. SearchLocalPoints: frustum test with the new pose, scale prediction, projection search
+    sgs_frustum_batch fr;
+    std::memset(&fr, 0, sizeof fr);
+    fr.cam = t->cam; fr.tcw = a->tcw_motion; fr.mp_xyz = a->mp_xyz; fr.mp_normal = a->mp_normal; fr.mp_min_dist = a->mp_min_dist; fr.mp_max_dist = a->mp_max_dist;
+    fr.mp_n = a->mp_n; fr.point_cap = a->mp_cap; fr.viewing_cos_limit = 0.5f;
+    fr.mp_inview = t->d_inview; fr.proj_x = t->d_projx; fr.proj_y = t->d_projy; fr.proj_xr = t->d_projxr; fr.level = t->d_level; fr.view_cos = t->d_viewcos;
+    rc = sgs_frustum_batch_device(&fr, F, st);
+    if (rc != SGS_OK) return rc;
+    chain_mask_kernel<<<F, 256, 0, st>>>(a->mp_n, a->mp_cap, a->mp_valid, t->d_seen, t->d_inview, a->stats);
+    sgs_localmap_batch lm;
+    std::memset(&lm, 0, sizeof lm);
+    lm.cam = t->cam; lm.cur_kps = t->d_kps2; lm.cur_desc = t->d_desc2; lm.cur_uright = t->d_uright2; lm.cur_n = t->d_cnt2;
+    lm.mp_inview = t->d_inview; lm.proj_x = t->d_projx; lm.proj_y = t->d_projy; lm.proj_xr = t->d_projxr; lm.level = t->d_level; lm.view_cos = t->d_viewcos;
+    lm.mp_desc = a->mp_desc; lm.mp_obs = a->mp_obs; lm.mp_n = a->mp_n; lm.th = a->th_local; lm.nnratio = a->nnratio_local; lm.id_base = t->point_cap;
+    lm.f_mp = t->d_mp; lm.f_mp_obs = t->d_obs; lm.nmatches = t->d_nml; lm.ncand = (uint64_t*)t->d_ncand2;
+    rc = sgs_match_project_localmap_batch_device(t->mt_local, &lm, F, st);
+    if (rc != SGS_OK) return rc;
+    // 5. PoseOptimization on last-frame + local-map matches, inlier count
+    po.tcw_in = a->tcw_motion; po.tcw_out = a->tcw_final; po.points2_xyz = a->mp_xyz; po.id_base2 = t->point_cap; po.point2_cap = a->mp_cap;
+    rc = sgs_pose_optimization_batch_device(&po, F, st);
+    if (rc != SGS_OK) return rc;
+    chain_final_kernel<<<F, 256, 0, st>>>(t->d_cnt2, cap, t->d_mp, a->outlier, t->d_obs, t->d_nml, a->f_mp, a->stats);
+    SGS_CUDA_TRY(cudaGetLastError());
+    return SGS_OK;
+}
+
 SGS_API int sgs_tracker_detect_device(sgs_tracker* t, sgs_detector* det, const uint8_t* d_rgb, int64_t frame_stride, int pitch, int width, int height, int nframes,
                                       void* stream) {
     if (!t || !det || !d_rgb) return bad("sgs_tracker_detect_device: NULL argument");

@@ -55,13 +55,24 @@ class LastFrameBatch(C.Structure):
                 ('last_xyz', C.c_void_p), ('last_desc', C.c_void_p), ('last_flags', C.c_void_p), ('last_octave', C.c_void_p),
                 ('last_angle', C.c_void_p), ('last_n', C.c_void_p), ('tcw_cur', C.c_void_p), ('tcw_last', C.c_void_p),
                 ('th', C.c_float), ('mono', C.c_int32), ('check_orientation', C.c_int32),
-                ('cur_mp', C.c_void_p), ('cur_mp_obs_in', C.c_void_p), ('nmatches', C.c_void_p), ('ncand', C.c_void_p)]
+                ('cur_mp', C.c_void_p), ('cur_mp_obs_in', C.c_void_p), ('nmatches', C.c_void_p), ('ncand', C.c_void_p), ('frame_enable', C.c_void_p)]
 
 
 class PoseOptBatch(C.Structure):
     _fields_ = [('cam', Camera), ('tcw_in', C.c_void_p), ('kps', C.c_void_p), ('uright', C.c_void_p), ('n', C.c_void_p), ('cap', C.c_int32),
                 ('has_mp', C.c_void_p), ('mp_index', C.c_void_p), ('points_xyz', C.c_void_p), ('point_cap', C.c_int32), ('inv_level_sigma2', C.c_float * 16),
-                ('tcw_out', C.c_void_p), ('outlier', C.c_void_p), ('ninliers', C.c_void_p), ('scratch_err', C.c_void_p), ('scratch_level', C.c_void_p)]
+                ('tcw_out', C.c_void_p), ('outlier', C.c_void_p), ('ninliers', C.c_void_p), ('scratch_err', C.c_void_p), ('scratch_level', C.c_void_p),
+                ('points2_xyz', C.c_void_p), ('id_base2', C.c_int32), ('point2_cap', C.c_int32)]
+
+
+class PoseChainBatch(C.Structure):          # sgs_posechain_batch
+    _fields_ = [('last_xyz', C.c_void_p), ('last_desc', C.c_void_p), ('last_flags', C.c_void_p), ('last_octave', C.c_void_p), ('last_angle', C.c_void_p),
+                ('last_n', C.c_void_p), ('tcw_cur', C.c_void_p), ('tcw_last', C.c_void_p), ('th', C.c_float), ('mono', C.c_int32), ('check_orientation', C.c_int32),
+                ('last_local_id', C.c_void_p),
+                ('mp_xyz', C.c_void_p), ('mp_normal', C.c_void_p), ('mp_min_dist', C.c_void_p), ('mp_max_dist', C.c_void_p), ('mp_desc', C.c_void_p),
+                ('mp_valid', C.c_void_p), ('mp_obs', C.c_void_p), ('mp_n', C.c_void_p), ('mp_cap', C.c_int32),
+                ('th_local', C.c_float), ('nnratio_local', C.c_float), ('inv_level_sigma2', C.c_float * 16),
+                ('tcw_motion', C.c_void_p), ('tcw_final', C.c_void_p), ('f_mp', C.c_void_p), ('outlier', C.c_void_p), ('stats', C.c_void_p)]
 
 
 class FuseBatch(C.Structure):
@@ -102,6 +113,7 @@ class LocalMapBatch(C.Structure):
 
 
 ABI_SYMBOLS = [
+    'sgs_tracker_pose_chain_device',
     'sgs_abi_version', 'sgs_last_error', 'sgs_device_count', 'sgs_settings_load',
     'sgs_extractor_create', 'sgs_extractor_destroy', 'sgs_extractor_tables', 'sgs_extractor_max_keypoints', 'sgs_extractor_level_info',
     'sgs_extract', 'sgs_extract_batch', 'sgs_extract_batch_device', 'sgs_extractor_results_device', 'sgs_extractor_fetch', 'sgs_extractor_read_level',
