@@ -563,8 +563,9 @@ def main():
     B.check(L.sgs_lk_stage_times(lkh, ms2, C.byref(ncalls)))
     lk_pyr_ms, lk_track_ms = ms2[0] / max(1, ncalls.value), ms2[1] / max(1, ncalls.value)
     B.check(L.sgs_lk_set_profiling(lkh, 0))
-    det_ms = None
+    det_ms = None; det_fam = None; det_kinds = None
     if use_det:
+        det.set_profiling(1)                                  # CUDA events around every kernel of the call, on the launching stream
         with torch.cuda.stream(st_det):
             dev_detect()
             ed0, ed1 = torch.cuda.Event(True), torch.cuda.Event(True)
@@ -574,6 +575,54 @@ def main():
             ed1.record(st_det)
         torch.cuda.synchronize()
         det_ms = ed0.elapsed_time(ed1) / 3
+        kms, kcalls = det.kernel_times()
+        det.set_profiling(0)
+        det_fam, det_kinds = detector_gemm_table(det, kms, kcalls, NB)
+
+    # ---- the rest of the tracking thread's chain (TrackWithMotionModel after the search + TrackLocalMap), timed beside the step ---------------------
+    chain_info = None
+    try:
+        rngc = np.random.default_rng(17)
+        mcap = (pcap // 2 + cap // 3 + 127) // 64 * 64
+        with torch.cuda.stream(st):
+            dev_step(use_det)
+        torch.cuda.synchronize()
+        pk, pd, pu, pc_, pm, pn, pnc = (C.c_void_p() for _ in range(7))
+        B.check(L.sgs_tracker_results_device(trk.h, C.byref(pk), C.byref(pd), C.byref(pu), C.byref(pc_), C.byref(pm), C.byref(pn), C.byref(pnc)))
+        nsamp = min(NB, 16)                                   # local maps are built on the host from a few frames and tiled over the batch
+        ck = B.memcpy_d2h(np.zeros((NB, cap), B.KP_DTYPE), pk.value); cd = B.memcpy_d2h(np.zeros((NB, cap, 32), np.uint8), pd.value)
+        cc = B.memcpy_d2h(np.zeros(NB, np.int32), pc_.value)
+        lms = [make_local_map(f, ck[f], cd[f], int(cc[f]), ti, mcap, camd, sf, rngc, W, H) for f in range(nsamp)]
+        tile = lambda k, dt: torch.from_numpy(np.ascontiguousarray(np.stack([lms[f % nsamp][k] for f in range(NB)]).astype(dt))).cuda()
+        cm = dict(lid=tile('lid', np.int32), xyz=tile('xyz', np.float32), nrm=tile('nrm', np.float32), mn=tile('mn', np.float32), mx=tile('mx', np.float32),
+                  dsc=tile('dsc', np.uint8), valid=tile('valid', np.uint8), obs=tile('obs', np.uint8),
+                  n=torch.from_numpy(np.array([lms[f % nsamp]['n'] for f in range(NB)], np.int32)).cuda())
+        co = dict(T1=torch.zeros((NB, 16), device='cuda'), T2=torch.zeros((NB, 16), device='cuda'), mp=torch.zeros((NB, cap), dtype=torch.int32, device='cuda'),
+                  outl=torch.zeros((NB, cap), dtype=torch.uint8, device='cuda'), st=torch.zeros((NB, 8), dtype=torch.int32, device='cuda'))
+        pa = B.PoseChainBatch()
+        pa.last_xyz, pa.last_desc, pa.last_flags, pa.last_octave, pa.last_angle, pa.last_n = [dv[k].data_ptr() for k in ('lxyz', 'ldesc', 'lflags', 'loct', 'lang', 'ln')]
+        pa.tcw_cur = pa.tcw_last = dv['T'].data_ptr(); pa.th, pa.mono, pa.check_orientation, pa.last_local_id = TH, 0, 1, cm['lid'].data_ptr()
+        pa.mp_xyz, pa.mp_normal, pa.mp_min_dist, pa.mp_max_dist, pa.mp_desc, pa.mp_valid, pa.mp_obs, pa.mp_n, pa.mp_cap = [cm[k].data_ptr() for k in ('xyz', 'nrm', 'mn', 'mx', 'dsc', 'valid', 'obs', 'n')] + [mcap]
+        pa.th_local, pa.nnratio_local = 3.0, 0.8
+        for l in range(16): pa.inv_level_sigma2[l] = float(1.0 / (sf[l] * sf[l])) if l < len(sf) else 0.0
+        pa.tcw_motion, pa.tcw_final, pa.f_mp, pa.outlier, pa.stats = co['T1'].data_ptr(), co['T2'].data_ptr(), co['mp'].data_ptr(), co['outl'].data_ptr(), co['st'].data_ptr()
+
+        def dev_chain():
+            B.check(L.sgs_tracker_pose_chain_device(trk.h, C.byref(pa), NB, v(S)))
+        with torch.cuda.stream(st):
+            dev_track(use_det); dev_chain()                     # warm-up (allocates the chain's scratch)
+            ec = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            for i in range(3):
+                dev_track(use_det); ec[2 * i].record(st); dev_chain(); ec[2 * i + 1].record(st)
+        torch.cuda.synchronize()
+        chain_ms = sum(ec[2 * i].elapsed_time(ec[2 * i + 1]) for i in range(3)) / 3
+        stc = co['st'].cpu().numpy()
+        chain_info = {'call': 'sgs_tracker_pose_chain_device (2 th retry, PoseOptimization, outlier discard, SearchLocalPoints: frustum + scale + projection search, PoseOptimization, inlier count)',
+                      'ms_per_step': chain_ms, 'frames_per_s': NB / chain_ms * 1e3, 'local_map_points_per_frame': float(np.mean([m['n'] for m in lms])),
+                      'mean_matches_last_frame': float(stc[:, 2].mean()), 'mean_in_frustum': float(stc[:, 5].mean()), 'mean_matches_added': float(stc[:, 6].mean()),
+                      'mean_inliers': float(stc[:, 7].mean()), 'not_in_value': 'timed beside the step: BASELINE metric = extract + match + dyn-reject'}
+    except Exception as ex_:
+        log('[bench] pose chain stage skipped: %r' % (ex_,))
 
     # ---- e2e leg: host buffers through the C ABI (sgs_tracker_step / sgs_tracker_extract + _track_lk), copies inside the timed region ----
     def host_ptrs(hpi, out, sl=slice(None)):
@@ -667,16 +716,34 @@ def main():
     dom_bytes = alg[dom] * NB
     achieved = dom_bytes / (all_ms[dom] * 1e-3) / 1e9
     step_alg = (ab['extract'] + ab['lk_pyr'] + ab['lk_track'] + ab['fm'] + ab['track']) * NB
-    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
-                'traffic': None, 'traffic_note': 'not measured in this run: the ncu --set full captures of the step kernels are under profiles/',
-                'peak_kind': ('measured copy bandwidth (MEASURED_PEAKS.json)' if peak_kind == 'measured' else 'fallback 6650 GB/s'),
-                'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': all_ms[dom],
-                'stage_ms': {k: round(x, 4) for k, x in all_ms.items()}, 'extract_ms': extract_ms, 'lk_ms': lk_ms, 'fundamental_ms': fm_ms, 'dynreject_match_ms': track_ms,
-                'tracker_step_ms': trk_ms, 'detector_ms': det_ms,
-                'per_kernel_alg_gbs': {k: round(alg[k] * NB / (all_ms[k] * 1e-3) / 1e9, 1) for k in all_ms},
-                'extract_alg_gbs': ab['extract'] * NB / (extract_ms * 1e-3) / 1e9, 'extract_frac_of_hbm': ab['extract'] * NB / (extract_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                'tracker_step_frac_of_hbm': step_alg / (trk_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                'note': 'the tracker kernels are instruction-issue / latency bound (integer fixed-point OpenCV semantics): the HBM fraction is reported as asked'}
+    peak_note = 'measured copy bandwidth (MEASURED_PEAKS.json)' if peak_kind == 'measured' else 'fallback 6650 GB/s'
+    tracker_dom = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
+                   'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': all_ms[dom],
+                   'note': 'largest single launch of the step; instruction-issue bound (exact OpenCV fixed-point arithmetic), the HBM fraction is reported as asked'}
+    common = {'stage_ms': {k: round(x, 4) for k, x in all_ms.items()}, 'extract_ms': extract_ms, 'lk_ms': lk_ms, 'fundamental_ms': fm_ms, 'dynreject_match_ms': track_ms,
+              'tracker_step_ms': trk_ms, 'detector_ms': det_ms,
+              'per_kernel_alg_gbs': {k: round(alg[k] * NB / (all_ms[k] * 1e-3) / 1e9, 1) for k in all_ms},
+              'extract_alg_gbs': ab['extract'] * NB / (extract_ms * 1e-3) / 1e9, 'extract_frac_of_hbm': ab['extract'] * NB / (extract_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+              'tracker_step_frac_of_hbm': step_alg / (trk_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+              'traffic': None, 'traffic_note': 'not measured in this run: the ncu --set full captures (dram__bytes_read/write per launch) are under profiles/'}
+    if use_det and det_fam and det_fam['ms'] > all_ms[dom]:
+        # with the detector in the step the kernel that takes most of it is the 1x1-convolution GEMM (one template, 66 launches of different shapes per call):
+        # its algorithmic bytes per call / the sum of its launch durations, both for the NB frames of one step
+        g_gbs = det_fam['bytes'] / (det_fam['ms'] * 1e-3) / 1e9
+        g_tf = det_fam['flop'] / (det_fam['ms'] * 1e-3) / 1e12
+        roofline = dict({'bound': 'hbm', 'kernel': 'conv1x1_tc_kernel (the detector\'s 1x1-convolution GEMM: %d launches per call, TMA + tcgen05/TMEM)' % det_fam['launches'],
+                         'achieved': g_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': g_gbs / peaks['hbm_gbs'], 'peak_kind': peak_note,
+                         'algorithmic_bytes_per_launch': int(det_fam['bytes'] / det_fam['launches']), 'algorithmic_bytes_per_call': int(det_fam['bytes']),
+                         'kernel_ms': det_fam['ms'], 'launches': det_fam['launches'],
+                         'tensor': {'achieved_fp32_equivalent': g_tf, 'tensor_pipe_tf32': 3 * g_tf, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac_of_dense_bf16_peak': 3 * g_tf / peaks['bf16_tflops'],
+                                    'note': 'K = 16..960 with FP32 activations: these layers stream (about %.0f FLOP per byte), the tensor pipe is never the bound' % (det_fam['flop'] / det_fam['bytes'])},
+                         'detector_kernels_ms': det_kinds, 'tracker_dominant': tracker_dom,
+                         'note': 'measured live: CUDA events around every kernel of sgs_detector_detect_device on its launching stream (sgs_detector_set_profiling), bytes = FP32 NHWC activations in + out + fused-tail tensor operands + weights'},
+                        **common)
+    else:
+        roofline = dict({'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'peak_kind': peak_note,
+                         'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': all_ms[dom],
+                         'note': 'the tracker kernels are instruction-issue / latency bound (integer fixed-point OpenCV semantics): the HBM fraction is reported as asked'}, **common)
     det_info = None
     if use_det:
         tf = NB * DET_GFLOP / det_ms
@@ -746,13 +813,75 @@ def main():
                                                 'note': 'the tracker-only step with ground-truth person boxes as inputs (the round-1 definition of the step)'},
                            'mean_keypoints': float(n0.mean()), 'mean_after_dynreject': float(res_gpu['cnt'].mean()), 'mean_matches': float(res_gpu['nm'].mean()),
                            'detector_person_boxes_per_frame': float(res_gpu['nb'].mean()) if use_det else None,
-                           'detector': det_info, 'full_chain_parity': parity},
+                           'detector': det_info, 'pose_chain': chain_info, 'full_chain_parity': parity},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': (TRACKER_LAUNCHES + (det.num_kernels if use_det else 0)) * args.steps, 'roofline': roofline, 'cpu_baseline': cpu}
         if bcast is not None:
             line['config']['startup_broadcast'] = bcast
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def detector_gemm_table(det, kernel_ms, ncalls, nframes):
+    """Joins the detector's kernel list (sgs_detector_describe) with its per-kernel times: algorithmic bytes and FLOPs of every 1x1-convolution GEMM for
+    `nframes` frames -- activations in + out (FP32 NHWC), the weights once, the same-shape tensor operands of the fused tail (residual add, SE gate) --
+    and the totals of the family."""
+    import re
+    ops = [l for l in det.describe().split('\n')[1:] if l]
+    fam = {'launches': 0, 'ms': 0.0, 'bytes': 0.0, 'flop': 0.0}
+    kinds = {}
+    for j, op in enumerate(ops):
+        kind = op.split()[0]
+        t = kernel_ms[j + 1] / max(1, ncalls)
+        kinds.setdefault(kind, [0, 0.0]); kinds[kind][0] += 1; kinds[kind][1] += t
+        if kind != 'conv1x1':
+            continue
+        g = re.search(r'geom (\d+)x(\d+)x(\d+)->(\d+)x', op)
+        cin, hh, ww, cout = [int(x) for x in g.groups()]
+        npx = hh * ww * nframes
+        tail = op.split('|', 1)[1] if '|' in op else ''
+        ntensor = len(re.findall(r'(?:add|mul|sub|div)(?:\(rev\))? [0-9A-Za-z_]+ buf', tail))
+        fam['launches'] += 1; fam['ms'] += t
+        fam['bytes'] += (cin + cout + ntensor * cout) * 4.0 * npx + 4.0 * cin * cout
+        fam['flop'] += 2.0 * cin * cout * npx
+    kinds['preprocess'] = [1, kernel_ms[0] / max(1, ncalls)]
+    kinds['detection_output'] = [2, (kernel_ms[-1] + kernel_ms[-2]) / max(1, ncalls)]
+    return fam, {k: {'launches': v[0], 'ms': round(v[1], 4)} for k, v in kinds.items()}
+
+
+def make_local_map(f, kps_c, desc_c, n_c, ti, mcap, cam, sf, rng, W, H):
+    """Synthetic local map of frame f for the pose chain (sgs_tracker_pose_chain_device): every other last-frame point (those are 'seen' when matched), then
+    points placed under every third keypoint of the current frame (candidates of the local search) with perturbed positions and descriptors; a few points
+    are bad, a few have no observations, a few lie behind the camera.  Shared by tests/test_gpu_pose_chain.py."""
+    from pysgs import synth
+    depth = synth.depth_s1(W, H)
+    m_last = int(ti['ln'][f])
+    take_last = np.arange(0, m_last, 2)
+    k = kps_c[:n_c]
+    sel = np.arange(1, n_c, 3)
+    kk = k[sel]
+    z = depth[np.clip(kk['y'].astype(np.int64), 0, H - 1), np.clip(kk['x'].astype(np.int64), 0, W - 1)].astype(np.float32)
+    xyz_new = np.stack([(kk['x'] - cam['cx']) * z / cam['fx'], (kk['y'] - cam['cy']) * z / cam['fy'], z], 1).astype(np.float32)
+    xyz_new += rng.normal(0, 0.002, xyz_new.shape).astype(np.float32)
+    d_new = desc_c[sel].copy()
+    flip = rng.integers(0, 256, (len(sel), 6))
+    np.bitwise_xor.at(d_new, (np.repeat(np.arange(len(sel)), 6), (flip >> 3).ravel()), (1 << (flip & 7)).astype(np.uint8).ravel())
+    oct_new = kk['octave'].astype(np.int64)
+    n = len(take_last) + len(sel)
+    assert n <= mcap
+    xyz = np.zeros((mcap, 3), np.float32); nrm = np.zeros((mcap, 3), np.float32); mn = np.zeros(mcap, np.float32); mx = np.zeros(mcap, np.float32)
+    dsc = np.zeros((mcap, 32), np.uint8); valid = np.zeros(mcap, np.uint8); obs = np.zeros(mcap, np.uint8)
+    xyz[:len(take_last)] = ti['lxyz'][f, take_last]; dsc[:len(take_last)] = ti['ldesc'][f, take_last]
+    oct_all = np.concatenate([ti['loct'][f, take_last].astype(np.int64), oct_new])
+    xyz[len(take_last):n] = xyz_new; dsc[len(take_last):n] = d_new
+    dist = np.linalg.norm(xyz[:n], axis=1).astype(np.float32)
+    mx[:n] = dist * sf[oct_all]; mn[:n] = mx[:n] / sf[-1]                # MapPoint::UpdateNormalAndDepth
+    nrm[:n] = xyz[:n] / np.maximum(dist, 1e-6)[:, None]                   # mean viewing direction, camera at the origin
+    valid[:n] = 1; valid[np.arange(5, n, 17)] = 0
+    obs[:n] = 1; obs[np.arange(3, n, 11)] = 0
+    xyz[np.arange(7, n, 29), 2] *= -1
+    lid = np.full(ti['lxyz'].shape[1], -1, np.int32); lid[take_last] = np.arange(len(take_last))
+    return dict(xyz=xyz, nrm=nrm, mn=mn, mx=mx, dsc=dsc, valid=valid, obs=obs, n=n, lid=lid)
 
 
 def pin_rank_to_numa_node(local):

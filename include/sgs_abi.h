@@ -686,6 +686,11 @@ SGS_API int sgs_tracker_step(sgs_tracker* t, sgs_detector* det, const uint8_t* g
 /* Text listing of the kernel list: one line per kernel with its fused element-wise tail and activation-pool buffers.  SGS_ERR_CAPACITY
  * with *n = bytes required (terminator included) when cap is too small. */
 SGS_API int sgs_detector_describe(const sgs_detector* d, char* out, int64_t cap, int64_t* n);
+/* Per-kernel timing of sgs_detector_detect_device, same contract as sgs_extractor_set_profiling: while enabled, CUDA events bracket every launch of a
+ * call on the launching stream (preprocess, the kernels in the order of sgs_detector_describe, the two DetectionOutput kernels); ms_total[i] accumulates
+ * over ncalls completed calls.  Costs one event per kernel: leave it off in production. */
+SGS_API int sgs_detector_set_profiling(sgs_detector* d, int enable);
+SGS_API int sgs_detector_kernel_times(sgs_detector* d, double* ms_total, int cap, int* nkernels, int* ncalls);
 /* Diagnostics: copies blob `name` of frame `frame` of the last batch to host floats (ncnn memory order c,h,w).  Needs flags bit 0. */
 SGS_API int sgs_detector_blob(sgs_detector* d, const char* name, int frame, float* out, int64_t cap, int64_t* n);
 

@@ -631,6 +631,8 @@ struct sgs_detector {
     uint8_t* d_img = nullptr; int64_t d_img_cap = 0;
     sgs_object2d* d_obj = nullptr; int32_t* d_cnt = nullptr;
     int last_frames = 0;
+    // optional per-kernel timing (sgs_detector_set_profiling): events around every launch of a call, read back at the next call / by sgs_detector_kernel_times
+    bool profiling = false, pending = false; std::vector<cudaEvent_t> ev; std::vector<double> ms_acc; int prof_calls = 0;
 };
 
 namespace {
@@ -1107,6 +1109,7 @@ void sgs_detector_destroy(sgs_detector* D) {
     for (float* p : D->weights) cudaFree(p);
     for (auto& op : D->ops) if (op.kind == OP_CONV1X1) tc::free_plan(&op.gp);
     cudaFree(D->d_picked); cudaFree(D->d_picked_n); cudaFree(D->d_img); cudaFree(D->d_obj); cudaFree(D->d_cnt);
+    for (auto& e : D->ev) if (e) cudaEventDestroy(e);
     delete D;
 }
 
@@ -1116,6 +1119,37 @@ int sgs_detector_info(const sgs_detector* D, int* rows_cap, int* input_size, int
     if (input_size) *input_size = D->T;
     if (num_layers) *num_layers = (int)D->layers.size();
     if (num_kernels) *num_kernels = (int)D->ops.size() + 3;
+    return SGS_OK;
+}
+
+static void det_collect_times(sgs_detector* D) {
+    if (!D->pending) return;
+    const size_t nk = D->ops.size() + 3;
+    if (cudaEventSynchronize(D->ev[nk]) == cudaSuccess) {
+        for (size_t i = 0; i < nk; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, D->ev[i], D->ev[i + 1]) == cudaSuccess) D->ms_acc[i] += ms; }
+        D->prof_calls++;
+    }
+    D->pending = false;
+}
+
+int sgs_detector_set_profiling(sgs_detector* D, int enable) {
+    if (!D || (D->flags & 2)) { set_error("sgs_detector_set_profiling: NULL or plan-only handle"); return SGS_ERR_INVALID; }
+    SGS_CUDA_TRY(cudaSetDevice(D->device));
+    const size_t nk = D->ops.size() + 3;
+    if (enable && D->ev.empty()) { D->ev.resize(nk + 1); for (auto& e : D->ev) SGS_CUDA_TRY(cudaEventCreate(&e)); }
+    D->profiling = enable != 0; D->pending = false; D->ms_acc.assign(nk, 0.0); D->prof_calls = 0;
+    return SGS_OK;
+}
+
+int sgs_detector_kernel_times(sgs_detector* D, double* ms_total, int cap, int* nkernels, int* ncalls) {
+    if (!D || !nkernels || !ncalls) { set_error("sgs_detector_kernel_times: NULL"); return SGS_ERR_INVALID; }
+    const int nk = (int)D->ops.size() + 3;
+    *nkernels = nk; *ncalls = 0;
+    if (!D->profiling) return SGS_OK;
+    SGS_CUDA_TRY(cudaSetDevice(D->device));
+    det_collect_times(D);
+    *ncalls = D->prof_calls;
+    if (ms_total) { if (cap < nk) { set_error("sgs_detector_kernel_times: %d entries needed", nk); return SGS_ERR_CAPACITY; } for (int i = 0; i < nk; ++i) ms_total[i] = D->ms_acc[i]; }
     return SGS_OK;
 }
 
@@ -1133,9 +1167,15 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
     cudaStream_t st = (cudaStream_t)stream;
     const int F = nframes, T = D->T;
     auto& B = D->blobs;
+    const bool prof = D->profiling;
+    if (prof) det_collect_times(D);
+    size_t evi = 0;
+#define SGS_DET_MARK() do { if (prof) cudaEventRecord(D->ev[evi++], st); } while (0)
+    SGS_DET_MARK();
     preprocess_kernel<<<dim3(nblk((int64_t)T * T), F), 256, 0, st>>>(d_rgb, frame_stride, pitch, width, height, T, 123.675f, 116.28f, 103.53f,
                                                                      B[D->input_blob].dev);
     for (const Op& op : D->ops) {
+        SGS_DET_MARK();
         const Blob& bi = B[op.in]; const Blob& bo = B[op.out];
         const Epi epi = make_epi(D, op.epi);
         switch (op.kind) {
@@ -1189,12 +1229,17 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
         }
     }
     const DetOutParams P = D->dp;
+    SGS_DET_MARK();
     detout_class_kernel<<<dim3(P.ncls - 1, F), 256, kDetSortCap * 8 + P.nms_topk * 20, st>>>(B[D->loc_blob].dev, B[D->conf_blob].dev, D->d_prior, D->d_var, P,
                                                                                                 D->d_picked, D->d_picked_n);
     PostParams Q{D->det_thr, D->dyn_thr, (float)T, width, height, 15, P.keep_topk, max_boxes};
+    SGS_DET_MARK();
     detout_merge_kernel<<<F, 256, kMergeCap * 8 + P.keep_topk * 24, st>>>(B[D->loc_blob].dev, D->d_prior, D->d_var, P, D->d_picked, D->d_picked_n, Q, d_rows,
                                                                           d_nrows, d_objects, d_nobjects, d_dyn_map, d_ndyn_map, d_dyn_rm, d_ndyn_rm,
                                                                           d_have_dyn_rm, d_status);
+    SGS_DET_MARK();
+#undef SGS_DET_MARK
+    if (prof) D->pending = true;
     SGS_CUDA_TRY(cudaGetLastError());
     D->last_frames = F;
     return SGS_OK;

@@ -113,7 +113,7 @@ class LocalMapBatch(C.Structure):
 
 
 ABI_SYMBOLS = [
-    'sgs_tracker_pose_chain_device',
+    'sgs_tracker_pose_chain_device', 'sgs_detector_set_profiling', 'sgs_detector_kernel_times',
     'sgs_abi_version', 'sgs_last_error', 'sgs_device_count', 'sgs_settings_load',
     'sgs_extractor_create', 'sgs_extractor_destroy', 'sgs_extractor_tables', 'sgs_extractor_max_keypoints', 'sgs_extractor_level_info',
     'sgs_extract', 'sgs_extract_batch', 'sgs_extract_batch_device', 'sgs_extractor_results_device', 'sgs_extractor_fetch', 'sgs_extractor_read_level',
@@ -508,6 +508,17 @@ class Detector:
             self.close()
         except Exception:
             pass
+
+    def set_profiling(self, enable):
+        check(lib().sgs_detector_set_profiling(self.h, int(enable)))
+
+    def kernel_times(self):
+        """(ms_total per kernel [preprocess, the kernels of describe() in order, detout_class, detout_merge], completed calls)"""
+        nk, nc = C.c_int(), C.c_int()
+        check(lib().sgs_detector_kernel_times(self.h, None, 0, C.byref(nk), C.byref(nc)))
+        ms = (C.c_double * nk.value)()
+        check(lib().sgs_detector_kernel_times(self.h, ms, nk.value, C.byref(nk), C.byref(nc)))
+        return [ms[i] for i in range(nk.value)], nc.value
 
     def describe(self):
         n = C.c_int64()

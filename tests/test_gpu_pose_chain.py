@@ -21,41 +21,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 W, H, NF, TH = 640, 480, 1000, 15.0
 
 
-def build_local_map(f, kps_c, desc_c, n_c, ti, mcap, cam, sf, rng):
-    """Local map of frame f: the last-frame points (so that some are 'seen'), then points placed under the current frame's keypoints (new matches),
-    a few of them bad, a few with zero observations, a few behind the camera / at a wrong scale."""
-    depth = synth.depth_s1(W, H)
-    m_last = int(ti['ln'][f])
-    take_last = np.arange(0, m_last, 2)                              # every other last-frame point is part of the local map
-    k = kps_c[:n_c]
-    sel = np.arange(1, n_c, 3)
-    kk = k[sel]
-    z = depth[np.clip(kk['y'].astype(np.int64), 0, H - 1), np.clip(kk['x'].astype(np.int64), 0, W - 1)].astype(np.float32)
-    xyz_new = np.stack([(kk['x'] - cam['cx']) * z / cam['fx'], (kk['y'] - cam['cy']) * z / cam['fy'], z], 1).astype(np.float32)
-    xyz_new += rng.normal(0, 0.002, xyz_new.shape).astype(np.float32)
-    d_new = desc_c[sel].copy()
-    flip = rng.integers(0, 256, (len(sel), 6))
-    for j in range(len(sel)):
-        for b in flip[j]:
-            d_new[j, b >> 3] ^= np.uint8(1 << (b & 7))
-    oct_new = kk['octave'].astype(np.int64)
-    n = len(take_last) + len(sel)
-    assert n <= mcap
-    xyz = np.zeros((mcap, 3), np.float32); nrm = np.zeros((mcap, 3), np.float32); mn = np.zeros(mcap, np.float32); mx = np.zeros(mcap, np.float32)
-    dsc = np.zeros((mcap, 32), np.uint8); valid = np.zeros(mcap, np.uint8); obs = np.zeros(mcap, np.uint8)
-    xyz[:len(take_last)] = ti['lxyz'][f, take_last]; dsc[:len(take_last)] = ti['ldesc'][f, take_last]
-    oct_all = np.concatenate([ti['loct'][f, take_last].astype(np.int64), oct_new])
-    xyz[len(take_last):n] = xyz_new; dsc[len(take_last):n] = d_new
-    dist = np.linalg.norm(xyz[:n], axis=1).astype(np.float32)
-    mx[:n] = dist * sf[oct_all]; mn[:n] = mx[:n] / sf[-1]                # MapPoint::UpdateNormalAndDepth
-    nrm[:n] = xyz[:n] / np.maximum(dist, 1e-6)[:, None]                   # mean viewing direction (camera at the origin -> point), MapPoint::UpdateNormalAndDepth
-    valid[:n] = 1; valid[np.arange(5, n, 17)] = 0                         # some bad points
-    obs[:n] = 1; obs[np.arange(3, n, 11)] = 0
-    xyz[np.arange(7, n, 29), 2] *= -1                                     # behind the camera
-    lid = np.full(ti['lxyz'].shape[1], -1, np.int32); lid[take_last] = np.arange(len(take_last))
-    return dict(xyz=xyz, nrm=nrm, mn=mn, mx=mx, dsc=dsc, valid=valid, obs=obs, n=n, lid=lid)
-
-
 def oracle_chain(f, cur, nm0, mp0, ti, lm, cam, camd, sf, isig, th, tcw_motion_gpu=None):
     """Returns a dict with the chain's outputs for frame f, composed from the oracle's functions."""
     pc = ti['lxyz'].shape[1]
@@ -140,7 +105,7 @@ def test_pose_chain_against_the_oracle_functions():
                                    P(ti['loct']), P(ti['lang']), P(ti['ln']), P(Tc), P(ti['T']), C.c_float(TH), 0, 1, P(o['kps']), P(o['desc']), P(o['ur']), P(o['cnt']),
                                    P(o['mp']), P(o['nm'])))
     rng = np.random.default_rng(5)
-    lms = [build_local_map(f, o['kps'][f], o['desc'][f], int(o['cnt'][f]), ti, mcap, camd, sf, rng) for f in range(nb)]
+    lms = [bench.make_local_map(f, o['kps'][f], o['desc'][f], int(o['cnt'][f]), ti, mcap, camd, sf, rng, W, H) for f in range(nb)]
     stack = lambda k, dt: np.ascontiguousarray(np.stack([m[k] for m in lms]).astype(dt))
     dev = {k: torch.from_numpy(a).cuda() for k, a in dict(lxyz=ti['lxyz'], ldesc=ti['ldesc'], lflags=ti['lflags'], loct=ti['loct'], lang=ti['lang'], ln=ti['ln'], Tc=Tc, Tl=ti['T'],
                                                           lid=stack('lid', np.int32), xyz=stack('xyz', np.float32), nrm=stack('nrm', np.float32), mn=stack('mn', np.float32),
