@@ -43,8 +43,8 @@ CONFIGS = {
     's2':   dict(W=640, H=480, NFEAT=1000, batch=512, cam_scale=1.0, name='S2 walking_xyz-shaped synthetic 640x480 stream (BASELINE configs[1])'),
     '720p': dict(W=1280, H=720, NFEAT=2000, batch=192, cam_scale=2.0, name='S3 synthetic 1280x720 stream, 2000 features (BASELINE configs[2])'),
 }
-# launches of one tracker step: extract (7 resize, FAST, quadtree, 8 blur, describe) + LK (3 pyrDown, 4 Scharr, 4 border, track) + RANSAC F + depth lookup + dyn-reject/compact (2) + match
-TRACKER_LAUNCHES = 18 + 12 + 1 + 1 + 2 + 1
+# launches of one tracker step: extract (7 resize, FAST, quadtree, blur, describe) + LK (3 pyrDown, 4 Scharr, 4 border, track) + RANSAC F + depth lookup + dyn-reject/compact (2) + match
+TRACKER_LAUNCHES = 11 + 12 + 1 + 1 + 2 + 1
 
 
 def alg_bytes(W, H, nk):
@@ -706,8 +706,8 @@ def main():
     peaks, peak_kind = measured_peaks()
     nk = int(n0.mean())
     ab = alg_bytes(W, H, nk)
-    names = ['pyramid(7 launches)', 'fast_warp_cells_kernel', 'quadtree_kernel', 'blur(8 launches)', 'describe_kernel']
-    alg = {'pyramid(7 launches)': ab['pyramid'], 'fast_warp_cells_kernel': ab['fast'] + 40 * nk, 'quadtree_kernel': 84 * nk, 'blur(8 launches)': ab['blur'],
+    names = ['pyramid(7 launches)', 'fast_warp_cells_kernel', 'quadtree_kernel', 'blur_tile_kernel', 'describe_kernel']
+    alg = {'pyramid(7 launches)': ab['pyramid'], 'fast_warp_cells_kernel': ab['fast'] + 40 * nk, 'quadtree_kernel': 84 * nk, 'blur_tile_kernel': ab['blur'],
            'describe_kernel': ab['describe'], 'lk_pyramid+deriv(11 launches)': ab['lk_pyr'], 'lk_track_kernel': ab['lk_track'], 'fm_ransac_kernel': ab['fm'],
            'stereo+dynreject+compact+match(4 launches)': ab['track']}
     all_ms = dict(zip(names, stage_ms))

@@ -21,7 +21,7 @@ void launch_quadtree(const DevPlan& P, int smem_key_cap, int node_cap, size_t sm
                      const int64_t* d_key_scratch_off, cudaStream_t st);
 cudaError_t configure_quadtree_smem(size_t smem_bytes);
 size_t quadtree_node_bytes(int cap);
-void launch_blur(const DevPlan& P, int level, cudaStream_t st);
+void launch_blur_all(const DevPlan& P, cudaStream_t st);          // every level in one launch
 void launch_describe(const DevPlan& P, cudaStream_t st);
 const char* last_error_cstr();
 }  // namespace sgs

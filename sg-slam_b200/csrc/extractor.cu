@@ -130,7 +130,7 @@ int enqueue(sgs_extractor* ex, const uint8_t* d_l0, int pitch, int64_t fstride, 
     if (prof) cudaEventRecord(ex->ev[2], st);
     launch_quadtree(P, ex->smem_key_cap, ex->node_cap, ex->qt_smem, key_scratch, ex->key_scratch_fstride, ex->d_key_scratch_off, st);
     if (prof) cudaEventRecord(ex->ev[3], st);
-    for (int l = 0; l < L; ++l) launch_blur(P, l, st);
+    launch_blur_all(P, st);
     if (prof) cudaEventRecord(ex->ev[4], st);
     launch_describe(P, st);
     if (prof) { cudaEventRecord(ex->ev[5], st); ex->stage_pending = true; }
