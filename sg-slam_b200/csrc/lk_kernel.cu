@@ -144,7 +144,13 @@ __device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c) { int d
 __device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ uint32_t lk_pack_weights(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 
-__device__ __forceinline__ uint32_t lk_pack_row(uint32_t p0, uint32_t p1, uint32_t p2) { return p0 | (p1 * 0x00010100u) | (p2 << 24); }
+// Read from an arbitrarily aligned address with two aligned 32-bit loads (the padded planes have 256 bytes of slack behind the last row).
+__device__ __forceinline__ uint32_t lk_load_row3(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t x = __funnelshift_r(__ldg(q), __ldg(q + 1), 8u * (uint32_t)(a & 3));      // bytes p[0..3]
+    return __byte_perm(x, 0, 0x2110);
+}
 
 __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
     w00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), 16384.f));
@@ -169,7 +175,7 @@ __device__ __forceinline__ void lk_setup_tiles(const uint8_t* __restrict__ img, 
         const uint8_t* p = img + o; const uint32_t* q = der + o;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            Rw[r] = lk_pack_row(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+            Rw[r] = lk_load_row3(p);
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
                 const uint32_t d = __ldg(q + x);
@@ -212,14 +218,14 @@ __device__ __forceinline__ void lk_load_j_tile(const uint8_t* __restrict__ img, 
     const uint8_t* p = img + (int64_t)(iny + g7) * pitch + (inx + k2);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        v[r] = lk_pack_row(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+        v[r] = lk_load_row3(p);
         p += pitch;
     }
     const uint8_t* q = img + (int64_t)(iny + erow) * pitch + (inx + 20);
     e = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + pitch) << 16) | ((uint32_t)__ldg(q + pitch + 1) << 24);
 }
 
-// v[r] = packed row r of the lane's 8x3 tile of J (lk_pack_row), e = the 2x2 pixels under its pixel of column 20 (top pair | bottom pair << 16);
+// v[r] = packed row r of the lane's 8x3 tile of J (lk_load_row3), e = the 2x2 pixels under its pixel of column 20 (top pair | bottom pair << 16);
 // wt = w00 | w01 << 16, wb = w10 | w11 << 16.  
 __device__ __forceinline__ void lk_mismatch_tiles(const uint32_t (&v)[8], uint32_t e, bool lane30, uint32_t wt, uint32_t wb,
                                                   const int (&C)[14], const int (&GX)[14], const int (&GY)[14], int Ce, int GXe, int GYe, int& s1, int& s2) {
