@@ -1220,8 +1220,8 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
         }
         case OP_DWCONV: {
             const int V = op.g.Cout % 4 == 0 ? 4 : 1;
-            // two output rows per thread on the vectorised stride-1 layers (the K + 1 input rows serve both: 1.5x / 1.67x fewer row loads for 3x3 / 5x5)
-            const int YT = (V == 4 && op.g.stride == 1 && op.g.OH >= 4) ? 2 : 1;
+            // two output rows per thread on the vectorised layers (the K + S input rows serve both: 1.5x / 1.67x fewer row loads for 3x3 / 5x5 at stride 1)
+            const int YT = (V == 4 && op.g.OH >= 4) ? 2 : 1;
             const int64_t total = (int64_t)F * ((op.g.OH + YT - 1) / YT) * ((op.g.OW + 3) / 4) * (op.g.Cout / V);
 #define SGS_DW(K, S) do { if (V == 4 && YT == 2) dwconv_kernel<K, S, 4, 2><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi); \
                           else if (V == 4) dwconv_kernel<K, S, 4, 1><<<nblk(total), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, total, epi); \
