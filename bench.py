@@ -251,28 +251,58 @@ def run_reference(args, cfg):
     ch0.run(0, NB, nthreads=cores)
     ti = make_track_inputs(ch0.out['kps'], ch0.out['desc'], ch0.out['counts'], boxes, cap, cap, pidx, W, H, cam)
     ch = O.Chain(frames, pidx, ti, cam, cap, nfeatures=NF, th=TH, want_outputs=False)
-    det_fps = None
-    det_n = 0
-    if os.path.exists(MODEL + '.param') and not args.no_detector:
-        det_n = 8
-        det_fps = detector_cpu_rate(synth.gray_to_rgb(frames[:det_n]))
+    # Every timed step really runs both parts on the same bounded sample of S frames of the batch (no extrapolation: steps x ms_per_step is the wall time
+    # of the timed region): the tracking chain on all cores, then the detector restatement frame by frame on all cores.  S is sized from a probe so that a
+    # step takes about two seconds.
+    with_det = os.path.exists(MODEL + '.param') and not args.no_detector
+    det_run = None
+    if with_det:
+        import detector_oracle as DO
+        import ncnn_model as NM
+        import torch
+        torch.set_num_threads(cores)
+        layers = NM.parse_param(MODEL + '.param'); NM.load_weights(layers, MODEL + '.bin')
+        rgb = synth.gray_to_rgb(frames[:min(NB, 256)])
+
+        def det_run(n):
+            for f in range(n):
+                DO.detect(layers, rgb[f % len(rgb)])
+        det_run(1)
+    ch.run(0, min(NB, cores), nthreads=cores)
+    t0 = time.perf_counter(); ch.run(0, min(NB, 2 * cores), nthreads=cores); probe_chain = (time.perf_counter() - t0) / min(NB, 2 * cores)
+    probe_det = 0.0
+    if with_det:
+        t0 = time.perf_counter(); det_run(4); probe_det = (time.perf_counter() - t0) / 4
+    S = int(max(8, min(NB, round(2.0 / max(1e-6, probe_chain + probe_det)))))
+    if S >= cores:
+        S = S // cores * cores                        # whole rounds of the worker threads
+    t_chain = t_det = 0.0
+
+    def ref_step(timed):
+        nonlocal t_chain, t_det
+        a = time.perf_counter(); ch.run(0, S, nthreads=cores); b = time.perf_counter()
+        if with_det:
+            det_run(S)
+        c = time.perf_counter()
+        if timed:
+            t_chain += b - a; t_det += c - b
     for _ in range(args.warmup):
-        ch.run(0, NB, nthreads=cores)
+        ref_step(False)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ch.run(0, NB, nthreads=cores)
-    dt_chain = (time.perf_counter() - t0) / args.steps
+        ref_step(True)
+    dt_step = (time.perf_counter() - t0) / args.steps
     t0 = time.perf_counter(); ch.run(0, 4, nthreads=1); one_fps = 4 / (time.perf_counter() - t0)
-    dt_step = dt_chain + (NB / det_fps if det_fps else 0.0)
-    fps = NB / dt_step
+    fps = S / dt_step
     line = {'impl': 'reference', 'metric': 'frames/sec ORB extract+match+dyn-reject %dx%d' % (W, H), 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-            'config': {'workload': workload_name(cfg, det_fps is not None), 'frames_per_gpu_per_step': NB,
-                       'note': 'CPU oracle port of the reference path (the reference itself needs OpenCV/ROS/ncnn: unbuildable here); tracking chain: C++ worker threads pinned one per core, every step processes the whole batch; detector: PyTorch-CPU FP32 restatement timed on %d frames and scaled to the batch' % det_n},
-            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': '%d frames per step x %d steps' % (NB, args.steps),
-                             'tracking_chain_all_cores': NB / dt_chain, 'tracking_chain_single_thread': one_fps, 'tracking_chain_per_core': NB / dt_chain / cores,
-                             'detector_all_cores': det_fps},
+            'config': {'workload': workload_name(cfg, with_det), 'frames_per_gpu_per_step': NB, 'sample_frames_per_step': S,
+                       'note': 'CPU oracle port of the reference path (the reference itself needs OpenCV/ROS/ncnn: unbuildable here).  Every step runs %d frames of the %d-frame batch through the tracking chain (C++ worker threads pinned one per core) and through the detector (PyTorch-CPU FP32 restatement, all threads); both inside the timed region' % (S, NB)},
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': '%d frames per step x %d steps, chain + detector both run on every frame of the sample' % (S, args.steps),
+                             'tracking_chain_all_cores': S * args.steps / t_chain if t_chain > 0 else None, 'tracking_chain_single_thread': one_fps,
+                             'tracking_chain_per_core': (S * args.steps / t_chain / cores) if t_chain > 0 else None,
+                             'detector_all_cores': (S * args.steps / t_det) if t_det > 0 else None},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(line)
 
@@ -394,6 +424,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=0, help='frames of the cpu_baseline sample (0: four per host thread, at least 64)')
     ap.add_argument('--parity-frames', type=int, default=256, help='frames of the full-chain parity check against the pure oracle')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-pipeline', action='store_true', help='e2e: skip the two-steps-in-flight mode')
     ap.add_argument('--no-detector', action='store_true', help='tracker-only step with ground-truth boxes (the round-1 definition of the step)')
     args = ap.parse_args()
     claim_stdout()
@@ -630,8 +661,8 @@ def main():
         outs = [out[k][sl].data_ptr() for k in ('kps', 'desc', 'ur', 'cnt', 'mp', 'nm', 'boxes', 'nb', 'have')]
         return ins, outs
 
-    def step_host(tk, dt_, nb, fr, rgb, hpi, sl=slice(None)):
-        ins, outs = host_ptrs(hpi, h_out, sl)
+    def step_host(tk, dt_, nb, fr, rgb, hpi, sl=slice(None), out=None):
+        ins, outs = host_ptrs(hpi, h_out if out is None else out, sl)
         if dt_ is not None:
             B.check(L.sgs_tracker_step(tk.h, dt_.h, v(fr.data_ptr()), C.c_size_t(W * H), W, v(rgb.data_ptr()), C.c_size_t(W * H * 3), W * 3, nb, *[v(p) for p in ins],
                                        C.c_float(TH), 0, 1, *[v(p) for p in outs]))
@@ -697,6 +728,42 @@ def main():
                 tk.close()
                 if dk is not None:
                     dk.close()
+        if use_det and args.steps >= 2 and not args.no_pipeline:
+            # whole steps alternating over two full-size handles (two steps in flight): the copies of one step overlap the kernels of the other at the full
+            # batch size of every launch
+            tk2 = B.Tracker(W, H, cam, NFEAT, 1.2, 8, 20, 7, max_batch=NB, point_cap=NFEAT + 64, max_boxes=4, device=local)
+            dk2 = B.Detector(MODEL + '.param', MODEL + '.bin', max_frames=NB, det_thr=0.9, dyn_thr=0.01, device=local)
+            h_out2 = {k: pin(tuple(t.shape), t.dtype) for k, t in h_out.items()}
+
+            def worker3(hx, nsteps, gate):
+                torch.cuda.set_device(local)
+                gate.wait()
+                for _ in range(nsteps):
+                    if hx == 0:
+                        step_host(trk, det, NB, h_frames, h_rgb, hp)
+                    else:
+                        step_host(tk2, dk2, NB, h_frames, h_rgb, hp, out=h_out2)
+
+            def run_alt(nsteps):
+                gate = threading.Barrier(3)
+                th = [threading.Thread(target=worker3, args=(hx, (nsteps + 1 - hx) // 2, gate)) for hx in range(2)]
+                for t in th:
+                    t.start()
+                barrier()
+                gate.wait()
+                t0 = time.perf_counter()
+                for t in th:
+                    t.join()
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0
+            run_alt(2)
+            same3 = bool(np.array_equal(res_gpu['cnt'], h_out2['cnt'].numpy()) and np.array_equal(res_gpu['nm'], h_out2['nm'].numpy()) and np.array_equal(res_gpu['mp'], h_out2['mp'].numpy()))
+            dt3 = max_over_ranks(run_alt(args.steps))
+            if not same3:
+                log('[bench] WARNING: pipelined e2e results differ from the single-handle ones')
+            elif dt3 < dt:
+                dt, mode = dt3, 'two full-size tracker + detector handles taking whole steps alternately (two steps in flight), two host threads'
+            tk2.close(); dk2.close()
         e2e = {'value': world * NB * args.steps / dt, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                'ms_per_step': 1e3 * dt / args.steps, 'mode': mode, 'single_handle_value': world * NB * args.steps / dt1,
                'note': ('sgs_tracker_step: host gray + colour frames and track inputs in, compacted keypoints / descriptors / matches / detector boxes out' if use_det else
