@@ -369,6 +369,62 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const float* __restrict
     });
 }
 
+// The network's first layer as its own kernel (3 -> 16 channels, 3x3, stride 2, pad 1: 0.82 ms per 512 frames through the generic kernel above, the largest
+// single launch of the detector; 0.55 ms here): one output pixel x all 16 channels per thread, the 27 x 16 weights in shared memory as [tap][channel]
+// (warp-wide broadcast reads), every loop unrolled.  Same accumulation order per output channel as conv_small_kernel (ky, kx, ci from zero, then the bias).
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                         float* __restrict__ out, ConvGeom g, Epi epi) {
+    __shared__ __align__(16) float sw[27 * 16];
+    const int f = blockIdx.y;
+    for (int e = threadIdx.x; e < 27 * 16; e += 256) {
+        const int tp = e >> 4, o = e & 15;                     // tp = (ky * 3 + kx) * 3 + ci
+        const int ci = tp % 3, kk = tp / 3;
+        sw[e] = __ldg(Wt + ((int64_t)o * 3 + ci) * 9 + kk);
+    }
+    __syncthreads();
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= g.OH * g.OW) return;
+    const int oy = p / g.OW, ox = p - oy * g.OW;
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+    const float* img = in + (int64_t)f * g.H * g.W * 3;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 - 1 + ky;
+        if (iy < 0 || iy >= g.H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * 2 - 1 + kx;
+            if (ix < 0 || ix >= g.W) continue;
+            const float* src = img + ((int64_t)iy * g.W + ix) * 3;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float x = __ldg(src + ci);
+                const float4* w4 = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + ci) * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 w = w4[q];
+                    acc[4 * q] = fmaf(w.x, x, acc[4 * q]); acc[4 * q + 1] = fmaf(w.y, x, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(w.z, x, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w.w, x, acc[4 * q + 3]);
+                }
+            }
+        }
+    }
+    const int64_t idx0 = ((int64_t)f * g.OH * g.OW + p) * 16;
+    epi_dispatch(epi.kind, [&](auto kind) {
+        constexpr int EK = decltype(kind)::value;
+#pragma unroll
+        for (int o = 0; o < 16; o += 4) {
+            float w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = __fadd_rn(acc[o + q], bias ? __ldg(bias + o + q) : 0.f);
+            apply_epi4<EK>(epi, w, idx0 + o);
+            *reinterpret_cast<float4*>(out + idx0 + o) = make_float4(w[0], w[1], w[2], w[3]);
+        }
+    });
+}
+
 __global__ void __launch_bounds__(256) eltwise_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total, Epi epi) {
     const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (idx >= total) return;
@@ -1214,6 +1270,10 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
             const size_t wbytes = (size_t)op.g.Cin * op.g.k * op.g.k * kCot * sizeof(float);
             if (wbytes > 96 * 1024) { set_error("sgs_detector_detect_device: layer %s: %zu bytes of weights per channel block do not fit shared memory", D->layers[op.layer].name.c_str(), wbytes); return SGS_ERR_UNSUPPORTED; }
             const int64_t fstride = op.cat ? bo.n : (int64_t)op.g.OH * op.g.OW * op.g.Cout;
+            if (!op.cat && op.g.k == 3 && op.g.Cin == 3 && op.g.Cout == 16 && op.g.stride == 2 && op.g.pad == 1 && op.g.dil == 1) {
+                conv_first_kernel<<<dim3(nblk((int64_t)op.g.OH * op.g.OW), F), 256, 0, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, epi);
+                break;
+            }
             conv_small_kernel<<<dim3(nblk((int64_t)op.g.OH * op.g.OW), (op.g.Cout + kCot - 1) / kCot, F), 256, wbytes, st>>>(bi.dev, op.d_w, op.d_b, bo.dev, op.g, fstride,
                                                                                                                         op.cat ? op.off : 0, epi);
             break;
