@@ -275,7 +275,7 @@ def run_reference(args, cfg):
         t0 = time.perf_counter(); det_run(4); probe_det = (time.perf_counter() - t0) / 4
     S = int(max(8, min(NB, round(2.0 / max(1e-6, probe_chain + probe_det)))))
     if S >= cores:
-        S = S // cores * cores                        # whole rounds of the worker threads
+        S = max(cores, int(round(S / cores)) * cores)  # whole rounds of the worker threads
     t_chain = t_det = 0.0
 
     def ref_step(timed):
@@ -424,7 +424,8 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=0, help='frames of the cpu_baseline sample (0: four per host thread, at least 64)')
     ap.add_argument('--parity-frames', type=int, default=256, help='frames of the full-chain parity check against the pure oracle')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--no-pipeline', action='store_true', help='e2e: skip the two-steps-in-flight mode')
+    ap.add_argument('--no-pipeline', action='store_true', help='e2e: skip the steps-in-flight mode')
+    ap.add_argument('--pipeline-handles', type=int, default=3, help='e2e: full-size handles taking whole steps in turn')
     ap.add_argument('--no-detector', action='store_true', help='tracker-only step with ground-truth boxes (the round-1 definition of the step)')
     args = ap.parse_args()
     claim_stdout()
@@ -731,9 +732,10 @@ def main():
         if use_det and args.steps >= 2 and not args.no_pipeline:
             # whole steps alternating over two full-size handles (two steps in flight): the copies of one step overlap the kernels of the other at the full
             # batch size of every launch
-            tk2 = B.Tracker(W, H, cam, NFEAT, 1.2, 8, 20, 7, max_batch=NB, point_cap=NFEAT + 64, max_boxes=4, device=local)
-            dk2 = B.Detector(MODEL + '.param', MODEL + '.bin', max_frames=NB, det_thr=0.9, dyn_thr=0.01, device=local)
-            h_out2 = {k: pin(tuple(t.shape), t.dtype) for k, t in h_out.items()}
+            NH = max(2, args.pipeline_handles)
+            extra = [(B.Tracker(W, H, cam, NFEAT, 1.2, 8, 20, 7, max_batch=NB, point_cap=NFEAT + 64, max_boxes=4, device=local),
+                      B.Detector(MODEL + '.param', MODEL + '.bin', max_frames=NB, det_thr=0.9, dyn_thr=0.01, device=local),
+                      {k: pin(tuple(t.shape), t.dtype) for k, t in h_out.items()}) for _ in range(NH - 1)]
 
             def worker3(hx, nsteps, gate):
                 torch.cuda.set_device(local)
@@ -742,11 +744,11 @@ def main():
                     if hx == 0:
                         step_host(trk, det, NB, h_frames, h_rgb, hp)
                     else:
-                        step_host(tk2, dk2, NB, h_frames, h_rgb, hp, out=h_out2)
+                        step_host(extra[hx - 1][0], extra[hx - 1][1], NB, h_frames, h_rgb, hp, out=extra[hx - 1][2])
 
             def run_alt(nsteps):
-                gate = threading.Barrier(3)
-                th = [threading.Thread(target=worker3, args=(hx, (nsteps + 1 - hx) // 2, gate)) for hx in range(2)]
+                gate = threading.Barrier(NH + 1)
+                th = [threading.Thread(target=worker3, args=(hx, (nsteps + NH - 1 - hx) // NH, gate)) for hx in range(NH)]
                 for t in th:
                     t.start()
                 barrier()
@@ -756,14 +758,16 @@ def main():
                     t.join()
                 torch.cuda.synchronize()
                 return time.perf_counter() - t0
-            run_alt(2)
-            same3 = bool(np.array_equal(res_gpu['cnt'], h_out2['cnt'].numpy()) and np.array_equal(res_gpu['nm'], h_out2['nm'].numpy()) and np.array_equal(res_gpu['mp'], h_out2['mp'].numpy()))
+            run_alt(NH)
+            same3 = all(bool(np.array_equal(res_gpu['cnt'], e[2]['cnt'].numpy()) and np.array_equal(res_gpu['nm'], e[2]['nm'].numpy()) and np.array_equal(res_gpu['mp'], e[2]['mp'].numpy()))
+                        for e in extra)
             dt3 = max_over_ranks(run_alt(args.steps))
             if not same3:
                 log('[bench] WARNING: pipelined e2e results differ from the single-handle ones')
             elif dt3 < dt:
-                dt, mode = dt3, 'two full-size tracker + detector handles taking whole steps alternately (two steps in flight), two host threads'
-            tk2.close(); dk2.close()
+                dt, mode = dt3, '%d full-size tracker + detector handles taking whole steps in turn (%d steps in flight), one host thread each' % (NH, NH)
+            for e in extra:
+                e[0].close(); e[1].close()
         e2e = {'value': world * NB * args.steps / dt, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                'ms_per_step': 1e3 * dt / args.steps, 'mode': mode, 'single_handle_value': world * NB * args.steps / dt1,
                'note': ('sgs_tracker_step: host gray + colour frames and track inputs in, compacted keypoints / descriptors / matches / detector boxes out' if use_det else
