@@ -126,7 +126,7 @@ public:
             for (int k = 0; k < 3; ++k) xyz[3 * (size_t)i + k] = P.template at<float>(k, 0);
             std::memcpy(&desc[(size_t)i * 32], d.template ptr<uint8_t>(), 32);
             ang[i] = pKF->mvKeysUn[i].angle;
-            mn[i] = pMP->GetMinDistanceInvariance() / 0.8f; mx[i] = pMP->GetMaxDistanceInvariance() / 1.2f;      // raw mfMinDistance / mfMaxDistance
+            mn[i] = raw_distance(pMP->GetMinDistanceInvariance(), 0.8f); mx[i] = raw_distance(pMP->GetMaxDistanceInvariance(), 1.2f);      // mfMinDistance / mfMaxDistance
         }
         std::vector<int32_t> cmp(n, -1);
         for (int j = 0; j < n; ++j) if (CurrentFrame.mvpMapPoints[j]) cmp[j] = nkf + j;
@@ -451,7 +451,7 @@ protected:
             for (int k = 0; k < 3; ++k) xyz[3 * (size_t)i + k] = P.template at<float>(k, 0);
             if (variant != 2) { const cv::Mat Nn = p->GetNormal(); for (int k = 0; k < 3; ++k) nrm[3 * (size_t)i + k] = Nn.template at<float>(k, 0); }
             std::memcpy(&desc[(size_t)i * 32], d.template ptr<uint8_t>(), 32);
-            mn[i] = p->GetMinDistanceInvariance() / 0.8f; mx[i] = p->GetMaxDistanceInvariance() / 1.2f;
+            mn[i] = raw_distance(p->GetMinDistanceInvariance(), 0.8f); mx[i] = raw_distance(p->GetMaxDistanceInvariance(), 1.2f);
         }
         bi.assign(nmp, -1); bd.assign(nmp, 256);
         int nmatches = 0;
@@ -462,6 +462,19 @@ protected:
 
     static void check(int status) {
         if (status != SGS_OK) throw std::runtime_error(std::string("sgs: ") + sgs_last_error());
+    }
+
+    // MapPoint only exposes k * mfMinDistance / k * mfMaxDistance (GetMin/MaxDistanceInvariance, k = 0.8f / 1.2f); the C ABI takes the raw distances and
+    // applies k itself.  inv / k is not always a float whose product with k gives inv back, so the neighbours are tried: the value returned satisfies
+    // k * x == inv exactly, i.e. the kernels' distance gates are bit-identical to the reference's.  (PredictScale divides the raw mfMaxDistance; where several
+    // floats satisfy the equation the one chosen may be 1 ulp off the member -- add `float GetMaxDistance()` to MapPoint to remove even that.)
+    static float raw_distance(float inv, float k) {
+        float x = inv / k;
+        if (k * x != inv) {
+            const float up = std::nextafter(x, INFINITY), dn = std::nextafter(x, -INFINITY);
+            if (k * up == inv) x = up; else if (k * dn == inv) x = dn;
+        }
+        return x;
     }
 
     float mfNNratio;
