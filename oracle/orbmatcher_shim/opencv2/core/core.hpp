@@ -1,0 +1,151 @@
+// Stand-in for <opencv2/core/core.hpp>, just enough to compile the reference's own src/ORBmatcher.cc WITHOUT OpenCV as the parity pin of the matcher
+// control flow (oracle/_ref/liborbmatcher_ref.so, recipe in oracle/Makefile).  TEST INFRASTRUCTURE: nothing under sg-slam_b200/ or include/ includes it.
+//
+// cv::Mat here is a reference-counted 2-D array of CV_32F or CV_8U with row / column views.  The float arithmetic the matchers use goes through a small
+// MatExpr so that it is evaluated the way OpenCV evaluates it -- the rules were probed with cv2 and are pinned by tests/golden/frustum.npz
+// (tests/golden/make_golden_frustum.py evaluates the reference's expressions with the real cv2.gemm / cv2.norm):
+//   * A*B (+C) with untransposed small operands = gemm(A, B, alpha, C, beta) on OpenCV's small-matrix path: float products summed in float, left to
+//     right, then one rounding of (double)sum * alpha + (double)c * beta;
+//   * a transposed operand (A.t()*B, as in -Rcw.t()*tcw) takes the general path: double accumulator, one cast;
+//   * cv::norm and Mat::dot accumulate in double.
+// Scalar scaling (s*A, A/s: Sim3 helpers of the loop-closing matchers) is plain float arithmetic here and NOT part of the pin.
+#pragma once
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#define CV_8U 0
+#define CV_32F 5
+typedef unsigned char uchar;
+
+namespace cv {
+
+struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
+
+class MatExpr;
+
+class Mat {
+public:
+    int rows = 0, cols = 0;
+    uchar* data = nullptr;
+    size_t step = 0;                                       // bytes between rows
+    Mat() {}
+    Mat(int r, int c, int type) { create(r, c, type); }
+    Mat(const MatExpr& e);
+    Mat& operator=(const MatExpr& e);
+    void create(int r, int c, int type) {
+        type_ = type; rows = r; cols = c; step = (size_t)c * esz();
+        buf_ = std::make_shared<std::vector<uchar>>((size_t)r * step, (uchar)0);
+        data = buf_->data();
+    }
+    int type() const { return type_; }
+    bool empty() const { return !data || rows * cols == 0; }
+    Mat clone() const {
+        Mat m(rows, cols, type_);
+        for (int r = 0; r < rows; ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz());
+        return m;
+    }
+    static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
+    static Mat eye(int r, int c, int type) { Mat m(r, c, type); for (int i = 0; i < std::min(r, c); ++i) m.at<float>(i, i) = 1.f; return m; }
+    Mat view(int r0, int r1, int c0, int c1) const {
+        Mat m; m.type_ = type_; m.buf_ = buf_; m.rows = r1 - r0; m.cols = c1 - c0; m.step = step; m.data = data + (size_t)r0 * step + (size_t)c0 * esz();
+        return m;
+    }
+    Mat row(int r) const { return view(r, r + 1, 0, cols); }
+    Mat col(int c) const { return view(0, rows, c, c + 1); }
+    Mat rowRange(int a, int b) const { return view(a, b, 0, cols); }
+    Mat colRange(int a, int b) const { return view(0, rows, a, b); }
+    template <class T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
+    template <class T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
+    template <class T> T& at(int r, int c) { return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+    template <class T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+    template <class T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }                       // vectors only
+    template <class T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+    MatExpr t() const;
+    double dot(const Mat& o) const {
+        double s = 0;
+        for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) s += (double)at<float>(r, c) * (double)o.at<float>(r, c);
+        return s;
+    }
+    void copyTo(Mat& o) const { o = clone(); }
+private:
+    int type_ = CV_8U;
+    size_t esz() const { return type_ == CV_32F ? 4 : 1; }
+    std::shared_ptr<std::vector<uchar>> buf_;
+};
+
+// alpha * op(a) [* b] [+ beta * c]   or   a + sign * b
+class MatExpr {
+public:
+    enum Kind { SCALE, GEMM, ADD };
+    Kind kind = SCALE;
+    Mat a, b, c;
+    bool ta = false, has_c = false;
+    double alpha = 1, beta = 0, sign = 1;
+    Mat eval() const {
+        if (kind == ADD) {
+            Mat m(a.rows, a.cols, CV_32F);
+            for (int r = 0; r < a.rows; ++r) for (int cc = 0; cc < a.cols; ++cc) m.at<float>(r, cc) = sign > 0 ? a.at<float>(r, cc) + b.at<float>(r, cc) : a.at<float>(r, cc) - b.at<float>(r, cc);
+            return m;
+        }
+        if (kind == SCALE) {
+            const int R = ta ? a.cols : a.rows, C = ta ? a.rows : a.cols;
+            Mat m(R, C, CV_32F);
+            for (int r = 0; r < R; ++r) for (int cc = 0; cc < C; ++cc) { const float v = ta ? a.at<float>(cc, r) : a.at<float>(r, cc); m.at<float>(r, cc) = alpha == 1 ? v : alpha == -1 ? -v : (float)alpha * v; }
+            return m;
+        }
+        const int M = ta ? a.cols : a.rows, K = ta ? a.rows : a.cols, N = b.cols;
+        Mat m(M, N, CV_32F);
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < N; ++j) {
+                if (!ta) {                                // small-matrix path: float sum, left to right
+                    float acc = 0.f;
+                    for (int k = 0; k < K; ++k) { const float p = a.at<float>(i, k) * b.at<float>(k, j); acc = k == 0 ? p : acc + p; }
+                    m.at<float>(i, j) = (float)((double)acc * alpha + (has_c ? (double)c.at<float>(i, j) * beta : 0.0));
+                } else {                                  // general path: double accumulator
+                    double acc = 0;
+                    for (int k = 0; k < K; ++k) acc += (double)a.at<float>(k, i) * (double)b.at<float>(k, j);
+                    m.at<float>(i, j) = (float)(acc * alpha + (has_c ? (double)c.at<float>(i, j) * beta : 0.0));
+                }
+            }
+        return m;
+    }
+    MatExpr t() const { MatExpr e = *this; if (e.kind == SCALE) e.ta = !e.ta; else { Mat m = eval(); e = MatExpr(); e.a = m; e.ta = true; } return e; }
+    template <class T> T at(int i) const { return eval().at<T>(i); }
+};
+inline Mat::Mat(const MatExpr& e) { *this = e.eval(); }
+inline Mat& Mat::operator=(const MatExpr& e) { *this = e.eval(); return *this; }
+inline MatExpr Mat::t() const { MatExpr e; e.a = *this; e.ta = true; return e; }
+
+inline MatExpr operator*(const Mat& a, const Mat& b) { MatExpr e; e.kind = MatExpr::GEMM; e.a = a; e.b = b; return e; }
+inline MatExpr operator*(const MatExpr& x, const Mat& b) {
+    MatExpr e;
+    if (x.kind == MatExpr::SCALE) { e.kind = MatExpr::GEMM; e.a = x.a; e.ta = x.ta; e.alpha = x.alpha; e.b = b; }
+    else { e.kind = MatExpr::GEMM; e.a = x.eval(); e.b = b; }
+    return e;
+}
+inline MatExpr operator+(const MatExpr& x, const Mat& c) {
+    if (x.kind == MatExpr::GEMM && !x.has_c) { MatExpr e = x; e.c = c; e.has_c = true; e.beta = 1; return e; }
+    MatExpr e; e.kind = MatExpr::ADD; e.a = x.eval(); e.b = c; return e;
+}
+inline MatExpr operator+(const Mat& a, const Mat& b) { MatExpr e; e.kind = MatExpr::ADD; e.a = a; e.b = b; return e; }
+inline MatExpr operator-(const Mat& a, const Mat& b) { MatExpr e; e.kind = MatExpr::ADD; e.a = a; e.b = b; e.sign = -1; return e; }
+inline MatExpr operator-(const Mat& a) { MatExpr e; e.a = a; e.alpha = -1; return e; }
+inline MatExpr operator-(const MatExpr& x) { MatExpr e = x; if (e.kind == MatExpr::ADD) { Mat m = x.eval(); e = MatExpr(); e.a = m; e.alpha = -1; } else e.alpha = -e.alpha; return e; }
+inline MatExpr operator*(double s, const Mat& a) { MatExpr e; e.a = a; e.alpha = s; return e; }
+inline MatExpr operator*(double s, const MatExpr& x) { MatExpr e = x; if (e.kind == MatExpr::ADD) { Mat m = x.eval(); e = MatExpr(); e.a = m; e.alpha = s; } else e.alpha *= s; return e; }
+inline MatExpr operator/(const Mat& a, double s) { MatExpr e; e.a = a; e.alpha = (double)(1.f / (float)s); return e; }
+
+inline double norm(const Mat& m) {
+    double s = 0;
+    for (int r = 0; r < m.rows; ++r) for (int c = 0; c < m.cols; ++c) { const double v = m.at<float>(r, c); s += v * v; }
+    return std::sqrt(s);
+}
+inline double norm(const MatExpr& e) { return norm(e.eval()); }
+
+}  // namespace cv
