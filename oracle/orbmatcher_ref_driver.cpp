@@ -187,3 +187,121 @@ REF_API int ref_search_by_bow_kfkf(int n1, const int32_t* node1, const double* w
     for (int i = 0; i < n1; ++i) match_1[i] = vp[i] ? (int32_t)(vp[i] - p2.data()) : -1;
     return nm;
 }
+
+// ORBmatcher(0.6, check_ori).SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)  (src/ORBmatcher.cc:659-827).  free = the feature has NO map
+// point; stereo = mvuRight >= 0.  The epipole comes from the poses as in the reference: KF2 at the identity, KF1's camera centre at `cw1`.  match_1[i1] = i2 or -1.
+REF_API int ref_search_for_triangulation(int n1, const int32_t* node1, const double* weight1, const uint8_t* free1, const uint8_t* stereo1, const uint8_t* desc1,
+                                         const float* xy1, const float* angle1, int n2, const int32_t* node2, const double* weight2, const uint8_t* free2,
+                                         const uint8_t* stereo2, const uint8_t* desc2, const float* xy2, const int32_t* octave2, const float* angle2, const float* F12,
+                                         const float* cw1, const float* cam, int nlevels, const float* sigma2, const float* scale, int only_stereo, int check_ori,
+                                         int32_t* match_1) {
+    KeyFrame k1, k2;
+    std::vector<MapPoint> p1(n1), p2(n2);
+    auto fill = [&](KeyFrame& k, std::vector<MapPoint>& pts, int n, const int32_t* node, const double* w, const uint8_t* fr, const uint8_t* st, const uint8_t* desc,
+                    const float* xy, const int32_t* oct, const float* ang) {
+        k.N = n; k.mvKeysUn.resize(n); k.mvpMapPoints.assign(n, static_cast<MapPoint*>(NULL)); k.mDescriptors.create(n > 0 ? n : 1, 32, CV_8U); k.mvuRight.resize(n);
+        for (int i = 0; i < n; ++i) {
+            k.mvKeysUn[i].pt.x = xy[2 * i]; k.mvKeysUn[i].pt.y = xy[2 * i + 1]; k.mvKeysUn[i].angle = ang[i]; k.mvKeysUn[i].octave = oct ? oct[i] : 0;
+            std::memcpy(k.mDescriptors.ptr<uint8_t>(i), desc + 32 * (size_t)i, 32);
+            if (!fr[i]) k.mvpMapPoints[i] = &pts[i];
+            k.mvuRight[i] = st[i] ? 1.f : -1.f;
+        }
+        fill_featvec(k.mFeatVec, n, node, w);
+        k.fx = cam[0]; k.fy = cam[1]; k.cx = cam[2]; k.cy = cam[3];
+        k.mvScaleFactors.assign(scale, scale + nlevels); k.mvLevelSigma2.assign(sigma2, sigma2 + nlevels);
+        k.Tcw = cv::Mat::eye(4, 4, CV_32F); k.Ow = cv::Mat::zeros(3, 1, CV_32F);
+    };
+    fill(k1, p1, n1, node1, weight1, free1, stereo1, desc1, xy1, nullptr, angle1);
+    fill(k2, p2, n2, node2, weight2, free2, stereo2, desc2, xy2, octave2, angle2);
+    for (int k = 0; k < 3; ++k) k1.Ow.at<float>(k) = cw1[k];
+    cv::Mat F(3, 3, CV_32F);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F.at<float>(r, c) = F12[3 * r + c];
+    std::vector<std::pair<size_t, size_t> > pairs;
+    ORBmatcher matcher(0.6, check_ori != 0);
+    const int nm = matcher.SearchForTriangulation(&k1, &k2, F, pairs, only_stereo != 0);
+    for (int i = 0; i < n1; ++i) match_1[i] = -1;
+    for (const auto& pr : pairs) match_1[pr.first] = (int32_t)pr.second;
+    return nm;
+}
+
+// ORBmatcher(0.75, true).SearchByProjection(pKF, Scw, vpPoints, vpMatched, th)  (src/ORBmatcher.cc:292-405, loop closing).  kf_matched_inout[idx] >= 0 = the key
+// frame's feature idx is already matched on entry; features claimed by the call hold the claiming point's index afterwards.
+REF_API int ref_search_by_projection_sim3(int n, const Kp* kps, const float* uright, const uint8_t* desc, const float* cam, int nlevels, const float* scale_factors,
+                                          const float* scw16, int nmp, const uint8_t* mp_valid, const float* mp_xyz, const float* mp_normal, const float* min_dist,
+                                          const float* max_dist, const uint8_t* mp_desc, int th, int32_t* kf_matched_inout) {
+    KeyFrame kf;
+    {   // the grid owner part of a key frame is filled like a frame's
+        Frame tmp;
+        fill_frame(tmp, n, kps, uright, desc, cam, nlevels, scale_factors, nullptr);
+        static_cast<GridOwner&>(kf) = static_cast<GridOwner&>(tmp);
+    }
+    std::vector<MapPoint> pts(nmp), taken(n);
+    std::vector<MapPoint*> vp(nmp), vm(n, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < nmp; ++i) {
+        MapPoint& p = pts[i];
+        set_vec3(p.mWorldPos, mp_xyz + 3 * i); set_vec3(p.mNormalVector, mp_normal + 3 * i); set_desc(p.mDescriptor, mp_desc + 32 * (size_t)i);
+        p.mfMinDistance = min_dist[i]; p.mfMaxDistance = max_dist[i]; p.mbBad = !mp_valid[i]; p.nObs = 1;
+        vp[i] = &p;
+    }
+    for (int j = 0; j < n; ++j) if (kf_matched_inout[j] >= 0) vm[j] = &taken[j];
+    cv::Mat Scw(4, 4, CV_32F);
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) Scw.at<float>(r, c) = scw16[4 * r + c];
+    ORBmatcher matcher(0.75, true);
+    const int nm = matcher.SearchByProjection(&kf, Scw, vp, vm, th);
+    for (int j = 0; j < n; ++j) if (vm[j] && vm[j] >= pts.data() && vm[j] < pts.data() + nmp) kf_matched_inout[j] = (int32_t)(vm[j] - pts.data());
+    return nm;
+}
+
+// ORBmatcher().Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:829-980) and Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (:982-1104, scw16 != NULL).  The key
+// frame starts without map points; kf_obs[j] = -1, or the Observations() of a map point the feature j already holds.  Outputs per input point: best_idx =
+// the feature it was fused onto (read back from the side effects: AddObservation's index, the resident of a Replace, vpReplacePoint) or -1 when the reference
+// did not fuse it; returns nFused.
+REF_API int ref_fuse(int n, const Kp* kps, const float* uright, const uint8_t* desc, const float* cam, int nlevels, const float* scale_factors, const float* tcw16,
+                     const float* ow3, const float* scw16, int nmp, const uint8_t* mp_valid, const float* mp_xyz, const float* mp_normal, const float* min_dist,
+                     const float* max_dist, const uint8_t* mp_desc, const int32_t* mp_nobs, const int32_t* kf_obs, float th, const float* inv_level_sigma2,
+                     int32_t* best_idx) {
+    KeyFrame kf;
+    {
+        Frame tmp;
+        fill_frame(tmp, n, kps, uright, desc, cam, nlevels, scale_factors, nullptr);
+        static_cast<GridOwner&>(kf) = static_cast<GridOwner&>(tmp);
+    }
+    kf.mvInvLevelSigma2.assign(inv_level_sigma2, inv_level_sigma2 + nlevels);
+    kf.mvpMapPoints.assign(n, static_cast<MapPoint*>(NULL));
+    kf.Tcw.create(4, 4, CV_32F);
+    if (tcw16) for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) kf.Tcw.at<float>(r, c) = tcw16[4 * r + c];
+    kf.Ow.create(3, 1, CV_32F);
+    if (ow3) for (int k = 0; k < 3; ++k) kf.Ow.at<float>(k) = ow3[k];
+    std::vector<MapPoint> pts(nmp), res(n);
+    std::vector<MapPoint*> vp(nmp);
+    for (int j = 0; j < n; ++j) if (kf_obs[j] >= 0) { res[j].nObs = kf_obs[j]; res[j].mObservations[&kf] = j; kf.mvpMapPoints[j] = &res[j]; }
+    for (int i = 0; i < nmp; ++i) {
+        MapPoint& p = pts[i];
+        set_vec3(p.mWorldPos, mp_xyz + 3 * i); set_vec3(p.mNormalVector, mp_normal + 3 * i); set_desc(p.mDescriptor, mp_desc + 32 * (size_t)i);
+        p.mfMinDistance = min_dist[i]; p.mfMaxDistance = max_dist[i]; p.mbBad = !mp_valid[i]; p.nObs = mp_nobs[i];
+        vp[i] = &p; best_idx[i] = -1;
+    }
+    std::vector<RefEvent> log;
+    ref_event_log() = &log;
+    int nf;
+    ORBmatcher matcher;
+    if (scw16) {
+        cv::Mat Scw(4, 4, CV_32F);
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) Scw.at<float>(r, c) = scw16[4 * r + c];
+        std::vector<MapPoint*> rep(nmp, static_cast<MapPoint*>(NULL));
+        nf = matcher.Fuse(&kf, Scw, vp, th, rep);
+        for (int i = 0; i < nmp; ++i) if (rep[i]) best_idx[i] = (int32_t)rep[i]->GetIndexInKeyFrame(&kf);
+    } else nf = matcher.Fuse(&kf, vp, th);
+    ref_event_log() = nullptr;
+    auto is_input = [&](MapPoint* p) { return p >= pts.data() && p < pts.data() + nmp; };
+    for (const RefEvent& e : log) {
+        if (e.kind == 0) { if (is_input(e.a)) best_idx[e.a - pts.data()] = (int32_t)e.idx; }
+        else {                                                         // a->Replace(b): one of the two is the point being fused, the other sits in the key frame
+            MapPoint* in = nullptr; MapPoint* resident = nullptr;
+            if (e.a->IsInKeyFrame(&kf) && !e.b->IsInKeyFrame(&kf)) { resident = e.a; in = e.b; }
+            else if (e.b->IsInKeyFrame(&kf) && !e.a->IsInKeyFrame(&kf)) { resident = e.b; in = e.a; }
+            if (in && is_input(in)) best_idx[in - pts.data()] = (int32_t)resident->GetIndexInKeyFrame(&kf);
+        }
+    }
+    return nf;
+}

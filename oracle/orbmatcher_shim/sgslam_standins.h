@@ -26,6 +26,11 @@ namespace ORB_SLAM2 {
 
 class KeyFrame;
 class Frame;
+class MapPoint;
+
+// side effects of Fuse, in call order, for the driver to read back (kind 0: a->AddObservation(kf, idx); kind 1: a->Replace(b))
+struct RefEvent { int kind; MapPoint* a; MapPoint* b; long idx; };
+inline std::vector<RefEvent>*& ref_event_log() { static std::vector<RefEvent>* log = nullptr; return log; }
 
 class MapPoint {
 public:
@@ -50,8 +55,12 @@ public:
     inline int PredictScale(const float& currentDist, Frame* pF);
     bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
     int GetIndexInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) ? (int)mObservations[pKF] : -1; }
-    void AddObservation(KeyFrame* pKF, size_t idx) { if (!mObservations.count(pKF)) { mObservations[pKF] = idx; ++nObs; } }
-    void Replace(MapPoint* pMP) { mpReplaced = pMP; mbBad = true; }
+    void AddObservation(KeyFrame* pKF, size_t idx) {
+        if (ref_event_log()) ref_event_log()->push_back(RefEvent{0, this, nullptr, (long)idx});
+        if (!mObservations.count(pKF)) { mObservations[pKF] = idx; ++nObs; }
+    }
+    // recorded only: the point stays usable, so that every later fusion onto the same feature leaves a trace too (the real Replace rewires the map)
+    void Replace(MapPoint* pMP) { if (ref_event_log()) ref_event_log()->push_back(RefEvent{1, this, pMP, -1}); mpReplaced = pMP; }
 };
 
 struct GridOwner {       // the members Frame and KeyFrame share for the feature grid

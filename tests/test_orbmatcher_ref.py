@@ -168,3 +168,102 @@ def test_search_by_bow_equals_the_reference(seed):
         m1 = np.zeros(len(nk), np.int32)
         nm_r = L.ref_search_by_bow_kfkf(len(nk), _p(nk), _p(wk), _p(kv), _p(kd), _p(ka), len(nf), _p(nf), _p(wf), _p(fv), _p(fd), _p(fa), C.c_float(0.8), int(ori), _p(m1))
         assert nm_r == nm_o and np.array_equal(m1, m_o) and nm_o > 50
+
+
+@pytest.mark.parametrize('only,ori', [(False, False), (True, False), (False, True)])
+def test_search_for_triangulation_equals_the_reference(only, ori):
+    """SearchForTriangulation + CheckDistEpipolarLine (src/ORBmatcher.cc:659-827, :140-157); the epipole is computed by the reference's own lines from the poses."""
+    L = _lib(); L.ref_search_for_triangulation.restype = C.c_int
+    f32 = np.float32
+    voc = S.random_vocabulary(6, k=6, L=2)
+    V = O.Vocabulary(voc['k'], voc['L'], voc['parent'], voc['desc'], voc['weight'])
+    rs = np.random.RandomState(2)
+    n1, n2 = 420, 460
+    s = S.bow_pair_scenario(11, voc, n_kf=n1, n_f=n2, flips=25)
+    d1b = np.unpackbits(s['kf_desc'], axis=1).astype(np.int16); d2b = np.unpackbits(s['f_desc'], axis=1).astype(np.int16)
+    src = np.array([int(np.argmin(np.abs(d1b - d2b[j]).sum(1))) for j in range(n2)])
+    xy1 = np.c_[rs.uniform(20, 620, n1), rs.uniform(20, 460, n1)].astype(f32)
+    xy2 = np.c_[xy1[src, 0] + rs.uniform(-40, 40, n2), xy1[src, 1] + rs.normal(0, 1.5, n2)].astype(f32)
+    sf = S.scale_factors().astype(f32); sigma2 = (sf * sf).astype(f32)
+    _, w1, nd1 = V.transform(s['kf_desc'], 1); _, w2, nd2 = V.transform(s['f_desc'], 1)
+    k1 = dict(node=nd1, weight=w1, free=(rs.rand(n1) < 0.8).astype(np.uint8), stereo=(rs.rand(n1) < 0.5).astype(np.uint8), desc=s['kf_desc'], xy=xy1, angle=s['kf_angle'])
+    k2 = dict(node=nd2, weight=w2, free=(rs.rand(n2) < 0.8).astype(np.uint8), stereo=(rs.rand(n2) < 0.5).astype(np.uint8), desc=s['f_desc'], xy=xy2,
+              octave=rs.randint(0, 8, n2).astype(np.int32), angle=s['f_angle'])
+    F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], f32)
+    cam = np.array([535.4, 539.2, 320.1, 247.6, 40.0, 0, 0, 640, 480], f32)
+    cw = np.array([0.31, -0.07, 2.5], f32)
+    # the reference's lines :666-672 with KF2 at the identity: C2 = R2w*Cw + t2w = Cw (small-matrix gemm: exact here), invz = 1.0f / C2z, ex = fx*C2x*invz + cx
+    invz = f32(1.0) / cw[2]
+    ex = f32(f32(f32(cam[0] * cw[0]) * invz) + cam[2]); ey = f32(f32(f32(cam[1] * cw[1]) * invz) + cam[3])
+    nm_o, m_o = O.search_for_triangulation(k1, k2, F12, float(ex), float(ey), sigma2, sf, only, ori)
+    a = [np.ascontiguousarray(k1['node'], np.int32), np.ascontiguousarray(k1['weight'], np.float64), np.ascontiguousarray(k1['free'], np.uint8), np.ascontiguousarray(k1['stereo'], np.uint8),
+         np.ascontiguousarray(k1['desc'], np.uint8), np.ascontiguousarray(k1['xy'], f32), np.ascontiguousarray(k1['angle'], f32)]
+    b = [np.ascontiguousarray(k2['node'], np.int32), np.ascontiguousarray(k2['weight'], np.float64), np.ascontiguousarray(k2['free'], np.uint8), np.ascontiguousarray(k2['stereo'], np.uint8),
+         np.ascontiguousarray(k2['desc'], np.uint8), np.ascontiguousarray(k2['xy'], f32), np.ascontiguousarray(k2['octave'], np.int32), np.ascontiguousarray(k2['angle'], f32)]
+    m = np.zeros(n1, np.int32)
+    nm_r = L.ref_search_for_triangulation(n1, *[_p(x) for x in a], n2, *[_p(x) for x in b], _p(F12.reshape(9).copy()), _p(cw), _p(cam), len(sf), _p(sigma2), _p(sf), int(only), int(ori), _p(m))
+    assert nm_r == nm_o, (nm_r, nm_o)
+    assert np.array_equal(m, m_o) and nm_o > 5
+
+
+@pytest.mark.parametrize('seed,ncur,nmp,th', [(0, 900, 1200, 10), (1, 1000, 1500, 10), (2, 800, 900, 4)])
+def test_search_by_projection_sim3_equals_the_reference(seed, ncur, nmp, th):
+    """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (src/ORBmatcher.cc:292-405): the order-dependent claims of the loop-closing search.  Scw has scale 1
+    (RGB-D); the reference's own decomposition (row norm, division, -Rcw.t()*tcw) runs inside the call -- the test requires that the row norm rounds to 1.0f so
+    that the Mat / scalar division (not pinned by the stand-in) is the identity."""
+    import test_match_sim3 as TS
+    L = _lib(); L.ref_search_by_projection_sim3.restype = C.c_int
+    f32 = np.float32
+    s, _, nrm, matched = TS.sim3_inputs(seed, ncur, nmp)
+    T = np.ascontiguousarray(s['Tcw_cur'], f32)
+    R = T[:3, :3]; t = T[:3, 3]
+    assert f32(np.sqrt(np.dot(R[0].astype(np.float64), R[0].astype(np.float64)))) == f32(1.0)
+    Ow = np.array([f32(-(float(R[0, r]) * float(t[0]) + float(R[1, r]) * float(t[1]) + float(R[2, r]) * float(t[2]))) for r in range(3)], f32)      # -Rcw.t()*tcw, double accumulator
+    fo = _frame(s)
+    nm_o, m_o = O.search_by_projection_sim3(fo, T, Ow, s['kf_valid'], s['last_xyz'], nrm, s['min_dist'], s['max_dist'], s['last_desc'], float(th), matched)
+    kps = np.ascontiguousarray(s['kps'], O.KP_DTYPE); ur = np.ascontiguousarray(s['uright'], f32); d = np.ascontiguousarray(s['desc'], np.uint8)
+    sf = np.ascontiguousarray(s['sf'], f32); cam = _cam(s)
+    a = [np.ascontiguousarray(s['kf_valid'], np.uint8), np.ascontiguousarray(s['last_xyz'], f32), np.ascontiguousarray(nrm, f32), np.ascontiguousarray(s['min_dist'], f32),
+         np.ascontiguousarray(s['max_dist'], f32), np.ascontiguousarray(s['last_desc'], np.uint8)]
+    m = np.ascontiguousarray(matched, np.int32).copy()
+    nm_r = L.ref_search_by_projection_sim3(len(kps), _p(kps), _p(ur), _p(d), _p(cam), len(sf), _p(sf), _p(T.reshape(16).copy()), len(a[0]), *[_p(x) for x in a], int(th), _p(m))
+    assert nm_r == nm_o, (nm_r, nm_o)
+    assert np.array_equal(m, m_o) and nm_o > 20
+
+
+def _fuse_inputs(seed, ncur, nmp):
+    s = S.keyframe_scenario(seed, n_cur=ncur, n_kf=nmp, conflict=0.3)
+    rs = np.random.RandomState(seed + 7)
+    T = np.ascontiguousarray(s['Tcw_cur'], np.float32)
+    R = T[:3, :3]; t = T[:3, 3]
+    Ow = np.array([np.float32(-(float(R[0, r]) * float(t[0]) + float(R[1, r]) * float(t[1]) + float(R[2, r]) * float(t[2]))) for r in range(3)], np.float32)
+    to = s['last_xyz'].astype(np.float64) - Ow.astype(np.float64); d = np.linalg.norm(to, axis=1)
+    nrm = to / np.maximum(d[:, None], 1e-9) + rs.normal(0, 0.6, (nmp, 3)); nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    return s, T, Ow, nrm, rs
+
+
+@pytest.mark.parametrize('seed,ncur,nmp,th,sim3', [(1, 1000, 1000, 3.0, 0), (2, 1500, 3000, 3.0, 0), (3, 400, 2000, 5.0, 0), (4, 1000, 2000, 4.0, 1), (6, 900, 1500, 4.0, 1)])
+def test_fuse_equals_the_reference(seed, ncur, nmp, th, sim3):
+    """Both Fuse forms (src/ORBmatcher.cc:829-980, :982-1104): the feature every map point is fused onto, read back from the reference's side effects
+    (AddObservation / Replace / vpReplacePoint), must be the oracle's best feature whenever its distance is <= TH_LOW, and nFused the number of those."""
+    L = _lib(); L.ref_fuse.restype = C.c_int
+    f32 = np.float32
+    s, T, Ow, nrm, rs = _fuse_inputs(seed, ncur, nmp)
+    sf = np.ascontiguousarray(s['sf'], f32); inv_s2 = (1.0 / (sf * sf)).astype(f32)
+    if sim3:
+        assert f32(np.sqrt(np.dot(T[0, :3].astype(np.float64), T[0, :3].astype(np.float64)))) == f32(1.0)       # Scw / scw is the identity (see the Sim3 projection test)
+    fo = _frame(s)
+    bi_o, bd_o = O.fuse_search(fo, T, Ow, s['kf_valid'], s['last_xyz'], nrm, s['min_dist'], s['max_dist'], s['last_desc'], th, inv_s2, sim3_variant=sim3)
+    fused_o = (bi_o >= 0) & (bd_o <= 50)
+    kps = np.ascontiguousarray(s['kps'], O.KP_DTYPE); ur = np.ascontiguousarray(s['uright'], f32); d = np.ascontiguousarray(s['desc'], np.uint8); cam = _cam(s)
+    a = [np.ascontiguousarray(s['kf_valid'], np.uint8), np.ascontiguousarray(s['last_xyz'], f32), np.ascontiguousarray(nrm, f32), np.ascontiguousarray(s['min_dist'], f32),
+         np.ascontiguousarray(s['max_dist'], f32), np.ascontiguousarray(s['last_desc'], np.uint8)]
+    nobs = rs.randint(0, 5, nmp).astype(np.int32)
+    kf_obs = np.where(rs.rand(ncur) < 0.3, rs.randint(0, 5, ncur), -1).astype(np.int32)       # some features of the key frame already hold a map point
+    best = np.zeros(nmp, np.int32)
+    nf = L.ref_fuse(len(kps), _p(kps), _p(ur), _p(d), _p(cam), len(sf), _p(sf), _p(T.reshape(16).copy()), _p(Ow), _p(T.reshape(16).copy()) if sim3 else None, nmp,
+                    *[_p(x) for x in a], _p(nobs), _p(kf_obs), C.c_float(th), _p(inv_s2), _p(best))
+    assert nf == int(fused_o.sum()), (nf, int(fused_o.sum()))
+    assert np.array_equal(best >= 0, fused_o)
+    assert np.array_equal(best[fused_o], bi_o[fused_o])
+    assert nf > 10
