@@ -206,7 +206,7 @@ def postprocess(rows, img_w, img_h, det_thr, dyn_thr):
             objs.append([lab, v[1], *r])
             if lab == PERSON:
                 dyn_map.append(r)
-                if v[1] > np.float32(0.2): dyn_rm.append(r)
+                if float(v[1]) > 0.2: dyn_rm.append(r)          # `object2d.prob > 0.2`: the float against the DOUBLE literal (Detector2D.cc:78; pinned by tests/test_detector2d_ref.py)
     f = lambda a, k: np.array(a, np.float32).reshape(-1, k)
     return f(objs, 6), f(dyn_map, 4), f(dyn_rm, 4)
 

@@ -26,6 +26,18 @@ typedef unsigned char uchar;
 namespace cv {
 
 struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
+// geometry PODs of the detector's post-processing and of its (never executed) drawing helper
+struct Point { int x = 0, y = 0; Point() {} Point(int x_, int y_) : x(x_), y(y_) {} };
+struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };
+struct Scalar { double v[4]; Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : v{a, b, c, d} {} };
+template <class T> struct Rect_ {
+    T x = 0, y = 0, width = 0, height = 0;
+    Rect_() {}
+    Rect_(T x_, T y_, T w, T h) : x(x_), y(y_), width(w), height(h) {}
+    Rect_(const Point& p, const Size& s) : x((T)p.x), y((T)p.y), width((T)s.width), height((T)s.height) {}
+    template <class U> Rect_(const Rect_<U>& r) : x((T)r.x), y((T)r.y), width((T)r.width), height((T)r.height) {}
+};
+typedef Rect_<int> Rect;
 
 class MatExpr;
 
