@@ -19,13 +19,20 @@
 #include <memory>
 #include <vector>
 
+#define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
+#define CV_8UC1 0
 #define CV_32F 5
 typedef unsigned char uchar;
 
 namespace cv {
 
-struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
+struct Point2f {
+    float x = 0, y = 0;
+    Point2f() {}
+    Point2f(float x_, float y_) : x(x_), y(y_) {}
+    Point2f& operator*=(float s) { x = x * s; y = y * s; return *this; }      // Point_<float> *= float: one float multiply per coordinate
+};
 // geometry PODs of the detector's post-processing and of its (never executed) drawing helper
 struct Point { int x = 0, y = 0; Point() {} Point(int x_, int y_) : x(x_), y(y_) {} };
 struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };
@@ -38,6 +45,7 @@ template <class T> struct Rect_ {
     template <class U> Rect_(const Rect_<U>& r) : x((T)r.x), y((T)r.y), width((T)r.width), height((T)r.height) {}
 };
 typedef Rect_<int> Rect;
+typedef Point Point2i;
 
 class MatExpr;
 
@@ -48,6 +56,7 @@ public:
     size_t step = 0;                                       // bytes between rows
     Mat() {}
     Mat(int r, int c, int type) { create(r, c, type); }
+    Mat(Size sz, int type) { create(sz.height, sz.width, type); }
     Mat(const MatExpr& e);
     Mat& operator=(const MatExpr& e);
     void create(int r, int c, int type) {
@@ -62,12 +71,26 @@ public:
         for (int r = 0; r < rows; ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz());
         return m;
     }
-    static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
+    // Mat::zeros is a MatExpr in OpenCV: ASSIGNING it to a matrix of the same size and type clears that matrix IN PLACE (ORBextractor's computeDescriptors
+    // relies on it: its `descriptors = Mat::zeros(...)` must keep writing into the row range of the caller's output)
+    struct ZerosExpr { int r, c, type; };
+    static ZerosExpr zeros(int r, int c, int type) { return ZerosExpr{r, c, type}; }
+    Mat(const ZerosExpr& z) { create(z.r, z.c, z.type); }
+    Mat& operator=(const ZerosExpr& z) {
+        if (data && rows == z.r && cols == z.c && type_ == z.type) { for (int r = 0; r < rows; ++r) std::memset(data + (size_t)r * step, 0, (size_t)cols * esz()); }
+        else create(z.r, z.c, z.type);
+        return *this;
+    }
     static Mat eye(int r, int c, int type) { Mat m(r, c, type); for (int i = 0; i < std::min(r, c); ++i) m.at<float>(i, i) = 1.f; return m; }
     Mat view(int r0, int r1, int c0, int c1) const {
         Mat m; m.type_ = type_; m.buf_ = buf_; m.rows = r1 - r0; m.cols = c1 - c0; m.step = step; m.data = data + (size_t)r0 * step + (size_t)c0 * esz();
         return m;
     }
+    Mat operator()(const Rect_<int>& r) const { return view(r.y, r.y + r.height, r.x, r.x + r.width); }
+    size_t step1() const { return step / esz(); }
+    Size size() const { return Size(cols, rows); }
+    uchar* ptr(int r = 0) { return data + (size_t)r * step; }
+    const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
     Mat row(int r) const { return view(r, r + 1, 0, cols); }
     Mat col(int c) const { return view(0, rows, c, c + 1); }
     Mat rowRange(int a, int b) const { return view(a, b, 0, cols); }
@@ -160,4 +183,24 @@ inline double norm(const Mat& m) {
 }
 inline double norm(const MatExpr& e) { return norm(e.eval()); }
 
+// array proxies of the extractor's call operator
+class _InputArray { const Mat* m_; public: _InputArray(const Mat& m) : m_(&m) {} bool empty() const { return m_->empty(); } Mat getMat() const { return *m_; } };
+typedef const _InputArray& InputArray;
+class _OutputArray {
+    Mat* m_;
+public:
+    _OutputArray(Mat& m) : m_(&m) {}
+    void release() const { *m_ = Mat(); }
+    void create(int r, int c, int type) const { if (m_->rows != r || m_->cols != c || m_->type() != type || !m_->data) m_->create(r, c, type); }
+    Mat getMat() const { return *m_; }
+};
+typedef const _OutputArray& OutputArray;
+
 }  // namespace cv
+
+// cvRound = round half to even (SSE cvtsd2si / cvtss2si in OpenCV), cvFloor, cvCeil
+inline int cvRound(double v) { return (int)std::lrint(v); }
+inline int cvRound(float v) { return (int)std::lrintf(v); }
+inline int cvRound(int v) { return v; }
+inline int cvFloor(double v) { return (int)std::floor(v); }
+inline int cvCeil(double v) { return (int)std::ceil(v); }
