@@ -24,6 +24,9 @@ def main():
     once = False
     if argv and argv[0] == '--once':       # one warm-up call + one call (for an ncu launch list)
         once = True; argv = argv[1:]
+    layers = False
+    if argv and argv[0] == '--layers':     # per-kernel table (CUDA events around every launch, sgs_detector_set_profiling): kernel list of describe() with its us per call
+        layers = True; argv = argv[1:]
     if argv and argv[0] == '--size':
         W, H = [int(x) for x in argv[1].split('x')]; argv = argv[2:]
     batches = [int(a) for a in argv] or [1, 8, 64, 256]
@@ -48,6 +51,20 @@ def main():
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         print('%s %dx%d batch %4d: %8.3f ms/batch  %9.1f frames/s  %6.2f TFLOP/s (1.115 GFLOP/frame)  kernels/batch %d' % (name, W, H, F, ms, F / ms * 1e3, F * 1.115 / ms, det.num_kernels), flush=True)
+        if layers:
+            det.set_profiling(1)
+            for _ in range(6):
+                run()
+            torch.cuda.synchronize()
+            ms, nc = det.kernel_times()
+            ops = [l for l in det.describe().split('\n')[1:] if l]
+            rows = [('preprocess', ms[0])] + [(o, ms[1 + j]) for j, o in enumerate(ops)] + [('detout_class', ms[-2]), ('detout_merge', ms[-1])]
+            print('per-kernel us per call of %d frames (%d profiled calls), sum %.1f us' % (F, nc, sum(ms) / nc * 1e3))
+            for o, t in rows:
+                f = o.split(' | ')[0].split()
+                short = o if len(f) < 3 else ' '.join([f[0], f[1]] + [x for x in f if '->' in x] + (f[f.index('dw') + 2:f.index('dw') + 5] if 'dw' in f else []) + (f[f.index('tile'):] if 'tile' in f else []))
+                print('%9.1f  %s' % (t / nc * 1e3, short))
+            det.set_profiling(0)
         det.close()
 
 
