@@ -144,23 +144,35 @@ __device__ __forceinline__ void resize_coeff(int d, double scale, int sn, int& s
     a1 = max(-32768, min(32767, __float2int_rn(__fmul_rn(f, 2048.f))));
 }
 
-__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ rgb, int64_t frame_stride, int pitch, int sw, int sh, int T,
+// The coefficients depend on the destination coordinate only: one small table per source geometry (source index, the two 11-bit weights; columns, then
+// rows), rebuilt when the camera size changes -- the float / double evaluation of resize_coeff per pixel made the resize instruction-bound (81 % issue-active).
+__global__ void __launch_bounds__(256) preprocess_table_kernel(int sw, int sh, int T, int* __restrict__ tab) {
+    const int d = blockIdx.x * 256 + threadIdx.x;
+    if (d >= T) return;
+    int s, a0, a1;
+    resize_coeff(d, (double)sw / T, sw, s, a0, a1);
+    tab[d] = s; tab[T + d] = a0; tab[2 * T + d] = a1;
+    resize_coeff(d, (double)sh / T, sh, s, a0, a1);
+    tab[3 * T + d] = s; tab[4 * T + d] = a0; tab[5 * T + d] = a1;
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ rgb, int64_t frame_stride, int pitch, int T, const int* __restrict__ tab,
                                                          float m0, float m1, float m2, float* __restrict__ out) {
     const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
     if (i >= T * T) return;
     const int dy = i / T, dx = i - dy * T;
-    int sx, sy, a0, a1, b0, b1;
-    resize_coeff(dx, (double)sw / T, sw, sx, a0, a1);
-    resize_coeff(dy, (double)sh / T, sh, sy, b0, b1);
+    const int sx = __ldg(tab + dx), a0 = __ldg(tab + T + dx), a1 = __ldg(tab + 2 * T + dx);
+    const int sy = __ldg(tab + 3 * T + dy), b0 = __ldg(tab + 4 * T + dy), b1 = __ldg(tab + 5 * T + dy);
     const uint8_t* r0 = rgb + f * frame_stride + (int64_t)sy * pitch + sx * 3;
     const uint8_t* r1 = r0 + pitch;
     const float mean[3] = {m0, m1, m2};
+    float* o = out + ((int64_t)f * T * T + i) * 3;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const int h0 = r0[c] * a0 + r0[c + 3] * a1, h1 = r1[c] * a0 + r1[c + 3] * a1;
         int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
         v = max(0, min(255, v));
-        out[((int64_t)f * T * T + i) * 3 + c] = __fsub_rn((float)v, mean[c]);
+        o[c] = __fsub_rn((float)v, mean[c]);
     }
 }
 
@@ -704,6 +716,7 @@ struct sgs_detector {
     unsigned long long* d_picked = nullptr; int32_t* d_picked_n = nullptr;
     // host-call scratch
     uint8_t* d_img = nullptr; int64_t d_img_cap = 0;
+    int* d_pre_tab = nullptr; int pre_w = 0, pre_h = 0;       // resize coefficient table of the last source geometry (preprocess_table_kernel)
     sgs_object2d* d_obj = nullptr; int32_t* d_cnt = nullptr;
     int last_frames = 0;
     // optional per-kernel timing (sgs_detector_set_profiling): events around every launch of a call, read back at the next call / by sgs_detector_kernel_times
@@ -1183,7 +1196,7 @@ void sgs_detector_destroy(sgs_detector* D) {
     for (float* p : D->pool) cudaFree(p);
     for (float* p : D->weights) cudaFree(p);
     for (auto& op : D->ops) if (op.kind == OP_CONV1X1) tc::free_plan(&op.gp);
-    cudaFree(D->d_picked); cudaFree(D->d_picked_n); cudaFree(D->d_img); cudaFree(D->d_obj); cudaFree(D->d_cnt);
+    cudaFree(D->d_picked); cudaFree(D->d_picked_n); cudaFree(D->d_img); cudaFree(D->d_obj); cudaFree(D->d_cnt); cudaFree(D->d_pre_tab);
     for (auto& e : D->ev) if (e) cudaEventDestroy(e);
     delete D;
 }
@@ -1246,9 +1259,13 @@ int sgs_detector_detect_device(sgs_detector* D, const uint8_t* d_rgb, int64_t fr
     if (prof) det_collect_times(D);
     size_t evi = 0;
 #define SGS_DET_MARK() do { if (prof) cudaEventRecord(D->ev[evi++], st); } while (0)
+    if (!D->d_pre_tab) SGS_CUDA_TRY(cudaMalloc((void**)&D->d_pre_tab, (size_t)6 * T * sizeof(int)));
+    if (D->pre_w != width || D->pre_h != height) {          // stream-ordered in front of the resize; calls on one handle are serial (they share the activation pool)
+        preprocess_table_kernel<<<nblk(T), 256, 0, st>>>(width, height, T, D->d_pre_tab);
+        D->pre_w = width; D->pre_h = height;
+    }
     SGS_DET_MARK();
-    preprocess_kernel<<<dim3(nblk((int64_t)T * T), F), 256, 0, st>>>(d_rgb, frame_stride, pitch, width, height, T, 123.675f, 116.28f, 103.53f,
-                                                                     B[D->input_blob].dev);
+    preprocess_kernel<<<dim3(nblk((int64_t)T * T), F), 256, 0, st>>>(d_rgb, frame_stride, pitch, T, D->d_pre_tab, 123.675f, 116.28f, 103.53f, B[D->input_blob].dev);
     for (const Op& op : D->ops) {
         SGS_DET_MARK();
         const Blob& bi = B[op.in]; const Blob& bo = B[op.out];
