@@ -474,6 +474,9 @@ SGS_API int sgs_dynreject_batch_device(const sgs_keypoint* d_kps, const uint8_t*
  *                                  previous-frame boxes d_prev_boxes [F][max_boxes] / d_prev_nboxes [F] / d_prev_have_dyn [F]
  *                                  (all three may be NULL); d_prev_index (may be NULL): row of the batch whose boxes are the
  *                                  previous frame's, d_prev_index[f] == f marks "no previous frame"; d_F [F][9], d_info [F][4].
+ *                                  With d_prev_index the reference's file-scope state is followed: the flag of a row that is itself a
+ *                                  stream's first frame counts as false (src/Frame.cc:154-162, 482-491: the first frame never runs the
+ *                                  rejection, so it never records "previous frame had dynamic objects"; quirk Q13 in DESIGN.md).
  * ------------------------------------------------------------------------------------ */
 SGS_API int sgs_fundamental_ransac(const float* pts1_xy, const float* pts2_xy, int n, double ransac_thresh, double confidence,
                                    int max_iters, double* F, uint8_t* mask, int32_t* info, int device);

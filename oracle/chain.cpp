@@ -76,7 +76,10 @@ static void chain_one(const SgoChainArgs& A, int f) {
     double Fm[9]; int have_F = 0;
     if (g != f) {
         std::vector<float> s1(2 * (size_t)n), s2(2 * (size_t)n);
-        const int ns = sgo_select_static_pairs(cur.data(), prev.data(), n, A.boxes + (size_t)g * A.max_boxes * 4, A.nboxes[g], A.have_dyn[g], s1.data(), s2.data());
+        // the previous-frame flag is file-scope state written only inside the rejection (src/Frame.cc:482-491): a stream's first frame (its own predecessor here)
+        // never sets it, so its detections do not filter the pairs of the second frame (quirk Q13; tests/test_frame_ref.py runs the reference's own Frame.cc)
+        const int pre_have = A.have_dyn[g] && A.prev_index[g] != g;
+        const int ns = sgo_select_static_pairs(cur.data(), prev.data(), n, A.boxes + (size_t)g * A.max_boxes * 4, A.nboxes[g], pre_have, s1.data(), s2.data());
         have_F = sgo_find_fundamental_ransac(s1.data(), s2.data(), ns, 1.0, 0.99, 1000, Fm, nullptr, nullptr);
     }
     std::vector<uint8_t> keep(n > 0 ? n : 1);

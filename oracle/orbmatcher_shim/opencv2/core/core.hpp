@@ -23,6 +23,7 @@
 #define CV_8U 0
 #define CV_8UC1 0
 #define CV_32F 5
+#define CV_64F 6
 typedef unsigned char uchar;
 
 namespace cv {
@@ -108,9 +109,24 @@ public:
         return s;
     }
     void copyTo(Mat& o) const { o = clone(); }
+    // ---- what src/Frame.cc needs on top (oracle/frame_shim, the Frame.cc pin)
+    static Mat ones(int r, int c, int type) { Mat m(r, c, type); for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) m.at<float>(i, j) = 1.f; return m; }      // CV_32F only
+    void convertTo(Mat& o, int type) const {                 // CV_8U -> CV_32F (the stereo matcher's patches)
+        Mat m(rows, cols, type);
+        for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) m.at<float>(r, c) = type_ == CV_32F ? at<float>(r, c) : (float)at<uchar>(r, c);
+        o = m;
+    }
+    Mat reshape(int) const { return *this; }                // N x 2 one-channel <-> N x 1 two-channel: the same memory; cv::undistortPoints below reads N x 2 floats
+    void push_back(const Mat& row) {                         // append one row (a fresh buffer: the destination of the reference's compaction loop is never a view)
+        const int c = rows ? cols : row.cols, t = rows ? type_ : row.type_;
+        Mat m(rows + 1, c, t);
+        for (int r = 0; r < rows; ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)c * m.esz());
+        std::memcpy(m.data + (size_t)rows * m.step, row.data, (size_t)c * m.esz());
+        *this = m;
+    }
 private:
     int type_ = CV_8U;
-    size_t esz() const { return type_ == CV_32F ? 4 : 1; }
+    size_t esz() const { return type_ == CV_64F ? 8 : type_ == CV_32F ? 4 : 1; }
     std::shared_ptr<std::vector<uchar>> buf_;
 };
 

@@ -266,7 +266,10 @@ __global__ void __launch_bounds__(kFmThreads) fm_ransac_kernel(const sgs_keypoin
     // prev_index (may be NULL): the batch row holding the previous frame's boxes; prev_index[f] == f marks a frame without a previous one
     const int fb = prev_index ? prev_index[f] : f;
     const bool no_prev = prev_index && fb == f;
-    const bool pre_dyn = prev_have_dyn && prev_have_dyn[fb] != 0;
+    // The reference keeps "the previous frame had potential dynamic objects" at file scope and writes it only inside the rejection (src/Frame.cc:482-491), which
+    // the first frame of a stream never runs (:154-162): the detections of a stream's first frame do not filter the pairs of its second frame (quirk Q13,
+    // pinned by tests/test_frame_ref.py against the reference's own Frame.cc).  With prev_index the rows say which frames are first ones.
+    const bool pre_dyn = prev_have_dyn && prev_have_dyn[fb] != 0 && !(prev_index && prev_index[fb] == fb);
     if (tid == 0) s_carry = 0;
     __syncthreads();
     if (pre_dyn && !no_prev) {

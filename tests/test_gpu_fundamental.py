@@ -146,7 +146,8 @@ def test_batch_device_with_previous_boxes():
     for f in range(1, nframes):
         n = int(counts[f]); pf = int(prev_index[f])
         cur = np.stack([kps['x'][f, :n], kps['y'][f, :n]], 1)
-        s1, s2 = O.select_static_pairs(cur, prev[f, :n], boxes[pf, :nboxes[pf]], have[pf])
+        # the previous-frame flag exists only if the previous frame ran the rejection itself (quirk Q13: frame 0's boxes do not filter frame 1's pairs)
+        s1, s2 = O.select_static_pairs(cur, prev[f, :n], boxes[pf, :nboxes[pf]], have[pf] and prev_index[pf] != pf)
         Fo, mo, io = O.find_fundamental_ransac(s1, s2)
         assert info[f, 0] == len(s1), (f, info[f], len(s1))
         if Fo is None:
@@ -154,4 +155,5 @@ def test_batch_device_with_previous_boxes():
         else:
             assert _same(F[f], Fo), f
             assert info[f, 1] == io[1] and info[f, 2] == io[0]
+    assert info[1, 0] == counts[1] and info[2, 0] < counts[2]
     assert info[3, 0] == 14 and info[3, 2] == 300          # the 14-pair frame took the LMedS branch on the device as well
