@@ -24,7 +24,7 @@ namespace tc {
 constexpr int kBM = 128;        // pixels per tile = UMMA M = TMEM lanes
 constexpr int kBK = 32;         // floats per k-block = one 128-byte swizzle row (16 = one 64-byte row for layers with at most 16 input channels)
 constexpr int kMaxStages = 8;
-constexpr int kMaxNT = 128;      // output channels per tile (TMEM columns per CTA)
+constexpr int kMaxNT = 256;      // output channels per tile (UMMA N <= 256; two accumulators = 512 TMEM columns)
 
 // ---------------------------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -432,11 +432,25 @@ inline void split_tf32_host(float x, float& hi, float& lo) {
     memcpy(&lo, &l, 4);
 }
 
-// Tiling of one layer (no device access): output-channel tiles of at most kMaxNT, weights resident when all their k-blocks fit in 96 KB,
+// Tiling of one layer (no device access): output-channel tiles of at most kMaxNT channels, weights resident when all their k-blocks fit in 96 KB,
 // ring depth from what is left of the shared memory; small weight tiles leave room for two CTAs per SM (more loads in flight, two MMA issuers).
-inline void plan_tiling(int Cin, int Cout, GemmPlan* P, int force_nt = 0) {
+// m_tiles (128-pixel tiles of the largest batch, 0 = unknown) picks the number of output-channel tiles: every tile of a pixel block re-reads the
+// activations and pays the pipeline's fill, so fewer, wider tiles win as long as they still fill the machine -- measured (profiles/r02y_nt_sweep.txt):
+// 112->672 at 19x19 takes 76 us with 6 x 112, 58 us with 3 x 224; 256->512 at 5x5 (25 pixel tiles) is fastest with 4 x 128.  The cost of a plan is
+// modelled as  waves of the persistent grid x (NT + 100)  and the cheapest tile count between Cout / 256 and Cout / 128 is taken.
+constexpr int kPlanSMs = 148;
+inline void plan_tiling(int Cin, int Cout, GemmPlan* P, int force_nt = 0, int m_tiles = 0) {
     P->Cin = Cin; P->Cout = Cout;
-    const int nt = (Cout + kMaxNT - 1) / kMaxNT;
+    int nt = (Cout + 127) / 128;
+    if (m_tiles > 0) {
+        double best = 1e300;
+        for (int n = (Cout + kMaxNT - 1) / kMaxNT; n <= (Cout + 127) / 128; ++n) {
+            const int w = ((Cout + n - 1) / n + 15) & ~15;
+            const long long waves = ((long long)m_tiles * n + kPlanSMs - 1) / kPlanSMs;
+            const double cost = (double)waves * (w + 100);
+            if (cost < best) { best = cost; nt = n; }
+        }
+    }
     P->NT = force_nt > 0 ? force_nt : ((Cout + nt - 1) / nt + 15) & ~15;
     P->n_tiles = (Cout + P->NT - 1) / P->NT;
     P->BK = Cin <= 16 ? 16 : kBK;                                        // at most 16 input channels: 64-byte operand rows, half the ring slot
@@ -449,7 +463,7 @@ inline void plan_tiling(int Cin, int Cout, GemmPlan* P, int force_nt = 0) {
     P->ctas_per_sm = (P->b_resident && b_all + 2 * a_stage + 4 * 4096 + 1024 <= 110 * 1024) ? 2 : 1;
     P->epw = P->ctas_per_sm == 2 ? 4 : 8;                                // one CTA per SM: eight epilogue warps keep up with wide output tiles
     const int epi_stage = P->epw * 4096;                                 // the epilogue warps' transpose buffers
-    const int budget = (P->ctas_per_sm == 2 ? 110 : 220) * 1024 - 1024 - epi_stage - (P->b_resident ? b_all : 0);
+    const int budget = (P->ctas_per_sm == 2 ? 110 : 226) * 1024 - 1024 - epi_stage - (P->b_resident ? b_all : 0);
     const int stage_bytes = a_stage + (P->b_resident ? 0 : b_block);
     int st = budget / stage_bytes;
     if (st > kMaxStages) st = kMaxStages;
@@ -462,8 +476,8 @@ inline void plan_tiling(int Cin, int Cout, GemmPlan* P, int force_nt = 0) {
 }
 
 // Splits and uploads W [Cout][Cin], picks the tiling.  Returns false when TMA is unavailable or an allocation fails.
-inline bool plan_weights(const float* W, int Cin, int Cout, GemmPlan* P, int force_nt = 0) {
-    plan_tiling(Cin, Cout, P, force_nt);
+inline bool plan_weights(const float* W, int Cin, int Cout, GemmPlan* P, int force_nt = 0, int m_tiles = 0) {
+    plan_tiling(Cin, Cout, P, force_nt, m_tiles);
     std::vector<float> hi((size_t)P->Np * P->Kp, 0.f), lo((size_t)P->Np * P->Kp, 0.f);
     for (int co = 0; co < Cout; ++co)
         for (int c = 0; c < Cin; ++c) split_tf32_host(W[(size_t)co * Cin + c], hi[(size_t)co * P->Kp + c], lo[(size_t)co * P->Kp + c]);
@@ -531,7 +545,7 @@ inline bool launch_conv1x1_tc_map(const GemmPlan& P, const CUtensorMap& mapA, in
     if (gx > G.m_tiles) gx = G.m_tiles;
     const dim3 grid(gx, P.n_tiles);
     auto go = [&](auto kern, int threads) -> bool {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return false;   // cheap; per device
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) return false;   // cheap; per device
         kern<<<grid, threads, P.smem_bytes, st>>>(mapA, P.map_hi, P.map_lo, bias, out, G, epi);
         return true;
     };

@@ -1027,8 +1027,9 @@ int build_graph(sgs_detector* D) {
             int fin = lout[i][0];
             if (!diag) build_tail((int)i, lout[i][0], op.epi, fin);
             if (op.kind == OP_CONV1X1) {
-                if (D->flags & 2) tc::plan_tiling(op.g.Cin, op.g.Cout, &op.gp);
-                else if (!tc::plan_weights(L.weight.data(), op.g.Cin, op.g.Cout, &op.gp)) { set_error("sgs_detector_create: layer %s: the tcgen05 GEMM could not be set up (TMA tensor maps need a CUDA 12 driver; %s)", L.name.c_str(), cudaGetErrorString(cudaGetLastError())); return SGS_ERR_CUDA; }
+                const int m_tiles = (int)std::min<int64_t>(((int64_t)D->max_frames * op.g.OH * op.g.OW + tc::kBM - 1) / tc::kBM, 1 << 30);      // pixel tiles of a full batch
+                if (D->flags & 2) tc::plan_tiling(op.g.Cin, op.g.Cout, &op.gp, 0, m_tiles);
+                else if (!tc::plan_weights(L.weight.data(), op.g.Cin, op.g.Cout, &op.gp, 0, m_tiles)) { set_error("sgs_detector_create: layer %s: the tcgen05 GEMM could not be set up (TMA tensor maps need a CUDA 12 driver; %s)", L.name.c_str(), cudaGetErrorString(cudaGetLastError())); return SGS_ERR_CUDA; }
             } else if (op.kind == OP_DWCONV) {                    // [c][ky][kx] -> [ky][kx][c]: channel vectors
                 std::vector<float> wt(L.weight.size());
                 const int kk = op.g.k * op.g.k;
