@@ -297,8 +297,8 @@ SGS_API int sgs_match_project_localmap_batch_device(sgs_matcher* m, const sgs_lo
  * Optimizer::PoseOptimization(Frame*) (src/Optimizer.cc:239-451): motion-only bundle adjustment after every matcher call, for `nframes`
  * frames (device pointers).  Map point of keypoint i: points_xyz[mp_index[i]] when mp_index is given (-1 = none; this is the cur_mp array the
  * projection matchers write), else points_xyz[i] with has_mp[i].  uright < 0 = monocular observation.  Outputs: the optimised pose, the
- * outlier flags (mvbOutlier) and nInitialCorrespondences - nBad.  Checked against a CPU restatement of the g2o algorithm (g2o itself cannot
- * be run without Eigen: parity unpinned).  scratch_err: 3 doubles per keypoint, scratch_level: 1 byte per keypoint.
+ * outlier flags (mvbOutlier) and nInitialCorrespondences - nBad.  Checked against a CPU restatement of the g2o algorithm, itself pinned against the
+ * reference's Optimizer.cc + g2o compiled unmodified on an Eigen stand-in (tests/test_optimizer_ref.py).  scratch_err: 3 doubles per keypoint, scratch_level: 1 byte per keypoint.
  * ------------------------------------------------------------------------------------ */
 typedef struct sgs_poseopt_batch {
     sgs_camera cam;                       /* fx, fy, cx, cy, bf are used */

@@ -6,7 +6,8 @@
 //
 // The function reads what the reference reads (mvpMapPoints + GetWorldPos, mvKeysUn, mvuRight, mvInvLevelSigma2, fx..cy, mbf, mTcw), writes
 // mvbOutlier and the pose (SetPose) and returns nInitialCorrespondences - nBad.  The optimiser is a restatement of the g2o algorithm the
-// reference configures (see sg-slam_b200/csrc/pose_opt.cu); it could not be compared with g2o itself in this repository (no Eigen).
+// reference configures (see sg-slam_b200/csrc/pose_opt.cu); the restatement it is checked against is pinned against the reference's own
+// Optimizer.cc + g2o compiled unmodified (tests/test_optimizer_ref.py).
 #pragma once
 #include <stdexcept>
 #include <string>

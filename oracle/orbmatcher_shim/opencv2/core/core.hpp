@@ -34,6 +34,7 @@ struct Point2f {
     Point2f(float x_, float y_) : x(x_), y(y_) {}
     Point2f& operator*=(float s) { x = x * s; y = y * s; return *this; }      // Point_<float> *= float: one float multiply per coordinate
 };
+struct Point3f { float x = 0, y = 0, z = 0; Point3f() {} Point3f(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {} };      // include/Converter.h:49
 // geometry PODs of the detector's post-processing and of its (never executed) drawing helper
 struct Point { int x = 0, y = 0; Point() {} Point(int x_, int y_) : x(x_), y(y_) {} };
 struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };

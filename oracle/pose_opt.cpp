@@ -1,6 +1,7 @@
 // oracle/pose_opt.cpp -- TEST INFRASTRUCTURE ONLY: CPU restatement of Optimizer::PoseOptimization(Frame*) (src/Optimizer.cc:239-451), the motion-only
-// bundle adjustment that follows every matcher call of the tracking thread.  PARITY UNPINNED: the reference runs g2o (vendored under
-// Thirdparty/g2o) on Eigen, and Eigen is not available here, so the real code cannot be executed to produce golden vectors.  What is restated,
+// bundle adjustment that follows every matcher call of the tracking thread.  PINNED against the reference's own src/Optimizer.cc + src/Converter.cc + vendored
+// Thirdparty/g2o compiled unmodified (oracle/_ref/liboptimizer_ref.so, on the Eigen stand-in of g2o_shim/ because this image has no Eigen): same inlier count, outlier
+// flags and float32 pose on every case of tests/test_optimizer_ref.py.  What is restated,
 // from the vendored sources, file:line relative to Thirdparty/g2o/g2o:
 //   * graph set-up, the four rounds of ten iterations from the INITIAL pose, chi-square re-classification (5.991 mono / 7.815 stereo, float
 //     compares), robust kernel dropped after the third round, early exit when fewer than ten edges exist          src/Optimizer.cc:239-451

@@ -1,5 +1,5 @@
-"""Oracle of Optimizer::PoseOptimization (src/Optimizer.cc:239-451).  g2o cannot be run here (no Eigen): the restatement is "parity unpinned".
-What can be checked without g2o: the result is the least-squares optimum of the final inlier set (an independent numpy Gauss-Newton on rotation
+"""Oracle of Optimizer::PoseOptimization (src/Optimizer.cc:239-451).  The restatement is pinned against the reference's own Optimizer.cc + g2o in
+tests/test_optimizer_ref.py; checked here independently of g2o: the result is the least-squares optimum of the final inlier set (an independent numpy Gauss-Newton on rotation
 matrices reaches the same pose), gross outliers are flagged, clean data keeps every edge, degenerate inputs behave like the reference."""
 import numpy as np
 
