@@ -206,19 +206,26 @@ def cpu_chain_rates(frames, pidx, ti, cam, cap, nfeat, nframes, want_outputs=Fal
     return nframes / dt_all, n1 / dt_one, cores, ch
 
 
-def detector_cpu_rate(rgb_frames):
-    """Detector2D::detect on the CPU: the FP32 restatement (PyTorch convolutions on all host threads + numpy glue, oracle/detector_oracle.py) --
-    NOT ncnn, which is not installable here.  frames/s over the sample."""
-    import detector_oracle as DO
+def cpu_detector(threads):
+    """Detector2D::detect on the CPU for the baseline legs: the FP32 restatement evaluated on chunks of 16 frames with PyTorch-CPU tensors in channels-last
+    layout on all host threads (oracle/detector_batched.py; same graph walk as the parity checker oracle/detector_oracle.py, which interprets one frame layer
+    by layer through numpy and is ~7x slower) -- NOT ncnn, which is not installable here.  Returns run(frames) -> list of detections."""
+    import detector_batched as DB
     import ncnn_model as NM
-    import oracle as O
     import torch
-    torch.set_num_threads(O.online_cpus())                # the CPUs this process may really use (affinity mask capped by the cgroup quota)
+    torch.set_num_threads(threads)                        # the CPUs this process may really use (affinity mask capped by the cgroup quota)
     layers = NM.parse_param(MODEL + '.param'); NM.load_weights(layers, MODEL + '.bin')
-    DO.detect(layers, rgb_frames[0])                      # warm-up
+    bd = DB.BatchedDetector(layers)
+    return lambda frames: bd.detect(frames)
+
+
+def detector_cpu_rate(rgb_frames):
+    """frames/s of cpu_detector over the sample (after a warm-up on its first chunk)."""
+    import oracle as O
+    run = cpu_detector(O.online_cpus())
+    run(rgb_frames[:16])
     t0 = time.perf_counter()
-    for f in rgb_frames:
-        DO.detect(layers, f)
+    run(rgb_frames)
     return len(rgb_frames) / (time.perf_counter() - t0)
 
 
@@ -252,27 +259,22 @@ def run_reference(args, cfg):
     ti = make_track_inputs(ch0.out['kps'], ch0.out['desc'], ch0.out['counts'], boxes, cap, cap, pidx, W, H, cam)
     ch = O.Chain(frames, pidx, ti, cam, cap, nfeatures=NF, th=TH, want_outputs=False)
     # Every timed step really runs both parts on the same bounded sample of S frames of the batch (no extrapolation: steps x ms_per_step is the wall time
-    # of the timed region): the tracking chain on all cores, then the detector restatement frame by frame on all cores.  S is sized from a probe so that a
+    # of the timed region): the tracking chain on all cores, then the detector restatement in chunks of 16 frames on all cores.  S is sized from a probe so that a
     # step takes about two seconds.
     with_det = os.path.exists(MODEL + '.param') and not args.no_detector
     det_run = None
     if with_det:
-        import detector_oracle as DO
-        import ncnn_model as NM
-        import torch
-        torch.set_num_threads(cores)
-        layers = NM.parse_param(MODEL + '.param'); NM.load_weights(layers, MODEL + '.bin')
+        det_fn = cpu_detector(cores)
         rgb = synth.gray_to_rgb(frames[:min(NB, 256)])
 
         def det_run(n):
-            for f in range(n):
-                DO.detect(layers, rgb[f % len(rgb)])
-        det_run(1)
+            det_fn([rgb[f % len(rgb)] for f in range(n)])
+        det_run(16)
     ch.run(0, min(NB, cores), nthreads=cores)
     t0 = time.perf_counter(); ch.run(0, min(NB, 2 * cores), nthreads=cores); probe_chain = (time.perf_counter() - t0) / min(NB, 2 * cores)
     probe_det = 0.0
     if with_det:
-        t0 = time.perf_counter(); det_run(4); probe_det = (time.perf_counter() - t0) / 4
+        t0 = time.perf_counter(); det_run(16); probe_det = (time.perf_counter() - t0) / 16
     S = int(max(8, min(NB, round(2.0 / max(1e-6, probe_chain + probe_det)))))
     if S >= cores:
         S = max(cores, int(round(S / cores)) * cores)  # whole rounds of the worker threads
@@ -298,7 +300,7 @@ def run_reference(args, cfg):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
             'config': {'workload': workload_name(cfg, with_det), 'frames_per_gpu_per_step': NB, 'sample_frames_per_step': S,
-                       'note': 'CPU oracle port of the reference path (the reference itself needs OpenCV/ROS/ncnn: unbuildable here).  Every step runs %d frames of the %d-frame batch through the tracking chain (C++ worker threads pinned one per core) and through the detector (PyTorch-CPU FP32 restatement, all threads); both inside the timed region' % (S, NB)},
+                       'note': 'CPU oracle port of the reference path (the reference itself needs OpenCV/ROS/ncnn: unbuildable here).  Every step runs %d frames of the %d-frame batch through the tracking chain (C++ worker threads pinned one per core) and through the detector (PyTorch-CPU FP32 restatement, chunks of 16 frames in channels-last layout on all threads); both inside the timed region' % (S, NB)},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': '%d frames per step x %d steps, chain + detector both run on every frame of the sample' % (S, args.steps),
                              'tracking_chain_all_cores': S * args.steps / t_chain if t_chain > 0 else None, 'tracking_chain_single_thread': one_fps,
                              'tracking_chain_per_core': (S * args.steps / t_chain / cores) if t_chain > 0 else None,
@@ -865,11 +867,11 @@ def main():
         det_cpu = None
         if use_det:
             try:
-                det_cpu = detector_cpu_rate([h_rgb.numpy()[f] for f in range(4)])
+                det_cpu = detector_cpu_rate([h_rgb.numpy()[f] for f in range(min(NB, 64))])
             except Exception as ex_:
                 log('[bench] detector CPU baseline skipped: %r' % (ex_,))
         cpu = {'value': combine_rates(fps_all, det_cpu), 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-               'sample': '%d frames of the same batch on %d pinned C++ worker threads (tracking chain)%s' % (nrun, cores, '; detector restatement (PyTorch CPU, all threads) on 4 frames' if use_det else ''),
+               'sample': '%d frames of the same batch on %d pinned C++ worker threads (tracking chain)%s' % (nrun, cores, '; detector restatement (PyTorch CPU, chunks of 16 frames, channels-last, all threads) on %d frames' % min(NB, 64) if use_det else ''),
                'tracking_chain_all_cores': fps_all, 'tracking_chain_single_thread': fps_one, 'tracking_chain_per_core': fps_all / cores, 'detector_all_cores': det_cpu}
 
     if rank == 0:

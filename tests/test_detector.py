@@ -173,3 +173,29 @@ def test_plan_of_the_reference_model():
     layers = NM.parse_param(REAL + '.param')
     used, total = NM.load_weights(layers, REAL + '.bin')
     assert used == total == 9693828
+
+
+def test_batched_cpu_baseline_detector_matches_the_oracle(tmp_path):
+    """bench.py's CPU baseline runs the restatement on chunks of frames with PyTorch tensors end to end (oracle/detector_batched.py).  It must be the same
+    detector as the parity checker: identical DetectionOutput rows for identical head outputs (vectorised NMS), and the same detections from pixels (scores to
+    2e-5: batched / channels-last convolutions may round differently from the single-frame ones)."""
+    import detector_batched as DB
+    import torch
+    models = [DM.write_mini_model(str(tmp_path), 0)] + ([(REAL + '.param', REAL + '.bin')] if os.path.exists(REAL + '.param') else [])
+    for pp, bp in models:
+        layers = NM.parse_param(pp); NM.load_weights(layers, bp)
+        bd = DB.BatchedDetector(layers)
+        imgs = [DM.synthetic_rgb(480, 640, s) for s in (1, 2, 3)]
+        xb = torch.from_numpy(np.stack([DO.preprocess(f) for f in imgs])).contiguous(memory_format=torch.channels_last)
+        L, loc, conf, prior = bd.forward(xb)
+        for i in range(len(imgs)):
+            a = DO.detection_output(L, loc[i].numpy(), conf[i].numpy(), prior)
+            b = DB.detection_output_fast(L, loc[i].numpy(), conf[i].numpy(), prior)
+            assert a.shape == b.shape and np.array_equal(a, b)
+        got = bd.detect(imgs, chunk=2)
+        for f, (rows, post) in zip(imgs, got):
+            ref_rows, ref_post = DO.detect(layers, f)
+            assert rows.shape == ref_rows.shape
+            if len(rows):
+                assert np.array_equal(rows[:, 0], ref_rows[:, 0]) and np.abs(rows[:, 1:] - ref_rows[:, 1:]).max() < 2e-5
+            assert all(x.shape == y.shape for x, y in zip(post, ref_post))
