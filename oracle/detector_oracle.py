@@ -4,8 +4,11 @@ reference's post-processing of the "detection_out" rows.
 
 PARITY UNPINNED: ncnn is an un-vendored, unpinned dependency (ThirdpartyBuild.sh:21) and is not installed here, so nothing below was run
 against ncnn itself.  Layer semantics are restated from ncnn's published layer definitions; the two places where that restatement carries a
-real assumption are marked ASSUMPTION.  The only pinned piece is the input resize, which is checked against cv2.resize (ncnn documents
-from_pixels_resize as OpenCV-compatible fixed-point bilinear).
+real assumption are marked ASSUMPTION.  Pinned pieces: the input resize against cv2.resize (ncnn documents from_pixels_resize as
+OpenCV-compatible fixed-point bilinear); the post-processing of the rows against the reference's own Detector2D.cc compiled unmodified
+(tests/test_detector2d_ref.py); PriorBox and DetectionOutput against OpenCV's dnn implementation of the same Caffe-SSD layers that ncnn ported
+(tests/test_detector_cv2.py: same rows to 1e-6); the convolutions are PyTorch's.  Still carried as assumptions: ncnn's two mmdetection switches of
+PriorBox and the order of equal scores.
 """
 import math
 import numpy as np
