@@ -109,7 +109,12 @@ public:
         for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) s += (double)at<float>(r, c) * (double)o.at<float>(r, c);
         return s;
     }
-    void copyTo(Mat& o) const { o = clone(); }
+    // OpenCV's copyTo writes INTO a destination that already has the right size and type (views included) and reallocates otherwise
+    void copyTo(Mat& o) const {
+        if (o.data && o.rows == rows && o.cols == cols && o.type_ == type_) { for (int r = 0; r < rows; ++r) std::memmove(o.data + (size_t)r * o.step, data + (size_t)r * step, (size_t)cols * esz()); }
+        else o = clone();
+    }
+    void copyTo(Mat&& view) const { Mat& o = view; copyTo(o); }       // Rcw.copyTo(Tcw.rowRange(0,3).colRange(0,3))
     // ---- what src/Frame.cc needs on top (oracle/frame_shim, the Frame.cc pin)
     static Mat ones(int r, int c, int type) { Mat m(r, c, type); for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) m.at<float>(i, j) = 1.f; return m; }      // CV_32F only
     void convertTo(Mat& o, int type) const {                 // CV_8U -> CV_32F (the stereo matcher's patches)
@@ -117,6 +122,15 @@ public:
         for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) m.at<float>(r, c) = type_ == CV_32F ? at<float>(r, c) : (float)at<uchar>(r, c);
         o = m;
     }
+    // ---- what src/Tracking.cc needs on top (oracle/tracking_shim, the tracking front-end pin; none of it is on the pinned path)
+    int channels() const { return 1; }
+    void resize(size_t nrows) { Mat m((int)nrows, cols, type_); for (int r = 0; r < std::min(rows, (int)nrows); ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz()); *this = m; }
+    void convertTo(Mat& o, int type, double scale) const {
+        Mat m(rows, cols, type);
+        for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) m.at<float>(r, c) = (float)((type_ == CV_32F ? (double)at<float>(r, c) : (double)at<uchar>(r, c)) * scale);
+        o = m;
+    }
+    explicit Mat(const Point3f& p) { create(3, 1, CV_32F); at<float>(0) = p.x; at<float>(1) = p.y; at<float>(2) = p.z; }
     Mat reshape(int) const { return *this; }                // N x 2 one-channel <-> N x 1 two-channel: the same memory; cv::undistortPoints below reads N x 2 floats
     void push_back(const Mat& row) {                         // append one row (a fresh buffer: the destination of the reference's compaction loop is never a view)
         const int c = rows ? cols : row.cols, t = rows ? type_ : row.type_;
@@ -190,6 +204,7 @@ inline MatExpr operator-(const Mat& a, const Mat& b) { MatExpr e; e.kind = MatEx
 inline MatExpr operator-(const Mat& a) { MatExpr e; e.a = a; e.alpha = -1; return e; }
 inline MatExpr operator-(const MatExpr& x) { MatExpr e = x; if (e.kind == MatExpr::ADD) { Mat m = x.eval(); e = MatExpr(); e.a = m; e.alpha = -1; } else e.alpha = -e.alpha; return e; }
 inline MatExpr operator*(double s, const Mat& a) { MatExpr e; e.a = a; e.alpha = s; return e; }
+inline MatExpr operator*(const Mat& a, double s) { MatExpr e; e.a = a; e.alpha = s; return e; }
 inline MatExpr operator*(double s, const MatExpr& x) { MatExpr e = x; if (e.kind == MatExpr::ADD) { Mat m = x.eval(); e = MatExpr(); e.a = m; e.alpha = s; } else e.alpha *= s; return e; }
 inline MatExpr operator/(const Mat& a, double s) { MatExpr e; e.a = a; e.alpha = (double)(1.f / (float)s); return e; }
 
