@@ -124,6 +124,7 @@ public:
     }
     // ---- what src/Tracking.cc needs on top (oracle/tracking_shim, the tracking front-end pin; none of it is on the pinned path)
     int channels() const { return 1; }
+    Mat inv() const;                                         // declared only: mapping-thread sources that are compiled for the drop-in check, never linked or run
     void resize(size_t nrows) { Mat m((int)nrows, cols, type_); for (int r = 0; r < std::min(rows, (int)nrows); ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz()); *this = m; }
     void convertTo(Mat& o, int type, double scale) const {
         Mat m(rows, cols, type);
@@ -183,6 +184,7 @@ public:
     }
     MatExpr t() const { MatExpr e = *this; if (e.kind == SCALE) e.ta = !e.ta; else { Mat m = eval(); e = MatExpr(); e.a = m; e.ta = true; } return e; }
     template <class T> T at(int i) const { return eval().at<T>(i); }
+    Mat inv() const;                                         // declared only (see Mat::inv)
 };
 inline Mat::Mat(const MatExpr& e) { *this = e.eval(); }
 inline Mat& Mat::operator=(const MatExpr& e) { *this = e.eval(); return *this; }

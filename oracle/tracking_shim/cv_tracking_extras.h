@@ -10,6 +10,7 @@
 #define CV_BGRA2GRAY 10
 namespace cv {
 inline void cvtColor(const Mat&, Mat&, int) {}
+struct SVD { enum { MODIFY_A = 1, NO_UV = 2, FULL_UV = 4 }; static void compute(const Mat&, Mat&, Mat&, Mat&, int = 0); };      // declared only (LocalMapping's triangulation: compiled for the drop-in check, never linked)
 struct FileNode {
     double v; bool ok;
     operator float() const { return (float)v; }

@@ -10,8 +10,12 @@
 #define MAP_H
 #define KEYFRAMEDATABASE_H
 #define ORBVOCABULARY_H
+#ifndef SGS_REAL_LOCALMAPPING
 #define LOCALMAPPING_H
+#endif
+#ifndef SGS_REAL_LOOPCLOSING
 #define LOOPCLOSING_H
+#endif
 #define VIEWER_H
 #define FRAMEDRAWER_H
 #define MAPDRAWER_H
@@ -135,6 +139,8 @@ public:
     int GetWeight(KeyFrame*) { return 0; }
     void SetNotErase() {}
     void SetErase() {}
+    void SetBadFlag() { mbBad = true; }
+    cv::Mat UnprojectStereo(int) { return cv::Mat(); }
     bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }      // src/KeyFrame.cc:611-614
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;                                     // driver (src/KeyFrame.cc:570-609)
 };
@@ -162,6 +168,7 @@ public:
     void clear() {}
 };
 
+#ifndef SGS_REAL_LOCALMAPPING
 class LocalMapping {
 public:
     bool AcceptKeyFrames() { return true; }
@@ -173,12 +180,16 @@ public:
     bool isStopped() { return false; }
     bool stopRequested() { return false; }
 };
+#endif
 
+#ifndef SGS_REAL_LOOPCLOSING
 class LoopClosing {
 public:
     typedef map<KeyFrame*, g2o::Sim3, std::less<KeyFrame*>, Eigen::aligned_allocator<std::pair<KeyFrame* const, g2o::Sim3> > > KeyFrameAndPose;    // include/LoopClosing.h:50-51
     void RequestReset() {}
+    void InsertKeyFrame(KeyFrame*) {}
 };
+#endif
 
 class Viewer { public: void Release() {} void RequestStop() {} bool isStopped() { return true; } };
 class FrameDrawer { public: void Update(Tracking*) {} };
