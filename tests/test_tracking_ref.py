@@ -46,11 +46,12 @@ def reference_chain(camv, sf, isig, cur, Tc, m, ti, f, lm, pc):
     return out
 
 
-def test_pose_chain_composition_equals_the_reference_tracking_code():
+@pytest.mark.parametrize('seed,mono_every', [(11, 0), (23, 7)])
+def test_pose_chain_composition_equals_the_reference_tracking_code(seed, mono_every):
     import bench
     from test_gpu_pose_chain import oracle_chain
     nb, unique = 12, 6
-    frames, boxes, unique = bench.make_frames(nb, 11, W, H, unique=unique)
+    frames, boxes, unique = bench.make_frames(nb, seed, W, H, unique=unique)
     pidx = bench.prev_index(nb, unique)
     camd = dict(synth.TUM3)
     sf = synth.scale_factors(); cam = B.make_camera(W, H, camd, sf)
@@ -61,6 +62,8 @@ def test_pose_chain_composition_equals_the_reference_tracking_code():
         cnt[f] = len(k); kps[f, :len(k)] = k; desc[f, :len(k)] = d
     ti = bench.make_track_inputs(kps, desc, cnt, boxes, cap, pc, pidx, W, H, camd)
     ti['lflags'][:, 9::23] |= 4                                         # some last-frame points are bad
+    if mono_every:
+        ti['ur'][:, ::mono_every] = -1.0                                # keypoints without depth: monocular observations in both searches and both optimisations
     assert np.array_equal(ti['T'], np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (nb, 1)))     # the driver's velocity trick needs identity last poses
     Tc = ti['T'].copy()
 
@@ -73,7 +76,7 @@ def test_pose_chain_composition_equals_the_reference_tracking_code():
     Tc[3] = rot('y', 60.0 / camd['fx']); Tc[7] = rot('x', -58.0 / camd['fy']); Tc[9] = rot('y', 6.0 / camd['fx'])
     ti['ln'][5] = 0; ti['ln'][3] = 300; ti['ln'][7] = 300
     ti['Tc'] = Tc
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(seed)
     isig = np.zeros(16, np.float32); isig[:8] = 1.0 / (sf.astype(np.float32) ** 2)
     camv = np.array([camd['fx'], camd['fy'], camd['cx'], camd['cy'], camd['bf'], cam.min_x, cam.min_y, cam.max_x, cam.max_y], np.float32)
     full = bailed = added = retried = 0
