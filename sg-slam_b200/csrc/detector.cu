@@ -771,7 +771,7 @@ int load_bin(const char* path, std::vector<Layer>& layers) {
     size_t off = 0;
     auto take = [&](std::vector<float>& dst, size_t n) -> bool {
         if (off + 4 * n > buf.size()) return false;
-        dst.resize(n); memcpy(dst.data(), buf.data() + off, 4 * n); off += 4 * n; return true;
+        dst.resize(n); if (n) memcpy(dst.data(), buf.data() + off, 4 * n); off += 4 * n; return true;      // n == 0 (a hostile count): no null pointers into memcpy
     };
     for (auto& L : layers) {
         if (L.type == "Convolution" || L.type == "ConvolutionDepthWise") {
