@@ -27,8 +27,8 @@ def _p(a):
     return a.ctypes.data_as(v)
 
 
-def reference_chain(camv, sf, isig, cur, Tc, m, ti, f, lm, pc):
-    L = C.CDLL(LIB)
+def reference_chain(camv, sf, isig, cur, Tc, m, ti, f, lm, pc, lib=None):
+    L = C.CDLL(lib or LIB)
     n = cur.c.N
     xy = np.ascontiguousarray(np.stack([cur.keysUn['x'], cur.keysUn['y']], 1), np.float32)
     octv = np.ascontiguousarray(cur.keysUn['octave'], np.int32); ang = np.ascontiguousarray(cur.keysUn['angle'], np.float32)
