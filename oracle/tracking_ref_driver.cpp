@@ -36,6 +36,7 @@ struct OpenTracking : Tracking {
     using Tracking::Tracking;
     bool motion_model() { return TrackWithMotionModel(); }
     bool local_map() { return TrackLocalMap(); }
+    bool reference_keyframe(KeyFrame* kf) { mpReferenceKF = kf; return TrackReferenceKeyFrame(); }
     void state(const Frame& cur, const Frame& last, const cv::Mat& velocity, const cv::Mat& Tlr, KeyFrame* local) {
         mCurrentFrame = Frame(cur); mLastFrame = Frame(last);
         mVelocity = velocity.clone();
@@ -144,4 +145,61 @@ REF_API void ref_track_motion_and_local_map(const float* cam9, const float* scal
         for (int l = 0; l < L; ++l) if (local[l] == p) { mp_final[i] = point_cap + l; break; }
     }
     *inliers = trk.inliers();
+}
+
+// Tracking::TrackReferenceKeyFrame (src/Tracking.cc:796-838): SearchByBoW(reference key frame, current frame) with nnratio 0.7, the pose of the last frame as the start,
+// PoseOptimization, outlier discard.  *_node: the vocabulary node of every feature (the FeatureVector both sides hold; -1 = not listed); kf_flags bit 0 = the feature
+// holds a map point, bit 1 = it has observations, bit 2 = it is bad.  Outputs: the return value, the pose, per keypoint the key-frame feature whose point it holds, the
+// number of keypoints holding a point before the optimisation.
+REF_API void ref_track_reference_keyframe(const float* cam9, const float* scale_factors, const float* inv_level_sigma2, int nlevels,
+                                          int n, const float* cur_xy, const int32_t* cur_octave, const float* cur_angle, const float* cur_uright, const uint8_t* cur_desc, const int32_t* cur_node,
+                                          int m, const float* kf_xyz, const uint8_t* kf_desc, const uint8_t* kf_flags, const float* kf_angle, const int32_t* kf_node, const float* tcw_last,
+                                          int32_t* ok, float* tcw_out, int32_t* mp_out, int32_t* nheld) {
+    Frame::fx = cam9[0]; Frame::fy = cam9[1]; Frame::cx = cam9[2]; Frame::cy = cam9[3]; Frame::invfx = 1.0f / Frame::fx; Frame::invfy = 1.0f / Frame::fy;
+    Frame::mnMinX = cam9[5]; Frame::mnMinY = cam9[6]; Frame::mnMaxX = cam9[7]; Frame::mnMaxY = cam9[8];
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (Frame::mnMaxY - Frame::mnMinY);
+    Frame::mbInitialComputations = false;
+    std::map<std::string, double>& S = cv::FileStorage::values();
+    S.clear();
+    S["Camera.fx"] = cam9[0]; S["Camera.fy"] = cam9[1]; S["Camera.cx"] = cam9[2]; S["Camera.cy"] = cam9[3]; S["Camera.bf"] = cam9[4]; S["Camera.fps"] = 30; S["Camera.RGB"] = 1;
+    S["ORBextractor.nFeatures"] = 1000; S["ORBextractor.scaleFactor"] = scale_factors[1]; S["ORBextractor.nLevels"] = nlevels; S["ORBextractor.iniThFAST"] = 20; S["ORBextractor.minThFAST"] = 7;
+    S["ThDepth"] = 40; S["DepthMapFactor"] = 1;
+    Map map; KeyFrameDatabase db; ORBVocabulary voc; FrameDrawer fd; MapDrawer md; System sys;
+    OpenTracking trk(&sys, &voc, &fd, &md, &map, &db, std::string("planted"), (int)System::RGBD, boost::shared_ptr<PointCloudMapping>());
+
+    KeyFrame kf; kf.Tcw = cv::Mat::eye(4, 4, CV_32F);
+    kf.N = m; kf.mvKeysUn.resize(m); kf.mvKeys.resize(m); kf.mDescriptors = cv::Mat(m > 0 ? m : 1, 32, CV_8U); kf.mvpMapPoints.assign(m, static_cast<MapPoint*>(NULL));
+    std::vector<std::unique_ptr<OpenPoint> > pool;
+    for (int j = 0; j < m; ++j) {
+        kf.mvKeysUn[j].angle = kf_angle[j]; kf.mvKeys[j].angle = kf_angle[j];
+        std::memcpy(kf.mDescriptors.ptr(j), kf_desc + 32 * (size_t)j, 32);
+        if (kf_node[j] >= 0) kf.mFeatVec[kf_node[j]].push_back(j);
+        if (kf_flags[j] & 1) {
+            pool.emplace_back(new OpenPoint(vec3(kf_xyz + 3 * j), &kf, &map));
+            pool.back()->set(NULL, 0.f, 0.f, kf_desc + 32 * (size_t)j, (kf_flags[j] & 2) ? 1 : 0, (kf_flags[j] & 4) != 0);
+            kf.mvpMapPoints[j] = pool.back().get();
+        }
+    }
+    Frame cur, last;
+    fill_frame(cur, n, cur_xy, cur_octave, cur_angle, cur_uright, cur_desc, scale_factors, inv_level_sigma2, nlevels, cam9[4], 100);
+    for (int i = 0; i < n; ++i) if (cur_node[i] >= 0) cur.mFeatVec[cur_node[i]].push_back(i);
+    cur.mBowVec[0] = 1.0;                                                     // not empty: Frame::ComputeBoW (src/Frame.cc:422-429) keeps the planted vectors
+    cur.mpORBvocabulary = &voc;
+    std::vector<float> zero2(2, 0.f); std::vector<int32_t> zo(1, 0);
+    fill_frame(last, 0, zero2.data(), zo.data(), NULL, NULL, NULL, scale_factors, inv_level_sigma2, nlevels, cam9[4], 99);
+    last.mTcw = mat44(tcw_last); last.UpdatePoseMatrices(); last.mpReferenceKF = &kf;
+    trk.state(cur, last, cv::Mat::eye(4, 4, CV_32F), mat44(tcw_last), &kf);
+    *ok = trk.reference_keyframe(&kf) ? 1 : 0;
+    Frame& F = trk.mCurrentFrame;
+    if (F.mTcw.empty()) F.mTcw = cv::Mat::eye(4, 4, CV_32F);                  // bailed out before SetPose
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) tcw_out[4 * i + j] = F.mTcw.at<float>(i, j);
+    *nheld = 0;
+    for (int i = 0; i < n; ++i) {
+        mp_out[i] = -1;
+        MapPoint* p = F.mvpMapPoints[i];
+        if (!p) continue;
+        ++*nheld;
+        for (int j = 0; j < m; ++j) if (kf.mvpMapPoints[j] == p) { mp_out[i] = j; break; }
+    }
 }

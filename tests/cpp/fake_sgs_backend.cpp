@@ -1,5 +1,5 @@
-// TEST INFRASTRUCTURE: the three host entry points of the C ABI that the tracking thread reaches through the mirror headers -- sgs_match_project_lastframe,
-// sgs_match_project_localmap, sgs_pose_optimization -- answered by the CPU oracle (liboracle.so) instead of the CUDA library, so that tests/test_mirror_on_reference.py
+// TEST INFRASTRUCTURE: the host entry points of the C ABI that the tracking thread reaches through the mirror headers -- sgs_match_project_lastframe,
+// sgs_match_project_localmap, sgs_match_bow, sgs_pose_optimization -- answered by the CPU oracle (liboracle.so) instead of the CUDA library, so that tests/test_mirror_on_reference.py
 // can RUN include/sgslam/ORBmatcher.h and Optimizer.h inside the reference's own Tracking.cc without a device: what is under test there is the mirror's host logic
 // (flattening the reference's object graph, the ids it hands to the matchers, writing results back), not the kernels (tests/test_gpu_*.py).  Never linked into the product.
 #include <cmath>
@@ -21,6 +21,8 @@ int sgo_search_by_projection_last(const SgoFrame* cur, const float* Tcw_cur, con
 int sgo_search_by_projection_local(const SgoFrame* fr, int nmp, const uint8_t* mp_inview, const float* projx, const float* projy, const float* projxr, const int32_t* level,
                                    const float* viewcos, const uint8_t* mp_desc, const uint8_t* mp_obs, float th, float nnratio, int32_t id_base, int32_t* f_mp_inout,
                                    uint8_t* f_mp_obs_inout, int64_t* ncand_out);
+int sgo_search_by_bow(int nkf, const int32_t* kf_node, const double* kf_weight, const uint8_t* kf_valid, const uint8_t* kf_desc, const float* kf_angle, int nf, const int32_t* f_node,
+                      const double* f_weight, const uint8_t* f_desc, const float* f_angle, float nnratio, int checkOri, int32_t* match_f);
 int sgo_pose_optimization(const float* Tcw_in, int n, const uint8_t* has_mp, const float* xyz, const float* kp_xy, const int32_t* octave, const float* uright,
                           const float* inv_level_sigma2, float fx, float fy, float cx, float cy, float bf, float* Tcw_out, uint8_t* outlier);
 }
@@ -52,6 +54,13 @@ SGS_API int sgs_match_project_localmap(const sgs_frame_view* f, int nmp, const u
                                        int32_t* f_mp_inout, uint8_t* f_mp_obs_inout, int* nmatches, int) {
     SgoFrame s = view(f); int64_t nc = 0;
     const int n = sgo_search_by_projection_local(&s, nmp, mp_inview, proj_x, proj_y, proj_xr, level, view_cos, mp_desc, mp_obs, th, nnratio, id_base, f_mp_inout, f_mp_obs_inout, &nc);
+    if (nmatches) *nmatches = n;
+    return n < 0 ? SGS_ERR_INVALID : SGS_OK;
+}
+
+SGS_API int sgs_match_bow(int nkf, const int32_t* kf_node, const double* kf_weight, const uint8_t* kf_valid, const uint8_t* kf_desc, const float* kf_angle, int nf, const int32_t* f_node,
+                          const double* f_weight, const uint8_t* f_desc, const float* f_angle, float nnratio, int check_orientation, int32_t* match_f, int* nmatches, int) {
+    const int n = sgo_search_by_bow(nkf, kf_node, kf_weight, kf_valid, kf_desc, kf_angle, nf, f_node, f_weight, f_desc, f_angle, nnratio, check_orientation, match_f);
     if (nmatches) *nmatches = n;
     return n < 0 ? SGS_ERR_INVALID : SGS_OK;
 }

@@ -80,3 +80,59 @@ def test_mirror_headers_inside_the_reference_tracking_thread(mirror_lib, seed, m
         assert np.abs(a['T1'] - b['T1']).max() <= 1e-6 and np.abs(a['T2'] - b['T2']).max() <= 1e-6, f
         nmatched += int((a['mp2'] >= 0).sum())
     assert nmatched > 500 * nb // 2
+
+
+def _reference_keyframe(lib, camv, sf, isig, cur, cur_node, kf, Tl):
+    L = C.CDLL(lib)
+    n = cur.c.N; m = len(kf['xyz'])
+    v = C.c_void_p
+    P = lambda a: a.ctypes.data_as(v)
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    xy = a(np.stack([cur.keysUn['x'], cur.keysUn['y']], 1), np.float32)
+    keep = [xy, a(cur.keysUn['octave'], np.int32), a(cur.keysUn['angle'], np.float32), cur.uRight, cur.desc, a(cur_node, np.int32),
+            a(kf['xyz'], np.float32), a(kf['desc'], np.uint8), a(kf['flags'], np.uint8), a(kf['angle'], np.float32), a(kf['node'], np.int32), a(Tl, np.float32)]
+    out = dict(ok=C.c_int32(), T=np.zeros(16, np.float32), mp=np.zeros(n, np.int32), held=C.c_int32())
+    L.ref_track_reference_keyframe(P(camv), P(a(sf, np.float32)), P(isig), 8, n, *[P(x) for x in keep[:6]], m, *[P(x) for x in keep[6:]],
+                                   C.byref(out['ok']), P(out['T']), P(out['mp']), C.byref(out['held']))
+    return out
+
+
+@pytest.mark.parametrize('seed', [3, 8])
+def test_mirror_search_by_bow_inside_track_reference_keyframe(mirror_lib, seed):
+    """Tracking::TrackReferenceKeyFrame (src/Tracking.cc:796-838): SearchByBoW(reference key frame, frame) through the mirror + PoseOptimization + outlier discard,
+    against the all-reference build.  The key frame is the previous frame of the stream with its depth-backed points; the vocabulary node of a feature is a coarse
+    function of its position and octave (any partition works for the comparison; this one keeps true correspondences in the same node)."""
+    import bench
+    nb, unique = 8, 4
+    frames, boxes, unique = bench.make_frames(nb, seed, W, H, unique=unique)
+    pidx = bench.prev_index(nb, unique)
+    camd = dict(synth.TUM3)
+    sf = synth.scale_factors(); cam = B.make_camera(W, H, camd, sf)
+    NF = 1000; pc = NF + 64; cap = NF + 8 * 8 + 64
+    kps = np.zeros((nb, cap), O.KP_DTYPE); desc = np.zeros((nb, cap, 32), np.uint8); cnt = np.zeros(nb, np.int32)
+    for f in range(nb):
+        k, d = O.extract(frames[f])[:2]
+        cnt[f] = len(k); kps[f, :len(k)] = k; desc[f, :len(k)] = d
+    ti = bench.make_track_inputs(kps, desc, cnt, boxes, cap, pc, pidx, W, H, camd)
+    ti['lflags'][:, 9::23] |= 4
+    isig = np.zeros(16, np.float32); isig[:8] = 1.0 / (sf.astype(np.float32) ** 2)
+    camv = np.array([camd['fx'], camd['fy'], camd['cx'], camd['cy'], camd['bf'], cam.min_x, cam.min_y, cam.max_x, cam.max_y], np.float32)
+    node_of = lambda k: (k['octave'].astype(np.int64) * 64 + (k['y'] // 96).astype(np.int64) * 8 + (k['x'] // 96).astype(np.int64)).astype(np.int32)
+    accepted = 0
+    for f in range(nb):
+        n = int(cnt[f]); g = int(pidx[f]); m = int(ti['ln'][f])
+        cur = O.FrameArrays(kps[f, :n], ti['ur'][f, :n], desc[f, :n], W, H, camd['fx'], camd['fy'], camd['cx'], camd['cy'], camd['bf'], sf)
+        cur_node = node_of(kps[f, :n]); cur_node[::13] = -1                      # some features are not listed in the FeatureVector
+        kf = dict(xyz=ti['lxyz'][f, :m], desc=ti['ldesc'][f, :m], flags=ti['lflags'][f, :m].copy(), angle=ti['lang'][f, :m], node=node_of(kps[g, :m]))
+        kf['flags'][::17] = 0                                                     # features of the key frame without a map point
+        if f == 5:
+            kf['flags'][:] = 0; kf['flags'][:10] = 3                             # too few points: nmatches < 15, the function returns before SetPose
+        a = _reference_keyframe(REFLIB, camv, sf, isig, cur, cur_node, kf, ti['T'][f])
+        b = _reference_keyframe(mirror_lib, camv, sf, isig, cur, cur_node, kf, ti['T'][f])
+        assert a['ok'].value == b['ok'].value and a['held'].value == b['held'].value, (f, a['ok'].value, b['ok'].value, a['held'].value, b['held'].value)
+        assert np.array_equal(a['mp'], b['mp']), (f, int((a['mp'] != b['mp']).sum()))
+        assert np.abs(a['T'] - b['T']).max() <= 1e-6, f
+        accepted += a['ok'].value
+        if f == 5:
+            assert a['ok'].value == 0
+    assert accepted >= nb - 3
