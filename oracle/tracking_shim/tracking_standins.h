@@ -77,6 +77,7 @@ class Tracking;
 class ORBVocabulary {
 public:
     void transform(const std::vector<cv::Mat>&, DBoW2::BowVector&, DBoW2::FeatureVector&, int) {}      // pinned separately (libdbow2_ref.so)
+    double score(const DBoW2::BowVector&, const DBoW2::BowVector&) const { return 0.0; }
 };
 
 class Detector2D {                 // include/Detector2D.h:42-66
@@ -140,6 +141,8 @@ public:
     void SetNotErase() {}
     void SetErase() {}
     void SetBadFlag() { mbBad = true; }
+    std::set<KeyFrame*> GetConnectedKeyFrames() { return std::set<KeyFrame*>(); }
+    void AddLoopEdge(KeyFrame*) {}
     cv::Mat UnprojectStereo(int) { return cv::Mat(); }
     bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }      // src/KeyFrame.cc:611-614
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;                                     // driver (src/KeyFrame.cc:570-609)
@@ -159,12 +162,15 @@ public:
     long unsigned int MapPointsInMap() { return 0; }
     long unsigned int KeyFramesInMap() { return 0; }
     long unsigned int GetMaxKFid() { return 0; }
+    void InformNewBigChange() {}
     void clear() {}
 };
 
 class KeyFrameDatabase {
 public:
     std::vector<KeyFrame*> DetectRelocalizationCandidates(Frame*) { return std::vector<KeyFrame*>(); }
+    std::vector<KeyFrame*> DetectLoopCandidates(KeyFrame*, float) { return std::vector<KeyFrame*>(); }
+    void add(KeyFrame*) {}
     void clear() {}
 };
 
@@ -179,6 +185,9 @@ public:
     bool SetNotStop(bool) { return true; }
     bool isStopped() { return false; }
     bool stopRequested() { return false; }
+    void RequestStop() {}
+    void Release() {}
+    bool isFinished() { return true; }
 };
 #endif
 
